@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""Benchmark of the entailment-cone hot path (BASELINE.json metric: cone pairs/s fwd+bwd).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg1|cfg4]
+
+One "step" = one pass of the hot path over one batch: row transform -> fused cone loss fwd+bwd over
+B*(1+2N) pairs -> (N>1: NCCL all-reduce of the label-table gradient) -> Riemannian SGD update of the
+whole table.  Workload cfg1 (BASELINE.json configs[1]): Poincare cones, label-only, ETHEC 723-node
+hierarchy, D=10, RSGD, 10 negatives per edge; the 1 974 closure edges are tiled to --pairs pairs per
+GPU per step and every step uses a different pre-sampled batch out of a rotation larger than L2.
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "cone pairs/s fwd+bwd"
+UNIT = "pairs/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg1", choices=["cfg1", "cfg4"])
+    ap.add_argument("--pairs", type=int, default=1 << 21, help="pairs per GPU per step (rounded to whole groups)")
+    ap.add_argument("--precision", type=int, default=None, help="0 fp32 core, 1 fp64 core (default: per workload)")
+    ap.add_argument("--rotation", type=int, default=0, help="distinct batches to rotate through (0 = enough to exceed L2)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------
+def workload_spec(name):
+    if name == "cfg1":
+        return dict(name="cfg1: Poincare cones, label-only, ETHEC 723-node hierarchy, D=10, RSGD, 10 negatives/edge",
+                    geom="hyp", D=10, n_neg=5, K=0.1, alpha=0.05, lr=1e-3, tree="ethec")
+    return dict(name="cfg4: Poincare cones, 82115-node random tree, D=50, RSGD, 50 negatives/edge",
+                geom="hyp", D=50, n_neg=25, K=0.1, alpha=0.05, lr=1e-3, tree="random82k")
+
+
+def build_hierarchy(spec):
+    from learning_embeddings_b200 import hierarchy as H
+    if spec["tree"] == "ethec":
+        return H.ethec()
+    return H.random_tree(82115, 1.4056, seed=0)
+
+
+def init_table(n, D, K, seed):
+    """order_embeddings_h.py:198-203: N(0,1) direction, norm r_in + U[0, 0.05)."""
+    from learning_embeddings_b200.criterion import inner_radius
+    g = torch.Generator().manual_seed(seed)
+    w = torch.randn(n, D, generator=g)
+    return (inner_radius(K) + 0.05 * torch.rand(n, 1, generator=g)) * w / w.norm(dim=1, keepdim=True)
+
+
+def make_batches(h, spec, groups, count, seed):
+    """`count` host index blocks of `groups` positives each (closure edges tiled in shuffled order)."""
+    from learning_embeddings_b200.engine import pack_index_block
+    rng = np.random.default_rng(seed)
+    edges = h.closure_edges()
+    out = []
+    for _ in range(count):
+        sel = rng.integers(0, len(edges), size=groups)
+        u, v = edges[sel, 0], edges[sel, 1]
+        neg_to, neg_from = h.sample_negatives(u, v, spec["n_neg"], rng)
+        out.append(pack_index_block(u, v, neg_to, neg_from))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.active = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        while not self._stop_evt.is_set():
+            if self.active.is_set():
+                try:
+                    self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                    r = int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                    for bit, name in self.REASONS.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+            time.sleep(0.002)
+
+    def stop(self):
+        self._stop_evt.set()
+
+    def summary(self):
+        return {"sm_mhz": (float(np.median(self.samples)) if self.samples else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm (oracle port of the reference's PyTorch-on-CPU step)
+# ------------------------------------------------------------------------------------------------
+def cpu_step_runner(spec, table, blk, B):
+    """Returns a closure running one full reference-style step on the host cores: gather + row transform
+    + E_operator + hinge + backward (autograd) + RSGD table update, all in torch fp32 on CPU."""
+    from oracle import cones
+    Nn = spec["n_neg"]
+    b = blk[:B * (2 + 2 * Nn)].long()
+    u, v = b[:B], b[B:2 * B]
+    neg_to = b[2 * B:2 * B + B * Nn].view(B, Nn)
+    neg_from = b[2 * B + B * Nn:].view(B, Nn)
+    nf = torch.cat([u[:, None].expand(B, Nn), neg_from], 1).reshape(-1)
+    nt = torch.cat([neg_to, v[:, None].expand(B, Nn)], 1).reshape(-1)
+    W = table.clone()
+    r_in = cones.inner_radius(spec["K"])
+
+    def run():
+        nonlocal W
+        r = cones.label_step(spec["geom"], W, cones.ROW_HYP_SHELL, spec["K"], spec["alpha"], u, v, nf, nt)
+        _, W = cones.rsgd_step(W, r["gW"], spec["lr"], r_in)
+        return float(r["loss"])
+
+    return run
+
+
+def time_cpu(spec, table, blk, groups, steps, warmup, budget_s=25.0):
+    """Bounded sample: `groups` positives (x(1+2N) pairs) per CPU step."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    run = cpu_step_runner(spec, table, blk, groups)
+    for _ in range(warmup):
+        run()
+    times = []
+    t_all = time.perf_counter()
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        run()
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_all > budget_s:
+            break
+    pairs = groups * (1 + 2 * spec["n_neg"])
+    return pairs / float(np.mean(times)), float(np.mean(times)), len(times), pairs
+
+
+def main():
+    args = parse()
+    spec = workload_spec(args.workload)
+    Nn, D = spec["n_neg"], spec["D"]
+    ppg = 1 + 2 * Nn
+    groups = max(1, args.pairs // ppg)
+    pairs_per_step = groups * ppg
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    precision = args.precision if args.precision is not None else 0
+    cfg = {"workload": spec["name"], "pairs_per_gpu_per_step": pairs_per_step, "positives_per_gpu_per_step": groups,
+           "dim": D, "negatives_per_edge": 2 * Nn, "table_rows": None, "update": "rsgd",
+           "scalar_core": "fp64" if precision == 1 else "fp32", "index_dtype": "int32",
+           "parallelism": "dp%d (pairs sharded, table replicated)" % world}
+
+    h = build_hierarchy(spec)
+    cfg["table_rows"] = int(h.n)
+    table0 = init_table(h.n, D, spec["K"], seed=0)
+
+    # ---------------- reference arm: CPU only, rank 0 only ----------------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cpu_groups = min(groups, 23831)  # 262 141 pairs per CPU step at N=5: a bounded sample of the batch
+        blk = make_batches(h, spec, cpu_groups, 1, seed=1)[0]
+        v, mean_s, n_done, pairs = time_cpu(spec, table0, blk, cpu_groups, args.steps, args.warmup, budget_s=150.0)
+        cores = os.cpu_count() or 1
+        sample = "%d pairs per step (first %d positives of the batch), %d timed steps" % (pairs, cpu_groups, n_done)
+        cfg["pairs_per_gpu_per_step"] = pairs
+        cfg["positives_per_gpu_per_step"] = cpu_groups
+        cfg["parallelism"] = "host cores only"
+        print(json.dumps({
+            "metric": METRIC, "value": v, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": n_done,
+            "warmup": args.warmup, "ms_per_step": mean_s * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}))
+        return
+
+    # ---------------- B200 arm ----------------
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    pg = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+
+    from learning_embeddings_b200 import _native, ops
+    from learning_embeddings_b200.engine import ConeStep
+
+    bytes_per_batch = groups * (2 + 2 * Nn) * 4 + groups * ppg * 4  # indices in + energies out
+    rotation = args.rotation or max(4, int(np.ceil(160e6 / bytes_per_batch)))
+    cfg["l2_policy"] = "inputs rotate through %d distinct batches (%.0f MB > 126 MB L2)" % (
+        rotation, rotation * bytes_per_batch / 1e6)
+    host_batches = make_batches(h, spec, groups, rotation, seed=100 + rank)
+    dev_batches = [b.to(dev) for b in host_batches]
+    table = table0.to(dev).clone()
+    eng = ConeStep(table, spec["geom"], Nn, groups, K=spec["K"], alpha=spec["alpha"], lr=spec["lr"],
+                   precision=precision, process_group=pg)
+
+    def dev_step(i):
+        eng.step_device(*eng._split(dev_batches[i % rotation], groups))
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    def sync_all():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up
+    for i in range(max(3, args.warmup)):
+        dev_step(i)
+    sync_all()
+
+    # timed region: inputs resident in HBM
+    launches0 = _native.launch_count()
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.active.set()
+    sync_all()
+    t0.record()
+    for i in range(args.steps):
+        eng.kernel_events = kev[i]
+        dev_step(i)
+    t1.record()
+    sync_all()
+    sampler.active.clear()
+    eng.kernel_events = None
+    lec_launches = _native.launch_count() - launches0
+    elapsed_ms = t0.elapsed_time(t1)
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    final_loss = float(eng.loss.item())
+    if world > 1:
+        tt = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+        elapsed_ms = float(tt.item())
+    value = world * pairs_per_step * args.steps / (elapsed_ms * 1e-3)
+
+    # end to end: host index block -> H2D -> step -> loss D2H, every step
+    e2e = None
+    if not args.no_e2e:
+        for i in range(3):
+            eng.step_host(host_batches[i % rotation], groups)
+        sync_all()
+        e_steps = args.steps
+        sampler.active.set()
+        w0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(e_steps):
+            eng.step_host(host_batches[i % rotation], groups)
+        e1.record()
+        sync_all()
+        sampler.active.clear()
+        e_ms = e0.elapsed_time(e1)
+        wall_ms = (time.perf_counter() - w0) * 1e3
+        e_ms = max(e_ms, wall_ms)
+        if world > 1:
+            tt = torch.tensor([e_ms], device=dev, dtype=torch.float64)
+            torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+            e_ms = float(tt.item())
+        e2e = {"value": world * pairs_per_step * e_steps / (e_ms * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": groups * (2 + 2 * Nn) * 4, "d2h_bytes_per_step": 8, "ms_per_step": e_ms / e_steps}
+    sampler.stop()
+
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+
+    # roofline of the dominant kernel (the fused pair kernel): algorithmic bytes model of SURVEY.md 8(d)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    bytes_per_pair = 24 + 16 * D
+    achieved = pairs_per_step * bytes_per_pair / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.workload)
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "kernel": "pairs_grouped_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_pair": bytes_per_pair, "kernel_ms": kernel_ms,
+                "kernel_share_of_step": kernel_ms / (elapsed_ms / args.steps),
+                "note": "logical-bytes model (24+16*D B per pair); the table is L2/L1-resident so DRAM traffic is far "
+                        "below it -- the kernel is bound by FP32/FP64 issue and L2 vector reductions, not HBM"}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu_groups = min(groups, 23831)
+        v, mean_s, n_done, pairs = time_cpu(spec, table0, host_batches[0], cpu_groups, steps=40, warmup=2, budget_s=20.0)
+        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": "%d pairs per CPU step (first %d positives of batch 0), %d steps, torch fp32 on all host "
+                         "threads, same step (gather+transform+energy+hinge+backward+RSGD)" % (pairs, cpu_groups, n_done)}
+
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+           "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic", "config": cfg, "clocks": sampler.summary(), "e2e": e2e,
+           "gpu_launches": int(lec_launches), "roofline": roofline, "cpu_baseline": cpu, "final_loss": final_loss}
+    print(json.dumps(out))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,149 @@
+/*
+ * lec_b200.h -- C ABI of the B200 (sm_100a) entailment-cone kernels.
+ *
+ * The reference (ankitdhall/learning_embeddings) is pure Python/PyTorch and has no FFI of its own
+ * (SURVEY.md 8b); its "operator interface" for this path is the Python class protocol of
+ * network/order_embeddings*.py and network/oe*.py.  Each entry point below names the reference
+ * code it replaces.  The Python host (learning_embeddings_b200/) binds these with ctypes; a
+ * maintainer of the reference would bind them the same way.
+ *
+ * Conventions
+ *   - plain C, raw DEVICE pointers, explicit sizes, explicit stream (a cudaStream_t passed as void*)
+ *   - returns 0 on success, a positive cudaError_t, or a negative LEC_E_* argument error
+ *   - never allocates, frees or synchronises; all buffers are owned by the caller
+ *   - all floating point is IEEE fp32 storage; `precision` selects the arithmetic of the per-pair
+ *     scalar core: LEC_PREC_F32 (fp32 throughout) or LEC_PREC_F64CORE (dot products and the
+ *     angle/aperture algebra in fp64, vectors and outputs fp32)
+ *   - "rows" is the TRANSFORMED embedding table the energies are evaluated on: [n_rows, ld] fp32,
+ *     ld a multiple of 4 (>= D), pad columns zero, base 16-byte aligned.  It is produced from the
+ *     raw parameter table by lec_rows_fwd and its gradient is mapped back by lec_rows_bwd.
+ *   - index arrays are int32 or int64 (idx_bytes = 4 or 8)
+ */
+#ifndef LEC_B200_H
+#define LEC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LEC_ABI_VERSION 1
+
+/* geometry of the energy */
+#define LEC_GEOM_EUC 0 /* EucConesLoss.E_operator, order_embeddings.py:954-969 = oe.py:721-739 (cos-space) */
+#define LEC_GEOM_HYP 1 /* hyperbolic EucConesLoss.E_operator, order_embeddings_h.py:1097-1120 = oe_h.py:811-833 */
+#define LEC_GEOM_OE  2 /* OrderEmbeddingLoss.E_operator, order_embeddings.py:818-824 */
+
+/* per-row transform applied to the raw parameter rows (Embedder.forward / FeatNet tail) */
+#define LEC_ROWS_NONE          0 /* plain nn.Embedding lookup (order embeddings) */
+#define LEC_ROWS_EUC_SOFTCLIP  1 /* e/|e|*(|e|+K): order_embeddings.py:195-200, oe.py:75-80, oe.py:133-138 */
+#define LEC_ROWS_HYP_SHELL     2 /* +1e-15, project into [r_in, 1-1e-5], straight-through: order_embeddings_h.py:205-228 */
+#define LEC_ROWS_HYP_TANH      3 /* tanh(clamp(atanh(r_in)+|e|))*e/|e| then projection: oe_h.py:77-104 */
+#define LEC_ROWS_HYP_TANH_FEAT 4 /* same on FeatNet output, (1e-6+x)/(1e-6+|x|) projection: oe_h.py:168-224 */
+
+#define LEC_PREC_F32     0
+#define LEC_PREC_F64CORE 1
+
+/* negative return codes */
+#define LEC_E_NULL      (-1) /* required pointer is NULL */
+#define LEC_E_DIM       (-2) /* D < 1, D > LEC_MAX_DIM, ld < D or ld % 4 != 0 */
+#define LEC_E_ENUM      (-3) /* unknown geometry / mode / precision / idx_bytes */
+#define LEC_E_SIZE      (-4) /* negative count */
+#define LEC_E_ALIGN     (-5) /* rows / grad_rows base not 16-byte aligned */
+#define LEC_E_K         (-6) /* k out of range for top-k */
+#define LEC_MAX_DIM 1024
+#define LEC_MAX_TOPK 8
+#define LEC_MAX_LEVELS 8
+
+int lec_abi_version(void);
+const char* lec_error_string(int code);
+/* kernels launched by this library since load (the bench's gpu_launches claim) */
+int64_t lec_launch_count(void);
+
+/* ---- row transforms ----------------------------------------------------------------------------
+ * Replaces Embedder.forward (order_embeddings.py:188-200, order_embeddings_h.py:205-228,
+ * oe_h.py:77-104) and the FeatNet tail after fc1 (oe.py:127-138, oe_h.py:168-224), applied once per
+ * table row instead of once per gathered pair endpoint.
+ *   in        [n, D] raw rows (row stride D)
+ *   rows_out  [n, ld] transformed rows, pad columns written as 0
+ *   zero_out  optional [n, ld] buffer cleared in the same pass (the gradient accumulator), may be NULL
+ */
+int lec_rows_fwd(const float* in, int64_t n, int D, int mode, float K, float* rows_out, int ld,
+                 float* zero_out, void* stream);
+
+/* Vector-Jacobian product of lec_rows_fwd: grad_in[n, D] (=|+=) J^T grad_rows[n, ld].
+ * Replaces autograd through Embedder.forward incl. embedding_dense_backward.  accumulate != 0 adds. */
+int lec_rows_bwd(const float* in, const float* grad_rows, int64_t n, int D, int ld, int mode, float K,
+                 float* grad_in, int accumulate, void* stream);
+
+/* ---- pair energies on gathered rows ------------------------------------------------------------
+ * Flat pair list.  Replaces E_operator + positive_pair/negative_pair + the loss sum of
+ * EucConesLoss.forward / OrderEmbeddingLoss.forward (order_embeddings.py:971-975, :1029-1042 eval
+ * branch, :1056-1102 train branch) for an arbitrary list of (from, to) endpoints.
+ *   from_idx,to_idx  [P] row numbers into rows
+ *   w                optional [P] pair weights (NULL = 1)
+ *   is_pos           optional [P] uint8, 1 = positive term w*E, 0 = negative term w*max(0, alpha-E)
+ *                    (NULL = all positive)
+ *   E_out            [P] raw energies
+ *   loss_out         optional double[1], the weighted hinge sum is ADDED to it
+ *   grad_rows        optional [n_rows, ld]; if non-NULL d loss / d rows is atomically ADDED to it
+ */
+int lec_pairs_flat(int geom, int precision, const float* rows, int64_t n_rows, int D, int ld,
+                   const void* from_idx, const void* to_idx, int idx_bytes, const float* w,
+                   const uint8_t* is_pos, int64_t P, float K, float alpha, float* E_out,
+                   double* loss_out, float* grad_rows, void* stream);
+
+/* Training-layout batch: B positives (u_i, v_i), each with N negatives (u_i, v'_ip) and N negatives
+ * (u'_ip, v_i) -- the layout EucConesLoss.forward builds at order_embeddings.py:1063-1091,
+ * kept in compact form (only the corrupted endpoint is stored).
+ *   pos_from,pos_to   [B]
+ *   neg_to            [B, N]  corrupted children v' of u_i   (reference slots 2N*i + p)
+ *   neg_from          [B, N]  corrupted parents  u' of v_i   (reference slots 2N*i + N + p)
+ *   w_pos [B], w_neg [B, 2N]  optional weights (NULL = 1)
+ *   E_pos [B], E_neg [B, 2N]  raw energies in the reference's order
+ *   loss_out, grad_rows       as above (grad_rows required unless NULL = forward only)
+ */
+int lec_pairs_grouped(int geom, int precision, const float* rows, int64_t n_rows, int D, int ld,
+                      const void* pos_from, const void* pos_to, const void* neg_to, const void* neg_from,
+                      int idx_bytes, int64_t B, int N, const float* w_pos, const float* w_neg, float K,
+                      float alpha, float* E_pos, float* E_neg, double* loss_out, float* grad_rows,
+                      void* stream);
+
+/* Dense operands (no gather): E_operator(x, y) on arbitrary [P, D] tensors, as the reference calls
+ * it from check_graph_embedding (order_embeddings.py:550-551) and the scoring loops. */
+int lec_energy_dense(int geom, int precision, const float* x, const float* y, int64_t P, int D, float K,
+                     float* E_out, void* stream);
+/* gx, gy [P, D] = gE[p] * dE/dx, dE/dy (E already includes its own max(0, .)). */
+int lec_energy_dense_bwd(int geom, int precision, const float* x, const float* y, const float* gE,
+                         int64_t P, int D, float K, float* gx, float* gy, void* stream);
+
+/* ---- Riemannian SGD on the Poincare ball --------------------------------------------------------
+ * Replaces order_embeddings_h.py:769-775 (lambda_x :662, exp_map_x :668, mob_add :649, soft_clip :634;
+ * joint copy oe_h.py:1604-1644, :1761-1762).  Whole table, in place.
+ *   grad [n, ld_g] Euclidean gradient (ld_g = D for a dense nn.Embedding grad)
+ *   lambda_mode 0: reference conformal factor 2/(1-|x|); 1: textbook 2/(1-|x|^2)
+ *   grad_out optional [n, D]: receives the rescaled (Riemannian) gradient as the reference leaves it
+ *   in weight.grad; may alias grad when ld_g == D.
+ */
+int lec_rsgd_update(float* table, const float* grad, int64_t n, int D, int ld_g, float lr, float r_in,
+                    int lambda_mode, float* grad_out, void* stream);
+
+/* ---- all-pairs image x label scoring ------------------------------------------------------------
+ * Replaces the per-image loop of JointEmbeddings.calculate_classification_metrics
+ * (oe.py:1764-1779, oe_h.py:2018-2036): e[i, l] = E(x = label_l, y = image_i), then per level
+ * torch.topk(k, largest=False).
+ *   labels [L, D], images [N, D] (row stride D)
+ *   level_start/level_stop  HOST int32[n_levels], label ranges [start, stop)
+ *   scores    optional [N, L] full energy matrix
+ *   topk_idx  optional int32 [N, n_levels, k] label ids (ascending energy), -1 if fewer than k finite
+ *   topk_val  optional float [N, n_levels, k]
+ */
+int lec_score_topk(int geom, int precision, const float* labels, int64_t L, const float* images,
+                   int64_t N, int D, float K, const int32_t* level_start, const int32_t* level_stop,
+                   int n_levels, int k, float* scores, int32_t* topk_idx, float* topk_val, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LEC_B200_H */

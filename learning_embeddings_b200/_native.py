@@ -1,0 +1,84 @@
+"""ctypes binding of liblec_b200.so (the C ABI declared in include/lec_b200.h).
+
+There is no fallback: if the shared library has not been built (`python -c "import
+__graft_entry__ as g; g.build()"` or `make -C learning_embeddings_b200/csrc`) every op raises.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "liblec_b200.so")
+
+GEOM = {"euc": 0, "hyp": 1, "oe": 2}
+ROWS_NONE, ROWS_EUC_SOFTCLIP, ROWS_HYP_SHELL, ROWS_HYP_TANH, ROWS_HYP_TANH_FEAT = 0, 1, 2, 3, 4
+PREC_F32, PREC_F64CORE = 0, 1
+
+EXPORTS = (
+    "lec_abi_version", "lec_error_string", "lec_launch_count", "lec_rows_fwd", "lec_rows_bwd", "lec_pairs_flat",
+    "lec_pairs_grouped", "lec_energy_dense", "lec_energy_dense_bwd", "lec_rsgd_update", "lec_score_topk",
+)
+
+
+class LecError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def _p(t):
+    """device pointer of a tensor (or NULL)."""
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LecError(
+                "liblec_b200.so is not built (%s). Run __graft_entry__.build(); there is no CPU or eager fallback."
+                % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        c_i, c_i64, c_f, c_vp = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
+        L.lec_abi_version.restype = c_i
+        L.lec_error_string.restype = ctypes.c_char_p
+        L.lec_error_string.argtypes = [c_i]
+        L.lec_launch_count.restype = c_i64
+        L.lec_rows_fwd.argtypes = [c_vp, c_i64, c_i, c_i, c_f, c_vp, c_i, c_vp, c_vp]
+        L.lec_rows_bwd.argtypes = [c_vp, c_vp, c_i64, c_i, c_i, c_i, c_f, c_vp, c_i, c_vp]
+        L.lec_pairs_flat.argtypes = [c_i, c_i, c_vp, c_i64, c_i, c_i, c_vp, c_vp, c_i, c_vp, c_vp, c_i64, c_f, c_f,
+                                     c_vp, c_vp, c_vp, c_vp]
+        L.lec_pairs_grouped.argtypes = [c_i, c_i, c_vp, c_i64, c_i, c_i, c_vp, c_vp, c_vp, c_vp, c_i, c_i64, c_i,
+                                        c_vp, c_vp, c_f, c_f, c_vp, c_vp, c_vp, c_vp, c_vp]
+        L.lec_energy_dense.argtypes = [c_i, c_i, c_vp, c_vp, c_i64, c_i, c_f, c_vp, c_vp]
+        L.lec_energy_dense_bwd.argtypes = [c_i, c_i, c_vp, c_vp, c_vp, c_i64, c_i, c_f, c_vp, c_vp, c_vp]
+        L.lec_rsgd_update.argtypes = [c_vp, c_vp, c_i64, c_i, c_i, c_f, c_f, c_i, c_vp, c_vp]
+        L.lec_score_topk.argtypes = [c_i, c_i, c_vp, c_i64, c_vp, c_i64, c_i, c_f, c_vp, c_vp, c_i, c_i, c_vp, c_vp,
+                                     c_vp, c_vp]
+        for name in EXPORTS:
+            fn = getattr(L, name)
+            if fn.restype is ctypes.c_int and name != "lec_abi_version":
+                pass
+        _lib = L
+    return _lib
+
+
+def check(code, what):
+    if code != 0:
+        raise LecError("%s failed: %s (code %d)" % (what, lib().lec_error_string(code).decode(), code))
+
+
+def stream_ptr(device=None):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise LecError("learning_embeddings_b200 runs on CUDA tensors only (got %s); there is no CPU path" % t.device)
+
+
+def launch_count():
+    return int(lib().lec_launch_count())

@@ -1,0 +1,180 @@
+// extern "C" surface of liblec_b200.so: argument validation + dispatch.  See include/lec_b200.h.
+#include "lec_pairs_impl.cuh"
+
+namespace lec {
+unsigned long long g_launches = 0;
+
+int launch_flat_euc32(const FlatArgs&, cudaStream_t);
+int launch_flat_hyp32(const FlatArgs&, cudaStream_t);
+int launch_flat_hyp64(const FlatArgs&, cudaStream_t);
+int launch_flat_oe32(const FlatArgs&, cudaStream_t);
+int launch_grouped_euc32(const GroupArgs&, cudaStream_t);
+int launch_grouped_hyp32(const GroupArgs&, cudaStream_t);
+int launch_grouped_hyp64(const GroupArgs&, cudaStream_t);
+int launch_grouped_oe32(const GroupArgs&, cudaStream_t);
+int launch_dense_euc32(const DenseArgs&, bool, cudaStream_t);
+int launch_dense_hyp32(const DenseArgs&, bool, cudaStream_t);
+int launch_dense_hyp64(const DenseArgs&, bool, cudaStream_t);
+int launch_dense_oe32(const DenseArgs&, bool, cudaStream_t);
+
+int rows_fwd_launch(const float*, int64_t, int, int, float, float*, int, float*, cudaStream_t);
+int rows_bwd_launch(const float*, const float*, int64_t, int, int, int, float, float*, int, cudaStream_t);
+int rsgd_launch(float*, const float*, int64_t, int, int, float, float, int, float*, cudaStream_t);
+int score_launch(int, int, const float*, int64_t, const float*, int64_t, int, float, const int32_t*, const int32_t*,
+                 int, int, float*, int32_t*, float*, cudaStream_t);
+
+static int pick_core(int geom, int precision) {
+    if (precision != LEC_PREC_F32 && precision != LEC_PREC_F64CORE) return -1;
+    switch (geom) {
+        case LEC_GEOM_EUC: return CORE_EUC32;  // fp64 core is defined for the hyperbolic energy only
+        case LEC_GEOM_HYP: return precision == LEC_PREC_F64CORE ? CORE_HYP64 : CORE_HYP32;
+        case LEC_GEOM_OE: return CORE_OE32;
+    }
+    return -1;
+}
+
+static int check_rows(const float* rows, int D, int ld) {
+    if (!rows) return LEC_E_NULL;
+    if (D < 1 || D > LEC_MAX_DIM || ld < D || (ld & 3)) return LEC_E_DIM;
+    if (reinterpret_cast<uintptr_t>(rows) & 15) return LEC_E_ALIGN;
+    return 0;
+}
+}  // namespace lec
+
+using namespace lec;
+
+extern "C" {
+
+int lec_abi_version(void) { return LEC_ABI_VERSION; }
+
+int64_t lec_launch_count(void) { return (int64_t)g_launches; }
+
+const char* lec_error_string(int code) {
+    switch (code) {
+        case 0: return "ok";
+        case LEC_E_NULL: return "required pointer is NULL";
+        case LEC_E_DIM: return "bad dimension: need 1 <= D <= 1024, ld >= D, ld % 4 == 0";
+        case LEC_E_ENUM: return "unknown geometry / mode / precision / idx_bytes";
+        case LEC_E_SIZE: return "negative element count";
+        case LEC_E_ALIGN: return "rows / grad_rows must be 16-byte aligned";
+        case LEC_E_K: return "top-k: need 1 <= k <= 8 and 1 <= n_levels <= 8";
+    }
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "unknown lec error";
+}
+
+int lec_rows_fwd(const float* in, int64_t n, int D, int mode, float K, float* rows_out, int ld, float* zero_out,
+                 void* stream) {
+    if (!in || !rows_out) return LEC_E_NULL;
+    if (n < 0) return LEC_E_SIZE;
+    if (mode < LEC_ROWS_NONE || mode > LEC_ROWS_HYP_TANH_FEAT) return LEC_E_ENUM;
+    if (int e = check_rows(rows_out, D, ld)) return e;
+    return rows_fwd_launch(in, n, D, mode, K, rows_out, ld, zero_out, (cudaStream_t)stream);
+}
+
+int lec_rows_bwd(const float* in, const float* grad_rows, int64_t n, int D, int ld, int mode, float K, float* grad_in,
+                 int accumulate, void* stream) {
+    if (!in || !grad_rows || !grad_in) return LEC_E_NULL;
+    if (n < 0) return LEC_E_SIZE;
+    if (mode < LEC_ROWS_NONE || mode > LEC_ROWS_HYP_TANH_FEAT) return LEC_E_ENUM;
+    if (int e = check_rows(grad_rows, D, ld)) return e;
+    return rows_bwd_launch(in, grad_rows, n, D, ld, mode, K, grad_in, accumulate, (cudaStream_t)stream);
+}
+
+int lec_pairs_flat(int geom, int precision, const float* rows, int64_t n_rows, int D, int ld, const void* from_idx,
+                   const void* to_idx, int idx_bytes, const float* w, const uint8_t* is_pos, int64_t P, float K,
+                   float alpha, float* E_out, double* loss_out, float* grad_rows, void* stream) {
+    const int core = pick_core(geom, precision);
+    if (core < 0 || (idx_bytes != 4 && idx_bytes != 8)) return LEC_E_ENUM;
+    if (P < 0 || n_rows < 0) return LEC_E_SIZE;
+    if (int e = check_rows(rows, D, ld)) return e;
+    if (grad_rows && (reinterpret_cast<uintptr_t>(grad_rows) & 15)) return LEC_E_ALIGN;
+    if (P == 0) return 0;
+    if (!from_idx || !to_idx || !E_out) return LEC_E_NULL;
+    FlatArgs a{rows, ld, from_idx, to_idx, idx_bytes, w, is_pos, P, K, alpha, E_out, loss_out, grad_rows};
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (core) {
+        case CORE_EUC32: return launch_flat_euc32(a, st);
+        case CORE_HYP32: return launch_flat_hyp32(a, st);
+        case CORE_HYP64: return launch_flat_hyp64(a, st);
+        default: return launch_flat_oe32(a, st);
+    }
+}
+
+int lec_pairs_grouped(int geom, int precision, const float* rows, int64_t n_rows, int D, int ld, const void* pos_from,
+                      const void* pos_to, const void* neg_to, const void* neg_from, int idx_bytes, int64_t B, int N,
+                      const float* w_pos, const float* w_neg, float K, float alpha, float* E_pos, float* E_neg,
+                      double* loss_out, float* grad_rows, void* stream) {
+    const int core = pick_core(geom, precision);
+    if (core < 0 || (idx_bytes != 4 && idx_bytes != 8)) return LEC_E_ENUM;
+    if (B < 0 || N < 0 || n_rows < 0) return LEC_E_SIZE;
+    if (int e = check_rows(rows, D, ld)) return e;
+    if (grad_rows && (reinterpret_cast<uintptr_t>(grad_rows) & 15)) return LEC_E_ALIGN;
+    if (B == 0) return 0;
+    if (!pos_from || !pos_to || !E_pos) return LEC_E_NULL;
+    if (N > 0 && (!neg_to || !neg_from || !E_neg)) return LEC_E_NULL;
+    GroupArgs a{rows, ld, pos_from, pos_to, neg_to, neg_from, idx_bytes, B, N, w_pos, w_neg, K, alpha,
+                E_pos, E_neg, loss_out, grad_rows};
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (core) {
+        case CORE_EUC32: return launch_grouped_euc32(a, st);
+        case CORE_HYP32: return launch_grouped_hyp32(a, st);
+        case CORE_HYP64: return launch_grouped_hyp64(a, st);
+        default: return launch_grouped_oe32(a, st);
+    }
+}
+
+static int dense_common(int geom, int precision, const DenseArgs& a, bool bwd, void* stream) {
+    const int core = pick_core(geom, precision);
+    if (core < 0) return LEC_E_ENUM;
+    if (a.P < 0) return LEC_E_SIZE;
+    if (a.D < 1 || a.D > LEC_MAX_DIM) return LEC_E_DIM;
+    if (a.P == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (core) {
+        case CORE_EUC32: return launch_dense_euc32(a, bwd, st);
+        case CORE_HYP32: return launch_dense_hyp32(a, bwd, st);
+        case CORE_HYP64: return launch_dense_hyp64(a, bwd, st);
+        default: return launch_dense_oe32(a, bwd, st);
+    }
+}
+
+int lec_energy_dense(int geom, int precision, const float* x, const float* y, int64_t P, int D, float K, float* E_out,
+                     void* stream) {
+    if (P > 0 && (!x || !y || !E_out)) return LEC_E_NULL;
+    DenseArgs a{x, y, nullptr, P, D, K, E_out, nullptr, nullptr};
+    return dense_common(geom, precision, a, false, stream);
+}
+
+int lec_energy_dense_bwd(int geom, int precision, const float* x, const float* y, const float* gE, int64_t P, int D,
+                         float K, float* gx, float* gy, void* stream) {
+    if (P > 0 && (!x || !y || !gE || !gx || !gy)) return LEC_E_NULL;
+    DenseArgs a{x, y, gE, P, D, K, nullptr, gx, gy};
+    return dense_common(geom, precision, a, true, stream);
+}
+
+int lec_rsgd_update(float* table, const float* grad, int64_t n, int D, int ld_g, float lr, float r_in, int lambda_mode,
+                    float* grad_out, void* stream) {
+    if (!table || !grad) return LEC_E_NULL;
+    if (n < 0) return LEC_E_SIZE;
+    if (D < 1 || D > LEC_MAX_DIM || ld_g < D) return LEC_E_DIM;
+    if (lambda_mode != 0 && lambda_mode != 1) return LEC_E_ENUM;
+    return rsgd_launch(table, grad, n, D, ld_g, lr, r_in, lambda_mode, grad_out, (cudaStream_t)stream);
+}
+
+int lec_score_topk(int geom, int precision, const float* labels, int64_t L, const float* images, int64_t N, int D,
+                   float K, const int32_t* level_start, const int32_t* level_stop, int n_levels, int k, float* scores,
+                   int32_t* topk_idx, float* topk_val, void* stream) {
+    if (pick_core(geom, precision) < 0) return LEC_E_ENUM;
+    if (L < 0 || N < 0) return LEC_E_SIZE;
+    if (D < 1 || D > 128) return LEC_E_DIM;
+    if (n_levels < 0 || n_levels > LEC_MAX_LEVELS) return LEC_E_K;
+    if (topk_idx && (k < 1 || k > LEC_MAX_TOPK || n_levels < 1)) return LEC_E_K;
+    if (!topk_idx) { n_levels = 0; k = 1; }
+    if (n_levels > 0 && (!level_start || !level_stop)) return LEC_E_NULL;
+    if (N > 0 && L > 0 && (!labels || !images)) return LEC_E_NULL;
+    return score_launch(geom, precision, labels, L, images, N, D, K, level_start, level_stop, n_levels, k, scores,
+                        topk_idx, topk_val, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,394 @@
+// Pair-energy kernels (flat list, training-layout groups, dense operands), templated on the scalar
+// core.  Each lec_pairs_<core>.cu instantiates this header once for its core and exports three
+// launchers that lec_api.cu dispatches to.
+#pragma once
+#include "lec_common.cuh"
+
+namespace lec {
+
+enum Core { CORE_EUC32 = 0, CORE_HYP32 = 1, CORE_HYP64 = 2, CORE_OE32 = 3 };
+
+template <int CORE> struct CoreTraits;
+template <> struct CoreTraits<CORE_EUC32> { using Acc = float;  static constexpr bool ax = true,  ay = false, oe = false; };
+template <> struct CoreTraits<CORE_HYP32> { using Acc = float;  static constexpr bool ax = true,  ay = true,  oe = false; };
+template <> struct CoreTraits<CORE_HYP64> { using Acc = double; static constexpr bool ax = true,  ay = true,  oe = false; };
+template <> struct CoreTraits<CORE_OE32>  { using Acc = float;  static constexpr bool ax = false, ay = false, oe = true;  };
+
+struct FlatArgs {
+    const float* rows; int ld;
+    const void* from_idx; const void* to_idx; int idx_bytes;
+    const float* w; const uint8_t* is_pos;
+    int64_t P; float K, alpha;
+    float* E_out; double* loss_out; float* grad_rows;
+};
+
+struct GroupArgs {
+    const float* rows; int ld;
+    const void* pos_from; const void* pos_to; const void* neg_to; const void* neg_from; int idx_bytes;
+    int64_t B; int N;
+    const float* w_pos; const float* w_neg;
+    float K, alpha;
+    float* E_pos; float* E_neg; double* loss_out; float* grad_rows;
+};
+
+struct DenseArgs {
+    const float* x; const float* y; const float* gE;
+    int64_t P; int D; float K;
+    float* E_out; float* gx; float* gy;
+};
+
+__device__ __forceinline__ int64_t ld_index(const void* p, int64_t i, int idx_bytes) {
+    return idx_bytes == 4 ? (int64_t)__ldg(reinterpret_cast<const int32_t*>(p) + i)
+                          : (int64_t)__ldg(reinterpret_cast<const long long*>(p) + i);
+}
+
+// z and (optionally) dz/dx, dz/dy coefficients of one pair held by a team.  AX=<x,x>, AY=<y,y> are
+// passed in when the caller already has them (they are per-row, not per-pair).
+template <int CORE, int T, int V, bool GRAD>
+__device__ __forceinline__ void eval_pair(const Vec<V>& X, const Vec<V>& Y, typename CoreTraits<CORE>::Acc AX,
+                                          typename CoreTraits<CORE>::Acc AY, float K, PairGrad& o) {
+    using Acc = typename CoreTraits<CORE>::Acc;
+    if (CORE == CORE_EUC32) {
+        const Acc DD = team_sum<T, Acc>(dist2_part<Acc, V>(Y, X));
+        const Acc XD = team_sum<T, Acc>(dot_diff_part<Acc, V>(X, Y));
+        euc_core<Acc, GRAD>(AX, DD, XD, K, o);
+    } else if (CORE == CORE_HYP32 || CORE == CORE_HYP64) {
+        const Acc P = team_sum<T, Acc>(dot_part<Acc, V>(X, Y));
+        const Acc S2 = team_sum<T, Acc>(dist2_part<Acc, V>(X, Y));
+        hyp_core<Acc, GRAD>(AX, AY, P, S2, K, o);
+    } else {
+        o.z = (float)team_sum<T, Acc>(relu_diff2_part<Acc, V>(X, Y));
+        o.zxx = o.zxy = o.zyx = o.zyy = 0.f;
+    }
+}
+
+template <int CORE, int T, int V>
+__device__ __forceinline__ typename CoreTraits<CORE>::Acc row_norm2(const Vec<V>& X) {
+    using Acc = typename CoreTraits<CORE>::Acc;
+    return team_sum<T, Acc>(dot_part<Acc, V>(X, X));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Flat pair list
+// ------------------------------------------------------------------------------------------------
+template <int CORE, int T, int V, bool GRAD>
+__global__ void __launch_bounds__(kThreads) pairs_flat_kernel(const FlatArgs a) {
+    using Tr = CoreTraits<CORE>;
+    using Acc = typename Tr::Acc;
+    const int lane_t = threadIdx.x % T;
+    const int64_t n_teams = (int64_t)gridDim.x * (kThreads / T);
+    const int64_t team = (int64_t)blockIdx.x * (kThreads / T) + threadIdx.x / T;
+    const int64_t iters = (a.P + n_teams - 1) / n_teams;
+    const int Q = a.ld >> 2;
+    double loss = 0.0;
+    for (int64_t it = 0; it < iters; ++it) {
+        const int64_t p = team + it * n_teams;
+        const bool valid = p < a.P;
+        const int64_t pc = valid ? p : a.P - 1;
+        const int64_t ix = ld_index(a.from_idx, pc, a.idx_bytes);
+        const int64_t iy = ld_index(a.to_idx, pc, a.idx_bytes);
+        Vec<V> X, Y;
+        load_row<T, V>(X, a.rows, ix, a.ld, lane_t);
+        load_row<T, V>(Y, a.rows, iy, a.ld, lane_t);
+        Acc AX = 0, AY = 0;
+        if (Tr::ax) AX = row_norm2<CORE, T, V>(X);
+        if (Tr::ay) AY = row_norm2<CORE, T, V>(Y);
+        PairGrad g;
+        eval_pair<CORE, T, V, GRAD>(X, Y, AX, AY, a.K, g);
+        const float w = a.w ? __ldg(a.w + pc) : 1.f;
+        const bool pos = a.is_pos ? (__ldg(a.is_pos + pc) != 0) : true;
+        float E;
+        double l = 0.0;
+        const float cf = hinge(g.z, pos, w, a.alpha, E, l);
+        if (valid && lane_t == 0) {
+            a.E_out[p] = E;
+            loss += l;
+        }
+        if (GRAD && valid && cf != 0.f) {
+            float* gx = a.grad_rows + ix * (int64_t)a.ld;
+            float* gy = a.grad_rows + iy * (int64_t)a.ld;
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                const int q = lane_t + T * j;
+                if (q < Q) {
+                    if (Tr::oe) {
+                        const float4 r = relu_diff4(X.c[j], Y.c[j]);
+                        const float c2 = 2.f * cf;
+                        red_add4(gx + 4 * q, make_float4(c2 * r.x, c2 * r.y, c2 * r.z, c2 * r.w));
+                        red_add4(gy + 4 * q, make_float4(-c2 * r.x, -c2 * r.y, -c2 * r.z, -c2 * r.w));
+                    } else {
+                        red_add4(gx + 4 * q, axpby4(cf * g.zxx, X.c[j], cf * g.zxy, Y.c[j]));
+                        red_add4(gy + 4 * q, axpby4(cf * g.zyx, X.c[j], cf * g.zyy, Y.c[j]));
+                    }
+                }
+            }
+        }
+    }
+    block_add_double(loss, a.loss_out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Training layout: one team per positive and its 2N negatives.  The gradients of the two shared
+// endpoints u_i, v_i are accumulated in registers and written with one vector reduction each; only
+// the 2N corrupted rows need their own reduction.
+// ------------------------------------------------------------------------------------------------
+template <int CORE, int T, int V, bool GRAD>
+__global__ void __launch_bounds__(kThreads) pairs_grouped_kernel(const GroupArgs a) {
+    using Tr = CoreTraits<CORE>;
+    using Acc = typename Tr::Acc;
+    const int lane_t = threadIdx.x % T;
+    const int64_t n_teams = (int64_t)gridDim.x * (kThreads / T);
+    const int64_t team = (int64_t)blockIdx.x * (kThreads / T) + threadIdx.x / T;
+    const int64_t iters = (a.B + n_teams - 1) / n_teams;
+    const int Q = a.ld >> 2;
+    const int N = a.N;
+    double loss = 0.0;
+    for (int64_t it = 0; it < iters; ++it) {
+        const int64_t gidx = team + it * n_teams;
+        const bool valid = gidx < a.B;
+        const int64_t gc = valid ? gidx : a.B - 1;
+        const bool writer = valid && lane_t == 0;
+        const int64_t iu = ld_index(a.pos_from, gc, a.idx_bytes);
+        const int64_t iv = ld_index(a.pos_to, gc, a.idx_bytes);
+        Vec<V> U, W;
+        load_row<T, V>(U, a.rows, iu, a.ld, lane_t);
+        load_row<T, V>(W, a.rows, iv, a.ld, lane_t);
+        Acc AU = 0, AW = 0;
+        if (Tr::ax || Tr::ay) {
+            AU = row_norm2<CORE, T, V>(U);
+            AW = row_norm2<CORE, T, V>(W);
+        }
+        float su_u = 0.f, su_w = 0.f, sw_u = 0.f, sw_w = 0.f;
+        Vec<V> accU, accW;
+#pragma unroll
+        for (int j = 0; j < V; ++j) accU.c[j] = accW.c[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool touch_u = false, touch_w = false;
+
+        PairGrad g;
+        float E;
+        double l = 0.0;
+        // positive (x = u, y = v)
+        {
+            eval_pair<CORE, T, V, GRAD>(U, W, AU, AW, a.K, g);
+            const float w = a.w_pos ? __ldg(a.w_pos + gc) : 1.f;
+            const float cf = hinge(g.z, true, w, a.alpha, E, l);
+            if (writer) a.E_pos[gidx] = E;
+            if (GRAD && cf != 0.f) {
+                touch_u = touch_w = true;
+                if (Tr::oe) {
+#pragma unroll
+                    for (int j = 0; j < V; ++j) {
+                        const float4 r = relu_diff4(U.c[j], W.c[j]);
+                        fma4(accU.c[j], 2.f * cf, r);
+                        fma4(accW.c[j], -2.f * cf, r);
+                    }
+                } else {
+                    su_u += cf * g.zxx; su_w += cf * g.zxy; sw_u += cf * g.zyx; sw_w += cf * g.zyy;
+                }
+            }
+        }
+        const int64_t nbase = gc * (int64_t)N;
+        const int64_t ebase = gc * (int64_t)(2 * N);
+        // negatives with a corrupted child: (x = u, y = c)
+        for (int p = 0; p < N; ++p) {
+            const int64_t ic = ld_index(a.neg_to, nbase + p, a.idx_bytes);
+            Vec<V> C;
+            load_row<T, V>(C, a.rows, ic, a.ld, lane_t);
+            Acc AC = 0;
+            if (Tr::ay) AC = row_norm2<CORE, T, V>(C);
+            eval_pair<CORE, T, V, GRAD>(U, C, AU, AC, a.K, g);
+            const float w = a.w_neg ? __ldg(a.w_neg + ebase + p) : 1.f;
+            const float cf = hinge(g.z, false, w, a.alpha, E, l);
+            if (writer) a.E_neg[ebase + p] = E;
+            if (GRAD && valid && cf != 0.f) {
+                touch_u = true;
+                float* gcp = a.grad_rows + ic * (int64_t)a.ld;
+                if (!Tr::oe) su_u += cf * g.zxx;
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    const int q = lane_t + T * j;
+                    if (Tr::oe) {
+                        const float4 r = relu_diff4(U.c[j], C.c[j]);
+                        const float c2 = 2.f * cf;
+                        fma4(accU.c[j], c2, r);
+                        if (q < Q) red_add4(gcp + 4 * q, make_float4(-c2 * r.x, -c2 * r.y, -c2 * r.z, -c2 * r.w));
+                    } else {
+                        fma4(accU.c[j], cf * g.zxy, C.c[j]);
+                        if (q < Q) red_add4(gcp + 4 * q, axpby4(cf * g.zyx, U.c[j], cf * g.zyy, C.c[j]));
+                    }
+                }
+            }
+        }
+        // negatives with a corrupted parent: (x = c, y = v)
+        for (int p = 0; p < N; ++p) {
+            const int64_t ic = ld_index(a.neg_from, nbase + p, a.idx_bytes);
+            Vec<V> C;
+            load_row<T, V>(C, a.rows, ic, a.ld, lane_t);
+            Acc AC = 0;
+            if (Tr::ax) AC = row_norm2<CORE, T, V>(C);
+            eval_pair<CORE, T, V, GRAD>(C, W, AC, AW, a.K, g);
+            const float w = a.w_neg ? __ldg(a.w_neg + ebase + N + p) : 1.f;
+            const float cf = hinge(g.z, false, w, a.alpha, E, l);
+            if (writer) a.E_neg[ebase + N + p] = E;
+            if (GRAD && valid && cf != 0.f) {
+                touch_w = true;
+                float* gcp = a.grad_rows + ic * (int64_t)a.ld;
+                if (!Tr::oe) sw_w += cf * g.zyy;
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    const int q = lane_t + T * j;
+                    if (Tr::oe) {
+                        const float4 r = relu_diff4(C.c[j], W.c[j]);
+                        const float c2 = 2.f * cf;
+                        fma4(accW.c[j], -c2, r);
+                        if (q < Q) red_add4(gcp + 4 * q, make_float4(c2 * r.x, c2 * r.y, c2 * r.z, c2 * r.w));
+                    } else {
+                        fma4(accW.c[j], cf * g.zyx, C.c[j]);
+                        if (q < Q) red_add4(gcp + 4 * q, axpby4(cf * g.zxx, C.c[j], cf * g.zxy, W.c[j]));
+                    }
+                }
+            }
+        }
+        if (writer) loss += l;
+        if (GRAD && valid) {
+            float* gu = a.grad_rows + iu * (int64_t)a.ld;
+            float* gw = a.grad_rows + iv * (int64_t)a.ld;
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                const int q = lane_t + T * j;
+                if (q < Q) {
+                    if (touch_u) {
+                        float4 v = accU.c[j];
+                        if (!Tr::oe) { fma4(v, su_u, U.c[j]); fma4(v, su_w, W.c[j]); }
+                        red_add4(gu + 4 * q, v);
+                    }
+                    if (touch_w) {
+                        float4 v = accW.c[j];
+                        if (!Tr::oe) { fma4(v, sw_u, U.c[j]); fma4(v, sw_w, W.c[j]); }
+                        red_add4(gw + 4 * q, v);
+                    }
+                }
+            }
+        }
+    }
+    block_add_double(loss, a.loss_out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Dense operands x, y [P, D] (row stride D): one thread per pair.
+// ------------------------------------------------------------------------------------------------
+template <int CORE, bool BWD>
+__global__ void __launch_bounds__(kThreads) energy_dense_kernel(const DenseArgs a) {
+    using Tr = CoreTraits<CORE>;
+    using Acc = typename Tr::Acc;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t p = (int64_t)blockIdx.x * kThreads + threadIdx.x; p < a.P; p += stride) {
+        const float* x = a.x + p * a.D;
+        const float* y = a.y + p * a.D;
+        Acc s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+        for (int d = 0; d < a.D; ++d) {
+            const float xv = __ldg(x + d), yv = __ldg(y + d);
+            if (CORE == CORE_EUC32) {
+                const float dv = yv - xv;
+                s0 += (Acc)xv * (Acc)xv; s1 += (Acc)dv * (Acc)dv; s2 += (Acc)xv * (Acc)dv;
+            } else if (CORE == CORE_OE32) {
+                const float r = fmaxf(xv - yv, 0.f);
+                s0 += (Acc)r * (Acc)r;
+            } else {
+                const float dv = xv - yv;
+                s0 += (Acc)xv * (Acc)xv; s1 += (Acc)yv * (Acc)yv; s2 += (Acc)xv * (Acc)yv; s3 += (Acc)dv * (Acc)dv;
+            }
+        }
+        PairGrad g;
+        if (CORE == CORE_EUC32) euc_core<Acc, BWD>(s0, s1, s2, a.K, g);
+        else if (CORE == CORE_OE32) { g.z = (float)s0; }
+        else hyp_core<Acc, BWD>(s0, s1, s2, s3, a.K, g);
+        if (!BWD) {
+            a.E_out[p] = relu_nan(g.z);
+        } else {
+            const float cf = (g.z >= 0.f) ? __ldg(a.gE + p) : 0.f;
+            float* gx = a.gx + p * a.D;
+            float* gy = a.gy + p * a.D;
+            for (int d = 0; d < a.D; ++d) {
+                const float xv = __ldg(x + d), yv = __ldg(y + d);
+                if (Tr::oe) {
+                    const float r = 2.f * cf * fmaxf(xv - yv, 0.f);
+                    gx[d] = r; gy[d] = -r;
+                } else {
+                    gx[d] = cf * fmaf(g.zxx, xv, g.zxy * yv);
+                    gy[d] = cf * fmaf(g.zyx, xv, g.zyy * yv);
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host-side launch helpers
+// ------------------------------------------------------------------------------------------------
+inline int grid_for(int64_t items, int teams_per_block, int blocks_per_sm) {
+    int64_t need = (items + teams_per_block - 1) / teams_per_block;
+    int64_t cap = (int64_t)sm_count() * blocks_per_sm;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+template <int CORE, int T, int V>
+int launch_flat_tv(const FlatArgs& a, cudaStream_t st) {
+    const int grid = grid_for(a.P, kThreads / T, 8);
+    if (a.grad_rows) pairs_flat_kernel<CORE, T, V, true><<<grid, kThreads, 0, st>>>(a);
+    else pairs_flat_kernel<CORE, T, V, false><<<grid, kThreads, 0, st>>>(a);
+    ++g_launches;
+    return (int)cudaGetLastError();
+}
+
+template <int CORE, int T, int V>
+int launch_grouped_tv(const GroupArgs& a, cudaStream_t st) {
+    const int grid = grid_for(a.B, kThreads / T, 8);
+    if (a.grad_rows) pairs_grouped_kernel<CORE, T, V, true><<<grid, kThreads, 0, st>>>(a);
+    else pairs_grouped_kernel<CORE, T, V, false><<<grid, kThreads, 0, st>>>(a);
+    ++g_launches;
+    return (int)cudaGetLastError();
+}
+
+#define LEC_DISPATCH_TV(FN, CORE, Q, ...)                                   \
+    do {                                                                    \
+        if ((Q) == 1) return FN<CORE, 1, 1>(__VA_ARGS__);                   \
+        if ((Q) == 2) return FN<CORE, 1, 2>(__VA_ARGS__);                   \
+        if ((Q) == 3) return FN<CORE, 1, 3>(__VA_ARGS__);                   \
+        if ((Q) == 4) return FN<CORE, 1, 4>(__VA_ARGS__);                   \
+        if ((Q) <= 16) return FN<CORE, 4, 4>(__VA_ARGS__);                  \
+        if ((Q) <= 64) return FN<CORE, 16, 4>(__VA_ARGS__);                 \
+        return FN<CORE, 32, 8>(__VA_ARGS__);                                \
+    } while (0)
+
+template <int CORE>
+int launch_flat(const FlatArgs& a, cudaStream_t st) {
+    LEC_DISPATCH_TV(launch_flat_tv, CORE, a.ld >> 2, a, st);
+}
+template <int CORE>
+int launch_grouped(const GroupArgs& a, cudaStream_t st) {
+    LEC_DISPATCH_TV(launch_grouped_tv, CORE, a.ld >> 2, a, st);
+}
+template <int CORE>
+int launch_dense(const DenseArgs& a, bool bwd, cudaStream_t st) {
+    const int grid = grid_for(a.P, kThreads, 8);
+    if (bwd) energy_dense_kernel<CORE, true><<<grid, kThreads, 0, st>>>(a);
+    else energy_dense_kernel<CORE, false><<<grid, kThreads, 0, st>>>(a);
+    ++g_launches;
+    return (int)cudaGetLastError();
+}
+
+// one translation unit per core defines these
+int launch_flat_core(int core, const FlatArgs& a, cudaStream_t st);
+int launch_grouped_core(int core, const GroupArgs& a, cudaStream_t st);
+int launch_dense_core(int core, const DenseArgs& a, bool bwd, cudaStream_t st);
+
+#define LEC_DEFINE_CORE_TU(CORE, NAME)                                                                      \
+    namespace lec {                                                                                         \
+    int launch_flat_##NAME(const FlatArgs& a, cudaStream_t st) { return launch_flat<CORE>(a, st); }          \
+    int launch_grouped_##NAME(const GroupArgs& a, cudaStream_t st) { return launch_grouped<CORE>(a, st); }   \
+    int launch_dense_##NAME(const DenseArgs& a, bool bwd, cudaStream_t st) { return launch_dense<CORE>(a, bwd, st); } \
+    }
+
+}  // namespace lec

@@ -1,0 +1,289 @@
+// Per-row kernels: Embedder / FeatNet row transforms (forward + VJP) and the fused Riemannian-SGD
+// table update.  One team of TT lanes per table row; lanes stride over the D columns so a team's
+// loads are contiguous.  These are full-table elementwise passes: 8*D bytes per row for the
+// transforms, 12*D bytes per row for the update (read w, read g, write w).
+#include "lec_common.cuh"
+
+namespace lec {
+
+struct RowsArgs {
+    const float* in; int64_t n; int D; int mode; float K; float r_in; float c0;
+    float* out; int ld; float* zero_out;
+    const float* grad_rows; float* grad_in; int accumulate;
+};
+
+template <int TT>
+__device__ __forceinline__ float tsum(float v) { return team_sum<TT, float>(v); }
+
+// shell projection of a row held as e[] (order_embeddings_h.py:217-228): factor applied to the row
+__device__ __forceinline__ void shell_factor(float r, float r_in, bool feat, float& mul, float& add, float& div) {
+    // out = (add + e) / (div) * mul ; identity when mul == 1, add == 0, div == 1
+    mul = 1.f; add = 0.f; div = 1.f;
+    if (r <= r_in) { mul = r_in; div = feat ? (1e-6f + r) : r; add = feat ? 1e-6f : 0.f; }
+    if (r >= 1.0f) { mul = (float)(1.0 - 1e-5); div = r; add = 0.f; }
+}
+
+template <int TT>
+__global__ void __launch_bounds__(kThreads) rows_fwd_kernel(const RowsArgs a) {
+    const int lane = threadIdx.x % TT;
+    const int64_t n_teams = (int64_t)gridDim.x * (kThreads / TT);
+    const int64_t team = (int64_t)blockIdx.x * (kThreads / TT) + threadIdx.x / TT;
+    const int64_t iters = (a.n + n_teams - 1) / n_teams;
+    const int D = a.D;
+    for (int64_t it = 0; it < iters; ++it) {
+        const int64_t row = team + it * n_teams;
+        const bool valid = row < a.n;
+        const float* e = a.in + (valid ? row : 0) * (int64_t)D;
+        const bool hyp = a.mode >= LEC_ROWS_HYP_SHELL;
+        float ss = 0.f;
+        for (int d = lane; d < D; d += TT) {
+            float v = __ldg(e + d);
+            if (hyp) v += 1e-15f;
+            ss = fmaf(v, v, ss);
+        }
+        ss = tsum<TT>(ss);
+        const float r = sqrtf(ss);
+        float scale = 1.f;   // first-stage multiplier
+        if (a.mode == LEC_ROWS_EUC_SOFTCLIP) {
+            scale = (r + a.K);  // applied to e / max(r, eps)
+        } else if (a.mode == LEC_ROWS_HYP_TANH || a.mode == LEC_ROWS_HYP_TANH_FEAT) {
+            scale = tanhf(fminf(fmaxf(a.c0 + r, -15.f), 15.f));
+        }
+        const float rn = fmaxf(r, kNormEps);
+        // second stage (hyperbolic only): projection on the norm of the first-stage output
+        float mul = 1.f, add = 0.f, div = 1.f;
+        if (hyp) {
+            float r2;
+            if (a.mode == LEC_ROWS_HYP_SHELL) {
+                r2 = r;
+            } else {
+                float s2 = 0.f;
+                for (int d = lane; d < D; d += TT) {
+                    const float v = scale * ((__ldg(e + d) + 1e-15f) / rn);
+                    s2 = fmaf(v, v, s2);
+                }
+                r2 = sqrtf(tsum<TT>(s2));
+            }
+            shell_factor(r2, a.r_in, a.mode == LEC_ROWS_HYP_TANH_FEAT, mul, add, div);
+        }
+        if (valid) {
+            float* o = a.out + row * (int64_t)a.ld;
+            float* zo = a.zero_out ? a.zero_out + row * (int64_t)a.ld : nullptr;
+            for (int d = lane; d < a.ld; d += TT) {
+                float v = 0.f;
+                if (d < D) {
+                    v = __ldg(e + d);
+                    if (hyp) v += 1e-15f;
+                    if (a.mode == LEC_ROWS_EUC_SOFTCLIP) v = (v / rn) * scale;
+                    else if (a.mode == LEC_ROWS_HYP_TANH || a.mode == LEC_ROWS_HYP_TANH_FEAT) v = scale * (v / rn);
+                    if (hyp && (mul != 1.f || div != 1.f)) v = ((add + v) / div) * mul;
+                }
+                o[d] = v;
+                if (zo) zo[d] = 0.f;
+            }
+        }
+    }
+}
+
+template <int TT>
+__global__ void __launch_bounds__(kThreads) rows_bwd_kernel(const RowsArgs a) {
+    const int lane = threadIdx.x % TT;
+    const int64_t n_teams = (int64_t)gridDim.x * (kThreads / TT);
+    const int64_t team = (int64_t)blockIdx.x * (kThreads / TT) + threadIdx.x / TT;
+    const int64_t iters = (a.n + n_teams - 1) / n_teams;
+    const int D = a.D;
+    for (int64_t it = 0; it < iters; ++it) {
+        const int64_t row = team + it * n_teams;
+        const bool valid = row < a.n;
+        const int64_t rc = valid ? row : 0;
+        const float* e = a.in + rc * (int64_t)D;
+        const float* g = a.grad_rows + rc * (int64_t)a.ld;
+        float c_g = 1.f, c_e = 0.f;  // grad_in = c_g * g + c_e * e'
+        if (a.mode == LEC_ROWS_EUC_SOFTCLIP) {
+            float ss = 0.f, eg = 0.f;
+            for (int d = lane; d < D; d += TT) {
+                const float ev = __ldg(e + d), gv = __ldg(g + d);
+                ss = fmaf(ev, ev, ss);
+                eg = fmaf(ev, gv, eg);
+            }
+            ss = tsum<TT>(ss); eg = tsum<TT>(eg);
+            const float r = sqrtf(ss);
+            c_g = 1.f + a.K / r;
+            c_e = -a.K * eg / (r * ss);
+        } else if (a.mode == LEC_ROWS_HYP_TANH || a.mode == LEC_ROWS_HYP_TANH_FEAT) {
+            float ss = 0.f, eg = 0.f;
+            for (int d = lane; d < D; d += TT) {
+                const float ev = __ldg(e + d) + 1e-15f, gv = __ldg(g + d);
+                ss = fmaf(ev, ev, ss);
+                eg = fmaf(ev, gv, eg);
+            }
+            ss = tsum<TT>(ss); eg = tsum<TT>(eg);
+            const float r = sqrtf(ss);
+            const float arg = a.c0 + r;
+            const float t = tanhf(fminf(fmaxf(arg, -15.f), 15.f));
+            const float tp = (arg >= -15.f && arg <= 15.f) ? (1.f - t * t) : 0.f;
+            // grad = tp*(eh.g)*eh + (t/r)*(g - eh*(eh.g)),  eh = e'/r
+            c_g = t / r;
+            c_e = (tp - t / r) * eg / ss;
+        }
+        if (valid) {
+            float* o = a.grad_in + row * (int64_t)D;
+            const bool hyp = a.mode >= LEC_ROWS_HYP_SHELL;
+            for (int d = lane; d < D; d += TT) {
+                float ev = __ldg(e + d);
+                if (hyp) ev += 1e-15f;
+                float v = fmaf(c_e, ev, c_g * __ldg(g + d));
+                if (a.accumulate) v += o[d];
+                o[d] = v;
+            }
+        }
+    }
+}
+
+struct RsgdArgs {
+    float* table; const float* grad; int64_t n; int D; int ld_g; float lr; float r_in; int lambda_mode;
+    float* grad_out;
+};
+
+template <int TT>
+__global__ void __launch_bounds__(kThreads) rsgd_kernel(const RsgdArgs a) {
+    const int lane = threadIdx.x % TT;
+    const int64_t n_teams = (int64_t)gridDim.x * (kThreads / TT);
+    const int64_t team = (int64_t)blockIdx.x * (kThreads / TT) + threadIdx.x / TT;
+    const int64_t iters = (a.n + n_teams - 1) / n_teams;
+    const int D = a.D;
+    for (int64_t it = 0; it < iters; ++it) {
+        const int64_t row = team + it * n_teams;
+        const bool valid = row < a.n;
+        const int64_t rc = valid ? row : 0;
+        float* w = a.table + rc * (int64_t)D;
+        const float* g = a.grad + rc * (int64_t)a.ld_g;
+        // |w|
+        float uu = 0.f;
+        for (int d = lane; d < D; d += TT) { const float v = w[d]; uu = fmaf(v, v, uu); }
+        uu = tsum<TT>(uu);
+        const float wn = sqrtf(uu);
+        // conformal factor (order_embeddings_h.py:662-666; SURVEY F4: norm, not norm^2)
+        const float lam = 2.f / (1.f - (a.lambda_mode == 1 ? uu : wn));
+        const float inv = 1.f / lam;
+        const float gs = inv * inv;
+        // v = -lr * g' + 1e-15 ; |v|
+        float vv = 0.f;
+        for (int d = lane; d < D; d += TT) {
+            const float v = -a.lr * (g[d] * gs) + 1e-15f;
+            vv = fmaf(v, v, vv);
+        }
+        vv = tsum<TT>(vv);
+        const float vn = sqrtf(vv);
+        const float th = tanhf(fminf(fmaxf(lam * vn / 2.f, -15.f), 15.f));
+        // t = th * v / |v| + 1e-6 ; Moebius sums
+        float uv = 0.f, tt = 0.f;
+        for (int d = lane; d < D; d += TT) {
+            const float v = -a.lr * (g[d] * gs) + 1e-15f;
+            const float t = th * v / vn + 1e-6f;
+            uv = fmaf(w[d], t, uv);
+            tt = fmaf(t, t, tt);
+        }
+        uv = 2.f * tsum<TT>(uv);
+        tt = tsum<TT>(tt);
+        const float den = 1.f + uv + tt * uu;
+        const float cw = (1.f + uv + tt) / den;
+        const float ct = (1.f - uu) / den;
+        float rr = 0.f;
+        for (int d = lane; d < D; d += TT) {
+            const float v = -a.lr * (g[d] * gs) + 1e-15f;
+            const float t = th * v / vn + 1e-6f;
+            const float res = cw * w[d] + ct * t;
+            rr = fmaf(res, res, rr);
+        }
+        rr = sqrtf(tsum<TT>(rr));
+        float mul, add, div;
+        shell_factor(rr, a.r_in, false, mul, add, div);
+        if (valid) {
+            float* go = a.grad_out ? a.grad_out + row * (int64_t)D : nullptr;
+            for (int d = lane; d < D; d += TT) {
+                const float gsc = g[d] * gs;
+                const float v = -a.lr * gsc + 1e-15f;
+                const float t = th * v / vn + 1e-6f;
+                float res = cw * w[d] + ct * t;
+                if (mul != 1.f || div != 1.f) res = (res / div) * mul;
+                w[d] = res;
+                if (go) go[d] = gsc;
+            }
+        }
+    }
+}
+
+static int team_width(int D) {
+    int t = 1;
+    while (t < D && t < 32) t <<= 1;
+    return t;
+}
+
+#define LEC_ROWS_LAUNCH(KERNEL, TT, ARGS, N, ST)                                             \
+    do {                                                                                     \
+        const int tpb = kThreads / (TT);                                                     \
+        int64_t need = ((N) + tpb - 1) / tpb;                                                \
+        const int64_t cap = (int64_t)sm_count() * 8;                                         \
+        if (need < 1) need = 1;                                                              \
+        const int grid = (int)(need < cap ? need : cap);                                     \
+        KERNEL<TT><<<grid, kThreads, 0, ST>>>(ARGS);                                         \
+    } while (0)
+
+#define LEC_ROWS_DISPATCH(KERNEL, ARGS, N, D, ST)                                            \
+    do {                                                                                     \
+        switch (team_width(D)) {                                                             \
+            case 1: LEC_ROWS_LAUNCH(KERNEL, 1, ARGS, N, ST); break;                          \
+            case 2: LEC_ROWS_LAUNCH(KERNEL, 2, ARGS, N, ST); break;                          \
+            case 4: LEC_ROWS_LAUNCH(KERNEL, 4, ARGS, N, ST); break;                          \
+            case 8: LEC_ROWS_LAUNCH(KERNEL, 8, ARGS, N, ST); break;                          \
+            case 16: LEC_ROWS_LAUNCH(KERNEL, 16, ARGS, N, ST); break;                        \
+            default: LEC_ROWS_LAUNCH(KERNEL, 32, ARGS, N, ST); break;                        \
+        }                                                                                    \
+        ++g_launches;                                                                        \
+    } while (0)
+
+static float inner_radius(float K) {
+    const double k = (double)K;
+    return (float)(2.0 * k / (1.0 + sqrt(1.0 + 4.0 * k * k)));
+}
+static float atanh_clamped(double v) {  // oe_h.py:106-110
+    if (v < -1 + 1e-5) v = -1 + 1e-5;
+    if (v > 1 - 1e-5) v = 1 - 1e-5;
+    return (float)(0.5 * (log(1 + v) - log(1 - v)));
+}
+
+int rows_fwd_launch(const float* in, int64_t n, int D, int mode, float K, float* out, int ld, float* zero_out,
+                    cudaStream_t st) {
+    RowsArgs a{};
+    a.in = in; a.n = n; a.D = D; a.mode = mode; a.K = K; a.out = out; a.ld = ld; a.zero_out = zero_out;
+    const double k = (double)K;
+    const double rin = 2.0 * k / (1.0 + sqrt(1.0 + 4.0 * k * k));
+    a.r_in = (float)rin;
+    a.c0 = atanh_clamped(rin);
+    if (n == 0) return 0;
+    LEC_ROWS_DISPATCH(rows_fwd_kernel, a, n, D, st);
+    return (int)cudaGetLastError();
+}
+
+int rows_bwd_launch(const float* in, const float* grad_rows, int64_t n, int D, int ld, int mode, float K,
+                    float* grad_in, int accumulate, cudaStream_t st) {
+    RowsArgs a{};
+    a.in = in; a.n = n; a.D = D; a.mode = mode; a.K = K; a.ld = ld; a.grad_rows = grad_rows; a.grad_in = grad_in;
+    a.accumulate = accumulate;
+    a.r_in = inner_radius(K);
+    a.c0 = atanh_clamped((double)2.0 * K / (1.0 + sqrt(1.0 + 4.0 * (double)K * K)));
+    if (n == 0) return 0;
+    LEC_ROWS_DISPATCH(rows_bwd_kernel, a, n, D, st);
+    return (int)cudaGetLastError();
+}
+
+int rsgd_launch(float* table, const float* grad, int64_t n, int D, int ld_g, float lr, float r_in, int lambda_mode,
+                float* grad_out, cudaStream_t st) {
+    RsgdArgs a{table, grad, n, D, ld_g, lr, r_in, lambda_mode, grad_out};
+    if (n == 0) return 0;
+    LEC_ROWS_DISPATCH(rsgd_kernel, a, n, D, st);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace lec

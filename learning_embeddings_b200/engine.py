@@ -1,0 +1,126 @@
+"""Step engine: one fused training step of a label-only cone model on preallocated buffers.
+
+This is the public fast path (what bench.py drives).  It does what one iteration of the reference's
+`pass_samples('train')` loop does between `optimizer.zero_grad()` and the weight update
+(order_embeddings_h.py:752-775 for the hyperbolic trainer, order_embeddings.py:619-635 for the
+Euclidean one) with the negatives already drawn:
+
+    rows      = transform(table)                    lec_rows_fwd   (also clears grad_rows)
+    loss, dL/drows = cone loss over B*(1+2N) pairs   lec_pairs_grouped
+    [sum dL/drows and loss over ranks]               NCCL all-reduce, only when world_size > 1
+    dL/dtable = J^T dL/drows                         lec_rows_bwd
+    table     = RSGD(table, dL/dtable)               lec_rsgd_update   (hyperbolic)  | plain SGD (Euclidean)
+
+Index batches use the compact training layout of include/lec_b200.h (lec_pairs_grouped) as one int32
+block [pos_from | pos_to | neg_to | neg_from] so a step's indices travel host->device in one copy.
+"""
+import numpy as np
+import torch
+
+from . import _native as N
+from . import ops
+from .criterion import inner_radius
+
+
+def pack_index_block(pos_from, pos_to, neg_to, neg_from, pin=True):
+    """Host int32 block [B | B | B*N | B*N] for ConeStep.step_host."""
+    parts = [np.ascontiguousarray(a, dtype=np.int32).reshape(-1) for a in (pos_from, pos_to, neg_to, neg_from)]
+    blk = torch.from_numpy(np.concatenate(parts))
+    return blk.pin_memory() if (pin and torch.cuda.is_available()) else blk
+
+
+class ConeStep:
+    def __init__(self, table, geom, n_neg, max_groups, K=None, alpha=1.0, lr=1e-3, row_mode=None, update="auto",
+                 precision=ops.PREC_F32, process_group=None):
+        N.require_cuda(table)
+        if table.dtype != torch.float32 or not table.is_contiguous():
+            raise N.LecError("ConeStep: table must be a contiguous float32 CUDA tensor (updated in place)")
+        self.table = table
+        self.geom = geom
+        self.n, self.D = table.shape
+        self.ld = ops.padded_dim(self.D)
+        self.n_neg = int(n_neg)
+        self.K = {"euc": 3.0, "hyp": 0.1, "oe": 0.0}[geom] if K is None else float(K)
+        self.alpha = float(alpha)
+        self.lr = float(lr)
+        self.row_mode = {"euc": N.ROWS_EUC_SOFTCLIP, "hyp": N.ROWS_HYP_SHELL, "oe": N.ROWS_NONE}[geom] \
+            if row_mode is None else int(row_mode)
+        self.update = ("rsgd" if geom == "hyp" else "sgd") if update == "auto" else update
+        self.r_in = float(inner_radius(self.K)) if geom == "hyp" else 0.0
+        self.precision = int(precision)
+        self.pg = process_group
+        self.max_groups = int(max_groups)
+        dev = table.device
+        self.rows = torch.empty((self.n, self.ld), device=dev, dtype=torch.float32)
+        self.grad_rows = torch.empty((self.n, self.ld), device=dev, dtype=torch.float32)
+        self.grad_table = torch.empty((self.n, self.D), device=dev, dtype=torch.float32)
+        self.E_pos = torch.empty(self.max_groups, device=dev, dtype=torch.float32)
+        self.E_neg = torch.empty((self.max_groups, 2 * self.n_neg), device=dev, dtype=torch.float32)
+        self.loss = torch.zeros(1, device=dev, dtype=torch.float64)
+        self.idx_dev = torch.empty(self.max_groups * (2 + 2 * self.n_neg), device=dev, dtype=torch.int32)
+        self.loss_host = torch.zeros(1, dtype=torch.float64).pin_memory()
+        self.kernel_events = None  # optional (start, stop) pairs around the pair kernel, set by bench
+
+    # -- pieces ---------------------------------------------------------------------------------
+    def _split(self, blk, B):
+        Nn = self.n_neg
+        return blk[:B], blk[B:2 * B], blk[2 * B:2 * B + B * Nn], blk[2 * B + B * Nn:2 * B + 2 * B * Nn]
+
+    def forward_backward(self, pos_from, pos_to, neg_to, neg_from, w_pos=None, w_neg=None):
+        """rows, loss and d loss / d rows for one batch (no collective, no update)."""
+        lib, st = N.lib(), N.stream_ptr(self.table.device)
+        B = int(pos_from.numel())
+        if B > self.max_groups:
+            raise N.LecError("batch of %d positives exceeds max_groups=%d" % (B, self.max_groups))
+        N.check(lib.lec_rows_fwd(N._p(self.table), self.n, self.D, self.row_mode, self.K, N._p(self.rows), self.ld,
+                                 N._p(self.grad_rows), st), "lec_rows_fwd")
+        self.loss.zero_()
+        ev = self.kernel_events
+        if ev is not None:
+            ev[0].record()
+        N.check(lib.lec_pairs_grouped(
+            N.GEOM[self.geom], self.precision, N._p(self.rows), self.n, self.D, self.ld, N._p(pos_from), N._p(pos_to),
+            N._p(neg_to), N._p(neg_from), pos_from.element_size(), B, self.n_neg, N._p(w_pos), N._p(w_neg), self.K,
+            self.alpha, N._p(self.E_pos), N._p(self.E_neg), N._p(self.loss), N._p(self.grad_rows), st),
+            "lec_pairs_grouped")
+        if ev is not None:
+            ev[1].record()
+        return B
+
+    def reduce_and_update(self):
+        lib, st = N.lib(), N.stream_ptr(self.table.device)
+        if self.pg is not None and torch.distributed.get_world_size(self.pg) > 1:
+            torch.distributed.all_reduce(self.grad_rows, group=self.pg)
+            torch.distributed.all_reduce(self.loss, group=self.pg)
+        if self.update == "rsgd" and self.row_mode == N.ROWS_HYP_SHELL:
+            # straight-through rows: d/dtable == d/drows, feed the padded buffer to the update directly
+            N.check(lib.lec_rsgd_update(N._p(self.table), N._p(self.grad_rows), self.n, self.D, self.ld, self.lr,
+                                        self.r_in, 0, N._p(self.grad_table), st), "lec_rsgd_update")
+            return
+        N.check(lib.lec_rows_bwd(N._p(self.table), N._p(self.grad_rows), self.n, self.D, self.ld, self.row_mode,
+                                 self.K, N._p(self.grad_table), 0, st), "lec_rows_bwd")
+        if self.update == "rsgd":
+            N.check(lib.lec_rsgd_update(N._p(self.table), N._p(self.grad_table), self.n, self.D, self.D, self.lr,
+                                        self.r_in, 0, N._p(self.grad_table), st), "lec_rsgd_update")
+        elif self.update == "sgd":
+            self.table.add_(self.grad_table, alpha=-self.lr)
+        elif self.update != "none":
+            raise N.LecError("unknown update rule %r" % (self.update,))
+
+    # -- whole steps ----------------------------------------------------------------------------
+    def step_device(self, pos_from, pos_to, neg_to, neg_from, w_pos=None, w_neg=None):
+        """Indices already on the device (int32 or int64).  Returns the device loss (float64[1])."""
+        self.forward_backward(pos_from, pos_to, neg_to, neg_from, w_pos, w_neg)
+        self.reduce_and_update()
+        return self.loss
+
+    def step_host(self, index_block, B):
+        """index_block: pinned host int32 block from pack_index_block.  Copies it in, runs the step and
+        reads the scalar loss back (one H2D, one D2H, one sync) -- the end-to-end path."""
+        n = B * (2 + 2 * self.n_neg)
+        dst = self.idx_dev[:n]
+        dst.copy_(index_block[:n], non_blocking=True)
+        self.step_device(*self._split(dst, B))
+        self.loss_host.copy_(self.loss, non_blocking=True)
+        torch.cuda.current_stream(self.table.device).synchronize()
+        return float(self.loss_host[0])

@@ -1,0 +1,269 @@
+"""torch-facing operators over the C ABI (include/lec_b200.h).
+
+Everything here is thin plumbing: allocate outputs with torch, pass raw device pointers and the
+current CUDA stream to liblec_b200.so.  The autograd Functions follow the scheme of SURVEY.md 8b:
+the fused kernels produce d loss / d rows in the forward launch; backward only scales it by the
+incoming gradient of the scalar loss.
+"""
+import ctypes
+
+import torch
+
+from . import _native as N
+from ._native import GEOM, PREC_F32, PREC_F64CORE  # noqa: F401  (re-exported)
+
+
+def padded_dim(D):
+    """Row stride of the transformed table: D rounded up to a multiple of 4 floats (16-byte chunks)."""
+    return (int(D) + 3) // 4 * 4
+
+
+def _idx(t, device):
+    if not torch.is_tensor(t):
+        t = torch.as_tensor(t)
+    if t.dtype not in (torch.int32, torch.int64):
+        t = t.to(torch.int64)
+    if t.device != device:
+        t = t.to(device, non_blocking=True)
+    return t.contiguous()
+
+
+def _f32(t, device):
+    if t is None:
+        return None
+    if not torch.is_tensor(t):
+        t = torch.as_tensor(t, dtype=torch.float32)
+    return t.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+
+
+# --------------------------------------------------------------------------------------------------
+# Row transforms
+# --------------------------------------------------------------------------------------------------
+def rows_forward(W, mode, K, zero_out=None):
+    """Transformed table [n, ld] of the raw parameter rows W [n, D] (lec_rows_fwd)."""
+    N.require_cuda(W)
+    W = W.detach().contiguous().float()
+    n, D = W.shape
+    ld = padded_dim(D)
+    rows = torch.empty((n, ld), device=W.device, dtype=torch.float32)
+    N.check(N.lib().lec_rows_fwd(N._p(W), n, D, int(mode), float(K or 0.0), N._p(rows), ld, N._p(zero_out),
+                                 N.stream_ptr(W.device)), "lec_rows_fwd")
+    return rows
+
+
+def rows_backward(W, grad_rows, mode, K, out=None, accumulate=False):
+    """grad wrt the raw rows W [n, D] from grad wrt the transformed rows [n, ld] (lec_rows_bwd)."""
+    N.require_cuda(W, grad_rows)
+    W = W.detach().contiguous().float()
+    grad_rows = grad_rows.contiguous()
+    n, D = W.shape
+    if out is None:
+        out = torch.empty((n, D), device=W.device, dtype=torch.float32)
+        accumulate = False
+    N.check(N.lib().lec_rows_bwd(N._p(W), N._p(grad_rows), n, D, grad_rows.shape[1], int(mode), float(K or 0.0),
+                                 N._p(out), int(bool(accumulate)), N.stream_ptr(W.device)), "lec_rows_bwd")
+    return out
+
+
+class RowTransform(torch.autograd.Function):
+    """rows = transform(W); differentiable (straight-through where the reference is)."""
+
+    @staticmethod
+    def forward(ctx, W, mode, K):
+        ctx.mode, ctx.K = int(mode), float(K or 0.0)
+        ctx.save_for_backward(W)
+        return rows_forward(W, mode, K)
+
+    @staticmethod
+    def backward(ctx, grad_rows):
+        (W,) = ctx.saved_tensors
+        return rows_backward(W, grad_rows, ctx.mode, ctx.K), None, None
+
+
+def transform_rows(W, mode, K):
+    return RowTransform.apply(W, mode, K)
+
+
+# --------------------------------------------------------------------------------------------------
+# Pair losses on gathered rows
+# --------------------------------------------------------------------------------------------------
+def pairs_grouped_raw(geom, rows, D, pos_from, pos_to, neg_to, neg_from, n_neg, K, alpha, w_pos=None, w_neg=None,
+                      grad_rows=None, loss_out=None, precision=PREC_F32, E_pos=None, E_neg=None):
+    """Direct call of lec_pairs_grouped on preallocated buffers (used by the step engine and bench)."""
+    dev = rows.device
+    B = int(pos_from.numel())
+    if E_pos is None:
+        E_pos = torch.empty(B, device=dev, dtype=torch.float32)
+    if E_neg is None:
+        E_neg = torch.empty((B, 2 * n_neg), device=dev, dtype=torch.float32)
+    if loss_out is None:
+        loss_out = torch.zeros(1, device=dev, dtype=torch.float64)
+    N.check(N.lib().lec_pairs_grouped(
+        GEOM[geom], int(precision), N._p(rows), rows.shape[0], int(D), rows.shape[1], N._p(pos_from), N._p(pos_to),
+        N._p(neg_to), N._p(neg_from), pos_from.element_size(), B, int(n_neg), N._p(w_pos), N._p(w_neg),
+        float(K or 0.0), float(alpha), N._p(E_pos), N._p(E_neg), N._p(loss_out), N._p(grad_rows),
+        N.stream_ptr(dev)), "lec_pairs_grouped")
+    return loss_out, E_pos, E_neg
+
+
+class GroupedPairLoss(torch.autograd.Function):
+    """loss, E_pos[B], E_neg[B, 2N] for the training layout (include/lec_b200.h: lec_pairs_grouped)."""
+
+    @staticmethod
+    def forward(ctx, rows, D, pos_from, pos_to, neg_to, neg_from, n_neg, w_pos, w_neg, geom, K, alpha, precision):
+        N.require_cuda(rows)
+        dev = rows.device
+        rows_c = rows.detach().contiguous()
+        pos_from, pos_to = _idx(pos_from, dev), _idx(pos_to, dev)
+        neg_to, neg_from = _idx(neg_to, dev), _idx(neg_from, dev)
+        if not (pos_from.dtype == pos_to.dtype == neg_to.dtype == neg_from.dtype):
+            pos_from, pos_to, neg_to, neg_from = (t.to(torch.int64) for t in (pos_from, pos_to, neg_to, neg_from))
+        need_grad = ctx.needs_input_grad[0]
+        grad_rows = torch.zeros_like(rows_c) if need_grad else None
+        loss64, E_pos, E_neg = pairs_grouped_raw(geom, rows_c, D, pos_from, pos_to, neg_to, neg_from, n_neg, K, alpha,
+                                                 _f32(w_pos, dev), _f32(w_neg, dev), grad_rows, None, precision)
+        ctx.save_for_backward(grad_rows)
+        ctx.mark_non_differentiable(E_pos, E_neg)
+        return loss64[0].float(), E_pos, E_neg
+
+    @staticmethod
+    def backward(ctx, g_loss, _gp, _gn):
+        (grad_rows,) = ctx.saved_tensors
+        return (grad_rows * g_loss,) + (None,) * 12
+
+
+def grouped_pair_loss(rows, D, pos_from, pos_to, neg_to, neg_from, n_neg, geom, K, alpha, w_pos=None, w_neg=None,
+                      precision=PREC_F32):
+    return GroupedPairLoss.apply(rows, D, pos_from, pos_to, neg_to, neg_from, n_neg, w_pos, w_neg, geom, K, alpha,
+                                 precision)
+
+
+def pairs_flat_raw(geom, rows, D, from_idx, to_idx, K, alpha, w=None, is_pos=None, grad_rows=None, loss_out=None,
+                   precision=PREC_F32, E_out=None):
+    dev = rows.device
+    P = int(from_idx.numel())
+    if E_out is None:
+        E_out = torch.empty(P, device=dev, dtype=torch.float32)
+    if loss_out is None:
+        loss_out = torch.zeros(1, device=dev, dtype=torch.float64)
+    N.check(N.lib().lec_pairs_flat(
+        GEOM[geom], int(precision), N._p(rows), rows.shape[0], int(D), rows.shape[1], N._p(from_idx), N._p(to_idx),
+        from_idx.element_size(), N._p(w), N._p(is_pos), P, float(K or 0.0), float(alpha), N._p(E_out),
+        N._p(loss_out), N._p(grad_rows), N.stream_ptr(dev)), "lec_pairs_flat")
+    return loss_out, E_out
+
+
+class FlatPairLoss(torch.autograd.Function):
+    """loss, E[P] for an arbitrary list of (from, to) pairs with positive/negative flags."""
+
+    @staticmethod
+    def forward(ctx, rows, D, from_idx, to_idx, is_pos, w, geom, K, alpha, precision):
+        N.require_cuda(rows)
+        dev = rows.device
+        rows_c = rows.detach().contiguous()
+        from_idx, to_idx = _idx(from_idx, dev), _idx(to_idx, dev)
+        if from_idx.dtype != to_idx.dtype:
+            from_idx, to_idx = from_idx.to(torch.int64), to_idx.to(torch.int64)
+        if is_pos is not None:
+            is_pos = torch.as_tensor(is_pos).to(device=dev, dtype=torch.uint8).contiguous()
+        need_grad = ctx.needs_input_grad[0]
+        grad_rows = torch.zeros_like(rows_c) if need_grad else None
+        loss64, E = pairs_flat_raw(geom, rows_c, D, from_idx, to_idx, K, alpha, _f32(w, dev), is_pos, grad_rows, None,
+                                   precision)
+        ctx.save_for_backward(grad_rows)
+        ctx.mark_non_differentiable(E)
+        return loss64[0].float(), E
+
+    @staticmethod
+    def backward(ctx, g_loss, _ge):
+        (grad_rows,) = ctx.saved_tensors
+        return (grad_rows * g_loss,) + (None,) * 9
+
+
+def flat_pair_loss(rows, D, from_idx, to_idx, geom, K, alpha, is_pos=None, w=None, precision=PREC_F32):
+    return FlatPairLoss.apply(rows, D, from_idx, to_idx, is_pos, w, geom, K, alpha, precision)
+
+
+# --------------------------------------------------------------------------------------------------
+# Dense E_operator (no gather)
+# --------------------------------------------------------------------------------------------------
+class DenseEnergy(torch.autograd.Function):
+    """E_operator(x, y) on arbitrary [..., D] CUDA tensors, differentiable in x and y."""
+
+    @staticmethod
+    def forward(ctx, x, y, geom, K, precision):
+        N.require_cuda(x, y)
+        shp = x.shape
+        D = shp[-1]
+        x2 = x.detach().reshape(-1, D).contiguous().float()
+        y2 = y.detach().reshape(-1, D).contiguous().float()
+        if x2.shape != y2.shape:
+            raise N.LecError("E_operator: x and y must have the same shape, got %s vs %s" % (tuple(x.shape), tuple(y.shape)))
+        E = torch.empty(x2.shape[0], device=x.device, dtype=torch.float32)
+        N.check(N.lib().lec_energy_dense(GEOM[geom], int(precision), N._p(x2), N._p(y2), x2.shape[0], D,
+                                         float(K or 0.0), N._p(E), N.stream_ptr(x.device)), "lec_energy_dense")
+        ctx.save_for_backward(x2, y2)
+        ctx.meta = (geom, float(K or 0.0), int(precision), shp, y.shape)
+        return E.view(shp[:-1])
+
+    @staticmethod
+    def backward(ctx, gE):
+        x2, y2 = ctx.saved_tensors
+        geom, K, precision, xs, ys = ctx.meta
+        gE = gE.reshape(-1).contiguous().float()
+        gx, gy = torch.empty_like(x2), torch.empty_like(y2)
+        N.check(N.lib().lec_energy_dense_bwd(GEOM[geom], precision, N._p(x2), N._p(y2), N._p(gE), x2.shape[0],
+                                             x2.shape[1], K, N._p(gx), N._p(gy), N.stream_ptr(x2.device)),
+                "lec_energy_dense_bwd")
+        return gx.view(xs), gy.view(ys), None, None, None
+
+
+def energy(x, y, geom, K=None, precision=PREC_F32):
+    return DenseEnergy.apply(x, y, geom, K, precision)
+
+
+# --------------------------------------------------------------------------------------------------
+# RSGD
+# --------------------------------------------------------------------------------------------------
+def rsgd_update_(table, grad, lr, r_in, textbook_lambda=False, write_rescaled_grad=True):
+    """In-place Riemannian SGD step on the whole table (lec_rsgd_update).
+
+    `grad` is the Euclidean gradient [n, D] (or [n, ld] padded).  With write_rescaled_grad the gradient
+    buffer is left holding the Riemannian-rescaled gradient, as the reference leaves weight.grad."""
+    N.require_cuda(table, grad)
+    if not table.is_contiguous() or table.dtype != torch.float32:
+        raise N.LecError("rsgd_update_: table must be a contiguous float32 tensor (updated in place)")
+    n, D = table.shape
+    grad = grad.contiguous()
+    ld_g = grad.shape[1]
+    grad_out = grad if (write_rescaled_grad and ld_g == D) else None
+    N.check(N.lib().lec_rsgd_update(N._p(table), N._p(grad), n, D, ld_g, float(lr), float(r_in),
+                                    1 if textbook_lambda else 0, N._p(grad_out), N.stream_ptr(table.device)),
+            "lec_rsgd_update")
+    return table
+
+
+# --------------------------------------------------------------------------------------------------
+# Scoring
+# --------------------------------------------------------------------------------------------------
+def score_topk(labels, images, geom, K, level_start, level_stop, k=5, want_scores=False, want_values=True,
+               precision=PREC_F32):
+    """Per image, per level: the k labels of lowest energy E(x=label, y=image) (lec_score_topk).
+
+    Returns (topk_idx int32 [N, n_levels, k], topk_val float32 or None, scores [N, L] or None)."""
+    N.require_cuda(labels, images)
+    labels = labels.detach().contiguous().float()
+    images = images.detach().contiguous().float()
+    L, D = labels.shape
+    n_img = images.shape[0]
+    nl = len(level_start)
+    ls = (ctypes.c_int32 * max(nl, 1))(*[int(v) for v in level_start])
+    le = (ctypes.c_int32 * max(nl, 1))(*[int(v) for v in level_stop])
+    dev = labels.device
+    idx = torch.empty((n_img, nl, k), device=dev, dtype=torch.int32)
+    val = torch.empty((n_img, nl, k), device=dev, dtype=torch.float32) if want_values else None
+    scores = torch.empty((n_img, L), device=dev, dtype=torch.float32) if want_scores else None
+    N.check(N.lib().lec_score_topk(GEOM[geom], int(precision), N._p(labels), L, N._p(images), n_img, D,
+                                   float(K or 0.0), ctypes.cast(ls, ctypes.c_void_p), ctypes.cast(le, ctypes.c_void_p),
+                                   nl, int(k), N._p(scores), N._p(idx), N._p(val), N.stream_ptr(dev)), "lec_score_topk")
+    return idx, val, scores

@@ -1,0 +1,60 @@
+"""CPU-side checks of the C ABI: the shared library loads, exports every symbol the header declares,
+and validates its arguments (no kernel is launched, so no GPU is needed)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+from learning_embeddings_b200 import _native
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "lec_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(lec_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_header_symbol():
+    lib = _native.lib()
+    names = header_symbols()
+    assert len(names) >= 11
+    for n in names:
+        assert hasattr(lib, n), n
+    assert sorted(_native.EXPORTS) == names
+    assert lib.lec_abi_version() == 1
+
+
+def test_argument_validation_codes():
+    lib = _native.lib()
+    null = ctypes.c_void_p(0)
+    fake = ctypes.c_void_p(0x1000)      # 16-byte aligned, never dereferenced: validation fails first
+    odd = ctypes.c_void_p(0x1004)
+    # NULL rows
+    assert lib.lec_pairs_flat(0, 0, null, 10, 4, 4, fake, fake, 8, null, null, 5, 3.0, 1.0, fake, null, null, null) == -1
+    # ld not a multiple of 4 / smaller than D
+    assert lib.lec_pairs_flat(0, 0, fake, 10, 4, 6, fake, fake, 8, null, null, 5, 3.0, 1.0, fake, null, null, null) == -2
+    assert lib.lec_pairs_flat(0, 0, fake, 10, 8, 4, fake, fake, 8, null, null, 5, 3.0, 1.0, fake, null, null, null) == -2
+    # unknown geometry / index width
+    assert lib.lec_pairs_flat(7, 0, fake, 10, 4, 4, fake, fake, 8, null, null, 5, 3.0, 1.0, fake, null, null, null) == -3
+    assert lib.lec_pairs_flat(0, 0, fake, 10, 4, 4, fake, fake, 2, null, null, 5, 3.0, 1.0, fake, null, null, null) == -3
+    # negative count, misaligned rows
+    assert lib.lec_pairs_flat(0, 0, fake, 10, 4, 4, fake, fake, 8, null, null, -1, 3.0, 1.0, fake, null, null, null) == -4
+    assert lib.lec_pairs_flat(0, 0, odd, 10, 4, 4, fake, fake, 8, null, null, 5, 3.0, 1.0, fake, null, null, null) == -5
+    # empty batch is a no-op success
+    assert lib.lec_pairs_flat(0, 0, fake, 10, 4, 4, null, null, 8, null, null, 0, 3.0, 1.0, null, null, null, null) == 0
+    assert lib.lec_pairs_grouped(1, 1, fake, 10, 4, 4, null, null, null, null, 4, 0, 5, null, null, 0.1, 1.0, null,
+                                 null, null, null, null) == 0
+    assert lib.lec_score_topk(1, 0, fake, 5, fake, 5, 10, 0.1, null, null, 4, 9, null, fake, null, null) == -6
+    assert lib.lec_rsgd_update(fake, fake, 5, 0, 0, 0.1, 0.1, 0, null, null) == -2
+    assert b"16-byte" in lib.lec_error_string(-5)
+
+
+def test_ops_refuse_cpu_tensors():
+    import torch
+    from learning_embeddings_b200 import ops
+    with pytest.raises(_native.LecError):
+        ops.energy(torch.zeros(4, 3), torch.zeros(4, 3), "euc", 3.0)
+    with pytest.raises(_native.LecError):
+        ops.rows_forward(torch.zeros(4, 3), _native.ROWS_EUC_SOFTCLIP, 3.0)

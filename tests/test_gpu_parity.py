@@ -1,0 +1,438 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the reference's golden
+vectors.  Tolerance contract, written out here:
+
+    |new - ref64| <= max(1e-5 * |ref64|, 2 * |ref32 - ref64|, 2e-6)
+
+where ref64 / ref32 are the reference's own FP64 / FP32 results on the same FP32 inputs; for
+gradients the same inequality on per-row L2 norms.  Indices and predicted label sets: bit-exact
+(away from energy ties > 1e-5).
+"""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import cones, sampler
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from learning_embeddings_b200 import _native as N
+    from learning_embeddings_b200 import ops
+
+DEV = "cuda"
+DIMS = (2, 10, 50)
+PRECS = (0, 1)
+
+
+def t(a, dtype=None):
+    x = torch.from_numpy(np.ascontiguousarray(a))
+    return x.to(dtype) if dtype is not None else x
+
+
+def contract(new, ref64, ref32, what, rel=1e-5, floor=2e-6):
+    new, ref64, ref32 = (np.asarray(a, dtype=np.float64) for a in (new, ref64, ref32))
+    finite = np.isfinite(ref64)
+    assert (np.isnan(new) == np.isnan(ref64)).all(), what + ": NaN pattern differs"
+    err = np.abs(new - ref64)[finite]
+    bound = np.maximum.reduce([rel * np.abs(ref64), 2 * np.abs(ref32 - ref64), np.full_like(ref64, floor)])[finite]
+    bad = err > bound
+    assert not bad.any(), "%s: %d/%d outside the contract, worst err %.3e (bound %.3e)" % (
+        what, bad.sum(), bad.size, err[bad].max(), bound[bad][err[bad].argmax()])
+
+
+def contract_rows(new, ref64, ref32, what, rel=1e-5, floor=2e-6):
+    new, ref64, ref32 = (np.asarray(a, dtype=np.float64) for a in (new, ref64, ref32))
+    err = np.linalg.norm(new - ref64, axis=1)
+    bound = np.maximum.reduce([rel * np.linalg.norm(ref64, axis=1), 2 * np.linalg.norm(ref32 - ref64, axis=1),
+                               np.full(len(err), floor)])
+    bad = err > bound
+    assert not bad.any(), "%s: %d/%d rows outside the contract, worst err %.3e (bound %.3e)" % (
+        what, bad.sum(), bad.size, err[bad].max(), bound[bad][err[bad].argmax()])
+
+
+def padded(x):
+    P, D = x.shape
+    ld = ops.padded_dim(D)
+    out = torch.zeros(P, ld)
+    out[:, :D] = x
+    return out
+
+
+def pair_files():
+    out = []
+    for D in DIMS:
+        for a in ("1p0", "0p05"):
+            out.append(("euc", "pairs_euc_D%d_a%s" % (D, a)))
+            out.append(("hyp", "pairs_hyp_D%d_a%s" % (D, a)))
+        out.append(("oe", "pairs_oe_D%d" % D))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# pair kernels vs the reference's golden vectors
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("idx_dtype", (torch.int32, torch.int64))
+@pytest.mark.parametrize("geom,name", pair_files())
+def test_flat_kernel_matches_reference(geom, name, idx_dtype, prec):
+    g = load_golden(name)
+    x, y = t(g["x"]), t(g["y"])
+    P, D = x.shape
+    K, alpha = float(g.get("K", 0.0)), float(g["alpha"])
+    rows = torch.cat([padded(x), padded(y)]).to(DEV)
+    fi = torch.arange(P, dtype=idx_dtype, device=DEV)
+    ti = fi + P
+    grad = torch.zeros_like(rows)
+    loss, E = ops.pairs_flat_raw(geom, rows, D, fi, ti, K, alpha, w=t(g["w"]).to(DEV),
+                                 is_pos=t(g["is_pos"]).to(torch.uint8).to(DEV), grad_rows=grad, precision=prec)
+    torch.cuda.synchronize()
+    contract(E.cpu().numpy(), g["E64"], g["E32"], name + " E")
+    assert abs(float(loss) - float(g["L64"])) <= max(1e-5 * abs(float(g["L64"])), 2 * abs(float(g["L32"]) - float(g["L64"])))
+    gx, gy = grad[:P, :D].cpu().numpy(), grad[P:, :D].cpu().numpy()
+    contract_rows(gx, g["gx64"], g["gx32"], name + " gx")
+    contract_rows(gy, g["gy64"], g["gy32"], name + " gy")
+    assert float(grad[:, D:].abs().max()) == 0.0 if rows.shape[1] > D else True
+    # hinge-active sets identical away from ties
+    z64 = g["E64"]
+    act_new = (np.linalg.norm(gx, axis=1) > 0)
+    act_ref = (np.linalg.norm(g["gx64"], axis=1) > 0)
+    far = (np.abs(z64) > 1e-5) & (np.abs(alpha - z64) > 1e-5)
+    assert (act_new[far] == act_ref[far]).all()
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("geom,name", pair_files())
+def test_dense_energy_and_backward_match_reference(geom, name, prec):
+    g = load_golden(name)
+    K, alpha = float(g.get("K", 0.0)), float(g["alpha"])
+    x = t(g["x"]).to(DEV).requires_grad_(True)
+    y = t(g["y"]).to(DEV).requires_grad_(True)
+    E = ops.energy(x, y, geom, K, prec)
+    pos = t(g["is_pos"]).to(DEV).bool()
+    w = t(g["w"]).to(DEV)
+    loss = (w * E)[pos].sum() + (w * (alpha - E).clamp(min=0))[~pos].sum()
+    loss.backward()
+    contract(E.detach().cpu().numpy(), g["E64"], g["E32"], name + " E")
+    contract_rows(x.grad.cpu().numpy(), g["gx64"], g["gx32"], name + " gx")
+    contract_rows(y.grad.cpu().numpy(), g["gy64"], g["gy32"], name + " gy")
+
+
+# ------------------------------------------------------------------------------------------------
+# row transforms and RSGD vs golden
+# ------------------------------------------------------------------------------------------------
+ROW_CASES = [("rows_euc", 1, "W"), ("rows_hyp_shell", 2, "W"), ("rows_hyp_tanh", 3, "W"),
+             ("feat_euc", 1, "Z"), ("feat_hyp", 4, "Z")]
+
+
+@pytest.mark.parametrize("D", DIMS)
+@pytest.mark.parametrize("prefix,mode,key", ROW_CASES)
+def test_row_transforms_match_reference(prefix, mode, key, D):
+    g = load_golden("%s_D%d" % (prefix, D))
+    K = float(g["K"])
+    W = t(g[key]).to(DEV).requires_grad_(True)
+    rows = ops.transform_rows(W, mode, K)
+    assert rows.shape[1] == ops.padded_dim(D)
+    if key == "W":
+        idx = t(g["idx"]).to(DEV)
+        out = rows.index_select(0, idx)[:, :D]
+    else:
+        out = rows[:, :D]
+    out.backward(t(g["G_up"]).to(DEV))
+    np.testing.assert_allclose(out.detach().cpu().numpy(), g["out"], rtol=3e-6, atol=2e-7)
+    gref = g["gW"] if key == "W" else g["gZ"]
+    scale = np.abs(gref).max()
+    np.testing.assert_allclose(W.grad.cpu().numpy(), gref, rtol=2e-4, atol=5e-6 * scale)
+    if rows.shape[1] > D:
+        assert float(rows[:, D:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("D", DIMS)
+@pytest.mark.parametrize("lr", ("0p001", "0p1"))
+def test_rsgd_update_matches_reference(D, lr):
+    g = load_golden("rsgd_D%d_lr%s" % (D, lr))
+    W = t(g["W"]).to(DEV).clone()
+    grad = t(g["grad"]).to(DEV).clone()
+    ops.rsgd_update_(W, grad, float(g["lr"]), float(g["r_in"]))
+    contract(W.cpu().numpy(), g["W_new64"], g["W_new"], "rsgd W", rel=1e-5, floor=1e-7)
+    np.testing.assert_allclose(grad.cpu().numpy(), g["rescaled_grad"], rtol=3e-6, atol=0)
+    # padded gradient input gives the same update
+    W2 = t(g["W"]).to(DEV).clone()
+    gp = padded(t(g["grad"])).to(DEV)
+    ops.rsgd_update_(W2, gp, float(g["lr"]), float(g["r_in"]))
+    assert torch.equal(W, W2)
+
+
+# ------------------------------------------------------------------------------------------------
+# full training / eval steps on the ETHEC hierarchy: grouped kernel + row transform + sampler
+# ------------------------------------------------------------------------------------------------
+STEP_CASES = [
+    ("step_euc_D2", "euc", 1), ("step_euc_D2_a0p05", "euc", 1), ("step_euc_D10_ppl", "euc", 1),
+    ("step_hyp_D10", "hyp", 2), ("step_hyp_D10_a0p05", "hyp", 2), ("step_hyp_D50_ppl", "hyp", 2),
+    ("step_oe_D10", "oe", 0),
+]
+
+
+def _neg_adj(h):
+    n = len(h["parents"])
+    A = np.ones((n, n), dtype=bool)
+    A[h["tc_edges"][:, 0], h["tc_edges"][:, 1]] = False
+    np.fill_diagonal(A, False)
+    return A
+
+
+class _LabelMap:
+    def __init__(self, h):
+        self.levels = h["levels"].tolist()
+        self.level_start = h["level_start"].tolist()
+        self.level_stop = h["level_stop"].tolist()
+        self.level_names = ["family", "subfamily", "genus", "genus_specific_epithet"]
+        self.n_classes = int(sum(self.levels))
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("name,geom,mode", STEP_CASES)
+def test_grouped_step_matches_reference(name, geom, mode, prec, ethec):
+    g = load_golden(name)
+    Nn, K, alpha = int(g["N"]), float(g["K"]), float(g["alpha"])
+    B = len(g["u"])
+    D = g["W0"].shape[1]
+    drawn = g["drawn"].reshape(B, Nn, 2)
+    neg_to, neg_from = drawn[:, :, 0].copy(), drawn[:, :, 1].copy()
+    W = t(g["W0"]).to(DEV).requires_grad_(True)
+    rows = ops.transform_rows(W, mode, K)
+    loss, E_pos, E_neg = ops.grouped_pair_loss(rows, D, t(g["u"]).to(DEV), t(g["v"]).to(DEV), t(neg_to).to(DEV),
+                                               t(neg_from).to(DEV), Nn, geom, K, alpha, precision=prec)
+    loss.backward()
+    # ground truth: oracle in fp64 on the same fp32 table; like-for-like: the reference's fp32 golden
+    nf = np.concatenate([np.repeat(g["u"][:, None], Nn, 1), neg_from], 1).reshape(-1)
+    nt = np.concatenate([neg_to, np.repeat(g["v"][:, None], Nn, 1)], 1).reshape(-1)
+    r64 = cones.label_step(geom, t(g["W0"], torch.float64), mode, K, alpha, t(g["u"]), t(g["v"]), t(nf), t(nt))
+    contract(E_pos.cpu().numpy(), r64["E_pos"].numpy(), g["E_pos"], name + " E_pos")
+    contract(E_neg.reshape(-1).cpu().numpy(), r64["E_neg"].numpy(), g["E_neg"], name + " E_neg")
+    assert abs(float(loss) - float(r64["loss"])) <= max(1e-5 * abs(float(r64["loss"])),
+                                                       2 * abs(float(g["loss"]) - float(r64["loss"])))
+    contract_rows(W.grad.cpu().numpy(), r64["gW"].numpy(), g["gW"], name + " gW", floor=2e-5)
+    np.testing.assert_allclose(rows.index_select(0, t(g["u"]).to(DEV))[:, :D].detach().cpu().numpy(), g["from_emb"],
+                               rtol=3e-6, atol=2e-7)
+    # the flat kernel on the expanded pair list gives the same numbers
+    W2 = t(g["W0"]).to(DEV).requires_grad_(True)
+    rows2 = ops.transform_rows(W2, mode, K)
+    fi = torch.cat([t(g["u"]), t(nf)]).to(DEV)
+    ti = torch.cat([t(g["v"]), t(nt)]).to(DEV)
+    is_pos = torch.cat([torch.ones(B), torch.zeros(len(nf))]).to(torch.uint8).to(DEV)
+    loss2, E2 = ops.flat_pair_loss(rows2, D, fi, ti, geom, K, alpha, is_pos=is_pos, precision=prec)
+    loss2.backward()
+    assert torch.equal(E2[:B], E_pos) and torch.equal(E2[B:], E_neg.reshape(-1))
+    np.testing.assert_allclose(float(loss2), float(loss), rtol=1e-6)
+    scale = float(W.grad.abs().max())
+    np.testing.assert_allclose(W2.grad.cpu().numpy(), W.grad.cpu().numpy(), rtol=1e-4, atol=2e-6 * scale)
+
+
+@pytest.mark.parametrize("name,geom", [("step_euc_D2_a0p05", "euc"), ("step_euc_D10_ppl", "euc"),
+                                       ("step_hyp_D10_a0p05", "hyp"), ("step_hyp_D50_ppl", "hyp"),
+                                       ("step_oe_D10", "oe"), ("step_oe_D10_weighted", "oe")])
+def test_dropin_criterion_reproduces_reference_step(name, geom, ethec):
+    """The reference-facing classes: same ctor, same forward signature, bit-exact negatives."""
+    from learning_embeddings_b200 import order_embeddings as oe_mod
+    from learning_embeddings_b200 import order_embeddings_h as oeh_mod
+    import networkx as nx
+
+    g = load_golden(name)
+    lm = _LabelMap(ethec)
+    Nn, alpha = int(g["N"]), float(g["alpha"])
+    D = g["W0"].shape[1]
+    ppl = bool(g["pick_per_level"])
+    if geom == "euc":
+        crit = oe_mod.EucConesLoss(lm, Nn, alpha=alpha, pick_per_level=ppl)
+        model = oe_mod.Embedder(D, lm, K=crit.K)
+    elif geom == "hyp":
+        crit = oeh_mod.EucConesLoss(lm, Nn, alpha=alpha, pick_per_level=ppl)
+        model = oeh_mod.Embedder(D, lm, K=crit.K)
+    else:
+        kw = dict(weigh_neg_term=True, level_weights=t(g["level_weights"])) if bool(g["weigh_neg_term"]) else {}
+        crit = oe_mod.OrderEmbeddingLoss(lm, Nn, alpha=alpha, pick_per_level=ppl, **kw)
+        model = oe_mod.Embedder(D, lm)
+    with torch.no_grad():
+        model.embeddings.weight.copy_(t(g["W0"]))
+    model = model.to(DEV)
+    ident = {i: i for i in range(lm.n_classes)}
+    crit.set_negative_graph(_neg_adj(ethec), ident, ident)
+    G_tc = nx.DiGraph()
+    G_tc.add_nodes_from(range(lm.n_classes))
+    G_tc.add_edges_from(ethec["tc_edges"].tolist())
+    crit.set_graph_tc(G_tc)
+    random.seed(0)
+    u, v = g["u"].tolist(), g["v"].tolist()
+    status = torch.ones(len(u), dtype=torch.int64)
+    from_emb, to_emb, loss, E_pos, E_neg = crit(model, u, v, status, "train", Nn)
+    loss.backward()
+    nf, nt = crit.last_negatives
+    B = len(u)
+    drawn = np.stack([nt.reshape(B, 2 * Nn)[:, :Nn], nf.reshape(B, 2 * Nn)[:, Nn:]], axis=2).reshape(-1)
+    assert drawn.tolist() == g["drawn"].tolist()  # bit-exact negative indices
+    np.testing.assert_allclose(float(loss), float(g["loss"]), rtol=2e-5)
+    np.testing.assert_allclose(E_pos.cpu().numpy(), g["E_pos"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(E_neg.cpu().numpy(), g["E_neg"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(from_emb.detach().cpu().numpy(), g["from_emb"], rtol=3e-6, atol=2e-7)
+    np.testing.assert_allclose(to_emb.detach().cpu().numpy(), g["to_emb"], rtol=3e-6, atol=2e-7)
+    gW = model.embeddings.weight.grad.cpu().numpy()
+    scale = np.abs(g["gW"]).max()
+    np.testing.assert_allclose(gW, g["gW"], rtol=5e-3, atol=1e-4 * scale)
+    # eval phase on a mixed-status batch
+    with torch.no_grad():
+        _, _, ev_loss, ev_Ep, ev_En = crit(model, g["ev_from"].tolist(), g["ev_to"].tolist(), t(g["ev_status"]),
+                                           "val", Nn)
+    np.testing.assert_allclose(ev_Ep.cpu().numpy(), g["ev_E_pos"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(ev_En.cpu().numpy(), g["ev_E_neg"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(float(ev_loss), float(g["ev_loss"]), rtol=2e-5)
+    # E_operator on CPU tensors (the reference's reconstruction check does this)
+    e_cpu = crit.E_operator(from_emb.detach().cpu(), to_emb.detach().cpu())
+    assert not e_cpu.is_cuda
+    np.testing.assert_allclose(e_cpu.numpy(), g["E_pos"], rtol=1e-4, atol=1e-4)
+
+
+def test_hyperbolic_training_step_with_rsgd_matches_reference_update(ethec):
+    """criterion -> backward -> rsgd_step, against oracle.rsgd_step on the reference's own gradient."""
+    from learning_embeddings_b200 import order_embeddings_h as oeh_mod
+    g = load_golden("step_hyp_D10_a0p05")
+    lm = _LabelMap(ethec)
+    crit = oeh_mod.EucConesLoss(lm, 5, alpha=0.05)
+    model = oeh_mod.Embedder(10, lm, K=crit.K)
+    with torch.no_grad():
+        model.embeddings.weight.copy_(t(g["W0"]))
+    model = model.to(DEV)
+    ident = {i: i for i in range(lm.n_classes)}
+    crit.set_negative_graph(_neg_adj(ethec), ident, ident)
+    random.seed(0)
+    _, _, loss, _, _ = crit(model, g["u"].tolist(), g["v"].tolist(), torch.ones(len(g["u"]), dtype=torch.int64), "train", 5)
+    loss.backward()
+    oeh_mod.rsgd_step(model, 0.001, crit.inner_radius)
+    _, W_ref = cones.rsgd_step(t(g["W0"]), t(g["gW"]), 0.001, crit.inner_radius)
+    np.testing.assert_allclose(model.embeddings.weight.detach().cpu().numpy(), W_ref.numpy(), rtol=1e-5, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------------
+# scoring
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("name,geom", [("scoring_hyp_D10", "hyp"), ("scoring_hyp_D50", "hyp"),
+                                       ("scoring_euc_D10", "euc"), ("scoring_oe_D10", "oe")])
+def test_scoring_matches_reference_loop(name, geom, prec):
+    g = load_golden(name)
+    K = float(g["K"])
+    idx, val, scores = ops.score_topk(t(g["labels"]).to(DEV), t(g["images"]).to(DEV), geom, K, g["level_start"],
+                                      g["level_stop"], k=5, want_scores=True, precision=prec)
+    contract(scores.cpu().numpy(), g["E64"], g["E"], name + " scores")
+    tv = g["top_val"]
+    contract(val.cpu().numpy(), tv, tv, name + " topk values", floor=5e-6)
+    distinct = np.ones_like(tv, dtype=bool)
+    gap = (tv[..., 1:] - tv[..., :-1]) > 1e-5
+    distinct[..., 1:] &= gap
+    distinct[..., :-1] &= gap
+    assert (idx.cpu().numpy()[distinct] == g["top_idx"][distinct]).all()  # predicted label sets
+    # NaN row (the reference's off-by-one leaves the last label zero) is never predicted
+    assert not (idx.cpu().numpy() == g["labels"].shape[0] - 1).any()
+    # top-k agrees with torch.topk over the kernel's own full score matrix
+    ridx, rval = cones.topk_per_level(scores.cpu(), g["level_start"], g["level_stop"], 5)
+    np.testing.assert_array_equal(val.cpu().numpy(), rval.numpy())
+
+
+# ------------------------------------------------------------------------------------------------
+# size-independent properties at larger sizes + edge cases
+# ------------------------------------------------------------------------------------------------
+def _ball(gen, n, D, lo, hi):
+    d = torch.randn(n, D, generator=gen)
+    return d / d.norm(dim=1, keepdim=True) * (lo + (hi - lo) * torch.rand(n, 1, generator=gen))
+
+
+@pytest.mark.parametrize("geom,D", [("hyp", 10), ("hyp", 50), ("euc", 10), ("oe", 10), ("hyp", 3), ("euc", 129),
+                                    ("hyp", 300), ("oe", 1)])
+def test_grouped_equals_flat_and_oracle_on_random_tree_batches(geom, D):
+    gen = torch.Generator().manual_seed(D)
+    n, B, Nn = 2000, 3001, 7
+    K = {"euc": 3.0, "hyp": 0.1, "oe": 0.0}[geom]
+    mode = {"euc": 1, "hyp": 2, "oe": 0}[geom]
+    W = _ball(gen, n, D, 0.1, 0.95) if geom == "hyp" else torch.randn(n, D, generator=gen)
+    u = torch.randint(0, n, (B,), generator=gen)
+    v = (u + 1 + torch.randint(0, n - 1, (B,), generator=gen)) % n
+    neg_to = torch.randint(0, n, (B, Nn), generator=gen)
+    neg_from = torch.randint(0, n, (B, Nn), generator=gen)
+    neg_to = torch.where(neg_to == u[:, None], (neg_to + 1) % n, neg_to)
+    neg_from = torch.where(neg_from == v[:, None], (neg_from + 1) % n, neg_from)
+    w_pos = 0.5 + torch.rand(B, generator=gen)
+    w_neg = 0.5 + torch.rand(B, 2 * Nn, generator=gen)
+    nf = torch.cat([u[:, None].expand(B, Nn), neg_from], 1).reshape(-1)
+    nt = torch.cat([neg_to, v[:, None].expand(B, Nn)], 1).reshape(-1)
+    ref = cones.label_step(geom, W.double(), mode, K, 0.7, u, v, nf, nt, w_pos=w_pos.double(),
+                           w_neg=w_neg.reshape(-1).double())
+    ref32 = cones.label_step(geom, W, mode, K, 0.7, u, v, nf, nt, w_pos=w_pos, w_neg=w_neg.reshape(-1))
+    for prec in PRECS:
+        Wd = W.to(DEV).requires_grad_(True)
+        rows = ops.transform_rows(Wd, mode, K)
+        loss, E_pos, E_neg = ops.grouped_pair_loss(rows, D, u.to(DEV).int(), v.to(DEV).int(), neg_to.to(DEV).int(),
+                                                   neg_from.to(DEV).int(), Nn, geom, K, 0.7, w_pos=w_pos, w_neg=w_neg,
+                                                   precision=prec)
+        loss.backward()
+        contract(E_pos.cpu().numpy(), ref["E_pos"].numpy(), ref32["E_pos"].numpy(), "E_pos")
+        contract(E_neg.reshape(-1).cpu().numpy(), ref["E_neg"].numpy(), ref32["E_neg"].numpy(), "E_neg")
+        contract_rows(Wd.grad.cpu().numpy(), ref["gW"].numpy(), ref32["gW"].numpy(), "gW", floor=2e-5)
+        assert abs(float(loss) - float(ref["loss"])) <= 1e-5 * abs(float(ref["loss"])) + 2 * abs(
+            float(ref32["loss"]) - float(ref["loss"]))
+
+
+def test_empty_and_degenerate_batches():
+    rows = torch.zeros(8, 12, device=DEV)
+    rows[:, :10] = torch.rand(8, 10, device=DEV) * 0.2 + 0.05
+    e = torch.empty(0, dtype=torch.int64, device=DEV)
+    loss, E = ops.pairs_flat_raw("hyp", rows, 10, e, e, 0.1, 1.0)
+    assert E.numel() == 0 and float(loss) == 0.0
+    loss, Ep, En = ops.pairs_grouped_raw("hyp", rows, 10, e, e, e.view(0, 5), e.view(0, 5), 5, 0.1, 1.0)
+    assert Ep.numel() == 0 and float(loss) == 0.0
+    # N = 0: positives only
+    u = torch.tensor([0, 1, 2], device=DEV)
+    v = torch.tensor([3, 4, 5], device=DEV)
+    grad = torch.zeros_like(rows)
+    loss, Ep, En = ops.pairs_grouped_raw("hyp", rows, 10, u, v, e.view(3, 0), e.view(3, 0), 0, 0.1, 1.0, grad_rows=grad)
+    ref = cones.energy_hyp(rows[u, :10].cpu().double(), rows[v, :10].cpu().double(), 0.1)
+    np.testing.assert_allclose(Ep.cpu().numpy(), ref.numpy(), rtol=1e-5, atol=2e-6)
+    assert En.numel() == 0
+    # x == y: the reference yields NaN (0/0); so do we
+    E = ops.energy(rows[:2, :10].contiguous(), rows[:2, :10].contiguous(), "hyp", 0.1)
+    assert torch.isnan(E).all()
+    # Euclidean apex inside the K-ball: NaN like the reference
+    x = torch.full((1, 4), 0.1, device=DEV)
+    y = torch.ones(1, 4, device=DEV)
+    assert torch.isnan(ops.energy(x, y, "euc", 3.0)).all()
+    assert torch.isnan(cones.energy_euc(x.cpu(), y.cpu(), 3.0)).all()
+
+
+def test_scoring_full_size_properties():
+    """1 M-image scale is covered by bench.py; here 40 K images x 723 labels: top-k of the kernel equals
+    torch.topk of its own score matrix, shards concatenate, and image order does not matter."""
+    gen = torch.Generator().manual_seed(3)
+    h = load_golden("ethec_hierarchy")
+    L, D, n_img = 723, 10, 40000
+    labels = torch.zeros(L, D)
+    for l in range(4):
+        s, e = int(h["level_start"][l]), int(h["level_stop"][l])
+        labels[s:e] = _ball(gen, e - s, D, 0.10 + 0.2 * l, 0.30 + 0.2 * l)
+    images = _ball(gen, n_img, D, 0.30, 0.95)
+    lab_d, img_d = labels.to(DEV), images.to(DEV)
+    idx, val, scores = ops.score_topk(lab_d, img_d, "hyp", 0.1, h["level_start"], h["level_stop"], k=5, want_scores=True)
+    ridx, rval = cones.topk_per_level(scores.cpu(), h["level_start"], h["level_stop"], 5)
+    np.testing.assert_array_equal(val.cpu().numpy(), rval.numpy())
+    ties = (rval[..., 1:] == rval[..., :-1]).any(dim=-1)
+    assert (idx.cpu()[~ties] == ridx[~ties].int()).all()
+    ref = cones.score_matrix("hyp", labels.double(), images[:512].double(), 0.1)
+    ref32 = cones.score_matrix("hyp", labels, images[:512], 0.1)
+    contract(scores[:512].cpu().numpy(), ref.numpy(), ref32.numpy(), "scores")
+    # sharding: two halves give the same answer as one call
+    i1, v1, _ = ops.score_topk(lab_d, img_d[: n_img // 2], "hyp", 0.1, h["level_start"], h["level_stop"], k=5)
+    i2, v2, _ = ops.score_topk(lab_d, img_d[n_img // 2:], "hyp", 0.1, h["level_start"], h["level_stop"], k=5)
+    assert torch.equal(torch.cat([i1, i2]), idx) and torch.equal(torch.cat([v1, v2]), val)
+    perm = torch.randperm(n_img, generator=gen).to(DEV)
+    ip, vp, _ = ops.score_topk(lab_d, img_d[perm], "hyp", 0.1, h["level_start"], h["level_stop"], k=5)
+    assert torch.equal(ip, idx[perm]) and torch.equal(vp, val[perm])

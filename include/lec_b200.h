@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define LEC_ABI_VERSION 1
+#define LEC_ABI_VERSION 2
 
 /* geometry of the energy */
 #define LEC_GEOM_EUC 0 /* EucConesLoss.E_operator, order_embeddings.py:954-969 = oe.py:721-739 (cos-space) */
@@ -52,6 +52,7 @@ extern "C" {
 #define LEC_E_SIZE      (-4) /* negative count */
 #define LEC_E_ALIGN     (-5) /* rows / grad_rows base not 16-byte aligned */
 #define LEC_E_K         (-6) /* k out of range for top-k */
+#define LEC_E_REPLICAS  (-7) /* grad_replicas < 1 */
 #define LEC_MAX_DIM 1024
 #define LEC_MAX_TOPK 8
 #define LEC_MAX_LEVELS 8
@@ -67,15 +68,20 @@ int64_t lec_launch_count(void);
  * table row instead of once per gathered pair endpoint.
  *   in        [n, D] raw rows (row stride D)
  *   rows_out  [n, ld] transformed rows, pad columns written as 0
- *   zero_out  optional [n, ld] buffer cleared in the same pass (the gradient accumulator), may be NULL
+ *   zero_out  optional [zero_replicas, n, ld] buffer cleared in the same pass (the gradient
+ *             accumulator of the pair kernels), may be NULL
  */
 int lec_rows_fwd(const float* in, int64_t n, int D, int mode, float K, float* rows_out, int ld,
-                 float* zero_out, void* stream);
+                 float* zero_out, int zero_replicas, void* stream);
 
 /* Vector-Jacobian product of lec_rows_fwd: grad_in[n, D] (=|+=) J^T grad_rows[n, ld].
+ * grad_rows is [grad_replicas, n, ld]; the replicas are summed on the fly.
  * Replaces autograd through Embedder.forward incl. embedding_dense_backward.  accumulate != 0 adds. */
-int lec_rows_bwd(const float* in, const float* grad_rows, int64_t n, int D, int ld, int mode, float K,
-                 float* grad_in, int accumulate, void* stream);
+int lec_rows_bwd(const float* in, const float* grad_rows, int grad_replicas, int64_t n, int D, int ld, int mode,
+                 float K, float* grad_in, int accumulate, void* stream);
+
+/* out[count] = sum over r of in[r, count] (the replica sum on its own, e.g. before an all-reduce). */
+int lec_reduce_replicas(const float* in, int replicas, int64_t count, float* out, void* stream);
 
 /* ---- pair energies on gathered rows ------------------------------------------------------------
  * Flat pair list.  Replaces E_operator + positive_pair/negative_pair + the loss sum of
@@ -87,12 +93,17 @@ int lec_rows_bwd(const float* in, const float* grad_rows, int64_t n, int D, int 
  *                    (NULL = all positive)
  *   E_out            [P] raw energies
  *   loss_out         optional double[1], the weighted hinge sum is ADDED to it
- *   grad_rows        optional [n_rows, ld]; if non-NULL d loss / d rows is atomically ADDED to it
+ *   grad_rows        optional [grad_replicas, n_rows, ld]; if non-NULL d loss / d rows is atomically
+ *                    ADDED to it.  The scatter is an L2 vector reduction (REDG.F32x4) whose throughput is
+ *                    limited by same-address serialisation on hot rows, so the kernel spreads its
+ *                    thread blocks over grad_replicas private copies (block b adds to copy b %
+ *                    grad_replicas); the true gradient is their sum (lec_rows_bwd, lec_rsgd_update and
+ *                    lec_reduce_replicas sum them).  grad_replicas >= 1.
  */
 int lec_pairs_flat(int geom, int precision, const float* rows, int64_t n_rows, int D, int ld,
                    const void* from_idx, const void* to_idx, int idx_bytes, const float* w,
                    const uint8_t* is_pos, int64_t P, float K, float alpha, float* E_out,
-                   double* loss_out, float* grad_rows, void* stream);
+                   double* loss_out, float* grad_rows, int grad_replicas, void* stream);
 
 /* Training-layout batch: B positives (u_i, v_i), each with N negatives (u_i, v'_ip) and N negatives
  * (u'_ip, v_i) -- the layout EucConesLoss.forward builds at order_embeddings.py:1063-1091,
@@ -108,7 +119,7 @@ int lec_pairs_grouped(int geom, int precision, const float* rows, int64_t n_rows
                       const void* pos_from, const void* pos_to, const void* neg_to, const void* neg_from,
                       int idx_bytes, int64_t B, int N, const float* w_pos, const float* w_neg, float K,
                       float alpha, float* E_pos, float* E_neg, double* loss_out, float* grad_rows,
-                      void* stream);
+                      int grad_replicas, void* stream);
 
 /* Dense operands (no gather): E_operator(x, y) on arbitrary [P, D] tensors, as the reference calls
  * it from check_graph_embedding (order_embeddings.py:550-551) and the scoring loops. */
@@ -121,13 +132,14 @@ int lec_energy_dense_bwd(int geom, int precision, const float* x, const float* y
 /* ---- Riemannian SGD on the Poincare ball --------------------------------------------------------
  * Replaces order_embeddings_h.py:769-775 (lambda_x :662, exp_map_x :668, mob_add :649, soft_clip :634;
  * joint copy oe_h.py:1604-1644, :1761-1762).  Whole table, in place.
- *   grad [n, ld_g] Euclidean gradient (ld_g = D for a dense nn.Embedding grad)
+ *   grad [grad_replicas, n, ld_g] Euclidean gradient, replicas summed on the fly (ld_g = D and
+ *        grad_replicas = 1 for a dense nn.Embedding grad)
  *   lambda_mode 0: reference conformal factor 2/(1-|x|); 1: textbook 2/(1-|x|^2)
  *   grad_out optional [n, D]: receives the rescaled (Riemannian) gradient as the reference leaves it
- *   in weight.grad; may alias grad when ld_g == D.
+ *   in weight.grad; may alias grad when ld_g == D and grad_replicas == 1.
  */
-int lec_rsgd_update(float* table, const float* grad, int64_t n, int D, int ld_g, float lr, float r_in,
-                    int lambda_mode, float* grad_out, void* stream);
+int lec_rsgd_update(float* table, const float* grad, int grad_replicas, int64_t n, int D, int ld_g, float lr,
+                    float r_in, int lambda_mode, float* grad_out, void* stream);
 
 /* ---- all-pairs image x label scoring ------------------------------------------------------------
  * Replaces the per-image loop of JointEmbeddings.calculate_classification_metrics

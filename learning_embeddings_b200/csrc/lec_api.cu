@@ -17,9 +17,10 @@ int launch_dense_hyp32(const DenseArgs&, bool, cudaStream_t);
 int launch_dense_hyp64(const DenseArgs&, bool, cudaStream_t);
 int launch_dense_oe32(const DenseArgs&, bool, cudaStream_t);
 
-int rows_fwd_launch(const float*, int64_t, int, int, float, float*, int, float*, cudaStream_t);
-int rows_bwd_launch(const float*, const float*, int64_t, int, int, int, float, float*, int, cudaStream_t);
-int rsgd_launch(float*, const float*, int64_t, int, int, float, float, int, float*, cudaStream_t);
+int rows_fwd_launch(const float*, int64_t, int, int, float, float*, int, float*, int, cudaStream_t);
+int rows_bwd_launch(const float*, const float*, int, int64_t, int, int, int, float, float*, int, cudaStream_t);
+int rsgd_launch(float*, const float*, int, int64_t, int, int, float, float, int, float*, cudaStream_t);
+int reduce_replicas_launch(const float*, int, int64_t, float*, cudaStream_t);
 int score_launch(int, int, const float*, int64_t, const float*, int64_t, int, float, const int32_t*, const int32_t*,
                  int, int, float*, int32_t*, float*, cudaStream_t);
 
@@ -58,40 +59,52 @@ const char* lec_error_string(int code) {
         case LEC_E_SIZE: return "negative element count";
         case LEC_E_ALIGN: return "rows / grad_rows must be 16-byte aligned";
         case LEC_E_K: return "top-k: need 1 <= k <= 8 and 1 <= n_levels <= 8";
+        case LEC_E_REPLICAS: return "grad_replicas must be >= 1";
     }
     if (code > 0) return cudaGetErrorString((cudaError_t)code);
     return "unknown lec error";
 }
 
 int lec_rows_fwd(const float* in, int64_t n, int D, int mode, float K, float* rows_out, int ld, float* zero_out,
-                 void* stream) {
+                 int zero_replicas, void* stream) {
+    if (zero_out && zero_replicas < 1) return LEC_E_REPLICAS;
     if (!in || !rows_out) return LEC_E_NULL;
     if (n < 0) return LEC_E_SIZE;
     if (mode < LEC_ROWS_NONE || mode > LEC_ROWS_HYP_TANH_FEAT) return LEC_E_ENUM;
     if (int e = check_rows(rows_out, D, ld)) return e;
-    return rows_fwd_launch(in, n, D, mode, K, rows_out, ld, zero_out, (cudaStream_t)stream);
+    return rows_fwd_launch(in, n, D, mode, K, rows_out, ld, zero_out, zero_replicas, (cudaStream_t)stream);
 }
 
-int lec_rows_bwd(const float* in, const float* grad_rows, int64_t n, int D, int ld, int mode, float K, float* grad_in,
-                 int accumulate, void* stream) {
+int lec_rows_bwd(const float* in, const float* grad_rows, int grad_replicas, int64_t n, int D, int ld, int mode, float K,
+                 float* grad_in, int accumulate, void* stream) {
+    if (grad_replicas < 1) return LEC_E_REPLICAS;
     if (!in || !grad_rows || !grad_in) return LEC_E_NULL;
     if (n < 0) return LEC_E_SIZE;
     if (mode < LEC_ROWS_NONE || mode > LEC_ROWS_HYP_TANH_FEAT) return LEC_E_ENUM;
     if (int e = check_rows(grad_rows, D, ld)) return e;
-    return rows_bwd_launch(in, grad_rows, n, D, ld, mode, K, grad_in, accumulate, (cudaStream_t)stream);
+    return rows_bwd_launch(in, grad_rows, grad_replicas, n, D, ld, mode, K, grad_in, accumulate, (cudaStream_t)stream);
+}
+
+int lec_reduce_replicas(const float* in, int replicas, int64_t count, float* out, void* stream) {
+    if (!in || !out) return LEC_E_NULL;
+    if (count < 0) return LEC_E_SIZE;
+    if (replicas < 1) return LEC_E_REPLICAS;
+    return reduce_replicas_launch(in, replicas, count, out, (cudaStream_t)stream);
 }
 
 int lec_pairs_flat(int geom, int precision, const float* rows, int64_t n_rows, int D, int ld, const void* from_idx,
                    const void* to_idx, int idx_bytes, const float* w, const uint8_t* is_pos, int64_t P, float K,
-                   float alpha, float* E_out, double* loss_out, float* grad_rows, void* stream) {
+                   float alpha, float* E_out, double* loss_out, float* grad_rows, int grad_replicas, void* stream) {
     const int core = pick_core(geom, precision);
     if (core < 0 || (idx_bytes != 4 && idx_bytes != 8)) return LEC_E_ENUM;
     if (P < 0 || n_rows < 0) return LEC_E_SIZE;
     if (int e = check_rows(rows, D, ld)) return e;
     if (grad_rows && (reinterpret_cast<uintptr_t>(grad_rows) & 15)) return LEC_E_ALIGN;
+    if (grad_rows && grad_replicas < 1) return LEC_E_REPLICAS;
     if (P == 0) return 0;
     if (!from_idx || !to_idx || !E_out) return LEC_E_NULL;
-    FlatArgs a{rows, ld, from_idx, to_idx, idx_bytes, w, is_pos, P, K, alpha, E_out, loss_out, grad_rows};
+    FlatArgs a{rows, ld, from_idx, to_idx, idx_bytes, w, is_pos, P, K, alpha, E_out, loss_out, grad_rows,
+               grad_replicas, n_rows * (int64_t)ld};
     cudaStream_t st = (cudaStream_t)stream;
     switch (core) {
         case CORE_EUC32: return launch_flat_euc32(a, st);
@@ -104,17 +117,18 @@ int lec_pairs_flat(int geom, int precision, const float* rows, int64_t n_rows, i
 int lec_pairs_grouped(int geom, int precision, const float* rows, int64_t n_rows, int D, int ld, const void* pos_from,
                       const void* pos_to, const void* neg_to, const void* neg_from, int idx_bytes, int64_t B, int N,
                       const float* w_pos, const float* w_neg, float K, float alpha, float* E_pos, float* E_neg,
-                      double* loss_out, float* grad_rows, void* stream) {
+                      double* loss_out, float* grad_rows, int grad_replicas, void* stream) {
     const int core = pick_core(geom, precision);
     if (core < 0 || (idx_bytes != 4 && idx_bytes != 8)) return LEC_E_ENUM;
     if (B < 0 || N < 0 || n_rows < 0) return LEC_E_SIZE;
     if (int e = check_rows(rows, D, ld)) return e;
     if (grad_rows && (reinterpret_cast<uintptr_t>(grad_rows) & 15)) return LEC_E_ALIGN;
+    if (grad_rows && grad_replicas < 1) return LEC_E_REPLICAS;
     if (B == 0) return 0;
     if (!pos_from || !pos_to || !E_pos) return LEC_E_NULL;
     if (N > 0 && (!neg_to || !neg_from || !E_neg)) return LEC_E_NULL;
     GroupArgs a{rows, ld, pos_from, pos_to, neg_to, neg_from, idx_bytes, B, N, w_pos, w_neg, K, alpha,
-                E_pos, E_neg, loss_out, grad_rows};
+                E_pos, E_neg, loss_out, grad_rows, grad_replicas, n_rows * (int64_t)ld};
     cudaStream_t st = (cudaStream_t)stream;
     switch (core) {
         case CORE_EUC32: return launch_grouped_euc32(a, st);
@@ -153,13 +167,14 @@ int lec_energy_dense_bwd(int geom, int precision, const float* x, const float* y
     return dense_common(geom, precision, a, true, stream);
 }
 
-int lec_rsgd_update(float* table, const float* grad, int64_t n, int D, int ld_g, float lr, float r_in, int lambda_mode,
-                    float* grad_out, void* stream) {
+int lec_rsgd_update(float* table, const float* grad, int grad_replicas, int64_t n, int D, int ld_g, float lr, float r_in,
+                    int lambda_mode, float* grad_out, void* stream) {
     if (!table || !grad) return LEC_E_NULL;
+    if (grad_replicas < 1) return LEC_E_REPLICAS;
     if (n < 0) return LEC_E_SIZE;
     if (D < 1 || D > LEC_MAX_DIM || ld_g < D) return LEC_E_DIM;
     if (lambda_mode != 0 && lambda_mode != 1) return LEC_E_ENUM;
-    return rsgd_launch(table, grad, n, D, ld_g, lr, r_in, lambda_mode, grad_out, (cudaStream_t)stream);
+    return rsgd_launch(table, grad, grad_replicas, n, D, ld_g, lr, r_in, lambda_mode, grad_out, (cudaStream_t)stream);
 }
 
 int lec_score_topk(int geom, int precision, const float* labels, int64_t L, const float* images, int64_t N, int D,

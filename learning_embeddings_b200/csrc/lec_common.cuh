@@ -64,17 +64,18 @@ __device__ __forceinline__ S dot_part(const Vec<V>& a, const Vec<V>& b) {
     return s;
 }
 
-// sum (a-b)^2 with the subtraction done in fp32 exactly as torch.norm(x - y) sees it
+// sum (a-b)^2; the subtraction is done in the accumulator type (fp32: exactly what torch.norm(x - y)
+// sees in the reference's fp32 run; fp64: exact difference of the fp32 inputs)
 template <typename S, int V>
 __device__ __forceinline__ S dist2_part(const Vec<V>& a, const Vec<V>& b) {
     S s = 0;
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-        float d;
-        d = a.c[j].x - b.c[j].x; s += (S)d * (S)d;
-        d = a.c[j].y - b.c[j].y; s += (S)d * (S)d;
-        d = a.c[j].z - b.c[j].z; s += (S)d * (S)d;
-        d = a.c[j].w - b.c[j].w; s += (S)d * (S)d;
+        S d;
+        d = (S)a.c[j].x - (S)b.c[j].x; s += d * d;
+        d = (S)a.c[j].y - (S)b.c[j].y; s += d * d;
+        d = (S)a.c[j].z - (S)b.c[j].z; s += d * d;
+        d = (S)a.c[j].w - (S)b.c[j].w; s += d * d;
     }
     return s;
 }
@@ -85,10 +86,10 @@ __device__ __forceinline__ S dot_diff_part(const Vec<V>& x, const Vec<V>& y) {
     S s = 0;
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-        s += (S)x.c[j].x * (S)(y.c[j].x - x.c[j].x);
-        s += (S)x.c[j].y * (S)(y.c[j].y - x.c[j].y);
-        s += (S)x.c[j].z * (S)(y.c[j].z - x.c[j].z);
-        s += (S)x.c[j].w * (S)(y.c[j].w - x.c[j].w);
+        s += (S)x.c[j].x * ((S)y.c[j].x - (S)x.c[j].x);
+        s += (S)x.c[j].y * ((S)y.c[j].y - (S)x.c[j].y);
+        s += (S)x.c[j].z * ((S)y.c[j].z - (S)x.c[j].z);
+        s += (S)x.c[j].w * ((S)y.c[j].w - (S)x.c[j].w);
     }
     return s;
 }
@@ -132,6 +133,14 @@ struct PairGrad {
 };
 
 template <typename S> __device__ __forceinline__ S s_sqrt(S v);
+// a*b - c*d with both products rounded before the subtraction (no FMA contraction), so that the
+// numerator of the hyperbolic angle is exactly 0 when x == y, as in the reference (0/0 -> NaN)
+__device__ __forceinline__ float diff_of_products(float a, float b, float c, float d) {
+    return __fsub_rn(__fmul_rn(a, b), __fmul_rn(c, d));
+}
+__device__ __forceinline__ double diff_of_products(double a, double b, double c, double d) {
+    return __dsub_rn(__dmul_rn(a, b), __dmul_rn(c, d));
+}
 template <> __device__ __forceinline__ float s_sqrt<float>(float v) { return sqrtf(v); }
 template <> __device__ __forceinline__ double s_sqrt<double>(double v) { return sqrt(v); }
 
@@ -166,7 +175,7 @@ __device__ __forceinline__ void hyp_core(S A, S B, S P, S S2, float K, PairGrad&
     const S w2 = one + A * B - (S)2 * P;
     const S den = a * s_sqrt<S>(S2) * s_sqrt<S>(w2);
     const S inv_den = one / den;
-    const S g = (P * (one + A) - A * (one + B)) * inv_den;
+    const S g = diff_of_products(P, one + A, A, one + B) * inv_den;
     const S h = (S)K * (one - A) / a;
     const S gc = g < lo ? lo : (g > hi ? hi : g);  // NaN falls through unchanged, like torch.clamp
     const S hc = h < lo ? lo : (h > hi ? hi : h);

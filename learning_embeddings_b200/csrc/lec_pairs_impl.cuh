@@ -19,7 +19,7 @@ struct FlatArgs {
     const void* from_idx; const void* to_idx; int idx_bytes;
     const float* w; const uint8_t* is_pos;
     int64_t P; float K, alpha;
-    float* E_out; double* loss_out; float* grad_rows;
+    float* E_out; double* loss_out; float* grad_rows; int grad_replicas; int64_t replica_stride;
 };
 
 struct GroupArgs {
@@ -28,7 +28,7 @@ struct GroupArgs {
     int64_t B; int N;
     const float* w_pos; const float* w_neg;
     float K, alpha;
-    float* E_pos; float* E_neg; double* loss_out; float* grad_rows;
+    float* E_pos; float* E_neg; double* loss_out; float* grad_rows; int grad_replicas; int64_t replica_stride;
 };
 
 struct DenseArgs {
@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(kThreads) pairs_flat_kernel(const FlatArgs a) 
     const int64_t team = (int64_t)blockIdx.x * (kThreads / T) + threadIdx.x / T;
     const int64_t iters = (a.P + n_teams - 1) / n_teams;
     const int Q = a.ld >> 2;
+    float* const grad_base = GRAD ? a.grad_rows + (int64_t)(blockIdx.x % a.grad_replicas) * a.replica_stride : nullptr;
     double loss = 0.0;
     for (int64_t it = 0; it < iters; ++it) {
         const int64_t p = team + it * n_teams;
@@ -105,8 +106,8 @@ __global__ void __launch_bounds__(kThreads) pairs_flat_kernel(const FlatArgs a) 
             loss += l;
         }
         if (GRAD && valid && cf != 0.f) {
-            float* gx = a.grad_rows + ix * (int64_t)a.ld;
-            float* gy = a.grad_rows + iy * (int64_t)a.ld;
+            float* gx = grad_base + ix * (int64_t)a.ld;
+            float* gy = grad_base + iy * (int64_t)a.ld;
 #pragma unroll
             for (int j = 0; j < V; ++j) {
                 const int q = lane_t + T * j;
@@ -142,6 +143,7 @@ __global__ void __launch_bounds__(kThreads) pairs_grouped_kernel(const GroupArgs
     const int64_t iters = (a.B + n_teams - 1) / n_teams;
     const int Q = a.ld >> 2;
     const int N = a.N;
+    float* const grad_base = GRAD ? a.grad_rows + (int64_t)(blockIdx.x % a.grad_replicas) * a.replica_stride : nullptr;
     double loss = 0.0;
     for (int64_t it = 0; it < iters; ++it) {
         const int64_t gidx = team + it * n_teams;
@@ -202,7 +204,7 @@ __global__ void __launch_bounds__(kThreads) pairs_grouped_kernel(const GroupArgs
             if (writer) a.E_neg[ebase + p] = E;
             if (GRAD && valid && cf != 0.f) {
                 touch_u = true;
-                float* gcp = a.grad_rows + ic * (int64_t)a.ld;
+                float* gcp = grad_base + ic * (int64_t)a.ld;
                 if (!Tr::oe) su_u += cf * g.zxx;
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
@@ -232,7 +234,7 @@ __global__ void __launch_bounds__(kThreads) pairs_grouped_kernel(const GroupArgs
             if (writer) a.E_neg[ebase + N + p] = E;
             if (GRAD && valid && cf != 0.f) {
                 touch_w = true;
-                float* gcp = a.grad_rows + ic * (int64_t)a.ld;
+                float* gcp = grad_base + ic * (int64_t)a.ld;
                 if (!Tr::oe) sw_w += cf * g.zyy;
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
@@ -251,8 +253,8 @@ __global__ void __launch_bounds__(kThreads) pairs_grouped_kernel(const GroupArgs
         }
         if (writer) loss += l;
         if (GRAD && valid) {
-            float* gu = a.grad_rows + iu * (int64_t)a.ld;
-            float* gw = a.grad_rows + iv * (int64_t)a.ld;
+            float* gu = grad_base + iu * (int64_t)a.ld;
+            float* gw = grad_base + iv * (int64_t)a.ld;
 #pragma unroll
             for (int j = 0; j < V; ++j) {
                 const int q = lane_t + T * j;

@@ -8,9 +8,16 @@ namespace lec {
 
 struct RowsArgs {
     const float* in; int64_t n; int D; int mode; float K; float r_in; float c0;
-    float* out; int ld; float* zero_out;
+    float* out; int ld; float* zero_out; int replicas; int64_t replica_stride;
     const float* grad_rows; float* grad_in; int accumulate;
 };
+
+// sum of the gradient replicas at one element
+__device__ __forceinline__ float rsum(const float* g, int replicas, int64_t stride) {
+    float v = g[0];
+    for (int r = 1; r < replicas; ++r) v += g[r * stride];
+    return v;
+}
 
 template <int TT>
 __device__ __forceinline__ float tsum(float v) { return team_sum<TT, float>(v); }
@@ -79,7 +86,8 @@ __global__ void __launch_bounds__(kThreads) rows_fwd_kernel(const RowsArgs a) {
                     if (hyp && (mul != 1.f || div != 1.f)) v = ((add + v) / div) * mul;
                 }
                 o[d] = v;
-                if (zo) zo[d] = 0.f;
+                if (zo)
+                    for (int r = 0; r < a.replicas; ++r) zo[r * a.replica_stride + d] = 0.f;
             }
         }
     }
@@ -102,7 +110,7 @@ __global__ void __launch_bounds__(kThreads) rows_bwd_kernel(const RowsArgs a) {
         if (a.mode == LEC_ROWS_EUC_SOFTCLIP) {
             float ss = 0.f, eg = 0.f;
             for (int d = lane; d < D; d += TT) {
-                const float ev = __ldg(e + d), gv = __ldg(g + d);
+                const float ev = __ldg(e + d), gv = rsum(g + d, a.replicas, a.replica_stride);
                 ss = fmaf(ev, ev, ss);
                 eg = fmaf(ev, gv, eg);
             }
@@ -113,7 +121,7 @@ __global__ void __launch_bounds__(kThreads) rows_bwd_kernel(const RowsArgs a) {
         } else if (a.mode == LEC_ROWS_HYP_TANH || a.mode == LEC_ROWS_HYP_TANH_FEAT) {
             float ss = 0.f, eg = 0.f;
             for (int d = lane; d < D; d += TT) {
-                const float ev = __ldg(e + d) + 1e-15f, gv = __ldg(g + d);
+                const float ev = __ldg(e + d) + 1e-15f, gv = rsum(g + d, a.replicas, a.replica_stride);
                 ss = fmaf(ev, ev, ss);
                 eg = fmaf(ev, gv, eg);
             }
@@ -132,7 +140,7 @@ __global__ void __launch_bounds__(kThreads) rows_bwd_kernel(const RowsArgs a) {
             for (int d = lane; d < D; d += TT) {
                 float ev = __ldg(e + d);
                 if (hyp) ev += 1e-15f;
-                float v = fmaf(c_e, ev, c_g * __ldg(g + d));
+                float v = fmaf(c_e, ev, c_g * rsum(g + d, a.replicas, a.replica_stride));
                 if (a.accumulate) v += o[d];
                 o[d] = v;
             }
@@ -142,7 +150,7 @@ __global__ void __launch_bounds__(kThreads) rows_bwd_kernel(const RowsArgs a) {
 
 struct RsgdArgs {
     float* table; const float* grad; int64_t n; int D; int ld_g; float lr; float r_in; int lambda_mode;
-    float* grad_out;
+    float* grad_out; int replicas; int64_t replica_stride;
 };
 
 template <int TT>
@@ -170,7 +178,7 @@ __global__ void __launch_bounds__(kThreads) rsgd_kernel(const RsgdArgs a) {
         // v = -lr * g' + 1e-15 ; |v|
         float vv = 0.f;
         for (int d = lane; d < D; d += TT) {
-            const float v = -a.lr * (g[d] * gs) + 1e-15f;
+            const float v = -a.lr * (rsum(g + d, a.replicas, a.replica_stride) * gs) + 1e-15f;
             vv = fmaf(v, v, vv);
         }
         vv = tsum<TT>(vv);
@@ -179,7 +187,7 @@ __global__ void __launch_bounds__(kThreads) rsgd_kernel(const RsgdArgs a) {
         // t = th * v / |v| + 1e-6 ; Moebius sums
         float uv = 0.f, tt = 0.f;
         for (int d = lane; d < D; d += TT) {
-            const float v = -a.lr * (g[d] * gs) + 1e-15f;
+            const float v = -a.lr * (rsum(g + d, a.replicas, a.replica_stride) * gs) + 1e-15f;
             const float t = th * v / vn + 1e-6f;
             uv = fmaf(w[d], t, uv);
             tt = fmaf(t, t, tt);
@@ -191,7 +199,7 @@ __global__ void __launch_bounds__(kThreads) rsgd_kernel(const RsgdArgs a) {
         const float ct = (1.f - uu) / den;
         float rr = 0.f;
         for (int d = lane; d < D; d += TT) {
-            const float v = -a.lr * (g[d] * gs) + 1e-15f;
+            const float v = -a.lr * (rsum(g + d, a.replicas, a.replica_stride) * gs) + 1e-15f;
             const float t = th * v / vn + 1e-6f;
             const float res = cw * w[d] + ct * t;
             rr = fmaf(res, res, rr);
@@ -202,7 +210,7 @@ __global__ void __launch_bounds__(kThreads) rsgd_kernel(const RsgdArgs a) {
         if (valid) {
             float* go = a.grad_out ? a.grad_out + row * (int64_t)D : nullptr;
             for (int d = lane; d < D; d += TT) {
-                const float gsc = g[d] * gs;
+                const float gsc = rsum(g + d, a.replicas, a.replica_stride) * gs;
                 const float v = -a.lr * gsc + 1e-15f;
                 const float t = th * v / vn + 1e-6f;
                 float res = cw * w[d] + ct * t;
@@ -212,6 +220,22 @@ __global__ void __launch_bounds__(kThreads) rsgd_kernel(const RsgdArgs a) {
             }
         }
     }
+}
+
+__global__ void __launch_bounds__(kThreads) reduce_replicas_kernel(const float* in, int replicas, int64_t count,
+                                                                   float* out) {
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < count; i += stride)
+        out[i] = rsum(in + i, replicas, count);
+}
+
+int reduce_replicas_launch(const float* in, int replicas, int64_t count, float* out, cudaStream_t st) {
+    if (count == 0) return 0;
+    int64_t need = (count + kThreads - 1) / kThreads;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    reduce_replicas_kernel<<<(int)(need < cap ? need : cap), kThreads, 0, st>>>(in, replicas, count, out);
+    ++g_launches;
+    return (int)cudaGetLastError();
 }
 
 static int team_width(int D) {
@@ -254,9 +278,10 @@ static float atanh_clamped(double v) {  // oe_h.py:106-110
 }
 
 int rows_fwd_launch(const float* in, int64_t n, int D, int mode, float K, float* out, int ld, float* zero_out,
-                    cudaStream_t st) {
+                    int zero_replicas, cudaStream_t st) {
     RowsArgs a{};
     a.in = in; a.n = n; a.D = D; a.mode = mode; a.K = K; a.out = out; a.ld = ld; a.zero_out = zero_out;
+    a.replicas = zero_replicas; a.replica_stride = n * (int64_t)ld;
     const double k = (double)K;
     const double rin = 2.0 * k / (1.0 + sqrt(1.0 + 4.0 * k * k));
     a.r_in = (float)rin;
@@ -266,9 +291,10 @@ int rows_fwd_launch(const float* in, int64_t n, int D, int mode, float K, float*
     return (int)cudaGetLastError();
 }
 
-int rows_bwd_launch(const float* in, const float* grad_rows, int64_t n, int D, int ld, int mode, float K,
+int rows_bwd_launch(const float* in, const float* grad_rows, int replicas, int64_t n, int D, int ld, int mode, float K,
                     float* grad_in, int accumulate, cudaStream_t st) {
     RowsArgs a{};
+    a.replicas = replicas; a.replica_stride = n * (int64_t)ld;
     a.in = in; a.n = n; a.D = D; a.mode = mode; a.K = K; a.ld = ld; a.grad_rows = grad_rows; a.grad_in = grad_in;
     a.accumulate = accumulate;
     a.r_in = inner_radius(K);
@@ -278,9 +304,9 @@ int rows_bwd_launch(const float* in, const float* grad_rows, int64_t n, int D, i
     return (int)cudaGetLastError();
 }
 
-int rsgd_launch(float* table, const float* grad, int64_t n, int D, int ld_g, float lr, float r_in, int lambda_mode,
-                float* grad_out, cudaStream_t st) {
-    RsgdArgs a{table, grad, n, D, ld_g, lr, r_in, lambda_mode, grad_out};
+int rsgd_launch(float* table, const float* grad, int replicas, int64_t n, int D, int ld_g, float lr, float r_in,
+                int lambda_mode, float* grad_out, cudaStream_t st) {
+    RsgdArgs a{table, grad, n, D, ld_g, lr, r_in, lambda_mode, grad_out, replicas, n * (int64_t)ld_g};
     if (n == 0) return 0;
     LEC_ROWS_DISPATCH(rsgd_kernel, a, n, D, st);
     return (int)cudaGetLastError();

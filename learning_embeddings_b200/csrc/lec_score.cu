@@ -142,12 +142,12 @@ __global__ void __launch_bounds__(kThreads) score_kernel(const ScoreArgs a) {
                 if (GEOMC == SC_HYP64) {
                     const double Ad = A, Bd = B, pd = p;
                     const double w2 = 1.0 + Ad * Bd - 2.0 * pd;
-                    const double g = (pd * (1.0 + Ad) - Ad * (1.0 + Bd)) / (sqrt(Ad) * sqrt((double)s2) * sqrt(w2));
+                    const double g = diff_of_products(pd, 1.0 + Ad, Ad, 1.0 + Bd) / (sqrt(Ad) * sqrt((double)s2) * sqrt(w2));
                     const double gc = g < -1.0 + 1e-5 ? -1.0 + 1e-5 : (g > 1.0 - 1e-5 ? 1.0 - 1e-5 : g);
                     theta = atan2f((float)sqrt((1.0 - gc) * (1.0 + gc)), (float)gc);
                 } else {
                     const float w2 = 1.f + A * B - 2.f * p;
-                    const float g = (p * (1.f + A) - A * (1.f + B)) / (sqrtf(A) * sqrtf(s2) * sqrtf(w2));
+                    const float g = diff_of_products(p, 1.f + A, A, 1.f + B) / (sqrtf(A) * sqrtf(s2) * sqrtf(w2));
                     const float gc = g < -1.f + kClampEps ? -1.f + kClampEps : (g > 1.f - kClampEps ? 1.f - kClampEps : g);
                     theta = acosf(gc);
                 }

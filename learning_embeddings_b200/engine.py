@@ -31,7 +31,7 @@ def pack_index_block(pos_from, pos_to, neg_to, neg_from, pin=True):
 
 class ConeStep:
     def __init__(self, table, geom, n_neg, max_groups, K=None, alpha=1.0, lr=1e-3, row_mode=None, update="auto",
-                 precision=ops.PREC_F32, process_group=None):
+                 precision=ops.PREC_F32, process_group=None, replicas=None):
         N.require_cuda(table)
         if table.dtype != torch.float32 or not table.is_contiguous():
             raise N.LecError("ConeStep: table must be a contiguous float32 CUDA tensor (updated in place)")
@@ -51,8 +51,9 @@ class ConeStep:
         self.pg = process_group
         self.max_groups = int(max_groups)
         dev = table.device
+        self.replicas = ops.default_replicas(self.n, self.ld) if replicas is None else int(replicas)
         self.rows = torch.empty((self.n, self.ld), device=dev, dtype=torch.float32)
-        self.grad_rows = torch.empty((self.n, self.ld), device=dev, dtype=torch.float32)
+        self.grad_rows = torch.empty((self.replicas, self.n, self.ld), device=dev, dtype=torch.float32)
         self.grad_table = torch.empty((self.n, self.D), device=dev, dtype=torch.float32)
         self.E_pos = torch.empty(self.max_groups, device=dev, dtype=torch.float32)
         self.E_neg = torch.empty((self.max_groups, 2 * self.n_neg), device=dev, dtype=torch.float32)
@@ -73,7 +74,7 @@ class ConeStep:
         if B > self.max_groups:
             raise N.LecError("batch of %d positives exceeds max_groups=%d" % (B, self.max_groups))
         N.check(lib.lec_rows_fwd(N._p(self.table), self.n, self.D, self.row_mode, self.K, N._p(self.rows), self.ld,
-                                 N._p(self.grad_rows), st), "lec_rows_fwd")
+                                 N._p(self.grad_rows), self.replicas, st), "lec_rows_fwd")
         self.loss.zero_()
         ev = self.kernel_events
         if ev is not None:
@@ -81,7 +82,7 @@ class ConeStep:
         N.check(lib.lec_pairs_grouped(
             N.GEOM[self.geom], self.precision, N._p(self.rows), self.n, self.D, self.ld, N._p(pos_from), N._p(pos_to),
             N._p(neg_to), N._p(neg_from), pos_from.element_size(), B, self.n_neg, N._p(w_pos), N._p(w_neg), self.K,
-            self.alpha, N._p(self.E_pos), N._p(self.E_neg), N._p(self.loss), N._p(self.grad_rows), st),
+            self.alpha, N._p(self.E_pos), N._p(self.E_neg), N._p(self.loss), N._p(self.grad_rows), self.replicas, st),
             "lec_pairs_grouped")
         if ev is not None:
             ev[1].record()
@@ -89,18 +90,20 @@ class ConeStep:
 
     def reduce_and_update(self):
         lib, st = N.lib(), N.stream_ptr(self.table.device)
-        if self.pg is not None and torch.distributed.get_world_size(self.pg) > 1:
-            torch.distributed.all_reduce(self.grad_rows, group=self.pg)
-            torch.distributed.all_reduce(self.loss, group=self.pg)
-        if self.update == "rsgd" and self.row_mode == N.ROWS_HYP_SHELL:
-            # straight-through rows: d/dtable == d/drows, feed the padded buffer to the update directly
-            N.check(lib.lec_rsgd_update(N._p(self.table), N._p(self.grad_rows), self.n, self.D, self.ld, self.lr,
-                                        self.r_in, 0, N._p(self.grad_table), st), "lec_rsgd_update")
+        multi = self.pg is not None and torch.distributed.get_world_size(self.pg) > 1
+        if not multi and self.update == "rsgd" and self.row_mode == N.ROWS_HYP_SHELL:
+            # straight-through rows: d/dtable == d/drows; the update sums the replicas itself
+            N.check(lib.lec_rsgd_update(N._p(self.table), N._p(self.grad_rows), self.replicas, self.n, self.D, self.ld,
+                                        self.lr, self.r_in, 0, N._p(self.grad_table), st), "lec_rsgd_update")
             return
-        N.check(lib.lec_rows_bwd(N._p(self.table), N._p(self.grad_rows), self.n, self.D, self.ld, self.row_mode,
-                                 self.K, N._p(self.grad_table), 0, st), "lec_rows_bwd")
+        # d/dtable = J^T (sum of replicas); it is linear, so ranks can be summed after it
+        N.check(lib.lec_rows_bwd(N._p(self.table), N._p(self.grad_rows), self.replicas, self.n, self.D, self.ld,
+                                 self.row_mode, self.K, N._p(self.grad_table), 0, st), "lec_rows_bwd")
+        if multi:
+            torch.distributed.all_reduce(self.grad_table, group=self.pg)
+            torch.distributed.all_reduce(self.loss, group=self.pg)
         if self.update == "rsgd":
-            N.check(lib.lec_rsgd_update(N._p(self.table), N._p(self.grad_table), self.n, self.D, self.D, self.lr,
+            N.check(lib.lec_rsgd_update(N._p(self.table), N._p(self.grad_table), 1, self.n, self.D, self.D, self.lr,
                                         self.r_in, 0, N._p(self.grad_table), st), "lec_rsgd_update")
         elif self.update == "sgd":
             self.table.add_(self.grad_table, alpha=-self.lr)

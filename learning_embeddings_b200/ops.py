@@ -13,6 +13,25 @@ from . import _native as N
 from ._native import GEOM, PREC_F32, PREC_F64CORE  # noqa: F401  (re-exported)
 
 
+def default_replicas(n_rows, ld):
+    """How many private copies of the gradient table the pair kernels scatter into.
+
+    Same-address L2 reductions serialise, so a small hot table (ETHEC: 723 rows) is replicated; a big
+    table (82 K rows) has little per-address contention and stays single.  Budget: 2 M floats."""
+    return int(max(1, min(32, (2 << 20) // max(1, int(n_rows) * int(ld)))))
+
+
+def reduce_replicas(grad_rows):
+    """[R, n, ld] -> [n, ld] (lec_reduce_replicas)."""
+    R = grad_rows.shape[0]
+    if R == 1:
+        return grad_rows[0]
+    out = torch.empty_like(grad_rows[0])
+    N.check(N.lib().lec_reduce_replicas(N._p(grad_rows), R, out.numel(), N._p(out), N.stream_ptr(out.device)),
+            "lec_reduce_replicas")
+    return out
+
+
 def padded_dim(D):
     """Row stride of the transformed table: D rounded up to a multiple of 4 floats (16-byte chunks)."""
     return (int(D) + 3) // 4 * 4
@@ -46,21 +65,23 @@ def rows_forward(W, mode, K, zero_out=None):
     n, D = W.shape
     ld = padded_dim(D)
     rows = torch.empty((n, ld), device=W.device, dtype=torch.float32)
-    N.check(N.lib().lec_rows_fwd(N._p(W), n, D, int(mode), float(K or 0.0), N._p(rows), ld, N._p(zero_out),
+    zr = 0 if zero_out is None else (zero_out.shape[0] if zero_out.dim() == 3 else 1)
+    N.check(N.lib().lec_rows_fwd(N._p(W), n, D, int(mode), float(K or 0.0), N._p(rows), ld, N._p(zero_out), zr,
                                  N.stream_ptr(W.device)), "lec_rows_fwd")
     return rows
 
 
 def rows_backward(W, grad_rows, mode, K, out=None, accumulate=False):
-    """grad wrt the raw rows W [n, D] from grad wrt the transformed rows [n, ld] (lec_rows_bwd)."""
+    """grad wrt the raw rows W [n, D] from grad wrt the transformed rows [n, ld] or [R, n, ld] (lec_rows_bwd)."""
     N.require_cuda(W, grad_rows)
     W = W.detach().contiguous().float()
     grad_rows = grad_rows.contiguous()
+    R = grad_rows.shape[0] if grad_rows.dim() == 3 else 1
     n, D = W.shape
     if out is None:
         out = torch.empty((n, D), device=W.device, dtype=torch.float32)
         accumulate = False
-    N.check(N.lib().lec_rows_bwd(N._p(W), N._p(grad_rows), n, D, grad_rows.shape[1], int(mode), float(K or 0.0),
+    N.check(N.lib().lec_rows_bwd(N._p(W), N._p(grad_rows), R, n, D, grad_rows.shape[-1], int(mode), float(K or 0.0),
                                  N._p(out), int(bool(accumulate)), N.stream_ptr(W.device)), "lec_rows_bwd")
     return out
 
@@ -98,10 +119,11 @@ def pairs_grouped_raw(geom, rows, D, pos_from, pos_to, neg_to, neg_from, n_neg, 
         E_neg = torch.empty((B, 2 * n_neg), device=dev, dtype=torch.float32)
     if loss_out is None:
         loss_out = torch.zeros(1, device=dev, dtype=torch.float64)
+    R = 1 if grad_rows is None or grad_rows.dim() == 2 else grad_rows.shape[0]
     N.check(N.lib().lec_pairs_grouped(
         GEOM[geom], int(precision), N._p(rows), rows.shape[0], int(D), rows.shape[1], N._p(pos_from), N._p(pos_to),
         N._p(neg_to), N._p(neg_from), pos_from.element_size(), B, int(n_neg), N._p(w_pos), N._p(w_neg),
-        float(K or 0.0), float(alpha), N._p(E_pos), N._p(E_neg), N._p(loss_out), N._p(grad_rows),
+        float(K or 0.0), float(alpha), N._p(E_pos), N._p(E_neg), N._p(loss_out), N._p(grad_rows), R,
         N.stream_ptr(dev)), "lec_pairs_grouped")
     return loss_out, E_pos, E_neg
 
@@ -119,9 +141,13 @@ class GroupedPairLoss(torch.autograd.Function):
         if not (pos_from.dtype == pos_to.dtype == neg_to.dtype == neg_from.dtype):
             pos_from, pos_to, neg_to, neg_from = (t.to(torch.int64) for t in (pos_from, pos_to, neg_to, neg_from))
         need_grad = ctx.needs_input_grad[0]
-        grad_rows = torch.zeros_like(rows_c) if need_grad else None
+        grad_rows = None
+        if need_grad:
+            grad_rows = torch.zeros((default_replicas(*rows_c.shape),) + tuple(rows_c.shape), device=dev)
         loss64, E_pos, E_neg = pairs_grouped_raw(geom, rows_c, D, pos_from, pos_to, neg_to, neg_from, n_neg, K, alpha,
                                                  _f32(w_pos, dev), _f32(w_neg, dev), grad_rows, None, precision)
+        if need_grad:
+            grad_rows = reduce_replicas(grad_rows)
         ctx.save_for_backward(grad_rows)
         ctx.mark_non_differentiable(E_pos, E_neg)
         return loss64[0].float(), E_pos, E_neg
@@ -146,10 +172,11 @@ def pairs_flat_raw(geom, rows, D, from_idx, to_idx, K, alpha, w=None, is_pos=Non
         E_out = torch.empty(P, device=dev, dtype=torch.float32)
     if loss_out is None:
         loss_out = torch.zeros(1, device=dev, dtype=torch.float64)
+    R = 1 if grad_rows is None or grad_rows.dim() == 2 else grad_rows.shape[0]
     N.check(N.lib().lec_pairs_flat(
         GEOM[geom], int(precision), N._p(rows), rows.shape[0], int(D), rows.shape[1], N._p(from_idx), N._p(to_idx),
         from_idx.element_size(), N._p(w), N._p(is_pos), P, float(K or 0.0), float(alpha), N._p(E_out),
-        N._p(loss_out), N._p(grad_rows), N.stream_ptr(dev)), "lec_pairs_flat")
+        N._p(loss_out), N._p(grad_rows), R, N.stream_ptr(dev)), "lec_pairs_flat")
     return loss_out, E_out
 
 
@@ -167,9 +194,13 @@ class FlatPairLoss(torch.autograd.Function):
         if is_pos is not None:
             is_pos = torch.as_tensor(is_pos).to(device=dev, dtype=torch.uint8).contiguous()
         need_grad = ctx.needs_input_grad[0]
-        grad_rows = torch.zeros_like(rows_c) if need_grad else None
+        grad_rows = None
+        if need_grad:
+            grad_rows = torch.zeros((default_replicas(*rows_c.shape),) + tuple(rows_c.shape), device=dev)
         loss64, E = pairs_flat_raw(geom, rows_c, D, from_idx, to_idx, K, alpha, _f32(w, dev), is_pos, grad_rows, None,
                                    precision)
+        if need_grad:
+            grad_rows = reduce_replicas(grad_rows)
         ctx.save_for_backward(grad_rows)
         ctx.mark_non_differentiable(E)
         return loss64[0].float(), E
@@ -228,16 +259,17 @@ def energy(x, y, geom, K=None, precision=PREC_F32):
 def rsgd_update_(table, grad, lr, r_in, textbook_lambda=False, write_rescaled_grad=True):
     """In-place Riemannian SGD step on the whole table (lec_rsgd_update).
 
-    `grad` is the Euclidean gradient [n, D] (or [n, ld] padded).  With write_rescaled_grad the gradient
+    `grad` is the Euclidean gradient [n, D] (or [n, ld] padded, or [R, n, ld] replicas).  With write_rescaled_grad the gradient
     buffer is left holding the Riemannian-rescaled gradient, as the reference leaves weight.grad."""
     N.require_cuda(table, grad)
     if not table.is_contiguous() or table.dtype != torch.float32:
         raise N.LecError("rsgd_update_: table must be a contiguous float32 tensor (updated in place)")
     n, D = table.shape
     grad = grad.contiguous()
-    ld_g = grad.shape[1]
-    grad_out = grad if (write_rescaled_grad and ld_g == D) else None
-    N.check(N.lib().lec_rsgd_update(N._p(table), N._p(grad), n, D, ld_g, float(lr), float(r_in),
+    R = grad.shape[0] if grad.dim() == 3 else 1
+    ld_g = grad.shape[-1]
+    grad_out = grad if (write_rescaled_grad and ld_g == D and R == 1) else None
+    N.check(N.lib().lec_rsgd_update(N._p(table), N._p(grad), R, n, D, ld_g, float(lr), float(r_in),
                                     1 if textbook_lambda else 0, N._p(grad_out), N.stream_ptr(table.device)),
             "lec_rsgd_update")
     return table

@@ -19,11 +19,11 @@ def header_symbols():
 def test_library_exports_every_header_symbol():
     lib = _native.lib()
     names = header_symbols()
-    assert len(names) >= 11
+    assert len(names) >= 12
     for n in names:
         assert hasattr(lib, n), n
     assert sorted(_native.EXPORTS) == names
-    assert lib.lec_abi_version() == 1
+    assert lib.lec_abi_version() == _native.ABI_VERSION == 2
 
 
 def test_argument_validation_codes():
@@ -32,22 +32,25 @@ def test_argument_validation_codes():
     fake = ctypes.c_void_p(0x1000)      # 16-byte aligned, never dereferenced: validation fails first
     odd = ctypes.c_void_p(0x1004)
     # NULL rows
-    assert lib.lec_pairs_flat(0, 0, null, 10, 4, 4, fake, fake, 8, null, null, 5, 3.0, 1.0, fake, null, null, null) == -1
+    assert lib.lec_pairs_flat(0, 0, null, 10, 4, 4, fake, fake, 8, null, null, 5, 3.0, 1.0, fake, null, null, 1, null) == -1
     # ld not a multiple of 4 / smaller than D
-    assert lib.lec_pairs_flat(0, 0, fake, 10, 4, 6, fake, fake, 8, null, null, 5, 3.0, 1.0, fake, null, null, null) == -2
-    assert lib.lec_pairs_flat(0, 0, fake, 10, 8, 4, fake, fake, 8, null, null, 5, 3.0, 1.0, fake, null, null, null) == -2
+    assert lib.lec_pairs_flat(0, 0, fake, 10, 4, 6, fake, fake, 8, null, null, 5, 3.0, 1.0, fake, null, null, 1, null) == -2
+    assert lib.lec_pairs_flat(0, 0, fake, 10, 8, 4, fake, fake, 8, null, null, 5, 3.0, 1.0, fake, null, null, 1, null) == -2
     # unknown geometry / index width
-    assert lib.lec_pairs_flat(7, 0, fake, 10, 4, 4, fake, fake, 8, null, null, 5, 3.0, 1.0, fake, null, null, null) == -3
-    assert lib.lec_pairs_flat(0, 0, fake, 10, 4, 4, fake, fake, 2, null, null, 5, 3.0, 1.0, fake, null, null, null) == -3
+    assert lib.lec_pairs_flat(7, 0, fake, 10, 4, 4, fake, fake, 8, null, null, 5, 3.0, 1.0, fake, null, null, 1, null) == -3
+    assert lib.lec_pairs_flat(0, 0, fake, 10, 4, 4, fake, fake, 2, null, null, 5, 3.0, 1.0, fake, null, null, 1, null) == -3
     # negative count, misaligned rows
-    assert lib.lec_pairs_flat(0, 0, fake, 10, 4, 4, fake, fake, 8, null, null, -1, 3.0, 1.0, fake, null, null, null) == -4
-    assert lib.lec_pairs_flat(0, 0, odd, 10, 4, 4, fake, fake, 8, null, null, 5, 3.0, 1.0, fake, null, null, null) == -5
+    assert lib.lec_pairs_flat(0, 0, fake, 10, 4, 4, fake, fake, 8, null, null, -1, 3.0, 1.0, fake, null, null, 1, null) == -4
+    assert lib.lec_pairs_flat(0, 0, odd, 10, 4, 4, fake, fake, 8, null, null, 5, 3.0, 1.0, fake, null, null, 1, null) == -5
     # empty batch is a no-op success
-    assert lib.lec_pairs_flat(0, 0, fake, 10, 4, 4, null, null, 8, null, null, 0, 3.0, 1.0, null, null, null, null) == 0
+    assert lib.lec_pairs_flat(0, 0, fake, 10, 4, 4, null, null, 8, null, null, 0, 3.0, 1.0, null, null, null, 1, null) == 0
     assert lib.lec_pairs_grouped(1, 1, fake, 10, 4, 4, null, null, null, null, 4, 0, 5, null, null, 0.1, 1.0, null,
-                                 null, null, null, null) == 0
+                                 null, null, null, 1, null) == 0
+    # gradient requested with zero replicas
+    assert lib.lec_pairs_flat(0, 0, fake, 10, 4, 4, fake, fake, 8, null, null, 5, 3.0, 1.0, fake, null, fake, 0, null) == -7
+    assert lib.lec_rows_bwd(fake, fake, 0, 5, 4, 4, 1, 3.0, fake, 0, null) == -7
     assert lib.lec_score_topk(1, 0, fake, 5, fake, 5, 10, 0.1, null, null, 4, 9, null, fake, null, null) == -6
-    assert lib.lec_rsgd_update(fake, fake, 5, 0, 0, 0.1, 0.1, 0, null, null) == -2
+    assert lib.lec_rsgd_update(fake, fake, 1, 5, 0, 0, 0.1, 0.1, 0, null, null) == -2
     assert b"16-byte" in lib.lec_error_string(-5)
 
 

@@ -180,7 +180,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    precision = args.precision if args.precision is not None else 0
+    precision = args.precision if args.precision is not None else 1
     cfg = {"workload": spec["name"], "pairs_per_gpu_per_step": pairs_per_step, "positives_per_gpu_per_step": groups,
            "dim": D, "negatives_per_edge": 2 * Nn, "table_rows": None, "update": "rsgd",
            "scalar_core": "fp64" if precision == 1 else "fp32", "index_dtype": "int32",

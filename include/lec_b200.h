@@ -16,7 +16,8 @@
  *     angle/aperture algebra in fp64, vectors and outputs fp32)
  *   - "rows" is the TRANSFORMED embedding table the energies are evaluated on: [n_rows, ld] fp32,
  *     ld a multiple of 4 (>= D), pad columns zero, base 16-byte aligned.  It is produced from the
- *     raw parameter table by lec_rows_fwd and its gradient is mapped back by lec_rows_bwd.
+ *     raw parameter table by lec_rows_fwd (together with the per-row "aux" terms) and its gradient is
+ *     mapped back by lec_rows_bwd.
  *   - index arrays are int32 or int64 (idx_bytes = 4 or 8)
  */
 #ifndef LEC_B200_H
@@ -28,7 +29,7 @@
 extern "C" {
 #endif
 
-#define LEC_ABI_VERSION 2
+#define LEC_ABI_VERSION 3
 
 /* geometry of the energy */
 #define LEC_GEOM_EUC 0 /* EucConesLoss.E_operator, order_embeddings.py:954-969 = oe.py:721-739 (cos-space) */
@@ -68,11 +69,15 @@ int64_t lec_launch_count(void);
  * table row instead of once per gathered pair endpoint.
  *   in        [n, D] raw rows (row stride D)
  *   rows_out  [n, ld] transformed rows, pad columns written as 0
+ *   aux_out   optional [n, 4] doubles (16-byte aligned): the per-row terms of energy `geom` that depend on
+ *             one endpoint only -- { |x|^2, 1/|x|, half-aperture term, its dz/dx coefficient } -- computed
+ *             in fp64 once per row so that the pair kernels never recompute them per pair.  Required by
+ *             lec_pairs_flat / lec_pairs_grouped for LEC_GEOM_EUC and LEC_GEOM_HYP.
  *   zero_out  optional [zero_replicas, n, ld] buffer cleared in the same pass (the gradient
  *             accumulator of the pair kernels), may be NULL
  */
-int lec_rows_fwd(const float* in, int64_t n, int D, int mode, float K, float* rows_out, int ld,
-                 float* zero_out, int zero_replicas, void* stream);
+int lec_rows_fwd(const float* in, int64_t n, int D, int mode, int geom, float K, float* rows_out, int ld,
+                 double* aux_out, float* zero_out, int zero_replicas, void* stream);
 
 /* Vector-Jacobian product of lec_rows_fwd: grad_in[n, D] (=|+=) J^T grad_rows[n, ld].
  * grad_rows is [grad_replicas, n, ld]; the replicas are summed on the fly.
@@ -87,6 +92,7 @@ int lec_reduce_replicas(const float* in, int replicas, int64_t count, float* out
  * Flat pair list.  Replaces E_operator + positive_pair/negative_pair + the loss sum of
  * EucConesLoss.forward / OrderEmbeddingLoss.forward (order_embeddings.py:971-975, :1029-1042 eval
  * branch, :1056-1102 train branch) for an arbitrary list of (from, to) endpoints.
+ *   rows, aux        transformed table and its per-row terms from lec_rows_fwd (aux may be NULL for OE)
  *   from_idx,to_idx  [P] row numbers into rows
  *   w                optional [P] pair weights (NULL = 1)
  *   is_pos           optional [P] uint8, 1 = positive term w*E, 0 = negative term w*max(0, alpha-E)
@@ -100,7 +106,7 @@ int lec_reduce_replicas(const float* in, int replicas, int64_t count, float* out
  *                    grad_replicas); the true gradient is their sum (lec_rows_bwd, lec_rsgd_update and
  *                    lec_reduce_replicas sum them).  grad_replicas >= 1.
  */
-int lec_pairs_flat(int geom, int precision, const float* rows, int64_t n_rows, int D, int ld,
+int lec_pairs_flat(int geom, int precision, const float* rows, const double* aux, int64_t n_rows, int D, int ld,
                    const void* from_idx, const void* to_idx, int idx_bytes, const float* w,
                    const uint8_t* is_pos, int64_t P, float K, float alpha, float* E_out,
                    double* loss_out, float* grad_rows, int grad_replicas, void* stream);
@@ -115,8 +121,8 @@ int lec_pairs_flat(int geom, int precision, const float* rows, int64_t n_rows, i
  *   E_pos [B], E_neg [B, 2N]  raw energies in the reference's order
  *   loss_out, grad_rows       as above (grad_rows required unless NULL = forward only)
  */
-int lec_pairs_grouped(int geom, int precision, const float* rows, int64_t n_rows, int D, int ld,
-                      const void* pos_from, const void* pos_to, const void* neg_to, const void* neg_from,
+int lec_pairs_grouped(int geom, int precision, const float* rows, const double* aux, int64_t n_rows, int D,
+                      int ld, const void* pos_from, const void* pos_to, const void* neg_to, const void* neg_from,
                       int idx_bytes, int64_t B, int N, const float* w_pos, const float* w_neg, float K,
                       float alpha, float* E_pos, float* E_neg, double* loss_out, float* grad_rows,
                       int grad_replicas, void* stream);

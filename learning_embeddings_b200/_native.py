@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "_lib", "liblec_b200.so")
 GEOM = {"euc": 0, "hyp": 1, "oe": 2}
 ROWS_NONE, ROWS_EUC_SOFTCLIP, ROWS_HYP_SHELL, ROWS_HYP_TANH, ROWS_HYP_TANH_FEAT = 0, 1, 2, 3, 4
 PREC_F32, PREC_F64CORE = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 EXPORTS = (
     "lec_abi_version", "lec_error_string", "lec_launch_count", "lec_rows_fwd", "lec_rows_bwd", "lec_reduce_replicas",
@@ -48,12 +48,12 @@ def lib():
         L.lec_error_string.restype = ctypes.c_char_p
         L.lec_error_string.argtypes = [c_i]
         L.lec_launch_count.restype = c_i64
-        L.lec_rows_fwd.argtypes = [c_vp, c_i64, c_i, c_i, c_f, c_vp, c_i, c_vp, c_i, c_vp]
+        L.lec_rows_fwd.argtypes = [c_vp, c_i64, c_i, c_i, c_i, c_f, c_vp, c_i, c_vp, c_vp, c_i, c_vp]
         L.lec_rows_bwd.argtypes = [c_vp, c_vp, c_i, c_i64, c_i, c_i, c_i, c_f, c_vp, c_i, c_vp]
         L.lec_reduce_replicas.argtypes = [c_vp, c_i, c_i64, c_vp, c_vp]
-        L.lec_pairs_flat.argtypes = [c_i, c_i, c_vp, c_i64, c_i, c_i, c_vp, c_vp, c_i, c_vp, c_vp, c_i64, c_f, c_f,
+        L.lec_pairs_flat.argtypes = [c_i, c_i, c_vp, c_vp, c_i64, c_i, c_i, c_vp, c_vp, c_i, c_vp, c_vp, c_i64, c_f, c_f,
                                      c_vp, c_vp, c_vp, c_i, c_vp]
-        L.lec_pairs_grouped.argtypes = [c_i, c_i, c_vp, c_i64, c_i, c_i, c_vp, c_vp, c_vp, c_vp, c_i, c_i64, c_i,
+        L.lec_pairs_grouped.argtypes = [c_i, c_i, c_vp, c_vp, c_i64, c_i, c_i, c_vp, c_vp, c_vp, c_vp, c_i, c_i64, c_i,
                                         c_vp, c_vp, c_f, c_f, c_vp, c_vp, c_vp, c_vp, c_i, c_vp]
         L.lec_energy_dense.argtypes = [c_i, c_i, c_vp, c_vp, c_i64, c_i, c_f, c_vp, c_vp]
         L.lec_energy_dense_bwd.argtypes = [c_i, c_i, c_vp, c_vp, c_vp, c_i64, c_i, c_f, c_vp, c_vp, c_vp]

@@ -33,20 +33,22 @@ class _EmbedderBase(nn.Module):
     def table(self):
         return self.embeddings.weight
 
-    def rows(self):
-        """Transformed table [n, ld] (differentiable w.r.t. the embedding weight)."""
-        return ops.transform_rows(self.embeddings.weight, self.row_mode, self.K)
+    def rows(self, geom=None):
+        """(rows [n, ld], aux): transformed table (differentiable w.r.t. the embedding weight) and the
+        per-row aperture terms of energy `geom`."""
+        return ops.transform_rows(self.embeddings.weight, self.row_mode, self.K, geom)
 
     def forward(self, inputs):
         D = self.embedding_dim
         shape = tuple(inputs.shape)
-        out = self.rows().index_select(0, inputs.reshape(-1).to(self.embeddings.weight.device))[:, :D]
+        rows, _ = self.rows()
+        out = rows.index_select(0, inputs.reshape(-1).to(self.embeddings.weight.device))[:, :D]
         return out.reshape(shape + (D,))
 
     def soft_clip(self, x):
         shp = x.shape
         x2 = x.reshape(-1, shp[-1])
-        return ops.transform_rows(x2, self.row_mode, self.K)[:, :shp[-1]].reshape(shp)
+        return ops.transform_rows(x2, self.row_mode, self.K)[0][:, :shp[-1]].reshape(shp)
 
 
 class EuclideanEmbedder(_EmbedderBase):
@@ -123,7 +125,7 @@ class _PairCriterion(nn.Module):
     """Shared machinery of OrderEmbeddingLoss / EucConesLoss (Euclidean and hyperbolic)."""
 
     geom = None
-    precision = ops.PREC_F32
+    precision = ops.PREC_F64CORE  # strict parity by default; PREC_F32 is the fast mode
 
     def _common_init(self, labelmap, neg_to_pos_ratio, alpha, pick_per_level, weigh_neg_term, level_weights,
                      weigh_pos_term):
@@ -227,7 +229,10 @@ class _PairCriterion(nn.Module):
             raise N.LecError("model must live on a CUDA device (got %s)" % dev)
         D = m.embedding_dim
         K = getattr(self, "K", None)
-        rows = m.rows() if hasattr(m, "rows") else ops.transform_rows(m.embeddings.weight, self.default_row_mode, K)
+        if hasattr(m, "rows"):
+            rows, aux = m.rows(self.geom)
+        else:
+            rows, aux = ops.transform_rows(m.embeddings.weight, self.default_row_mode, K, self.geom)
         frm = torch.as_tensor(np.asarray(inputs_from, dtype=np.int64))
         to = torch.as_tensor(np.asarray(inputs_to, dtype=np.int64))
         frm_d, to_d = frm.to(dev, non_blocking=True), to.to(dev, non_blocking=True)
@@ -235,7 +240,7 @@ class _PairCriterion(nn.Module):
         to_emb = rows.index_select(0, to_d)[:, :D]
 
         if phase != "train":  # order_embeddings.py:1029-1042
-            loss, E = ops.flat_pair_loss(rows, D, frm_d, to_d, self.geom, K, self.alpha,
+            loss, E = ops.flat_pair_loss(rows, aux, D, frm_d, to_d, self.geom, K, self.alpha,
                                          is_pos=(status == 1), precision=self.precision)
             st = status.to(dev)
             return from_emb, to_emb, loss, E[st == 1], E[st == 0]
@@ -250,7 +255,7 @@ class _PairCriterion(nn.Module):
         self.last_negatives = (nf.reshape(-1), nt.reshape(-1))
         w_pos, w_neg = self._weights(inputs_to, nf.reshape(-1), nt.reshape(-1))
         loss, E_pos, E_neg = ops.grouped_pair_loss(
-            rows, D, frm_d, to_d, torch.from_numpy(neg_to).to(dev, non_blocking=True),
+            rows, aux, D, frm_d, to_d, torch.from_numpy(neg_to).to(dev, non_blocking=True),
             torch.from_numpy(neg_from).to(dev, non_blocking=True), Nn, self.geom, K, self.alpha,
             w_pos=w_pos, w_neg=w_neg, precision=self.precision)
         return from_emb, to_emb, loss, E_pos, E_neg.reshape(-1)

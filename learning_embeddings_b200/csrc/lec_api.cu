@@ -17,7 +17,7 @@ int launch_dense_hyp32(const DenseArgs&, bool, cudaStream_t);
 int launch_dense_hyp64(const DenseArgs&, bool, cudaStream_t);
 int launch_dense_oe32(const DenseArgs&, bool, cudaStream_t);
 
-int rows_fwd_launch(const float*, int64_t, int, int, float, float*, int, float*, int, cudaStream_t);
+int rows_fwd_launch(const float*, int64_t, int, int, int, float, float*, int, double*, float*, int, cudaStream_t);
 int rows_bwd_launch(const float*, const float*, int, int64_t, int, int, int, float, float*, int, cudaStream_t);
 int rsgd_launch(float*, const float*, int, int64_t, int, int, float, float, int, float*, cudaStream_t);
 int reduce_replicas_launch(const float*, int, int64_t, float*, cudaStream_t);
@@ -65,14 +65,16 @@ const char* lec_error_string(int code) {
     return "unknown lec error";
 }
 
-int lec_rows_fwd(const float* in, int64_t n, int D, int mode, float K, float* rows_out, int ld, float* zero_out,
-                 int zero_replicas, void* stream) {
+int lec_rows_fwd(const float* in, int64_t n, int D, int mode, int geom, float K, float* rows_out, int ld,
+                 double* aux_out, float* zero_out, int zero_replicas, void* stream) {
     if (zero_out && zero_replicas < 1) return LEC_E_REPLICAS;
+    if (aux_out && (geom < LEC_GEOM_EUC || geom > LEC_GEOM_OE)) return LEC_E_ENUM;
+    if (aux_out && (reinterpret_cast<uintptr_t>(aux_out) & 15)) return LEC_E_ALIGN;
     if (!in || !rows_out) return LEC_E_NULL;
     if (n < 0) return LEC_E_SIZE;
     if (mode < LEC_ROWS_NONE || mode > LEC_ROWS_HYP_TANH_FEAT) return LEC_E_ENUM;
     if (int e = check_rows(rows_out, D, ld)) return e;
-    return rows_fwd_launch(in, n, D, mode, K, rows_out, ld, zero_out, zero_replicas, (cudaStream_t)stream);
+    return rows_fwd_launch(in, n, D, mode, geom, K, rows_out, ld, aux_out, zero_out, zero_replicas, (cudaStream_t)stream);
 }
 
 int lec_rows_bwd(const float* in, const float* grad_rows, int grad_replicas, int64_t n, int D, int ld, int mode, float K,
@@ -92,7 +94,7 @@ int lec_reduce_replicas(const float* in, int replicas, int64_t count, float* out
     return reduce_replicas_launch(in, replicas, count, out, (cudaStream_t)stream);
 }
 
-int lec_pairs_flat(int geom, int precision, const float* rows, int64_t n_rows, int D, int ld, const void* from_idx,
+int lec_pairs_flat(int geom, int precision, const float* rows, const double* aux, int64_t n_rows, int D, int ld, const void* from_idx,
                    const void* to_idx, int idx_bytes, const float* w, const uint8_t* is_pos, int64_t P, float K,
                    float alpha, float* E_out, double* loss_out, float* grad_rows, int grad_replicas, void* stream) {
     const int core = pick_core(geom, precision);
@@ -103,7 +105,9 @@ int lec_pairs_flat(int geom, int precision, const float* rows, int64_t n_rows, i
     if (grad_rows && grad_replicas < 1) return LEC_E_REPLICAS;
     if (P == 0) return 0;
     if (!from_idx || !to_idx || !E_out) return LEC_E_NULL;
-    FlatArgs a{rows, ld, from_idx, to_idx, idx_bytes, w, is_pos, P, K, alpha, E_out, loss_out, grad_rows,
+    if (geom != LEC_GEOM_OE && !aux) return LEC_E_NULL;
+    if (aux && (reinterpret_cast<uintptr_t>(aux) & 15)) return LEC_E_ALIGN;
+    FlatArgs a{rows, aux, ld, from_idx, to_idx, idx_bytes, w, is_pos, P, K, alpha, E_out, loss_out, grad_rows,
                grad_replicas, n_rows * (int64_t)ld};
     cudaStream_t st = (cudaStream_t)stream;
     switch (core) {
@@ -114,7 +118,7 @@ int lec_pairs_flat(int geom, int precision, const float* rows, int64_t n_rows, i
     }
 }
 
-int lec_pairs_grouped(int geom, int precision, const float* rows, int64_t n_rows, int D, int ld, const void* pos_from,
+int lec_pairs_grouped(int geom, int precision, const float* rows, const double* aux, int64_t n_rows, int D, int ld, const void* pos_from,
                       const void* pos_to, const void* neg_to, const void* neg_from, int idx_bytes, int64_t B, int N,
                       const float* w_pos, const float* w_neg, float K, float alpha, float* E_pos, float* E_neg,
                       double* loss_out, float* grad_rows, int grad_replicas, void* stream) {
@@ -127,7 +131,9 @@ int lec_pairs_grouped(int geom, int precision, const float* rows, int64_t n_rows
     if (B == 0) return 0;
     if (!pos_from || !pos_to || !E_pos) return LEC_E_NULL;
     if (N > 0 && (!neg_to || !neg_from || !E_neg)) return LEC_E_NULL;
-    GroupArgs a{rows, ld, pos_from, pos_to, neg_to, neg_from, idx_bytes, B, N, w_pos, w_neg, K, alpha,
+    if (geom != LEC_GEOM_OE && !aux) return LEC_E_NULL;
+    if (aux && (reinterpret_cast<uintptr_t>(aux) & 15)) return LEC_E_ALIGN;
+    GroupArgs a{rows, aux, ld, pos_from, pos_to, neg_to, neg_from, idx_bytes, B, N, w_pos, w_neg, K, alpha,
                 E_pos, E_neg, loss_out, grad_rows, grad_replicas, n_rows * (int64_t)ld};
     cudaStream_t st = (cudaStream_t)stream;
     switch (core) {

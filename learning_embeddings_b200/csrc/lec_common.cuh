@@ -64,6 +64,23 @@ __device__ __forceinline__ S dot_part(const Vec<V>& a, const Vec<V>& b) {
     return s;
 }
 
+// <a, b> to double accuracy without double copies of the operands: each fp32 product is split exactly
+// into hi + lo (lo via FMA); hi parts are summed in double, lo parts (2^-24 smaller) in fp32.
+template <int V>
+__device__ __forceinline__ double dot_exact_part(const Vec<V>& a, const Vec<V>& b) {
+    double s = 0.0;
+    float lo = 0.f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        float h;
+        h = __fmul_rn(a.c[j].x, b.c[j].x); lo += __fmaf_rn(a.c[j].x, b.c[j].x, -h); s += (double)h;
+        h = __fmul_rn(a.c[j].y, b.c[j].y); lo += __fmaf_rn(a.c[j].y, b.c[j].y, -h); s += (double)h;
+        h = __fmul_rn(a.c[j].z, b.c[j].z); lo += __fmaf_rn(a.c[j].z, b.c[j].z, -h); s += (double)h;
+        h = __fmul_rn(a.c[j].w, b.c[j].w); lo += __fmaf_rn(a.c[j].w, b.c[j].w, -h); s += (double)h;
+    }
+    return s + (double)lo;
+}
+
 // sum (a-b)^2; the subtraction is done in the accumulator type (fp32: exactly what torch.norm(x - y)
 // sees in the reference's fp32 run; fp64: exact difference of the fp32 inputs)
 template <typename S, int V>
@@ -124,86 +141,142 @@ template <typename S>
 __device__ __forceinline__ S relu_nan(S v) { return v < (S)0 ? (S)0 : v; }
 
 // ------------------------------------------------------------------------------------------------
-// Per-pair scalar cores.  Input: team-reduced dot products.  Output: raw z (energy before the outer
-// max(0,.)), and the four coefficients of dz/dx = zxx*x + zxy*y, dz/dy = zyx*x + zyy*y.
+// Scalar cores.
+//
+// Everything that depends on ONE endpoint only (its squared norm, 1/norm, the half-aperture psi(x) and
+// the aperture's contribution to dz/dx) is computed once per table row by lec_rows_fwd and stored as
+// four doubles per row ("aux"); the per-pair cores below only do the genuinely pairwise algebra.
+//   hyperbolic: aux = { |x|^2, 1/|x|, psi(x) = asin(clamp(K(1-|x|^2)/|x|)), -psi'(h) * dh/d|x|^2 * 2 }
+//   Euclidean : aux = { |x|^2, 1/max(|x|,1e-12), sqrt(1 - K^2/|x|^2), K^2 / (|x|^4 sqrt(1 - K^2/|x|^2)) }
+// Output of a pair core: raw z (energy before the outer max(0,.)), and the four coefficients of
+// dz/dx = zxx*x + zxy*y, dz/dy = zyx*x + zyy*y.
 // ------------------------------------------------------------------------------------------------
 struct PairGrad {
     float z;
     float zxx, zxy, zyx, zyy;
 };
 
+template <typename S>
+struct Aux {
+    S A, ria, t0, t1;
+};
+
 template <typename S> __device__ __forceinline__ S s_sqrt(S v);
-// a*b - c*d with both products rounded before the subtraction (no FMA contraction), so that the
-// numerator of the hyperbolic angle is exactly 0 when x == y, as in the reference (0/0 -> NaN)
+template <> __device__ __forceinline__ float s_sqrt<float>(float v) { return sqrtf(v); }
+template <> __device__ __forceinline__ double s_sqrt<double>(double v) { return sqrt(v); }
+template <typename S> __device__ __forceinline__ S s_rsqrt(S v);
+template <> __device__ __forceinline__ float s_rsqrt<float>(float v) { return rsqrtf(v); }
+template <> __device__ __forceinline__ double s_rsqrt<double>(double v) { return rsqrt(v); }
+template <typename S> __device__ __forceinline__ S s_asin(S v);
+template <> __device__ __forceinline__ float s_asin<float>(float v) { return asinf(v); }
+template <> __device__ __forceinline__ double s_asin<double>(double v) { return asin(v); }
+
+// a*b - c*d with both products rounded before the subtraction (no FMA contraction)
 __device__ __forceinline__ float diff_of_products(float a, float b, float c, float d) {
     return __fsub_rn(__fmul_rn(a, b), __fmul_rn(c, d));
 }
 __device__ __forceinline__ double diff_of_products(double a, double b, double c, double d) {
     return __dsub_rn(__dmul_rn(a, b), __dmul_rn(c, d));
 }
-template <> __device__ __forceinline__ float s_sqrt<float>(float v) { return sqrtf(v); }
-template <> __device__ __forceinline__ double s_sqrt<double>(double v) { return sqrt(v); }
 
-// Euclidean cone, cos-space (order_embeddings.py:954-969).  A=<x,x>, DD=<d,d>, XD=<x,d>, d=y-x.
+template <typename S>
+__device__ __forceinline__ S clamp_eps(S v, bool& inside) {
+    const S lo = (S)(-1.0 + 1e-5), hi = (S)(1.0 - 1e-5);
+    inside = (v >= lo && v <= hi);               // torch.clamp passes the gradient on the closed interval
+    return v < lo ? lo : (v > hi ? hi : v);      // NaN falls through unchanged, like torch.clamp
+}
+
+// per-row terms from A = |x|^2 (geom: LEC_GEOM_*)
+template <typename S>
+__device__ __forceinline__ Aux<S> row_aux(int geom, S A, float Kf) {
+    Aux<S> o;
+    const S K = (S)Kf, one = (S)1;
+    o.A = A;
+    if (geom == LEC_GEOM_HYP) {
+        const S a = s_sqrt<S>(A);
+        o.ria = one / a;
+        bool in;
+        const S hc = clamp_eps<S>(K * (one - A) / a, in);  // order_embeddings_h.py:1114
+        o.t0 = s_asin<S>(hc);
+        const S h_A = -K * (one + A) / ((S)2 * a * A);
+        o.t1 = in ? -(one / s_sqrt<S>((one - hc) * (one + hc))) * h_A * (S)2 : (S)0;
+    } else if (geom == LEC_GEOM_EUC) {
+        const S a = s_sqrt<S>(A);
+        o.ria = one / (a > (S)kNormEps ? a : (S)kNormEps);
+        const S root = s_sqrt<S>(one - K * K / A);           // order_embeddings.py:967 (NaN when |x| < K)
+        o.t0 = root;
+        o.t1 = K * K / (A * A * root);
+    } else {
+        o.ria = o.t0 = o.t1 = (S)0;
+    }
+    return o;
+}
+
+template <typename S>
+__device__ __forceinline__ Aux<S> load_aux(const double* __restrict__ aux, int64_t row) {
+    const double2 p0 = __ldg(reinterpret_cast<const double2*>(aux + 4 * row));
+    const double2 p1 = __ldg(reinterpret_cast<const double2*>(aux + 4 * row) + 1);
+    Aux<S> o;
+    o.A = (S)p0.x; o.ria = (S)p0.y; o.t0 = (S)p1.x; o.t1 = (S)p1.y;
+    return o;
+}
+template <typename S>
+__device__ __forceinline__ S load_aux_A(const double* __restrict__ aux, int64_t row) {
+    return (S)__ldg(aux + 4 * row);
+}
+
+// Euclidean cone, cos-space (order_embeddings.py:954-969).  x = apex with aux ax; DD=<d,d>, XD=<x,d>, d=y-x.
 template <typename S, bool GRAD>
-__device__ __forceinline__ void euc_core(S A, S DD, S XD, float K, PairGrad& o) {
-    const S a = s_sqrt<S>(A), b = s_sqrt<S>(DD);
-    const S an = a > (S)kNormEps ? a : (S)kNormEps;
-    const S bn = b > (S)kNormEps ? b : (S)kNormEps;
-    const S inv_ab = (S)1 / (an * bn);
+__device__ __forceinline__ void euc_pair(const Aux<S>& ax, S DD, S XD, PairGrad& o) {
+    const S b = s_sqrt<S>(DD);
+    const S rb = (S)1 / (b > (S)kNormEps ? b : (S)kNormEps);
+    const S inv_ab = ax.ria * rb;
     const S c = XD * inv_ab;
-    const S K2 = (S)K * (S)K;
-    const S root = s_sqrt<S>((S)1 - K2 / A);
-    o.z = (float)(root - c);
+    o.z = (float)(ax.t0 - c);
     if (GRAD) {
-        const S inv_a2 = (S)1 / (an * an), inv_b2 = (S)1 / (bn * bn);
-        const S kt = K2 / (A * A * root);
-        const S m = -inv_ab - c * inv_b2;  // coefficient of x in dz/dy (and of y in dz/dx)
+        const S c_b2 = c * rb * rb;
+        const S m = -inv_ab - c_b2;  // coefficient of x in dz/dy (and of y in dz/dx)
         o.zyx = (float)m;
-        o.zyy = (float)(c * inv_b2);
+        o.zyy = (float)c_b2;
         o.zxy = (float)m;
-        o.zxx = (float)((S)2 * inv_ab + c * inv_a2 + c * inv_b2 + kt);
+        o.zxx = (float)((S)2 * inv_ab + c * ax.ria * ax.ria + c_b2 + ax.t1);
     }
 }
 
-// Poincare cone (order_embeddings_h.py:1097-1120).  A=<x,x>, B=<y,y>, P=<x,y>, S2=|x-y|^2.
+// Poincare cone (order_embeddings_h.py:1097-1120).  x = apex with aux ax; B=<y,y>, P=<x,y>, S2=|x-y|^2.
+// One reciprocal square root of A*S2*w2 yields 1/den and, by multiplication, 1/w2 and 1/S2.
 template <typename S, bool GRAD>
-__device__ __forceinline__ void hyp_core(S A, S B, S P, S S2, float K, PairGrad& o) {
+__device__ __forceinline__ void hyp_pair(const Aux<S>& ax, S B, S P, S S2, PairGrad& o) {
     const S one = (S)1;
-    const S lo = (S)(-1.0 + 1e-5), hi = (S)(1.0 - 1e-5);
-    const S a = s_sqrt<S>(A);
+    const S A = ax.A;
     const S w2 = one + A * B - (S)2 * P;
-    const S den = a * s_sqrt<S>(S2) * s_sqrt<S>(w2);
-    const S inv_den = one / den;
-    const S g = diff_of_products(P, one + A, A, one + B) * inv_den;
-    const S h = (S)K * (one - A) / a;
-    const S gc = g < lo ? lo : (g > hi ? hi : g);  // NaN falls through unchanged, like torch.clamp
-    const S hc = h < lo ? lo : (h > hi ? hi : h);
-    const S sg = s_sqrt<S>((one - gc) * (one + gc));
-    const S sh = s_sqrt<S>((one - hc) * (one + hc));
-    float theta, psi;
-    if (sizeof(S) == 8) {
-        // fp64 core: angle from (cos, sin) both known to double accuracy
-        theta = atan2f((float)sg, (float)gc);
-        psi = atan2f((float)hc, (float)sh);
-    } else {
-        theta = acosf((float)gc);
-        psi = asinf((float)hc);
-    }
-    o.z = theta - psi;
+    const S AS = A * S2;
+    const S rden = s_rsqrt<S>(AS * w2);
+    // identical endpoints: the reference evaluates 0/0 here (NaN up to the rounding of its norms); we
+    // return NaN deterministically.  A zero apex row gives 0 * inf = NaN by itself.
+    const S g = (S2 == (S)0) ? (S)NAN : diff_of_products(P, one + A, A, one + B) * rden;
+    bool in;
+    const S gc = clamp_eps<S>(g, in);
+    const S tg = (one - gc) * (one + gc);
+    const S rsg = s_rsqrt<S>(tg);
+    float theta;
+    if (sizeof(S) == 8) theta = atan2f((float)(tg * rsg), (float)gc);  // angle from (sin, cos), both accurate
+    else theta = acosf((float)gc);
+    o.z = theta - (float)ax.t0;
     if (GRAD) {
-        const S th = (g >= lo && g <= hi) ? -one / sg : (S)0;  // d acos(clamp(g))
-        const S ps = (h >= lo && h <= hi) ? one / sh : (S)0;   // d asin(clamp(h))
-        const S inv_w2 = one / w2;
-        const S g_p = (one + A) * inv_den + g * inv_w2;
-        const S g_A = (P - one - B) * inv_den - g * ((S)0.5 / A + (S)0.5 * B * inv_w2);
-        const S g_B = -A * inv_den - g * (S)0.5 * A * inv_w2;
-        const S gs_over_s = -g / S2;  // (dg/ds)/s
-        const S h_A = -(S)K * (one + A) / ((S)2 * a * A);
-        o.zxx = (float)(th * ((S)2 * g_A + gs_over_s) - ps * h_A * (S)2);
-        o.zxy = (float)(th * (g_p - gs_over_s));
-        o.zyx = (float)(th * (g_p - gs_over_s));
-        o.zyy = (float)(th * ((S)2 * g_B + gs_over_s));
+        const S th = in ? -rsg : (S)0;  // d acos(clamp(g)) / dg
+        const S rden2 = rden * rden;
+        const S inv_w2 = rden2 * AS;
+        const S inv_S2 = rden2 * A * w2;
+        const S g_p = (one + A) * rden + g * inv_w2;
+        const S g_A2 = (S)2 * (P - one - B) * rden - g * (ax.ria * ax.ria + B * inv_w2);  // 2 * dg/dA
+        const S g_B2 = (S)-2 * A * rden - g * A * inv_w2;                                 // 2 * dg/dB
+        const S gs = -g * inv_S2;                                                          // (dg/ds)/s
+        const S cross = th * (g_p - gs);
+        o.zxx = (float)(th * (g_A2 + gs) + ax.t1);
+        o.zxy = (float)cross;
+        o.zyx = (float)cross;
+        o.zyy = (float)(th * (g_B2 + gs));
     }
 }
 

@@ -9,13 +9,13 @@ namespace lec {
 enum Core { CORE_EUC32 = 0, CORE_HYP32 = 1, CORE_HYP64 = 2, CORE_OE32 = 3 };
 
 template <int CORE> struct CoreTraits;
-template <> struct CoreTraits<CORE_EUC32> { using Acc = float;  static constexpr bool ax = true,  ay = false, oe = false; };
-template <> struct CoreTraits<CORE_HYP32> { using Acc = float;  static constexpr bool ax = true,  ay = true,  oe = false; };
-template <> struct CoreTraits<CORE_HYP64> { using Acc = double; static constexpr bool ax = true,  ay = true,  oe = false; };
-template <> struct CoreTraits<CORE_OE32>  { using Acc = float;  static constexpr bool ax = false, ay = false, oe = true;  };
+template <> struct CoreTraits<CORE_EUC32> { using Acc = float;  static constexpr bool cone = true,  hyp = false; static constexpr int geom = LEC_GEOM_EUC; };
+template <> struct CoreTraits<CORE_HYP32> { using Acc = float;  static constexpr bool cone = true,  hyp = true;  static constexpr int geom = LEC_GEOM_HYP; };
+template <> struct CoreTraits<CORE_HYP64> { using Acc = double; static constexpr bool cone = true,  hyp = true;  static constexpr int geom = LEC_GEOM_HYP; };
+template <> struct CoreTraits<CORE_OE32>  { using Acc = float;  static constexpr bool cone = false, hyp = false; static constexpr int geom = LEC_GEOM_OE; };
 
 struct FlatArgs {
-    const float* rows; int ld;
+    const float* rows; const double* aux; int ld;
     const void* from_idx; const void* to_idx; int idx_bytes;
     const float* w; const uint8_t* is_pos;
     int64_t P; float K, alpha;
@@ -23,7 +23,7 @@ struct FlatArgs {
 };
 
 struct GroupArgs {
-    const float* rows; int ld;
+    const float* rows; const double* aux; int ld;
     const void* pos_from; const void* pos_to; const void* neg_to; const void* neg_from; int idx_bytes;
     int64_t B; int N;
     const float* w_pos; const float* w_neg;
@@ -42,30 +42,36 @@ __device__ __forceinline__ int64_t ld_index(const void* p, int64_t i, int idx_by
                           : (int64_t)__ldg(reinterpret_cast<const long long*>(p) + i);
 }
 
-// z and (optionally) dz/dx, dz/dy coefficients of one pair held by a team.  AX=<x,x>, AY=<y,y> are
-// passed in when the caller already has them (they are per-row, not per-pair).
+// z and (optionally) the dz/dx, dz/dy coefficients of one pair held by a team.
+//   ax : per-row terms of the apex x;  By : |y|^2 (hyperbolic only)
 template <int CORE, int T, int V, bool GRAD>
-__device__ __forceinline__ void eval_pair(const Vec<V>& X, const Vec<V>& Y, typename CoreTraits<CORE>::Acc AX,
-                                          typename CoreTraits<CORE>::Acc AY, float K, PairGrad& o) {
+__device__ __forceinline__ void eval_pair(const Vec<V>& X, const Vec<V>& Y,
+                                          const Aux<typename CoreTraits<CORE>::Acc>& ax,
+                                          typename CoreTraits<CORE>::Acc By, PairGrad& o) {
     using Acc = typename CoreTraits<CORE>::Acc;
     if (CORE == CORE_EUC32) {
         const Acc DD = team_sum<T, Acc>(dist2_part<Acc, V>(Y, X));
         const Acc XD = team_sum<T, Acc>(dot_diff_part<Acc, V>(X, Y));
-        euc_core<Acc, GRAD>(AX, DD, XD, K, o);
-    } else if (CORE == CORE_HYP32 || CORE == CORE_HYP64) {
+        euc_pair<Acc, GRAD>(ax, DD, XD, o);
+    } else if (CORE == CORE_HYP32) {
         const Acc P = team_sum<T, Acc>(dot_part<Acc, V>(X, Y));
         const Acc S2 = team_sum<T, Acc>(dist2_part<Acc, V>(X, Y));
-        hyp_core<Acc, GRAD>(AX, AY, P, S2, K, o);
+        hyp_pair<Acc, GRAD>(ax, By, P, S2, o);
+    } else if (CORE == CORE_HYP64) {
+        const double P = team_sum<T, double>(dot_exact_part<V>(X, Y));
+        // |x-y|^2 = |x|^2 + |y|^2 - 2<x,y> is accurate to ~2^-52 (|x|^2+|y|^2)/|x-y|^2 in double; only for
+        // nearly coincident points fall back to summing the squared differences directly.
+        double S2 = (double)ax.A + (double)By - 2.0 * P;
+        const bool close = S2 < 1e-6 * ((double)ax.A + (double)By);
+        if (__any_sync(0xffffffffu, close)) {
+            const double direct = team_sum<T, double>(dist2_part<double, V>(X, Y));
+            if (close) S2 = direct;
+        }
+        hyp_pair<Acc, GRAD>(ax, By, (Acc)P, (Acc)S2, o);
     } else {
         o.z = (float)team_sum<T, Acc>(relu_diff2_part<Acc, V>(X, Y));
         o.zxx = o.zxy = o.zyx = o.zyy = 0.f;
     }
-}
-
-template <int CORE, int T, int V>
-__device__ __forceinline__ typename CoreTraits<CORE>::Acc row_norm2(const Vec<V>& X) {
-    using Acc = typename CoreTraits<CORE>::Acc;
-    return team_sum<T, Acc>(dot_part<Acc, V>(X, X));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -91,11 +97,12 @@ __global__ void __launch_bounds__(kThreads) pairs_flat_kernel(const FlatArgs a) 
         Vec<V> X, Y;
         load_row<T, V>(X, a.rows, ix, a.ld, lane_t);
         load_row<T, V>(Y, a.rows, iy, a.ld, lane_t);
-        Acc AX = 0, AY = 0;
-        if (Tr::ax) AX = row_norm2<CORE, T, V>(X);
-        if (Tr::ay) AY = row_norm2<CORE, T, V>(Y);
+        Aux<Acc> ax{};
+        Acc By = 0;
+        if (Tr::cone) ax = load_aux<Acc>(a.aux, ix);
+        if (Tr::hyp) By = load_aux_A<Acc>(a.aux, iy);
         PairGrad g;
-        eval_pair<CORE, T, V, GRAD>(X, Y, AX, AY, a.K, g);
+        eval_pair<CORE, T, V, GRAD>(X, Y, ax, By, g);
         const float w = a.w ? __ldg(a.w + pc) : 1.f;
         const bool pos = a.is_pos ? (__ldg(a.is_pos + pc) != 0) : true;
         float E;
@@ -112,7 +119,7 @@ __global__ void __launch_bounds__(kThreads) pairs_flat_kernel(const FlatArgs a) 
             for (int j = 0; j < V; ++j) {
                 const int q = lane_t + T * j;
                 if (q < Q) {
-                    if (Tr::oe) {
+                    if (!Tr::cone) {
                         const float4 r = relu_diff4(X.c[j], Y.c[j]);
                         const float c2 = 2.f * cf;
                         red_add4(gx + 4 * q, make_float4(c2 * r.x, c2 * r.y, c2 * r.z, c2 * r.w));
@@ -155,11 +162,10 @@ __global__ void __launch_bounds__(kThreads) pairs_grouped_kernel(const GroupArgs
         Vec<V> U, W;
         load_row<T, V>(U, a.rows, iu, a.ld, lane_t);
         load_row<T, V>(W, a.rows, iv, a.ld, lane_t);
-        Acc AU = 0, AW = 0;
-        if (Tr::ax || Tr::ay) {
-            AU = row_norm2<CORE, T, V>(U);
-            AW = row_norm2<CORE, T, V>(W);
-        }
+        Aux<Acc> au{};
+        Acc AW = 0;
+        if (Tr::cone) au = load_aux<Acc>(a.aux, iu);
+        if (Tr::hyp) AW = load_aux_A<Acc>(a.aux, iv);
         float su_u = 0.f, su_w = 0.f, sw_u = 0.f, sw_w = 0.f;
         Vec<V> accU, accW;
 #pragma unroll
@@ -171,13 +177,13 @@ __global__ void __launch_bounds__(kThreads) pairs_grouped_kernel(const GroupArgs
         double l = 0.0;
         // positive (x = u, y = v)
         {
-            eval_pair<CORE, T, V, GRAD>(U, W, AU, AW, a.K, g);
+            eval_pair<CORE, T, V, GRAD>(U, W, au, AW, g);
             const float w = a.w_pos ? __ldg(a.w_pos + gc) : 1.f;
             const float cf = hinge(g.z, true, w, a.alpha, E, l);
             if (writer) a.E_pos[gidx] = E;
             if (GRAD && cf != 0.f) {
                 touch_u = touch_w = true;
-                if (Tr::oe) {
+                if (!Tr::cone) {
 #pragma unroll
                     for (int j = 0; j < V; ++j) {
                         const float4 r = relu_diff4(U.c[j], W.c[j]);
@@ -197,19 +203,19 @@ __global__ void __launch_bounds__(kThreads) pairs_grouped_kernel(const GroupArgs
             Vec<V> C;
             load_row<T, V>(C, a.rows, ic, a.ld, lane_t);
             Acc AC = 0;
-            if (Tr::ay) AC = row_norm2<CORE, T, V>(C);
-            eval_pair<CORE, T, V, GRAD>(U, C, AU, AC, a.K, g);
+            if (Tr::hyp) AC = load_aux_A<Acc>(a.aux, ic);
+            eval_pair<CORE, T, V, GRAD>(U, C, au, AC, g);
             const float w = a.w_neg ? __ldg(a.w_neg + ebase + p) : 1.f;
             const float cf = hinge(g.z, false, w, a.alpha, E, l);
             if (writer) a.E_neg[ebase + p] = E;
             if (GRAD && valid && cf != 0.f) {
                 touch_u = true;
                 float* gcp = grad_base + ic * (int64_t)a.ld;
-                if (!Tr::oe) su_u += cf * g.zxx;
+                if (Tr::cone) su_u += cf * g.zxx;
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
                     const int q = lane_t + T * j;
-                    if (Tr::oe) {
+                    if (!Tr::cone) {
                         const float4 r = relu_diff4(U.c[j], C.c[j]);
                         const float c2 = 2.f * cf;
                         fma4(accU.c[j], c2, r);
@@ -226,20 +232,20 @@ __global__ void __launch_bounds__(kThreads) pairs_grouped_kernel(const GroupArgs
             const int64_t ic = ld_index(a.neg_from, nbase + p, a.idx_bytes);
             Vec<V> C;
             load_row<T, V>(C, a.rows, ic, a.ld, lane_t);
-            Acc AC = 0;
-            if (Tr::ax) AC = row_norm2<CORE, T, V>(C);
-            eval_pair<CORE, T, V, GRAD>(C, W, AC, AW, a.K, g);
+            Aux<Acc> ac{};
+            if (Tr::cone) ac = load_aux<Acc>(a.aux, ic);
+            eval_pair<CORE, T, V, GRAD>(C, W, ac, AW, g);
             const float w = a.w_neg ? __ldg(a.w_neg + ebase + N + p) : 1.f;
             const float cf = hinge(g.z, false, w, a.alpha, E, l);
             if (writer) a.E_neg[ebase + N + p] = E;
             if (GRAD && valid && cf != 0.f) {
                 touch_w = true;
                 float* gcp = grad_base + ic * (int64_t)a.ld;
-                if (!Tr::oe) sw_w += cf * g.zyy;
+                if (Tr::cone) sw_w += cf * g.zyy;
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
                     const int q = lane_t + T * j;
-                    if (Tr::oe) {
+                    if (!Tr::cone) {
                         const float4 r = relu_diff4(C.c[j], W.c[j]);
                         const float c2 = 2.f * cf;
                         fma4(accW.c[j], -c2, r);
@@ -261,12 +267,12 @@ __global__ void __launch_bounds__(kThreads) pairs_grouped_kernel(const GroupArgs
                 if (q < Q) {
                     if (touch_u) {
                         float4 v = accU.c[j];
-                        if (!Tr::oe) { fma4(v, su_u, U.c[j]); fma4(v, su_w, W.c[j]); }
+                        if (Tr::cone) { fma4(v, su_u, U.c[j]); fma4(v, su_w, W.c[j]); }
                         red_add4(gu + 4 * q, v);
                     }
                     if (touch_w) {
                         float4 v = accW.c[j];
-                        if (!Tr::oe) { fma4(v, sw_u, U.c[j]); fma4(v, sw_w, W.c[j]); }
+                        if (Tr::cone) { fma4(v, sw_u, U.c[j]); fma4(v, sw_w, W.c[j]); }
                         red_add4(gw + 4 * q, v);
                     }
                 }
@@ -277,7 +283,7 @@ __global__ void __launch_bounds__(kThreads) pairs_grouped_kernel(const GroupArgs
 }
 
 // ------------------------------------------------------------------------------------------------
-// Dense operands x, y [P, D] (row stride D): one thread per pair.
+// Dense operands x, y [P, D] (row stride D): one thread per pair, per-row terms computed in line.
 // ------------------------------------------------------------------------------------------------
 template <int CORE, bool BWD>
 __global__ void __launch_bounds__(kThreads) energy_dense_kernel(const DenseArgs a) {
@@ -291,20 +297,21 @@ __global__ void __launch_bounds__(kThreads) energy_dense_kernel(const DenseArgs 
         for (int d = 0; d < a.D; ++d) {
             const float xv = __ldg(x + d), yv = __ldg(y + d);
             if (CORE == CORE_EUC32) {
-                const float dv = yv - xv;
-                s0 += (Acc)xv * (Acc)xv; s1 += (Acc)dv * (Acc)dv; s2 += (Acc)xv * (Acc)dv;
+                const Acc dv = (Acc)yv - (Acc)xv;
+                s0 += (Acc)xv * (Acc)xv; s1 += dv * dv; s2 += (Acc)xv * dv;
             } else if (CORE == CORE_OE32) {
                 const float r = fmaxf(xv - yv, 0.f);
                 s0 += (Acc)r * (Acc)r;
             } else {
-                const float dv = xv - yv;
-                s0 += (Acc)xv * (Acc)xv; s1 += (Acc)yv * (Acc)yv; s2 += (Acc)xv * (Acc)yv; s3 += (Acc)dv * (Acc)dv;
+                const Acc dv = (Acc)xv - (Acc)yv;
+                s0 += (Acc)xv * (Acc)xv; s1 += (Acc)yv * (Acc)yv; s2 += (Acc)xv * (Acc)yv; s3 += dv * dv;
             }
         }
         PairGrad g;
-        if (CORE == CORE_EUC32) euc_core<Acc, BWD>(s0, s1, s2, a.K, g);
-        else if (CORE == CORE_OE32) { g.z = (float)s0; }
-        else hyp_core<Acc, BWD>(s0, s1, s2, s3, a.K, g);
+        g.zxx = g.zxy = g.zyx = g.zyy = 0.f;
+        if (CORE == CORE_EUC32) euc_pair<Acc, BWD>(row_aux<Acc>(LEC_GEOM_EUC, s0, a.K), s1, s2, g);
+        else if (CORE == CORE_OE32) g.z = (float)s0;
+        else hyp_pair<Acc, BWD>(row_aux<Acc>(LEC_GEOM_HYP, s0, a.K), s1, s2, s3, g);
         if (!BWD) {
             a.E_out[p] = relu_nan(g.z);
         } else {
@@ -313,7 +320,7 @@ __global__ void __launch_bounds__(kThreads) energy_dense_kernel(const DenseArgs 
             float* gy = a.gy + p * a.D;
             for (int d = 0; d < a.D; ++d) {
                 const float xv = __ldg(x + d), yv = __ldg(y + d);
-                if (Tr::oe) {
+                if (!Tr::cone) {
                     const float r = 2.f * cf * fmaxf(xv - yv, 0.f);
                     gx[d] = r; gy[d] = -r;
                 } else {
@@ -380,11 +387,6 @@ int launch_dense(const DenseArgs& a, bool bwd, cudaStream_t st) {
     ++g_launches;
     return (int)cudaGetLastError();
 }
-
-// one translation unit per core defines these
-int launch_flat_core(int core, const FlatArgs& a, cudaStream_t st);
-int launch_grouped_core(int core, const GroupArgs& a, cudaStream_t st);
-int launch_dense_core(int core, const DenseArgs& a, bool bwd, cudaStream_t st);
 
 #define LEC_DEFINE_CORE_TU(CORE, NAME)                                                                      \
     namespace lec {                                                                                         \

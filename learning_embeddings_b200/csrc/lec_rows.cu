@@ -1,14 +1,15 @@
-// Per-row kernels: Embedder / FeatNet row transforms (forward + VJP) and the fused Riemannian-SGD
-// table update.  One team of TT lanes per table row; lanes stride over the D columns so a team's
-// loads are contiguous.  These are full-table elementwise passes: 8*D bytes per row for the
-// transforms, 12*D bytes per row for the update (read w, read g, write w).
+// Per-row kernels: Embedder / FeatNet row transforms (forward + VJP), the per-row aperture terms
+// ("aux") consumed by the pair kernels, and the fused Riemannian-SGD table update.
+// One team of TT lanes per table row; lanes stride over the D columns so a team's accesses are
+// contiguous.  These are full-table elementwise passes: 8*D bytes per row for the transforms,
+// 12*D bytes per row for the update (read w, read g, write w).
 #include "lec_common.cuh"
 
 namespace lec {
 
 struct RowsArgs {
-    const float* in; int64_t n; int D; int mode; float K; float r_in; float c0;
-    float* out; int ld; float* zero_out; int replicas; int64_t replica_stride;
+    const float* in; int64_t n; int D; int mode; int geom; float K; float r_in; float c0;
+    float* out; int ld; double* aux; float* zero_out; int replicas; int64_t replica_stride;
     const float* grad_rows; float* grad_in; int accumulate;
 };
 
@@ -21,10 +22,11 @@ __device__ __forceinline__ float rsum(const float* g, int replicas, int64_t stri
 
 template <int TT>
 __device__ __forceinline__ float tsum(float v) { return team_sum<TT, float>(v); }
+template <int TT>
+__device__ __forceinline__ double tsumd(double v) { return team_sum<TT, double>(v); }
 
-// shell projection of a row held as e[] (order_embeddings_h.py:217-228): factor applied to the row
+// shell projection (order_embeddings_h.py:217-228): out = (add + e) / div * mul
 __device__ __forceinline__ void shell_factor(float r, float r_in, bool feat, float& mul, float& add, float& div) {
-    // out = (add + e) / (div) * mul ; identity when mul == 1, add == 0, div == 1
     mul = 1.f; add = 0.f; div = 1.f;
     if (r <= r_in) { mul = r_in; div = feat ? (1e-6f + r) : r; add = feat ? 1e-6f : 0.f; }
     if (r >= 1.0f) { mul = (float)(1.0 - 1e-5); div = r; add = 0.f; }
@@ -73,21 +75,32 @@ __global__ void __launch_bounds__(kThreads) rows_fwd_kernel(const RowsArgs a) {
             }
             shell_factor(r2, a.r_in, a.mode == LEC_ROWS_HYP_TANH_FEAT, mul, add, div);
         }
-        if (valid) {
-            float* o = a.out + row * (int64_t)a.ld;
-            float* zo = a.zero_out ? a.zero_out + row * (int64_t)a.ld : nullptr;
-            for (int d = lane; d < a.ld; d += TT) {
-                float v = 0.f;
-                if (d < D) {
-                    v = __ldg(e + d);
-                    if (hyp) v += 1e-15f;
-                    if (a.mode == LEC_ROWS_EUC_SOFTCLIP) v = (v / rn) * scale;
-                    else if (a.mode == LEC_ROWS_HYP_TANH || a.mode == LEC_ROWS_HYP_TANH_FEAT) v = scale * (v / rn);
-                    if (hyp && (mul != 1.f || div != 1.f)) v = ((add + v) / div) * mul;
-                }
+        double A = 0.0;  // |row|^2 of the values as stored
+        float* o = a.out + (valid ? row : 0) * (int64_t)a.ld;
+        float* zo = a.zero_out ? a.zero_out + (valid ? row : 0) * (int64_t)a.ld : nullptr;
+        for (int d = lane; d < a.ld; d += TT) {
+            float v = 0.f;
+            if (d < D) {
+                v = __ldg(e + d);
+                if (hyp) v += 1e-15f;
+                if (a.mode == LEC_ROWS_EUC_SOFTCLIP) v = (v / rn) * scale;
+                else if (a.mode == LEC_ROWS_HYP_TANH || a.mode == LEC_ROWS_HYP_TANH_FEAT) v = scale * (v / rn);
+                if (hyp && (mul != 1.f || div != 1.f)) v = ((add + v) / div) * mul;
+            }
+            A += (double)v * (double)v;
+            if (valid) {
                 o[d] = v;
                 if (zo)
-                    for (int r = 0; r < a.replicas; ++r) zo[r * a.replica_stride + d] = 0.f;
+                    for (int rr = 0; rr < a.replicas; ++rr) zo[rr * a.replica_stride + d] = 0.f;
+            }
+        }
+        if (a.aux) {
+            A = tsumd<TT>(A);
+            if (valid && lane == 0) {
+                const Aux<double> x = row_aux<double>(a.geom, A, a.K);
+                double2* dst = reinterpret_cast<double2*>(a.aux + 4 * row);
+                dst[0] = make_double2(x.A, x.ria);
+                dst[1] = make_double2(x.t0, x.t1);
             }
         }
     }
@@ -148,12 +161,18 @@ __global__ void __launch_bounds__(kThreads) rows_bwd_kernel(const RowsArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Riemannian SGD (order_embeddings_h.py:764-775).  A team keeps its row (w and the rescaled gradient)
+// in registers: E elements per lane, element d = lane + TT*j.  Per-element arithmetic is fp32 like the
+// reference's; the row-wide sums and the Moebius coefficients built from them are carried in fp64 so
+// the update stays accurate when |w| is close to 1 (the denominators there cancel heavily).
+// ------------------------------------------------------------------------------------------------
 struct RsgdArgs {
     float* table; const float* grad; int64_t n; int D; int ld_g; float lr; float r_in; int lambda_mode;
     float* grad_out; int replicas; int64_t replica_stride;
 };
 
-template <int TT>
+template <int TT, int E>
 __global__ void __launch_bounds__(kThreads) rsgd_kernel(const RsgdArgs a) {
     const int lane = threadIdx.x % TT;
     const int64_t n_teams = (int64_t)gridDim.x * (kThreads / TT);
@@ -166,57 +185,69 @@ __global__ void __launch_bounds__(kThreads) rsgd_kernel(const RsgdArgs a) {
         const int64_t rc = valid ? row : 0;
         float* w = a.table + rc * (int64_t)D;
         const float* g = a.grad + rc * (int64_t)a.ld_g;
-        // |w|
-        float uu = 0.f;
-        for (int d = lane; d < D; d += TT) { const float v = w[d]; uu = fmaf(v, v, uu); }
-        uu = tsum<TT>(uu);
-        const float wn = sqrtf(uu);
-        // conformal factor (order_embeddings_h.py:662-666; SURVEY F4: norm, not norm^2)
-        const float lam = 2.f / (1.f - (a.lambda_mode == 1 ? uu : wn));
+        float wv[E], gv[E];
+        double uu = 0.0;
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+            const int d = lane + TT * j;
+            wv[j] = (d < D) ? w[d] : 0.f;
+            gv[j] = (d < D) ? rsum(g + d, a.replicas, a.replica_stride) : 0.f;
+            uu += (double)wv[j] * (double)wv[j];
+        }
+        uu = tsumd<TT>(uu);
+        // conformal factor (order_embeddings_h.py:662-666; SURVEY F4: the norm, not its square)
+        const float wn = (float)sqrt(uu);
+        const float lam = 2.f / (1.f - (a.lambda_mode == 1 ? (float)uu : wn));
         const float inv = 1.f / lam;
         const float gs = inv * inv;
-        // v = -lr * g' + 1e-15 ; |v|
-        float vv = 0.f;
-        for (int d = lane; d < D; d += TT) {
-            const float v = -a.lr * (rsum(g + d, a.replicas, a.replica_stride) * gs) + 1e-15f;
-            vv = fmaf(v, v, vv);
+        // v = -lr * g' + 1e-15
+        double vv = 0.0;
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+            gv[j] *= gs;                                   // the Riemannian gradient, as left in weight.grad
+            const float v = -a.lr * gv[j] + 1e-15f;
+            if (lane + TT * j < D) vv += (double)v * (double)v;
         }
-        vv = tsum<TT>(vv);
-        const float vn = sqrtf(vv);
+        vv = tsumd<TT>(vv);
+        const float vn = (float)sqrt(vv);
         const float th = tanhf(fminf(fmaxf(lam * vn / 2.f, -15.f), 15.f));
         // t = th * v / |v| + 1e-6 ; Moebius sums
-        float uv = 0.f, tt = 0.f;
-        for (int d = lane; d < D; d += TT) {
-            const float v = -a.lr * (rsum(g + d, a.replicas, a.replica_stride) * gs) + 1e-15f;
-            const float t = th * v / vn + 1e-6f;
-            uv = fmaf(w[d], t, uv);
-            tt = fmaf(t, t, tt);
+        float tv[E];
+        double uv = 0.0, tt = 0.0;
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+            const float v = -a.lr * gv[j] + 1e-15f;
+            tv[j] = th * v / vn + 1e-6f;
+            if (lane + TT * j < D) {
+                uv += (double)wv[j] * (double)tv[j];
+                tt += (double)tv[j] * (double)tv[j];
+            }
         }
-        uv = 2.f * tsum<TT>(uv);
-        tt = tsum<TT>(tt);
-        const float den = 1.f + uv + tt * uu;
-        const float cw = (1.f + uv + tt) / den;
-        const float ct = (1.f - uu) / den;
-        float rr = 0.f;
-        for (int d = lane; d < D; d += TT) {
-            const float v = -a.lr * (rsum(g + d, a.replicas, a.replica_stride) * gs) + 1e-15f;
-            const float t = th * v / vn + 1e-6f;
-            const float res = cw * w[d] + ct * t;
-            rr = fmaf(res, res, rr);
+        uv = 2.0 * tsumd<TT>(uv);
+        tt = tsumd<TT>(tt);
+        const double den = 1.0 + uv + tt * uu;
+        const float cw = (float)((1.0 + uv + tt) / den);
+        const float ct = (float)((1.0 - uu) / den);
+        double rr = 0.0;
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+            tv[j] = cw * wv[j] + ct * tv[j];
+            if (lane + TT * j < D) rr += (double)tv[j] * (double)tv[j];
         }
-        rr = sqrtf(tsum<TT>(rr));
+        const float rn = (float)sqrt(tsumd<TT>(rr));
         float mul, add, div;
-        shell_factor(rr, a.r_in, false, mul, add, div);
+        shell_factor(rn, a.r_in, false, mul, add, div);
         if (valid) {
             float* go = a.grad_out ? a.grad_out + row * (int64_t)D : nullptr;
-            for (int d = lane; d < D; d += TT) {
-                const float gsc = rsum(g + d, a.replicas, a.replica_stride) * gs;
-                const float v = -a.lr * gsc + 1e-15f;
-                const float t = th * v / vn + 1e-6f;
-                float res = cw * w[d] + ct * t;
-                if (mul != 1.f || div != 1.f) res = (res / div) * mul;
-                w[d] = res;
-                if (go) go[d] = gsc;
+#pragma unroll
+            for (int j = 0; j < E; ++j) {
+                const int d = lane + TT * j;
+                if (d < D) {
+                    float res = tv[j];
+                    if (mul != 1.f || div != 1.f) res = (res / div) * mul;
+                    w[d] = res;
+                    if (go) go[d] = gv[j];
+                }
             }
         }
     }
@@ -244,48 +275,43 @@ static int team_width(int D) {
     return t;
 }
 
-#define LEC_ROWS_LAUNCH(KERNEL, TT, ARGS, N, ST)                                             \
-    do {                                                                                     \
-        const int tpb = kThreads / (TT);                                                     \
-        int64_t need = ((N) + tpb - 1) / tpb;                                                \
-        const int64_t cap = (int64_t)sm_count() * 8;                                         \
-        if (need < 1) need = 1;                                                              \
-        const int grid = (int)(need < cap ? need : cap);                                     \
-        KERNEL<TT><<<grid, kThreads, 0, ST>>>(ARGS);                                         \
-    } while (0)
+static int grid_rows(int64_t n, int tt) {
+    const int tpb = kThreads / tt;
+    int64_t need = (n + tpb - 1) / tpb;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
 
 #define LEC_ROWS_DISPATCH(KERNEL, ARGS, N, D, ST)                                            \
     do {                                                                                     \
         switch (team_width(D)) {                                                             \
-            case 1: LEC_ROWS_LAUNCH(KERNEL, 1, ARGS, N, ST); break;                          \
-            case 2: LEC_ROWS_LAUNCH(KERNEL, 2, ARGS, N, ST); break;                          \
-            case 4: LEC_ROWS_LAUNCH(KERNEL, 4, ARGS, N, ST); break;                          \
-            case 8: LEC_ROWS_LAUNCH(KERNEL, 8, ARGS, N, ST); break;                          \
-            case 16: LEC_ROWS_LAUNCH(KERNEL, 16, ARGS, N, ST); break;                        \
-            default: LEC_ROWS_LAUNCH(KERNEL, 32, ARGS, N, ST); break;                        \
+            case 1: KERNEL<1><<<grid_rows(N, 1), kThreads, 0, ST>>>(ARGS); break;             \
+            case 2: KERNEL<2><<<grid_rows(N, 2), kThreads, 0, ST>>>(ARGS); break;             \
+            case 4: KERNEL<4><<<grid_rows(N, 4), kThreads, 0, ST>>>(ARGS); break;             \
+            case 8: KERNEL<8><<<grid_rows(N, 8), kThreads, 0, ST>>>(ARGS); break;             \
+            case 16: KERNEL<16><<<grid_rows(N, 16), kThreads, 0, ST>>>(ARGS); break;          \
+            default: KERNEL<32><<<grid_rows(N, 32), kThreads, 0, ST>>>(ARGS); break;          \
         }                                                                                    \
         ++g_launches;                                                                        \
     } while (0)
 
-static float inner_radius(float K) {
+static void hyp_constants(float K, float& r_in, float& c0) {
     const double k = (double)K;
-    return (float)(2.0 * k / (1.0 + sqrt(1.0 + 4.0 * k * k)));
-}
-static float atanh_clamped(double v) {  // oe_h.py:106-110
+    const double rin = 2.0 * k / (1.0 + sqrt(1.0 + 4.0 * k * k));  // order_embeddings_h.py:1089
+    double v = rin;                                                 // oe_h.py:106-110 (arctanh with clamp)
     if (v < -1 + 1e-5) v = -1 + 1e-5;
     if (v > 1 - 1e-5) v = 1 - 1e-5;
-    return (float)(0.5 * (log(1 + v) - log(1 - v)));
+    r_in = (float)rin;
+    c0 = (float)(0.5 * (log(1 + v) - log(1 - v)));
 }
 
-int rows_fwd_launch(const float* in, int64_t n, int D, int mode, float K, float* out, int ld, float* zero_out,
-                    int zero_replicas, cudaStream_t st) {
+int rows_fwd_launch(const float* in, int64_t n, int D, int mode, int geom, float K, float* out, int ld, double* aux,
+                    float* zero_out, int zero_replicas, cudaStream_t st) {
     RowsArgs a{};
-    a.in = in; a.n = n; a.D = D; a.mode = mode; a.K = K; a.out = out; a.ld = ld; a.zero_out = zero_out;
-    a.replicas = zero_replicas; a.replica_stride = n * (int64_t)ld;
-    const double k = (double)K;
-    const double rin = 2.0 * k / (1.0 + sqrt(1.0 + 4.0 * k * k));
-    a.r_in = (float)rin;
-    a.c0 = atanh_clamped(rin);
+    a.in = in; a.n = n; a.D = D; a.mode = mode; a.geom = geom; a.K = K; a.out = out; a.ld = ld; a.aux = aux;
+    a.zero_out = zero_out; a.replicas = zero_replicas; a.replica_stride = n * (int64_t)ld;
+    hyp_constants(K, a.r_in, a.c0);
     if (n == 0) return 0;
     LEC_ROWS_DISPATCH(rows_fwd_kernel, a, n, D, st);
     return (int)cudaGetLastError();
@@ -297,18 +323,34 @@ int rows_bwd_launch(const float* in, const float* grad_rows, int replicas, int64
     a.replicas = replicas; a.replica_stride = n * (int64_t)ld;
     a.in = in; a.n = n; a.D = D; a.mode = mode; a.K = K; a.ld = ld; a.grad_rows = grad_rows; a.grad_in = grad_in;
     a.accumulate = accumulate;
-    a.r_in = inner_radius(K);
-    a.c0 = atanh_clamped((double)2.0 * K / (1.0 + sqrt(1.0 + 4.0 * (double)K * K)));
+    hyp_constants(K, a.r_in, a.c0);
     if (n == 0) return 0;
     LEC_ROWS_DISPATCH(rows_bwd_kernel, a, n, D, st);
     return (int)cudaGetLastError();
+}
+
+template <int TT, int E>
+static void rsgd_go(const RsgdArgs& a, cudaStream_t st) {
+    rsgd_kernel<TT, E><<<grid_rows(a.n, TT), kThreads, 0, st>>>(a);
 }
 
 int rsgd_launch(float* table, const float* grad, int replicas, int64_t n, int D, int ld_g, float lr, float r_in,
                 int lambda_mode, float* grad_out, cudaStream_t st) {
     RsgdArgs a{table, grad, n, D, ld_g, lr, r_in, lambda_mode, grad_out, replicas, n * (int64_t)ld_g};
     if (n == 0) return 0;
-    LEC_ROWS_DISPATCH(rsgd_kernel, a, n, D, st);
+    // E elements per lane in registers; TT lanes per row
+    if (D <= 1) rsgd_go<1, 1>(a, st);
+    else if (D <= 2) rsgd_go<1, 2>(a, st);
+    else if (D <= 4) rsgd_go<1, 4>(a, st);
+    else if (D <= 8) rsgd_go<2, 4>(a, st);
+    else if (D <= 16) rsgd_go<4, 4>(a, st);
+    else if (D <= 32) rsgd_go<8, 4>(a, st);
+    else if (D <= 64) rsgd_go<16, 4>(a, st);
+    else if (D <= 128) rsgd_go<32, 4>(a, st);
+    else if (D <= 256) rsgd_go<32, 8>(a, st);
+    else if (D <= 512) rsgd_go<32, 16>(a, st);
+    else rsgd_go<32, 32>(a, st);
+    ++g_launches;
     return (int)cudaGetLastError();
 }
 

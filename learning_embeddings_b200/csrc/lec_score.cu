@@ -20,33 +20,23 @@ struct ScoreArgs {
 
 enum { SC_EUC = 0, SC_HYP32 = 1, SC_HYP64 = 2, SC_OE = 3 };
 
-// per-label scalars: s0 = |x|^2 ; s1 = sqrt(1-K^2/|x|^2) (euc) or asin(clamp(K(1-|x|^2)/|x|)) (hyp)
+// per-label scalars (fp64, once per label per block): s0 = |x|^2 ; s1 = sqrt(1-K^2/|x|^2) (euc) or
+// asin(clamp(K(1-|x|^2)/|x|)) (hyp) -- the same per-row terms lec_rows_fwd stores as "aux"
 template <int GEOMC>
-__device__ __forceinline__ void label_scalars(float A, float K, float& s0, float& s1) {
-    s0 = A;
-    if (GEOMC == SC_EUC) {
-        s1 = sqrtf(1.f - K * K / A);
-    } else if (GEOMC == SC_HYP32) {
-        const float h = K * (1.f - A) / sqrtf(A);
-        const float hc = h < -1.f + kClampEps ? -1.f + kClampEps : (h > 1.f - kClampEps ? 1.f - kClampEps : h);
-        s1 = asinf(hc);
-    } else if (GEOMC == SC_HYP64) {
-        const double Ad = (double)A;
-        const double h = (double)K * (1.0 - Ad) / sqrt(Ad);
-        const double hc = h < -1.0 + 1e-5 ? -1.0 + 1e-5 : (h > 1.0 - 1e-5 ? 1.0 - 1e-5 : h);
-        s1 = atan2f((float)hc, (float)sqrt((1.0 - hc) * (1.0 + hc)));
-    } else {
-        s1 = 0.f;
-    }
+__device__ __forceinline__ void label_scalars(double A, float K, double& s0, double& s1) {
+    const int geom = (GEOMC == SC_EUC) ? LEC_GEOM_EUC : (GEOMC == SC_OE ? LEC_GEOM_OE : LEC_GEOM_HYP);
+    const Aux<double> x = row_aux<double>(geom, A, K);
+    s0 = x.A;
+    s1 = x.t0;
 }
 
 template <int GEOMC, int DQ>
 __global__ void __launch_bounds__(kThreads) score_kernel(const ScoreArgs a) {
     extern __shared__ __align__(16) float smem[];
     constexpr int DP = 4 * DQ;
-    float* lab = smem;                               // [tile][DP]
-    float* ls0 = smem + (size_t)a.tile_labels * DP;  // [tile]
-    float* ls1 = ls0 + a.tile_labels;                // [tile]
+    float* lab = smem;                                                                  // [tile][DP]
+    double* ls0 = reinterpret_cast<double*>(smem + (size_t)a.tile_labels * DP);         // [tile]
+    double* ls1 = ls0 + a.tile_labels;                                                  // [tile]
 
     const int64_t img = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const bool valid = img < a.N;
@@ -76,8 +66,8 @@ __global__ void __launch_bounds__(kThreads) score_kernel(const ScoreArgs a) {
         }
         __syncthreads();
         for (int r = threadIdx.x; r < tl; r += kThreads) {
-            float A = 0.f;
-            for (int d = 0; d < DP; ++d) A = fmaf(lab[r * DP + d], lab[r * DP + d], A);
+            double A = 0.0;
+            for (int d = 0; d < DP; ++d) A += (double)lab[r * DP + d] * (double)lab[r * DP + d];
             label_scalars<GEOMC>(A, a.K, ls0[r], ls1[r]);
         }
         __syncthreads();
@@ -123,9 +113,9 @@ __global__ void __launch_bounds__(kThreads) score_kernel(const ScoreArgs a) {
                     d = y[4 * q + 2] - x.z; dd = fmaf(d, d, dd); xd = fmaf(x.z, d, xd);
                     d = y[4 * q + 3] - x.w; dd = fmaf(d, d, dd); xd = fmaf(x.w, d, xd);
                 }
-                const float A = ls0[r];
+                const float A = (float)ls0[r];
                 const float an = fmaxf(sqrtf(A), kNormEps), bn = fmaxf(sqrtf(dd), kNormEps);
-                E = relu_nan(ls1[r] - xd / (an * bn));
+                E = relu_nan((float)ls1[r] - xd / (an * bn));
             } else {
                 float p = 0.f, s2 = 0.f;
 #pragma unroll
@@ -137,21 +127,21 @@ __global__ void __launch_bounds__(kThreads) score_kernel(const ScoreArgs a) {
                     p = fmaf(x.z, y[4 * q + 2], p); d = x.z - y[4 * q + 2]; s2 = fmaf(d, d, s2);
                     p = fmaf(x.w, y[4 * q + 3], p); d = x.w - y[4 * q + 3]; s2 = fmaf(d, d, s2);
                 }
-                const float A = ls0[r];
+                const float A = (float)ls0[r];
                 float theta;
                 if (GEOMC == SC_HYP64) {
-                    const double Ad = A, Bd = B, pd = p;
+                    const double Ad = ls0[r], Bd = B, pd = p;
                     const double w2 = 1.0 + Ad * Bd - 2.0 * pd;
-                    const double g = diff_of_products(pd, 1.0 + Ad, Ad, 1.0 + Bd) / (sqrt(Ad) * sqrt((double)s2) * sqrt(w2));
+                    const double g = (s2 == 0.f) ? (double)NAN : diff_of_products(pd, 1.0 + Ad, Ad, 1.0 + Bd) / (sqrt(Ad) * sqrt((double)s2) * sqrt(w2));
                     const double gc = g < -1.0 + 1e-5 ? -1.0 + 1e-5 : (g > 1.0 - 1e-5 ? 1.0 - 1e-5 : g);
                     theta = atan2f((float)sqrt((1.0 - gc) * (1.0 + gc)), (float)gc);
                 } else {
                     const float w2 = 1.f + A * B - 2.f * p;
-                    const float g = diff_of_products(p, 1.f + A, A, 1.f + B) / (sqrtf(A) * sqrtf(s2) * sqrtf(w2));
+                    const float g = (s2 == 0.f) ? NAN : diff_of_products(p, 1.f + A, A, 1.f + B) / (sqrtf(A) * sqrtf(s2) * sqrtf(w2));
                     const float gc = g < -1.f + kClampEps ? -1.f + kClampEps : (g > 1.f - kClampEps ? 1.f - kClampEps : g);
                     theta = acosf(gc);
                 }
-                E = relu_nan(theta - ls1[r]);
+                E = relu_nan(theta - (float)ls1[r]);
             }
             if (valid && a.scores) a.scores[img * a.L + l] = E;
             if (level < a.n_levels && l >= a.level_start[level]) {
@@ -191,7 +181,7 @@ __global__ void __launch_bounds__(kThreads) score_kernel(const ScoreArgs a) {
 template <int GEOMC, int DQ>
 static int score_launch_dq(ScoreArgs& a, cudaStream_t st) {
     constexpr int DP = 4 * DQ;
-    const size_t per_label = (size_t)(DP + 2) * sizeof(float);
+    const size_t per_label = (size_t)(DP + 4) * sizeof(float);  // row + two doubles
     const size_t budget = 200 * 1024;
     int64_t tile = (int64_t)(budget / per_label);
     if (tile > a.L) tile = a.L;

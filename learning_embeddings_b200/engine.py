@@ -5,7 +5,8 @@ This is the public fast path (what bench.py drives).  It does what one iteration
 (order_embeddings_h.py:752-775 for the hyperbolic trainer, order_embeddings.py:619-635 for the
 Euclidean one) with the negatives already drawn:
 
-    rows      = transform(table)                    lec_rows_fwd   (also clears grad_rows)
+    rows, aux = transform(table)                    lec_rows_fwd   (also clears grad_rows; aux = per-row
+                                                    aperture terms in fp64)
     loss, dL/drows = cone loss over B*(1+2N) pairs   lec_pairs_grouped
     [sum dL/drows and loss over ranks]               NCCL all-reduce, only when world_size > 1
     dL/dtable = J^T dL/drows                         lec_rows_bwd
@@ -31,7 +32,7 @@ def pack_index_block(pos_from, pos_to, neg_to, neg_from, pin=True):
 
 class ConeStep:
     def __init__(self, table, geom, n_neg, max_groups, K=None, alpha=1.0, lr=1e-3, row_mode=None, update="auto",
-                 precision=ops.PREC_F32, process_group=None, replicas=None):
+                 precision=ops.PREC_F64CORE, process_group=None, replicas=None):
         N.require_cuda(table)
         if table.dtype != torch.float32 or not table.is_contiguous():
             raise N.LecError("ConeStep: table must be a contiguous float32 CUDA tensor (updated in place)")
@@ -53,6 +54,7 @@ class ConeStep:
         dev = table.device
         self.replicas = ops.default_replicas(self.n, self.ld) if replicas is None else int(replicas)
         self.rows = torch.empty((self.n, self.ld), device=dev, dtype=torch.float32)
+        self.aux = torch.empty((self.n, 4), device=dev, dtype=torch.float64)
         self.grad_rows = torch.empty((self.replicas, self.n, self.ld), device=dev, dtype=torch.float32)
         self.grad_table = torch.empty((self.n, self.D), device=dev, dtype=torch.float32)
         self.E_pos = torch.empty(self.max_groups, device=dev, dtype=torch.float32)
@@ -73,14 +75,16 @@ class ConeStep:
         B = int(pos_from.numel())
         if B > self.max_groups:
             raise N.LecError("batch of %d positives exceeds max_groups=%d" % (B, self.max_groups))
-        N.check(lib.lec_rows_fwd(N._p(self.table), self.n, self.D, self.row_mode, self.K, N._p(self.rows), self.ld,
-                                 N._p(self.grad_rows), self.replicas, st), "lec_rows_fwd")
+        N.check(lib.lec_rows_fwd(N._p(self.table), self.n, self.D, self.row_mode, N.GEOM[self.geom], self.K,
+                                 N._p(self.rows), self.ld, N._p(self.aux), N._p(self.grad_rows), self.replicas, st),
+                "lec_rows_fwd")
         self.loss.zero_()
         ev = self.kernel_events
         if ev is not None:
             ev[0].record()
         N.check(lib.lec_pairs_grouped(
-            N.GEOM[self.geom], self.precision, N._p(self.rows), self.n, self.D, self.ld, N._p(pos_from), N._p(pos_to),
+            N.GEOM[self.geom], self.precision, N._p(self.rows), N._p(self.aux), self.n, self.D, self.ld,
+            N._p(pos_from), N._p(pos_to),
             N._p(neg_to), N._p(neg_from), pos_from.element_size(), B, self.n_neg, N._p(w_pos), N._p(w_neg), self.K,
             self.alpha, N._p(self.E_pos), N._p(self.E_neg), N._p(self.loss), N._p(self.grad_rows), self.replicas, st),
             "lec_pairs_grouped")

@@ -58,17 +58,20 @@ def _f32(t, device):
 # --------------------------------------------------------------------------------------------------
 # Row transforms
 # --------------------------------------------------------------------------------------------------
-def rows_forward(W, mode, K, zero_out=None):
-    """Transformed table [n, ld] of the raw parameter rows W [n, D] (lec_rows_fwd)."""
+def rows_forward(W, mode, K, geom=None, zero_out=None):
+    """Transformed table [n, ld] of the raw parameter rows W [n, D], plus (when `geom` is given) the
+    per-row aperture terms aux [n, 4] float64 the pair kernels consume (lec_rows_fwd)."""
     N.require_cuda(W)
     W = W.detach().contiguous().float()
     n, D = W.shape
     ld = padded_dim(D)
     rows = torch.empty((n, ld), device=W.device, dtype=torch.float32)
+    aux = torch.empty((n, 4), device=W.device, dtype=torch.float64) if geom is not None else None
     zr = 0 if zero_out is None else (zero_out.shape[0] if zero_out.dim() == 3 else 1)
-    N.check(N.lib().lec_rows_fwd(N._p(W), n, D, int(mode), float(K or 0.0), N._p(rows), ld, N._p(zero_out), zr,
-                                 N.stream_ptr(W.device)), "lec_rows_fwd")
-    return rows
+    N.check(N.lib().lec_rows_fwd(N._p(W), n, D, int(mode), GEOM[geom] if geom is not None else 0, float(K or 0.0),
+                                 N._p(rows), ld, N._p(aux), N._p(zero_out), zr, N.stream_ptr(W.device)),
+            "lec_rows_fwd")
+    return rows, aux
 
 
 def rows_backward(W, grad_rows, mode, K, out=None, accumulate=False):
@@ -87,29 +90,43 @@ def rows_backward(W, grad_rows, mode, K, out=None, accumulate=False):
 
 
 class RowTransform(torch.autograd.Function):
-    """rows = transform(W); differentiable (straight-through where the reference is)."""
+    """rows, aux = transform(W); rows is differentiable (straight-through where the reference is), aux
+    (the per-row aperture terms of energy `geom`) is a by-product of the same launch."""
 
     @staticmethod
-    def forward(ctx, W, mode, K):
+    def forward(ctx, W, mode, K, geom):
         ctx.mode, ctx.K = int(mode), float(K or 0.0)
         ctx.save_for_backward(W)
-        return rows_forward(W, mode, K)
+        rows, aux = rows_forward(W, mode, K, geom)
+        if aux is None:
+            aux = torch.empty((0, 4), device=W.device, dtype=torch.float64)
+        ctx.mark_non_differentiable(aux)
+        return rows, aux
 
     @staticmethod
-    def backward(ctx, grad_rows):
+    def backward(ctx, grad_rows, _grad_aux):
         (W,) = ctx.saved_tensors
-        return rows_backward(W, grad_rows, ctx.mode, ctx.K), None, None
+        return rows_backward(W, grad_rows, ctx.mode, ctx.K), None, None, None
 
 
-def transform_rows(W, mode, K):
-    return RowTransform.apply(W, mode, K)
+def transform_rows(W, mode, K, geom=None):
+    """-> (rows [n, ld], aux [n, 4] float64 or an empty tensor when geom is None)."""
+    return RowTransform.apply(W, mode, K, geom)
 
 
 # --------------------------------------------------------------------------------------------------
 # Pair losses on gathered rows
 # --------------------------------------------------------------------------------------------------
-def pairs_grouped_raw(geom, rows, D, pos_from, pos_to, neg_to, neg_from, n_neg, K, alpha, w_pos=None, w_neg=None,
-                      grad_rows=None, loss_out=None, precision=PREC_F32, E_pos=None, E_neg=None):
+def _aux_ptr(geom, aux):
+    if aux is None or aux.numel() == 0:
+        if geom != "oe":
+            raise N.LecError("the %s energy needs the per-row aux terms (transform_rows(..., geom=%r))" % (geom, geom))
+        return N._p(None)
+    return N._p(aux)
+
+
+def pairs_grouped_raw(geom, rows, aux, D, pos_from, pos_to, neg_to, neg_from, n_neg, K, alpha, w_pos=None, w_neg=None,
+                      grad_rows=None, loss_out=None, precision=PREC_F64CORE, E_pos=None, E_neg=None):
     """Direct call of lec_pairs_grouped on preallocated buffers (used by the step engine and bench)."""
     dev = rows.device
     B = int(pos_from.numel())
@@ -121,7 +138,8 @@ def pairs_grouped_raw(geom, rows, D, pos_from, pos_to, neg_to, neg_from, n_neg, 
         loss_out = torch.zeros(1, device=dev, dtype=torch.float64)
     R = 1 if grad_rows is None or grad_rows.dim() == 2 else grad_rows.shape[0]
     N.check(N.lib().lec_pairs_grouped(
-        GEOM[geom], int(precision), N._p(rows), rows.shape[0], int(D), rows.shape[1], N._p(pos_from), N._p(pos_to),
+        GEOM[geom], int(precision), N._p(rows), _aux_ptr(geom, aux), rows.shape[0], int(D), rows.shape[1],
+        N._p(pos_from), N._p(pos_to),
         N._p(neg_to), N._p(neg_from), pos_from.element_size(), B, int(n_neg), N._p(w_pos), N._p(w_neg),
         float(K or 0.0), float(alpha), N._p(E_pos), N._p(E_neg), N._p(loss_out), N._p(grad_rows), R,
         N.stream_ptr(dev)), "lec_pairs_grouped")
@@ -132,7 +150,7 @@ class GroupedPairLoss(torch.autograd.Function):
     """loss, E_pos[B], E_neg[B, 2N] for the training layout (include/lec_b200.h: lec_pairs_grouped)."""
 
     @staticmethod
-    def forward(ctx, rows, D, pos_from, pos_to, neg_to, neg_from, n_neg, w_pos, w_neg, geom, K, alpha, precision):
+    def forward(ctx, rows, aux, D, pos_from, pos_to, neg_to, neg_from, n_neg, w_pos, w_neg, geom, K, alpha, precision):
         N.require_cuda(rows)
         dev = rows.device
         rows_c = rows.detach().contiguous()
@@ -144,7 +162,7 @@ class GroupedPairLoss(torch.autograd.Function):
         grad_rows = None
         if need_grad:
             grad_rows = torch.zeros((default_replicas(*rows_c.shape),) + tuple(rows_c.shape), device=dev)
-        loss64, E_pos, E_neg = pairs_grouped_raw(geom, rows_c, D, pos_from, pos_to, neg_to, neg_from, n_neg, K, alpha,
+        loss64, E_pos, E_neg = pairs_grouped_raw(geom, rows_c, aux, D, pos_from, pos_to, neg_to, neg_from, n_neg, K, alpha,
                                                  _f32(w_pos, dev), _f32(w_neg, dev), grad_rows, None, precision)
         if need_grad:
             grad_rows = reduce_replicas(grad_rows)
@@ -155,17 +173,17 @@ class GroupedPairLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_loss, _gp, _gn):
         (grad_rows,) = ctx.saved_tensors
-        return (grad_rows * g_loss,) + (None,) * 12
+        return (grad_rows * g_loss,) + (None,) * 13
 
 
-def grouped_pair_loss(rows, D, pos_from, pos_to, neg_to, neg_from, n_neg, geom, K, alpha, w_pos=None, w_neg=None,
-                      precision=PREC_F32):
-    return GroupedPairLoss.apply(rows, D, pos_from, pos_to, neg_to, neg_from, n_neg, w_pos, w_neg, geom, K, alpha,
+def grouped_pair_loss(rows, aux, D, pos_from, pos_to, neg_to, neg_from, n_neg, geom, K, alpha, w_pos=None, w_neg=None,
+                      precision=PREC_F64CORE):
+    return GroupedPairLoss.apply(rows, aux, D, pos_from, pos_to, neg_to, neg_from, n_neg, w_pos, w_neg, geom, K, alpha,
                                  precision)
 
 
-def pairs_flat_raw(geom, rows, D, from_idx, to_idx, K, alpha, w=None, is_pos=None, grad_rows=None, loss_out=None,
-                   precision=PREC_F32, E_out=None):
+def pairs_flat_raw(geom, rows, aux, D, from_idx, to_idx, K, alpha, w=None, is_pos=None, grad_rows=None, loss_out=None,
+                   precision=PREC_F64CORE, E_out=None):
     dev = rows.device
     P = int(from_idx.numel())
     if E_out is None:
@@ -174,7 +192,8 @@ def pairs_flat_raw(geom, rows, D, from_idx, to_idx, K, alpha, w=None, is_pos=Non
         loss_out = torch.zeros(1, device=dev, dtype=torch.float64)
     R = 1 if grad_rows is None or grad_rows.dim() == 2 else grad_rows.shape[0]
     N.check(N.lib().lec_pairs_flat(
-        GEOM[geom], int(precision), N._p(rows), rows.shape[0], int(D), rows.shape[1], N._p(from_idx), N._p(to_idx),
+        GEOM[geom], int(precision), N._p(rows), _aux_ptr(geom, aux), rows.shape[0], int(D), rows.shape[1],
+        N._p(from_idx), N._p(to_idx),
         from_idx.element_size(), N._p(w), N._p(is_pos), P, float(K or 0.0), float(alpha), N._p(E_out),
         N._p(loss_out), N._p(grad_rows), R, N.stream_ptr(dev)), "lec_pairs_flat")
     return loss_out, E_out
@@ -184,7 +203,7 @@ class FlatPairLoss(torch.autograd.Function):
     """loss, E[P] for an arbitrary list of (from, to) pairs with positive/negative flags."""
 
     @staticmethod
-    def forward(ctx, rows, D, from_idx, to_idx, is_pos, w, geom, K, alpha, precision):
+    def forward(ctx, rows, aux, D, from_idx, to_idx, is_pos, w, geom, K, alpha, precision):
         N.require_cuda(rows)
         dev = rows.device
         rows_c = rows.detach().contiguous()
@@ -197,7 +216,7 @@ class FlatPairLoss(torch.autograd.Function):
         grad_rows = None
         if need_grad:
             grad_rows = torch.zeros((default_replicas(*rows_c.shape),) + tuple(rows_c.shape), device=dev)
-        loss64, E = pairs_flat_raw(geom, rows_c, D, from_idx, to_idx, K, alpha, _f32(w, dev), is_pos, grad_rows, None,
+        loss64, E = pairs_flat_raw(geom, rows_c, aux, D, from_idx, to_idx, K, alpha, _f32(w, dev), is_pos, grad_rows, None,
                                    precision)
         if need_grad:
             grad_rows = reduce_replicas(grad_rows)
@@ -208,11 +227,11 @@ class FlatPairLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_loss, _ge):
         (grad_rows,) = ctx.saved_tensors
-        return (grad_rows * g_loss,) + (None,) * 9
+        return (grad_rows * g_loss,) + (None,) * 10
 
 
-def flat_pair_loss(rows, D, from_idx, to_idx, geom, K, alpha, is_pos=None, w=None, precision=PREC_F32):
-    return FlatPairLoss.apply(rows, D, from_idx, to_idx, is_pos, w, geom, K, alpha, precision)
+def flat_pair_loss(rows, aux, D, from_idx, to_idx, geom, K, alpha, is_pos=None, w=None, precision=PREC_F64CORE):
+    return FlatPairLoss.apply(rows, aux, D, from_idx, to_idx, is_pos, w, geom, K, alpha, precision)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -249,7 +268,7 @@ class DenseEnergy(torch.autograd.Function):
         return gx.view(xs), gy.view(ys), None, None, None
 
 
-def energy(x, y, geom, K=None, precision=PREC_F32):
+def energy(x, y, geom, K=None, precision=PREC_F64CORE):
     return DenseEnergy.apply(x, y, geom, K, precision)
 
 
@@ -279,7 +298,7 @@ def rsgd_update_(table, grad, lr, r_in, textbook_lambda=False, write_rescaled_gr
 # Scoring
 # --------------------------------------------------------------------------------------------------
 def score_topk(labels, images, geom, K, level_start, level_stop, k=5, want_scores=False, want_values=True,
-               precision=PREC_F32):
+               precision=PREC_F32):  # scoring only ranks: the fp32 core is the default here
     """Per image, per level: the k labels of lowest energy E(x=label, y=image) (lec_score_topk).
 
     Returns (topk_idx int32 [N, n_levels, k], topk_val float32 or None, scores [N, L] or None)."""

@@ -37,7 +37,9 @@ def main():
         nt, nf = h.sample_negatives(u, v, Nn, rng)
         P = B * (1 + 2 * Nn)
         W = ball(h.n, D, 0.1, 0.15, g).to(dev)
-        rows = ops.rows_forward(W, N.ROWS_HYP_SHELL, 0.1)
+        rows, aux_h = ops.rows_forward(W, N.ROWS_HYP_SHELL, 0.1, 'hyp')
+        _, aux_e = ops.rows_forward(W, N.ROWS_HYP_SHELL, 0.01, 'euc')
+        AUX = {'hyp': aux_h, 'euc': aux_e, 'oe': None}
         ud, vd, ntd, nfd = (torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev) for a in (u, v, nt, nf))
         grad = torch.zeros((int(os.environ.get('LEC_R', ops.default_replicas(*rows.shape))),) + tuple(rows.shape), device=dev)
         print('replicas', grad.shape[0])
@@ -47,7 +49,7 @@ def main():
             K = {"hyp": 0.1, "euc": 0.01, "oe": 0.0}[geom]
             for prec in ((0, 1) if geom == "hyp" else (0,)):
                 for gr in (None, grad):
-                    t = timeit(lambda: ops.pairs_grouped_raw(geom, rows, D, ud, vd, ntd, nfd, Nn, K, 0.05, grad_rows=gr,
+                    t = timeit(lambda: ops.pairs_grouped_raw(geom, rows, AUX[geom], D, ud, vd, ntd, nfd, Nn, K, 0.05, grad_rows=gr,
                                                              loss_out=loss, precision=prec, E_pos=Ep, E_neg=En))
                     print("grouped D=%d N=%d %s prec=%d grad=%d: %8.1f us  %6.2f Gpairs/s" % (D, Nn, geom, prec, gr is not None, t, P / t / 1e3))
         # flat kernel on the expanded list
@@ -56,7 +58,7 @@ def main():
         isp = torch.cat([torch.ones(B), torch.zeros(2 * Nn * B)]).to(torch.uint8).to(dev)
         E = torch.empty(P, device=dev)
         for gr in (None, grad):
-            t = timeit(lambda: ops.pairs_flat_raw("hyp", rows, D, fi, ti, 0.1, 0.05, is_pos=isp, grad_rows=gr, loss_out=loss, precision=1, E_out=E))
+            t = timeit(lambda: ops.pairs_flat_raw("hyp", rows, aux_h, D, fi, ti, 0.1, 0.05, is_pos=isp, grad_rows=gr, loss_out=loss, precision=1, E_out=E))
             print("flat    D=%d hyp prec=1 grad=%d: %8.1f us  %6.2f Gpairs/s" % (D, gr is not None, t, P / t / 1e3))
         # dense energy
         x = rows[fi.long(), :D].contiguous(); y = rows[ti.long(), :D].contiguous()

@@ -23,7 +23,7 @@ def test_library_exports_every_header_symbol():
     for n in names:
         assert hasattr(lib, n), n
     assert sorted(_native.EXPORTS) == names
-    assert lib.lec_abi_version() == _native.ABI_VERSION == 2
+    assert lib.lec_abi_version() == _native.ABI_VERSION == 3
 
 
 def test_argument_validation_codes():
@@ -32,22 +32,25 @@ def test_argument_validation_codes():
     fake = ctypes.c_void_p(0x1000)      # 16-byte aligned, never dereferenced: validation fails first
     odd = ctypes.c_void_p(0x1004)
     # NULL rows
-    assert lib.lec_pairs_flat(0, 0, null, 10, 4, 4, fake, fake, 8, null, null, 5, 3.0, 1.0, fake, null, null, 1, null) == -1
+    assert lib.lec_pairs_flat(0, 0, null, fake, 10, 4, 4, fake, fake, 8, null, null, 5, 3.0, 1.0, fake, null, null, 1, null) == -1
     # ld not a multiple of 4 / smaller than D
-    assert lib.lec_pairs_flat(0, 0, fake, 10, 4, 6, fake, fake, 8, null, null, 5, 3.0, 1.0, fake, null, null, 1, null) == -2
-    assert lib.lec_pairs_flat(0, 0, fake, 10, 8, 4, fake, fake, 8, null, null, 5, 3.0, 1.0, fake, null, null, 1, null) == -2
+    assert lib.lec_pairs_flat(0, 0, fake, fake, 10, 4, 6, fake, fake, 8, null, null, 5, 3.0, 1.0, fake, null, null, 1, null) == -2
+    assert lib.lec_pairs_flat(0, 0, fake, fake, 10, 8, 4, fake, fake, 8, null, null, 5, 3.0, 1.0, fake, null, null, 1, null) == -2
     # unknown geometry / index width
-    assert lib.lec_pairs_flat(7, 0, fake, 10, 4, 4, fake, fake, 8, null, null, 5, 3.0, 1.0, fake, null, null, 1, null) == -3
-    assert lib.lec_pairs_flat(0, 0, fake, 10, 4, 4, fake, fake, 2, null, null, 5, 3.0, 1.0, fake, null, null, 1, null) == -3
+    assert lib.lec_pairs_flat(7, 0, fake, fake, 10, 4, 4, fake, fake, 8, null, null, 5, 3.0, 1.0, fake, null, null, 1, null) == -3
+    assert lib.lec_pairs_flat(0, 0, fake, fake, 10, 4, 4, fake, fake, 2, null, null, 5, 3.0, 1.0, fake, null, null, 1, null) == -3
     # negative count, misaligned rows
-    assert lib.lec_pairs_flat(0, 0, fake, 10, 4, 4, fake, fake, 8, null, null, -1, 3.0, 1.0, fake, null, null, 1, null) == -4
-    assert lib.lec_pairs_flat(0, 0, odd, 10, 4, 4, fake, fake, 8, null, null, 5, 3.0, 1.0, fake, null, null, 1, null) == -5
+    assert lib.lec_pairs_flat(0, 0, fake, fake, 10, 4, 4, fake, fake, 8, null, null, -1, 3.0, 1.0, fake, null, null, 1, null) == -4
+    assert lib.lec_pairs_flat(0, 0, odd, fake, 10, 4, 4, fake, fake, 8, null, null, 5, 3.0, 1.0, fake, null, null, 1, null) == -5
     # empty batch is a no-op success
-    assert lib.lec_pairs_flat(0, 0, fake, 10, 4, 4, null, null, 8, null, null, 0, 3.0, 1.0, null, null, null, 1, null) == 0
-    assert lib.lec_pairs_grouped(1, 1, fake, 10, 4, 4, null, null, null, null, 4, 0, 5, null, null, 0.1, 1.0, null,
+    assert lib.lec_pairs_flat(0, 0, fake, fake, 10, 4, 4, null, null, 8, null, null, 0, 3.0, 1.0, null, null, null, 1, null) == 0
+    assert lib.lec_pairs_grouped(1, 1, fake, fake, 10, 4, 4, null, null, null, null, 4, 0, 5, null, null, 0.1, 1.0, null,
                                  null, null, null, 1, null) == 0
+    # cone energies need the per-row aux terms
+    assert lib.lec_pairs_flat(1, 0, fake, null, 10, 4, 4, fake, fake, 8, null, null, 5, 0.1, 1.0, fake, null, null, 1, null) == -1
+    assert lib.lec_rows_fwd(fake, 5, 4, 1, 9, 3.0, fake, 4, fake, null, 0, null) == -3
     # gradient requested with zero replicas
-    assert lib.lec_pairs_flat(0, 0, fake, 10, 4, 4, fake, fake, 8, null, null, 5, 3.0, 1.0, fake, null, fake, 0, null) == -7
+    assert lib.lec_pairs_flat(0, 0, fake, fake, 10, 4, 4, fake, fake, 8, null, null, 5, 3.0, 1.0, fake, null, fake, 0, null) == -7
     assert lib.lec_rows_bwd(fake, fake, 0, 5, 4, 4, 1, 3.0, fake, 0, null) == -7
     assert lib.lec_score_topk(1, 0, fake, 5, fake, 5, 10, 0.1, null, null, 4, 9, null, fake, null, null) == -6
     assert lib.lec_rsgd_update(fake, fake, 1, 5, 0, 0, 0.1, 0.1, 0, null, null) == -2
@@ -60,4 +63,4 @@ def test_ops_refuse_cpu_tensors():
     with pytest.raises(_native.LecError):
         ops.energy(torch.zeros(4, 3), torch.zeros(4, 3), "euc", 3.0)
     with pytest.raises(_native.LecError):
-        ops.rows_forward(torch.zeros(4, 3), _native.ROWS_EUC_SOFTCLIP, 3.0)
+        ops.rows_forward(torch.zeros(4, 3), _native.ROWS_EUC_SOFTCLIP, 3.0, 'euc')

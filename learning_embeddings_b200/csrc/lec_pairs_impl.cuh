@@ -6,6 +6,9 @@
 
 namespace lec {
 
+#ifndef LEC_GROUPED_MINBLOCKS
+#define LEC_GROUPED_MINBLOCKS 1
+#endif
 enum Core { CORE_EUC32 = 0, CORE_HYP32 = 1, CORE_HYP64 = 2, CORE_OE32 = 3 };
 
 template <int CORE> struct CoreTraits;
@@ -141,7 +144,7 @@ __global__ void __launch_bounds__(kThreads) pairs_flat_kernel(const FlatArgs a) 
 // the 2N corrupted rows need their own reduction.
 // ------------------------------------------------------------------------------------------------
 template <int CORE, int T, int V, bool GRAD>
-__global__ void __launch_bounds__(kThreads) pairs_grouped_kernel(const GroupArgs a) {
+__global__ void __launch_bounds__(kThreads, LEC_GROUPED_MINBLOCKS) pairs_grouped_kernel(const GroupArgs a) {
     using Tr = CoreTraits<CORE>;
     using Acc = typename Tr::Acc;
     const int lane_t = threadIdx.x % T;

@@ -20,6 +20,7 @@ import torch
 
 from . import _native as N
 from . import ops
+from . import sharding
 from .criterion import inner_radius
 
 
@@ -104,8 +105,7 @@ class ConeStep:
         N.check(lib.lec_rows_bwd(N._p(self.table), N._p(self.grad_rows), self.replicas, self.n, self.D, self.ld,
                                  self.row_mode, self.K, N._p(self.grad_table), 0, st), "lec_rows_bwd")
         if multi:
-            torch.distributed.all_reduce(self.grad_table, group=self.pg)
-            torch.distributed.all_reduce(self.loss, group=self.pg)
+            sharding.allreduce_grad_and_loss(self.grad_table, self.loss, self.pg)
         if self.update == "rsgd":
             N.check(lib.lec_rsgd_update(N._p(self.table), N._p(self.grad_table), 1, self.n, self.D, self.D, self.lr,
                                         self.r_in, 0, N._p(self.grad_table), st), "lec_rsgd_update")

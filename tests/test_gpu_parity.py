@@ -477,3 +477,65 @@ def test_scoring_full_size_properties():
     perm = torch.randperm(n_img, generator=gen).to(DEV)
     ip, vp, _ = ops.score_topk(lab_d, img_d[perm], "hyp", 0.1, h["level_start"], h["level_stop"], k=5)
     assert torch.equal(ip, idx[perm]) and torch.equal(vp, val[perm])
+
+
+# ------------------------------------------------------------------------------------------------
+# joint image+label criteria (oe.py / oe_h.py drop-ins)
+# ------------------------------------------------------------------------------------------------
+class _SmallLabelMap:
+    def __init__(self, g):
+        self.level_start = g["level_start"].tolist()
+        self.level_stop = g["level_stop"].tolist()
+        self.levels = [e - s for s, e in zip(self.level_start, self.level_stop)]
+        self.level_names = ["family", "subfamily", "genus", "genus_specific_epithet"]
+        self.n_classes = int(g["n_lab"])
+
+
+@pytest.mark.parametrize("name,geom", [("joint_euc", "euc"), ("joint_euc_ppl", "euc"), ("joint_oe", "oe"),
+                                       ("joint_hyp", "hyp")])
+def test_joint_dropin_reproduces_reference_step(name, geom):
+    from learning_embeddings_b200 import oe as oe_mod
+    from learning_embeddings_b200 import oe_h as oeh_mod
+    g = load_golden(name)
+    lm = _SmallLabelMap(g)
+    Nn, K, alpha, n_lab, nn_ = int(g["N"]), float(g["K"]), float(g["alpha"]), int(g["n_lab"]), int(g["n_nodes"])
+    D, F = g["W0"].shape[1], g["feat"].shape[1]
+    A = np.unpackbits(g["neg_adj"], axis=1)[:, :nn_].astype(bool)
+    ix2node = {i: (i if i < n_lab else "img_%d" % i) for i in range(nn_)}
+    node2ix = {v: k for k, v in ix2node.items()}
+    feats = {ix2node[n_lab + i]: g["feat"][i].tolist() for i in range(nn_ - n_lab)}
+    ppl = bool(g["pick_per_level"])
+    if geom == "euc":
+        crit = oe_mod.EuclideanConesWithImagesHypernymLoss(lm, Nn, feats, alpha, pick_per_level=ppl, K=K)
+        model, fnet = oe_mod.Embedder(D, lm, None, K=K), oe_mod.FeatNet(None, input_dim=F, output_dim=D, K=K)
+    elif geom == "oe":
+        crit = oe_mod.OrderEmbeddingWithImagesHypernymLoss(lm, Nn, feats, alpha, pick_per_level=ppl)
+        model, fnet = oe_mod.Embedder(D, lm, None, K=None), oe_mod.FeatNet(None, input_dim=F, output_dim=D, K=None)
+    else:
+        crit = oeh_mod.EuclideanConesWithImagesHypernymLoss(lm, Nn, feats, alpha, pick_per_level=ppl, K=K)
+        model, fnet = oeh_mod.Embedder(D, lm, None, K=K), oeh_mod.FeatNet(None, input_dim=F, output_dim=D, K=K)
+    with torch.no_grad():
+        model.embeddings.weight.copy_(t(g["W0"]))
+        fnet.fc1.weight.copy_(t(g["fc_w"]))
+        fnet.fc1.bias.copy_(t(g["fc_b"]))
+    model, fnet = model.to(DEV), fnet.to(DEV)
+    crit.set_negative_graph(A, node2ix, ix2node)
+    b_from = [ix2node[int(i)] for i in g["b_from"]]
+    b_to = [ix2node[int(i)] for i in g["b_to"]]
+    random.seed(0)
+    loss, E_pos, E_neg = crit(model, fnet, b_from, b_to, b_from, b_to, torch.ones(len(b_from), dtype=torch.int64), "train")
+    loss.backward()
+    nf, nt = crit.last_negatives
+    B = len(b_from)
+    drawn = []
+    for i in range(B):
+        for p in range(Nn):
+            drawn += [node2ix[nt[2 * Nn * i + p]], node2ix[nf[2 * Nn * i + Nn + p]]]
+    assert drawn == g["drawn"].tolist()  # bit-exact negative indices, labels and images
+    assert tuple(E_neg.shape) == (B, 2 * Nn, 1) and tuple(E_pos.shape) == (B,)
+    np.testing.assert_allclose(E_pos.cpu().numpy(), g["E_pos"].reshape(-1), rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(E_neg.reshape(-1).cpu().numpy(), g["E_neg"].reshape(-1), rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(float(loss), float(g["loss"]), rtol=2e-5)
+    for got, key in ((model.embeddings.weight.grad, "gW"), (fnet.fc1.weight.grad, "g_fc_w"), (fnet.fc1.bias.grad, "g_fc_b")):
+        scale = np.abs(g[key]).max()
+        np.testing.assert_allclose(got.cpu().numpy(), g[key], rtol=2e-3, atol=5e-5 * scale)

@@ -37,6 +37,8 @@ def parse():
     ap.add_argument("--pairs", type=int, default=1 << 21, help="pairs per GPU per step (rounded to whole groups)")
     ap.add_argument("--precision", type=int, default=None, help="0 fp32 core, 1 fp64 core (default: per workload)")
     ap.add_argument("--rotation", type=int, default=0, help="distinct batches to rotate through (0 = enough to exceed L2)")
+    ap.add_argument("--comm", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="multi-GPU gradient exchange: fused peer-memory all-reduce+update, or NCCL")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -233,7 +235,8 @@ def main():
     dev_batches = [b.to(dev) for b in host_batches]
     table = table0.to(dev).clone()
     eng = ConeStep(table, spec["geom"], Nn, groups, K=spec["K"], alpha=spec["alpha"], lr=spec["lr"],
-                   precision=precision, process_group=pg)
+                   precision=precision, process_group=pg, comm=args.comm)
+    cfg["exchange"] = (eng.comm + (" " + eng.comm_note if eng.comm_note else "")) if world > 1 else "none (1 GPU)"
 
     def dev_step(i):
         eng.step_device(*eng._split(dev_batches[i % rotation], groups))
@@ -268,7 +271,7 @@ def main():
     lec_launches = _native.launch_count() - launches0
     elapsed_ms = t0.elapsed_time(t1)
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
-    final_loss = float(eng.loss.item())
+    final_loss = float(eng.global_loss().item())
     if world > 1:
         tt = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
         torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define LEC_ABI_VERSION 3
+#define LEC_ABI_VERSION 4
 
 /* geometry of the energy */
 #define LEC_GEOM_EUC 0 /* EucConesLoss.E_operator, order_embeddings.py:954-969 = oe.py:721-739 (cos-space) */
@@ -54,6 +54,7 @@ extern "C" {
 #define LEC_E_ALIGN     (-5) /* rows / grad_rows base not 16-byte aligned */
 #define LEC_E_K         (-6) /* k out of range for top-k */
 #define LEC_E_REPLICAS  (-7) /* grad_replicas < 1 */
+#define LEC_E_PEERS     (-8) /* world/rank/slot out of range or slot_floats too small */
 #define LEC_MAX_DIM 1024
 #define LEC_MAX_TOPK 8
 #define LEC_MAX_LEVELS 8
@@ -146,6 +147,31 @@ int lec_energy_dense_bwd(int geom, int precision, const float* x, const float* y
  */
 int lec_rsgd_update(float* table, const float* grad, int grad_replicas, int64_t n, int D, int ld_g, float lr,
                     float r_in, int lambda_mode, float* grad_out, void* stream);
+
+/* ---- data-parallel exchange fused into the update (NVLink / NVSwitch peer memory) ------------------
+ * One process per GPU; every rank owns an exchange buffer that all ranks have mapped (CUDA IPC /
+ * torch symmetric memory), laid out as
+ *     float  slot[2][slot_floats]     slot_floats >= n*D + 2, multiple of 4; the last two floats of a
+ *                                     slot hold that rank's loss as one double
+ *     uint32 flag[2][world]           flag[s][r] = tag of the latest step rank r published into slot s
+ * Step t uses slot t % 2 and tag t + 1 (tags increase monotonically; buffers start zeroed).
+ *   1. lec_rows_bwd(..., grad_in = my_buf + slot*slot_floats)   partial table gradient of this rank
+ *   2. lec_p2p_publish     stores the local loss, then release-stores flag[slot][rank] = tag into EVERY
+ *                          rank's buffer over NVLink
+ *   3. lec_rsgd_update_p2p waits (acquire) until all world flags of the slot reach tag, then each row's
+ *                          gradient is read from all ranks' slots over peer loads and summed in rank order
+ *                          (bit-identical on every rank), and the RSGD update of lec_rsgd_update is applied.
+ * This is a one-shot all-reduce fused into the update kernel: no NCCL launch, no extra pass.  It replaces
+ * the implicit reduce_add of nn.DataParallel in the reference (order_embeddings.py:360).
+ * peer_bufs: HOST array of `world` device pointers (rank order).  error_out (optional device int) is set
+ * to 1 if a peer's flag did not arrive within ~4 s (the kernel then returns without updating).
+ */
+int lec_p2p_publish(const double* loss_local, void* const* peer_bufs, int64_t slot_floats, int world, int rank,
+                    int slot, uint32_t tag, void* stream);
+int lec_rsgd_update_p2p(float* table, void* const* peer_bufs, int64_t slot_floats, int world, int rank, int slot,
+                        uint32_t tag, int64_t n, int D, float lr, float r_in, int lambda_mode,
+                        double* loss_global_out, int* error_out, void* stream);
+#define LEC_MAX_PEERS 16
 
 /* ---- all-pairs image x label scoring ------------------------------------------------------------
  * Replaces the per-image loop of JointEmbeddings.calculate_classification_metrics

@@ -14,12 +14,13 @@ LIB_PATH = os.path.join(_HERE, "_lib", "liblec_b200.so")
 GEOM = {"euc": 0, "hyp": 1, "oe": 2}
 ROWS_NONE, ROWS_EUC_SOFTCLIP, ROWS_HYP_SHELL, ROWS_HYP_TANH, ROWS_HYP_TANH_FEAT = 0, 1, 2, 3, 4
 PREC_F32, PREC_F64CORE = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 EXPORTS = (
     "lec_abi_version", "lec_error_string", "lec_launch_count", "lec_rows_fwd", "lec_rows_bwd", "lec_reduce_replicas",
     "lec_pairs_flat",
-    "lec_pairs_grouped", "lec_energy_dense", "lec_energy_dense_bwd", "lec_rsgd_update", "lec_score_topk",
+    "lec_pairs_grouped", "lec_energy_dense", "lec_energy_dense_bwd", "lec_rsgd_update", "lec_p2p_publish",
+    "lec_rsgd_update_p2p", "lec_score_topk",
 )
 
 
@@ -58,6 +59,9 @@ def lib():
         L.lec_energy_dense.argtypes = [c_i, c_i, c_vp, c_vp, c_i64, c_i, c_f, c_vp, c_vp]
         L.lec_energy_dense_bwd.argtypes = [c_i, c_i, c_vp, c_vp, c_vp, c_i64, c_i, c_f, c_vp, c_vp, c_vp]
         L.lec_rsgd_update.argtypes = [c_vp, c_vp, c_i, c_i64, c_i, c_i, c_f, c_f, c_i, c_vp, c_vp]
+        L.lec_p2p_publish.argtypes = [c_vp, c_vp, c_i64, c_i, c_i, c_i, ctypes.c_uint32, c_vp]
+        L.lec_rsgd_update_p2p.argtypes = [c_vp, c_vp, c_i64, c_i, c_i, c_i, ctypes.c_uint32, c_i64, c_i, c_f, c_f, c_i,
+                                          c_vp, c_vp, c_vp]
         L.lec_score_topk.argtypes = [c_i, c_i, c_vp, c_i64, c_vp, c_i64, c_i, c_f, c_vp, c_vp, c_i, c_i, c_vp, c_vp,
                                      c_vp, c_vp]
         for name in EXPORTS:

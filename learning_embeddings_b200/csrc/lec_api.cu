@@ -21,6 +21,9 @@ int rows_fwd_launch(const float*, int64_t, int, int, int, float, float*, int, do
 int rows_bwd_launch(const float*, const float*, int, int64_t, int, int, int, float, float*, int, cudaStream_t);
 int rsgd_launch(float*, const float*, int, int64_t, int, int, float, float, int, float*, cudaStream_t);
 int reduce_replicas_launch(const float*, int, int64_t, float*, cudaStream_t);
+int p2p_publish_launch(const double*, void* const*, int64_t, int, int, int, unsigned, cudaStream_t);
+int rsgd_p2p_launch(float*, void* const*, int64_t, int, int, int, unsigned, int64_t, int, float, float, int, double*, int*,
+                    cudaStream_t);
 int score_launch(int, int, const float*, int64_t, const float*, int64_t, int, float, const int32_t*, const int32_t*,
                  int, int, float*, int32_t*, float*, cudaStream_t);
 
@@ -60,6 +63,7 @@ const char* lec_error_string(int code) {
         case LEC_E_ALIGN: return "rows / grad_rows must be 16-byte aligned";
         case LEC_E_K: return "top-k: need 1 <= k <= 8 and 1 <= n_levels <= 8";
         case LEC_E_REPLICAS: return "grad_replicas must be >= 1";
+        case LEC_E_PEERS: return "peer exchange: need 1 <= world <= 16, 0 <= rank < world, slot in {0,1}, slot_floats >= n*D+2 and % 4 == 0";
     }
     if (code > 0) return cudaGetErrorString((cudaError_t)code);
     return "unknown lec error";
@@ -181,6 +185,34 @@ int lec_rsgd_update(float* table, const float* grad, int grad_replicas, int64_t 
     if (D < 1 || D > LEC_MAX_DIM || ld_g < D) return LEC_E_DIM;
     if (lambda_mode != 0 && lambda_mode != 1) return LEC_E_ENUM;
     return rsgd_launch(table, grad, grad_replicas, n, D, ld_g, lr, r_in, lambda_mode, grad_out, (cudaStream_t)stream);
+}
+
+static int check_peers(void* const* peer_bufs, int64_t slot_floats, int world, int rank, int slot) {
+    if (!peer_bufs) return LEC_E_NULL;
+    if (world < 1 || world > LEC_MAX_PEERS || rank < 0 || rank >= world || (slot != 0 && slot != 1)) return LEC_E_PEERS;
+    if (slot_floats < 4 || (slot_floats & 3)) return LEC_E_PEERS;
+    for (int p = 0; p < world; ++p)
+        if (!peer_bufs[p]) return LEC_E_NULL;
+    return 0;
+}
+
+int lec_p2p_publish(const double* loss_local, void* const* peer_bufs, int64_t slot_floats, int world, int rank, int slot,
+                    uint32_t tag, void* stream) {
+    if (int e = check_peers(peer_bufs, slot_floats, world, rank, slot)) return e;
+    return p2p_publish_launch(loss_local, peer_bufs, slot_floats, world, rank, slot, tag, (cudaStream_t)stream);
+}
+
+int lec_rsgd_update_p2p(float* table, void* const* peer_bufs, int64_t slot_floats, int world, int rank, int slot,
+                        uint32_t tag, int64_t n, int D, float lr, float r_in, int lambda_mode, double* loss_global_out,
+                        int* error_out, void* stream) {
+    if (!table) return LEC_E_NULL;
+    if (int e = check_peers(peer_bufs, slot_floats, world, rank, slot)) return e;
+    if (n < 0) return LEC_E_SIZE;
+    if (D < 1 || D > LEC_MAX_DIM) return LEC_E_DIM;
+    if (slot_floats < n * D + 2) return LEC_E_PEERS;
+    if (lambda_mode != 0 && lambda_mode != 1) return LEC_E_ENUM;
+    return rsgd_p2p_launch(table, peer_bufs, slot_floats, world, rank, slot, tag, n, D, lr, r_in, lambda_mode,
+                           loss_global_out, error_out, (cudaStream_t)stream);
 }
 
 int lec_score_topk(int geom, int precision, const float* labels, int64_t L, const float* images, int64_t N, int D,

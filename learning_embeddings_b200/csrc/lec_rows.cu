@@ -167,13 +167,56 @@ __global__ void __launch_bounds__(kThreads) rows_bwd_kernel(const RowsArgs a) {
 // reference's; the row-wide sums and the Moebius coefficients built from them are carried in fp64 so
 // the update stays accurate when |w| is close to 1 (the denominators there cancel heavily).
 // ------------------------------------------------------------------------------------------------
+constexpr int kMaxPeers = 16;
+
 struct RsgdArgs {
     float* table; const float* grad; int64_t n; int D; int ld_g; float lr; float r_in; int lambda_mode;
     float* grad_out; int replicas; int64_t replica_stride;
+    // peer-memory mode (lec_rsgd_update_p2p): the gradient is the sum over ranks of peer[p][row*D + d]
+    int world; int rank; int slot; unsigned tag; int64_t slot_floats;
+    const float* peer[kMaxPeers]; double* loss_out; int* error_out;
 };
 
-template <int TT, int E>
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// layout of one rank's exchange buffer: [2 slots][slot_floats] fp32, then flags[2][world] u32
+__device__ __forceinline__ const unsigned* p2p_flags(const float* buf, int64_t slot_floats) {
+    return reinterpret_cast<const unsigned*>(buf + 2 * slot_floats);
+}
+
+template <int TT, int E, bool P2P>
 __global__ void __launch_bounds__(kThreads) rsgd_kernel(const RsgdArgs a) {
+    if (P2P) {
+        // wait until every rank has published its partial gradient of this step into slot a.slot
+        __shared__ int s_ok;
+        if (threadIdx.x == 0) {
+            const unsigned* flags = p2p_flags(a.peer[a.rank], a.slot_floats) + a.slot * a.world;
+            int ok = 1;
+            const long long t0 = clock64();
+            for (int p = 0; p < a.world; ++p) {
+                while (ld_acquire_sys(flags + p) < a.tag) {
+                    if (clock64() - t0 > 8000000000LL) { ok = 0; break; }   // ~4 s: a peer died; do not hang
+                }
+            }
+            if (!ok && a.error_out) atomicExch(a.error_out, 1);
+            s_ok = ok;
+            if (blockIdx.x == 0 && a.loss_out) {
+                double l = 0.0;
+                for (int p = 0; p < a.world; ++p)
+                    l += __ldcv(reinterpret_cast<const double*>(a.peer[p] + a.slot * a.slot_floats + a.slot_floats - 2));
+                *a.loss_out = l;
+            }
+        }
+        __syncthreads();
+        if (!s_ok) return;
+    }
     const int lane = threadIdx.x % TT;
     const int64_t n_teams = (int64_t)gridDim.x * (kThreads / TT);
     const int64_t team = (int64_t)blockIdx.x * (kThreads / TT) + threadIdx.x / TT;
@@ -191,7 +234,15 @@ __global__ void __launch_bounds__(kThreads) rsgd_kernel(const RsgdArgs a) {
         for (int j = 0; j < E; ++j) {
             const int d = lane + TT * j;
             wv[j] = (d < D) ? w[d] : 0.f;
-            gv[j] = (d < D) ? rsum(g + d, a.replicas, a.replica_stride) : 0.f;
+            if (P2P) {
+                float acc = 0.f;
+                if (d < D)
+                    for (int p = 0; p < a.world; ++p)   // fixed rank order: every rank computes the identical sum
+                        acc += __ldcv(a.peer[p] + a.slot * a.slot_floats + rc * (int64_t)D + d);
+                gv[j] = acc;
+            } else {
+                gv[j] = (d < D) ? rsum(g + d, a.replicas, a.replica_stride) : 0.f;
+            }
             uu += (double)wv[j] * (double)wv[j];
         }
         uu = tsumd<TT>(uu);
@@ -331,12 +382,61 @@ int rows_bwd_launch(const float* in, const float* grad_rows, int replicas, int64
 
 template <int TT, int E>
 static void rsgd_go(const RsgdArgs& a, cudaStream_t st) {
-    rsgd_kernel<TT, E><<<grid_rows(a.n, TT), kThreads, 0, st>>>(a);
+    if (a.world > 0) rsgd_kernel<TT, E, true><<<grid_rows(a.n, TT), kThreads, 0, st>>>(a);
+    else rsgd_kernel<TT, E, false><<<grid_rows(a.n, TT), kThreads, 0, st>>>(a);
 }
+
+static int rsgd_dispatch(const RsgdArgs& a, cudaStream_t st);
 
 int rsgd_launch(float* table, const float* grad, int replicas, int64_t n, int D, int ld_g, float lr, float r_in,
                 int lambda_mode, float* grad_out, cudaStream_t st) {
-    RsgdArgs a{table, grad, n, D, ld_g, lr, r_in, lambda_mode, grad_out, replicas, n * (int64_t)ld_g};
+    RsgdArgs a{};
+    a.table = table; a.grad = grad; a.n = n; a.D = D; a.ld_g = ld_g; a.lr = lr; a.r_in = r_in;
+    a.lambda_mode = lambda_mode; a.grad_out = grad_out; a.replicas = replicas; a.replica_stride = n * (int64_t)ld_g;
+    a.world = 0;
+    return rsgd_dispatch(a, st);
+}
+
+// ---- peer-memory exchange (NVLink / NVSwitch P2P) ------------------------------------------------
+// publish: stores this rank's loss next to its partial gradient (already written into the slot by
+// lec_rows_bwd), then raises flag[slot][rank] = tag in EVERY rank's buffer with release semantics.
+__global__ void p2p_publish_kernel(const double* loss_local, RsgdArgs a) {
+    float* mine = const_cast<float*>(a.peer[a.rank]) + a.slot * a.slot_floats;
+    if (threadIdx.x == 0 && loss_local)
+        *reinterpret_cast<double*>(mine + a.slot_floats - 2) = *loss_local;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < a.world) {
+        unsigned* flags = const_cast<unsigned*>(p2p_flags(a.peer[threadIdx.x], a.slot_floats)) + a.slot * a.world;
+        st_release_sys(flags + a.rank, a.tag);
+    }
+}
+
+int p2p_publish_launch(const double* loss_local, void* const* peer_bufs, int64_t slot_floats, int world, int rank,
+                       int slot, unsigned tag, cudaStream_t st) {
+    RsgdArgs a{};
+    a.world = world; a.rank = rank; a.slot = slot; a.tag = tag; a.slot_floats = slot_floats;
+    for (int p = 0; p < world; ++p) a.peer[p] = static_cast<const float*>(peer_bufs[p]);
+    p2p_publish_kernel<<<1, 32, 0, st>>>(loss_local, a);
+    ++g_launches;
+    return (int)cudaGetLastError();
+}
+
+int rsgd_p2p_launch(float* table, void* const* peer_bufs, int64_t slot_floats, int world, int rank, int slot,
+                    unsigned tag, int64_t n, int D, float lr, float r_in, int lambda_mode, double* loss_out,
+                    int* error_out, cudaStream_t st) {
+    RsgdArgs a{};
+    a.table = table; a.grad = nullptr; a.n = n; a.D = D; a.ld_g = D; a.lr = lr; a.r_in = r_in;
+    a.lambda_mode = lambda_mode; a.grad_out = nullptr; a.replicas = 1; a.replica_stride = 0;
+    a.world = world; a.rank = rank; a.slot = slot; a.tag = tag; a.slot_floats = slot_floats;
+    a.loss_out = loss_out; a.error_out = error_out;
+    for (int p = 0; p < world; ++p) a.peer[p] = static_cast<const float*>(peer_bufs[p]);
+    return rsgd_dispatch(a, st);
+}
+
+static int rsgd_dispatch(const RsgdArgs& a, cudaStream_t st) {
+    const int64_t n = a.n;
+    const int D = a.D;
     if (n == 0) return 0;
     // E elements per lane in registers; TT lanes per row
     if (D <= 1) rsgd_go<1, 1>(a, st);

@@ -33,7 +33,7 @@ def pack_index_block(pos_from, pos_to, neg_to, neg_from, pin=True):
 
 class ConeStep:
     def __init__(self, table, geom, n_neg, max_groups, K=None, alpha=1.0, lr=1e-3, row_mode=None, update="auto",
-                 precision=ops.PREC_F64CORE, process_group=None, replicas=None):
+                 precision=ops.PREC_F64CORE, process_group=None, replicas=None, comm="auto"):
         N.require_cuda(table)
         if table.dtype != torch.float32 or not table.is_contiguous():
             raise N.LecError("ConeStep: table must be a contiguous float32 CUDA tensor (updated in place)")
@@ -64,6 +64,20 @@ class ConeStep:
         self.idx_dev = torch.empty(self.max_groups * (2 + 2 * self.n_neg), device=dev, dtype=torch.int32)
         self.loss_host = torch.zeros(1, dtype=torch.float64).pin_memory()
         self.kernel_events = None  # optional (start, stop) pairs around the pair kernel, set by bench
+        # multi-GPU exchange: "p2p" = one-shot all-reduce over NVLink peer memory fused into the RSGD kernel,
+        # "nccl" = all_reduce of the table gradient; "auto" tries p2p for the RSGD update and falls back
+        self.comm, self.comm_note, self.px = "none", "", None
+        if self.pg is not None and torch.distributed.get_world_size(self.pg) > 1:
+            self.comm = "nccl"
+            if comm in ("auto", "p2p") and self.update == "rsgd":
+                try:
+                    self.px = sharding.PeerExchange(self.n, self.D, dev, self.pg)
+                    self.comm = "p2p"
+                except Exception as e:  # noqa: BLE001 -- any failure of the symmetric-memory setup
+                    if comm == "p2p":
+                        raise
+                    self.comm_note = "p2p unavailable (%s: %s)" % (type(e).__name__, str(e)[:120])
+            self.loss_global = torch.zeros(1, device=dev, dtype=torch.float64)
 
     # -- pieces ---------------------------------------------------------------------------------
     def _split(self, blk, B):
@@ -101,11 +115,29 @@ class ConeStep:
             N.check(lib.lec_rsgd_update(N._p(self.table), N._p(self.grad_rows), self.replicas, self.n, self.D, self.ld,
                                         self.lr, self.r_in, 0, N._p(self.grad_table), st), "lec_rsgd_update")
             return
+        if multi and self.comm == "p2p":
+            import ctypes
+            px = self.px
+            slot, tag = px.slot_and_tag()
+            # partial d/dtable of this rank straight into its exchange slot, publish, fused reduce + update
+            N.check(lib.lec_rows_bwd(N._p(self.table), N._p(self.grad_rows), self.replicas, self.n, self.D, self.ld,
+                                     self.row_mode, self.K, ctypes.c_void_p(px.my_slot_ptr(slot)), 0, st),
+                    "lec_rows_bwd")
+            N.check(lib.lec_p2p_publish(N._p(self.loss), px.peer_ptrs, px.slot_floats, px.world, px.rank, slot, tag, st),
+                    "lec_p2p_publish")
+            N.check(lib.lec_rsgd_update_p2p(N._p(self.table), px.peer_ptrs, px.slot_floats, px.world, px.rank, slot,
+                                            tag, self.n, self.D, self.lr, self.r_in, 0, N._p(self.loss_global),
+                                            N._p(px.error), st), "lec_rsgd_update_p2p")
+            px.step += 1
+            return
         # d/dtable = J^T (sum of replicas); it is linear, so ranks can be summed after it
         N.check(lib.lec_rows_bwd(N._p(self.table), N._p(self.grad_rows), self.replicas, self.n, self.D, self.ld,
                                  self.row_mode, self.K, N._p(self.grad_table), 0, st), "lec_rows_bwd")
         if multi:
-            sharding.allreduce_grad_and_loss(self.grad_table, self.loss, self.pg)
+            # one collective per step: the table gradient.  The scalar loss stays rank-local until someone
+            # asks for it (global_loss), so logging does not put a second latency-bound all-reduce on the
+            # critical path.
+            torch.distributed.all_reduce(self.grad_table, group=self.pg)
         if self.update == "rsgd":
             N.check(lib.lec_rsgd_update(N._p(self.table), N._p(self.grad_table), 1, self.n, self.D, self.D, self.lr,
                                         self.r_in, 0, N._p(self.grad_table), st), "lec_rsgd_update")
@@ -113,6 +145,17 @@ class ConeStep:
             self.table.add_(self.grad_table, alpha=-self.lr)
         elif self.update != "none":
             raise N.LecError("unknown update rule %r" % (self.update,))
+
+    def global_loss(self):
+        """Loss of the latest step summed over ranks (float64 tensor on the device)."""
+        if self.comm == "p2p":
+            if int(self.px.error.item()) != 0:
+                raise N.LecError("peer exchange timed out: a rank did not publish its gradient")
+            return self.loss_global.clone()
+        out = self.loss.clone()
+        if self.pg is not None and torch.distributed.get_world_size(self.pg) > 1:
+            torch.distributed.all_reduce(out, group=self.pg)
+        return out
 
     # -- whole steps ----------------------------------------------------------------------------
     def step_device(self, pos_from, pos_to, neg_to, neg_from, w_pos=None, w_neg=None):

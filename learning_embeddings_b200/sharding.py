@@ -27,3 +27,39 @@ def allreduce_grad_and_loss(grad_table, loss, group=None):
         dist.all_reduce(grad_table, op=dist.ReduceOp.SUM, group=group)
         dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
     return grad_table, loss
+
+
+class PeerExchange:
+    """Exchange buffers for the fused all-reduce + RSGD update (include/lec_b200.h: lec_p2p_publish,
+    lec_rsgd_update_p2p): one buffer per rank, mapped by every rank through torch symmetric memory
+    (CUDA IPC over NVLink / NVSwitch).  Layout: float slot[2][slot_floats]; uint32 flag[2][world]."""
+
+    def __init__(self, n, D, device, group):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm_mem
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.slot_floats = (n * D + 2 + 3) // 4 * 4
+        total = 2 * self.slot_floats + 2 * self.world
+        total = (total + 3) // 4 * 4
+        self.buf = symm_mem.empty(total, dtype=torch.float32, device=device)
+        name = getattr(group, "group_name", None)
+        try:
+            self.handle = symm_mem.rendezvous(self.buf, group=name if name is not None else group)
+        except TypeError:
+            self.handle = symm_mem.rendezvous(self.buf, name)
+        self.buf.zero_()
+        torch.cuda.synchronize(device)
+        dist.barrier(group)
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        if len(ptrs) != self.world or ptrs[self.rank] != self.buf.data_ptr():
+            raise RuntimeError("symmetric memory rendezvous returned unexpected peer pointers")
+        self.peer_ptrs = (ctypes.c_void_p * self.world)(*ptrs)
+        self.step = 0
+        self.error = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def slot_and_tag(self):
+        return self.step % 2, self.step + 1
+
+    def my_slot_ptr(self, slot):
+        return self.buf.data_ptr() + 4 * slot * self.slot_floats

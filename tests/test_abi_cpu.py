@@ -19,11 +19,11 @@ def header_symbols():
 def test_library_exports_every_header_symbol():
     lib = _native.lib()
     names = header_symbols()
-    assert len(names) >= 12
+    assert len(names) >= 14
     for n in names:
         assert hasattr(lib, n), n
     assert sorted(_native.EXPORTS) == names
-    assert lib.lec_abi_version() == _native.ABI_VERSION == 3
+    assert lib.lec_abi_version() == _native.ABI_VERSION == 4
 
 
 def test_argument_validation_codes():
@@ -54,6 +54,12 @@ def test_argument_validation_codes():
     assert lib.lec_rows_bwd(fake, fake, 0, 5, 4, 4, 1, 3.0, fake, 0, null) == -7
     assert lib.lec_score_topk(1, 0, fake, 5, fake, 5, 10, 0.1, null, null, 4, 9, null, fake, null, null) == -6
     assert lib.lec_rsgd_update(fake, fake, 1, 5, 0, 0, 0.1, 0.1, 0, null, null) == -2
+    # peer exchange
+    arr = (ctypes.c_void_p * 2)(0x1000, 0x2000)
+    assert lib.lec_p2p_publish(null, arr, 64, 2, 5, 0, 1, null) == -8        # rank out of range
+    assert lib.lec_p2p_publish(null, arr, 63, 2, 0, 0, 1, null) == -8        # slot_floats % 4
+    assert lib.lec_rsgd_update_p2p(fake, arr, 8, 2, 0, 0, 1, 10, 4, 0.1, 0.1, 0, null, null, null) == -8  # slot too small
+    assert lib.lec_rsgd_update_p2p(fake, null, 64, 2, 0, 0, 1, 10, 4, 0.1, 0.1, 0, null, null, null) == -1
     assert b"16-byte" in lib.lec_error_string(-5)
 
 

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define LEC_ABI_VERSION 4
+#define LEC_ABI_VERSION 5
 
 /* geometry of the energy */
 #define LEC_GEOM_EUC 0 /* EucConesLoss.E_operator, order_embeddings.py:954-969 = oe.py:721-739 (cos-space) */
@@ -76,9 +76,10 @@ int64_t lec_launch_count(void);
  *             lec_pairs_flat / lec_pairs_grouped for LEC_GEOM_EUC and LEC_GEOM_HYP.
  *   zero_out  optional [zero_replicas, n, ld] buffer cleared in the same pass (the gradient
  *             accumulator of the pair kernels), may be NULL
+ *   zero_scalar optional double[1] cleared in the same pass (the loss accumulator), may be NULL
  */
 int lec_rows_fwd(const float* in, int64_t n, int D, int mode, int geom, float K, float* rows_out, int ld,
-                 double* aux_out, float* zero_out, int zero_replicas, void* stream);
+                 double* aux_out, float* zero_out, int zero_replicas, double* zero_scalar, void* stream);
 
 /* Vector-Jacobian product of lec_rows_fwd: grad_in[n, D] (=|+=) J^T grad_rows[n, ld].
  * grad_rows is [grad_replicas, n, ld]; the replicas are summed on the fly.
@@ -172,6 +173,34 @@ int lec_rsgd_update_p2p(float* table, void* const* peer_bufs, int64_t slot_float
                         uint32_t tag, int64_t n, int D, float lr, float r_in, int lambda_mode,
                         double* loss_global_out, int* error_out, void* stream);
 #define LEC_MAX_PEERS 16
+
+/* ---- one whole training step in one call ---------------------------------------------------------
+ * The launch sequence of one label-only cone step (what one iteration of the reference's
+ * pass_samples('train') loop does between zero_grad() and the weight update, order_embeddings_h.py:752-775 /
+ * order_embeddings.py:619-635) issued from C, so the host pays one FFI call per step instead of one per
+ * kernel:
+ *     lec_rows_fwd (clears grad_rows and *loss) -> lec_pairs_grouped ->
+ *       world <= 1, update == RSGD on straight-through rows : lec_rsgd_update on the replicas
+ *       world <= 1, otherwise                               : lec_rows_bwd [-> lec_rsgd_update]
+ *       world  > 1                                          : lec_rows_bwd into the exchange slot ->
+ *                                                             lec_p2p_publish -> lec_rsgd_update_p2p
+ * update: 0 none (gradient left in grad_table), 1 RSGD.  ev_pairs_start/stop: optional cudaEvent_t recorded
+ * around the pair kernel (for the roofline timing).  All pointers as in the individual entry points.
+ */
+typedef struct lec_step {
+    int geom, precision, row_mode, update, lambda_mode;
+    float K, alpha, lr, r_in;
+    float* table; int64_t n; int D; int ld;
+    float* rows; double* aux; float* grad_rows; int grad_replicas; float* grad_table;
+    const void* pos_from; const void* pos_to; const void* neg_to; const void* neg_from; int idx_bytes;
+    int64_t B; int N;
+    const float* w_pos; const float* w_neg;
+    float* E_pos; float* E_neg; double* loss;
+    void* const* peer_bufs; int64_t slot_floats; int world, rank, slot; uint32_t tag;
+    double* loss_global; int* error;
+    void* ev_pairs_start; void* ev_pairs_stop;
+} lec_step_t;
+int lec_cone_step(const lec_step_t* s, void* stream);
 
 /* ---- all-pairs image x label scoring ------------------------------------------------------------
  * Replaces the per-image loop of JointEmbeddings.calculate_classification_metrics

@@ -14,18 +14,39 @@ LIB_PATH = os.path.join(_HERE, "_lib", "liblec_b200.so")
 GEOM = {"euc": 0, "hyp": 1, "oe": 2}
 ROWS_NONE, ROWS_EUC_SOFTCLIP, ROWS_HYP_SHELL, ROWS_HYP_TANH, ROWS_HYP_TANH_FEAT = 0, 1, 2, 3, 4
 PREC_F32, PREC_F64CORE = 0, 1
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 EXPORTS = (
     "lec_abi_version", "lec_error_string", "lec_launch_count", "lec_rows_fwd", "lec_rows_bwd", "lec_reduce_replicas",
     "lec_pairs_flat",
     "lec_pairs_grouped", "lec_energy_dense", "lec_energy_dense_bwd", "lec_rsgd_update", "lec_p2p_publish",
-    "lec_rsgd_update_p2p", "lec_score_topk",
+    "lec_rsgd_update_p2p", "lec_cone_step", "lec_score_topk",
 )
 
 
 class LecError(RuntimeError):
     pass
+
+
+class LecStep(ctypes.Structure):
+    """lec_step_t of include/lec_b200.h."""
+    _fields_ = [
+        ("geom", ctypes.c_int), ("precision", ctypes.c_int), ("row_mode", ctypes.c_int), ("update", ctypes.c_int),
+        ("lambda_mode", ctypes.c_int),
+        ("K", ctypes.c_float), ("alpha", ctypes.c_float), ("lr", ctypes.c_float), ("r_in", ctypes.c_float),
+        ("table", ctypes.c_void_p), ("n", ctypes.c_int64), ("D", ctypes.c_int), ("ld", ctypes.c_int),
+        ("rows", ctypes.c_void_p), ("aux", ctypes.c_void_p), ("grad_rows", ctypes.c_void_p),
+        ("grad_replicas", ctypes.c_int), ("grad_table", ctypes.c_void_p),
+        ("pos_from", ctypes.c_void_p), ("pos_to", ctypes.c_void_p), ("neg_to", ctypes.c_void_p),
+        ("neg_from", ctypes.c_void_p), ("idx_bytes", ctypes.c_int),
+        ("B", ctypes.c_int64), ("N", ctypes.c_int),
+        ("w_pos", ctypes.c_void_p), ("w_neg", ctypes.c_void_p),
+        ("E_pos", ctypes.c_void_p), ("E_neg", ctypes.c_void_p), ("loss", ctypes.c_void_p),
+        ("peer_bufs", ctypes.c_void_p), ("slot_floats", ctypes.c_int64), ("world", ctypes.c_int),
+        ("rank", ctypes.c_int), ("slot", ctypes.c_int), ("tag", ctypes.c_uint32),
+        ("loss_global", ctypes.c_void_p), ("error", ctypes.c_void_p),
+        ("ev_pairs_start", ctypes.c_void_p), ("ev_pairs_stop", ctypes.c_void_p),
+    ]
 
 
 _lib = None
@@ -49,7 +70,7 @@ def lib():
         L.lec_error_string.restype = ctypes.c_char_p
         L.lec_error_string.argtypes = [c_i]
         L.lec_launch_count.restype = c_i64
-        L.lec_rows_fwd.argtypes = [c_vp, c_i64, c_i, c_i, c_i, c_f, c_vp, c_i, c_vp, c_vp, c_i, c_vp]
+        L.lec_rows_fwd.argtypes = [c_vp, c_i64, c_i, c_i, c_i, c_f, c_vp, c_i, c_vp, c_vp, c_i, c_vp, c_vp]
         L.lec_rows_bwd.argtypes = [c_vp, c_vp, c_i, c_i64, c_i, c_i, c_i, c_f, c_vp, c_i, c_vp]
         L.lec_reduce_replicas.argtypes = [c_vp, c_i, c_i64, c_vp, c_vp]
         L.lec_pairs_flat.argtypes = [c_i, c_i, c_vp, c_vp, c_i64, c_i, c_i, c_vp, c_vp, c_i, c_vp, c_vp, c_i64, c_f, c_f,
@@ -62,6 +83,7 @@ def lib():
         L.lec_p2p_publish.argtypes = [c_vp, c_vp, c_i64, c_i, c_i, c_i, ctypes.c_uint32, c_vp]
         L.lec_rsgd_update_p2p.argtypes = [c_vp, c_vp, c_i64, c_i, c_i, c_i, ctypes.c_uint32, c_i64, c_i, c_f, c_f, c_i,
                                           c_vp, c_vp, c_vp]
+        L.lec_cone_step.argtypes = [ctypes.POINTER(LecStep), c_vp]
         L.lec_score_topk.argtypes = [c_i, c_i, c_vp, c_i64, c_vp, c_i64, c_i, c_f, c_vp, c_vp, c_i, c_i, c_vp, c_vp,
                                      c_vp, c_vp]
         for name in EXPORTS:

@@ -17,7 +17,7 @@ int launch_dense_hyp32(const DenseArgs&, bool, cudaStream_t);
 int launch_dense_hyp64(const DenseArgs&, bool, cudaStream_t);
 int launch_dense_oe32(const DenseArgs&, bool, cudaStream_t);
 
-int rows_fwd_launch(const float*, int64_t, int, int, int, float, float*, int, double*, float*, int, cudaStream_t);
+int rows_fwd_launch(const float*, int64_t, int, int, int, float, float*, int, double*, float*, int, double*, cudaStream_t);
 int rows_bwd_launch(const float*, const float*, int, int64_t, int, int, int, float, float*, int, cudaStream_t);
 int rsgd_launch(float*, const float*, int, int64_t, int, int, float, float, int, float*, cudaStream_t);
 int reduce_replicas_launch(const float*, int, int64_t, float*, cudaStream_t);
@@ -70,7 +70,7 @@ const char* lec_error_string(int code) {
 }
 
 int lec_rows_fwd(const float* in, int64_t n, int D, int mode, int geom, float K, float* rows_out, int ld,
-                 double* aux_out, float* zero_out, int zero_replicas, void* stream) {
+                 double* aux_out, float* zero_out, int zero_replicas, double* zero_scalar, void* stream) {
     if (zero_out && zero_replicas < 1) return LEC_E_REPLICAS;
     if (aux_out && (geom < LEC_GEOM_EUC || geom > LEC_GEOM_OE)) return LEC_E_ENUM;
     if (aux_out && (reinterpret_cast<uintptr_t>(aux_out) & 15)) return LEC_E_ALIGN;
@@ -78,7 +78,8 @@ int lec_rows_fwd(const float* in, int64_t n, int D, int mode, int geom, float K,
     if (n < 0) return LEC_E_SIZE;
     if (mode < LEC_ROWS_NONE || mode > LEC_ROWS_HYP_TANH_FEAT) return LEC_E_ENUM;
     if (int e = check_rows(rows_out, D, ld)) return e;
-    return rows_fwd_launch(in, n, D, mode, geom, K, rows_out, ld, aux_out, zero_out, zero_replicas, (cudaStream_t)stream);
+    return rows_fwd_launch(in, n, D, mode, geom, K, rows_out, ld, aux_out, zero_out, zero_replicas, zero_scalar,
+                           (cudaStream_t)stream);
 }
 
 int lec_rows_bwd(const float* in, const float* grad_rows, int grad_replicas, int64_t n, int D, int ld, int mode, float K,
@@ -213,6 +214,41 @@ int lec_rsgd_update_p2p(float* table, void* const* peer_bufs, int64_t slot_float
     if (lambda_mode != 0 && lambda_mode != 1) return LEC_E_ENUM;
     return rsgd_p2p_launch(table, peer_bufs, slot_floats, world, rank, slot, tag, n, D, lr, r_in, lambda_mode,
                            loss_global_out, error_out, (cudaStream_t)stream);
+}
+
+int lec_cone_step(const lec_step_t* s, void* stream) {
+    if (!s) return LEC_E_NULL;
+    if (s->update != 0 && s->update != 1) return LEC_E_ENUM;
+    if (!s->grad_rows || !s->loss) return LEC_E_NULL;
+    int e = lec_rows_fwd(s->table, s->n, s->D, s->row_mode, s->geom, s->K, s->rows, s->ld, s->aux, s->grad_rows,
+                         s->grad_replicas, s->loss, stream);
+    if (e) return e;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (s->ev_pairs_start) cudaEventRecord((cudaEvent_t)s->ev_pairs_start, st);
+    e = lec_pairs_grouped(s->geom, s->precision, s->rows, s->aux, s->n, s->D, s->ld, s->pos_from, s->pos_to, s->neg_to,
+                          s->neg_from, s->idx_bytes, s->B, s->N, s->w_pos, s->w_neg, s->K, s->alpha, s->E_pos, s->E_neg,
+                          s->loss, s->grad_rows, s->grad_replicas, stream);
+    if (s->ev_pairs_stop) cudaEventRecord((cudaEvent_t)s->ev_pairs_stop, st);
+    if (e) return e;
+    if (s->world > 1) {
+        if (s->update != 1) return LEC_E_ENUM;  // the fused exchange exists for the RSGD update
+        if (int pe = check_peers(s->peer_bufs, s->slot_floats, s->world, s->rank, s->slot)) return pe;
+        if (s->slot_floats < s->n * s->D + 2) return LEC_E_PEERS;
+        float* mine = static_cast<float*>(s->peer_bufs[s->rank]) + (int64_t)s->slot * s->slot_floats;
+        e = lec_rows_bwd(s->table, s->grad_rows, s->grad_replicas, s->n, s->D, s->ld, s->row_mode, s->K, mine, 0, stream);
+        if (e) return e;
+        e = lec_p2p_publish(s->loss, s->peer_bufs, s->slot_floats, s->world, s->rank, s->slot, s->tag, stream);
+        if (e) return e;
+        return lec_rsgd_update_p2p(s->table, s->peer_bufs, s->slot_floats, s->world, s->rank, s->slot, s->tag, s->n, s->D,
+                                   s->lr, s->r_in, s->lambda_mode, s->loss_global, s->error, stream);
+    }
+    if (s->update == 1 && s->row_mode == LEC_ROWS_HYP_SHELL)
+        return lec_rsgd_update(s->table, s->grad_rows, s->grad_replicas, s->n, s->D, s->ld, s->lr, s->r_in, s->lambda_mode,
+                               s->grad_table, stream);
+    if (!s->grad_table) return LEC_E_NULL;
+    e = lec_rows_bwd(s->table, s->grad_rows, s->grad_replicas, s->n, s->D, s->ld, s->row_mode, s->K, s->grad_table, 0, stream);
+    if (e || s->update == 0) return e;
+    return lec_rsgd_update(s->table, s->grad_table, 1, s->n, s->D, s->D, s->lr, s->r_in, s->lambda_mode, s->grad_table, stream);
 }
 
 int lec_score_topk(int geom, int precision, const float* labels, int64_t L, const float* images, int64_t N, int D,

@@ -9,7 +9,7 @@ namespace lec {
 
 struct RowsArgs {
     const float* in; int64_t n; int D; int mode; int geom; float K; float r_in; float c0;
-    float* out; int ld; double* aux; float* zero_out; int replicas; int64_t replica_stride;
+    float* out; int ld; double* aux; float* zero_out; int replicas; int64_t replica_stride; double* zero_scalar;
     const float* grad_rows; float* grad_in; int accumulate;
 };
 
@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(kThreads) rows_fwd_kernel(const RowsArgs a) {
     const int64_t team = (int64_t)blockIdx.x * (kThreads / TT) + threadIdx.x / TT;
     const int64_t iters = (a.n + n_teams - 1) / n_teams;
     const int D = a.D;
+    if (a.zero_scalar && blockIdx.x == 0 && threadIdx.x == 0) *a.zero_scalar = 0.0;
     for (int64_t it = 0; it < iters; ++it) {
         const int64_t row = team + it * n_teams;
         const bool valid = row < a.n;
@@ -358,8 +359,9 @@ static void hyp_constants(float K, float& r_in, float& c0) {
 }
 
 int rows_fwd_launch(const float* in, int64_t n, int D, int mode, int geom, float K, float* out, int ld, double* aux,
-                    float* zero_out, int zero_replicas, cudaStream_t st) {
+                    float* zero_out, int zero_replicas, double* zero_scalar, cudaStream_t st) {
     RowsArgs a{};
+    a.zero_scalar = zero_scalar;
     a.in = in; a.n = n; a.D = D; a.mode = mode; a.geom = geom; a.K = K; a.out = out; a.ld = ld; a.aux = aux;
     a.zero_out = zero_out; a.replicas = zero_replicas; a.replica_stride = n * (int64_t)ld;
     hyp_constants(K, a.r_in, a.c0);

@@ -64,6 +64,7 @@ class ConeStep:
         self.idx_dev = torch.empty(self.max_groups * (2 + 2 * self.n_neg), device=dev, dtype=torch.int32)
         self.loss_host = torch.zeros(1, dtype=torch.float64).pin_memory()
         self.kernel_events = None  # optional (start, stop) pairs around the pair kernel, set by bench
+        self._struct = None
         # multi-GPU exchange: "p2p" = one-shot all-reduce over NVLink peer memory fused into the RSGD kernel,
         # "nccl" = all_reduce of the table gradient; "auto" tries p2p for the RSGD update and falls back
         self.comm, self.comm_note, self.px = "none", "", None
@@ -91,9 +92,8 @@ class ConeStep:
         if B > self.max_groups:
             raise N.LecError("batch of %d positives exceeds max_groups=%d" % (B, self.max_groups))
         N.check(lib.lec_rows_fwd(N._p(self.table), self.n, self.D, self.row_mode, N.GEOM[self.geom], self.K,
-                                 N._p(self.rows), self.ld, N._p(self.aux), N._p(self.grad_rows), self.replicas, st),
-                "lec_rows_fwd")
-        self.loss.zero_()
+                                 N._p(self.rows), self.ld, N._p(self.aux), N._p(self.grad_rows), self.replicas,
+                                 N._p(self.loss), st), "lec_rows_fwd")
         ev = self.kernel_events
         if ev is not None:
             ev[0].record()
@@ -158,8 +158,56 @@ class ConeStep:
         return out
 
     # -- whole steps ----------------------------------------------------------------------------
+    def _step_struct(self):
+        """lec_step_t with everything that does not change from step to step filled in."""
+        import ctypes
+        s = N.LecStep()
+        s.geom, s.precision, s.row_mode = N.GEOM[self.geom], self.precision, self.row_mode
+        s.update = {"none": 0, "rsgd": 1}[self.update]
+        s.lambda_mode = 0
+        s.K, s.alpha, s.lr, s.r_in = self.K, self.alpha, self.lr, self.r_in
+        s.table, s.n, s.D, s.ld = self.table.data_ptr(), self.n, self.D, self.ld
+        s.rows, s.aux, s.grad_rows = self.rows.data_ptr(), self.aux.data_ptr(), self.grad_rows.data_ptr()
+        s.grad_replicas, s.grad_table = self.replicas, self.grad_table.data_ptr()
+        s.N = self.n_neg
+        s.E_pos, s.E_neg, s.loss = self.E_pos.data_ptr(), self.E_neg.data_ptr(), self.loss.data_ptr()
+        s.world = 0
+        if self.comm == "p2p":
+            px = self.px
+            s.peer_bufs = ctypes.cast(px.peer_ptrs, ctypes.c_void_p)
+            s.slot_floats, s.world, s.rank = px.slot_floats, px.world, px.rank
+            s.loss_global, s.error = self.loss_global.data_ptr(), px.error.data_ptr()
+        return s
+
     def step_device(self, pos_from, pos_to, neg_to, neg_from, w_pos=None, w_neg=None):
         """Indices already on the device (int32 or int64).  Returns the device loss (float64[1])."""
+        if self.update in ("none", "rsgd") and self.comm in ("none", "p2p"):
+            # the whole step as ONE call into the library (lec_cone_step): one FFI crossing, 3-5 launches
+            B = int(pos_from.numel())
+            if B > self.max_groups:
+                raise N.LecError("batch of %d positives exceeds max_groups=%d" % (B, self.max_groups))
+            s = self._struct if self._struct is not None else self._step_struct()
+            self._struct = s
+            s.pos_from, s.pos_to = pos_from.data_ptr(), pos_to.data_ptr()
+            s.neg_to, s.neg_from = neg_to.data_ptr(), neg_from.data_ptr()
+            s.idx_bytes, s.B = pos_from.element_size(), B
+            s.w_pos = w_pos.data_ptr() if w_pos is not None else None
+            s.w_neg = w_neg.data_ptr() if w_neg is not None else None
+            if self.comm == "p2p":
+                s.slot, s.tag = self.px.slot_and_tag()
+            ev = self.kernel_events
+            if ev is not None:
+                for e in ev:
+                    if not e.cuda_event:
+                        e.record()  # torch creates the cudaEvent lazily
+                s.ev_pairs_start, s.ev_pairs_stop = ev[0].cuda_event, ev[1].cuda_event
+            else:
+                s.ev_pairs_start, s.ev_pairs_stop = None, None
+            import ctypes
+            N.check(N.lib().lec_cone_step(ctypes.byref(s), N.stream_ptr(self.table.device)), "lec_cone_step")
+            if self.comm == "p2p":
+                self.px.step += 1
+            return self.loss
         self.forward_backward(pos_from, pos_to, neg_to, neg_from, w_pos, w_neg)
         self.reduce_and_update()
         return self.loss

@@ -69,7 +69,7 @@ def rows_forward(W, mode, K, geom=None, zero_out=None):
     aux = torch.empty((n, 4), device=W.device, dtype=torch.float64) if geom is not None else None
     zr = 0 if zero_out is None else (zero_out.shape[0] if zero_out.dim() == 3 else 1)
     N.check(N.lib().lec_rows_fwd(N._p(W), n, D, int(mode), GEOM[geom] if geom is not None else 0, float(K or 0.0),
-                                 N._p(rows), ld, N._p(aux), N._p(zero_out), zr, N.stream_ptr(W.device)),
+                                 N._p(rows), ld, N._p(aux), N._p(zero_out), zr, N._p(None), N.stream_ptr(W.device)),
             "lec_rows_fwd")
     return rows, aux
 

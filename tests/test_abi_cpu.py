@@ -19,11 +19,11 @@ def header_symbols():
 def test_library_exports_every_header_symbol():
     lib = _native.lib()
     names = header_symbols()
-    assert len(names) >= 14
+    assert len(names) >= 15
     for n in names:
         assert hasattr(lib, n), n
     assert sorted(_native.EXPORTS) == names
-    assert lib.lec_abi_version() == _native.ABI_VERSION == 4
+    assert lib.lec_abi_version() == _native.ABI_VERSION == 5
 
 
 def test_argument_validation_codes():
@@ -48,7 +48,8 @@ def test_argument_validation_codes():
                                  null, null, null, 1, null) == 0
     # cone energies need the per-row aux terms
     assert lib.lec_pairs_flat(1, 0, fake, null, 10, 4, 4, fake, fake, 8, null, null, 5, 0.1, 1.0, fake, null, null, 1, null) == -1
-    assert lib.lec_rows_fwd(fake, 5, 4, 1, 9, 3.0, fake, 4, fake, null, 0, null) == -3
+    assert lib.lec_rows_fwd(fake, 5, 4, 1, 9, 3.0, fake, 4, fake, null, 0, null, null) == -3
+    assert lib.lec_cone_step(None, null) == -1
     # gradient requested with zero replicas
     assert lib.lec_pairs_flat(0, 0, fake, fake, 10, 4, 4, fake, fake, 8, null, null, 5, 3.0, 1.0, fake, null, fake, 0, null) == -7
     assert lib.lec_rows_bwd(fake, fake, 0, 5, 4, 4, 1, 3.0, fake, 0, null) == -7

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define LEC_ABI_VERSION 5
+#define LEC_ABI_VERSION 6
 
 /* geometry of the energy */
 #define LEC_GEOM_EUC 0 /* EucConesLoss.E_operator, order_embeddings.py:954-969 = oe.py:721-739 (cos-space) */
@@ -215,6 +215,21 @@ int lec_cone_step(const lec_step_t* s, void* stream);
 int lec_score_topk(int geom, int precision, const float* labels, int64_t L, const float* images,
                    int64_t N, int D, float K, const int32_t* level_start, const int32_t* level_stop,
                    int n_levels, int k, float* scores, int32_t* topk_idx, float* topk_val, void* stream);
+
+/* Same, with the layout of the optional full energy matrix chosen by the caller.  The reference never
+ * materialises this matrix (it holds one image's L energies at a time, oe_h.py:2018-2028), so its
+ * layout is ours to define:
+ *   LEC_SCORES_IMAGE_MAJOR  scores[i * L + l]   (what lec_score_topk writes)
+ *   LEC_SCORES_LABEL_MAJOR  scores[l * N + i]   the kernel's threads own images, so this is the layout
+ *                           whose stores coalesce (128 B per warp); the host wrapper returns it as the
+ *                           transposed view, i.e. still indexed scores[i, l].
+ * level ranges must be ascending and disjoint. */
+#define LEC_SCORES_IMAGE_MAJOR 0
+#define LEC_SCORES_LABEL_MAJOR 1
+int lec_score_topk_ex(int geom, int precision, const float* labels, int64_t L, const float* images,
+                      int64_t N, int D, float K, const int32_t* level_start, const int32_t* level_stop,
+                      int n_levels, int k, float* scores, int scores_layout, int32_t* topk_idx,
+                      float* topk_val, void* stream);
 
 #ifdef __cplusplus
 }

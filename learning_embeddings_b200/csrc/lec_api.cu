@@ -25,7 +25,7 @@ int p2p_publish_launch(const double*, void* const*, int64_t, int, int, int, unsi
 int rsgd_p2p_launch(float*, void* const*, int64_t, int, int, int, unsigned, int64_t, int, float, float, int, double*, int*,
                     cudaStream_t);
 int score_launch(int, int, const float*, int64_t, const float*, int64_t, int, float, const int32_t*, const int32_t*,
-                 int, int, float*, int32_t*, float*, cudaStream_t);
+                 int, int, float*, int64_t, int64_t, int32_t*, float*, cudaStream_t);
 
 static int pick_core(int geom, int precision) {
     if (precision != LEC_PREC_F32 && precision != LEC_PREC_F64CORE) return -1;
@@ -251,10 +251,11 @@ int lec_cone_step(const lec_step_t* s, void* stream) {
     return lec_rsgd_update(s->table, s->grad_table, 1, s->n, s->D, s->D, s->lr, s->r_in, s->lambda_mode, s->grad_table, stream);
 }
 
-int lec_score_topk(int geom, int precision, const float* labels, int64_t L, const float* images, int64_t N, int D,
-                   float K, const int32_t* level_start, const int32_t* level_stop, int n_levels, int k, float* scores,
-                   int32_t* topk_idx, float* topk_val, void* stream) {
+int lec_score_topk_ex(int geom, int precision, const float* labels, int64_t L, const float* images, int64_t N, int D,
+                      float K, const int32_t* level_start, const int32_t* level_stop, int n_levels, int k, float* scores,
+                      int scores_layout, int32_t* topk_idx, float* topk_val, void* stream) {
     if (pick_core(geom, precision) < 0) return LEC_E_ENUM;
+    if (scores_layout != LEC_SCORES_IMAGE_MAJOR && scores_layout != LEC_SCORES_LABEL_MAJOR) return LEC_E_ENUM;
     if (L < 0 || N < 0) return LEC_E_SIZE;
     if (D < 1 || D > 128) return LEC_E_DIM;
     if (n_levels < 0 || n_levels > LEC_MAX_LEVELS) return LEC_E_K;
@@ -262,8 +263,18 @@ int lec_score_topk(int geom, int precision, const float* labels, int64_t L, cons
     if (!topk_idx) { n_levels = 0; k = 1; }
     if (n_levels > 0 && (!level_start || !level_stop)) return LEC_E_NULL;
     if (N > 0 && L > 0 && (!labels || !images)) return LEC_E_NULL;
+    const int64_t s_img = scores_layout == LEC_SCORES_IMAGE_MAJOR ? L : 1;
+    int64_t s_lab = scores_layout == LEC_SCORES_IMAGE_MAJOR ? 1 : N;
+    if (getenv("LEC_SCORE_DEBUG_SLAB0")) s_lab = 0;  // measurement aid: every label overwrites row 0 (no HBM stream)
     return score_launch(geom, precision, labels, L, images, N, D, K, level_start, level_stop, n_levels, k, scores,
-                        topk_idx, topk_val, (cudaStream_t)stream);
+                        s_img, s_lab, topk_idx, topk_val, (cudaStream_t)stream);
+}
+
+int lec_score_topk(int geom, int precision, const float* labels, int64_t L, const float* images, int64_t N, int D,
+                   float K, const int32_t* level_start, const int32_t* level_stop, int n_levels, int k, float* scores,
+                   int32_t* topk_idx, float* topk_val, void* stream) {
+    return lec_score_topk_ex(geom, precision, labels, L, images, N, D, K, level_start, level_stop, n_levels, k, scores,
+                             LEC_SCORES_IMAGE_MAJOR, topk_idx, topk_val, stream);
 }
 
 }  // extern "C"

@@ -14,7 +14,7 @@ struct ScoreArgs {
     const float* labels; int64_t L; const float* images; int64_t N; int D; float K;
     int n_levels; int k;
     int level_start[LEC_MAX_LEVELS]; int level_stop[LEC_MAX_LEVELS];
-    float* scores; int32_t* topk_idx; float* topk_val;
+    float* scores; int64_t s_img, s_lab; int32_t* topk_idx; float* topk_val;
     int tile_labels;  // labels per shared-memory tile
 };
 
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(kThreads) score_kernel(const ScoreArgs a) {
                 }
                 E = relu_nan(theta - (float)ls1[r]);
             }
-            if (valid && a.scores) a.scores[img * a.L + l] = E;
+            if (valid && a.scores) a.scores[img * a.s_img + (int64_t)l * a.s_lab] = E;
             if (level < a.n_levels && l >= a.level_start[level]) {
                 // sorted insertion, ascending; NaN never enters (comparison false), ties keep the lower label
                 if (E < thr) {
@@ -210,13 +210,22 @@ static int score_launch_geom(ScoreArgs& a, cudaStream_t st) {
     return LEC_E_DIM;  // scoring keeps the image row in registers: D <= 128
 }
 
+bool score_fast_supported(int geom, int precision, int D, int64_t L);
+int score_fast_launch(int geom, const float* labels, int64_t L, const float* images, int64_t N, int D, float K,
+                      const int32_t* level_start, const int32_t* level_stop, int n_levels, int k, float* scores,
+                      int64_t s_img, int64_t s_lab, int32_t* topk_idx, float* topk_val, cudaStream_t st);
+
+// s_img / s_lab: element strides of the score matrix (row-major [N, L]: L, 1; label-major [L, N]: 1, N)
 int score_launch(int geom, int precision, const float* labels, int64_t L, const float* images, int64_t N, int D,
                  float K, const int32_t* level_start, const int32_t* level_stop, int n_levels, int k, float* scores,
-                 int32_t* topk_idx, float* topk_val, cudaStream_t st) {
+                 int64_t s_img, int64_t s_lab, int32_t* topk_idx, float* topk_val, cudaStream_t st) {
+    if (score_fast_supported(geom, precision, D, L))
+        return score_fast_launch(geom, labels, L, images, N, D, K, level_start, level_stop, n_levels, k, scores, s_img,
+                                 s_lab, topk_idx, topk_val, st);
     ScoreArgs a{};
     a.labels = labels; a.L = L; a.images = images; a.N = N; a.D = D; a.K = K; a.n_levels = n_levels; a.k = k;
     for (int i = 0; i < n_levels; ++i) { a.level_start[i] = level_start[i]; a.level_stop[i] = level_stop[i]; }
-    a.scores = scores; a.topk_idx = topk_idx; a.topk_val = topk_val;
+    a.scores = scores; a.s_img = s_img; a.s_lab = s_lab; a.topk_idx = topk_idx; a.topk_val = topk_val;
     if (N == 0 || L == 0) return 0;
     switch (geom) {
         case LEC_GEOM_EUC: return score_launch_geom<SC_EUC>(a, st);

@@ -298,10 +298,12 @@ def rsgd_update_(table, grad, lr, r_in, textbook_lambda=False, write_rescaled_gr
 # Scoring
 # --------------------------------------------------------------------------------------------------
 def score_topk(labels, images, geom, K, level_start, level_stop, k=5, want_scores=False, want_values=True,
-               precision=PREC_F32):  # scoring only ranks: the fp32 core is the default here
-    """Per image, per level: the k labels of lowest energy E(x=label, y=image) (lec_score_topk).
+               precision=PREC_F32, scores_layout="label_major"):  # scoring only ranks: the fp32 core is the default here
+    """Per image, per level: the k labels of lowest energy E(x=label, y=image) (lec_score_topk_ex).
 
-    Returns (topk_idx int32 [N, n_levels, k], topk_val float32 or None, scores [N, L] or None)."""
+    Returns (topk_idx int32 [N, n_levels, k], topk_val float32 or None, scores [N, L] or None).  With the
+    default scores_layout="label_major" the matrix is stored [L, N] (the layout whose stores coalesce) and
+    returned as its transposed view, so it is still indexed scores[i, l]; "image_major" stores [N, L]."""
     N.require_cuda(labels, images)
     labels = labels.detach().contiguous().float()
     images = images.detach().contiguous().float()
@@ -313,8 +315,14 @@ def score_topk(labels, images, geom, K, level_start, level_stop, k=5, want_score
     dev = labels.device
     idx = torch.empty((n_img, nl, k), device=dev, dtype=torch.int32)
     val = torch.empty((n_img, nl, k), device=dev, dtype=torch.float32) if want_values else None
-    scores = torch.empty((n_img, L), device=dev, dtype=torch.float32) if want_scores else None
-    N.check(N.lib().lec_score_topk(GEOM[geom], int(precision), N._p(labels), L, N._p(images), n_img, D,
-                                   float(K or 0.0), ctypes.cast(ls, ctypes.c_void_p), ctypes.cast(le, ctypes.c_void_p),
-                                   nl, int(k), N._p(scores), N._p(idx), N._p(val), N.stream_ptr(dev)), "lec_score_topk")
+    layout = {"image_major": 0, "label_major": 1}[scores_layout]
+    scores = None
+    if want_scores:
+        scores = torch.empty((L, n_img) if layout == 1 else (n_img, L), device=dev, dtype=torch.float32)
+    N.check(N.lib().lec_score_topk_ex(GEOM[geom], int(precision), N._p(labels), L, N._p(images), n_img, D,
+                                      float(K or 0.0), ctypes.cast(ls, ctypes.c_void_p), ctypes.cast(le, ctypes.c_void_p),
+                                      nl, int(k), N._p(scores), layout, N._p(idx), N._p(val), N.stream_ptr(dev)),
+            "lec_score_topk_ex")
+    if scores is not None and layout == 1:
+        scores = scores.t()
     return idx, val, scores

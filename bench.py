@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the entailment-cone hot path (BASELINE.json metric: cone pairs/s fwd+bwd).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg1|cfg4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg1|cfg2|cfg4]
 
 One "step" = one pass of the hot path over one batch: row transform -> fused cone loss fwd+bwd over
 B*(1+2N) pairs -> (N>1: NCCL all-reduce of the label-table gradient) -> Riemannian SGD update of the
@@ -33,7 +33,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg1", choices=["cfg1", "cfg4"])
+    ap.add_argument("--workload", default="cfg1", choices=["cfg1", "cfg2", "cfg4"])
     ap.add_argument("--pairs", type=int, default=1 << 21, help="pairs per GPU per step (rounded to whole groups)")
     ap.add_argument("--precision", type=int, default=None, help="0 fp32 core, 1 fp64 core (default: per workload)")
     ap.add_argument("--rotation", type=int, default=0, help="distinct batches to rotate through (0 = enough to exceed L2)")
@@ -59,7 +59,7 @@ def build_hierarchy(spec):
     from learning_embeddings_b200 import hierarchy as H
     if spec["tree"] == "ethec":
         return H.ethec()
-    return H.random_tree(82115, 1.4056, seed=0)
+    return H.random_tree(82115, 1.0831, seed=0)
 
 
 def init_table(n, D, K, seed):
@@ -72,15 +72,16 @@ def init_table(n, D, K, seed):
 
 def make_batches(h, spec, groups, count, seed):
     """`count` host index blocks of `groups` positives each (closure edges tiled in shuffled order)."""
-    from learning_embeddings_b200.engine import pack_index_block
+    from learning_embeddings_b200.engine import pack_index_block, index_dtype_for
     rng = np.random.default_rng(seed)
+    dt = index_dtype_for(h.n)
     edges = h.closure_edges()
     out = []
     for _ in range(count):
         sel = rng.integers(0, len(edges), size=groups)
         u, v = edges[sel, 0], edges[sel, 1]
         neg_to, neg_from = h.sample_negatives(u, v, spec["n_neg"], rng)
-        out.append(pack_index_block(u, v, neg_to, neg_from))
+        out.append(pack_index_block(u, v, neg_to, neg_from, dtype=dt))
     return out
 
 
@@ -136,7 +137,7 @@ def cpu_step_runner(spec, table, blk, B):
     + E_operator + hinge + backward (autograd) + RSGD table update, all in torch fp32 on CPU."""
     from oracle import cones
     Nn = spec["n_neg"]
-    b = blk[:B * (2 + 2 * Nn)].long()
+    b = torch.from_numpy(blk[:B * (2 + 2 * Nn)].numpy().astype(np.int64))
     u, v = b[:B], b[B:2 * B]
     neg_to = b[2 * B:2 * B + B * Nn].view(B, Nn)
     neg_from = b[2 * B + B * Nn:].view(B, Nn)
@@ -172,8 +173,281 @@ def time_cpu(spec, table, blk, groups, steps, warmup, budget_s=25.0):
     return pairs / float(np.mean(times)), float(np.mean(times)), len(times), pairs
 
 
+# ------------------------------------------------------------------------------------------------
+# cfg2: joint image+label Euclidean cones (BASELINE.json configs[2])
+# ------------------------------------------------------------------------------------------------
+CFG2 = dict(name="cfg2: joint image+label Euclidean cones, 2048-d features -> FeatNet -> D=10, ETHEC labels, "
+                 "23831 positives x (1+10) = 262141 pairs/step, 16384 distinct images/step, Adam",
+            geom="euc", D=10, n_neg=5, K=3.0, alpha=1.0, lr=1e-3, B=23831, m=16384, F=2048, pool=65536)
+
+
+def make_joint_batches(h, leaf_of_img, B, Nn, m, count, rng, idx_dtype):
+    """`count` steps of (img_sel int64[m] rows of the feature pool, packed index block).  Positive (u, v): u a
+    label; v one of the step's images w.p. 0.99 (u = its leaf label or one of that leaf's ancestors) else a
+    child label (closure edge).  Negatives uniform over the step's mixed node set [labels ; images] minus the
+    reference's excluded sets (oe.py:846-863: descendants of u when the child is corrupted, ancestors of v
+    when the parent is corrupted).  Node ids: < n labels, >= n image slot (id - n) of the step."""
+    from learning_embeddings_b200.engine import pack_index_block
+    n = h.n
+    edges = h.closure_edges()
+    depth = h.depth
+    out = []
+    for _ in range(count):
+        sel = rng.choice(len(leaf_of_img), size=m, replace=False)
+        leaf = leaf_of_img[sel]                       # leaf label of every image slot
+        is_img = rng.random(B) < 0.99
+        slot = rng.integers(0, m, size=B)
+        up = rng.integers(0, 4, size=B)               # how many levels above the leaf the parent sits
+        u = leaf[slot].copy()
+        for _k in range(3):
+            step_up = (up > _k) & (h.parents[u] >= 0)
+            u[step_up] = h.parents[u[step_up]]
+        e = edges[rng.integers(0, len(edges), size=B)]
+        u = np.where(is_img, u, e[:, 0])
+        v = np.where(is_img, n + slot, e[:, 1])
+        v_lab = np.where(is_img, leaf[slot], e[:, 1])  # the label whose ancestors are v's ancestors
+        uu, vv, vl = (np.repeat(a[:, None], Nn, 1) for a in (u, v, v_lab))
+        vimg = np.repeat(is_img[:, None], Nn, 1)
+
+        def lab_of(x):                                 # label a node hangs under (itself for a label)
+            return np.where(x >= n, leaf[np.clip(x - n, 0, m - 1)], x)
+
+        neg_to = rng.integers(0, n + m, size=(B, Nn))
+        while True:                                    # corrupted child: not u, not below u
+            cl = lab_of(neg_to)
+            bad = (neg_to == uu) | h.is_descendant(uu, cl) | ((neg_to >= n) & (cl == uu))
+            k = int(bad.sum())
+            if k == 0:
+                break
+            neg_to[bad] = rng.integers(0, n + m, size=k)
+        neg_from = rng.integers(0, n + m, size=(B, Nn))
+        while True:                                    # corrupted parent: not v, not an ancestor of v
+            lab = neg_from < n
+            bad = (neg_from == vv) | (lab & (h.is_descendant(np.where(lab, neg_from, 0), vl) | (vimg & (neg_from == vl))))
+            k = int(bad.sum())
+            if k == 0:
+                break
+            neg_from[bad] = rng.integers(0, n + m, size=k)
+        blk = pack_index_block(u, v, neg_to, neg_from, dtype=idx_dtype)
+        sel_t = torch.from_numpy(sel.astype(np.int64))
+        out.append((sel_t.pin_memory() if torch.cuda.is_available() else sel_t, blk))
+    return out
+
+
+def cfg2_cpu_runner(c, table, fw, fb, feats, sel, blk, B):
+    """The same joint step on the host cores with the oracle's torch port (oe.py forward + autograd + Adam)."""
+    from oracle import cones
+    Nn, n = c["n_neg"], table.shape[0]
+    b = torch.from_numpy(blk[:B * (2 + 2 * Nn)].numpy().astype(np.int64))
+    u, v = b[:B], b[B:2 * B]
+    neg_to = b[2 * B:2 * B + B * Nn].view(B, Nn)
+    neg_from = b[2 * B + B * Nn:].view(B, Nn)
+    nf = torch.cat([u[:, None].expand(B, Nn), neg_from], 1).reshape(-1)
+    nt = torch.cat([neg_to, v[:, None].expand(B, Nn)], 1).reshape(-1)
+    W = table.clone().requires_grad_(True)
+    w1 = fw.clone().requires_grad_(True)
+    b1 = fb.clone().requires_grad_(True)
+    opt = torch.optim.Adam([W, w1, b1], lr=c["lr"])
+    X = feats[sel]
+
+    def run():
+        opt.zero_grad()
+        rows = torch.cat([cones.apply_rows(cones.ROW_EUC_SOFTCLIP, W, c["K"]),
+                          cones.apply_rows(cones.ROW_EUC_SOFTCLIP, X @ w1.t() + b1, c["K"])], 0)
+        E_pos = cones.energy(c["geom"], rows[u], rows[v], c["K"])
+        E_neg = cones.energy(c["geom"], rows[nf], rows[nt], c["K"])
+        loss = E_pos.sum() + (c["alpha"] - E_neg).clamp(min=0).sum()
+        loss.backward()
+        opt.step()
+        return float(loss)
+
+    return run
+
+
+def run_cfg2(args):
+    c = CFG2
+    Nn, D, B, m = c["n_neg"], c["D"], c["B"], c["m"]
+    pairs_per_step = B * (1 + 2 * Nn)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    from learning_embeddings_b200 import hierarchy as H
+    from learning_embeddings_b200.engine import index_dtype_for
+    h = H.ethec()
+    idx_dt = index_dtype_for(h.n + m)
+    idx_bytes = np.dtype(idx_dt).itemsize
+    cfg = {"workload": c["name"], "pairs_per_gpu_per_step": pairs_per_step, "positives_per_gpu_per_step": B,
+           "images_per_gpu_per_step": m, "feature_dim": c["F"], "dim": D, "negatives_per_edge": 2 * Nn,
+           "table_rows": int(h.n), "update": "adam (torch fused) on table + fc1", "scalar_core": "fp32",
+           "index_dtype": np.dtype(idx_dt).name, "feature_pool_images": c["pool"],
+           "parallelism": "dp%d (pairs and images sharded, table + fc1 replicated)" % world}
+    g = torch.Generator().manual_seed(0)
+    table0 = torch.randn(h.n, D, generator=g)
+    lin = torch.nn.Linear(c["F"], D)
+    with torch.no_grad():
+        fw0, fb0 = lin.weight.detach().clone(), lin.bias.detach().clone()
+    rng = np.random.default_rng(7 + rank)
+    leaves = np.arange(h.level_start[-1], h.level_stop[-1])
+    leaf_of_img = leaves[rng.integers(0, len(leaves), size=c["pool"])]
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        torch.set_num_threads(os.cpu_count() or 1)
+        pool_cpu = 4 * m  # a bounded feature pool for the host run
+        feats = torch.relu(torch.randn(pool_cpu, c["F"], generator=g))
+        sel, blk = make_joint_batches(h, leaf_of_img[:pool_cpu], B, Nn, m, 1, rng, idx_dt)[0]
+        run = cfg2_cpu_runner(c, table0, fw0, fb0, feats, sel, blk, B)
+        for _ in range(min(2, args.warmup)):
+            run()
+        ts = []
+        t_all = time.perf_counter()
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            run()
+            ts.append(time.perf_counter() - t0)
+            if time.perf_counter() - t_all > 150.0:
+                break
+        v = pairs_per_step / float(np.mean(ts))
+        cfg["parallelism"] = "host cores only"
+        print(json.dumps({
+            "metric": METRIC, "value": v, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": len(ts),
+            "warmup": min(2, args.warmup), "ms_per_step": float(np.mean(ts)) * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                             "sample": "the full cfg2 step (%d pairs, %d images), %d timed steps" % (pairs_per_step, m, len(ts))},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    pg = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+    from learning_embeddings_b200 import _native
+    from learning_embeddings_b200.engine import JointConeStep
+    gd = torch.Generator(device=dev).manual_seed(1 + rank)
+    feats = torch.relu(torch.randn(c["pool"], c["F"], generator=gd, device=dev))   # 537 MB, staged once
+    rotation = args.rotation or 8
+    batches = make_joint_batches(h, leaf_of_img, B, Nn, m, rotation, rng, idx_dt)
+    dev_batches = [(s_.to(dev), b_.to(dev)) for s_, b_ in batches]
+    cfg["l2_policy"] = "every step gathers %d of %d feature rows (%.0f MB read, > 126 MB L2); %d index batches rotate" % (
+        m, c["pool"], m * c["F"] * 4 / 1e6, rotation)
+    table, fw, fb = table0.to(dev).clone(), fw0.to(dev).clone(), fb0.to(dev).clone()
+    eng = JointConeStep(table, fw, fb, feats, c["geom"], Nn, B, m, K=c["K"], alpha=c["alpha"], lr=c["lr"],
+                        precision=0, process_group=pg)
+    cfg["exchange"] = "nccl all_reduce of one flat gradient buffer (table + fc1)" if world > 1 else "none (1 GPU)"
+
+    def dev_step(i):
+        s_, b_ = dev_batches[i % rotation]
+        eng.step_device(s_, *eng._split(b_, B))
+
+    def sync_all():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for i in range(max(3, args.warmup)):
+        dev_step(i)
+    sync_all()
+    launches0 = _native.launch_count()
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.active.set()
+    sync_all()
+    t0.record()
+    for i in range(args.steps):
+        eng.kernel_events = kev[i]
+        dev_step(i)
+    t1.record()
+    sync_all()
+    sampler.active.clear()
+    eng.kernel_events = None
+    lec_launches = _native.launch_count() - launches0
+    elapsed_ms = t0.elapsed_time(t1)
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+
+    def max_ranks(ms):
+        if world > 1:
+            tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+            torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+            return float(tt.item())
+        return ms
+
+    elapsed_ms = max_ranks(elapsed_ms)
+    value = world * pairs_per_step * args.steps / (elapsed_ms * 1e-3)
+    e2e = None
+    if not args.no_e2e:
+        for i in range(3):
+            eng.step_host(*batches[i % rotation], B)
+        sync_all()
+        sampler.active.set()
+        w0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            eng.step_host(*batches[i % rotation], B)
+        e1.record()
+        sync_all()
+        sampler.active.clear()
+        e_ms = max_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - w0) * 1e3))
+        e2e = {"value": world * pairs_per_step * args.steps / (e_ms * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": B * (2 + 2 * Nn) * idx_bytes + m * 8, "d2h_bytes_per_step": 8,
+               "ms_per_step": e_ms / args.steps,
+               "api": "JointConeStep.step_host (features device-resident; per step: image selection + index block in, loss out)"}
+    sampler.stop()
+    final_loss = float(eng.loss.item())
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    bytes_per_pair = 24 + 16 * D
+    achieved = pairs_per_step * bytes_per_pair / (kernel_ms * 1e-3) / 1e9
+    step_ms = elapsed_ms / args.steps
+    roofline = {"bound": "hbm", "kernel": "pairs_grouped_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_pair": bytes_per_pair,
+                "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / step_ms,
+                "step_floor_ms": 2 * m * c["F"] * 4 / (peak * 1e9) * 1e3 * 1.5,
+                "note": "the step is dominated by FeatNet traffic outside the product: gather of %d x %d fp32 feature rows "
+                        "(read + write), fc1 forward and weight-gradient GEMMs (two more reads), all stock torch/cuBLAS; "
+                        "step_floor_ms = those 3 passes over X at the measured HBM peak" % (m, c["F"])}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
+        run = cfg2_cpu_runner(c, table0, fw0, fb0, feats[:4 * m].cpu(), torch.from_numpy(np.arange(m)), batches[0][1], B)
+        run()
+        ts = []
+        t_all = time.perf_counter()
+        while len(ts) < 20 and time.perf_counter() - t_all < 20.0:
+            t0_ = time.perf_counter()
+            run()
+            ts.append(time.perf_counter() - t0_)
+        cpu = {"value": pairs_per_step / float(np.mean(ts)), "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": "the full cfg2 step (%d pairs, %d images) x %d, torch fp32 on all host threads" % (pairs_per_step, m, len(ts))}
+    print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                      "warmup": max(3, args.warmup), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg, "clocks": sampler.summary(),
+                      "e2e": e2e, "gpu_launches": int(lec_launches), "roofline": roofline, "cpu_baseline": cpu,
+                      "final_loss": final_loss}))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
 def main():
     args = parse()
+    if args.workload == "cfg2":
+        return run_cfg2(args)
     spec = workload_spec(args.workload)
     Nn, D = spec["n_neg"], spec["D"]
     ppg = 1 + 2 * Nn
@@ -185,11 +459,14 @@ def main():
     precision = args.precision if args.precision is not None else 1
     cfg = {"workload": spec["name"], "pairs_per_gpu_per_step": pairs_per_step, "positives_per_gpu_per_step": groups,
            "dim": D, "negatives_per_edge": 2 * Nn, "table_rows": None, "update": "rsgd",
-           "scalar_core": "fp64" if precision == 1 else "fp32", "index_dtype": "int32",
+           "scalar_core": "fp64" if precision == 1 else "fp32", "index_dtype": None,
            "parallelism": "dp%d (pairs sharded, table replicated)" % world}
 
     h = build_hierarchy(spec)
     cfg["table_rows"] = int(h.n)
+    from learning_embeddings_b200.engine import index_dtype_for
+    idx_bytes = np.dtype(index_dtype_for(h.n)).itemsize
+    cfg["index_dtype"] = np.dtype(index_dtype_for(h.n)).name
     table0 = init_table(h.n, D, spec["K"], seed=0)
 
     # ---------------- reference arm: CPU only, rank 0 only ----------------
@@ -227,7 +504,7 @@ def main():
     from learning_embeddings_b200 import _native, ops
     from learning_embeddings_b200.engine import ConeStep
 
-    bytes_per_batch = groups * (2 + 2 * Nn) * 4 + groups * ppg * 4  # indices in + energies out
+    bytes_per_batch = groups * (2 + 2 * Nn) * idx_bytes + groups * ppg * 4  # indices in + energies out
     rotation = args.rotation or max(4, int(np.ceil(160e6 / bytes_per_batch)))
     cfg["l2_policy"] = "inputs rotate through %d distinct batches (%.0f MB > 126 MB L2)" % (
         rotation, rotation * bytes_per_batch / 1e6)
@@ -278,31 +555,42 @@ def main():
         elapsed_ms = float(tt.item())
     value = world * pairs_per_step * args.steps / (elapsed_ms * 1e-3)
 
-    # end to end: host index block -> H2D -> step -> loss D2H, every step
+    # end to end through the public host API: pinned host index block -> H2D -> step -> loss D2H, every step.
+    # "value" is the pipelined path (ConeStep.submit_host / drain: the copy of step i+1 overlaps the kernels of
+    # step i, losses are read back asynchronously, every loss is delivered); "sync" is ConeStep.step_host, which
+    # returns each step's loss before the next step is issued.
     e2e = None
     if not args.no_e2e:
-        for i in range(3):
-            eng.step_host(host_batches[i % rotation], groups)
-        sync_all()
-        e_steps = args.steps
-        sampler.active.set()
-        w0 = time.perf_counter()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(e_steps):
-            eng.step_host(host_batches[i % rotation], groups)
-        e1.record()
-        sync_all()
-        sampler.active.clear()
-        e_ms = e0.elapsed_time(e1)
-        wall_ms = (time.perf_counter() - w0) * 1e3
-        e_ms = max(e_ms, wall_ms)
-        if world > 1:
-            tt = torch.tensor([e_ms], device=dev, dtype=torch.float64)
-            torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
-            e_ms = float(tt.item())
-        e2e = {"value": world * pairs_per_step * e_steps / (e_ms * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": groups * (2 + 2 * Nn) * 4, "d2h_bytes_per_step": 8, "ms_per_step": e_ms / e_steps}
+        def timed(fn_step, fn_end):
+            for i in range(3):
+                fn_step(i)
+            fn_end()
+            sync_all()
+            sampler.active.set()
+            w0 = time.perf_counter()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(args.steps):
+                fn_step(i)
+            got = fn_end()
+            e1.record()
+            sync_all()
+            sampler.active.clear()
+            ms = max(e0.elapsed_time(e1), (time.perf_counter() - w0) * 1e3)
+            if world > 1:
+                tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+                torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+                ms = float(tt.item())
+            return ms, got
+
+        sync_ms, _ = timed(lambda i: eng.step_host(host_batches[i % rotation], groups), lambda: None)
+        pipe_ms, losses = timed(lambda i: eng.submit_host(host_batches[i % rotation], groups), eng.drain)
+        assert len(losses) == args.steps, "every step's loss must come back to the host"
+        e2e = {"value": world * pairs_per_step * args.steps / (pipe_ms * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": groups * (2 + 2 * Nn) * idx_bytes, "d2h_bytes_per_step": 8,
+               "ms_per_step": pipe_ms / args.steps, "api": "ConeStep.submit_host/drain (copy of step i+1 overlaps step i)",
+               "sync": {"value": world * pairs_per_step * args.steps / (sync_ms * 1e-3), "ms_per_step": sync_ms / args.steps,
+                        "api": "ConeStep.step_host (loss returned before the next step is issued)"}}
     sampler.stop()
 
     if rank != 0:

@@ -18,7 +18,8 @@
  *     ld a multiple of 4 (>= D), pad columns zero, base 16-byte aligned.  It is produced from the
  *     raw parameter table by lec_rows_fwd (together with the per-row "aux" terms) and its gradient is
  *     mapped back by lec_rows_bwd.
- *   - index arrays are int32 or int64 (idx_bytes = 4 or 8)
+ *   - index arrays are uint16, int32 or int64 (idx_bytes = 2, 4 or 8; uint16 needs n_rows <= 65536 and
+ *     halves the host->device bytes of a step's index block)
  */
 #ifndef LEC_B200_H
 #define LEC_B200_H
@@ -29,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LEC_ABI_VERSION 6
+#define LEC_ABI_VERSION 7
 
 /* geometry of the energy */
 #define LEC_GEOM_EUC 0 /* EucConesLoss.E_operator, order_embeddings.py:954-969 = oe.py:721-739 (cos-space) */

@@ -103,7 +103,7 @@ int lec_pairs_flat(int geom, int precision, const float* rows, const double* aux
                    const void* to_idx, int idx_bytes, const float* w, const uint8_t* is_pos, int64_t P, float K,
                    float alpha, float* E_out, double* loss_out, float* grad_rows, int grad_replicas, void* stream) {
     const int core = pick_core(geom, precision);
-    if (core < 0 || (idx_bytes != 4 && idx_bytes != 8)) return LEC_E_ENUM;
+    if (core < 0 || (idx_bytes != 2 && idx_bytes != 4 && idx_bytes != 8)) return LEC_E_ENUM;
     if (P < 0 || n_rows < 0) return LEC_E_SIZE;
     if (int e = check_rows(rows, D, ld)) return e;
     if (grad_rows && (reinterpret_cast<uintptr_t>(grad_rows) & 15)) return LEC_E_ALIGN;
@@ -128,7 +128,7 @@ int lec_pairs_grouped(int geom, int precision, const float* rows, const double* 
                       const float* w_pos, const float* w_neg, float K, float alpha, float* E_pos, float* E_neg,
                       double* loss_out, float* grad_rows, int grad_replicas, void* stream) {
     const int core = pick_core(geom, precision);
-    if (core < 0 || (idx_bytes != 4 && idx_bytes != 8)) return LEC_E_ENUM;
+    if (core < 0 || (idx_bytes != 2 && idx_bytes != 4 && idx_bytes != 8)) return LEC_E_ENUM;
     if (B < 0 || N < 0 || n_rows < 0) return LEC_E_SIZE;
     if (int e = check_rows(rows, D, ld)) return e;
     if (grad_rows && (reinterpret_cast<uintptr_t>(grad_rows) & 15)) return LEC_E_ALIGN;
@@ -264,8 +264,7 @@ int lec_score_topk_ex(int geom, int precision, const float* labels, int64_t L, c
     if (n_levels > 0 && (!level_start || !level_stop)) return LEC_E_NULL;
     if (N > 0 && L > 0 && (!labels || !images)) return LEC_E_NULL;
     const int64_t s_img = scores_layout == LEC_SCORES_IMAGE_MAJOR ? L : 1;
-    int64_t s_lab = scores_layout == LEC_SCORES_IMAGE_MAJOR ? 1 : N;
-    if (getenv("LEC_SCORE_DEBUG_SLAB0")) s_lab = 0;  // measurement aid: every label overwrites row 0 (no HBM stream)
+    const int64_t s_lab = scores_layout == LEC_SCORES_IMAGE_MAJOR ? 1 : N;
     return score_launch(geom, precision, labels, L, images, N, D, K, level_start, level_stop, n_levels, k, scores,
                         s_img, s_lab, topk_idx, topk_val, (cudaStream_t)stream);
 }

@@ -41,8 +41,9 @@ struct DenseArgs {
 };
 
 __device__ __forceinline__ int64_t ld_index(const void* p, int64_t i, int idx_bytes) {
-    return idx_bytes == 4 ? (int64_t)__ldg(reinterpret_cast<const int32_t*>(p) + i)
-                          : (int64_t)__ldg(reinterpret_cast<const long long*>(p) + i);
+    if (idx_bytes == 4) return (int64_t)__ldg(reinterpret_cast<const int32_t*>(p) + i);
+    if (idx_bytes == 2) return (int64_t)__ldg(reinterpret_cast<const unsigned short*>(p) + i);
+    return (int64_t)__ldg(reinterpret_cast<const long long*>(p) + i);
 }
 
 // z and (optionally) the dz/dx, dz/dy coefficients of one pair held by a team.

@@ -24,10 +24,20 @@ from . import sharding
 from .criterion import inner_radius
 
 
-def pack_index_block(pos_from, pos_to, neg_to, neg_from, pin=True):
-    """Host int32 block [B | B | B*N | B*N] for ConeStep.step_host."""
-    parts = [np.ascontiguousarray(a, dtype=np.int32).reshape(-1) for a in (pos_from, pos_to, neg_to, neg_from)]
-    blk = torch.from_numpy(np.concatenate(parts))
+def index_dtype_for(n_rows):
+    """Narrowest index type the kernels take for a table of n_rows rows: uint16 up to 65 536 rows (ETHEC has
+    723), else int32.  The index block is the only per-step host->device traffic, so its width is the
+    end-to-end cost of a step."""
+    return np.uint16 if n_rows <= 65536 else np.int32
+
+
+def pack_index_block(pos_from, pos_to, neg_to, neg_from, pin=True, dtype=np.int32):
+    """Host index block [B | B | B*N | B*N] (int32, or uint16 for tables of <= 65 536 rows) for ConeStep.step_host."""
+    parts = [np.ascontiguousarray(a).reshape(-1) for a in (pos_from, pos_to, neg_to, neg_from)]
+    cat = np.concatenate(parts)
+    if cat.size and (cat.min() < 0 or cat.max() > np.iinfo(dtype).max):
+        raise ValueError("index out of range for %s" % np.dtype(dtype).name)
+    blk = torch.from_numpy(cat.astype(dtype))
     return blk.pin_memory() if (pin and torch.cuda.is_available()) else blk
 
 
@@ -61,8 +71,16 @@ class ConeStep:
         self.E_pos = torch.empty(self.max_groups, device=dev, dtype=torch.float32)
         self.E_neg = torch.empty((self.max_groups, 2 * self.n_neg), device=dev, dtype=torch.float32)
         self.loss = torch.zeros(1, device=dev, dtype=torch.float64)
-        self.idx_dev = torch.empty(self.max_groups * (2 + 2 * self.n_neg), device=dev, dtype=torch.int32)
-        self.loss_host = torch.zeros(1, dtype=torch.float64).pin_memory()
+        # host->device staging: `depth` slots so that the copy of step i+1 overlaps the kernels of step i
+        self.depth = 2
+        self._idx_bytes_dev = [torch.empty(self.max_groups * (2 + 2 * self.n_neg) * 4, device=dev, dtype=torch.uint8)
+                               for _ in range(self.depth)]
+        self.loss_host = torch.zeros(self.depth, dtype=torch.float64).pin_memory()
+        self._copy_stream = None
+        self._ev = None          # per slot: (indices copied, kernels done with the slot, loss read back)
+        self._inflight = [False] * self.depth
+        self._submitted = 0
+        self._losses = []
         self.kernel_events = None  # optional (start, stop) pairs around the pair kernel, set by bench
         self._struct = None
         # multi-GPU exchange: "p2p" = one-shot all-reduce over NVLink peer memory fused into the RSGD kernel,
@@ -212,13 +230,180 @@ class ConeStep:
         self.reduce_and_update()
         return self.loss
 
+    def _slot_view(self, slot, n, dtype):
+        return self._idx_bytes_dev[slot][:n * dtype.itemsize].view(dtype)
+
     def step_host(self, index_block, B):
-        """index_block: pinned host int32 block from pack_index_block.  Copies it in, runs the step and
-        reads the scalar loss back (one H2D, one D2H, one sync) -- the end-to-end path."""
+        """index_block: pinned host block from pack_index_block (uint16 / int32).  Copies it in, runs the
+        step and reads the scalar loss back (one H2D, one D2H, one sync) -- the synchronous end-to-end path."""
+        self._collect()
         n = B * (2 + 2 * self.n_neg)
-        dst = self.idx_dev[:n]
+        dst = self._slot_view(0, n, index_block.dtype)
         dst.copy_(index_block[:n], non_blocking=True)
         self.step_device(*self._split(dst, B))
+        self.loss_host[:1].copy_(self.loss, non_blocking=True)
+        torch.cuda.current_stream(self.table.device).synchronize()
+        return float(self.loss_host[0])
+
+    def submit_host(self, index_block, B):
+        """Pipelined end-to-end step: the index block goes host->device on a side stream into one of `depth`
+        staging slots while the previous step's kernels run; the step is enqueued behind its copy; its loss
+        comes back device->host asynchronously.  Blocks only when the slot it needs is still in flight
+        (i.e. on the loss of step i - depth).  Losses are returned, in order, by drain()."""
+        dev = self.table.device
+        main = torch.cuda.current_stream(dev)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(dev)
+            self._ev = [tuple(torch.cuda.Event() for _ in range(3)) for _ in range(self.depth)]
+        slot = self._submitted % self.depth
+        ev_copied, ev_free, ev_loss = self._ev[slot]
+        if self._inflight[slot]:
+            ev_loss.synchronize()
+            self._losses.append(float(self.loss_host[slot]))
+        n = B * (2 + 2 * self.n_neg)
+        dst = self._slot_view(slot, n, index_block.dtype)
+        with torch.cuda.stream(self._copy_stream):
+            if self._inflight[slot]:
+                self._copy_stream.wait_event(ev_free)
+            dst.copy_(index_block[:n], non_blocking=True)
+            ev_copied.record(self._copy_stream)
+        main.wait_event(ev_copied)
+        self.step_device(*self._split(dst, B))
+        ev_free.record(main)
+        self.loss_host[slot:slot + 1].copy_(self.loss, non_blocking=True)
+        ev_loss.record(main)
+        self._inflight[slot] = True
+        self._submitted += 1
+
+    def drain(self):
+        """Wait for every submitted step; returns their losses in submission order (and forgets them)."""
+        self._collect()
+        out, self._losses = self._losses, []
+        return out
+
+    def _collect(self):
+        if self._ev is not None:
+            for k in range(self.depth):
+                slot = (self._submitted + k) % self.depth  # oldest first
+                if self._inflight[slot]:
+                    self._ev[slot][2].synchronize()
+                    self._losses.append(float(self.loss_host[slot]))
+                    self._inflight[slot] = False
+
+
+class JointConeStep:
+    """One fused training step of a JOINT image+label cone model (the reference's oe.py / oe_h.py trainers,
+    `JointEmbeddings.pass_samples('train')`, oe.py:1489-1560) on preallocated buffers:
+
+        X        = features[img_sel]                         gather of the step's distinct images  (torch)
+        Y        = X @ fc1.weight^T + fc1.bias               FeatNet.fc1, oe.py:97,113            (cuBLAS)
+        rows,aux = [transform(table) ; transform(Y)]         lec_rows_fwd x2  (Embedder / FeatNet tail)
+        loss, dL/drows over B*(1+2N) pairs                   lec_pairs_grouped on the concatenated row table
+        dL/dtable, dL/dY                                     lec_reduce_replicas + lec_rows_bwd x2
+        dL/dfc1.weight = dL/dY^T @ X, dL/dfc1.bias           cuBLAS / torch
+        [one all-reduce of the flat gradient buffer]         NCCL, only when world_size > 1
+        Adam (fused) on table, fc1.weight, fc1.bias          torch.optim.Adam, the reference's default optimizer
+
+    Endpoints are row numbers of the concatenated table: < n_labels a label, >= n_labels image
+    (index - n_labels) of this step's img_sel.  The FeatNet GEMM stays cuBLAS (not the product)."""
+
+    def __init__(self, table, fc_weight, fc_bias, features, geom, n_neg, max_groups, max_images, K=None, alpha=1.0,
+                 lr=1e-3, precision=ops.PREC_F64CORE, process_group=None):
+        N.require_cuda(table, fc_weight, fc_bias, features)
+        self.table, self.fc_w, self.fc_b, self.features = table, fc_weight, fc_bias, features
+        self.geom = geom
+        self.n, self.D = table.shape
+        self.ld = ops.padded_dim(self.D)
+        self.n_neg, self.max_groups, self.max_images = int(n_neg), int(max_groups), int(max_images)
+        self.K = {"euc": 3.0, "hyp": 0.1, "oe": 0.0}[geom] if K is None else float(K)
+        self.alpha, self.lr, self.precision = float(alpha), float(lr), int(precision)
+        self.lab_mode = {"euc": N.ROWS_EUC_SOFTCLIP, "hyp": N.ROWS_HYP_TANH, "oe": N.ROWS_NONE}[geom]
+        self.img_mode = {"euc": N.ROWS_EUC_SOFTCLIP, "hyp": N.ROWS_HYP_TANH_FEAT, "oe": N.ROWS_NONE}[geom]
+        self.pg = process_group
+        dev = table.device
+        nt = self.n + self.max_images
+        self.n_total = nt
+        F = features.shape[1]
+        self.replicas = ops.default_replicas(nt, self.ld)
+        self.X = torch.empty((self.max_images, F), device=dev, dtype=torch.float32)
+        self.Y = torch.empty((self.max_images, self.D), device=dev, dtype=torch.float32)
+        self.rows = torch.empty((nt, self.ld), device=dev, dtype=torch.float32)
+        self.aux = torch.empty((nt, 4), device=dev, dtype=torch.float64)
+        self.grad_rows = torch.empty((self.replicas, nt, self.ld), device=dev, dtype=torch.float32)
+        self.grad_sum = torch.empty((nt, self.ld), device=dev, dtype=torch.float32)
+        self.gY = torch.empty((self.max_images, self.D), device=dev, dtype=torch.float32)
+        # flat gradient buffer [table | fc1.weight | fc1.bias]: one all-reduce, and the optimizer's .grad views
+        sizes = [self.n * self.D, fc_weight.numel(), fc_bias.numel()]
+        self.gflat = torch.zeros(sum(sizes), device=dev, dtype=torch.float32)
+        o = np.cumsum([0] + sizes)
+        self.g_table = self.gflat[o[0]:o[1]].view(self.n, self.D)
+        self.g_w = self.gflat[o[1]:o[2]].view_as(fc_weight)
+        self.g_b = self.gflat[o[2]:o[3]].view_as(fc_bias)
+        self.E_pos = torch.empty(self.max_groups, device=dev, dtype=torch.float32)
+        self.E_neg = torch.empty((self.max_groups, 2 * self.n_neg), device=dev, dtype=torch.float32)
+        self.loss = torch.zeros(1, device=dev, dtype=torch.float64)
+        self.params = [torch.nn.Parameter(t, requires_grad=False) for t in (table, fc_weight, fc_bias)]
+        for p, g in zip(self.params, (self.g_table, self.g_w, self.g_b)):
+            p.grad = g
+        self.opt = torch.optim.Adam(self.params, lr=self.lr, fused=True)
+        self.kernel_events = None
+        self._sel_dev = torch.empty(self.max_images, device=dev, dtype=torch.int64)
+        self._idx_bytes_dev = torch.empty(self.max_groups * (2 + 2 * self.n_neg) * 4, device=dev, dtype=torch.uint8)
+        self.loss_host = torch.zeros(1, dtype=torch.float64).pin_memory()
+
+    def _split(self, blk, B):
+        Nn = self.n_neg
+        return blk[:B], blk[B:2 * B], blk[2 * B:2 * B + B * Nn], blk[2 * B + B * Nn:2 * B + 2 * B * Nn]
+
+    def step_device(self, img_sel, pos_from, pos_to, neg_to, neg_from):
+        lib, st = N.lib(), N.stream_ptr(self.table.device)
+        m, B, n, D, ld = int(img_sel.numel()), int(pos_from.numel()), self.n, self.D, self.ld
+        if m > self.max_images or B > self.max_groups:
+            raise N.LecError("step of %d images / %d positives exceeds the engine's buffers" % (m, B))
+        X, Y = self.X[:m], self.Y[:m]
+        torch.index_select(self.features, 0, img_sel, out=X)
+        torch.addmm(self.fc_b, X, self.fc_w.t(), out=Y)
+        geom = N.GEOM[self.geom]
+        rows_img, aux_img = self.rows[n:n + m], self.aux[n:n + m]
+        # labels (clears the loss accumulator), then the projected images; the gradient accumulator spans both
+        N.check(lib.lec_rows_fwd(N._p(self.table), n, D, self.lab_mode, geom, self.K, N._p(self.rows), ld, N._p(self.aux),
+                                 N._p(None), 0, N._p(self.loss), st), "lec_rows_fwd")
+        self.grad_rows.zero_()
+        N.check(lib.lec_rows_fwd(N._p(Y), m, D, self.img_mode, geom, self.K, N._p(rows_img), ld, N._p(aux_img),
+                                 N._p(None), 0, N._p(None), st), "lec_rows_fwd")
+        ev = self.kernel_events
+        if ev is not None:
+            ev[0].record()
+        N.check(lib.lec_pairs_grouped(
+            geom, self.precision, N._p(self.rows), N._p(self.aux), self.n_total, D, ld, N._p(pos_from), N._p(pos_to),
+            N._p(neg_to), N._p(neg_from), pos_from.element_size(), B, self.n_neg, N._p(None), N._p(None), self.K,
+            self.alpha, N._p(self.E_pos), N._p(self.E_neg), N._p(self.loss), N._p(self.grad_rows), self.replicas, st),
+            "lec_pairs_grouped")
+        if ev is not None:
+            ev[1].record()
+        N.check(lib.lec_reduce_replicas(N._p(self.grad_rows), self.replicas, self.n_total * ld, N._p(self.grad_sum), st),
+                "lec_reduce_replicas")
+        N.check(lib.lec_rows_bwd(N._p(self.table), N._p(self.grad_sum), 1, n, D, ld, self.lab_mode, self.K,
+                                 N._p(self.g_table), 0, st), "lec_rows_bwd")
+        gY = self.gY[:m]
+        N.check(lib.lec_rows_bwd(N._p(Y), N._p(self.grad_sum[n:n + m]), 1, m, D, ld, self.img_mode, self.K, N._p(gY), 0, st),
+                "lec_rows_bwd")
+        torch.mm(gY.t(), X, out=self.g_w)
+        torch.sum(gY, dim=0, out=self.g_b)
+        if self.pg is not None and torch.distributed.get_world_size(self.pg) > 1:
+            torch.distributed.all_reduce(self.gflat, group=self.pg)
+        self.opt.step()
+        return self.loss
+
+    def step_host(self, img_sel_host, index_block, B):
+        """Pinned host inputs (int64 image selection, uint16/int32 index block) -> step -> loss on the host."""
+        m = int(img_sel_host.numel())
+        n = B * (2 + 2 * self.n_neg)
+        sel = self._sel_dev[:m]
+        sel.copy_(img_sel_host, non_blocking=True)
+        dst = self._idx_bytes_dev[:n * index_block.dtype.itemsize].view(index_block.dtype)
+        dst.copy_(index_block[:n], non_blocking=True)
+        self.step_device(sel, *self._split(dst, B))
         self.loss_host.copy_(self.loss, non_blocking=True)
         torch.cuda.current_stream(self.table.device).synchronize()
         return float(self.loss_host[0])

@@ -23,7 +23,7 @@ def test_library_exports_every_header_symbol():
     for n in names:
         assert hasattr(lib, n), n
     assert sorted(_native.EXPORTS) == names
-    assert lib.lec_abi_version() == _native.ABI_VERSION == 6
+    assert lib.lec_abi_version() == _native.ABI_VERSION == 7
 
 
 def test_argument_validation_codes():
@@ -38,7 +38,7 @@ def test_argument_validation_codes():
     assert lib.lec_pairs_flat(0, 0, fake, fake, 10, 8, 4, fake, fake, 8, null, null, 5, 3.0, 1.0, fake, null, null, 1, null) == -2
     # unknown geometry / index width
     assert lib.lec_pairs_flat(7, 0, fake, fake, 10, 4, 4, fake, fake, 8, null, null, 5, 3.0, 1.0, fake, null, null, 1, null) == -3
-    assert lib.lec_pairs_flat(0, 0, fake, fake, 10, 4, 4, fake, fake, 2, null, null, 5, 3.0, 1.0, fake, null, null, 1, null) == -3
+    assert lib.lec_pairs_flat(0, 0, fake, fake, 10, 4, 4, fake, fake, 3, null, null, 5, 3.0, 1.0, fake, null, null, 1, null) == -3
     # negative count, misaligned rows
     assert lib.lec_pairs_flat(0, 0, fake, fake, 10, 4, 4, fake, fake, 8, null, null, -1, 3.0, 1.0, fake, null, null, 1, null) == -4
     assert lib.lec_pairs_flat(0, 0, odd, fake, 10, 4, 4, fake, fake, 8, null, null, 5, 3.0, 1.0, fake, null, null, 1, null) == -5

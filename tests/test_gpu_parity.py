@@ -585,3 +585,69 @@ def test_engine_step_matches_oracle(name, geom, mode):
     e2.reduce_and_update()
     np.testing.assert_allclose(e2.E_neg.cpu().numpy(), eng.E_neg.cpu().numpy(), rtol=0, atol=0)
     np.testing.assert_allclose(t2.cpu().numpy(), table.cpu().numpy(), rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("idx_np", (np.uint16, np.int32))
+def test_pipelined_host_steps_equal_synchronous_steps(idx_np):
+    """ConeStep.submit_host/drain (copy of step i+1 overlapping step i, uint16 or int32 index blocks) must leave the
+    same table and return the same losses as step_host called step by step."""
+    from learning_embeddings_b200.engine import ConeStep, pack_index_block
+    from learning_embeddings_b200 import hierarchy
+    ethec = hierarchy.ethec()
+    rng = np.random.default_rng(5)
+    Nn, B, D = 5, 4096, 10
+    edges = ethec.closure_edges()
+    blocks = []
+    for _ in range(5):
+        sel = rng.integers(0, len(edges), size=B)
+        u, v = edges[sel, 0], edges[sel, 1]
+        neg_to, neg_from = ethec.sample_negatives(u, v, Nn, rng)
+        blocks.append(pack_index_block(u, v, neg_to, neg_from, dtype=idx_np))
+    g = torch.Generator().manual_seed(3)
+    w = torch.randn(ethec.n, D, generator=g)
+    W0 = (cones.inner_radius(0.1) + 0.05 * torch.rand(ethec.n, 1, generator=g)) * w / w.norm(dim=1, keepdim=True)
+    ta, tb = W0.to(DEV).clone(), W0.to(DEV).clone()
+    ea = ConeStep(ta, "hyp", Nn, B, K=0.1, alpha=0.05, lr=0.01)
+    eb = ConeStep(tb, "hyp", Nn, B, K=0.1, alpha=0.05, lr=0.01)
+    sync_losses = [ea.step_host(b, B) for b in blocks]
+    for b in blocks:
+        eb.submit_host(b, B)
+    pipe_losses = eb.drain()
+    assert len(pipe_losses) == len(blocks) and eb.drain() == []
+    # fp32 vector reductions into the gradient replicas are not order-deterministic: tolerance, not equality
+    np.testing.assert_allclose(pipe_losses, sync_losses, rtol=1e-6)
+    np.testing.assert_allclose(tb.cpu().numpy(), ta.cpu().numpy(), rtol=1e-4, atol=1e-6)
+    # the int64 reference layout gives the same first-step energies as the narrow block
+    tc = W0.to(DEV).clone()
+    ec = ConeStep(tc, "hyp", Nn, B, K=0.1, alpha=0.05, lr=0.01)
+    ec.step_device(*ec._split(torch.from_numpy(blocks[0].numpy().astype(np.int64)).to(DEV), B))
+    ed = ConeStep(W0.to(DEV).clone(), "hyp", Nn, B, K=0.1, alpha=0.05, lr=0.01)
+    ed.step_host(blocks[0], B)
+    assert torch.equal(ec.E_neg, ed.E_neg) and torch.equal(ec.E_pos, ed.E_pos)
+
+
+@pytest.mark.parametrize("name,geom", [("joint_euc", "euc"), ("joint_oe", "oe"), ("joint_hyp", "hyp")])
+def test_joint_engine_step_matches_reference_gradients(name, geom):
+    """engine.JointConeStep (gather -> fc1 -> row transforms -> fused pair kernel -> VJPs -> fc1 gradients) against the
+    reference's loss, energies and the three parameter gradients of the same step (golden, from oe.py / oe_h.py)."""
+    from learning_embeddings_b200.engine import JointConeStep, pack_index_block
+    g = load_golden(name)
+    Nn, K, alpha, n_lab = int(g["N"]), float(g["K"]), float(g["alpha"]), int(g["n_lab"])
+    B = len(g["b_from"])
+    drawn = g["drawn"].reshape(B, Nn, 2)
+    neg_to, neg_from = drawn[:, :, 0].copy(), drawn[:, :, 1].copy()
+    m = g["feat"].shape[0]
+    table, fw, fb = (t(g[k]).to(DEV).clone() for k in ("W0", "fc_w", "fc_b"))
+    feats = t(g["feat"]).to(DEV)
+    eng = JointConeStep(table, fw, fb, feats, geom, Nn, B, m, K=K if geom != "oe" else None, alpha=alpha, lr=1e-3)
+    blk = pack_index_block(g["b_from"], g["b_to"], neg_to, neg_from, dtype=np.uint16)
+    loss = eng.step_host(torch.arange(m, dtype=torch.int64), blk, B)
+    np.testing.assert_allclose(loss, float(g["loss"]), rtol=2e-5)
+    np.testing.assert_allclose(eng.E_pos.cpu().numpy(), g["E_pos"].reshape(-1), rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(eng.E_neg.reshape(-1).cpu().numpy(), g["E_neg"].reshape(-1), rtol=2e-5, atol=2e-5)
+    for got, key in ((eng.g_table, "gW"), (eng.g_w, "g_fc_w"), (eng.g_b, "g_fc_b")):
+        scale = np.abs(g[key]).max()
+        np.testing.assert_allclose(got.cpu().numpy(), g[key], rtol=2e-3, atol=5e-5 * scale)
+    # Adam moved every parameter that has a gradient, in place
+    assert not torch.equal(table.cpu(), t(g["W0"])) and not torch.equal(fw.cpu(), t(g["fc_w"]))
+    assert n_lab == table.shape[0]

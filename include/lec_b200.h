@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LEC_ABI_VERSION 7
+#define LEC_ABI_VERSION 8
 
 /* geometry of the energy */
 #define LEC_GEOM_EUC 0 /* EucConesLoss.E_operator, order_embeddings.py:954-969 = oe.py:721-739 (cos-space) */
@@ -231,6 +231,20 @@ int lec_score_topk_ex(int geom, int precision, const float* labels, int64_t L, c
                       int64_t N, int D, float K, const int32_t* level_start, const int32_t* level_stop,
                       int n_levels, int k, float* scores, int scores_layout, int32_t* topk_idx,
                       float* topk_val, void* stream);
+
+/* Tensor-core variant (tcgen05.mma kind::tf32 with the 3xTF32 split, fp32 accumulators in TMEM, fused
+ * angle / aperture / top-k epilogue): the <label, image> contraction leaves the FMA pipe, which is what
+ * bounds lec_score_topk_ex at every D.  Hyperbolic geometry, LEC_PREC_F32, D <= 128, label-major scores.
+ * The label side is repacked once per call into `workspace` (device memory, 128-byte aligned, at least
+ * lec_score_workspace_bytes(L, D, n_levels) bytes, owned by the caller -- the library never allocates).
+ * lec_score_tc_supported returns 1 when this entry point accepts the combination, else 0 (use
+ * lec_score_topk_ex).  Same outputs and conventions as lec_score_topk_ex with LEC_SCORES_LABEL_MAJOR. */
+int lec_score_tc_supported(int geom, int precision, int D, int64_t L, int n_levels);
+int64_t lec_score_workspace_bytes(int64_t L, int D, int n_levels);
+int lec_score_topk_tc(int geom, int precision, const float* labels, int64_t L, const float* images, int64_t N,
+                      int D, float K, const int32_t* level_start, const int32_t* level_stop, int n_levels, int k,
+                      float* scores, int32_t* topk_idx, float* topk_val, void* workspace, int64_t workspace_bytes,
+                      void* stream);
 
 #ifdef __cplusplus
 }

@@ -14,13 +14,14 @@ LIB_PATH = os.path.join(_HERE, "_lib", "liblec_b200.so")
 GEOM = {"euc": 0, "hyp": 1, "oe": 2}
 ROWS_NONE, ROWS_EUC_SOFTCLIP, ROWS_HYP_SHELL, ROWS_HYP_TANH, ROWS_HYP_TANH_FEAT = 0, 1, 2, 3, 4
 PREC_F32, PREC_F64CORE = 0, 1
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 EXPORTS = (
     "lec_abi_version", "lec_error_string", "lec_launch_count", "lec_rows_fwd", "lec_rows_bwd", "lec_reduce_replicas",
     "lec_pairs_flat",
     "lec_pairs_grouped", "lec_energy_dense", "lec_energy_dense_bwd", "lec_rsgd_update", "lec_p2p_publish",
-    "lec_rsgd_update_p2p", "lec_cone_step", "lec_score_topk", "lec_score_topk_ex",
+    "lec_rsgd_update_p2p", "lec_cone_step", "lec_score_topk", "lec_score_topk_ex", "lec_score_tc_supported",
+    "lec_score_workspace_bytes", "lec_score_topk_tc",
 )
 
 
@@ -88,6 +89,11 @@ def lib():
                                      c_vp, c_vp]
         L.lec_score_topk_ex.argtypes = [c_i, c_i, c_vp, c_i64, c_vp, c_i64, c_i, c_f, c_vp, c_vp, c_i, c_i, c_vp, c_i,
                                         c_vp, c_vp, c_vp]
+        L.lec_score_tc_supported.argtypes = [c_i, c_i, c_i, c_i64, c_i]
+        L.lec_score_workspace_bytes.argtypes = [c_i64, c_i, c_i]
+        L.lec_score_workspace_bytes.restype = c_i64
+        L.lec_score_topk_tc.argtypes = [c_i, c_i, c_vp, c_i64, c_vp, c_i64, c_i, c_f, c_vp, c_vp, c_i, c_i, c_vp, c_vp,
+                                        c_vp, c_vp, c_i64, c_vp]
         for name in EXPORTS:
             getattr(L, name)
         if L.lec_abi_version() != ABI_VERSION:

@@ -27,6 +27,11 @@ int rsgd_p2p_launch(float*, void* const*, int64_t, int, int, int, unsigned, int6
 int score_launch(int, int, const float*, int64_t, const float*, int64_t, int, float, const int32_t*, const int32_t*,
                  int, int, float*, int64_t, int64_t, int32_t*, float*, cudaStream_t);
 
+bool score_mma_supported(int geom, int precision, int D, int64_t L, int n_levels);
+int64_t score_mma_workspace_bytes(int64_t L, int D, int n_levels);
+int score_mma_launch(const float*, int64_t, const float*, int64_t, int, float, const int32_t*, const int32_t*, int, int, float*,
+                     int32_t*, float*, void*, int64_t, cudaStream_t);
+
 static int pick_core(int geom, int precision) {
     if (precision != LEC_PREC_F32 && precision != LEC_PREC_F64CORE) return -1;
     switch (geom) {
@@ -267,6 +272,31 @@ int lec_score_topk_ex(int geom, int precision, const float* labels, int64_t L, c
     const int64_t s_lab = scores_layout == LEC_SCORES_IMAGE_MAJOR ? 1 : N;
     return score_launch(geom, precision, labels, L, images, N, D, K, level_start, level_stop, n_levels, k, scores,
                         s_img, s_lab, topk_idx, topk_val, (cudaStream_t)stream);
+}
+
+int lec_score_tc_supported(int geom, int precision, int D, int64_t L, int n_levels) {
+    return (n_levels >= 0 && n_levels <= LEC_MAX_LEVELS && L >= 0 && score_mma_supported(geom, precision, D, L, n_levels)) ? 1 : 0;
+}
+
+int64_t lec_score_workspace_bytes(int64_t L, int D, int n_levels) {
+    if (L < 0 || D < 1 || n_levels < 0) return 0;
+    return score_mma_workspace_bytes(L, D, n_levels);
+}
+
+int lec_score_topk_tc(int geom, int precision, const float* labels, int64_t L, const float* images, int64_t N, int D,
+                      float K, const int32_t* level_start, const int32_t* level_stop, int n_levels, int k, float* scores,
+                      int32_t* topk_idx, float* topk_val, void* workspace, int64_t workspace_bytes, void* stream) {
+    if (pick_core(geom, precision) < 0) return LEC_E_ENUM;
+    if (L < 0 || N < 0) return LEC_E_SIZE;
+    if (D < 1 || D > 128) return LEC_E_DIM;
+    if (n_levels < 0 || n_levels > LEC_MAX_LEVELS) return LEC_E_K;
+    if (topk_idx && (k < 1 || k > LEC_MAX_TOPK || n_levels < 1)) return LEC_E_K;
+    if (!topk_idx) { n_levels = 0; k = 1; }
+    if (!score_mma_supported(geom, precision, D, L, n_levels)) return LEC_E_ENUM;
+    if (n_levels > 0 && (!level_start || !level_stop)) return LEC_E_NULL;
+    if (N > 0 && L > 0 && (!labels || !images || !workspace)) return LEC_E_NULL;
+    return score_mma_launch(labels, L, images, N, D, K, level_start, level_stop, n_levels, k, scores, topk_idx, topk_val,
+                            workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int lec_score_topk(int geom, int precision, const float* labels, int64_t L, const float* images, int64_t N, int D,

@@ -32,6 +32,7 @@ struct GroupArgs {
     const float* w_pos; const float* w_neg;
     float K, alpha;
     float* E_pos; float* E_neg; double* loss_out; float* grad_rows; int grad_replicas; int64_t replica_stride;
+    int split;  // teams per group (>= 1): team s of a group takes negatives p = s, s + split, ... of both lists
 };
 
 struct DenseArgs {
@@ -142,7 +143,9 @@ __global__ void __launch_bounds__(kThreads) pairs_flat_kernel(const FlatArgs a) 
 // ------------------------------------------------------------------------------------------------
 // Training layout: one team per positive and its 2N negatives.  The gradients of the two shared
 // endpoints u_i, v_i are accumulated in registers and written with one vector reduction each; only
-// the 2N corrupted rows need their own reduction.
+// the 2N corrupted rows need their own reduction.  When a batch has too few positives to fill the GPU
+// (cfg4: 2 520 positives x 51 pairs), a group is split over `split` teams: team s evaluates the positive
+// (s == 0 only) and every split-th negative of both lists, and flushes its own partial sums for u_i, v_i.
 // ------------------------------------------------------------------------------------------------
 template <int CORE, int T, int V, bool GRAD>
 __global__ void __launch_bounds__(kThreads, LEC_GROUPED_MINBLOCKS) pairs_grouped_kernel(const GroupArgs a) {
@@ -151,15 +154,20 @@ __global__ void __launch_bounds__(kThreads, LEC_GROUPED_MINBLOCKS) pairs_grouped
     const int lane_t = threadIdx.x % T;
     const int64_t n_teams = (int64_t)gridDim.x * (kThreads / T);
     const int64_t team = (int64_t)blockIdx.x * (kThreads / T) + threadIdx.x / T;
-    const int64_t iters = (a.B + n_teams - 1) / n_teams;
+    const int split = a.split;
+    const int64_t n_items = a.B * split;
+    const int64_t iters = (n_items + n_teams - 1) / n_teams;
     const int Q = a.ld >> 2;
     const int N = a.N;
     float* const grad_base = GRAD ? a.grad_rows + (int64_t)(blockIdx.x % a.grad_replicas) * a.replica_stride : nullptr;
     double loss = 0.0;
     for (int64_t it = 0; it < iters; ++it) {
-        const int64_t gidx = team + it * n_teams;
-        const bool valid = gidx < a.B;
-        const int64_t gc = valid ? gidx : a.B - 1;
+        const int64_t item = team + it * n_teams;
+        const bool valid = item < n_items;
+        const int64_t ic_item = valid ? item : n_items - 1;
+        const int64_t gidx = ic_item / split;
+        const int sub = (int)(ic_item - gidx * split);
+        const int64_t gc = gidx;
         const bool writer = valid && lane_t == 0;
         const int64_t iu = ld_index(a.pos_from, gc, a.idx_bytes);
         const int64_t iv = ld_index(a.pos_to, gc, a.idx_bytes);
@@ -179,13 +187,17 @@ __global__ void __launch_bounds__(kThreads, LEC_GROUPED_MINBLOCKS) pairs_grouped
         PairGrad g;
         float E;
         double l = 0.0;
-        // positive (x = u, y = v)
+        // positive (x = u, y = v): evaluated by every team of a split group (eval_pair votes warp-wide, so it
+        // cannot sit in a divergent branch), counted by team 0 only
         {
+            const bool act = sub == 0;
             eval_pair<CORE, T, V, GRAD>(U, W, au, AW, g);
             const float w = a.w_pos ? __ldg(a.w_pos + gc) : 1.f;
-            const float cf = hinge(g.z, true, w, a.alpha, E, l);
-            if (writer) a.E_pos[gidx] = E;
-            if (GRAD && cf != 0.f) {
+            double lp = 0.0;
+            const float cf = hinge(g.z, true, w, a.alpha, E, lp);
+            if (act) l += lp;
+            if (writer && act) a.E_pos[gidx] = E;
+            if (GRAD && valid && act && cf != 0.f) {
                 touch_u = touch_w = true;
                 if (!Tr::cone) {
 #pragma unroll
@@ -202,7 +214,13 @@ __global__ void __launch_bounds__(kThreads, LEC_GROUPED_MINBLOCKS) pairs_grouped
         const int64_t nbase = gc * (int64_t)N;
         const int64_t ebase = gc * (int64_t)(2 * N);
         // negatives with a corrupted child: (x = u, y = c)
-        for (int p = 0; p < N; ++p) {
+        // every team of a warp runs the same number of trips (eval_pair votes warp-wide); surplus trips of a
+        // split group re-evaluate the last negative with their writes masked off
+        const int trips = (N + split - 1) / split;
+        for (int pi = 0; pi < trips; ++pi) {
+            const int pr = sub + pi * split;
+            const bool act = pr < N;
+            const int p = act ? pr : N - 1;
             const int64_t ic = ld_index(a.neg_to, nbase + p, a.idx_bytes);
             Vec<V> C;
             load_row<T, V>(C, a.rows, ic, a.ld, lane_t);
@@ -210,9 +228,11 @@ __global__ void __launch_bounds__(kThreads, LEC_GROUPED_MINBLOCKS) pairs_grouped
             if (Tr::hyp) AC = load_aux_A<Acc>(a.aux, ic);
             eval_pair<CORE, T, V, GRAD>(U, C, au, AC, g);
             const float w = a.w_neg ? __ldg(a.w_neg + ebase + p) : 1.f;
-            const float cf = hinge(g.z, false, w, a.alpha, E, l);
-            if (writer) a.E_neg[ebase + p] = E;
-            if (GRAD && valid && cf != 0.f) {
+            double lp = 0.0;
+            const float cf = hinge(g.z, false, w, a.alpha, E, lp);
+            if (act) l += lp;
+            if (writer && act) a.E_neg[ebase + p] = E;
+            if (GRAD && valid && act && cf != 0.f) {
                 touch_u = true;
                 float* gcp = grad_base + ic * (int64_t)a.ld;
                 if (Tr::cone) su_u += cf * g.zxx;
@@ -232,7 +252,10 @@ __global__ void __launch_bounds__(kThreads, LEC_GROUPED_MINBLOCKS) pairs_grouped
             }
         }
         // negatives with a corrupted parent: (x = c, y = v)
-        for (int p = 0; p < N; ++p) {
+        for (int pi = 0; pi < trips; ++pi) {
+            const int pr = sub + pi * split;
+            const bool act = pr < N;
+            const int p = act ? pr : N - 1;
             const int64_t ic = ld_index(a.neg_from, nbase + p, a.idx_bytes);
             Vec<V> C;
             load_row<T, V>(C, a.rows, ic, a.ld, lane_t);
@@ -240,9 +263,11 @@ __global__ void __launch_bounds__(kThreads, LEC_GROUPED_MINBLOCKS) pairs_grouped
             if (Tr::cone) ac = load_aux<Acc>(a.aux, ic);
             eval_pair<CORE, T, V, GRAD>(C, W, ac, AW, g);
             const float w = a.w_neg ? __ldg(a.w_neg + ebase + N + p) : 1.f;
-            const float cf = hinge(g.z, false, w, a.alpha, E, l);
-            if (writer) a.E_neg[ebase + N + p] = E;
-            if (GRAD && valid && cf != 0.f) {
+            double lp = 0.0;
+            const float cf = hinge(g.z, false, w, a.alpha, E, lp);
+            if (act) l += lp;
+            if (writer && act) a.E_neg[ebase + N + p] = E;
+            if (GRAD && valid && act && cf != 0.f) {
                 touch_w = true;
                 float* gcp = grad_base + ic * (int64_t)a.ld;
                 if (Tr::cone) sw_w += cf * g.zyy;
@@ -356,8 +381,15 @@ int launch_flat_tv(const FlatArgs& a, cudaStream_t st) {
 }
 
 template <int CORE, int T, int V>
-int launch_grouped_tv(const GroupArgs& a, cudaStream_t st) {
-    const int grid = grid_for(a.B, kThreads / T, 8);
+int launch_grouped_tv(const GroupArgs& a0, cudaStream_t st) {
+    GroupArgs a = a0;
+    // enough teams for ~2 full waves of resident threads; a group is never split finer than its N negatives
+    const int64_t want = (int64_t)sm_count() * 2048 * 2 / T;
+    int64_t split = a.B > 0 ? (want + a.B - 1) / a.B : 1;
+    if (split > a.N) split = a.N;
+    if (split < 1) split = 1;
+    a.split = (int)split;
+    const int grid = grid_for(a.B * split, kThreads / T, 8);
     if (a.grad_rows) pairs_grouped_kernel<CORE, T, V, true><<<grid, kThreads, 0, st>>>(a);
     else pairs_grouped_kernel<CORE, T, V, false><<<grid, kThreads, 0, st>>>(a);
     ++g_launches;

@@ -25,7 +25,7 @@
 //
 // Deferred angle (hyperbolic, top-k only -- what the reference's caller consumes): acos is monotone, so
 // E < thr  <=>  g > cos(thr + psi) = cos(thr) cos(psi) - sin(thr) sin(psi)  for thr + psi <= pi.  The main
-// loop therefore tests g against that bound (2 packed FMAs, minus a 1e-6 slack so rounding can only let
+// loop therefore tests g against that bound (2 packed FMAs, minus a 4e-6 slack so rounding can only let
 // extra candidates through) and appends {g, label, -psi} to the ring; the acos polynomial runs only for
 // ring entries inside merge(), with the same instruction sequence as the full-matrix path, so top-k
 // values are bit-identical to the matrix entries.  thr > pi/2 or an unfilled list accepts everything.
@@ -34,55 +34,9 @@
 #include <cstdlib>
 
 #include "lec_common.cuh"
+#include "lec_packed.cuh"
 
 namespace lec {
-
-typedef unsigned long long u64;
-
-__device__ __forceinline__ u64 pack2(float a, float b) {
-    u64 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-    return r;
-}
-__device__ __forceinline__ void unpack2(u64 v, float& a, float& b) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-}
-__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
-    u64 d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-__device__ __forceinline__ u64 fmul2(u64 a, u64 b) {
-    u64 d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-__device__ __forceinline__ u64 fadd2(u64 a, u64 b) {
-    u64 d;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-__device__ __forceinline__ float rsqrt_approx(float v) {
-    float r;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
-    return r;
-}
-__device__ __forceinline__ float sqrt_approx(float v) {
-    float r;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
-    return r;
-}
-// min / max that propagate NaN like torch.clamp
-__device__ __forceinline__ float max_nan(float a, float b) {
-    float r;
-    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
-    return r;
-}
-__device__ __forceinline__ float min_nan(float a, float b) {
-    float r;
-    asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
-    return r;
-}
 
 constexpr int kMaxSeg = 2 * LEC_MAX_LEVELS + 1;
 constexpr int kRingDefault = 16;  // candidate ring entries per thread
@@ -98,46 +52,6 @@ struct FastArgs {
     int64_t groups;  // image groups of NT*RI images
     int ring;        // candidate ring entries per thread (> RI)
 };
-
-// acos(|g|-part) coefficients, Abramowitz & Stegun 4.4.46: acos(x) = sqrt(1-x) * sum a_i x^i, |err| <= 2e-8 on [0,1]
-#define LEC_ACOS_A0 1.5707963050f
-#define LEC_ACOS_A1 -0.2145988016f
-#define LEC_ACOS_A2 0.0889789874f
-#define LEC_ACOS_A3 -0.0501743046f
-#define LEC_ACOS_A4 0.0308918810f
-#define LEC_ACOS_A5 -0.0170881256f
-#define LEC_ACOS_A6 0.0066700901f
-#define LEC_ACOS_A7 -0.0012624911f
-
-// theta = acos(clamp(g, -1+1e-5, 1-1e-5)) for a packed pair; NaN propagates
-__device__ __forceinline__ u64 acos_clamped2(u64 g2) {
-    float g0, g1;
-    unpack2(g2, g0, g1);
-    const float lo = -1.f + kClampEps, hi = 1.f - kClampEps;
-    g0 = min_nan(max_nan(g0, lo), hi);
-    g1 = min_nan(max_nan(g1, lo), hi);
-    const float a0 = fabsf(g0), a1 = fabsf(g1);
-    const u64 ax = pack2(a0, a1);
-    const u64 t = ffma2(ax, pack2(-1.f, -1.f), pack2(1.f, 1.f));  // 1 - |g| (exact for |g| >= 0.5)
-    float t0, t1;
-    unpack2(t, t0, t1);
-    const u64 sq = pack2(sqrt_approx(t0), sqrt_approx(t1));
-    u64 P = pack2(LEC_ACOS_A7, LEC_ACOS_A7);
-    P = ffma2(P, ax, pack2(LEC_ACOS_A6, LEC_ACOS_A6));
-    P = ffma2(P, ax, pack2(LEC_ACOS_A5, LEC_ACOS_A5));
-    P = ffma2(P, ax, pack2(LEC_ACOS_A4, LEC_ACOS_A4));
-    P = ffma2(P, ax, pack2(LEC_ACOS_A3, LEC_ACOS_A3));
-    P = ffma2(P, ax, pack2(LEC_ACOS_A2, LEC_ACOS_A2));
-    P = ffma2(P, ax, pack2(LEC_ACOS_A1, LEC_ACOS_A1));
-    P = ffma2(P, ax, pack2(LEC_ACOS_A0, LEC_ACOS_A0));
-    const u64 r = fmul2(sq, P);
-    // g < 0: pi - r ; else r     (sign and offset taken from the sign bit)
-    const float sg0 = __int_as_float((__float_as_int(g0) & 0x80000000) | 0x3f800000);
-    const float sg1 = __int_as_float((__float_as_int(g1) & 0x80000000) | 0x3f800000);
-    const float b0 = __int_as_float((__float_as_int(g0) >> 31) & 0x40490fdb);
-    const float b1 = __int_as_float((__float_as_int(g1) >> 31) & 0x40490fdb);
-    return ffma2(pack2(sg0, sg1), r, pack2(b0, b1));
-}
 
 // Shared-memory layout of one staged label: DQ float4 chunks of the row (zero padded), then one float4
 // of constants.   hyp: {A, 1+A, A^2, -psi} {cos psi, sin psi, 0, 0}   euc: {A, t0, 0, 0}   oe: unused
@@ -281,7 +195,7 @@ __global__ void __launch_bounds__(NT, MINB) score_fast_kernel(const FastArgs a) 
     auto filter_terms = [&](float t, float psi_max, float& c, float& ns, float& off) {
         if (t <= 0.f) { c = 0.f; ns = 0.f; off = INFINITY; }                         // k zeros already: nothing can beat them
         else if (!(t + psi_max <= 3.1415f)) { c = 0.f; ns = 0.f; off = -INFINITY; }  // list not full / thr + psi may pass pi
-        else { float sn, cs; sincosf(t, &sn, &cs); c = cs; ns = -sn; off = -1e-6f; }
+        else { float sn, cs; __sincosf(t, &sn, &cs); c = cs; ns = -sn; off = -4e-6f; }  // MUFU sin/cos: |err| < 2e-6 on [0, pi]
     };
     auto refresh_filter = [&]() {
         const float psi_max = *psi_max_s;

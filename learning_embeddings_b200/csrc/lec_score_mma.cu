@@ -1,0 +1,564 @@
+// Tensor-core path of the all-pairs image x label scoring (hyperbolic cones), sm_100a only.
+//
+// Replaces the per-image CPU loop of JointEmbeddings.calculate_classification_metrics
+// (oe_h.py:2018-2036): e[i, l] = E(x = label_l, y = image_i), then per level topk(k, largest=False).
+//
+// The only part of the energy that couples an image with a label is p = <x, y>; everything else is a
+// per-image or a per-label scalar.  So the [128 images] x [64 labels] block of dot products is one
+// tcgen05.mma (kind::tf32, M=128, N=64, fp32 accumulator in TMEM), made fp32-accurate by the 3xTF32 split
+//     x = x_hi + x_lo,  y = y_hi + y_lo   (hi = tf32 round-to-nearest, lo = tf32(rest))
+//     <x, y> ~= y_hi.x_hi + y_hi.x_lo + y_lo.x_hi        (the dropped lo.lo term is 2^-22 |x||y|)
+// issued as three K-passes over the same accumulator, and the FMA pipe is left with the epilogue only:
+// each thread owns one image (= one TMEM lane), pulls 16 label columns at a time with tcgen05.ld and runs
+// the angle / aperture algebra on packed label PAIRS (fma.rn.f32x2), then either stores the label-major
+// score matrix (32 consecutive images per warp store: coalesced) or feeds the per-level top-k.
+//
+// Data movement:
+//   labels  -> lec_score_mma_prep (one small launch): per chunk of 64 labels a "blob" in the caller's
+//              workspace = B_hi tile | B_lo tile (K-major, no-swizzle UMMA canonical layout) | per-label-pair
+//              constants {A, 1+A, A^2, -psi, cos psi, sin psi} (fp64-computed, same terms as lec_rows_fwd's
+//              aux) | header.  The main kernel pulls blobs with cp.async.bulk (TMA, mbarrier complete_tx),
+//              double buffered.
+//   images  -> each CTA reads its 128 rows once, splits them into hi/lo and writes the A tiles to shared
+//              memory itself (generic proxy + fence.proxy.async).
+//   accumulators: TMEM, 2 x 64 columns: the MMAs of chunk c+1 run while the epilogue of chunk c executes.
+//
+// UMMA canonical layout used for both operands (Major-K, SWIZZLE_NONE; cute/atom/mma_traits_sm100.hpp
+// "((8,n),2):((1,SBO),LBO)" in 16-byte units): a core matrix is 8 rows x 16 bytes stored contiguously
+// (128 B); element (row r, k) of a tile with R rows lives at byte (k/4)*(16 R) + 16 r + 4 (k%4), i.e.
+// LBO = 16 R (next 16-byte K group), SBO = 128 (next 8 rows).  One MMA consumes K = 8 tf32 = two K groups.
+#include <cstdio>
+
+#include "lec_common.cuh"
+#include "lec_packed.cuh"
+
+namespace lec {
+
+constexpr int kMmaM = 128;       // images per CTA (TMEM lanes)
+constexpr int kMmaN = 64;        // labels per chunk (TMEM columns per accumulator buffer)
+constexpr int kMmaMaxChunks = 224;
+constexpr int kMmaRingCheck = 8; // ring room needed between two merge checks (4 label pairs)
+
+struct MmaChunk { int label0; short count; signed char level; unsigned char flags; };  // flags: 1 first, 2 last chunk of its level
+struct MmaChunkTable { int n; MmaChunk c[kMmaMaxChunks]; };
+
+struct MmaHdr { int label0, count, level, flags; float psi_max; int pad[3]; };  // 32 bytes, tail of a blob
+
+__host__ __device__ inline int mma_kp(int D) { return (D + 7) / 8 * 8; }
+__host__ __device__ inline int mma_tile_bytes(int Kp) { return kMmaN * Kp * 4; }                 // one B tile (hi or lo)
+__host__ __device__ inline int mma_const_bytes() { return (kMmaN / 2) * 12 * 4; }               // 32 pairs x 12 floats
+__host__ __device__ inline int mma_blob_bytes(int Kp) { return 2 * mma_tile_bytes(Kp) + mma_const_bytes() + (int)sizeof(MmaHdr); }
+
+__device__ __forceinline__ float to_tf32(float v) {
+    unsigned r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+
+// ------------------------------------------------------------------------------------------------
+// prep: labels -> chunk blobs
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kMmaN) score_mma_prep_kernel(const float* __restrict__ labels, int D, int Kp, float K,
+                                                                const MmaChunkTable tab, unsigned char* __restrict__ ws) {
+    const int c = blockIdx.x, j = threadIdx.x;
+    const MmaChunk ch = tab.c[c];
+    unsigned char* blob = ws + (size_t)c * mma_blob_bytes(Kp);
+    float* hi = reinterpret_cast<float*>(blob);
+    float* lo = reinterpret_cast<float*>(blob + mma_tile_bytes(Kp));
+    float* cst = reinterpret_cast<float*>(blob + 2 * mma_tile_bytes(Kp));
+    const bool live = j < ch.count;
+    const float* src = labels + (int64_t)(ch.label0 + (live ? j : 0)) * D;
+    double A = 0.0;
+    for (int k0 = 0; k0 < Kp; k0 += 4) {
+        float h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int k = k0 + e;
+            const float v = (live && k < D) ? __ldg(src + k) : 0.f;
+            A += (double)v * (double)v;
+            h[e] = to_tf32(v);
+            l[e] = to_tf32(v - h[e]);
+        }
+        const int off = (k0 >> 2) * (kMmaN * 4) + j * 4;  // floats: K group * (16 B * 64 rows) + row * 16 B
+        *reinterpret_cast<float4*>(hi + off) = make_float4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<float4*>(lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+    }
+    const Aux<double> x = row_aux<double>(LEC_GEOM_HYP, live ? A : 0.25, K);
+    const double Av = live ? A : 0.25;
+    const double sp = sin(x.t0);
+    float* q = cst + (j >> 1) * 12 + (j & 1);
+    q[0] = (float)Av; q[2] = (float)(1.0 + Av); q[4] = (float)(Av * Av); q[6] = (float)(-x.t0);
+    q[8] = (float)sqrt(fmax(0.0, 1.0 - sp * sp)); q[10] = (float)sp;
+    // largest half-aperture of the chunk (for the deferred-angle filter's validity test thr + psi <= pi)
+    float pm = live ? (float)x.t0 : -INFINITY;
+    __shared__ float wmax[kMmaN / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pm = fmaxf(pm, __shfl_xor_sync(0xffffffffu, pm, o));
+    if ((j & 31) == 0) wmax[j >> 5] = pm;
+    __syncthreads();
+    if (j == 0) {
+        MmaHdr* h = reinterpret_cast<MmaHdr*>(blob + 2 * mma_tile_bytes(Kp) + mma_const_bytes());
+        h->label0 = ch.label0; h->count = ch.count; h->level = ch.level; h->flags = ch.flags;
+        h->psi_max = fmaxf(wmax[0], wmax[1]);
+        h->pad[0] = h->pad[1] = h->pad[2] = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers (tcgen05 / mbarrier / bulk copy)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Spins on the phase; a lost arrival traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned ok = 0;
+    for (unsigned spin = 0; !ok; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (!ok && spin > (1u << 24)) __trap();
+    }
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(unsigned dst_smem, unsigned cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(unsigned taddr, unsigned cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(unsigned bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::tf32, issued by one thread
+__device__ __forceinline__ void tc_mma_tf32(unsigned d_tmem, uint64_t a_desc, uint64_t b_desc, unsigned idesc, unsigned accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(unsigned taddr, float (&v)[16]) {
+    unsigned r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// shared-memory matrix descriptor: Major-K, SWIZZLE_NONE, version 1 (cute/arch/mma_sm100_desc.hpp SmemDescriptor)
+__device__ __forceinline__ uint64_t umma_desc(unsigned saddr, unsigned lbo_bytes, unsigned sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) | (1ull << 46);
+}
+// instruction descriptor (InstrDescriptor): D fp32, A/B tf32, both K-major, N = 64, M = 128
+__host__ __device__ constexpr unsigned umma_idesc_tf32(int M, int Nn) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(Nn >> 3) << 17) | ((unsigned)(M >> 4) << 24);
+}
+
+struct MmaArgs {
+    const float* images; int64_t N; int D; int Kp;
+    const unsigned char* ws; int n_chunks;
+    float* scores;           // label-major [L, N] or NULL
+    int32_t* topk_idx; float* topk_val; int k, n_levels;
+    int ring;                // candidate ring entries per thread
+};
+
+constexpr int kEpiThreads = 2 * kMmaM;          // 8 epilogue warps: two threads per image, 32 label columns each
+constexpr int kMmaThreads = kEpiThreads + 32;   // + one producer warp (TMA bulk copies + tcgen05.mma issue)
+constexpr int kHalfCols = kMmaN / 2;
+
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() {  // named barrier of the 256 epilogue threads (the producer warp never joins)
+    asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32]) {
+    unsigned r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Warp roles: warps 0..7 = epilogue (warp w reads TMEM lanes 32 (w % 4) .., columns 32 (w / 4) .. of every chunk),
+// warp 8 = producer.  Pipelines: full[s] (blob landed), done[s] (accumulator complete), empty[s] (all 256 epilogue
+// threads are finished with blob stage s and accumulator buffer s), two stages each.
+// MODE 0: top-k only (deferred angle), 1: matrix only, 2: matrix + top-k
+template <int MODE>
+__global__ void __launch_bounds__(kMmaThreads, 1) score_mma_kernel(const MmaArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int Kp = a.Kp, KC = Kp >> 2, KS = Kp >> 3;
+    const int a_tile = kMmaM * Kp * 4;           // bytes of one A tile (hi or lo)
+    const int b_tile = mma_tile_bytes(Kp);
+    const int blob = mma_blob_bytes(Kp);
+    unsigned char* sA = smem_raw;                // A_hi | A_lo
+    unsigned char* sB = sA + 2 * a_tile;         // 2 blob stages
+    float2* top = reinterpret_cast<float2*>(sB + 2 * blob);                        // [k][256] {E, label}
+    float2* ring = top + (size_t)a.k * kEpiThreads;                                  // [ring][256] {E or g, label}
+    float* ringp = reinterpret_cast<float*>(ring + (size_t)a.ring * kEpiThreads);    // [ring][256] -psi
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ringp + (size_t)a.ring * kEpiThreads);  // full[2], done[2], empty[2]
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 6);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const unsigned bar_full0 = smem_u32(bars), bar_done0 = smem_u32(bars + 2), bar_empty0 = smem_u32(bars + 4);
+
+    if (warp == 8) tmem_alloc(smem_u32(tmem_slot), 2 * kMmaN);
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(bar_full0 + 8 * s, 1);
+            mbar_init(bar_done0 + 8 * s, 1);
+            mbar_init(bar_empty0 + 8 * s, kEpiThreads);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+
+    // ---- image rows -> hi/lo A tiles (two threads per row split the K groups), |y|^2 per thread
+    const int row = tid & (kMmaM - 1), half = (tid >> 7) & 1;
+    const int64_t img = (int64_t)blockIdx.x * kMmaM + row;
+    const bool img_ok = img < a.N;
+    float Bn = 0.f;
+    if (tid < kEpiThreads) {
+        const float* src = a.images + (img_ok ? img : 0) * (int64_t)a.D;
+        float* hi = reinterpret_cast<float*>(sA);
+        float* lo = reinterpret_cast<float*>(sA + a_tile);
+        for (int kc = 0; kc < KC; ++kc) {
+            float h[4], l[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int k = 4 * kc + e;
+                const float v = (img_ok && k < a.D) ? __ldg(src + k) : 0.f;
+                Bn = fmaf(v, v, Bn);
+                h[e] = to_tf32(v);
+                l[e] = to_tf32(v - h[e]);
+            }
+            if ((kc & 1) == half) {
+                const int off = kc * (kMmaM * 4) + row * 4;
+                *reinterpret_cast<float4*>(hi + off) = make_float4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<float4*>(lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+            }
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // A tiles: generic-proxy writes -> async-proxy (UMMA) reads
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmem_base = *tmem_slot;
+
+    // ================================ producer warp ================================
+    if (warp == 8) {
+        if ((tid & 31) == 0) {
+            const unsigned sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+            const unsigned idesc = umma_idesc_tf32(kMmaM, kMmaN);
+            auto load_chunk = [&](int c) {
+                const int s = c & 1;
+                mbar_expect_tx(bar_full0 + 8 * s, (unsigned)blob);
+                bulk_g2s(sB_u + s * blob, a.ws + (size_t)c * blob, (unsigned)blob, bar_full0 + 8 * s);
+            };
+            load_chunk(0);
+            if (a.n_chunks > 1) load_chunk(1);
+            for (int c = 0; c < a.n_chunks; ++c) {
+                const int s = c & 1;
+                mbar_wait(bar_full0 + 8 * s, (unsigned)((c >> 1) & 1));
+                // accumulator buffer s was drained by the epilogue of chunk c-2: blob c was only requested after
+                // empty[s] fired for that chunk, so the wait above already implies it
+                tc_fence_after();
+                const unsigned d = tmem_base + (unsigned)(s * kMmaN);
+                const unsigned bh = sB_u + s * blob, bl = bh + b_tile;
+                const unsigned ah = sA_u, al = sA_u + a_tile;
+                unsigned acc = 0;
+                for (int pass = 0; pass < 3; ++pass) {
+                    const unsigned pa = (pass == 2) ? al : ah;   // hi.hi, hi.lo, lo.hi
+                    const unsigned pb = (pass == 1) ? bl : bh;
+                    for (int ks = 0; ks < KS; ++ks) {
+                        tc_mma_tf32(d, umma_desc(pa + ks * 2 * (kMmaM * 16), kMmaM * 16, 128),
+                                    umma_desc(pb + ks * 2 * (kMmaN * 16), kMmaN * 16, 128), idesc, acc);
+                        acc = 1;
+                    }
+                }
+                tc_commit(bar_done0 + 8 * s);
+                // refill the other stage with chunk c+1's successor once its consumers are done
+                if (c >= 1 && c + 1 < a.n_chunks) {
+                    const int so = s ^ 1;
+                    mbar_wait(bar_empty0 + 8 * so, (unsigned)(((c - 1) >> 1) & 1));   // epilogue of chunk c-1 finished
+                    load_chunk(c + 1);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================================ epilogue warps ================================
+        const u64 B2 = pack2(Bn, Bn), C2 = pack2(-1.f - Bn, -1.f - Bn);
+        const int k = a.k;
+        const int et = tid;  // 0..255: slot in the per-thread top / ring arrays
+        const unsigned ring0 = smem_u32(ring + et), ringp0 = smem_u32(ringp + et);
+        unsigned rp = ring0;
+        const unsigned ring_trigger = ring0 + (unsigned)(a.ring - kMmaRingCheck) * kEpiThreads * 8;
+        float thr = INFINITY;                  // MODE 2: k-th best energy so far
+        float cT = 0.f, nsT = 0.f, off = -INFINITY;  // MODE 0: accept g >= cT cos(psi) - sT sin(psi) + off
+        float psi_max = 0.f;
+        float2* mytop = top + et;
+        const float2* peer_top = top + (et ^ kMmaM);   // the thread scanning the other 32 columns for the same image
+
+        auto refresh = [&]() {
+            // both halves feed one top-k: the tighter of the two k-th bests is a valid bound for either
+            const float t = fminf(mytop[(size_t)(k - 1) * kEpiThreads].x, peer_top[(size_t)(k - 1) * kEpiThreads].x);
+            thr = t;
+            if (t <= 0.f) { cT = 0.f; nsT = 0.f; off = INFINITY; }
+            else if (!(t + psi_max <= 3.1415f)) { cT = 0.f; nsT = 0.f; off = -INFINITY; }
+            else { float sn, cs; __sincosf(t, &sn, &cs); cT = cs; nsT = -sn; off = -4e-6f; }
+        };
+        auto insert = [&](float Ev, float lab_f) {   // into this thread's sorted list; ties keep the lower label first
+            if (Ev < mytop[(size_t)(k - 1) * kEpiThreads].x ||
+                (Ev == mytop[(size_t)(k - 1) * kEpiThreads].x && __float_as_int(lab_f) < __float_as_int(mytop[(size_t)(k - 1) * kEpiThreads].y))) {
+                int pos = k - 1;
+                while (pos > 0) {
+                    const float2 prev = mytop[(size_t)(pos - 1) * kEpiThreads];
+                    if (!(prev.x > Ev || (prev.x == Ev && __float_as_int(prev.y) > __float_as_int(lab_f)))) break;
+                    mytop[(size_t)pos * kEpiThreads] = prev;
+                    --pos;
+                }
+                mytop[(size_t)pos * kEpiThreads] = make_float2(Ev, lab_f);
+            }
+        };
+        auto merge = [&]() {
+            const int cnt = (int)((rp - ring0) / (kEpiThreads * 8));
+            for (int j = 0; j < cnt; ++j) {
+                const float2 e = ring[j * kEpiThreads + et];
+                float Ev = e.x;
+                if (MODE == 0) {  // deferred: the ring holds g; same instruction sequence as the matrix path
+                    const float np = ringp[j * kEpiThreads + et];
+                    float z0, z1;
+                    unpack2(fadd2(acos_clamped2(pack2(e.x, e.x)), pack2(np, np)), z0, z1);
+                    Ev = max_nan(z0, 0.f);
+                }
+                insert(Ev, e.y);
+            }
+            rp = ring0;
+            refresh();
+        };
+
+        const int lane_base = (warp & 3) * 32;
+        for (int c = 0; c < a.n_chunks; ++c) {
+            const int s = c & 1;
+            const unsigned par = (unsigned)((c >> 1) & 1);
+            mbar_wait(bar_full0 + 8 * s, par);   // constants + header of chunk c visible to this thread
+            const unsigned char* bl = sB + (size_t)s * blob;
+            const float* cst = reinterpret_cast<const float*>(bl + 2 * b_tile);
+            const MmaHdr hdr = *reinterpret_cast<const MmaHdr*>(bl + 2 * b_tile + mma_const_bytes());
+            const bool want_topk = (MODE != 1) && hdr.level >= 0;
+            if (want_topk) {
+                if (hdr.flags & 1) {
+                    for (int j = 0; j < k; ++j) mytop[(size_t)j * kEpiThreads] = make_float2(INFINITY, __int_as_float(-1));
+                    rp = ring0;
+                    epi_bar_sync();   // both halves reset before either reads the other's k-th best
+                }
+                psi_max = hdr.psi_max;
+                refresh();
+            }
+            mbar_wait(bar_done0 + 8 * s, par);   // accumulator of chunk c complete
+            tc_fence_after();
+
+            const int cbase = half * kHalfCols;              // this thread's first column of the chunk
+            const int my_count = hdr.count - cbase;          // columns of mine that hold labels (<= 0: none)
+            if (my_count > 0) {
+                float p[32];
+                tmem_ld32(tmem_base + ((unsigned)lane_base << 16) + (unsigned)(s * kMmaN + cbase), p);
+                float* out = (MODE != 0 && a.scores != nullptr && img_ok)
+                                 ? a.scores + (int64_t)(hdr.label0 + cbase) * a.N + img : nullptr;
+                const float* cp = cst + (cbase >> 1) * 12;
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const int col = 2 * q;
+                    if (col < my_count) {   // uniform over the CTA half
+                        const float4 k0 = *reinterpret_cast<const float4*>(cp + q * 12);       // A, A', 1+A, 1+A'
+                        const float4 k1 = *reinterpret_cast<const float4*>(cp + q * 12 + 4);   // A^2, A'^2, -psi, -psi'
+                        const u64 A2 = pack2(k0.x, k0.y), A12 = pack2(k0.z, k0.w), ASQ = pack2(k1.x, k1.y), NPSI = pack2(k1.z, k1.w);
+                        const u64 P = pack2(p[2 * q], p[2 * q + 1]);
+                        const u64 M2 = pack2(-2.f, -2.f), ONE2 = pack2(1.f, 1.f);
+                        const u64 qq = fmul2(P, M2);
+                        const u64 num = ffma2(P, A12, fmul2(A2, C2));            // p(1+A) - A(1+B)
+                        const u64 w2 = fadd2(qq, ffma2(A2, B2, ONE2));           // 1 + AB - 2p
+                        const u64 as2 = ffma2(A2, qq, ffma2(A2, B2, ASQ));       // A (A + B - 2p)
+                        const u64 d2 = fmul2(as2, w2);
+                        float d0, d1;
+                        unpack2(d2, d0, d1);
+                        const u64 g = fmul2(num, pack2(rsqrt_approx(d0), rsqrt_approx(d1)));
+                        const bool second = col + 1 < my_count;
+                        const int lab = hdr.label0 + cbase + col;
+                        if (MODE == 0) {
+                            if (want_topk) {
+                                const float4 k2 = *reinterpret_cast<const float4*>(cp + q * 12 + 8);  // cos psi x2, sin psi x2
+                                const u64 cb = ffma2(pack2(cT, cT), pack2(k2.x, k2.y), ffma2(pack2(nsT, nsT), pack2(k2.z, k2.w), pack2(off, off)));
+                                float g0, g1, b0, b1;
+                                unpack2(g, g0, g1);
+                                unpack2(cb, b0, b1);
+                                if (g0 >= b0) {
+                                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(rp), "f"(g0), "r"(lab) : "memory");
+                                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(ringp0 + ((rp - ring0) >> 1)), "f"(k1.z) : "memory");
+                                    rp += kEpiThreads * 8;
+                                }
+                                if (second && g1 >= b1) {
+                                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(rp), "f"(g1), "r"(lab + 1) : "memory");
+                                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(ringp0 + ((rp - ring0) >> 1)), "f"(k1.w) : "memory");
+                                    rp += kEpiThreads * 8;
+                                }
+                            }
+                        } else {
+                            float z0, z1;
+                            unpack2(fadd2(acos_clamped2(g), NPSI), z0, z1);
+                            const float E0 = max_nan(z0, 0.f), E1 = max_nan(z1, 0.f);
+                            if (out != nullptr) {
+                                out[0] = E0;
+                                if (second) out[a.N] = E1;
+                                out += 2 * a.N;
+                            }
+                            if (MODE == 2 && want_topk) {
+                                if (E0 < thr) {
+                                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(rp), "f"(E0), "r"(lab) : "memory");
+                                    rp += kEpiThreads * 8;
+                                }
+                                if (second && E1 < thr) {
+                                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(rp), "f"(E1), "r"(lab + 1) : "memory");
+                                    rp += kEpiThreads * 8;
+                                }
+                            }
+                        }
+                    }
+                    if (MODE != 1 && (q & 3) == 3) {
+                        if (__any_sync(0xffffffffu, rp > ring_trigger)) merge();
+                    }
+                }
+            }
+            if (want_topk && (hdr.flags & 2)) {
+                merge();
+                epi_bar_sync();       // both halves' lists are final
+                if (half == 0) {
+                    for (int j = 0; j < k; ++j) {   // fold the other half's k best into mine
+                        const float2 e = peer_top[(size_t)j * kEpiThreads];
+                        if (__float_as_int(e.y) >= 0) insert(e.x, e.y);
+                    }
+                    if (img_ok) {
+                        const int64_t o = (img * a.n_levels + hdr.level) * k;
+                        for (int j = 0; j < k; ++j) {
+                            const float2 e = mytop[(size_t)j * kEpiThreads];
+                            a.topk_idx[o + j] = __float_as_int(e.y);
+                            if (a.topk_val) a.topk_val[o + j] = e.x;
+                        }
+                    }
+                }
+                epi_bar_sync();       // the next level's reset must not overtake the fold
+            }
+            // this thread is done with accumulator buffer s and blob stage s
+            tc_fence_before();
+            mbar_arrive(bar_empty0 + 8 * s);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem_base, 2 * kMmaN);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static int build_chunks(int64_t L, const int32_t* level_start, const int32_t* level_stop, int n_levels, bool gaps, MmaChunkTable& t) {
+    t.n = 0;
+    auto add_segment = [&](int64_t s, int64_t e, int level) -> bool {
+        for (int64_t l0 = s; l0 < e || (l0 == s && level >= 0); l0 += kMmaN) {
+            if (t.n >= kMmaMaxChunks) return false;
+            MmaChunk& c = t.c[t.n++];
+            const int64_t cnt = e - l0 < kMmaN ? e - l0 : kMmaN;
+            c.label0 = (int)l0; c.count = (short)(cnt < 0 ? 0 : cnt); c.level = (signed char)level;
+            c.flags = (unsigned char)((l0 == s ? 1 : 0) | (l0 + kMmaN >= e ? 2 : 0));
+            if (e <= s) break;  // empty level: one empty chunk so that its top-k rows are still written
+        }
+        return true;
+    };
+    int64_t cursor = 0;
+    for (int i = 0; i < n_levels; ++i) {
+        int64_t s = level_start[i], e = level_stop[i];
+        if (s < cursor || e < s) return LEC_E_K;
+        if (e > L) e = L;
+        if (s > L) s = L;
+        if (gaps && s > cursor && !add_segment(cursor, s, -1)) return LEC_E_SIZE;
+        if (!add_segment(s, e, i)) return LEC_E_SIZE;
+        cursor = e;
+    }
+    if (gaps && cursor < L && !add_segment(cursor, L, -1)) return LEC_E_SIZE;
+    return 0;
+}
+
+int64_t score_mma_workspace_bytes(int64_t L, int D, int n_levels) {
+    const int64_t chunks = (L + kMmaN - 1) / kMmaN + 2 * (int64_t)n_levels + 2;
+    return chunks * mma_blob_bytes(mma_kp(D));
+}
+
+bool score_mma_supported(int geom, int precision, int D, int64_t L, int n_levels) {
+    return geom == LEC_GEOM_HYP && precision == LEC_PREC_F32 && D >= 1 && D <= 128 &&
+           (L + kMmaN - 1) / kMmaN + 2 * n_levels + 2 <= kMmaMaxChunks;
+}
+
+int score_mma_launch(const float* labels, int64_t L, const float* images, int64_t N, int D, float K, const int32_t* level_start,
+                     const int32_t* level_stop, int n_levels, int k, float* scores, int32_t* topk_idx, float* topk_val,
+                     void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+    if (N == 0 || L == 0) return 0;
+    MmaChunkTable tab;
+    if (int e = build_chunks(L, level_start, level_stop, topk_idx ? n_levels : 0, scores != nullptr, tab)) return e;
+    if (tab.n == 0) return 0;
+    const int Kp = mma_kp(D);
+    const int blob = mma_blob_bytes(Kp);
+    if ((int64_t)tab.n * blob > workspace_bytes) return LEC_E_SIZE;
+    if (reinterpret_cast<uintptr_t>(workspace) & 127) return LEC_E_ALIGN;
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    score_mma_prep_kernel<<<tab.n, kMmaN, 0, st>>>(labels, D, Kp, K, tab, ws);
+    ++g_launches;
+    cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) return (int)ce;
+
+    MmaArgs a{};
+    a.images = images; a.N = N; a.D = D; a.Kp = Kp; a.ws = ws; a.n_chunks = tab.n; a.scores = scores;
+    a.topk_idx = topk_idx; a.topk_val = topk_val; a.k = topk_idx ? k : 1; a.n_levels = n_levels;
+    a.ring = topk_idx ? 16 : 0;   // matrix-only launches need no candidate ring
+    const size_t smem = (size_t)2 * kMmaM * Kp * 4 + (size_t)2 * blob + (size_t)a.k * kEpiThreads * 8 + (size_t)a.ring * kEpiThreads * 12 + 128;
+    const int mode = topk_idx ? (scores ? 2 : 0) : 1;
+    const int64_t grid = (N + kMmaM - 1) / kMmaM;
+    if (grid > 0x7fffffffLL) return LEC_E_SIZE;
+    auto launch = [&](auto kern) -> int {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        kern<<<(unsigned)grid, kMmaThreads, smem, st>>>(a);
+        ++g_launches;
+        return (int)cudaGetLastError();
+    };
+    if (mode == 0) return launch(score_mma_kernel<0>);
+    if (mode == 1) return launch(score_mma_kernel<1>);
+    return launch(score_mma_kernel<2>);
+}
+
+}  // namespace lec

@@ -297,8 +297,20 @@ def rsgd_update_(table, grad, lr, r_in, textbook_lambda=False, write_rescaled_gr
 # --------------------------------------------------------------------------------------------------
 # Scoring
 # --------------------------------------------------------------------------------------------------
+_score_ws = {}  # device -> workspace tensor of the tensor-core scoring path (grown on demand, reused)
+
+
+def _score_workspace(dev, nbytes):
+    ws = _score_ws.get(dev)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(int(nbytes) + 128, device=dev, dtype=torch.uint8)
+        _score_ws[dev] = ws
+    off = (-ws.data_ptr()) % 128
+    return ws[off:]
+
+
 def score_topk(labels, images, geom, K, level_start, level_stop, k=5, want_scores=False, want_values=True,
-               precision=PREC_F32, scores_layout="label_major"):  # scoring only ranks: the fp32 core is the default here
+               precision=PREC_F32, scores_layout="label_major", engine="auto"):  # scoring only ranks: fp32 core by default
     """Per image, per level: the k labels of lowest energy E(x=label, y=image) (lec_score_topk_ex).
 
     Returns (topk_idx int32 [N, n_levels, k], topk_val float32 or None, scores [N, L] or None).  With the
@@ -319,6 +331,20 @@ def score_topk(labels, images, geom, K, level_start, level_stop, k=5, want_score
     scores = None
     if want_scores:
         scores = torch.empty((L, n_img) if layout == 1 else (n_img, L), device=dev, dtype=torch.float32)
+    # engine: "tc" = tcgen05 tensor-core contraction + fused epilogue (lec_score_topk_tc), "simt" = the packed-FMA
+    # tile kernel (lec_score_topk_ex); "auto" takes the tensor-core path whenever the library supports the case
+    lib = N.lib()
+    tc_ok = layout == 1 and bool(lib.lec_score_tc_supported(GEOM[geom], int(precision), D, L, nl))
+    if engine == "tc" and not tc_ok:
+        raise N.LecError("tensor-core scoring supports hyperbolic cones, fp32 core, label-major scores, D <= 128")
+    if tc_ok and engine in ("auto", "tc"):
+        nbytes = int(lib.lec_score_workspace_bytes(L, D, nl))
+        ws = _score_workspace(dev, nbytes)
+        N.check(lib.lec_score_topk_tc(GEOM[geom], int(precision), N._p(labels), L, N._p(images), n_img, D,
+                                      float(K or 0.0), ctypes.cast(ls, ctypes.c_void_p), ctypes.cast(le, ctypes.c_void_p),
+                                      nl, int(k), N._p(scores), N._p(idx), N._p(val), N._p(ws), nbytes, N.stream_ptr(dev)),
+                "lec_score_topk_tc")
+        return idx, val, (scores.t() if scores is not None else None)
     N.check(N.lib().lec_score_topk_ex(GEOM[geom], int(precision), N._p(labels), L, N._p(images), n_img, D,
                                       float(K or 0.0), ctypes.cast(ls, ctypes.c_void_p), ctypes.cast(le, ctypes.c_void_p),
                                       nl, int(k), N._p(scores), layout, N._p(idx), N._p(val), N.stream_ptr(dev)),

@@ -32,11 +32,23 @@ def make_inputs(n_img, D, dev, seed=0):
     return h, labels.to(dev), images.to(dev)
 
 
-def run(lib, geom, prec, labels, images, h, k, scores, layout, idx, val, st):
+WS = {}
+
+
+def run(lib, geom, prec, labels, images, h, k, scores, layout, idx, val, st, engine="simt"):
     L, D = labels.shape
     nl = len(h.level_start)
     ls = (ctypes.c_int32 * nl)(*h.level_start)
     le = (ctypes.c_int32 * nl)(*h.level_stop)
+    if engine == "tc":
+        nb = int(lib.lec_score_workspace_bytes(L, D, nl))
+        if WS.get("ws") is None or WS["ws"].numel() < nb + 128:
+            WS["ws"] = torch.empty(nb + 128, device=labels.device, dtype=torch.uint8)
+        ws = WS["ws"][(-WS["ws"].data_ptr()) % 128:]
+        N.check(lib.lec_score_topk_tc(ops.GEOM[geom], prec, N._p(labels), L, N._p(images), images.shape[0], D, 0.1,
+                                      ctypes.cast(ls, ctypes.c_void_p), ctypes.cast(le, ctypes.c_void_p), nl, k,
+                                      N._p(scores), N._p(idx), N._p(val), N._p(ws), nb, st), "lec_score_topk_tc")
+        return
     N.check(lib.lec_score_topk_ex(ops.GEOM[geom], prec, N._p(labels), L, N._p(images), images.shape[0], D, 0.1,
                                   ctypes.cast(ls, ctypes.c_void_p), ctypes.cast(le, ctypes.c_void_p), nl, k,
                                   N._p(scores), layout, N._p(idx), N._p(val), st), "lec_score_topk_ex")
@@ -66,6 +78,7 @@ def main():
     ap.add_argument("--geoms", default="hyp")
     ap.add_argument("--precs", default="0")
     ap.add_argument("--modes", default="topk,matrix_lm,both_lm,both_im")
+    ap.add_argument("--engines", default="simt")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     lib = N.lib()
@@ -83,26 +96,29 @@ def main():
         scores = torch.empty((L, n_img), device=dev, dtype=torch.float32)
         for geom in args.geoms.split(","):
             for prec in [int(x) for x in args.precs.split(",")]:
+              for engine in args.engines.split(","):
                 for mode in args.modes.split(","):
+                    if engine == "tc" and (mode == "both_im" or geom != "hyp" or prec != 0):
+                        continue
                     if mode == "topk":
-                        fn = lambda: run(lib, geom, prec, labels, images, h, 5, None, 1, idx, val, st)
+                        fn = lambda: run(lib, geom, prec, labels, images, h, 5, None, 1, idx, val, st, engine)
                         byts = n_img * (4 * D + 160)
                     elif mode == "matrix_lm":
-                        fn = lambda: run(lib, geom, prec, labels, images, h, 5, scores, 1, None, None, st)
+                        fn = lambda: run(lib, geom, prec, labels, images, h, 5, scores, 1, None, None, st, engine)
                         byts = n_img * L * 4 + n_img * 4 * D
                     elif mode == "both_lm":
-                        fn = lambda: run(lib, geom, prec, labels, images, h, 5, scores, 1, idx, val, st)
+                        fn = lambda: run(lib, geom, prec, labels, images, h, 5, scores, 1, idx, val, st, engine)
                         byts = n_img * L * 4 + n_img * (4 * D + 160)
                     else:
-                        fn = lambda: run(lib, geom, prec, labels, images, h, 5, scores, 0, idx, val, st)
+                        fn = lambda: run(lib, geom, prec, labels, images, h, 5, scores, 0, idx, val, st, engine)
                         byts = n_img * L * 4 + n_img * (4 * D + 160)
                     med, best = timeit(fn, args.iters)
-                    rec = {"geom": geom, "D": D, "prec": prec, "mode": mode, "images": n_img, "labels": L, "ms_median": med,
+                    rec = {"geom": geom, "D": D, "prec": prec, "mode": mode, "engine": engine, "images": n_img, "labels": L, "ms_median": med,
                            "ms_best": best, "Gscores_per_s": n_img * L / med / 1e6, "algorithmic_GBps": byts / med / 1e6,
                            "frac_of_measured_hbm_peak": byts / med / 1e6 / peak}
                     out.append(rec)
-                    print("%s D=%d prec=%d %-10s: %8.3f ms (best %8.3f)  %8.1f Gscores/s  %7.1f GB/s algorithmic (%.1f%% of %.0f)"
-                          % (geom, D, prec, mode, med, best, rec["Gscores_per_s"], rec["algorithmic_GBps"],
+                    print("%s %s D=%d prec=%d %-10s: %8.3f ms (best %8.3f)  %8.1f Gscores/s  %7.1f GB/s algorithmic (%.1f%% of %.0f)"
+                          % (engine, geom, D, prec, mode, med, best, rec["Gscores_per_s"], rec["algorithmic_GBps"],
                              100 * rec["frac_of_measured_hbm_peak"], peak), flush=True)
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(out, open("gpurun_out/score_bench.json", "w"), indent=1)

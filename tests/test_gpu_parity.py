@@ -357,14 +357,19 @@ def test_hyperbolic_training_step_with_rsgd_matches_reference_update(ethec):
 # ------------------------------------------------------------------------------------------------
 # scoring
 # ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("engine", ("simt", "tc"))
 @pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("name,geom", [("scoring_hyp_D10", "hyp"), ("scoring_hyp_D50", "hyp"),
                                        ("scoring_euc_D10", "euc"), ("scoring_oe_D10", "oe")])
-def test_scoring_matches_reference_loop(name, geom, prec):
+def test_scoring_matches_reference_loop(name, geom, prec, engine):
+    """engine "simt": packed-FMA tile kernel (lec_score_topk_ex); "tc": tcgen05 3xTF32 contraction with the fused
+    epilogue (lec_score_topk_tc, hyperbolic + fp32 core only).  Same contract for both."""
+    if engine == "tc" and not (geom == "hyp" and prec == 0):
+        pytest.skip("the tensor-core path is built for the hyperbolic energy with the fp32 core")
     g = load_golden(name)
     K = float(g["K"])
     idx, val, scores = ops.score_topk(t(g["labels"]).to(DEV), t(g["images"]).to(DEV), geom, K, g["level_start"],
-                                      g["level_stop"], k=5, want_scores=True, precision=prec)
+                                      g["level_stop"], k=5, want_scores=True, precision=prec, engine=engine)
     contract(scores.cpu().numpy(), g["E64"], g["E"], name + " scores", fp32_core=(geom == "hyp" and prec == 0))
     tv = g["top_val"]
     contract(val.cpu().numpy(), tv, tv, name + " topk values", floor=5e-6)
@@ -379,6 +384,11 @@ def test_scoring_matches_reference_loop(name, geom, prec):
     # top-k agrees with torch.topk over the kernel's own full score matrix
     ridx, rval = cones.topk_per_level(scores.cpu(), g["level_start"], g["level_stop"], 5)
     np.testing.assert_array_equal(val.cpu().numpy(), rval.numpy())
+    # top-k only (no matrix) returns the same values bit for bit (tc: deferred-angle path), and so does matrix only
+    idx2, val2, _ = ops.score_topk(t(g["labels"]).to(DEV), t(g["images"]).to(DEV), geom, K, g["level_start"],
+                                   g["level_stop"], k=5, want_scores=False, precision=prec, engine=engine)
+    assert torch.equal(val2, val)
+    assert (idx2.cpu().numpy()[distinct] == g["top_idx"][distinct]).all()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -450,19 +460,22 @@ def test_empty_and_degenerate_batches():
     assert torch.isnan(cones.energy_euc(x.cpu(), y.cpu(), 3.0)).all()
 
 
-def test_scoring_full_size_properties():
+@pytest.mark.parametrize("engine,D", [("simt", 10), ("tc", 10), ("tc", 50)])
+def test_scoring_full_size_properties(engine, D):
     """1 M-image scale is covered by bench.py; here 40 K images x 723 labels: top-k of the kernel equals
     torch.topk of its own score matrix, shards concatenate, and image order does not matter."""
+    import functools
     gen = torch.Generator().manual_seed(3)
     h = load_golden("ethec_hierarchy")
-    L, D, n_img = 723, 10, 40000
+    L, n_img = 723, 40000 + 37   # not a multiple of any tile size
+    score_topk = functools.partial(ops.score_topk, engine=engine)
     labels = torch.zeros(L, D)
     for l in range(4):
         s, e = int(h["level_start"][l]), int(h["level_stop"][l])
         labels[s:e] = _ball(gen, e - s, D, 0.10 + 0.2 * l, 0.30 + 0.2 * l)
     images = _ball(gen, n_img, D, 0.30, 0.95)
     lab_d, img_d = labels.to(DEV), images.to(DEV)
-    idx, val, scores = ops.score_topk(lab_d, img_d, "hyp", 0.1, h["level_start"], h["level_stop"], k=5, want_scores=True)
+    idx, val, scores = score_topk(lab_d, img_d, "hyp", 0.1, h["level_start"], h["level_stop"], k=5, want_scores=True)
     ridx, rval = cones.topk_per_level(scores.cpu(), h["level_start"], h["level_stop"], 5)
     np.testing.assert_array_equal(val.cpu().numpy(), rval.numpy())
     # exact ties (also one between the k-th and the (k+1)-th energy) leave the label choice open
@@ -473,11 +486,11 @@ def test_scoring_full_size_properties():
     ref32 = cones.score_matrix("hyp", labels, images[:512], 0.1)
     contract(scores[:512].cpu().numpy(), ref.numpy(), ref32.numpy(), "scores", fp32_core=True)
     # sharding: two halves give the same answer as one call
-    i1, v1, _ = ops.score_topk(lab_d, img_d[: n_img // 2], "hyp", 0.1, h["level_start"], h["level_stop"], k=5)
-    i2, v2, _ = ops.score_topk(lab_d, img_d[n_img // 2:], "hyp", 0.1, h["level_start"], h["level_stop"], k=5)
+    i1, v1, _ = score_topk(lab_d, img_d[: n_img // 2], "hyp", 0.1, h["level_start"], h["level_stop"], k=5)
+    i2, v2, _ = score_topk(lab_d, img_d[n_img // 2:], "hyp", 0.1, h["level_start"], h["level_stop"], k=5)
     assert torch.equal(torch.cat([i1, i2]), idx) and torch.equal(torch.cat([v1, v2]), val)
     perm = torch.randperm(n_img, generator=gen).to(DEV)
-    ip, vp, _ = ops.score_topk(lab_d, img_d[perm], "hyp", 0.1, h["level_start"], h["level_stop"], k=5)
+    ip, vp, _ = score_topk(lab_d, img_d[perm], "hyp", 0.1, h["level_start"], h["level_stop"], k=5)
     assert torch.equal(ip, idx[perm]) and torch.equal(vp, val[perm])
 
 

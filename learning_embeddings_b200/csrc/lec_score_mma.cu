@@ -28,6 +28,7 @@
 // (128 B); element (row r, k) of a tile with R rows lives at byte (k/4)*(16 R) + 16 r + 4 (k%4), i.e.
 // LBO = 16 R (next 16-byte K group), SBO = 128 (next 8 rows).  One MMA consumes K = 8 tf32 = two K groups.
 #include <cstdio>
+#include <type_traits>
 
 #include "lec_common.cuh"
 #include "lec_packed.cuh"
@@ -151,6 +152,21 @@ __device__ __forceinline__ void tc_mma_tf32(unsigned d_tmem, uint64_t a_desc, ui
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// same with the A operand read from tensor memory (lane = row, one 32-bit column per K element)
+__device__ __forceinline__ void tc_mma_tf32_ts(unsigned d_tmem, unsigned a_tmem, uint64_t b_desc, unsigned idesc, unsigned accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// this thread's lane, 8 consecutive columns
+__device__ __forceinline__ void tmem_st8(unsigned taddr, const float (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                   "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+                   "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])) : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(unsigned taddr, float (&v)[16]) {
     unsigned r[16];
     asm volatile(
@@ -178,10 +194,12 @@ struct MmaArgs {
     float* scores;           // label-major [L, N] or NULL
     int32_t* topk_idx; float* topk_val; int k, n_levels;
     int ring;                // candidate ring entries per thread
+    int stages;              // blob stages in shared memory = accumulator buffers in TMEM (2..4)
 };
 
+constexpr int kMmaMaxStages = 4;
 constexpr int kEpiThreads = 2 * kMmaM;          // 8 epilogue warps: two threads per image, 32 label columns each
-constexpr int kMmaThreads = kEpiThreads + 32;   // + one producer warp (TMA bulk copies + tcgen05.mma issue)
+constexpr int kMmaThreads = kEpiThreads + 64;   // + warp 8 (tcgen05.mma issue) + warp 9 (TMA bulk copies)
 constexpr int kHalfCols = kMmaN / 2;
 
 __device__ __forceinline__ void mbar_arrive(unsigned bar) {
@@ -206,30 +224,35 @@ __device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32]) {
 }
 
 // Warp roles: warps 0..7 = epilogue (warp w reads TMEM lanes 32 (w % 4) .., columns 32 (w / 4) .. of every chunk),
-// warp 8 = producer.  Pipelines: full[s] (blob landed), done[s] (accumulator complete), empty[s] (all 256 epilogue
+// warp 8 = MMA issuer (warp-uniform code so descriptors live in uniform registers; one lane issues), warp 9 =
+// loader (one lane issues the bulk copies).  Pipelines: full[s] (blob landed), done[s] (accumulator complete), empty[s] (all 256 epilogue
 // threads are finished with blob stage s and accumulator buffer s), two stages each.
 // MODE 0: top-k only (deferred angle), 1: matrix only, 2: matrix + top-k
 template <int MODE>
 __global__ void __launch_bounds__(kMmaThreads, 1) score_mma_kernel(const MmaArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int Kp = a.Kp, KC = Kp >> 2, KS = Kp >> 3;
-    const int a_tile = kMmaM * Kp * 4;           // bytes of one A tile (hi or lo)
+    const int Kp = a.Kp, KS = Kp >> 3;
     const int b_tile = mma_tile_bytes(Kp);
     const int blob = mma_blob_bytes(Kp);
-    unsigned char* sA = smem_raw;                // A_hi | A_lo
-    unsigned char* sB = sA + 2 * a_tile;         // 2 blob stages
-    float2* top = reinterpret_cast<float2*>(sB + 2 * blob);                        // [k][256] {E, label}
+    const int NS = a.stages;
+    unsigned char* sB = smem_raw;                // NS blob stages
+    float2* top = reinterpret_cast<float2*>(sB + (size_t)NS * blob);               // [k][256] {E, label}
     float2* ring = top + (size_t)a.k * kEpiThreads;                                  // [ring][256] {E or g, label}
     float* ringp = reinterpret_cast<float*>(ring + (size_t)a.ring * kEpiThreads);    // [ring][256] -psi
-    uint64_t* bars = reinterpret_cast<uint64_t*>(ringp + (size_t)a.ring * kEpiThreads);  // full[2], done[2], empty[2]
-    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 6);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ringp + (size_t)a.ring * kEpiThreads);  // full[4], done[4], empty[4]
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 3 * kMmaMaxStages);
 
     const int tid = threadIdx.x, warp = tid >> 5;
-    const unsigned bar_full0 = smem_u32(bars), bar_done0 = smem_u32(bars + 2), bar_empty0 = smem_u32(bars + 4);
+    const unsigned bar_full0 = smem_u32(bars), bar_done0 = smem_u32(bars + kMmaMaxStages), bar_empty0 = smem_u32(bars + 2 * kMmaMaxStages);
+    // tensor memory: NS accumulator buffers of 64 columns, then the image tile as the A operand: A_hi | A_lo, Kp
+    // columns each (lane = image row); rounded up to a power of two
+    const unsigned col_ahi = (unsigned)(NS * kMmaN), col_alo = col_ahi + (unsigned)Kp;
+    unsigned tmem_cols = 32;
+    while (tmem_cols < col_alo + (unsigned)Kp) tmem_cols <<= 1;
 
-    if (warp == 8) tmem_alloc(smem_u32(tmem_slot), 2 * kMmaN);
+    if (warp == 8) tmem_alloc(smem_u32(tmem_slot), tmem_cols);   // the allocating warp also frees
     if (tid == 0) {
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < NS; ++s) {
             mbar_init(bar_full0 + 8 * s, 1);
             mbar_init(bar_done0 + 8 * s, 1);
             mbar_init(bar_empty0 + 8 * s, kEpiThreads);
@@ -237,77 +260,81 @@ __global__ void __launch_bounds__(kMmaThreads, 1) score_mma_kernel(const MmaArgs
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
 
-    // ---- image rows -> hi/lo A tiles (two threads per row split the K groups), |y|^2 per thread
+    // ---- image rows -> the A operand in tensor memory.  Two threads per row: warps 0-3 write the tf32 hi parts,
+    //      warps 4-7 the lo parts (a warp can only touch TMEM lanes 32 (warp % 4) ..); both keep |y|^2.
+    tc_fence_before();
+    __syncthreads();           // TMEM base address + mbarrier inits visible
+    tc_fence_after();
+    const unsigned tmem_base = *tmem_slot;
     const int row = tid & (kMmaM - 1), half = (tid >> 7) & 1;
     const int64_t img = (int64_t)blockIdx.x * kMmaM + row;
     const bool img_ok = img < a.N;
     float Bn = 0.f;
     if (tid < kEpiThreads) {
         const float* src = a.images + (img_ok ? img : 0) * (int64_t)a.D;
-        float* hi = reinterpret_cast<float*>(sA);
-        float* lo = reinterpret_cast<float*>(sA + a_tile);
-        for (int kc = 0; kc < KC; ++kc) {
-            float h[4], l[4];
+        const unsigned dst = tmem_base + ((unsigned)((warp & 3) * 32) << 16) + (half ? col_alo : col_ahi);
+        for (int k0 = 0; k0 < Kp; k0 += 8) {
+            float o[8];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int k = 4 * kc + e;
+            for (int e = 0; e < 8; ++e) {
+                const int k = k0 + e;
                 const float v = (img_ok && k < a.D) ? __ldg(src + k) : 0.f;
                 Bn = fmaf(v, v, Bn);
-                h[e] = to_tf32(v);
-                l[e] = to_tf32(v - h[e]);
+                const float h = to_tf32(v);
+                o[e] = half ? to_tf32(v - h) : h;
             }
-            if ((kc & 1) == half) {
-                const int off = kc * (kMmaM * 4) + row * 4;
-                *reinterpret_cast<float4*>(hi + off) = make_float4(h[0], h[1], h[2], h[3]);
-                *reinterpret_cast<float4*>(lo + off) = make_float4(l[0], l[1], l[2], l[3]);
-            }
+            tmem_st8(dst + (unsigned)k0, o);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    } else if (warp == 9 && (tid & 31) == 0) {
+        // the first NS label blobs stream in while the image tile is being converted
+        const unsigned sB_u = smem_u32(sB);
+        for (int c = 0; c < NS && c < a.n_chunks; ++c) {
+            mbar_expect_tx(bar_full0 + 8 * c, (unsigned)blob);
+            bulk_g2s(sB_u + c * blob, a.ws + (size_t)c * blob, (unsigned)blob, bar_full0 + 8 * c);
         }
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // A tiles: generic-proxy writes -> async-proxy (UMMA) reads
     tc_fence_before();
-    __syncthreads();
+    __syncthreads();           // A operand complete before the first MMA
     tc_fence_after();
-    const unsigned tmem_base = *tmem_slot;
 
-    // ================================ producer warp ================================
-    if (warp == 8) {
+    // ================================ producer warps ================================
+    if (warp == 9) {
+        // loader: blob c goes into stage c % NS as soon as the epilogue of chunk c - NS has released it
         if ((tid & 31) == 0) {
-            const unsigned sA_u = smem_u32(sA), sB_u = smem_u32(sB);
-            const unsigned idesc = umma_idesc_tf32(kMmaM, kMmaN);
-            auto load_chunk = [&](int c) {
-                const int s = c & 1;
+            const unsigned sB_u = smem_u32(sB);
+            for (int c = NS; c < a.n_chunks; ++c) {
+                const int s = c % NS;
+                mbar_wait(bar_empty0 + 8 * s, (unsigned)(((c - NS) / NS) & 1));
                 mbar_expect_tx(bar_full0 + 8 * s, (unsigned)blob);
                 bulk_g2s(sB_u + s * blob, a.ws + (size_t)c * blob, (unsigned)blob, bar_full0 + 8 * s);
-            };
-            load_chunk(0);
-            if (a.n_chunks > 1) load_chunk(1);
-            for (int c = 0; c < a.n_chunks; ++c) {
-                const int s = c & 1;
-                mbar_wait(bar_full0 + 8 * s, (unsigned)((c >> 1) & 1));
-                // accumulator buffer s was drained by the epilogue of chunk c-2: blob c was only requested after
-                // empty[s] fired for that chunk, so the wait above already implies it
-                tc_fence_after();
-                const unsigned d = tmem_base + (unsigned)(s * kMmaN);
-                const unsigned bh = sB_u + s * blob, bl = bh + b_tile;
-                const unsigned ah = sA_u, al = sA_u + a_tile;
-                unsigned acc = 0;
-                for (int pass = 0; pass < 3; ++pass) {
-                    const unsigned pa = (pass == 2) ? al : ah;   // hi.hi, hi.lo, lo.hi
-                    const unsigned pb = (pass == 1) ? bl : bh;
-                    for (int ks = 0; ks < KS; ++ks) {
-                        tc_mma_tf32(d, umma_desc(pa + ks * 2 * (kMmaM * 16), kMmaM * 16, 128),
-                                    umma_desc(pb + ks * 2 * (kMmaN * 16), kMmaN * 16, 128), idesc, acc);
-                        acc = 1;
-                    }
-                }
-                tc_commit(bar_done0 + 8 * s);
-                // refill the other stage with chunk c+1's successor once its consumers are done
-                if (c >= 1 && c + 1 < a.n_chunks) {
-                    const int so = s ^ 1;
-                    mbar_wait(bar_empty0 + 8 * so, (unsigned)(((c - 1) >> 1) & 1));   // epilogue of chunk c-1 finished
-                    load_chunk(c + 1);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 8) {
+        // MMA issuer: runs up to NS - 1 chunks ahead of the epilogue.  Accumulator buffer c % NS is free when blob c
+        // has landed, because the loader only requested blob c after empty[c % NS] fired for chunk c - NS.
+        const unsigned sB_u = smem_u32(sB);
+        const unsigned idesc = umma_idesc_tf32(kMmaM, kMmaN);
+        const bool issuer = (tid & 31) == 0;
+        for (int c = 0; c < a.n_chunks; ++c) {
+            const int s = c % NS;
+            mbar_wait(bar_full0 + 8 * s, (unsigned)((c / NS) & 1));
+            tc_fence_after();
+            const unsigned d = tmem_base + (unsigned)(s * kMmaN);
+            const unsigned bh = sB_u + s * blob, bl = bh + b_tile;
+            unsigned acc = 0;
+            for (int pass = 0; pass < 3; ++pass) {
+                const unsigned pa = tmem_base + ((pass == 2) ? col_alo : col_ahi);   // hi.hi, hi.lo, lo.hi
+                const unsigned pb = (pass == 1) ? bl : bh;
+                for (int ks = 0; ks < KS; ++ks) {
+                    const uint64_t db = umma_desc(pb + ks * 2 * (kMmaN * 16), kMmaN * 16, 128);
+                    if (issuer) tc_mma_tf32_ts(d, pa + (unsigned)(ks * 8), db, idesc, acc);
+                    acc = 1;
                 }
             }
+            if (issuer) tc_commit(bar_done0 + 8 * s);
+            __syncwarp();
         }
         __syncwarp();
     } else {
@@ -364,8 +391,8 @@ __global__ void __launch_bounds__(kMmaThreads, 1) score_mma_kernel(const MmaArgs
 
         const int lane_base = (warp & 3) * 32;
         for (int c = 0; c < a.n_chunks; ++c) {
-            const int s = c & 1;
-            const unsigned par = (unsigned)((c >> 1) & 1);
+            const int s = c % NS;
+            const unsigned par = (unsigned)((c / NS) & 1);
             mbar_wait(bar_full0 + 8 * s, par);   // constants + header of chunk c visible to this thread
             const unsigned char* bl = sB + (size_t)s * blob;
             const float* cst = reinterpret_cast<const float*>(bl + 2 * b_tile);
@@ -391,10 +418,12 @@ __global__ void __launch_bounds__(kMmaThreads, 1) score_mma_kernel(const MmaArgs
                 float* out = (MODE != 0 && a.scores != nullptr && img_ok)
                                  ? a.scores + (int64_t)(hdr.label0 + cbase) * a.N + img : nullptr;
                 const float* cp = cst + (cbase >> 1) * 12;
+                auto columns = [&](auto full_c) {   // FULL: all 32 columns hold labels, no bound checks
+                constexpr bool FULL = decltype(full_c)::value != 0;
 #pragma unroll
                 for (int q = 0; q < 16; ++q) {
                     const int col = 2 * q;
-                    if (col < my_count) {   // uniform over the CTA half
+                    if (FULL || col < my_count) {   // uniform over the CTA half
                         const float4 k0 = *reinterpret_cast<const float4*>(cp + q * 12);       // A, A', 1+A, 1+A'
                         const float4 k1 = *reinterpret_cast<const float4*>(cp + q * 12 + 4);   // A^2, A'^2, -psi, -psi'
                         const u64 A2 = pack2(k0.x, k0.y), A12 = pack2(k0.z, k0.w), ASQ = pack2(k1.x, k1.y), NPSI = pack2(k1.z, k1.w);
@@ -408,7 +437,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) score_mma_kernel(const MmaArgs
                         float d0, d1;
                         unpack2(d2, d0, d1);
                         const u64 g = fmul2(num, pack2(rsqrt_approx(d0), rsqrt_approx(d1)));
-                        const bool second = col + 1 < my_count;
+                        const bool second = FULL || col + 1 < my_count;
                         const int lab = hdr.label0 + cbase + col;
                         if (MODE == 0) {
                             if (want_topk) {
@@ -453,6 +482,9 @@ __global__ void __launch_bounds__(kMmaThreads, 1) score_mma_kernel(const MmaArgs
                         if (__any_sync(0xffffffffu, rp > ring_trigger)) merge();
                     }
                 }
+                };
+                if (my_count >= kHalfCols) columns(std::integral_constant<int, 1>());
+                else columns(std::integral_constant<int, 0>());
             }
             if (want_topk && (hdr.flags & 2)) {
                 merge();
@@ -481,7 +513,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) score_mma_kernel(const MmaArgs
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem_base, 2 * kMmaN);
+    if (warp == 8) tmem_dealloc(tmem_base, tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -545,7 +577,12 @@ int score_mma_launch(const float* labels, int64_t L, const float* images, int64_
     a.images = images; a.N = N; a.D = D; a.Kp = Kp; a.ws = ws; a.n_chunks = tab.n; a.scores = scores;
     a.topk_idx = topk_idx; a.topk_val = topk_val; a.k = topk_idx ? k : 1; a.n_levels = n_levels;
     a.ring = topk_idx ? 16 : 0;   // matrix-only launches need no candidate ring
-    const size_t smem = (size_t)2 * kMmaM * Kp * 4 + (size_t)2 * blob + (size_t)a.k * kEpiThreads * 8 + (size_t)a.ring * kEpiThreads * 12 + 128;
+    const size_t fixed = (size_t)a.k * kEpiThreads * 8 + (size_t)a.ring * kEpiThreads * 12 + 256;
+    // two blob stages + two accumulator buffers keep a CTA within 256 TMEM columns and ~half of the shared memory,
+    // so two CTAs (20 warps) share an SM; wide rows fall back to one CTA per SM
+    a.stages = 2;
+    const size_t smem = fixed + (size_t)a.stages * blob;
+    if (smem > 227 * 1024) return LEC_E_DIM;
     const int mode = topk_idx ? (scores ? 2 : 0) : 1;
     const int64_t grid = (N + kMmaM - 1) / kMmaM;
     if (grid > 0x7fffffffLL) return LEC_E_SIZE;

@@ -1,0 +1,14 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests -m gpu -q -x --no-header -p no:cacheprovider -k "scoring" > gpurun_out/pytest_score.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest_score.log
+tail -4 gpurun_out/pytest_score.log
+timeout 300 python scripts/score_bench.py --dims 10,50 --iters 7 --modes topk,matrix_lm,both_lm --engines tc > gpurun_out/score_bench.log 2>&1
+cat gpurun_out/score_bench.log
+for D in 50; do
+  timeout 200 ncu --set full --clock-control none --import-source on -k regex:score_mma_kernel -s 2 -c 2 -o /tmp/prof_tc_d$D \
+      python scripts/score_bench.py --images 303104 --dims $D --iters 1 --modes topk,matrix_lm --engines tc > gpurun_out/ncu_tc_d$D.log 2>&1
+  ncu -i /tmp/prof_tc_d$D.ncu-rep --page raw --csv > gpurun_out/tc_d${D}_raw.csv 2>/dev/null
+  ncu -i /tmp/prof_tc_d$D.ncu-rep --page source --csv > gpurun_out/tc_d${D}_source.csv 2>/dev/null
+done

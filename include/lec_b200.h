@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LEC_ABI_VERSION 8
+#define LEC_ABI_VERSION 9
 
 /* geometry of the energy */
 #define LEC_GEOM_EUC 0 /* EucConesLoss.E_operator, order_embeddings.py:954-969 = oe.py:721-739 (cos-space) */
@@ -56,6 +56,8 @@ extern "C" {
 #define LEC_E_K         (-6) /* k out of range for top-k */
 #define LEC_E_REPLICAS  (-7) /* grad_replicas < 1 */
 #define LEC_E_PEERS     (-8) /* world/rank/slot out of range or slot_floats too small */
+#define LEC_E_EMPTY     (-9) /* a negative draw has no candidate (random.choice([]) -> IndexError in the reference) */
+#define LEC_E_INDEX     (-10) /* node index outside [0, n_nodes) */
 #define LEC_MAX_DIM 1024
 #define LEC_MAX_TOPK 8
 #define LEC_MAX_LEVELS 8
@@ -245,6 +247,52 @@ int lec_score_topk_tc(int geom, int precision, const float* labels, int64_t L, c
                       int D, float K, const int32_t* level_start, const int32_t* level_stop, int n_levels, int k,
                       float* scores, int32_t* topk_idx, float* topk_val, void* workspace, int64_t workspace_bytes,
                       void* stream);
+
+/* ---- negative-edge sampler ----------------------------------------------------------------------
+ * Replaces sample_negative_edge (order_embeddings.py:989-1008; joint variant oe.py:755-808) and the
+ * B x N x 2 Python loop that calls it (order_embeddings.py:1070-1091, oe.py:846-863).  The reference's
+ * dense negative_G (ones - transitive closure - diagonal, order_embeddings.py:417-423, oe.py:465-474) is
+ * replaced by two CSR lists of EXCLUDED node ids, each sorted ascending:
+ *   row_excl[row_excl_ptr[u] .. row_excl_ptr[u+1])   u itself and every closure descendant of u
+ *   col_excl[col_excl_ptr[v] .. col_excl_ptr[v+1])   v itself and every closure ancestor of v
+ * so the candidates of "corrupt the child of u" are [0, n_nodes) minus row_excl(u), in ascending order
+ * (= np.where(negative_G[u, :] == 1)[0]), and likewise for "corrupt the parent of v" with col_excl(v).
+ * pick_per_level != 0 restricts draw p to level (p % level_mod): label levels [level_start, level_stop)
+ * for p % level_mod < n_levels (level_mod = n_levels, order_embeddings.py:990-1006); joint graphs pass
+ * level_mod = n_levels + 1 and n_labels > 0, the extra slot being the image level (oe.py:786-804: label
+ * candidates when the fixed endpoint is an image, image candidates otherwise).
+ * Output layout: neg_to[i*N + p] = corrupted child of u_i, neg_from[i*N + p] = corrupted parent
+ * of v_i; draw order per positive i, per p: row draw, then column draw. */
+typedef struct {
+    int64_t n_nodes;
+    const int64_t* row_excl_ptr; const int32_t* row_excl;
+    const int64_t* col_excl_ptr; const int32_t* col_excl;
+    int pick_per_level; int n_levels; int level_mod;
+    int32_t level_start[LEC_MAX_LEVELS]; int32_t level_stop[LEC_MAX_LEVELS];
+    int64_t n_labels; /* joint graphs: node ids >= n_labels are images; 0 = label-only graph */
+} lec_sampler_graph;
+
+/* CPython's Mersenne Twister state (Modules/_randommodule.c): random.getstate()[1] = mt[0..623] + (index,) */
+typedef struct { uint32_t mt[624]; int32_t index; } lec_mt19937;
+/* random.seed(int): key = little-endian 32-bit words of |a| ({0} for 0), init_by_array */
+int lec_mt_seed(lec_mt19937* s, const uint32_t* key, int key_words);
+uint32_t lec_mt_uint32(lec_mt19937* s);
+/* Random._randbelow_with_getrandbits(n), 0 < n < 2^32; LEC_E_EMPTY for n == 0 */
+int64_t lec_mt_randbelow(lec_mt19937* s, uint32_t n);
+/* EXACT mode, HOST pointers everywhere, runs on the calling thread: consumes `rng` exactly as the
+ * reference's random.choice calls would (load random.getstate() before, store it back after), so the
+ * indices are bit-exact.  LEC_E_EMPTY where the reference raises IndexError (rng is left mid-stream). */
+int lec_sample_negatives(lec_mt19937* rng, const lec_sampler_graph* g, const int64_t* u, const int64_t* v,
+                         int64_t B, int N, int64_t* neg_to, int64_t* neg_from);
+/* FAST mode, one kernel: same candidate sets, same uniform law, Philox4x32-10 keyed by `seed`, counter
+ * (draw id = (i*N + p)*2 + side, stream_id); not the reference's stream.  `g` is a HOST struct holding DEVICE
+ * pointers; u, v, neg_to, neg_from are device arrays of idx_bytes-wide indices; *status (device int, zeroed
+ * by the caller) receives LEC_E_EMPTY / LEC_E_INDEX if any draw failed. */
+int lec_sample_negatives_philox(const lec_sampler_graph* g, const void* u, const void* v, int idx_bytes, int64_t B,
+                                int N, uint64_t seed, uint64_t stream_id, void* neg_to, void* neg_from, int* status,
+                                void* stream);
+/* the fast mode's integer draw, on the host (for tests): uniform in [0, n) */
+int64_t lec_philox_below(uint64_t seed, uint64_t stream_id, uint64_t draw, uint64_t n);
 
 #ifdef __cplusplus
 }

@@ -12,6 +12,7 @@ import torch
 from torch import nn
 
 from . import _native as N
+from .sampler import SamplerGraph
 from . import ops
 
 
@@ -158,6 +159,7 @@ class _PairCriterion(nn.Module):
         self.mapping_from_node_to_ix = mapping_from_node_to_ix
         self.mapping_from_ix_to_node = mapping_from_ix_to_node
         self._cands = CandidateCache(n_G)
+        self._graph = None  # native sampler graph, built on the first batch draw
 
     # ---- sampler (order_embeddings.py:989-1008) ----
     def sample_negative_edge(self, u=None, v=None, level_id=None):
@@ -207,17 +209,24 @@ class _PairCriterion(nn.Module):
         return None, None
 
     def draw_negatives(self, inputs_from, inputs_to):
-        """order_embeddings.py:1070-1091: N corrupt-v then corrupt-u draws per positive, in order."""
-        Nn = self.neg_to_pos_ratio
-        B = len(inputs_from)
-        neg_to = np.empty((B, Nn), dtype=np.int64)    # corrupted children of u_i
-        neg_from = np.empty((B, Nn), dtype=np.int64)  # corrupted parents of v_i
-        ix2node = self.mapping_from_ix_to_node
-        for i in range(B):
-            u, v = inputs_from[i], inputs_to[i]
-            for p in range(Nn):
-                neg_to[i, p] = ix2node[self.sample_negative_edge(u=u, v=None, level_id=p)]
-                neg_from[i, p] = ix2node[self.sample_negative_edge(u=None, v=v, level_id=p)]
+        """order_embeddings.py:1070-1091: N corrupt-v then corrupt-u draws per positive, in order.  One native
+        call (sampler.SamplerGraph.draw_exact) that consumes Python's global `random` stream exactly as the
+        reference's B x N x 2 sample_negative_edge calls would, so the indices are bit-identical."""
+        if getattr(self, "_graph", None) is None:
+            n_names = len(self.labelmap.level_names)
+            self._graph = SamplerGraph.from_negative_adjacency(
+                self.negative_G, level_start=list(self.labelmap.level_start)[:len(self.labelmap.levels)],
+                level_stop=list(self.labelmap.level_stop)[:len(self.labelmap.levels)],
+                pick_per_level=self.pick_per_level, level_mod=n_names)
+            n = self._graph.n
+            ix2node = [self.mapping_from_ix_to_node[i] for i in range(n)]
+            self._ix2node_arr = None if ix2node == list(range(n)) else np.asarray(ix2node, dtype=np.int64)
+        node2ix = self.mapping_from_node_to_ix
+        u_ix = [node2ix[u] for u in inputs_from]
+        v_ix = [node2ix[v] for v in inputs_to]
+        neg_to, neg_from = self._graph.draw_exact(u_ix, v_ix, self.neg_to_pos_ratio)
+        if self._ix2node_arr is not None:
+            neg_to, neg_from = self._ix2node_arr[neg_to], self._ix2node_arr[neg_from]
         return neg_to, neg_from
 
     def forward(self, model, inputs_from, inputs_to, status, phase, neg_to_pos_ratio):

@@ -68,6 +68,8 @@ const char* lec_error_string(int code) {
         case LEC_E_ALIGN: return "rows / grad_rows must be 16-byte aligned";
         case LEC_E_K: return "top-k: need 1 <= k <= 8 and 1 <= n_levels <= 8";
         case LEC_E_REPLICAS: return "grad_replicas must be >= 1";
+        case LEC_E_EMPTY: return "negative sampler: a draw has no candidate (the reference's random.choice raises IndexError)";
+        case LEC_E_INDEX: return "node index outside [0, n_nodes)";
         case LEC_E_PEERS: return "peer exchange: need 1 <= world <= 16, 0 <= rank < world, slot in {0,1}, slot_floats >= n*D+2 and % 4 == 0";
     }
     if (code > 0) return cudaGetErrorString((cudaError_t)code);

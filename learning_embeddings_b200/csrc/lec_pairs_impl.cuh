@@ -2,6 +2,8 @@
 // core.  Each lec_pairs_<core>.cu instantiates this header once for its core and exports three
 // launchers that lec_api.cu dispatches to.
 #pragma once
+#include <cstdlib>
+
 #include "lec_common.cuh"
 
 namespace lec {
@@ -380,16 +382,35 @@ int launch_flat_tv(const FlatArgs& a, cudaStream_t st) {
     return (int)cudaGetLastError();
 }
 
+// Teams per group.  A team's trip count is w(s) = 1 + 2*ceil(N/s) pair evaluations (the positive is re-evaluated by
+// every team of a split group), a launch holds `cap` teams at once, so time ~ w(s) * max(1, B*s/cap): splitting
+// pays only while the batch cannot fill the GPU (cfg4: 2 569 positives x 51 pairs); a batch that already fills it
+// (cfg1: 190 650 positives) stays at s = 1, where no pair is evaluated twice.  LEC_GROUP_SPLIT overrides (tuning).
+inline int choose_split(int64_t B, int N, int64_t cap) {
+    static const int forced = [] { const char* e = getenv("LEC_GROUP_SPLIT"); return e ? atoi(e) : 0; }();
+    if (forced > 0) return forced < N ? forced : (N > 0 ? N : 1);
+    if (B <= 0 || N <= 1 || cap <= 0) return 1;
+    int best = 1;
+    double best_t = 0.0;
+    for (int s = 1; s <= N; ++s) {
+        const double w = 1.0 + 2.0 * ((N + s - 1) / s);
+        const double fill = (double)B * s / (double)cap;
+        const double t = w * (fill > 1.0 ? fill : 1.0);
+        if (s == 1 || t < best_t * 0.97) { best = s; best_t = t; }
+    }
+    return best;
+}
+
 template <int CORE, int T, int V>
 int launch_grouped_tv(const GroupArgs& a0, cudaStream_t st) {
     GroupArgs a = a0;
-    // enough teams for ~2 full waves of resident threads; a group is never split finer than its N negatives
-    const int64_t want = (int64_t)sm_count() * 2048 * 2 / T;
-    int64_t split = a.B > 0 ? (want + a.B - 1) / a.B : 1;
-    if (split > a.N) split = a.N;
-    if (split < 1) split = 1;
-    a.split = (int)split;
-    const int grid = grid_for(a.B * split, kThreads / T, 8);
+    static const int resident_blocks = [] {
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pairs_grouped_kernel<CORE, T, V, true>, kThreads, 0);
+        return nb > 0 ? nb : 1;
+    }();
+    a.split = choose_split(a.B, a.N, (int64_t)sm_count() * resident_blocks * (kThreads / T));
+    const int grid = grid_for(a.B * a.split, kThreads / T, 8);
     if (a.grad_rows) pairs_grouped_kernel<CORE, T, V, true><<<grid, kThreads, 0, st>>>(a);
     else pairs_grouped_kernel<CORE, T, V, false><<<grid, kThreads, 0, st>>>(a);
     ++g_launches;

@@ -20,6 +20,7 @@ from torch import nn
 
 from . import _native as N
 from . import ops
+from .sampler import SamplerGraph
 from .criterion import CandidateCache, HyperbolicTanhEmbedder, EuclideanEmbedder, inner_radius, unwrap
 
 
@@ -103,6 +104,7 @@ class _JointCriterion(nn.Module):
         self.mapping_from_node_to_ix = mapping_from_node_to_ix
         self.mapping_from_ix_to_node = mapping_from_ix_to_node
         self._cands = CandidateCache(n_G)
+        self._graph = None  # native sampler graph, built on the first batch draw
 
     def get_img_features(self, x):
         """oe.py:680-707 for a flat list of filenames: [1, len(x), F] host tensor."""
@@ -212,10 +214,23 @@ class _JointCriterion(nn.Module):
         return fe, te
 
     def draw_negatives(self, original_from, original_to):
-        """oe.py:846-863."""
+        """oe.py:846-863.  One native call that consumes Python's `random` stream exactly as the reference's loop
+        (sampler.SamplerGraph.draw_exact); with hidden levels (oe.py:756-761 remaps level ids through a set) the
+        per-draw path below is used, which is the same stream drawn one choice at a time."""
         Nn = self.neg_to_pos_ratio
-        neg_to, neg_from = [], []
         ix2node = self.mapping_from_ix_to_node
+        if len(self.levels_to_hide) == 0:
+            if getattr(self, "_graph", None) is None:
+                nl = len(self.labelmap.levels)
+                self._graph = SamplerGraph.from_negative_adjacency(
+                    self.negative_G, level_start=list(self.labelmap.level_start)[:nl],
+                    level_stop=list(self.labelmap.level_stop)[:nl], pick_per_level=self.pick_per_level,
+                    n_labels=int(self.labelmap.level_stop[-1]), level_mod=len(self.labelmap.level_names) + 1)
+            node2ix = self.mapping_from_node_to_ix
+            nt, nf = self._graph.draw_exact([node2ix[u] for u in original_from], [node2ix[v] for v in original_to], Nn)
+            return ([[ix2node[i] for i in row] for row in nt.tolist()],
+                    [[ix2node[i] for i in row] for row in nf.tolist()])
+        neg_to, neg_from = [], []
         for u, v in zip(original_from, original_to):
             a, b = [None] * Nn, [None] * Nn
             for p in range(Nn):

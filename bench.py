@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the entailment-cone hot path (BASELINE.json metric: cone pairs/s fwd+bwd).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg1|cfg2|cfg4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg1|cfg2|cfg3|cfg4]
 
 One "step" = one pass of the hot path over one batch: row transform -> fused cone loss fwd+bwd over
 B*(1+2N) pairs -> (N>1: NCCL all-reduce of the label-table gradient) -> Riemannian SGD update of the
@@ -33,7 +33,12 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg1", choices=["cfg1", "cfg2", "cfg4"])
+    ap.add_argument("--workload", default="cfg1", choices=["cfg1", "cfg2", "cfg3", "cfg4"])
+    ap.add_argument("--dim", type=int, default=10, help="cfg3: embedding dimension (10 or 50)")
+    ap.add_argument("--images", type=int, default=1000000, help="cfg3: images per GPU per step")
+    ap.add_argument("--score-mode", default="both", choices=["both", "matrix", "topk"],
+                    help="cfg3: what a step writes: per-level top-5 + the full [L, N] energy matrix, or one of them")
+    ap.add_argument("--engine", default="auto", choices=["auto", "tc", "simt"], help="cfg3: scoring engine")
     ap.add_argument("--pairs", type=int, default=1 << 21, help="pairs per GPU per step (rounded to whole groups)")
     ap.add_argument("--precision", type=int, default=None, help="0 fp32 core, 1 fp64 core (default: per workload)")
     ap.add_argument("--rotation", type=int, default=0, help="distinct batches to rotate through (0 = enough to exceed L2)")
@@ -444,10 +449,234 @@ def run_cfg2(args):
         torch.distributed.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+# cfg3: all-pairs image x label scoring (BASELINE.json metric "image x label scores/s")
+# ------------------------------------------------------------------------------------------------
+def cfg3_inputs(n_img, D, seed):
+    """images uniform direction with |y| ~ U[0.30, 0.95]; ETHEC labels, norm by level
+    U[0.10 + 0.2 l, 0.30 + 0.2 l]."""
+    from learning_embeddings_b200 import hierarchy as H
+    h = H.ethec()
+    g = torch.Generator().manual_seed(seed)
+
+    def ball(n, lo, hi):
+        d = torch.randn(n, D, generator=g)
+        return d / d.norm(dim=1, keepdim=True) * (lo + (hi - lo) * torch.rand(n, 1, generator=g))
+    labels = torch.zeros(h.n, D)
+    for l in range(len(h.level_start)):
+        s, e = h.level_start[l], h.level_stop[l]
+        labels[s:e] = ball(e - s, 0.10 + 0.2 * l, 0.30 + 0.2 * l)
+    return h, labels, ball(n_img, 0.30, 0.95)
+
+
+def cfg3_cpu(h, labels, images, K, steps, warmup, budget_s):
+    """The reference's scoring (oe_h.py:2018-2036: E(label, image) for every pair, per-level topk(5, smallest)) as
+    restated by the oracle, on all host threads, over a bounded sample of the images."""
+    from oracle import cones
+    torch.set_num_threads(os.cpu_count() or 1)
+
+    def run():
+        E = cones.score_matrix("hyp", labels, images, K)
+        return cones.topk_per_level(E, h.level_start, h.level_stop, 5)
+    for _ in range(min(1, warmup)):
+        run()
+    ts = []
+    t_all = time.perf_counter()
+    while len(ts) < steps and (not ts or time.perf_counter() - t_all < budget_s):
+        t0 = time.perf_counter()
+        run()
+        ts.append(time.perf_counter() - t0)
+    return images.shape[0] * labels.shape[0] / float(np.mean(ts)), float(np.mean(ts)), len(ts)
+
+
+def run_cfg3(args):
+    metric, unit = "image x label scores/s", "scores/s"
+    D, n_img, K, k = args.dim, args.images, 0.1, 5
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    want_matrix, want_topk = args.score_mode in ("both", "matrix"), args.score_mode in ("both", "topk")
+    cfg = {"workload": "cfg3: hyperbolic cone inference scoring, %d synthetic image embeddings x 723 ETHEC labels per GPU, D=%d, "
+                       "per-level top-5%s" % (n_img, D, " + full [L, N] fp32 energy matrix" if want_matrix else ""),
+           "images_per_gpu_per_step": n_img, "labels": 723, "dim": D, "levels": 4, "topk": k, "writes": args.score_mode,
+           "parallelism": "dp%d (images sharded by contiguous ranges, labels replicated, no collective)" % world}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sample = min(n_img, 32768)
+        h, labels, images = cfg3_inputs(sample, D, seed=0)
+        v, mean_s, n_done = cfg3_cpu(h, labels, images, K, args.steps, args.warmup, budget_s=150.0)
+        cfg["images_per_gpu_per_step"] = sample
+        cfg["parallelism"] = "host cores only"
+        cores = os.cpu_count() or 1
+        print(json.dumps({
+            "metric": metric, "value": v, "unit": unit, "impl": "reference", "n_gpus": args.gpus, "steps": n_done,
+            "warmup": min(1, args.warmup), "ms_per_step": mean_s * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": "port",
+                             "sample": "%d images x 723 labels per step (energy matrix + per-level top-5), %d timed steps, torch "
+                                       "fp32 on all host threads" % (sample, n_done)},
+            "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    from learning_embeddings_b200 import _native, ops
+
+    h, labels, images0 = cfg3_inputs(n_img, D, seed=rank)
+    L = labels.shape[0]
+    labels_d = labels.to(dev)
+    # rotate through image sets so that no step finds its inputs in L2; a matrix-writing step also streams 2.9 GB out
+    rotation = args.rotation or max(2, int(np.ceil(160e6 / (n_img * D * 4))))
+    host_sets = [images0.pin_memory()]
+    for r in range(1, rotation):
+        host_sets.append(images0.roll(shifts=r * 977, dims=0).contiguous().pin_memory())
+    dev_sets = [x.to(dev) for x in host_sets]
+    cfg["l2_policy"] = "inputs rotate through %d image sets (%.0f MB > 126 MB L2)%s" % (
+        rotation, rotation * n_img * D * 4 / 1e6, "; every step also writes the %.2f GB matrix" % (L * n_img * 4 / 1e9) if want_matrix else "")
+    nl = len(h.level_start)
+    idx = torch.empty((n_img, nl, k), device=dev, dtype=torch.int32) if want_topk else None
+    val = torch.empty((n_img, nl, k), device=dev, dtype=torch.float32) if want_topk else None
+    scores = torch.empty((L, n_img), device=dev, dtype=torch.float32) if want_matrix else None
+
+    import ctypes
+    lib = _native.lib()
+    ls = (ctypes.c_int32 * nl)(*h.level_start)
+    le = (ctypes.c_int32 * nl)(*h.level_stop)
+    use_tc = args.engine != "simt" and bool(lib.lec_score_tc_supported(ops.GEOM["hyp"], 0, D, L, nl))
+    if args.engine == "tc" and not use_tc:
+        raise SystemExit("tensor-core scoring does not support this case")
+    cfg["engine"] = "tc (tcgen05 kind::tf32 3xTF32 + fused epilogue)" if use_tc else "simt (packed FFMA2 tile kernel)"
+    ws, nb = None, 0
+    if use_tc:
+        nb = int(lib.lec_score_workspace_bytes(L, D, nl))
+        ws = ops._score_workspace(dev, nb)
+    st = _native.stream_ptr(dev)
+
+    def score(imgs, idx_o, val_o, scores_o):
+        n = imgs.shape[0]
+        if use_tc:
+            _native.check(lib.lec_score_topk_tc(ops.GEOM["hyp"], 0, _native._p(labels_d), L, _native._p(imgs), n, D, K,
+                                                ctypes.cast(ls, ctypes.c_void_p), ctypes.cast(le, ctypes.c_void_p), nl, k,
+                                                _native._p(scores_o), _native._p(idx_o), _native._p(val_o), _native._p(ws), nb,
+                                                _native.stream_ptr(dev)), "lec_score_topk_tc")
+        else:
+            _native.check(lib.lec_score_topk_ex(ops.GEOM["hyp"], 0, _native._p(labels_d), L, _native._p(imgs), n, D, K,
+                                                ctypes.cast(ls, ctypes.c_void_p), ctypes.cast(le, ctypes.c_void_p), nl, k,
+                                                _native._p(scores_o), 1, _native._p(idx_o), _native._p(val_o),
+                                                _native.stream_ptr(dev)), "lec_score_topk_ex")
+
+    def sync_all():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def max_ranks(ms):
+        if world > 1:
+            tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+            torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+            return float(tt.item())
+        return ms
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    W = max(3, args.warmup)
+    for i in range(W):
+        score(dev_sets[i % rotation], idx, val, scores)
+    sync_all()
+    launches0 = _native.launch_count()
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.active.set()
+    sync_all()
+    t0.record()
+    for i in range(args.steps):
+        kev[i][0].record()
+        score(dev_sets[i % rotation], idx, val, scores)
+        kev[i][1].record()
+    t1.record()
+    sync_all()
+    sampler.active.clear()
+    lec_launches = _native.launch_count() - launches0
+    elapsed_ms = max_ranks(t0.elapsed_time(t1))
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    value = world * n_img * L * args.steps / (elapsed_ms * 1e-3)
+
+    # end to end: pinned host images -> H2D -> per-level top-5 -> predictions D2H, through ops.score_topk_host, which
+    # cuts the image set into slices and overlaps the copies of neighbouring slices with the kernel (what the
+    # reference's caller consumes is the top-5 per level, oe_h.py:2030-2036; the matrix never leaves the device)
+    e2e = None
+    if not args.no_e2e:
+        out_idx = torch.empty((n_img, nl, k), dtype=torch.int32).pin_memory()
+        pipe = ops.ScorePipeline(labels_d, "hyp", K, h.level_start, h.level_stop, k=k, slice_images=131072,
+                                 engine=("tc" if use_tc else "simt"))
+        for i in range(2):
+            pipe.run(host_sets[i % rotation], out_idx)
+        sync_all()
+        sampler.active.set()
+        w0 = time.perf_counter()
+        n_e2e = max(3, min(args.steps, 50))
+        for i in range(n_e2e):
+            pipe.run(host_sets[i % rotation], out_idx)   # returns with the predictions in host memory
+        e_ms = max_ranks((time.perf_counter() - w0) * 1e3)
+        sampler.active.clear()
+        e2e = {"value": world * n_img * L * n_e2e / (e_ms * 1e-3), "unit": unit, "h2d_bytes_per_step": n_img * D * 4,
+               "d2h_bytes_per_step": n_img * nl * k * 4, "ms_per_step": e_ms / n_e2e, "steps": n_e2e,
+               "api": "ops.ScorePipeline.run (host images in, host top-5 label ids per level out; 128K-image slices, copies "
+                      "overlap the kernel)"}
+        # the device result of the last slice equals the host copy
+        assert int(out_idx.min()) >= -1 and int(out_idx.max()) < L
+    sampler.stop()
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    # SURVEY 8(d): a matrix-writing step moves 4 B per score + the image rows once (+ 160 B of top-k per image);
+    # a top-k-only step moves (4 D + 160) / L per score
+    bytes_per_score = ((4.0 if want_matrix else 0.0) + 4.0 * D / L + (160.0 / L if want_topk else 0.0))
+    achieved = n_img * L * bytes_per_score / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic_cfg3_D%d_%s.json" % (D, args.score_mode))
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "kernel": "score_mma_kernel" if use_tc else "score_fast_kernel", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_score": bytes_per_score, "kernel_ms": kernel_ms,
+                "kernel_share_of_step": kernel_ms / (elapsed_ms / args.steps),
+                "note": "kernel_ms brackets the whole library call (label repack launch + scoring kernel)"
+                        + ("" if want_matrix else "; a top-k-only step is bound by FP32/MUFU issue, not HBM")}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        sample = min(n_img, 32768)
+        v, mean_s, n_done = cfg3_cpu(h, labels, images0[:sample], K, steps=8, warmup=1, budget_s=20.0)
+        cpu = {"value": v, "unit": unit, "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": "%d images x 723 labels per step (energy matrix + per-level top-5), %d steps, torch fp32 on all "
+                         "host threads" % (sample, n_done)}
+    print(json.dumps({"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": W,
+                      "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "f32", "data": "synthetic", "config": cfg, "clocks": sampler.summary(), "e2e": e2e,
+                      "gpu_launches": int(lec_launches), "roofline": roofline, "cpu_baseline": cpu}))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.workload == "cfg2":
         return run_cfg2(args)
+    if args.workload == "cfg3":
+        return run_cfg3(args)
     spec = workload_spec(args.workload)
     Nn, D = spec["n_neg"], spec["D"]
     ppg = 1 + 2 * Nn

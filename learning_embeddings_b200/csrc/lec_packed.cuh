@@ -84,12 +84,14 @@ __device__ __forceinline__ u64 acos_clamped2(u64 g2) {
     P = ffma2(P, ax, pack2(LEC_ACOS_A1, LEC_ACOS_A1));
     P = ffma2(P, ax, pack2(LEC_ACOS_A0, LEC_ACOS_A0));
     const u64 r = fmul2(sq, P);
-    // g < 0: pi - r ; else r     (sign and offset taken from the sign bit)
+    // g < 0: pi - r ; else r.   sg = copysign(1, g) (one LOP3 each); offset = pi/2 - sg * pi/2 is exactly 0 or
+    // fp32(pi) and comes from the FMA pipe as a packed op instead of two more ALU ops per score
     const float sg0 = __int_as_float((__float_as_int(g0) & 0x80000000) | 0x3f800000);
     const float sg1 = __int_as_float((__float_as_int(g1) & 0x80000000) | 0x3f800000);
-    const float b0 = __int_as_float((__float_as_int(g0) >> 31) & 0x40490fdb);
-    const float b1 = __int_as_float((__float_as_int(g1) >> 31) & 0x40490fdb);
-    return ffma2(pack2(sg0, sg1), r, pack2(b0, b1));
+    const u64 sg = pack2(sg0, sg1);
+    const u64 HP = pack2(1.57079637f, 1.57079637f);
+    const u64 off = ffma2(sg, pack2(-1.57079637f, -1.57079637f), HP);
+    return ffma2(sg, r, off);
 }
 
 }  // namespace lec

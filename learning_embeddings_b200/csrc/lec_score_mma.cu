@@ -3,27 +3,32 @@
 // Replaces the per-image CPU loop of JointEmbeddings.calculate_classification_metrics
 // (oe_h.py:2018-2036): e[i, l] = E(x = label_l, y = image_i), then per level topk(k, largest=False).
 //
-// The only part of the energy that couples an image with a label is p = <x, y>; everything else is a
-// per-image or a per-label scalar.  So the [128 images] x [64 labels] block of dot products is one
-// tcgen05.mma (kind::tf32, M=128, N=64, fp32 accumulator in TMEM), made fp32-accurate by the 3xTF32 split
-//     x = x_hi + x_lo,  y = y_hi + y_lo   (hi = tf32 round-to-nearest, lo = tf32(rest))
-//     <x, y> ~= y_hi.x_hi + y_hi.x_lo + y_lo.x_hi        (the dropped lo.lo term is 2^-22 |x||y|)
-// issued as three K-passes over the same accumulator, and the FMA pipe is left with the epilogue only:
-// each thread owns one image (= one TMEM lane), pulls 16 label columns at a time with tcgen05.ld and runs
-// the angle / aperture algebra on packed label PAIRS (fma.rn.f32x2), then either stores the label-major
-// score matrix (32 consecutive images per warp store: coalesced) or feeds the per-level top-k.
+// With A = |x|^2 (label), B = |y|^2 (image), p = <x, y> the cosine of the cone angle is
+//     g = num * rsqrt(as2 * w2),   num = p(1+A) - A(1+B),   w2 = 1 + AB - 2p,   as2 = A (A + B - 2p)
+// (order_embeddings_h.py:1097-1120).  All three are BILINEAR in the augmented rows y' = [y, B, 1] and
+//     x'_num = [(1+A) x, -A, -A]     x'_w2 = [-2 x, A, 1]     x'_as2 = [-2A x, A, A^2]
+// so one tcgen05.mma (kind::tf32, M = 128 images, N = 3 x 32 label rows, K = D + 2, fp32 accumulators in TMEM)
+// produces all three per pair and the FMA pipe is left with  g = num * rsqrt(as2 * w2), the clamped acos and the
+// hinge -- 13 FMA-pipe operations per score instead of ~30 for the in-register algebra + dot product.  fp32
+// accuracy comes from the 3xTF32 split
+//     x' = x_hi + x_lo,  y' = y_hi + y_lo   (hi = tf32 round-to-nearest, lo = tf32(rest))
+//     <x', y'> ~= y_hi.x_hi + y_hi.x_lo + y_lo.x_hi      (the dropped lo.lo term is 2^-22 |x'||y'|)
+// issued as three K-passes over the same accumulator.  Each epilogue thread owns one image (= one TMEM lane) and
+// 16 labels of the chunk, pulls its 3 x 16 columns with tcgen05.ld, releases the accumulator at once (so the
+// MMAs of the next chunk overlap the arithmetic even with a single accumulator buffer) and runs the epilogue on
+// packed label PAIRS (fma.rn.f32x2), then either stores the label-major score matrix (32 consecutive images per
+// warp store: coalesced) or feeds the per-level top-k.
 //
 // Data movement:
-//   labels  -> lec_score_mma_prep (one small launch): per chunk of 64 labels a "blob" in the caller's
-//              workspace = B_hi tile | B_lo tile (K-major, no-swizzle UMMA canonical layout) | per-label-pair
-//              constants {A, 1+A, A^2, -psi, cos psi, sin psi} (fp64-computed, same terms as lec_rows_fwd's
-//              aux) | header.  The main kernel pulls blobs with cp.async.bulk (TMA, mbarrier complete_tx),
-//              double buffered.
-//   images  -> each CTA reads its 128 rows once, splits them into hi/lo and writes the A tiles to shared
-//              memory itself (generic proxy + fence.proxy.async).
-//   accumulators: TMEM, 2 x 64 columns: the MMAs of chunk c+1 run while the epilogue of chunk c executes.
+//   labels  -> lec_score_mma_prep (one small launch): per chunk of 32 labels a "blob" in the caller's
+//              workspace = B_hi tile | B_lo tile (96 rows, K-major, no-swizzle UMMA canonical layout) | per-label-pair
+//              constants {-psi, cos psi, sin psi} (fp64-computed, same terms as lec_rows_fwd's aux) | header.
+//              The main kernel pulls blobs with cp.async.bulk (TMA, mbarrier complete_tx), double buffered.
+//   images  -> each CTA reads its 128 rows once, splits [y, |y|^2, 1] into hi/lo and writes them to tensor memory
+//              as the A operand (tcgen05.st, TS-form MMA).
+//   accumulators: TMEM, 1 or 2 buffers of 96 columns so that a CTA stays within 256 columns and two CTAs share an SM.
 //
-// UMMA canonical layout used for both operands (Major-K, SWIZZLE_NONE; cute/atom/mma_traits_sm100.hpp
+// UMMA canonical layout used for the B operand (Major-K, SWIZZLE_NONE; cute/atom/mma_traits_sm100.hpp
 // "((8,n),2):((1,SBO),LBO)" in 16-byte units): a core matrix is 8 rows x 16 bytes stored contiguously
 // (128 B); element (row r, k) of a tile with R rows lives at byte (k/4)*(16 R) + 16 r + 4 (k%4), i.e.
 // LBO = 16 R (next 16-byte K group), SBO = 128 (next 8 rows).  One MMA consumes K = 8 tf32 = two K groups.
@@ -36,7 +41,8 @@
 namespace lec {
 
 constexpr int kMmaM = 128;       // images per CTA (TMEM lanes)
-constexpr int kMmaN = 64;        // labels per chunk (TMEM columns per accumulator buffer)
+constexpr int kMmaNL = 32;       // labels per chunk
+constexpr int kMmaN = 3 * kMmaNL; // B rows per chunk = TMEM columns per accumulator buffer: num | w2 | as2
 constexpr int kMmaMaxChunks = 224;
 constexpr int kMmaRingCheck = 8; // ring room needed between two merge checks (4 label pairs)
 
@@ -45,9 +51,9 @@ struct MmaChunkTable { int n; MmaChunk c[kMmaMaxChunks]; };
 
 struct MmaHdr { int label0, count, level, flags; float psi_max; int pad[3]; };  // 32 bytes, tail of a blob
 
-__host__ __device__ inline int mma_kp(int D) { return (D + 7) / 8 * 8; }
+__host__ __device__ inline int mma_kp(int D) { return (D + 2 + 7) / 8 * 8; }                    // [row, |row|^2-slot, 1-slot], padded
 __host__ __device__ inline int mma_tile_bytes(int Kp) { return kMmaN * Kp * 4; }                 // one B tile (hi or lo)
-__host__ __device__ inline int mma_const_bytes() { return (kMmaN / 2) * 12 * 4; }               // 32 pairs x 12 floats
+__host__ __device__ inline int mma_const_bytes() { return (kMmaNL / 2) * 8 * 4; }               // 16 pairs x 8 floats
 __host__ __device__ inline int mma_blob_bytes(int Kp) { return 2 * mma_tile_bytes(Kp) + mma_const_bytes() + (int)sizeof(MmaHdr); }
 
 __device__ __forceinline__ float to_tf32(float v) {
@@ -61,35 +67,52 @@ __device__ __forceinline__ float to_tf32(float v) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kMmaN) score_mma_prep_kernel(const float* __restrict__ labels, int D, int Kp, float K,
                                                                 const MmaChunkTable tab, unsigned char* __restrict__ ws) {
-    const int c = blockIdx.x, j = threadIdx.x;
+    const int c = blockIdx.x, j = threadIdx.x;   // thread j writes B row j: form j / 32 of label j % 32
+    const int form = j / kMmaNL, jl = j % kMmaNL;
     const MmaChunk ch = tab.c[c];
     unsigned char* blob = ws + (size_t)c * mma_blob_bytes(Kp);
     float* hi = reinterpret_cast<float*>(blob);
     float* lo = reinterpret_cast<float*>(blob + mma_tile_bytes(Kp));
     float* cst = reinterpret_cast<float*>(blob + 2 * mma_tile_bytes(Kp));
-    const bool live = j < ch.count;
-    const float* src = labels + (int64_t)(ch.label0 + (live ? j : 0)) * D;
+    const bool live = jl < ch.count;
+    const float* src = labels + (int64_t)(ch.label0 + (live ? jl : 0)) * D;
     double A = 0.0;
+    for (int k = 0; k < D; ++k) {
+        const double v = live ? (double)__ldg(src + k) : 0.0;
+        A += v * v;
+    }
+    // x'_num = [(1+A) x, -A, -A]   x'_w2 = [-2 x, A, 1]   x'_as2 = [-2A x, A, A^2]     (against y' = [y, B, 1])
+    const double coef = form == 0 ? 1.0 + A : (form == 1 ? -2.0 : -2.0 * A);
+    const double tailB = form == 0 ? -A : A;
+    const double tail1 = form == 0 ? -A : (form == 1 ? 1.0 : A * A);
     for (int k0 = 0; k0 < Kp; k0 += 4) {
         float h[4], l[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const int k = k0 + e;
-            const float v = (live && k < D) ? __ldg(src + k) : 0.f;
-            A += (double)v * (double)v;
+            double dv = 0.0;
+            if (live) {
+                if (k < D) dv = coef * (double)__ldg(src + k);
+                else if (k == D) dv = tailB;
+                else if (k == D + 1) dv = tail1;
+            }
+            const float v = (float)dv;
             h[e] = to_tf32(v);
             l[e] = to_tf32(v - h[e]);
         }
-        const int off = (k0 >> 2) * (kMmaN * 4) + j * 4;  // floats: K group * (16 B * 64 rows) + row * 16 B
+        const int off = (k0 >> 2) * (kMmaN * 4) + j * 4;  // floats: K group * (16 B * 96 rows) + row * 16 B
         *reinterpret_cast<float4*>(hi + off) = make_float4(h[0], h[1], h[2], h[3]);
         *reinterpret_cast<float4*>(lo + off) = make_float4(l[0], l[1], l[2], l[3]);
     }
     const Aux<double> x = row_aux<double>(LEC_GEOM_HYP, live ? A : 0.25, K);
-    const double Av = live ? A : 0.25;
-    const double sp = sin(x.t0);
-    float* q = cst + (j >> 1) * 12 + (j & 1);
-    q[0] = (float)Av; q[2] = (float)(1.0 + Av); q[4] = (float)(Av * Av); q[6] = (float)(-x.t0);
-    q[8] = (float)sqrt(fmax(0.0, 1.0 - sp * sp)); q[10] = (float)sp;
+    if (form == 0) {
+        const double sp = sin(x.t0);
+        float* q = cst + (jl >> 1) * 8 + (jl & 1);   // pair layout: {-psi, -psi', cos psi, cos psi', sin psi, sin psi', 0, 0}
+        q[0] = (float)(-x.t0);
+        q[2] = (float)sqrt(fmax(0.0, 1.0 - sp * sp));
+        q[4] = (float)sp;
+        q[6] = 0.f;
+    }
     // largest half-aperture of the chunk (for the deferred-angle filter's validity test thr + psi <= pi)
     float pm = live ? (float)x.t0 : -INFINITY;
     __shared__ float wmax[kMmaN / 32];
@@ -100,7 +123,7 @@ __global__ void __launch_bounds__(kMmaN) score_mma_prep_kernel(const float* __re
     if (j == 0) {
         MmaHdr* h = reinterpret_cast<MmaHdr*>(blob + 2 * mma_tile_bytes(Kp) + mma_const_bytes());
         h->label0 = ch.label0; h->count = ch.count; h->level = ch.level; h->flags = ch.flags;
-        h->psi_max = fmaxf(wmax[0], wmax[1]);
+        h->psi_max = fmaxf(wmax[0], fmaxf(wmax[1], wmax[2]));
         h->pad[0] = h->pad[1] = h->pad[2] = 0;
     }
 }
@@ -194,13 +217,15 @@ struct MmaArgs {
     float* scores;           // label-major [L, N] or NULL
     int32_t* topk_idx; float* topk_val; int k, n_levels;
     int ring;                // candidate ring entries per thread
-    int stages;              // blob stages in shared memory = accumulator buffers in TMEM (2..4)
+    int stages;              // blob stages in shared memory (1..4)
+    int acc_stages;          // accumulator buffers in TMEM (1 or 2)
+    int tmem_cols;           // power of two >= acc_stages * 96 + 2 Kp
 };
 
 constexpr int kMmaMaxStages = 4;
-constexpr int kEpiThreads = 2 * kMmaM;          // 8 epilogue warps: two threads per image, 32 label columns each
+constexpr int kEpiThreads = 2 * kMmaM;          // 8 epilogue warps: two threads per image, 16 labels (3 x 16 columns) each
 constexpr int kMmaThreads = kEpiThreads + 64;   // + warp 8 (tcgen05.mma issue) + warp 9 (TMA bulk copies)
-constexpr int kHalfCols = kMmaN / 2;
+constexpr int kHalfLabels = kMmaNL / 2;
 
 __device__ __forceinline__ void mbar_arrive(unsigned bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -223,10 +248,11 @@ __device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// Warp roles: warps 0..7 = epilogue (warp w reads TMEM lanes 32 (w % 4) .., columns 32 (w / 4) .. of every chunk),
+// Warp roles: warps 0..7 = epilogue (warp w reads TMEM lanes 32 (w % 4) .., labels 16 (w / 4) .. of every chunk),
 // warp 8 = MMA issuer (warp-uniform code so descriptors live in uniform registers; one lane issues), warp 9 =
-// loader (one lane issues the bulk copies).  Pipelines: full[s] (blob landed), done[s] (accumulator complete), empty[s] (all 256 epilogue
-// threads are finished with blob stage s and accumulator buffer s), two stages each.
+// loader (one lane issues the bulk copies).  Pipelines: full[s] (blob landed in stage s), done[t] (accumulator t
+// complete), accfree[t] (all 256 epilogue threads hold accumulator t's values in registers), empty[s] (all 256
+// epilogue threads are finished with the constants of blob stage s, whose MMAs have completed).
 // MODE 0: top-k only (deferred angle), 1: matrix only, 2: matrix + top-k
 template <int MODE>
 __global__ void __launch_bounds__(kMmaThreads, 1) score_mma_kernel(const MmaArgs a) {
@@ -239,23 +265,25 @@ __global__ void __launch_bounds__(kMmaThreads, 1) score_mma_kernel(const MmaArgs
     float2* top = reinterpret_cast<float2*>(sB + (size_t)NS * blob);               // [k][256] {E, label}
     float2* ring = top + (size_t)a.k * kEpiThreads;                                  // [ring][256] {E or g, label}
     float* ringp = reinterpret_cast<float*>(ring + (size_t)a.ring * kEpiThreads);    // [ring][256] -psi
-    uint64_t* bars = reinterpret_cast<uint64_t*>(ringp + (size_t)a.ring * kEpiThreads);  // full[4], done[4], empty[4]
-    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 3 * kMmaMaxStages);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ringp + (size_t)a.ring * kEpiThreads);  // full[4], done[4], empty[4], accfree[4]
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 4 * kMmaMaxStages);
 
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int NA = a.acc_stages;
     const unsigned bar_full0 = smem_u32(bars), bar_done0 = smem_u32(bars + kMmaMaxStages), bar_empty0 = smem_u32(bars + 2 * kMmaMaxStages);
-    // tensor memory: NS accumulator buffers of 64 columns, then the image tile as the A operand: A_hi | A_lo, Kp
-    // columns each (lane = image row); rounded up to a power of two
-    const unsigned col_ahi = (unsigned)(NS * kMmaN), col_alo = col_ahi + (unsigned)Kp;
-    unsigned tmem_cols = 32;
-    while (tmem_cols < col_alo + (unsigned)Kp) tmem_cols <<= 1;
+    const unsigned bar_accfree0 = smem_u32(bars + 3 * kMmaMaxStages);
+    // tensor memory: NA accumulator buffers of 96 columns, then the image tile as the A operand: A_hi | A_lo, Kp
+    // columns each (lane = image row); the host rounded the total up to a power of two
+    const unsigned col_ahi = (unsigned)(NA * kMmaN), col_alo = col_ahi + (unsigned)Kp;
+    const unsigned tmem_cols = (unsigned)a.tmem_cols;
 
     if (warp == 8) tmem_alloc(smem_u32(tmem_slot), tmem_cols);   // the allocating warp also frees
     if (tid == 0) {
-        for (int s = 0; s < NS; ++s) {
+        for (int s = 0; s < kMmaMaxStages; ++s) {
             mbar_init(bar_full0 + 8 * s, 1);
             mbar_init(bar_done0 + 8 * s, 1);
             mbar_init(bar_empty0 + 8 * s, kEpiThreads);
+            mbar_init(bar_accfree0 + 8 * s, kEpiThreads);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -273,13 +301,16 @@ __global__ void __launch_bounds__(kMmaThreads, 1) score_mma_kernel(const MmaArgs
     if (tid < kEpiThreads) {
         const float* src = a.images + (img_ok ? img : 0) * (int64_t)a.D;
         const unsigned dst = tmem_base + ((unsigned)((warp & 3) * 32) << 16) + (half ? col_alo : col_ahi);
+        if (img_ok)
+            for (int k = 0; k < a.D; ++k) { const float v = __ldg(src + k); Bn = fmaf(v, v, Bn); }
+        // y' = [y, |y|^2, 1, 0 ...]
         for (int k0 = 0; k0 < Kp; k0 += 8) {
             float o[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 const int k = k0 + e;
-                const float v = (img_ok && k < a.D) ? __ldg(src + k) : 0.f;
-                Bn = fmaf(v, v, Bn);
+                float v = 0.f;
+                if (img_ok) v = (k < a.D) ? __ldg(src + k) : (k == a.D ? Bn : (k == a.D + 1 ? 1.f : 0.f));
                 const float h = to_tf32(v);
                 o[e] = half ? to_tf32(v - h) : h;
             }
@@ -312,16 +343,17 @@ __global__ void __launch_bounds__(kMmaThreads, 1) score_mma_kernel(const MmaArgs
         }
         __syncwarp();
     } else if (warp == 8) {
-        // MMA issuer: runs up to NS - 1 chunks ahead of the epilogue.  Accumulator buffer c % NS is free when blob c
-        // has landed, because the loader only requested blob c after empty[c % NS] fired for chunk c - NS.
+        // MMA issuer: chunk c needs its blob (full[c % NS]) and accumulator buffer c % NA, which is free as soon as
+        // every epilogue thread has pulled chunk c - NA out of it (accfree), i.e. before that chunk's arithmetic.
         const unsigned sB_u = smem_u32(sB);
         const unsigned idesc = umma_idesc_tf32(kMmaM, kMmaN);
         const bool issuer = (tid & 31) == 0;
         for (int c = 0; c < a.n_chunks; ++c) {
-            const int s = c % NS;
+            const int s = c % NS, t = c % NA;
             mbar_wait(bar_full0 + 8 * s, (unsigned)((c / NS) & 1));
+            if (c >= NA) mbar_wait(bar_accfree0 + 8 * t, (unsigned)(((c - NA) / NA) & 1));
             tc_fence_after();
-            const unsigned d = tmem_base + (unsigned)(s * kMmaN);
+            const unsigned d = tmem_base + (unsigned)(t * kMmaN);
             const unsigned bh = sB_u + s * blob, bl = bh + b_tile;
             unsigned acc = 0;
             for (int pass = 0; pass < 3; ++pass) {
@@ -333,13 +365,12 @@ __global__ void __launch_bounds__(kMmaThreads, 1) score_mma_kernel(const MmaArgs
                     acc = 1;
                 }
             }
-            if (issuer) tc_commit(bar_done0 + 8 * s);
+            if (issuer) tc_commit(bar_done0 + 8 * t);
             __syncwarp();
         }
         __syncwarp();
     } else {
         // ================================ epilogue warps ================================
-        const u64 B2 = pack2(Bn, Bn), C2 = pack2(-1.f - Bn, -1.f - Bn);
         const int k = a.k;
         const int et = tid;  // 0..255: slot in the per-thread top / ring arrays
         const unsigned ring0 = smem_u32(ring + et), ringp0 = smem_u32(ringp + et);
@@ -407,53 +438,55 @@ __global__ void __launch_bounds__(kMmaThreads, 1) score_mma_kernel(const MmaArgs
                 psi_max = hdr.psi_max;
                 refresh();
             }
-            mbar_wait(bar_done0 + 8 * s, par);   // accumulator of chunk c complete
+            const int t = c % NA;
+            mbar_wait(bar_done0 + 8 * t, (unsigned)((c / NA) & 1));   // accumulator of chunk c complete
             tc_fence_after();
 
-            const int cbase = half * kHalfCols;              // this thread's first column of the chunk
-            const int my_count = hdr.count - cbase;          // columns of mine that hold labels (<= 0: none)
+            const int lbase = half * kHalfLabels;            // this thread's first label of the chunk
+            const int my_count = hdr.count - lbase;          // labels of mine that exist (<= 0: none)
+            // num | w2 | as2 of my 16 labels -> registers, then the accumulator buffer is released at once
+            float vn[16], vw[16], vs[16];
+            {
+                const unsigned tcol = tmem_base + ((unsigned)lane_base << 16) + (unsigned)(t * kMmaN + lbase);
+                tmem_ld16(tcol, vn);
+                tmem_ld16(tcol + kMmaNL, vw);
+                tmem_ld16(tcol + 2 * kMmaNL, vs);
+            }
+            tc_fence_before();
+            mbar_arrive(bar_accfree0 + 8 * t);
             if (my_count > 0) {
-                float p[32];
-                tmem_ld32(tmem_base + ((unsigned)lane_base << 16) + (unsigned)(s * kMmaN + cbase), p);
                 float* out = (MODE != 0 && a.scores != nullptr && img_ok)
-                                 ? a.scores + (int64_t)(hdr.label0 + cbase) * a.N + img : nullptr;
-                const float* cp = cst + (cbase >> 1) * 12;
-                auto columns = [&](auto full_c) {   // FULL: all 32 columns hold labels, no bound checks
+                                 ? a.scores + (int64_t)(hdr.label0 + lbase) * a.N + img : nullptr;
+                const float* cp = cst + (lbase >> 1) * 8;
+                auto columns = [&](auto full_c) {   // FULL: all 16 labels exist, no bound checks
                 constexpr bool FULL = decltype(full_c)::value != 0;
 #pragma unroll
-                for (int q = 0; q < 16; ++q) {
+                for (int q = 0; q < 8; ++q) {
                     const int col = 2 * q;
                     if (FULL || col < my_count) {   // uniform over the CTA half
-                        const float4 k0 = *reinterpret_cast<const float4*>(cp + q * 12);       // A, A', 1+A, 1+A'
-                        const float4 k1 = *reinterpret_cast<const float4*>(cp + q * 12 + 4);   // A^2, A'^2, -psi, -psi'
-                        const u64 A2 = pack2(k0.x, k0.y), A12 = pack2(k0.z, k0.w), ASQ = pack2(k1.x, k1.y), NPSI = pack2(k1.z, k1.w);
-                        const u64 P = pack2(p[2 * q], p[2 * q + 1]);
-                        const u64 M2 = pack2(-2.f, -2.f), ONE2 = pack2(1.f, 1.f);
-                        const u64 qq = fmul2(P, M2);
-                        const u64 num = ffma2(P, A12, fmul2(A2, C2));            // p(1+A) - A(1+B)
-                        const u64 w2 = fadd2(qq, ffma2(A2, B2, ONE2));           // 1 + AB - 2p
-                        const u64 as2 = ffma2(A2, qq, ffma2(A2, B2, ASQ));       // A (A + B - 2p)
-                        const u64 d2 = fmul2(as2, w2);
+                        const float4 k1 = *reinterpret_cast<const float4*>(cp + q * 8);   // -psi, -psi', cos psi, cos psi'
+                        const u64 NPSI = pack2(k1.x, k1.y);
+                        const u64 d2 = fmul2(pack2(vs[col], vs[col + 1]), pack2(vw[col], vw[col + 1]));   // A s^2 w^2
                         float d0, d1;
                         unpack2(d2, d0, d1);
-                        const u64 g = fmul2(num, pack2(rsqrt_approx(d0), rsqrt_approx(d1)));
+                        const u64 g = fmul2(pack2(vn[col], vn[col + 1]), pack2(rsqrt_approx(d0), rsqrt_approx(d1)));
                         const bool second = FULL || col + 1 < my_count;
-                        const int lab = hdr.label0 + cbase + col;
+                        const int lab = hdr.label0 + lbase + col;
                         if (MODE == 0) {
                             if (want_topk) {
-                                const float4 k2 = *reinterpret_cast<const float4*>(cp + q * 12 + 8);  // cos psi x2, sin psi x2
-                                const u64 cb = ffma2(pack2(cT, cT), pack2(k2.x, k2.y), ffma2(pack2(nsT, nsT), pack2(k2.z, k2.w), pack2(off, off)));
+                                const float2 k2 = *reinterpret_cast<const float2*>(cp + q * 8 + 4);  // sin psi, sin psi'
+                                const u64 cb = ffma2(pack2(cT, cT), pack2(k1.z, k1.w), ffma2(pack2(nsT, nsT), pack2(k2.x, k2.y), pack2(off, off)));
                                 float g0, g1, b0, b1;
                                 unpack2(g, g0, g1);
                                 unpack2(cb, b0, b1);
                                 if (g0 >= b0) {
                                     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(rp), "f"(g0), "r"(lab) : "memory");
-                                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(ringp0 + ((rp - ring0) >> 1)), "f"(k1.z) : "memory");
+                                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(ringp0 + ((rp - ring0) >> 1)), "f"(k1.x) : "memory");
                                     rp += kEpiThreads * 8;
                                 }
                                 if (second && g1 >= b1) {
                                     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(rp), "f"(g1), "r"(lab + 1) : "memory");
-                                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(ringp0 + ((rp - ring0) >> 1)), "f"(k1.w) : "memory");
+                                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(ringp0 + ((rp - ring0) >> 1)), "f"(k1.y) : "memory");
                                     rp += kEpiThreads * 8;
                                 }
                             }
@@ -483,7 +516,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) score_mma_kernel(const MmaArgs
                     }
                 }
                 };
-                if (my_count >= kHalfCols) columns(std::integral_constant<int, 1>());
+                if (my_count >= kHalfLabels) columns(std::integral_constant<int, 1>());
                 else columns(std::integral_constant<int, 0>());
             }
             if (want_topk && (hdr.flags & 2)) {
@@ -505,8 +538,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) score_mma_kernel(const MmaArgs
                 }
                 epi_bar_sync();       // the next level's reset must not overtake the fold
             }
-            // this thread is done with accumulator buffer s and blob stage s
-            tc_fence_before();
+            // this thread is done with the constants of blob stage s (its MMAs completed before done[t] fired)
             mbar_arrive(bar_empty0 + 8 * s);
         }
     }
@@ -522,12 +554,12 @@ __global__ void __launch_bounds__(kMmaThreads, 1) score_mma_kernel(const MmaArgs
 static int build_chunks(int64_t L, const int32_t* level_start, const int32_t* level_stop, int n_levels, bool gaps, MmaChunkTable& t) {
     t.n = 0;
     auto add_segment = [&](int64_t s, int64_t e, int level) -> bool {
-        for (int64_t l0 = s; l0 < e || (l0 == s && level >= 0); l0 += kMmaN) {
+        for (int64_t l0 = s; l0 < e || (l0 == s && level >= 0); l0 += kMmaNL) {
             if (t.n >= kMmaMaxChunks) return false;
             MmaChunk& c = t.c[t.n++];
-            const int64_t cnt = e - l0 < kMmaN ? e - l0 : kMmaN;
+            const int64_t cnt = e - l0 < kMmaNL ? e - l0 : kMmaNL;
             c.label0 = (int)l0; c.count = (short)(cnt < 0 ? 0 : cnt); c.level = (signed char)level;
-            c.flags = (unsigned char)((l0 == s ? 1 : 0) | (l0 + kMmaN >= e ? 2 : 0));
+            c.flags = (unsigned char)((l0 == s ? 1 : 0) | (l0 + kMmaNL >= e ? 2 : 0));
             if (e <= s) break;  // empty level: one empty chunk so that its top-k rows are still written
         }
         return true;
@@ -547,13 +579,23 @@ static int build_chunks(int64_t L, const int32_t* level_start, const int32_t* le
 }
 
 int64_t score_mma_workspace_bytes(int64_t L, int D, int n_levels) {
-    const int64_t chunks = (L + kMmaN - 1) / kMmaN + 2 * (int64_t)n_levels + 2;
+    const int64_t chunks = (L + kMmaNL - 1) / kMmaNL + 2 * (int64_t)n_levels + 2;
     return chunks * mma_blob_bytes(mma_kp(D));
 }
 
+// TMEM budget of one CTA: acc_stages accumulator buffers of 96 columns + the image tile (2 Kp columns).  Two buffers
+// inside 256 columns when the rows are short (two CTAs per SM), else one buffer inside 256, else two inside 512.
+static bool mma_plan(int Kp, int& acc_stages, int& tmem_cols) {
+    if (2 * kMmaN + 2 * Kp <= 256) { acc_stages = 2; tmem_cols = 256; return true; }
+    if (kMmaN + 2 * Kp <= 256) { acc_stages = 1; tmem_cols = 256; return true; }
+    if (2 * kMmaN + 2 * Kp <= 512) { acc_stages = 2; tmem_cols = 512; return true; }
+    return false;
+}
+
 bool score_mma_supported(int geom, int precision, int D, int64_t L, int n_levels) {
-    return geom == LEC_GEOM_HYP && precision == LEC_PREC_F32 && D >= 1 && D <= 128 &&
-           (L + kMmaN - 1) / kMmaN + 2 * n_levels + 2 <= kMmaMaxChunks;
+    int na, tc;
+    return geom == LEC_GEOM_HYP && precision == LEC_PREC_F32 && D >= 1 && D <= 128 && mma_plan(mma_kp(D), na, tc) &&
+           (L + kMmaNL - 1) / kMmaNL + 2 * n_levels + 2 <= kMmaMaxChunks;
 }
 
 int score_mma_launch(const float* labels, int64_t L, const float* images, int64_t N, int D, float K, const int32_t* level_start,
@@ -578,10 +620,12 @@ int score_mma_launch(const float* labels, int64_t L, const float* images, int64_
     a.topk_idx = topk_idx; a.topk_val = topk_val; a.k = topk_idx ? k : 1; a.n_levels = n_levels;
     a.ring = topk_idx ? 16 : 0;   // matrix-only launches need no candidate ring
     const size_t fixed = (size_t)a.k * kEpiThreads * 8 + (size_t)a.ring * kEpiThreads * 12 + 256;
-    // two blob stages + two accumulator buffers keep a CTA within 256 TMEM columns and ~half of the shared memory,
-    // so two CTAs (20 warps) share an SM; wide rows fall back to one CTA per SM
+    // two blob stages and <= 256 TMEM columns keep two CTAs (20 warps) on an SM for short rows; wide rows fall back to
+    // one CTA per SM and, if shared memory is short, to a single blob stage
+    if (!mma_plan(Kp, a.acc_stages, a.tmem_cols)) return LEC_E_DIM;
     a.stages = 2;
-    const size_t smem = fixed + (size_t)a.stages * blob;
+    size_t smem = fixed + (size_t)a.stages * blob;
+    if (smem > 227 * 1024) { a.stages = 1; smem = fixed + (size_t)blob; }
     if (smem > 227 * 1024) return LEC_E_DIM;
     const int mode = topk_idx ? (scores ? 2 : 0) : 1;
     const int64_t grid = (N + kMmaM - 1) / kMmaM;

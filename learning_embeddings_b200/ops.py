@@ -309,6 +309,35 @@ def _score_workspace(dev, nbytes):
     return ws[off:]
 
 
+def score_topk_into(labels, images, geom, K, level_start, level_stop, k, idx, val=None, scores=None, scores_layout=1,
+                    precision=PREC_F32, engine="auto"):
+    """lec_score_topk_tc / lec_score_topk_ex on caller-owned outputs (any of idx / val / scores may be None)."""
+    L, D = labels.shape
+    n_img = images.shape[0]
+    nl = len(level_start)
+    ls = (ctypes.c_int32 * max(nl, 1))(*[int(v) for v in level_start])
+    le = (ctypes.c_int32 * max(nl, 1))(*[int(v) for v in level_stop])
+    dev = labels.device
+    # engine: "tc" = tcgen05 tensor-core contraction + fused epilogue (lec_score_topk_tc), "simt" = the packed-FMA
+    # tile kernel (lec_score_topk_ex); "auto" takes the tensor-core path whenever the library supports the case
+    lib = N.lib()
+    tc_ok = scores_layout == 1 and bool(lib.lec_score_tc_supported(GEOM[geom], int(precision), D, L, nl))
+    if engine == "tc" and not tc_ok:
+        raise N.LecError("tensor-core scoring supports hyperbolic cones, fp32 core, label-major scores, D <= 128")
+    if tc_ok and engine in ("auto", "tc"):
+        nbytes = int(lib.lec_score_workspace_bytes(L, D, nl))
+        ws = _score_workspace(dev, nbytes)
+        N.check(lib.lec_score_topk_tc(GEOM[geom], int(precision), N._p(labels), L, N._p(images), n_img, D,
+                                      float(K or 0.0), ctypes.cast(ls, ctypes.c_void_p), ctypes.cast(le, ctypes.c_void_p),
+                                      nl, int(k), N._p(scores), N._p(idx), N._p(val), N._p(ws), nbytes, N.stream_ptr(dev)),
+                "lec_score_topk_tc")
+        return
+    N.check(lib.lec_score_topk_ex(GEOM[geom], int(precision), N._p(labels), L, N._p(images), n_img, D,
+                                  float(K or 0.0), ctypes.cast(ls, ctypes.c_void_p), ctypes.cast(le, ctypes.c_void_p),
+                                  nl, int(k), N._p(scores), int(scores_layout), N._p(idx), N._p(val), N.stream_ptr(dev)),
+            "lec_score_topk_ex")
+
+
 def score_topk(labels, images, geom, K, level_start, level_stop, k=5, want_scores=False, want_values=True,
                precision=PREC_F32, scores_layout="label_major", engine="auto"):  # scoring only ranks: fp32 core by default
     """Per image, per level: the k labels of lowest energy E(x=label, y=image) (lec_score_topk_ex).
@@ -322,8 +351,6 @@ def score_topk(labels, images, geom, K, level_start, level_stop, k=5, want_score
     L, D = labels.shape
     n_img = images.shape[0]
     nl = len(level_start)
-    ls = (ctypes.c_int32 * max(nl, 1))(*[int(v) for v in level_start])
-    le = (ctypes.c_int32 * max(nl, 1))(*[int(v) for v in level_stop])
     dev = labels.device
     idx = torch.empty((n_img, nl, k), device=dev, dtype=torch.int32)
     val = torch.empty((n_img, nl, k), device=dev, dtype=torch.float32) if want_values else None
@@ -331,24 +358,57 @@ def score_topk(labels, images, geom, K, level_start, level_stop, k=5, want_score
     scores = None
     if want_scores:
         scores = torch.empty((L, n_img) if layout == 1 else (n_img, L), device=dev, dtype=torch.float32)
-    # engine: "tc" = tcgen05 tensor-core contraction + fused epilogue (lec_score_topk_tc), "simt" = the packed-FMA
-    # tile kernel (lec_score_topk_ex); "auto" takes the tensor-core path whenever the library supports the case
-    lib = N.lib()
-    tc_ok = layout == 1 and bool(lib.lec_score_tc_supported(GEOM[geom], int(precision), D, L, nl))
-    if engine == "tc" and not tc_ok:
-        raise N.LecError("tensor-core scoring supports hyperbolic cones, fp32 core, label-major scores, D <= 128")
-    if tc_ok and engine in ("auto", "tc"):
-        nbytes = int(lib.lec_score_workspace_bytes(L, D, nl))
-        ws = _score_workspace(dev, nbytes)
-        N.check(lib.lec_score_topk_tc(GEOM[geom], int(precision), N._p(labels), L, N._p(images), n_img, D,
-                                      float(K or 0.0), ctypes.cast(ls, ctypes.c_void_p), ctypes.cast(le, ctypes.c_void_p),
-                                      nl, int(k), N._p(scores), N._p(idx), N._p(val), N._p(ws), nbytes, N.stream_ptr(dev)),
-                "lec_score_topk_tc")
-        return idx, val, (scores.t() if scores is not None else None)
-    N.check(N.lib().lec_score_topk_ex(GEOM[geom], int(precision), N._p(labels), L, N._p(images), n_img, D,
-                                      float(K or 0.0), ctypes.cast(ls, ctypes.c_void_p), ctypes.cast(le, ctypes.c_void_p),
-                                      nl, int(k), N._p(scores), layout, N._p(idx), N._p(val), N.stream_ptr(dev)),
-            "lec_score_topk_ex")
+    score_topk_into(labels, images, geom, K, level_start, level_stop, k, idx, val, scores, layout, precision, engine)
     if scores is not None and layout == 1:
         scores = scores.t()
     return idx, val, scores
+
+
+class ScorePipeline:
+    """Host-to-host scoring of a large image set (the call the reference's calculate_classification_metrics would
+    make, oe_h.py:1971-2036): pinned host image embeddings in, per-level top-k label ids (and energies) out in pinned
+    host memory.  The set is cut into slices; the upload of slice j+1 and the download of slice j-1 run on their
+    own streams while slice j is scored, so the PCIe copies overlap the kernel."""
+
+    def __init__(self, labels, geom, K, level_start, level_stop, k=5, slice_images=131072, engine="auto",
+                 precision=PREC_F32):
+        N.require_cuda(labels)
+        self.labels = labels.detach().contiguous().float()
+        self.geom, self.K, self.k, self.engine, self.precision = geom, K, int(k), engine, precision
+        self.level_start, self.level_stop = list(level_start), list(level_stop)
+        dev = self.labels.device
+        self.dev, self.slice = dev, int(slice_images)
+        D, nl = self.labels.shape[1], len(self.level_start)
+        self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.img = [torch.empty((self.slice, D), device=dev) for _ in range(2)]
+        self.idx = [torch.empty((self.slice, nl, self.k), device=dev, dtype=torch.int32) for _ in range(2)]
+        self.val = [torch.empty((self.slice, nl, self.k), device=dev) for _ in range(2)]
+        self.ev_in = [torch.cuda.Event() for _ in range(2)]
+        self.ev_scored = [torch.cuda.Event() for _ in range(2)]
+        self.ev_out = [torch.cuda.Event() for _ in range(2)]
+
+    def run(self, images_host, out_idx_host, out_val_host=None):
+        if images_host.is_cuda or out_idx_host.is_cuda:
+            raise N.LecError("ScorePipeline.run takes host tensors (use ops.score_topk for device tensors)")
+        main = torch.cuda.current_stream(self.dev)
+        n_img = images_host.shape[0]
+        for j, s0 in enumerate(range(0, n_img, self.slice)):
+            b, n = j & 1, min(self.slice, n_img - s0)
+            with torch.cuda.stream(self.s_in):
+                self.s_in.wait_event(self.ev_scored[b])      # the kernel that last read this slot has finished
+                self.img[b][:n].copy_(images_host[s0:s0 + n], non_blocking=True)
+                self.ev_in[b].record(self.s_in)
+            main.wait_event(self.ev_in[b])
+            main.wait_event(self.ev_out[b])                  # the download that last read this slot's outputs has finished
+            score_topk_into(self.labels, self.img[b][:n], self.geom, self.K, self.level_start, self.level_stop, self.k,
+                            self.idx[b][:n], self.val[b][:n] if out_val_host is not None else None, None, 1,
+                            self.precision, self.engine)
+            self.ev_scored[b].record(main)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(self.ev_scored[b])
+                out_idx_host[s0:s0 + n].copy_(self.idx[b][:n], non_blocking=True)
+                if out_val_host is not None:
+                    out_val_host[s0:s0 + n].copy_(self.val[b][:n], non_blocking=True)
+                self.ev_out[b].record(self.s_out)
+        self.s_out.synchronize()
+        return out_idx_host

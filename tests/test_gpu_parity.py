@@ -494,6 +494,26 @@ def test_scoring_full_size_properties(engine, D):
     assert torch.equal(ip, idx[perm]) and torch.equal(vp, val[perm])
 
 
+@pytest.mark.parametrize("engine", ("simt", "tc"))
+def test_score_pipeline_host_to_host_equals_device_call(engine):
+    """ops.ScorePipeline (sliced, copies overlapped with the kernel) returns exactly what one device call returns."""
+    gen = torch.Generator().manual_seed(11)
+    h = load_golden("ethec_hierarchy")
+    D, n_img = 10, 5000 + 3
+    labels = _ball(gen, 723, D, 0.1, 0.9).to(DEV)
+    images = _ball(gen, n_img, D, 0.30, 0.95)
+    idx, val, _ = ops.score_topk(labels, images.to(DEV), "hyp", 0.1, h["level_start"], h["level_stop"], k=5, engine=engine)
+    pipe = ops.ScorePipeline(labels, "hyp", 0.1, h["level_start"], h["level_stop"], k=5, slice_images=1024, engine=engine)
+    out_idx = torch.empty((n_img, 4, 5), dtype=torch.int32).pin_memory()
+    out_val = torch.empty((n_img, 4, 5), dtype=torch.float32).pin_memory()
+    for _ in range(2):   # the second run reuses the slots
+        out_idx.fill_(-7)
+        pipe.run(images.pin_memory(), out_idx, out_val)
+        assert torch.equal(out_idx, idx.cpu()) and torch.equal(out_val, val.cpu())
+    with pytest.raises(N.LecError):
+        pipe.run(images.to(DEV), out_idx)
+
+
 # ------------------------------------------------------------------------------------------------
 # joint image+label criteria (oe.py / oe_h.py drop-ins)
 # ------------------------------------------------------------------------------------------------

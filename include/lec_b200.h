@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LEC_ABI_VERSION 9
+#define LEC_ABI_VERSION 10
 
 /* geometry of the energy */
 #define LEC_GEOM_EUC 0 /* EucConesLoss.E_operator, order_embeddings.py:954-969 = oe.py:721-739 (cos-space) */
@@ -293,6 +293,31 @@ int lec_sample_negatives_philox(const lec_sampler_graph* g, const void* u, const
                                 void* stream);
 /* the fast mode's integer draw, on the host (for tests): uniform in [0, n) */
 int64_t lec_philox_below(uint64_t seed, uint64_t stream_id, uint64_t draw, uint64_t n);
+
+/* ---- evaluation bookkeeping -----------------------------------------------------------------------
+ * lec_f1_sweep replaces EmbeddingMetrics.calculate_metrics, 'val' phase (order_embeddings.py:272-287 = oe.py:380-395:
+ * every unique energy is a candidate threshold, evaluated by a process pool with two passes over all energies each).
+ *   sorted_energies  device float[n]: positive and negative energies together, ascending, NaN last
+ *   pos_prefix       device int64[n]: number of POSITIVE-pair energies among sorted_energies[0..i]
+ *   out7             device double[7]: {f1, threshold, accuracy, precision, recall, correct_positives, correct_negatives}
+ *                    of the first threshold with maximal F1 -- the row calculate_metrics returns; computed with the
+ *                    reference's fp64 expression tree, so equal to its Python floats bit for bit
+ *   workspace        device, >= lec_f1_workspace_bytes() bytes */
+int64_t lec_f1_workspace_bytes(void);
+int lec_f1_sweep(const float* sorted_energies, const int64_t* pos_prefix, int64_t n, int64_t n_pos, int64_t n_neg,
+                 double* out7, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* lec_classify_counts replaces the per-image bookkeeping of JointEmbeddings.calculate_classification_metrics
+ * (oe.py:1775-1796, oe_h.py:2030-2051) on the output of lec_score_topk*.
+ *   topk_idx  device int32 [n_img, n_levels, k]   truth  device int32 [n_img, n_levels] (true label per level, < 0: skip)
+ *   k_vals    HOST int32[n_kvals] (the reference's k = [1, 3, 5])
+ *   hit            device uint64 [n_kvals, L]   += 1 at the TRUE label when it is among the first k_vals[j] predictions
+ *   counts         device uint64 [3, L]         tp (at the true label), fp (at the predicted label), fn (at the true label)
+ *   level_correct  device uint64 [n_levels]     correct top-1 predictions per level; tn[l] = level_correct[level(l)] - tp[l]
+ * All three outputs are accumulated into (zero them first). */
+int lec_classify_counts(const int32_t* topk_idx, const int32_t* truth, int64_t n_img, int n_levels, int k,
+                        const int32_t* k_vals, int n_kvals, int64_t L, uint64_t* hit, uint64_t* counts,
+                        uint64_t* level_correct, void* stream);
 
 #ifdef __cplusplus
 }

@@ -382,23 +382,18 @@ int launch_flat_tv(const FlatArgs& a, cudaStream_t st) {
     return (int)cudaGetLastError();
 }
 
-// Teams per group.  A team's trip count is w(s) = 1 + 2*ceil(N/s) pair evaluations (the positive is re-evaluated by
-// every team of a split group), a launch holds `cap` teams at once, so time ~ w(s) * max(1, B*s/cap): splitting
-// pays only while the batch cannot fill the GPU (cfg4: 2 569 positives x 51 pairs); a batch that already fills it
-// (cfg1: 190 650 positives) stays at s = 1, where no pair is evaluated twice.  LEC_GROUP_SPLIT overrides (tuning).
+// Teams per group.  A team's trip count is 1 + 2*ceil(N/s) pair evaluations (the positive is re-evaluated by every team
+// of a split group), so splitting only pays while the batch cannot fill the GPU: s is the largest split that still
+// fits one resident wave of `cap` teams.  cfg4 (2 569 positives x 51 pairs, cap 9 472) -> s = 3, measured 30.8 us against
+// 71.7 us unsplit and 37.0 us at s = 5 (profiles/r1d_cfg4_split_sweep.md); a batch that already fills the GPU (cfg1: 190 650
+// positives) stays at s = 1, where no pair is evaluated twice.  LEC_GROUP_SPLIT overrides (tuning).
 inline int choose_split(int64_t B, int N, int64_t cap) {
     static const int forced = [] { const char* e = getenv("LEC_GROUP_SPLIT"); return e ? atoi(e) : 0; }();
     if (forced > 0) return forced < N ? forced : (N > 0 ? N : 1);
     if (B <= 0 || N <= 1 || cap <= 0) return 1;
-    int best = 1;
-    double best_t = 0.0;
-    for (int s = 1; s <= N; ++s) {
-        const double w = 1.0 + 2.0 * ((N + s - 1) / s);
-        const double fill = (double)B * s / (double)cap;
-        const double t = w * (fill > 1.0 ? fill : 1.0);
-        if (s == 1 || t < best_t * 0.97) { best = s; best_t = t; }
-    }
-    return best;
+    int64_t s = cap / B;
+    if (s > N) s = N;
+    return s < 1 ? 1 : (int)s;
 }
 
 template <int CORE, int T, int V>

@@ -41,8 +41,11 @@
 namespace lec {
 
 constexpr int kMmaM = 128;       // images per CTA (TMEM lanes)
-constexpr int kMmaNL = 32;       // labels per chunk
-constexpr int kMmaN = 3 * kMmaNL; // B rows per chunk = TMEM columns per accumulator buffer: num | w2 | as2
+constexpr int kMmaN = 96;        // B rows per chunk = TMEM columns per accumulator buffer
+// FORMS = 3: the rows of a chunk are num | w2 | as2 of 32 labels (all pair algebra on the tensor pipe: 9 K-passes per
+// score); FORMS = 1: plain label rows of 96 labels, p = <x, y> only, the pair algebra stays on the FMA pipe.  Three
+// forms triple the tensor work (3 forms x 3 TF32 passes x Kp MACs per score), which the tensor pipe hides behind the
+// epilogue only while Kp <= 32; wider rows keep one form.
 constexpr int kMmaMaxChunks = 224;
 constexpr int kMmaRingCheck = 8; // ring room needed between two merge checks (4 label pairs)
 
@@ -51,10 +54,12 @@ struct MmaChunkTable { int n; MmaChunk c[kMmaMaxChunks]; };
 
 struct MmaHdr { int label0, count, level, flags; float psi_max; int pad[3]; };  // 32 bytes, tail of a blob
 
-__host__ __device__ inline int mma_kp(int D) { return (D + 2 + 7) / 8 * 8; }                    // [row, |row|^2-slot, 1-slot], padded
+__host__ __device__ inline int mma_forms(int D) { return (D + 2 + 7) / 8 * 8 <= 32 ? 3 : 1; }
+__host__ __device__ inline int mma_labels(int forms) { return kMmaN / forms; }                   // labels per chunk
+__host__ __device__ inline int mma_kp(int D, int forms) { return ((forms == 3 ? D + 2 : D) + 7) / 8 * 8; }  // forms 3: [row, |row|^2-slot, 1-slot]
 __host__ __device__ inline int mma_tile_bytes(int Kp) { return kMmaN * Kp * 4; }                 // one B tile (hi or lo)
-__host__ __device__ inline int mma_const_bytes() { return (kMmaNL / 2) * 8 * 4; }               // 16 pairs x 8 floats
-__host__ __device__ inline int mma_blob_bytes(int Kp) { return 2 * mma_tile_bytes(Kp) + mma_const_bytes() + (int)sizeof(MmaHdr); }
+__host__ __device__ inline int mma_const_bytes(int forms) { return (mma_labels(forms) / 2) * 12 * 4; }   // 12 floats per label pair
+__host__ __device__ inline int mma_blob_bytes(int Kp, int forms) { return 2 * mma_tile_bytes(Kp) + mma_const_bytes(forms) + (int)sizeof(MmaHdr); }
 
 __device__ __forceinline__ float to_tf32(float v) {
     unsigned r;
@@ -65,12 +70,13 @@ __device__ __forceinline__ float to_tf32(float v) {
 // ------------------------------------------------------------------------------------------------
 // prep: labels -> chunk blobs
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kMmaN) score_mma_prep_kernel(const float* __restrict__ labels, int D, int Kp, float K,
+__global__ void __launch_bounds__(kMmaN) score_mma_prep_kernel(const float* __restrict__ labels, int D, int Kp, int forms, float K,
                                                                 const MmaChunkTable tab, unsigned char* __restrict__ ws) {
-    const int c = blockIdx.x, j = threadIdx.x;   // thread j writes B row j: form j / 32 of label j % 32
-    const int form = j / kMmaNL, jl = j % kMmaNL;
+    const int c = blockIdx.x, j = threadIdx.x;   // thread j writes B row j: form j / NL of label j % NL
+    const int NL = mma_labels(forms);
+    const int form = j / NL, jl = j % NL;
     const MmaChunk ch = tab.c[c];
-    unsigned char* blob = ws + (size_t)c * mma_blob_bytes(Kp);
+    unsigned char* blob = ws + (size_t)c * mma_blob_bytes(Kp, forms);
     float* hi = reinterpret_cast<float*>(blob);
     float* lo = reinterpret_cast<float*>(blob + mma_tile_bytes(Kp));
     float* cst = reinterpret_cast<float*>(blob + 2 * mma_tile_bytes(Kp));
@@ -81,10 +87,14 @@ __global__ void __launch_bounds__(kMmaN) score_mma_prep_kernel(const float* __re
         const double v = live ? (double)__ldg(src + k) : 0.0;
         A += v * v;
     }
-    // x'_num = [(1+A) x, -A, -A]   x'_w2 = [-2 x, A, 1]   x'_as2 = [-2A x, A, A^2]     (against y' = [y, B, 1])
-    const double coef = form == 0 ? 1.0 + A : (form == 1 ? -2.0 : -2.0 * A);
-    const double tailB = form == 0 ? -A : A;
-    const double tail1 = form == 0 ? -A : (form == 1 ? 1.0 : A * A);
+    // forms == 3:  x'_num = [(1+A) x, -A, -A]   x'_w2 = [-2 x, A, 1]   x'_as2 = [-2A x, A, A^2]   (against y' = [y, B, 1])
+    // forms == 1:  x' = x
+    double coef = 1.0, tailB = 0.0, tail1 = 0.0;
+    if (forms == 3) {
+        coef = form == 0 ? 1.0 + A : (form == 1 ? -2.0 : -2.0 * A);
+        tailB = form == 0 ? -A : A;
+        tail1 = form == 0 ? -A : (form == 1 ? 1.0 : A * A);
+    }
     for (int k0 = 0; k0 < Kp; k0 += 4) {
         float h[4], l[4];
 #pragma unroll
@@ -104,14 +114,17 @@ __global__ void __launch_bounds__(kMmaN) score_mma_prep_kernel(const float* __re
         *reinterpret_cast<float4*>(hi + off) = make_float4(h[0], h[1], h[2], h[3]);
         *reinterpret_cast<float4*>(lo + off) = make_float4(l[0], l[1], l[2], l[3]);
     }
-    const Aux<double> x = row_aux<double>(LEC_GEOM_HYP, live ? A : 0.25, K);
+    const double Av = live ? A : 0.25;
+    const Aux<double> x = row_aux<double>(LEC_GEOM_HYP, Av, K);
     if (form == 0) {
-        const double sp = sin(x.t0);
-        float* q = cst + (jl >> 1) * 8 + (jl & 1);   // pair layout: {-psi, -psi', cos psi, cos psi', sin psi, sin psi', 0, 0}
-        q[0] = (float)(-x.t0);
-        q[2] = (float)sqrt(fmax(0.0, 1.0 - sp * sp));
-        q[4] = (float)sp;
-        q[6] = 0.f;
+        const double sp = sin(x.t0), cp = sqrt(fmax(0.0, 1.0 - sp * sp));
+        float* q = cst + (jl >> 1) * 12 + (jl & 1);
+        if (forms == 3) {   // {-psi, -psi', cos psi, cos psi'} {sin psi, sin psi', 0, 0} {0, 0, 0, 0}
+            q[0] = (float)(-x.t0); q[2] = (float)cp; q[4] = (float)sp; q[6] = 0.f; q[8] = 0.f; q[10] = 0.f;
+        } else {            // {A, A', 1+A, 1+A'} {A^2, A'^2, -psi, -psi'} {cos psi, cos psi', sin psi, sin psi'}
+            q[0] = (float)Av; q[2] = (float)(1.0 + Av); q[4] = (float)(Av * Av); q[6] = (float)(-x.t0);
+            q[8] = (float)cp; q[10] = (float)sp;
+        }
     }
     // largest half-aperture of the chunk (for the deferred-angle filter's validity test thr + psi <= pi)
     float pm = live ? (float)x.t0 : -INFINITY;
@@ -121,7 +134,7 @@ __global__ void __launch_bounds__(kMmaN) score_mma_prep_kernel(const float* __re
     if ((j & 31) == 0) wmax[j >> 5] = pm;
     __syncthreads();
     if (j == 0) {
-        MmaHdr* h = reinterpret_cast<MmaHdr*>(blob + 2 * mma_tile_bytes(Kp) + mma_const_bytes());
+        MmaHdr* h = reinterpret_cast<MmaHdr*>(blob + 2 * mma_tile_bytes(Kp) + mma_const_bytes(forms));
         h->label0 = ch.label0; h->count = ch.count; h->level = ch.level; h->flags = ch.flags;
         h->psi_max = fmaxf(wmax[0], fmaxf(wmax[1], wmax[2]));
         h->pad[0] = h->pad[1] = h->pad[2] = 0;
@@ -148,7 +161,10 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-        if (!ok && spin > (1u << 24)) __trap();
+        if (!ok) {
+            if (spin > 4) __nanosleep(32);   // a waiting warp must not eat the issue slots of the working ones
+            if (spin > (1u << 22)) __trap();
+        }
     }
 }
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
@@ -225,7 +241,6 @@ struct MmaArgs {
 constexpr int kMmaMaxStages = 4;
 constexpr int kEpiThreads = 2 * kMmaM;          // 8 epilogue warps: two threads per image, 16 labels (3 x 16 columns) each
 constexpr int kMmaThreads = kEpiThreads + 64;   // + warp 8 (tcgen05.mma issue) + warp 9 (TMA bulk copies)
-constexpr int kHalfLabels = kMmaNL / 2;
 
 __device__ __forceinline__ void mbar_arrive(unsigned bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -254,12 +269,15 @@ __device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32]) {
 // complete), accfree[t] (all 256 epilogue threads hold accumulator t's values in registers), empty[s] (all 256
 // epilogue threads are finished with the constants of blob stage s, whose MMAs have completed).
 // MODE 0: top-k only (deferred angle), 1: matrix only, 2: matrix + top-k
-template <int MODE>
-__global__ void __launch_bounds__(kMmaThreads, 1) score_mma_kernel(const MmaArgs a) {
+template <int MODE, int FORMS>
+__global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(const MmaArgs a) {
+    constexpr int NL = kMmaN / FORMS;        // labels per chunk
+    constexpr int LT = NL / 2;               // labels per epilogue thread and chunk
+    constexpr int GROUPS = LT / 16;          // groups of 16 labels (8 packed pairs) per thread and chunk
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int Kp = a.Kp, KS = Kp >> 3;
     const int b_tile = mma_tile_bytes(Kp);
-    const int blob = mma_blob_bytes(Kp);
+    const int blob = mma_blob_bytes(Kp, FORMS);
     const int NS = a.stages;
     unsigned char* sB = smem_raw;                // NS blob stages
     float2* top = reinterpret_cast<float2*>(sB + (size_t)NS * blob);               // [k][256] {E, label}
@@ -303,14 +321,14 @@ __global__ void __launch_bounds__(kMmaThreads, 1) score_mma_kernel(const MmaArgs
         const unsigned dst = tmem_base + ((unsigned)((warp & 3) * 32) << 16) + (half ? col_alo : col_ahi);
         if (img_ok)
             for (int k = 0; k < a.D; ++k) { const float v = __ldg(src + k); Bn = fmaf(v, v, Bn); }
-        // y' = [y, |y|^2, 1, 0 ...]
+        // FORMS == 3: y' = [y, |y|^2, 1, 0 ...];  FORMS == 1: y' = [y, 0 ...]
         for (int k0 = 0; k0 < Kp; k0 += 8) {
             float o[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 const int k = k0 + e;
                 float v = 0.f;
-                if (img_ok) v = (k < a.D) ? __ldg(src + k) : (k == a.D ? Bn : (k == a.D + 1 ? 1.f : 0.f));
+                if (img_ok) v = (k < a.D) ? __ldg(src + k) : ((FORMS == 3 && k == a.D) ? Bn : ((FORMS == 3 && k == a.D + 1) ? 1.f : 0.f));
                 const float h = to_tf32(v);
                 o[e] = half ? to_tf32(v - h) : h;
             }
@@ -371,6 +389,8 @@ __global__ void __launch_bounds__(kMmaThreads, 1) score_mma_kernel(const MmaArgs
         __syncwarp();
     } else {
         // ================================ epilogue warps ================================
+        const u64 B2 = pack2(Bn, Bn), C2 = pack2(-1.f - Bn, -1.f - Bn);   // FORMS == 1 only
+        (void)B2; (void)C2;
         const int k = a.k;
         const int et = tid;  // 0..255: slot in the per-thread top / ring arrays
         const unsigned ring0 = smem_u32(ring + et), ringp0 = smem_u32(ringp + et);
@@ -427,7 +447,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) score_mma_kernel(const MmaArgs
             mbar_wait(bar_full0 + 8 * s, par);   // constants + header of chunk c visible to this thread
             const unsigned char* bl = sB + (size_t)s * blob;
             const float* cst = reinterpret_cast<const float*>(bl + 2 * b_tile);
-            const MmaHdr hdr = *reinterpret_cast<const MmaHdr*>(bl + 2 * b_tile + mma_const_bytes());
+            const MmaHdr hdr = *reinterpret_cast<const MmaHdr*>(bl + 2 * b_tile + mma_const_bytes(FORMS));
             const bool want_topk = (MODE != 1) && hdr.level >= 0;
             if (want_topk) {
                 if (hdr.flags & 1) {
@@ -442,82 +462,118 @@ __global__ void __launch_bounds__(kMmaThreads, 1) score_mma_kernel(const MmaArgs
             mbar_wait(bar_done0 + 8 * t, (unsigned)((c / NA) & 1));   // accumulator of chunk c complete
             tc_fence_after();
 
-            const int lbase = half * kHalfLabels;            // this thread's first label of the chunk
+            const int lbase = half * LT;                     // this thread's first label of the chunk
             const int my_count = hdr.count - lbase;          // labels of mine that exist (<= 0: none)
-            // num | w2 | as2 of my 16 labels -> registers, then the accumulator buffer is released at once
-            float vn[16], vw[16], vs[16];
+            // my 48 accumulator columns -> registers, then the accumulator buffer is released at once.
+            // FORMS == 3: v[0] = num, v[1] = w2, v[2] = A s^2 of my 16 labels;  FORMS == 1: v[gi] = p of labels 16 gi ..
+            float v[3][16];
             {
-                const unsigned tcol = tmem_base + ((unsigned)lane_base << 16) + (unsigned)(t * kMmaN + lbase);
-                tmem_ld16(tcol, vn);
-                tmem_ld16(tcol + kMmaNL, vw);
-                tmem_ld16(tcol + 2 * kMmaNL, vs);
+                const unsigned tcol = tmem_base + ((unsigned)lane_base << 16) + (unsigned)(t * kMmaN);
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                    tmem_ld16(tcol + (unsigned)(FORMS == 3 ? i * NL + lbase : lbase + 16 * i), v[i]);
             }
             tc_fence_before();
             mbar_arrive(bar_accfree0 + 8 * t);
-            if (my_count > 0) {
-                float* out = (MODE != 0 && a.scores != nullptr && img_ok)
-                                 ? a.scores + (int64_t)(hdr.label0 + lbase) * a.N + img : nullptr;
-                const float* cp = cst + (lbase >> 1) * 8;
-                auto columns = [&](auto full_c) {   // FULL: all 16 labels exist, no bound checks
-                constexpr bool FULL = decltype(full_c)::value != 0;
+            const bool store = (MODE != 0) && a.scores != nullptr && img_ok;
+#pragma unroll
+            for (int gi = 0; gi < GROUPS; ++gi) {
+                const int gbase = lbase + 16 * gi;               // first label of this group within the chunk
+                const int g_count = hdr.count - gbase;           // labels of the group that exist
+                if (g_count <= 0) break;                         // uniform over the CTA half
+                const float* cp = cst + (gbase >> 1) * 12;
+                // ---- cos of the cone angle for 8 label pairs, branch-free so that the 8 dependent chains interleave
+                u64 g[8], NPSI[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    const int col = 2 * q;
-                    if (FULL || col < my_count) {   // uniform over the CTA half
-                        const float4 k1 = *reinterpret_cast<const float4*>(cp + q * 8);   // -psi, -psi', cos psi, cos psi'
-                        const u64 NPSI = pack2(k1.x, k1.y);
-                        const u64 d2 = fmul2(pack2(vs[col], vs[col + 1]), pack2(vw[col], vw[col + 1]));   // A s^2 w^2
-                        float d0, d1;
-                        unpack2(d2, d0, d1);
-                        const u64 g = fmul2(pack2(vn[col], vn[col + 1]), pack2(rsqrt_approx(d0), rsqrt_approx(d1)));
-                        const bool second = FULL || col + 1 < my_count;
-                        const int lab = hdr.label0 + lbase + col;
-                        if (MODE == 0) {
-                            if (want_topk) {
-                                const float2 k2 = *reinterpret_cast<const float2*>(cp + q * 8 + 4);  // sin psi, sin psi'
-                                const u64 cb = ffma2(pack2(cT, cT), pack2(k1.z, k1.w), ffma2(pack2(nsT, nsT), pack2(k2.x, k2.y), pack2(off, off)));
-                                float g0, g1, b0, b1;
-                                unpack2(g, g0, g1);
-                                unpack2(cb, b0, b1);
-                                if (g0 >= b0) {
-                                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(rp), "f"(g0), "r"(lab) : "memory");
-                                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(ringp0 + ((rp - ring0) >> 1)), "f"(k1.x) : "memory");
-                                    rp += kEpiThreads * 8;
-                                }
-                                if (second && g1 >= b1) {
-                                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(rp), "f"(g1), "r"(lab + 1) : "memory");
-                                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(ringp0 + ((rp - ring0) >> 1)), "f"(k1.y) : "memory");
-                                    rp += kEpiThreads * 8;
-                                }
+                    u64 num, d2;
+                    if (FORMS == 3) {
+                        const float2 k1 = *reinterpret_cast<const float2*>(cp + q * 12);        // -psi, -psi'
+                        NPSI[q] = pack2(k1.x, k1.y);
+                        num = pack2(v[0][2 * q], v[0][2 * q + 1]);
+                        d2 = fmul2(pack2(v[2][2 * q], v[2][2 * q + 1]), pack2(v[1][2 * q], v[1][2 * q + 1]));   // A s^2 w^2
+                    } else {
+                        const float4 k0 = *reinterpret_cast<const float4*>(cp + q * 12);       // A, A', 1+A, 1+A'
+                        const float4 k1 = *reinterpret_cast<const float4*>(cp + q * 12 + 4);   // A^2, A'^2, -psi, -psi'
+                        const u64 A2 = pack2(k0.x, k0.y), A12 = pack2(k0.z, k0.w), ASQ = pack2(k1.x, k1.y);
+                        NPSI[q] = pack2(k1.z, k1.w);
+                        const u64 P = pack2(v[gi][2 * q], v[gi][2 * q + 1]);
+                        const u64 qq = fmul2(P, pack2(-2.f, -2.f));
+                        num = ffma2(P, A12, fmul2(A2, C2));                                      // p(1+A) - A(1+B)
+                        const u64 w2 = fadd2(qq, ffma2(A2, B2, pack2(1.f, 1.f)));               // 1 + AB - 2p
+                        const u64 as2 = ffma2(A2, qq, ffma2(A2, B2, ASQ));                      // A (A + B - 2p)
+                        d2 = fmul2(as2, w2);
+                    }
+                    float d0, d1;
+                    unpack2(d2, d0, d1);
+                    g[q] = fmul2(num, pack2(rsqrt_approx(d0), rsqrt_approx(d1)));
+                }
+                const int lab0 = hdr.label0 + gbase;
+                if (MODE == 0) {
+                    if (want_topk) {
+                        // deferred angle: E < thr  <=>  g > cos(thr + psi); candidates go to the ring as {g, label, -psi}
+                        u64 cb[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 kc = *reinterpret_cast<const float4*>(cp + q * 12 + (FORMS == 3 ? 0 : 8));
+                            const float2 ks = *reinterpret_cast<const float2*>(cp + q * 12 + (FORMS == 3 ? 4 : 10));
+                            const u64 COS = FORMS == 3 ? pack2(kc.z, kc.w) : pack2(kc.x, kc.y);
+                            cb[q] = ffma2(pack2(cT, cT), COS, ffma2(pack2(nsT, nsT), pack2(ks.x, ks.y), pack2(off, off)));
+                        }
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            float g0, g1, b0, b1, np0, np1;
+                            unpack2(g[q], g0, g1);
+                            unpack2(cb[q], b0, b1);
+                            unpack2(NPSI[q], np0, np1);
+                            if (2 * q < g_count && g0 >= b0) {
+                                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(rp), "f"(g0), "r"(lab0 + 2 * q) : "memory");
+                                asm volatile("st.shared.b32 [%0], %1;" ::"r"(ringp0 + ((rp - ring0) >> 1)), "f"(np0) : "memory");
+                                rp += kEpiThreads * 8;
                             }
-                        } else {
-                            float z0, z1;
-                            unpack2(fadd2(acos_clamped2(g), NPSI), z0, z1);
-                            const float E0 = max_nan(z0, 0.f), E1 = max_nan(z1, 0.f);
-                            if (out != nullptr) {
-                                out[0] = E0;
-                                if (second) out[a.N] = E1;
-                                out += 2 * a.N;
+                            if (2 * q + 1 < g_count && g1 >= b1) {
+                                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(rp), "f"(g1), "r"(lab0 + 2 * q + 1) : "memory");
+                                asm volatile("st.shared.b32 [%0], %1;" ::"r"(ringp0 + ((rp - ring0) >> 1)), "f"(np1) : "memory");
+                                rp += kEpiThreads * 8;
                             }
-                            if (MODE == 2 && want_topk) {
-                                if (E0 < thr) {
-                                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(rp), "f"(E0), "r"(lab) : "memory");
-                                    rp += kEpiThreads * 8;
-                                }
-                                if (second && E1 < thr) {
-                                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(rp), "f"(E1), "r"(lab + 1) : "memory");
-                                    rp += kEpiThreads * 8;
-                                }
+                            if ((q & 3) == 3) {
+                                if (__any_sync(0xffffffffu, rp > ring_trigger)) merge();
                             }
                         }
                     }
-                    if (MODE != 1 && (q & 3) == 3) {
-                        if (__any_sync(0xffffffffu, rp > ring_trigger)) merge();
+                } else {
+                    float E[16];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        float z0, z1;
+                        unpack2(fadd2(acos_clamped2(g[q]), NPSI[q]), z0, z1);
+                        E[2 * q] = max_nan(z0, 0.f);
+                        E[2 * q + 1] = max_nan(z1, 0.f);
+                    }
+                    if (store) {
+                        float* out = a.scores + (int64_t)lab0 * a.N + img;
+                        if (g_count >= 16) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) out[(int64_t)j * a.N] = E[j];
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (j < g_count) out[(int64_t)j * a.N] = E[j];
+                        }
+                    }
+                    if (MODE == 2 && want_topk) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            if (j < g_count && E[j] < thr) {
+                                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(rp), "f"(E[j]), "r"(lab0 + j) : "memory");
+                                rp += kEpiThreads * 8;
+                            }
+                            if ((j & 7) == 7) {
+                                if (__any_sync(0xffffffffu, rp > ring_trigger)) merge();
+                            }
+                        }
                     }
                 }
-                };
-                if (my_count >= kHalfLabels) columns(std::integral_constant<int, 1>());
-                else columns(std::integral_constant<int, 0>());
             }
             if (want_topk && (hdr.flags & 2)) {
                 merge();
@@ -551,15 +607,16 @@ __global__ void __launch_bounds__(kMmaThreads, 1) score_mma_kernel(const MmaArgs
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-static int build_chunks(int64_t L, const int32_t* level_start, const int32_t* level_stop, int n_levels, bool gaps, MmaChunkTable& t) {
+static int build_chunks(int64_t L, const int32_t* level_start, const int32_t* level_stop, int n_levels, bool gaps, int NL,
+                        MmaChunkTable& t) {
     t.n = 0;
     auto add_segment = [&](int64_t s, int64_t e, int level) -> bool {
-        for (int64_t l0 = s; l0 < e || (l0 == s && level >= 0); l0 += kMmaNL) {
+        for (int64_t l0 = s; l0 < e || (l0 == s && level >= 0); l0 += NL) {
             if (t.n >= kMmaMaxChunks) return false;
             MmaChunk& c = t.c[t.n++];
-            const int64_t cnt = e - l0 < kMmaNL ? e - l0 : kMmaNL;
+            const int64_t cnt = e - l0 < NL ? e - l0 : NL;
             c.label0 = (int)l0; c.count = (short)(cnt < 0 ? 0 : cnt); c.level = (signed char)level;
-            c.flags = (unsigned char)((l0 == s ? 1 : 0) | (l0 + kMmaNL >= e ? 2 : 0));
+            c.flags = (unsigned char)((l0 == s ? 1 : 0) | (l0 + NL >= e ? 2 : 0));
             if (e <= s) break;  // empty level: one empty chunk so that its top-k rows are still written
         }
         return true;
@@ -578,9 +635,11 @@ static int build_chunks(int64_t L, const int32_t* level_start, const int32_t* le
     return 0;
 }
 
+static int64_t mma_max_chunks(int64_t L, int n_levels, int NL) { return (L + NL - 1) / NL + 2 * (int64_t)n_levels + 2; }
+
 int64_t score_mma_workspace_bytes(int64_t L, int D, int n_levels) {
-    const int64_t chunks = (L + kMmaNL - 1) / kMmaNL + 2 * (int64_t)n_levels + 2;
-    return chunks * mma_blob_bytes(mma_kp(D));
+    const int forms = mma_forms(D);
+    return mma_max_chunks(L, n_levels, mma_labels(forms)) * mma_blob_bytes(mma_kp(D, forms), forms);
 }
 
 // TMEM budget of one CTA: acc_stages accumulator buffers of 96 columns + the image tile (2 Kp columns).  Two buffers
@@ -594,23 +653,25 @@ static bool mma_plan(int Kp, int& acc_stages, int& tmem_cols) {
 
 bool score_mma_supported(int geom, int precision, int D, int64_t L, int n_levels) {
     int na, tc;
-    return geom == LEC_GEOM_HYP && precision == LEC_PREC_F32 && D >= 1 && D <= 128 && mma_plan(mma_kp(D), na, tc) &&
-           (L + kMmaNL - 1) / kMmaNL + 2 * n_levels + 2 <= kMmaMaxChunks;
+    if (!(geom == LEC_GEOM_HYP && precision == LEC_PREC_F32 && D >= 1 && D <= 128)) return false;
+    const int forms = mma_forms(D);
+    return mma_plan(mma_kp(D, forms), na, tc) && mma_max_chunks(L, n_levels, mma_labels(forms)) <= kMmaMaxChunks;
 }
 
 int score_mma_launch(const float* labels, int64_t L, const float* images, int64_t N, int D, float K, const int32_t* level_start,
                      const int32_t* level_stop, int n_levels, int k, float* scores, int32_t* topk_idx, float* topk_val,
                      void* workspace, int64_t workspace_bytes, cudaStream_t st) {
     if (N == 0 || L == 0) return 0;
+    const int forms = mma_forms(D);
     MmaChunkTable tab;
-    if (int e = build_chunks(L, level_start, level_stop, topk_idx ? n_levels : 0, scores != nullptr, tab)) return e;
+    if (int e = build_chunks(L, level_start, level_stop, topk_idx ? n_levels : 0, scores != nullptr, mma_labels(forms), tab)) return e;
     if (tab.n == 0) return 0;
-    const int Kp = mma_kp(D);
-    const int blob = mma_blob_bytes(Kp);
+    const int Kp = mma_kp(D, forms);
+    const int blob = mma_blob_bytes(Kp, forms);
     if ((int64_t)tab.n * blob > workspace_bytes) return LEC_E_SIZE;
     if (reinterpret_cast<uintptr_t>(workspace) & 127) return LEC_E_ALIGN;
     unsigned char* ws = static_cast<unsigned char*>(workspace);
-    score_mma_prep_kernel<<<tab.n, kMmaN, 0, st>>>(labels, D, Kp, K, tab, ws);
+    score_mma_prep_kernel<<<tab.n, kMmaN, 0, st>>>(labels, D, Kp, forms, K, tab, ws);
     ++g_launches;
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) return (int)ce;
@@ -637,9 +698,14 @@ int score_mma_launch(const float* labels, int64_t L, const float* images, int64_
         ++g_launches;
         return (int)cudaGetLastError();
     };
-    if (mode == 0) return launch(score_mma_kernel<0>);
-    if (mode == 1) return launch(score_mma_kernel<1>);
-    return launch(score_mma_kernel<2>);
+    if (forms == 3) {
+        if (mode == 0) return launch(score_mma_kernel<0, 3>);
+        if (mode == 1) return launch(score_mma_kernel<1, 3>);
+        return launch(score_mma_kernel<2, 3>);
+    }
+    if (mode == 0) return launch(score_mma_kernel<0, 1>);
+    if (mode == 1) return launch(score_mma_kernel<1, 1>);
+    return launch(score_mma_kernel<2, 1>);
 }
 
 }  // namespace lec

@@ -358,3 +358,33 @@ def best_f1_sweep(E_pos, E_neg):
     acc = (cp + cn) / (n_pos + n_neg)
     return (float(f1[best]), float(ts[best]), float(acc[best]), float(prec[best]), float(rec[best]),
             float(cp[best]), float(cn[best]))
+
+
+# ----------------------------------------------------------------------------------------------
+# Classification bookkeeping (JointEmbeddings.calculate_classification_metrics)
+# ----------------------------------------------------------------------------------------------
+def classification_counts(top_idx, truth, n_labels, level_start, level_stop, k_vals=(1, 3, 5)):
+    """oe.py:1775-1796 / oe_h.py:2030-2051, literally: per image and level, hit@k at the true label, tp / tn on a
+    correct top-1 (tn for every OTHER label of the level), else fp at the prediction and fn at the true label.
+    Pinned through tests/golden/classify_hyp_*.npz (the reference's own metric dict)."""
+    import numpy as np
+    top_idx = np.asarray(top_idx)
+    truth = np.asarray(truth)
+    hit = np.zeros((len(k_vals), n_labels), dtype=np.int64)
+    tp, fp, tn, fn = (np.zeros(n_labels, dtype=np.int64) for _ in range(4))
+    for i in range(top_idx.shape[0]):
+        for lvl in range(top_idx.shape[1]):
+            want = int(truth[i, lvl])
+            indices = top_idx[i, lvl]
+            for j, kv in enumerate(k_vals):
+                if want in indices[:kv]:
+                    hit[j, want] += 1
+            if want == int(indices[0]):
+                tp[want] += 1
+                for other in range(int(level_start[lvl]), int(level_stop[lvl])):
+                    if other != want:
+                        tn[other] += 1
+            else:
+                fp[int(indices[0])] += 1
+                fn[want] += 1
+    return hit, tp, fp, tn, fn

@@ -476,10 +476,62 @@ def gen_mt():
     save("mt_choice_streams", **out)
 
 
+# ---------------------------------------------------------------------------------------
+# J. Classification metrics of the joint trainers: the UNMODIFIED JointEmbeddings.calculate_classification_metrics
+#    (oe.py:1721-1921, oe_h.py:1971-2178) called unbound on a stand-in `self` that carries only what the method
+#    reads: graph_dict, labelmap, embedding_dim, use_CNN, device, model, img_feat_net, criterion.
+# ---------------------------------------------------------------------------------------
+def gen_classify():
+    # hyperbolic only: random Euclidean cones give many exact E = 0 ties (torch.topk's tie order is unspecified) and
+    # levels without a single hit, where the reference itself divides by zero (oe.py:1809)
+    for tag, mod, crit, D in (("hyp", ref_oeh, ref_oeh.EuclideanConesWithImagesHypernymLoss(lm, 5, {}, 1.0, K=0.1), 10),
+                              ("hyp", ref_oeh, ref_oeh.EuclideanConesWithImagesHypernymLoss(lm, 5, {}, 1.0, K=0.1), 50)):
+        g = torch.Generator().manual_seed(77)
+        n_img = 57
+        if tag == "hyp":
+            lab = torch.zeros(n, D)
+            for l in range(4):
+                s, e = lm.level_start[l], lm.level_stop[l]
+                lab[s:e] = ball_points(g, e - s, D, 0.10 + 0.2 * l, 0.30 + 0.2 * l)
+        else:
+            lab = ref_e.Embedder(D, lm, K=3.0).soft_clip(torch.randn(n, D, generator=g)).detach()
+        leaves = torch.randint(lm.level_start[3], lm.level_stop[3], (n_img,), generator=g)
+        truth = np.zeros((n_img, 4), dtype=np.int64)
+        img = torch.zeros(n_img, D)
+        for i in range(n_img):
+            node = int(leaves[i])
+            chain = [node]
+            while parents[chain[-1]] >= 0:
+                chain.append(int(parents[chain[-1]]))
+            truth[i] = sorted(chain)
+            # an image sits a little further out than its leaf label, with noise: some predictions hit, some miss
+            v = lab[node] * (1.25 if tag == "hyp" else 1.6) + (0.05 if tag == "hyp" else 0.01) * torch.randn(D, generator=g) * lab[node].norm()
+            if tag == "hyp" and v.norm() >= 0.97:
+                v = v / v.norm() * 0.97
+            img[i] = v
+        names = ["img_%03d.jpg" % i for i in range(n_img)]
+        Gv = nx.DiGraph()
+        Gv.add_nodes_from(range(n))
+        for i, name in enumerate(names):
+            for lbl in truth[i]:
+                Gv.add_edge(int(lbl), name)
+        crit.feature_dict = {name: img[i].tolist() for i, name in enumerate(names)}
+        stub = types.SimpleNamespace(graph_dict={"G_val": Gv}, labelmap=lm, embedding_dim=D, use_CNN=False,
+                                     device=torch.device("cpu"), criterion=crit, model=lambda ix: lab[ix],
+                                     img_feat_net=lambda x: x.squeeze(0))
+        m = mod.JointEmbeddings.calculate_classification_metrics(stub, "val")
+        out = {k: np.float64(v) for k, v in m.items() if k != "level_metrics"}
+        for lvl, d in m["level_metrics"].items():
+            for k, v in d.items():
+                out["level%d_%s" % (lvl, k)] = np.float64(v)
+        save("classify_%s_D%d" % (tag, D), labels=lab, images=img, truth=truth, level_start=np.array(lm.level_start),
+             level_stop=np.array(lm.level_stop), K=crit.K, **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["pairs", "transforms", "rsgd", "steps", "joint", "scoring", "metrics", "mt"]
+    which = sys.argv[1:] or ["pairs", "transforms", "rsgd", "steps", "joint", "scoring", "metrics", "mt", "classify"]
     fns = dict(pairs=gen_pairs, transforms=gen_transforms, rsgd=gen_rsgd, steps=gen_steps, joint=gen_joint,
-               scoring=gen_scoring, metrics=gen_metrics, mt=gen_mt)
+               scoring=gen_scoring, metrics=gen_metrics, mt=gen_mt, classify=gen_classify)
     for w in which:
         print("==", w)
         fns[w]()

@@ -252,3 +252,27 @@ def test_frozen_facts(ethec):
     assert ethec["levels"].tolist() == [6, 21, 135, 561] and ethec["level_start"].tolist() == [0, 6, 27, 162]
     assert abs(cones.inner_radius(0.1) - 0.09901951359278482) < 1e-15
     assert float(load_golden("step_hyp_D10_a0p05")["loss"]) == pytest.approx(2712.4351, abs=1e-3)
+
+
+@pytest.mark.parametrize("name", ["classify_hyp_D10", "classify_hyp_D50"])
+def test_classification_counts_reproduce_reference_metric_dict(name):
+    """oracle scoring + bookkeeping against the dict the unmodified calculate_classification_metrics returned."""
+    g = load_golden(name)
+    lab, img = t(g["labels"]).clone(), t(g["images"]).clone()
+    lab[-1] = 0.0   # the reference's slicing leaves the last label / image row zero (SURVEY F9)
+    img[-1] = 0.0
+    ls, le = g["level_start"].tolist(), g["level_stop"].tolist()
+    E = cones.score_matrix("hyp", lab, img, float(g["K"]))
+    idx, _ = cones.topk_per_level(E, ls, le, 5)
+    hit, tp, fp, tn, fn = cones.classification_counts(idx.numpy(), g["truth"], lab.shape[0], ls, le, (1, 3, 5))
+    n_img = img.shape[0]
+    for j, kv in enumerate((1, 3, 5)):
+        assert int(hit[j].sum()) / (4 * n_img) == float(g["hit@%d" % kv])
+        for lvl, (s, e) in enumerate(zip(ls, le)):
+            assert int(hit[j][s:e].sum()) / n_img == float(g["level%d_hit@%d" % (lvl, kv)])
+    TP, FP, TN, FN = int(tp.sum()), int(fp.sum()), int(tn.sum()), int(fn.sum())
+    assert (TP + TN) / (TP + TN + FP + FN) == float(g["accuracy"])
+    assert TP / (TP + FP) == float(g["m-precision"]) and TP / (TP + FN) == float(g["m-recall"])
+    for lvl, (s, e) in enumerate(zip(ls, le)):
+        a = (int(tp[s:e].sum()) + int(tn[s:e].sum())) / int((tp + tn + fp + fn)[s:e].sum())
+        assert a == float(g["level%d_accuracy" % lvl])

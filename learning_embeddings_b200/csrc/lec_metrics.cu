@@ -33,15 +33,29 @@ __device__ __forceinline__ bool f1_better(double fa, int64_t ia, double fb, int6
     return fa > fb || (fa == fb && ia < ib);
 }
 
-// metrics of threshold sorted[i] (a run end): the reference's expression tree in fp64
+// number of non-NaN energies: the sort puts NaNs last, so "is NaN" is monotone over the array
+__device__ __forceinline__ int64_t first_nan(const float* sorted, int64_t n) {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        const float v = sorted[mid];
+        if (v != v) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+// metrics of threshold sorted[i] (a run end): the reference's expression tree in fp64.  NaN energies (the zero label
+// row of the reference's off-by-one) satisfy neither E <= t nor E > t: they count in n_pos / n_neg only.
 __device__ __forceinline__ void f1_row(const float* sorted, const int64_t* pos_prefix, int64_t i, int64_t n_pos, int64_t n_neg,
-                                       double* row) {
+                                       int64_t n_fin, double* row) {
     const float t = sorted[i];
     int64_t cp, cn;
     if (t != t) { cp = 0; cn = 0; }   // NaN threshold: no comparison holds
     else {
-        cp = pos_prefix[i];                    // positives with E <= t
-        cn = n_neg - ((i + 1) - cp);           // negatives with E > t
+        cp = pos_prefix[i];                                              // positives with E <= t
+        const int64_t pos_fin = n_fin > 0 ? pos_prefix[n_fin - 1] : 0;   // positives that are not NaN
+        const int64_t neg_fin = n_fin - pos_fin;
+        cn = neg_fin - ((i + 1) - cp);                                   // negatives with E > t
     }
     const double acc = (double)(cp + cn) / (double)(n_pos + n_neg);
     const double prec = (double)cp / (double)(cp + (n_neg - cn));   // 0/0 -> NaN (the reference raises ZeroDivisionError)
@@ -53,6 +67,7 @@ __device__ __forceinline__ void f1_row(const float* sorted, const int64_t* pos_p
 __global__ void __launch_bounds__(kF1Threads) f1_sweep_kernel(const float* __restrict__ sorted, const int64_t* __restrict__ pos_prefix,
                                                                int64_t n, int64_t n_pos, int64_t n_neg, F1Best* __restrict__ block_best) {
     F1Best best{-1.0, INT64_MAX};
+    const int64_t n_fin = first_nan(sorted, n);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const float t = sorted[i];
         // run end: the last occurrence of a value (all NaNs form one run at the end, like np.unique)
@@ -63,7 +78,7 @@ __global__ void __launch_bounds__(kF1Threads) f1_sweep_kernel(const float* __res
         }
         if (!end) continue;
         double row[7];
-        f1_row(sorted, pos_prefix, i, n_pos, n_neg, row);
+        f1_row(sorted, pos_prefix, i, n_pos, n_neg, n_fin, row);
         double f1 = row[0];
         if (f1 != f1) f1 = -1.0;   // NaN never wins
         if (f1_better(f1, i, best.f1, best.idx)) { best.f1 = f1; best.idx = i; }
@@ -101,7 +116,7 @@ __global__ void __launch_bounds__(kF1Threads) f1_final_kernel(const float* __res
     }
     if (threadIdx.x == 0) {
         if (sh[0].idx == INT64_MAX) { for (int j = 0; j < 7; ++j) out7[j] = nan(""); }
-        else f1_row(sorted, pos_prefix, sh[0].idx, n_pos, n_neg, out7);
+        else f1_row(sorted, pos_prefix, sh[0].idx, n_pos, n_neg, first_nan(sorted, n), out7);
     }
 }
 

@@ -217,6 +217,27 @@ __device__ __forceinline__ void tmem_ld16(unsigned taddr, float (&v)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// three 16-column loads of this thread's lane in flight together, one wait
+__device__ __forceinline__ void tmem_ld16x3(unsigned t0, unsigned t1, unsigned t2, float (&a)[16], float (&b)[16], float (&c)[16]) {
+    unsigned r[48];
+#define LEC_LD16(OFF, ADDR)                                                                                                   \
+    asm volatile(                                                                                                             \
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];" \
+        : "=r"(r[OFF + 0]), "=r"(r[OFF + 1]), "=r"(r[OFF + 2]), "=r"(r[OFF + 3]), "=r"(r[OFF + 4]), "=r"(r[OFF + 5]),          \
+          "=r"(r[OFF + 6]), "=r"(r[OFF + 7]), "=r"(r[OFF + 8]), "=r"(r[OFF + 9]), "=r"(r[OFF + 10]), "=r"(r[OFF + 11]),       \
+          "=r"(r[OFF + 12]), "=r"(r[OFF + 13]), "=r"(r[OFF + 14]), "=r"(r[OFF + 15])                                          \
+        : "r"(ADDR) : "memory")
+    LEC_LD16(0, t0);
+    LEC_LD16(16, t1);
+    LEC_LD16(32, t2);
+#undef LEC_LD16
+    // the wait names every destination register as read-write, so no use of a loaded value can be scheduled above it
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 48; ++i) asm volatile("" : "+r"(r[i]));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { a[i] = __uint_as_float(r[i]); b[i] = __uint_as_float(r[16 + i]); c[i] = __uint_as_float(r[32 + i]); }
+}
 // shared-memory matrix descriptor: Major-K, SWIZZLE_NONE, version 1 (cute/arch/mma_sm100_desc.hpp SmemDescriptor)
 __device__ __forceinline__ uint64_t umma_desc(unsigned saddr, unsigned lbo_bytes, unsigned sbo_bytes) {
     return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16) |
@@ -352,11 +373,13 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(const MmaArgs
         // loader: blob c goes into stage c % NS as soon as the epilogue of chunk c - NS has released it
         if ((tid & 31) == 0) {
             const unsigned sB_u = smem_u32(sB);
+            int s = 0;
+            unsigned par = 0;
             for (int c = NS; c < a.n_chunks; ++c) {
-                const int s = c % NS;
-                mbar_wait(bar_empty0 + 8 * s, (unsigned)(((c - NS) / NS) & 1));
+                mbar_wait(bar_empty0 + 8 * s, par);
                 mbar_expect_tx(bar_full0 + 8 * s, (unsigned)blob);
                 bulk_g2s(sB_u + s * blob, a.ws + (size_t)c * blob, (unsigned)blob, bar_full0 + 8 * s);
+                if (++s == NS) { s = 0; par ^= 1u; }
             }
         }
         __syncwarp();
@@ -366,10 +389,11 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(const MmaArgs
         const unsigned sB_u = smem_u32(sB);
         const unsigned idesc = umma_idesc_tf32(kMmaM, kMmaN);
         const bool issuer = (tid & 31) == 0;
+        int s = 0, t = 0;
+        unsigned par = 0, par_t = 1;   // accfree[t] is first waited on for chunk NA, i.e. after one wrap of t
         for (int c = 0; c < a.n_chunks; ++c) {
-            const int s = c % NS, t = c % NA;
-            mbar_wait(bar_full0 + 8 * s, (unsigned)((c / NS) & 1));
-            if (c >= NA) mbar_wait(bar_accfree0 + 8 * t, (unsigned)(((c - NA) / NA) & 1));
+            mbar_wait(bar_full0 + 8 * s, par);
+            if (c >= NA) mbar_wait(bar_accfree0 + 8 * t, par_t);
             tc_fence_after();
             const unsigned d = tmem_base + (unsigned)(t * kMmaN);
             const unsigned bh = sB_u + s * blob, bl = bh + b_tile;
@@ -385,6 +409,8 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(const MmaArgs
             }
             if (issuer) tc_commit(bar_done0 + 8 * t);
             __syncwarp();
+            if (++s == NS) { s = 0; par ^= 1u; }
+            if (++t == NA) { t = 0; par_t ^= 1u; }
         }
         __syncwarp();
     } else {
@@ -441,9 +467,10 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(const MmaArgs
         };
 
         const int lane_base = (warp & 3) * 32;
+        // stage indices and phase parities advance by increments (no integer division in the chunk loop)
+        int s = 0, t = 0;
+        unsigned par = 0, par_t = 0;
         for (int c = 0; c < a.n_chunks; ++c) {
-            const int s = c % NS;
-            const unsigned par = (unsigned)((c / NS) & 1);
             mbar_wait(bar_full0 + 8 * s, par);   // constants + header of chunk c visible to this thread
             const unsigned char* bl = sB + (size_t)s * blob;
             const float* cst = reinterpret_cast<const float*>(bl + 2 * b_tile);
@@ -458,8 +485,7 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(const MmaArgs
                 psi_max = hdr.psi_max;
                 refresh();
             }
-            const int t = c % NA;
-            mbar_wait(bar_done0 + 8 * t, (unsigned)((c / NA) & 1));   // accumulator of chunk c complete
+            mbar_wait(bar_done0 + 8 * t, par_t);   // accumulator of chunk c complete
             tc_fence_after();
 
             const int lbase = half * LT;                     // this thread's first label of the chunk
@@ -469,9 +495,8 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(const MmaArgs
             float v[3][16];
             {
                 const unsigned tcol = tmem_base + ((unsigned)lane_base << 16) + (unsigned)(t * kMmaN);
-#pragma unroll
-                for (int i = 0; i < 3; ++i)
-                    tmem_ld16(tcol + (unsigned)(FORMS == 3 ? i * NL + lbase : lbase + 16 * i), v[i]);
+                tmem_ld16x3(tcol + (unsigned)lbase, tcol + (unsigned)(FORMS == 3 ? NL + lbase : lbase + 16),
+                            tcol + (unsigned)(FORMS == 3 ? 2 * NL + lbase : lbase + 32), v[0], v[1], v[2]);
             }
             tc_fence_before();
             mbar_arrive(bar_accfree0 + 8 * t);
@@ -596,6 +621,8 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(const MmaArgs
             }
             // this thread is done with the constants of blob stage s (its MMAs completed before done[t] fired)
             mbar_arrive(bar_empty0 + 8 * s);
+            if (++s == NS) { s = 0; par ^= 1u; }
+            if (++t == NA) { t = 0; par_t ^= 1u; }
         }
     }
 
@@ -681,13 +708,18 @@ int score_mma_launch(const float* labels, int64_t L, const float* images, int64_
     a.topk_idx = topk_idx; a.topk_val = topk_val; a.k = topk_idx ? k : 1; a.n_levels = n_levels;
     a.ring = topk_idx ? 16 : 0;   // matrix-only launches need no candidate ring
     const size_t fixed = (size_t)a.k * kEpiThreads * 8 + (size_t)a.ring * kEpiThreads * 12 + 256;
-    // two blob stages and <= 256 TMEM columns keep two CTAs (20 warps) on an SM for short rows; wide rows fall back to
-    // one CTA per SM and, if shared memory is short, to a single blob stage
+    // Blob stages: the loader can only refill a stage after the epilogue of its chunk, and a bulk copy from L2 takes
+    // longer than one chunk's epilogue (32 labels x 128 images), so short rows get up to four stages in flight (r1e
+    // profile: with two, the epilogue warps spent ~9 wait iterations per chunk on full[]).  Within 256 TMEM columns the
+    // budget is half an SM's shared memory so that two CTAs (20 warps) stay resident; otherwise the whole SM.
     if (!mma_plan(Kp, a.acc_stages, a.tmem_cols)) return LEC_E_DIM;
-    a.stages = 2;
-    size_t smem = fixed + (size_t)a.stages * blob;
-    if (smem > 227 * 1024) { a.stages = 1; smem = fixed + (size_t)blob; }
-    if (smem > 227 * 1024) return LEC_E_DIM;
+    const size_t half_sm = 113 * 1024, whole_sm = 226 * 1024;
+    auto stages_for = [&](size_t budget) { return budget > fixed ? (int)((budget - fixed) / (size_t)blob) : 0; };
+    int stages = a.tmem_cols <= 256 ? stages_for(half_sm) : 0;
+    if (stages < 2) stages = stages_for(whole_sm);
+    if (stages < 1) return LEC_E_DIM;
+    a.stages = stages > kMmaMaxStages ? kMmaMaxStages : stages;
+    const size_t smem = fixed + (size_t)a.stages * blob;
     const int mode = topk_idx ? (scores ? 2 : 0) : 1;
     const int64_t grid = (N + kMmaM - 1) / kMmaM;
     if (grid > 0x7fffffffLL) return LEC_E_SIZE;

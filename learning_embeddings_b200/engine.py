@@ -230,6 +230,20 @@ class ConeStep:
         self.reduce_and_update()
         return self.loss
 
+    def step_sampled(self, graph, pos_from, pos_to, seed, step):
+        """Device-resident training step: negatives are drawn on the GPU (sampler.SamplerGraph.draw_philox: the
+        reference's candidate sets and uniform law, Philox stream keyed by (seed, step)) and consumed by the step in the
+        same stream -- only the positive edges ever come from the host.  The fast mode: not the `random.choice` stream."""
+        B = int(pos_from.numel())
+        key = (pos_from.dtype, B)
+        if getattr(self, "_neg_key", None) != key:
+            dev = self.table.device
+            self._neg_bufs = (torch.empty((B, self.n_neg), dtype=pos_from.dtype, device=dev),
+                              torch.empty((B, self.n_neg), dtype=pos_from.dtype, device=dev))
+            self._neg_key = key
+        neg_to, neg_from = graph.draw_philox(pos_from, pos_to, self.n_neg, seed, step, out=self._neg_bufs, check=False)
+        return self.step_device(pos_from, pos_to, neg_to.view(-1), neg_from.view(-1))
+
     def _slot_view(self, slot, n, dtype):
         return self._idx_bytes_dev[slot][:n * dtype.itemsize].view(dtype)
 

@@ -346,10 +346,13 @@ def best_f1_sweep(E_pos, E_neg):
     E_pos = E_pos.reshape(-1)
     E_neg = E_neg.reshape(-1)
     ts = torch.unique(torch.cat([E_pos, E_neg]))  # ascending, like np.unique
-    sp, _ = torch.sort(E_pos)
-    sn, _ = torch.sort(E_neg)
+    # NaN energies (the reference's zero label row) satisfy neither E <= t nor E > t: they are counted in
+    # the sizes but never in cp / cn, and a NaN threshold scores F1 = 0, so only finite thresholds can win
+    ts = ts[~torch.isnan(ts)]
+    sp, _ = torch.sort(E_pos[~torch.isnan(E_pos)])
+    sn, _ = torch.sort(E_neg[~torch.isnan(E_neg)])
     cp = torch.searchsorted(sp, ts, right=True).double()
-    cn = (E_neg.numel() - torch.searchsorted(sn, ts, right=True)).double()
+    cn = (sn.numel() - torch.searchsorted(sn, ts, right=True)).double()
     n_pos, n_neg = float(E_pos.numel()), float(E_neg.numel())
     prec = cp / (cp + (n_neg - cn))
     rec = cp / n_pos

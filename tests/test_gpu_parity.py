@@ -649,7 +649,7 @@ def test_pipelined_host_steps_equal_synchronous_steps(idx_np):
     assert len(pipe_losses) == len(blocks) and eb.drain() == []
     # fp32 vector reductions into the gradient replicas are not order-deterministic: tolerance, not equality
     np.testing.assert_allclose(pipe_losses, sync_losses, rtol=1e-6)
-    np.testing.assert_allclose(tb.cpu().numpy(), ta.cpu().numpy(), rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(tb.cpu().numpy(), ta.cpu().numpy(), rtol=1e-4, atol=2e-5)
     # the int64 reference layout gives the same first-step energies as the narrow block
     tc = W0.to(DEV).clone()
     ec = ConeStep(tc, "hyp", Nn, B, K=0.1, alpha=0.05, lr=0.01)

@@ -84,3 +84,28 @@ def test_philox_reports_empty_candidate_list():
     dev = torch.device("cuda:0")
     with pytest.raises(IndexError):
         graph.draw_philox(torch.tensor([0], device=dev), torch.tensor([1], device=dev), 1, seed=0, step=0)
+
+
+def test_engine_step_with_device_sampler_equals_step_on_the_same_negatives():
+    """ConeStep.step_sampled = draw_philox + step_device: same loss and table as feeding those negatives explicitly."""
+    from learning_embeddings_b200.engine import ConeStep
+    from learning_embeddings_b200.criterion import inner_radius
+    h = H.ethec()
+    graph = S.SamplerGraph.from_hierarchy(h)
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(h.n, 10, generator=g)
+    table0 = (inner_radius(0.1) + 0.05 * torch.rand(h.n, 1, generator=g)) * w / w.norm(dim=1, keepdim=True)
+    e = h.closure_edges()
+    u = torch.from_numpy(e[:, 0].astype(np.int32)).to(dev)
+    v = torch.from_numpy(e[:, 1].astype(np.int32)).to(dev)
+    a = ConeStep(table0.to(dev).clone(), "hyp", 5, len(e), K=0.1, alpha=0.05, lr=1e-3)
+    b = ConeStep(table0.to(dev).clone(), "hyp", 5, len(e), K=0.1, alpha=0.05, lr=1e-3)
+    for step in range(3):
+        la = float(a.step_sampled(graph, u, v, seed=42, step=step).item())
+        nt, nf = graph.draw_philox(u, v, 5, seed=42, step=step)
+        lb = float(b.step_device(u, v, nt.view(-1), nf.view(-1)).item())
+        assert abs(la - lb) <= 1e-6 * abs(lb)   # the fp32 gradient reductions are not order-deterministic
+    assert torch.allclose(a.table, b.table, rtol=0, atol=1e-5)
+    status = graph.device_struct(dev)[2]
+    assert int(status.item()) == 0

@@ -548,9 +548,11 @@ def run_cfg3(args):
     lib = _native.lib()
     ls = (ctypes.c_int32 * nl)(*h.level_start)
     le = (ctypes.c_int32 * nl)(*h.level_stop)
-    use_tc = args.engine != "simt" and bool(lib.lec_score_tc_supported(ops.GEOM["hyp"], 0, D, L, nl))
-    if args.engine == "tc" and not use_tc:
+    tc_ok = bool(lib.lec_score_tc_supported(ops.GEOM["hyp"], 0, D, L, nl))
+    if args.engine == "tc" and not tc_ok:
         raise SystemExit("tensor-core scoring does not support this case")
+    # "auto" = what ops.score_topk picks: the tensor-core kernel for matrix-only steps, the SIMT kernel when top-k is wanted
+    use_tc = tc_ok and (args.engine == "tc" or (args.engine == "auto" and not want_topk))
     cfg["engine"] = "tc (tcgen05 kind::tf32 3xTF32 + fused epilogue)" if use_tc else "simt (packed FFMA2 tile kernel)"
     ws, nb = None, 0
     if use_tc:
@@ -614,7 +616,7 @@ def run_cfg3(args):
     if not args.no_e2e:
         out_idx = torch.empty((n_img, nl, k), dtype=torch.int32).pin_memory()
         pipe = ops.ScorePipeline(labels_d, "hyp", K, h.level_start, h.level_stop, k=k, slice_images=131072,
-                                 engine=("tc" if use_tc else "simt"))
+                                 engine=("tc" if args.engine == "tc" else "auto"))
         for i in range(2):
             pipe.run(host_sets[i % rotation], out_idx)
         sync_all()

@@ -66,10 +66,10 @@ __device__ __forceinline__ float min_nan(float a, float b) {
 __device__ __forceinline__ u64 acos_clamped2(u64 g2) {
     float g0, g1;
     unpack2(g2, g0, g1);
-    const float lo = -1.f + kClampEps, hi = 1.f - kClampEps;
-    g0 = min_nan(max_nan(g0, lo), hi);
-    g1 = min_nan(max_nan(g1, lo), hi);
-    const float a0 = fabsf(g0), a1 = fabsf(g1);
+    // clamp(g, -1+eps, 1-eps) only matters through |g| (the sign is taken from g's sign bit below), so one
+    // NaN-propagating min on |g| replaces the max/min pair
+    const float hi = 1.f - kClampEps;
+    const float a0 = min_nan(fabsf(g0), hi), a1 = min_nan(fabsf(g1), hi);
     const u64 ax = pack2(a0, a1);
     const u64 t = ffma2(ax, pack2(-1.f, -1.f), pack2(1.f, 1.f));  // 1 - |g| (exact for |g| >= 0.5)
     float t0, t1;

@@ -450,17 +450,42 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(const MmaArgs
             }
         };
         auto merge = [&]() {
+            // The sorted list lives in shared memory (the peer thread reads its k-th entry), but a merge works on a
+            // register copy: one compare-select sweep per ring entry instead of a load-compare-store chain per shifted
+            // slot (r1e profile: those chains were ~45 % of the top-k kernels' samples).  Ties keep the lower label.
             const int cnt = (int)((rp - ring0) / (kEpiThreads * 8));
-            for (int j = 0; j < cnt; ++j) {
-                const float2 e = ring[j * kEpiThreads + et];
-                float Ev = e.x;
-                if (MODE == 0) {  // deferred: the ring holds g; same instruction sequence as the matrix path
-                    const float np = ringp[j * kEpiThreads + et];
-                    float z0, z1;
-                    unpack2(fadd2(acos_clamped2(pack2(e.x, e.x)), pack2(np, np)), z0, z1);
-                    Ev = max_nan(z0, 0.f);
+            if (cnt > 0) {
+                float tv[LEC_MAX_TOPK];
+                int tl[LEC_MAX_TOPK];
+#pragma unroll
+                for (int j = 0; j < LEC_MAX_TOPK; ++j) {
+                    tv[j] = INFINITY; tl[j] = -1;
+                    if (j < k) { const float2 e = mytop[(size_t)j * kEpiThreads]; tv[j] = e.x; tl[j] = __float_as_int(e.y); }
                 }
-                insert(Ev, e.y);
+                for (int j = 0; j < cnt; ++j) {
+                    const float2 e = ring[j * kEpiThreads + et];
+                    float Ev = e.x;
+                    if (MODE == 0) {  // deferred: the ring holds g; same instruction sequence as the matrix path
+                        const float np = ringp[j * kEpiThreads + et];
+                        float z0, z1;
+                        unpack2(fadd2(acos_clamped2(pack2(e.x, e.x)), pack2(np, np)), z0, z1);
+                        Ev = max_nan(z0, 0.f);
+                    }
+                    const int lab = __float_as_int(e.y);
+                    bool before[LEC_MAX_TOPK];   // the entry sorts before slot j
+#pragma unroll
+                    for (int q = 0; q < LEC_MAX_TOPK; ++q) before[q] = (q < k) && (Ev < tv[q] || (Ev == tv[q] && lab < tl[q]));
+#pragma unroll
+                    for (int q = LEC_MAX_TOPK - 1; q > 0; --q) {
+                        tv[q] = before[q - 1] ? tv[q - 1] : (before[q] ? Ev : tv[q]);
+                        tl[q] = before[q - 1] ? tl[q - 1] : (before[q] ? lab : tl[q]);
+                    }
+                    tv[0] = before[0] ? Ev : tv[0];
+                    tl[0] = before[0] ? lab : tl[0];
+                }
+#pragma unroll
+                for (int j = 0; j < LEC_MAX_TOPK; ++j)
+                    if (j < k) mytop[(size_t)j * kEpiThreads] = make_float2(tv[j], __int_as_float(tl[j]));
             }
             rp = ring0;
             refresh();

@@ -319,12 +319,16 @@ def score_topk_into(labels, images, geom, K, level_start, level_stop, k, idx, va
     le = (ctypes.c_int32 * max(nl, 1))(*[int(v) for v in level_stop])
     dev = labels.device
     # engine: "tc" = tcgen05 tensor-core contraction + fused epilogue (lec_score_topk_tc), "simt" = the packed-FMA
-    # tile kernel (lec_score_topk_ex); "auto" takes the tensor-core path whenever the library supports the case
+    # tile kernel (lec_score_topk_ex).  "auto" follows the measurements (profiles/r1e_score_bench.log, 1 M x 723):
+    # matrix-only calls go to the tensor-core kernel (0.88 vs 1.02 ms at D=10, 1.12 vs 2.69 ms at D=50); calls that
+    # want top-k stay on the SIMT kernel, whose per-thread lists cover four images of a whole level (1.63 vs 2.86 ms).
     lib = N.lib()
     tc_ok = scores_layout == 1 and bool(lib.lec_score_tc_supported(GEOM[geom], int(precision), D, L, nl))
     if engine == "tc" and not tc_ok:
         raise N.LecError("tensor-core scoring supports hyperbolic cones, fp32 core, label-major scores, D <= 128")
-    if tc_ok and engine in ("auto", "tc"):
+    if engine == "auto":
+        engine = "tc" if (tc_ok and idx is None and val is None) else "simt"
+    if engine == "tc":
         nbytes = int(lib.lec_score_workspace_bytes(L, D, nl))
         ws = _score_workspace(dev, nbytes)
         N.check(lib.lec_score_topk_tc(GEOM[geom], int(precision), N._p(labels), L, N._p(images), n_img, D,

@@ -33,6 +33,7 @@
 // (128 B); element (row r, k) of a tile with R rows lives at byte (k/4)*(16 R) + 16 r + 4 (k%4), i.e.
 // LBO = 16 R (next 16-byte K group), SBO = 128 (next 8 rows).  One MMA consumes K = 8 tf32 = two K groups.
 #include <cstdio>
+#include <cstdlib>
 #include <type_traits>
 
 #include "lec_common.cuh"
@@ -47,7 +48,8 @@ constexpr int kMmaN = 96;        // B rows per chunk = TMEM columns per accumula
 // forms triple the tensor work (3 forms x 3 TF32 passes x Kp MACs per score), which the tensor pipe hides behind the
 // epilogue only while Kp <= 32; wider rows keep one form.
 constexpr int kMmaMaxChunks = 224;
-constexpr int kMmaRingCheck = 8; // ring room needed between two merge checks (4 label pairs)
+constexpr int kMmaRing = 24;      // candidate ring entries per epilogue thread (top-k launches)
+constexpr int kMmaRingRoom = 16;  // room a thread needs between two merge checks: one group of 16 labels
 
 struct MmaChunk { int label0; short count; signed char level; unsigned char flags; };  // flags: 1 first, 2 last chunk of its level
 struct MmaChunkTable { int n; MmaChunk c[kMmaMaxChunks]; };
@@ -71,7 +73,8 @@ __device__ __forceinline__ float to_tf32(float v) {
 // prep: labels -> chunk blobs
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kMmaN) score_mma_prep_kernel(const float* __restrict__ labels, int D, int Kp, int forms, float K,
-                                                                const MmaChunkTable tab, unsigned char* __restrict__ ws) {
+                                                                const MmaChunkTable tab, unsigned char* __restrict__ ws,
+                                                                float* __restrict__ npsi) {
     const int c = blockIdx.x, j = threadIdx.x;   // thread j writes B row j: form j / NL of label j % NL
     const int NL = mma_labels(forms);
     const int form = j / NL, jl = j % NL;
@@ -119,6 +122,7 @@ __global__ void __launch_bounds__(kMmaN) score_mma_prep_kernel(const float* __re
     if (form == 0) {
         const double sp = sin(x.t0), cp = sqrt(fmax(0.0, 1.0 - sp * sp));
         float* q = cst + (jl >> 1) * 12 + (jl & 1);
+        if (live) npsi[ch.label0 + jl] = (float)(-x.t0);   // per-label copy for the top-k merge (candidates outlive their blob)
         if (forms == 3) {   // {-psi, -psi', cos psi, cos psi'} {sin psi, sin psi', 0, 0} {0, 0, 0, 0}
             q[0] = (float)(-x.t0); q[2] = (float)cp; q[4] = (float)sp; q[6] = 0.f; q[8] = 0.f; q[10] = 0.f;
         } else {            // {A, A', 1+A, 1+A'} {A^2, A'^2, -psi, -psi'} {cos psi, cos psi', sin psi, sin psi'}
@@ -153,7 +157,7 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 // Spins on the phase; a lost arrival traps instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity, int sleep_ns = 32) {
     unsigned ok = 0;
     for (unsigned spin = 0; !ok; ++spin) {
         asm volatile(
@@ -162,7 +166,7 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
         if (!ok) {
-            if (spin > 4) __nanosleep(32);   // a waiting warp must not eat the issue slots of the working ones
+            if (spin > 4 && sleep_ns > 0) __nanosleep((unsigned)sleep_ns);   // a waiting warp must not eat the issue slots of the working ones
             if (spin > (1u << 22)) __trap();
         }
     }
@@ -253,10 +257,13 @@ struct MmaArgs {
     const unsigned char* ws; int n_chunks;
     float* scores;           // label-major [L, N] or NULL
     int32_t* topk_idx; float* topk_val; int k, n_levels;
+    const float* npsi;       // [L] -psi(label), written by the prep launch (top-k merge of deferred candidates)
     int ring;                // candidate ring entries per thread
     int stages;              // blob stages in shared memory (1..4)
     int acc_stages;          // accumulator buffers in TMEM (1 or 2)
     int tmem_cols;           // power of two >= acc_stages * 96 + 2 Kp
+    int sleep_ns;            // back-off of a warp that keeps finding its mbarrier phase incomplete
+    int alt;                 // matrix-only launches: the two epilogue warp groups alternate chunks
 };
 
 constexpr int kMmaMaxStages = 4;
@@ -265,9 +272,6 @@ constexpr int kMmaThreads = kEpiThreads + 64;   // + warp 8 (tcgen05.mma issue) 
 
 __device__ __forceinline__ void mbar_arrive(unsigned bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void epi_bar_sync() {  // named barrier of the 256 epilogue threads (the producer warp never joins)
-    asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32]) {
     unsigned r[32];
@@ -284,13 +288,58 @@ __device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+
+// Sorted k-best list of one epilogue thread, register resident for the whole level (r1f profile: with the list in
+// shared memory and a runtime k, one merged candidate cost ~135 issue slots and merges were 37 % of the top-k kernel).
+// KK = 5 serves the reference's k = 5; KK = LEC_MAX_TOPK keeps the 8 best and reports the first k.
+template <int KK>
+struct TopList {
+    float v[KK];
+    int l[KK];
+    __device__ __forceinline__ void reset() {
+#pragma unroll
+        for (int q = 0; q < KK; ++q) { v[q] = INFINITY; l[q] = -1; }
+    }
+    __device__ __forceinline__ void shift_in(const bool (&b)[KK], float E, int lab) {
+#pragma unroll
+        for (int q = KK - 1; q > 0; --q) {
+            v[q] = b[q - 1] ? v[q - 1] : (b[q] ? E : v[q]);
+            l[q] = b[q - 1] ? l[q - 1] : (b[q] ? lab : l[q]);
+        }
+        v[0] = b[0] ? E : v[0];
+        l[0] = b[0] ? lab : l[0];
+    }
+    // A thread meets its labels in ascending order, so an entry of its own stream carries a higher label than anything
+    // already listed: a strict compare keeps ties in label order.  NaN never enters (torch.topk ranks it last).
+    __device__ __forceinline__ void insert_ascending(float E, int lab) {
+        bool b[KK];
+#pragma unroll
+        for (int q = 0; q < KK; ++q) b[q] = E < v[q];
+        shift_in(b, E, lab);
+    }
+    // entry of another stream (the peer thread's list): ties go to the lower label; empty slots carry label -1
+    __device__ __forceinline__ void insert_any(float E, int lab) {
+        bool b[KK];
+#pragma unroll
+        for (int q = 0; q < KK; ++q) b[q] = E < v[q] || (E == v[q] && (unsigned)lab < (unsigned)l[q]);
+        shift_in(b, E, lab);
+    }
+    __device__ __forceinline__ float kth(int k) const {
+        if (KK == 5) return v[4];
+        float r = v[0];
+#pragma unroll
+        for (int q = 1; q < KK; ++q) r = (q < k) ? v[q] : r;
+        return r;
+    }
+};
+
 // Warp roles: warps 0..7 = epilogue (warp w reads TMEM lanes 32 (w % 4) .., labels 16 (w / 4) .. of every chunk),
 // warp 8 = MMA issuer (warp-uniform code so descriptors live in uniform registers; one lane issues), warp 9 =
 // loader (one lane issues the bulk copies).  Pipelines: full[s] (blob landed in stage s), done[t] (accumulator t
 // complete), accfree[t] (all 256 epilogue threads hold accumulator t's values in registers), empty[s] (all 256
 // epilogue threads are finished with the constants of blob stage s, whose MMAs have completed).
-// MODE 0: top-k only (deferred angle), 1: matrix only, 2: matrix + top-k
-template <int MODE, int FORMS>
+// MODE 0: top-k only (deferred angle), 1: matrix only, 2: matrix + top-k.  KK: slots of the per-thread k-best list.
+template <int MODE, int FORMS, int KK>
 __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(const MmaArgs a) {
     constexpr int NL = kMmaN / FORMS;        // labels per chunk
     constexpr int LT = NL / 2;               // labels per epilogue thread and chunk
@@ -301,10 +350,12 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(const MmaArgs
     const int blob = mma_blob_bytes(Kp, FORMS);
     const int NS = a.stages;
     unsigned char* sB = smem_raw;                // NS blob stages
-    float2* top = reinterpret_cast<float2*>(sB + (size_t)NS * blob);               // [k][256] {E, label}
-    float2* ring = top + (size_t)a.k * kEpiThreads;                                  // [ring][256] {E or g, label}
-    float* ringp = reinterpret_cast<float*>(ring + (size_t)a.ring * kEpiThreads);    // [ring][256] -psi
-    uint64_t* bars = reinterpret_cast<uint64_t*>(ringp + (size_t)a.ring * kEpiThreads);  // full[4], done[4], empty[4], accfree[4]
+    // top-k launches: final lists of the second thread of every image [2 buffers][KK][128] {E, label}, the k-th best
+    // every thread publishes for its peer [256] {E, level}, candidate ring [ring][256] {E or g, label}
+    float2* top = reinterpret_cast<float2*>(sB + (size_t)NS * blob);
+    float2* thr_pub = top + (MODE == 1 ? 0 : 2 * KK * kMmaM);
+    float2* ring = thr_pub + (MODE == 1 ? 0 : kEpiThreads);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)a.ring * kEpiThreads);  // full[4], done[4], empty[4], accfree[4]
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 4 * kMmaMaxStages);
 
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -321,11 +372,16 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(const MmaArgs
         for (int s = 0; s < kMmaMaxStages; ++s) {
             mbar_init(bar_full0 + 8 * s, 1);
             mbar_init(bar_done0 + 8 * s, 1);
-            mbar_init(bar_empty0 + 8 * s, kEpiThreads);
-            mbar_init(bar_accfree0 + 8 * s, kEpiThreads);
+            // matrix-only launches with two accumulators split the chunks between the two 4-warp groups (see the
+            // epilogue): a stage is then released by the 128 threads of its owner group only
+            const unsigned owners = (MODE == 1 && NA == 2 && a.alt) ? kEpiThreads / 2 : kEpiThreads;
+            mbar_init(bar_empty0 + 8 * s, owners);
+            mbar_init(bar_accfree0 + 8 * s, owners);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // no level is published yet (shared memory arrives with whatever the previous CTA left there)
+    if (MODE != 1 && tid < kEpiThreads) thr_pub[tid] = make_float2(INFINITY, __int_as_float(-1));
 
     // ---- image rows -> the A operand in tensor memory.  Two threads per row: warps 0-3 write the tf32 hi parts,
     //      warps 4-7 the lo parts (a warp can only touch TMEM lanes 32 (warp % 4) ..); both keep |y|^2.
@@ -376,7 +432,7 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(const MmaArgs
             int s = 0;
             unsigned par = 0;
             for (int c = NS; c < a.n_chunks; ++c) {
-                mbar_wait(bar_empty0 + 8 * s, par);
+                mbar_wait(bar_empty0 + 8 * s, par, a.sleep_ns);
                 mbar_expect_tx(bar_full0 + 8 * s, (unsigned)blob);
                 bulk_g2s(sB_u + s * blob, a.ws + (size_t)c * blob, (unsigned)blob, bar_full0 + 8 * s);
                 if (++s == NS) { s = 0; par ^= 1u; }
@@ -392,8 +448,8 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(const MmaArgs
         int s = 0, t = 0;
         unsigned par = 0, par_t = 1;   // accfree[t] is first waited on for chunk NA, i.e. after one wrap of t
         for (int c = 0; c < a.n_chunks; ++c) {
-            mbar_wait(bar_full0 + 8 * s, par);
-            if (c >= NA) mbar_wait(bar_accfree0 + 8 * t, par_t);
+            mbar_wait(bar_full0 + 8 * s, par, a.sleep_ns);
+            if (c >= NA) mbar_wait(bar_accfree0 + 8 * t, par_t, a.sleep_ns);
             tc_fence_after();
             const unsigned d = tmem_base + (unsigned)(t * kMmaN);
             const unsigned bh = sB_u + s * blob, bl = bh + b_tile;
@@ -418,114 +474,99 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(const MmaArgs
         const u64 B2 = pack2(Bn, Bn), C2 = pack2(-1.f - Bn, -1.f - Bn);   // FORMS == 1 only
         (void)B2; (void)C2;
         const int k = a.k;
-        const int et = tid;  // 0..255: slot in the per-thread top / ring arrays
-        const unsigned ring0 = smem_u32(ring + et), ringp0 = smem_u32(ringp + et);
+        const int et = tid;  // 0..255: slot in the per-thread ring / published-threshold arrays
+        const unsigned ring0 = smem_u32(ring + et);
         unsigned rp = ring0;
-        const unsigned ring_trigger = ring0 + (unsigned)(a.ring - kMmaRingCheck) * kEpiThreads * 8;
+        const unsigned ring_trigger = ring0 + (unsigned)(a.ring - kMmaRingRoom) * kEpiThreads * 8;
         float thr = INFINITY;                  // MODE 2: k-th best energy so far
         float cT = 0.f, nsT = 0.f, off = -INFINITY;  // MODE 0: accept g >= cT cos(psi) - sT sin(psi) + off
         float psi_max = 0.f;
-        float2* mytop = top + et;
-        const float2* peer_top = top + (et ^ kMmaM);   // the thread scanning the other 32 columns for the same image
+        int level = -1, lvl_buf = 0;
+        TopList<KK> list;
+        list.reset();
 
         auto refresh = [&]() {
-            // both halves feed one top-k: the tighter of the two k-th bests is a valid bound for either
-            const float t = fminf(mytop[(size_t)(k - 1) * kEpiThreads].x, peer_top[(size_t)(k - 1) * kEpiThreads].x);
+            // both threads of an image feed one top-k: the tighter of the two k-th bests bounds either stream.  The peer's
+            // published value counts only while it is working on the same level (it may be a chunk ahead or behind).
+            const float2 pe = thr_pub[et ^ kMmaM];
+            const float t = fminf(list.kth(k), __float_as_int(pe.y) == level ? pe.x : INFINITY);
             thr = t;
             if (t <= 0.f) { cT = 0.f; nsT = 0.f; off = INFINITY; }
             else if (!(t + psi_max <= 3.1415f)) { cT = 0.f; nsT = 0.f; off = -INFINITY; }
             else { float sn, cs; __sincosf(t, &sn, &cs); cT = cs; nsT = -sn; off = -4e-6f; }
         };
-        auto insert = [&](float Ev, float lab_f) {   // into this thread's sorted list; ties keep the lower label first
-            if (Ev < mytop[(size_t)(k - 1) * kEpiThreads].x ||
-                (Ev == mytop[(size_t)(k - 1) * kEpiThreads].x && __float_as_int(lab_f) < __float_as_int(mytop[(size_t)(k - 1) * kEpiThreads].y))) {
-                int pos = k - 1;
-                while (pos > 0) {
-                    const float2 prev = mytop[(size_t)(pos - 1) * kEpiThreads];
-                    if (!(prev.x > Ev || (prev.x == Ev && __float_as_int(prev.y) > __float_as_int(lab_f)))) break;
-                    mytop[(size_t)pos * kEpiThreads] = prev;
-                    --pos;
-                }
-                mytop[(size_t)pos * kEpiThreads] = make_float2(Ev, lab_f);
-            }
-        };
+        auto publish = [&]() { thr_pub[et] = make_float2(list.kth(k), __int_as_float(level)); };
         auto merge = [&]() {
-            // The sorted list lives in shared memory (the peer thread reads its k-th entry), but a merge works on a
-            // register copy: one compare-select sweep per ring entry instead of a load-compare-store chain per shifted
-            // slot (r1e profile: those chains were ~45 % of the top-k kernels' samples).  Ties keep the lower label.
+            // ring entries two at a time: one packed acos serves both (MODE 0: the ring holds g; the same instruction
+            // sequence as the matrix path, so deferred and direct energies agree bit for bit)
             const int cnt = (int)((rp - ring0) / (kEpiThreads * 8));
-            if (cnt > 0) {
-                float tv[LEC_MAX_TOPK];
-                int tl[LEC_MAX_TOPK];
-#pragma unroll
-                for (int j = 0; j < LEC_MAX_TOPK; ++j) {
-                    tv[j] = INFINITY; tl[j] = -1;
-                    if (j < k) { const float2 e = mytop[(size_t)j * kEpiThreads]; tv[j] = e.x; tl[j] = __float_as_int(e.y); }
+            for (int j = 0; j < cnt; j += 2) {
+                const bool two = j + 1 < cnt;
+                const float2 e0 = ring[j * kEpiThreads + et];
+                const float2 e1 = ring[(two ? j + 1 : j) * kEpiThreads + et];
+                const int lab0 = __float_as_int(e0.y), lab1 = __float_as_int(e1.y);
+                float E0 = e0.x, E1 = e1.x;
+                if (MODE == 0) {
+                    const float np0 = __ldg(a.npsi + lab0), np1 = __ldg(a.npsi + lab1);
+                    float z0, z1;
+                    unpack2(fadd2(acos_clamped2(pack2(e0.x, e1.x)), pack2(np0, np1)), z0, z1);
+                    E0 = max_nan(z0, 0.f);
+                    E1 = max_nan(z1, 0.f);
                 }
-                for (int j = 0; j < cnt; ++j) {
-                    const float2 e = ring[j * kEpiThreads + et];
-                    float Ev = e.x;
-                    if (MODE == 0) {  // deferred: the ring holds g; same instruction sequence as the matrix path
-                        const float np = ringp[j * kEpiThreads + et];
-                        float z0, z1;
-                        unpack2(fadd2(acos_clamped2(pack2(e.x, e.x)), pack2(np, np)), z0, z1);
-                        Ev = max_nan(z0, 0.f);
-                    }
-                    const int lab = __float_as_int(e.y);
-                    bool before[LEC_MAX_TOPK];   // the entry sorts before slot j
-#pragma unroll
-                    for (int q = 0; q < LEC_MAX_TOPK; ++q) before[q] = (q < k) && (Ev < tv[q] || (Ev == tv[q] && lab < tl[q]));
-#pragma unroll
-                    for (int q = LEC_MAX_TOPK - 1; q > 0; --q) {
-                        tv[q] = before[q - 1] ? tv[q - 1] : (before[q] ? Ev : tv[q]);
-                        tl[q] = before[q - 1] ? tl[q - 1] : (before[q] ? lab : tl[q]);
-                    }
-                    tv[0] = before[0] ? Ev : tv[0];
-                    tl[0] = before[0] ? lab : tl[0];
-                }
-#pragma unroll
-                for (int j = 0; j < LEC_MAX_TOPK; ++j)
-                    if (j < k) mytop[(size_t)j * kEpiThreads] = make_float2(tv[j], __int_as_float(tl[j]));
+                list.insert_ascending(E0, lab0);
+                if (two) list.insert_ascending(E1, lab1);
             }
+            if (cnt > 0) publish();
             rp = ring0;
             refresh();
         };
 
         const int lane_base = (warp & 3) * 32;
+        // Chunk ownership.  Top-k launches: every epilogue thread visits every chunk and takes half of its labels (the two
+        // threads of an image keep separate lists, merged at the end of a level).  Matrix-only launches with two
+        // accumulator buffers (ALT): warps 0-3 take the even chunks and warps 4-7 the odd ones, all labels of the chunk in
+        // two batches -- half as many barrier / header / TMEM-load prologues per warp, and the two groups run out of
+        // phase, so their MUFU- and FMA-heavy stretches interleave on an SM sub-partition instead of colliding.
+        const bool alt = (MODE == 1) && NA == 2 && a.alt;
+        const int cstep = alt ? 2 : 1;
         // stage indices and phase parities advance by increments (no integer division in the chunk loop)
-        int s = 0, t = 0;
+        int s = alt ? half : 0, t = alt ? half : 0;
         unsigned par = 0, par_t = 0;
-        for (int c = 0; c < a.n_chunks; ++c) {
-            mbar_wait(bar_full0 + 8 * s, par);   // constants + header of chunk c visible to this thread
+        while (s >= NS) { s -= NS; par ^= 1u; }
+        for (int c = alt ? half : 0; c < a.n_chunks; c += cstep) {
+            mbar_wait(bar_full0 + 8 * s, par, a.sleep_ns);   // constants + header of chunk c visible to this thread
             const unsigned char* bl = sB + (size_t)s * blob;
             const float* cst = reinterpret_cast<const float*>(bl + 2 * b_tile);
             const MmaHdr hdr = *reinterpret_cast<const MmaHdr*>(bl + 2 * b_tile + mma_const_bytes(FORMS));
             const bool want_topk = (MODE != 1) && hdr.level >= 0;
             if (want_topk) {
                 if (hdr.flags & 1) {
-                    for (int j = 0; j < k; ++j) mytop[(size_t)j * kEpiThreads] = make_float2(INFINITY, __int_as_float(-1));
+                    list.reset();
                     rp = ring0;
-                    epi_bar_sync();   // both halves reset before either reads the other's k-th best
+                    level = hdr.level;
+                    publish();
                 }
                 psi_max = hdr.psi_max;
                 refresh();
             }
-            mbar_wait(bar_done0 + 8 * t, par_t);   // accumulator of chunk c complete
+            mbar_wait(bar_done0 + 8 * t, par_t, a.sleep_ns);   // accumulator of chunk c complete
             tc_fence_after();
 
-            const int lbase = half * LT;                     // this thread's first label of the chunk
-            const int my_count = hdr.count - lbase;          // labels of mine that exist (<= 0: none)
-            // my 48 accumulator columns -> registers, then the accumulator buffer is released at once.
-            // FORMS == 3: v[0] = num, v[1] = w2, v[2] = A s^2 of my 16 labels;  FORMS == 1: v[gi] = p of labels 16 gi ..
+            const bool store = (MODE != 0) && a.scores != nullptr && img_ok;
+            for (int hb = 0; hb < cstep; ++hb) {
+            const int lbase = (alt ? hb : half) * LT;        // first label of this batch within the chunk
+            // 48 accumulator columns -> registers; the accumulator buffer is released right after the last batch's load.
+            // FORMS == 3: v[0] = num, v[1] = w2, v[2] = A s^2 of 16 labels;  FORMS == 1: v[gi] = p of labels 16 gi ..
             float v[3][16];
             {
                 const unsigned tcol = tmem_base + ((unsigned)lane_base << 16) + (unsigned)(t * kMmaN);
                 tmem_ld16x3(tcol + (unsigned)lbase, tcol + (unsigned)(FORMS == 3 ? NL + lbase : lbase + 16),
                             tcol + (unsigned)(FORMS == 3 ? 2 * NL + lbase : lbase + 32), v[0], v[1], v[2]);
             }
-            tc_fence_before();
-            mbar_arrive(bar_accfree0 + 8 * t);
-            const bool store = (MODE != 0) && a.scores != nullptr && img_ok;
+            if (hb == cstep - 1) {
+                tc_fence_before();
+                mbar_arrive(bar_accfree0 + 8 * t);
+            }
 #pragma unroll
             for (int gi = 0; gi < GROUPS; ++gi) {
                 const int gbase = lbase + 16 * gi;               // first label of this group within the chunk
@@ -572,24 +613,19 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(const MmaArgs
                         }
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
-                            float g0, g1, b0, b1, np0, np1;
+                            float g0, g1, b0, b1;
                             unpack2(g[q], g0, g1);
                             unpack2(cb[q], b0, b1);
-                            unpack2(NPSI[q], np0, np1);
                             if (2 * q < g_count && g0 >= b0) {
                                 asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(rp), "f"(g0), "r"(lab0 + 2 * q) : "memory");
-                                asm volatile("st.shared.b32 [%0], %1;" ::"r"(ringp0 + ((rp - ring0) >> 1)), "f"(np0) : "memory");
                                 rp += kEpiThreads * 8;
                             }
                             if (2 * q + 1 < g_count && g1 >= b1) {
                                 asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(rp), "f"(g1), "r"(lab0 + 2 * q + 1) : "memory");
-                                asm volatile("st.shared.b32 [%0], %1;" ::"r"(ringp0 + ((rp - ring0) >> 1)), "f"(np1) : "memory");
                                 rp += kEpiThreads * 8;
                             }
-                            if ((q & 3) == 3) {
-                                if (__any_sync(0xffffffffu, rp > ring_trigger)) merge();
-                            }
                         }
+                        if (__any_sync(0xffffffffu, rp > ring_trigger)) merge();
                     }
                 } else {
                     float E[16];
@@ -618,36 +654,53 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(const MmaArgs
                                 asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(rp), "f"(E[j]), "r"(lab0 + j) : "memory");
                                 rp += kEpiThreads * 8;
                             }
-                            if ((j & 7) == 7) {
-                                if (__any_sync(0xffffffffu, rp > ring_trigger)) merge();
+                        }
+                        if (__any_sync(0xffffffffu, rp > ring_trigger)) merge();
+                    }
+                }
+            }
+            }   // batches
+            if (want_topk && (hdr.flags & 2)) {
+                merge();
+                // The second thread of every image hands its list over (double buffered by level, so its next hand-over
+                // cannot overtake the fold) and a barrier of just the two warps that share the 32 images orders it.
+                float2* hand = top + (size_t)lvl_buf * (KK * kMmaM) + row;
+                if (half) {
+#pragma unroll
+                    for (int j = 0; j < KK; ++j) hand[j * kMmaM] = make_float2(list.v[j], __int_as_float(list.l[j]));
+                }
+                switch (warp & 3) {   // immediate barrier ids, so that the kernel reserves five barriers and not all sixteen
+                    case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+                    case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+                    case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+                    default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+                }
+                if (!half) {
+#pragma unroll
+                    for (int j = 0; j < KK; ++j) {
+                        const float2 e = hand[j * kMmaM];
+                        if (__float_as_int(e.y) >= 0) list.insert_any(e.x, __float_as_int(e.y));
+                    }
+                    if (img_ok) {
+                        const int64_t o = (img * a.n_levels + hdr.level) * k;
+#pragma unroll
+                        for (int j = 0; j < KK; ++j) {
+                            if (j < k) {
+                                a.topk_idx[o + j] = list.l[j];
+                                if (a.topk_val) a.topk_val[o + j] = list.v[j];
                             }
                         }
                     }
                 }
-            }
-            if (want_topk && (hdr.flags & 2)) {
-                merge();
-                epi_bar_sync();       // both halves' lists are final
-                if (half == 0) {
-                    for (int j = 0; j < k; ++j) {   // fold the other half's k best into mine
-                        const float2 e = peer_top[(size_t)j * kEpiThreads];
-                        if (__float_as_int(e.y) >= 0) insert(e.x, e.y);
-                    }
-                    if (img_ok) {
-                        const int64_t o = (img * a.n_levels + hdr.level) * k;
-                        for (int j = 0; j < k; ++j) {
-                            const float2 e = mytop[(size_t)j * kEpiThreads];
-                            a.topk_idx[o + j] = __float_as_int(e.y);
-                            if (a.topk_val) a.topk_val[o + j] = e.x;
-                        }
-                    }
-                }
-                epi_bar_sync();       // the next level's reset must not overtake the fold
+                lvl_buf ^= 1;
+                level = -1;
             }
             // this thread is done with the constants of blob stage s (its MMAs completed before done[t] fired)
             mbar_arrive(bar_empty0 + 8 * s);
-            if (++s == NS) { s = 0; par ^= 1u; }
-            if (++t == NA) { t = 0; par_t ^= 1u; }
+            s += cstep;
+            while (s >= NS) { s -= NS; par ^= 1u; }
+            if (alt) par_t ^= 1u;
+            else if (++t == NA) { t = 0; par_t ^= 1u; }
         }
     }
 
@@ -691,7 +744,8 @@ static int64_t mma_max_chunks(int64_t L, int n_levels, int NL) { return (L + NL 
 
 int64_t score_mma_workspace_bytes(int64_t L, int D, int n_levels) {
     const int forms = mma_forms(D);
-    return mma_max_chunks(L, n_levels, mma_labels(forms)) * mma_blob_bytes(mma_kp(D, forms), forms);
+    // chunk blobs + the per-label -psi table the top-k merge reads
+    return mma_max_chunks(L, n_levels, mma_labels(forms)) * mma_blob_bytes(mma_kp(D, forms), forms) + (L + 32) * 4;
 }
 
 // TMEM budget of one CTA: acc_stages accumulator buffers of 96 columns + the image tile (2 Kp columns).  Two buffers
@@ -720,10 +774,12 @@ int score_mma_launch(const float* labels, int64_t L, const float* images, int64_
     if (tab.n == 0) return 0;
     const int Kp = mma_kp(D, forms);
     const int blob = mma_blob_bytes(Kp, forms);
-    if ((int64_t)tab.n * blob > workspace_bytes) return LEC_E_SIZE;
+    if ((int64_t)tab.n * blob + L * 4 > workspace_bytes) return LEC_E_SIZE;
     if (reinterpret_cast<uintptr_t>(workspace) & 127) return LEC_E_ALIGN;
+    if (topk_idx && (k < 1 || k > LEC_MAX_TOPK)) return LEC_E_K;
     unsigned char* ws = static_cast<unsigned char*>(workspace);
-    score_mma_prep_kernel<<<tab.n, kMmaN, 0, st>>>(labels, D, Kp, forms, K, tab, ws);
+    float* npsi = reinterpret_cast<float*>(ws + (size_t)tab.n * blob);   // blob sizes are multiples of 32 bytes
+    score_mma_prep_kernel<<<tab.n, kMmaN, 0, st>>>(labels, D, Kp, forms, K, tab, ws, npsi);
     ++g_launches;
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) return (int)ce;
@@ -731,8 +787,14 @@ int score_mma_launch(const float* labels, int64_t L, const float* images, int64_
     MmaArgs a{};
     a.images = images; a.N = N; a.D = D; a.Kp = Kp; a.ws = ws; a.n_chunks = tab.n; a.scores = scores;
     a.topk_idx = topk_idx; a.topk_val = topk_val; a.k = topk_idx ? k : 1; a.n_levels = n_levels;
-    a.ring = topk_idx ? 16 : 0;   // matrix-only launches need no candidate ring
-    const size_t fixed = (size_t)a.k * kEpiThreads * 8 + (size_t)a.ring * kEpiThreads * 12 + 256;
+    a.npsi = npsi;
+    a.ring = topk_idx ? kMmaRing : 0;   // matrix-only launches need no candidate ring
+    const int kk = (a.k == 5) ? 5 : LEC_MAX_TOPK;
+    static const int sleep_env = [] { const char* e = getenv("LEC_TC_SLEEP_NS"); return e ? atoi(e) : 32; }();
+    a.sleep_ns = sleep_env;
+    static const int alt_env = [] { const char* e = getenv("LEC_TC_ALT"); return e ? atoi(e) : 1; }();
+    a.alt = alt_env;
+    const size_t fixed = (topk_idx ? (size_t)(2 * kk * kMmaM + kEpiThreads) * 8 : 0) + (size_t)a.ring * kEpiThreads * 8 + 256;
     // Blob stages: the loader can only refill a stage after the epilogue of its chunk, and a bulk copy from L2 takes
     // longer than one chunk's epilogue (32 labels x 128 images), so short rows get up to four stages in flight (r1e
     // profile: with two, the epilogue warps spent ~9 wait iterations per chunk on full[]).  Within 256 TMEM columns the
@@ -756,13 +818,13 @@ int score_mma_launch(const float* labels, int64_t L, const float* images, int64_
         return (int)cudaGetLastError();
     };
     if (forms == 3) {
-        if (mode == 0) return launch(score_mma_kernel<0, 3>);
-        if (mode == 1) return launch(score_mma_kernel<1, 3>);
-        return launch(score_mma_kernel<2, 3>);
+        if (mode == 1) return launch(score_mma_kernel<1, 3, 5>);
+        if (mode == 0) return kk == 5 ? launch(score_mma_kernel<0, 3, 5>) : launch(score_mma_kernel<0, 3, LEC_MAX_TOPK>);
+        return kk == 5 ? launch(score_mma_kernel<2, 3, 5>) : launch(score_mma_kernel<2, 3, LEC_MAX_TOPK>);
     }
-    if (mode == 0) return launch(score_mma_kernel<0, 1>);
-    if (mode == 1) return launch(score_mma_kernel<1, 1>);
-    return launch(score_mma_kernel<2, 1>);
+    if (mode == 1) return launch(score_mma_kernel<1, 1, 5>);
+    if (mode == 0) return kk == 5 ? launch(score_mma_kernel<0, 1, 5>) : launch(score_mma_kernel<0, 1, LEC_MAX_TOPK>);
+    return kk == 5 ? launch(score_mma_kernel<2, 1, 5>) : launch(score_mma_kernel<2, 1, LEC_MAX_TOPK>);
 }
 
 }  // namespace lec

@@ -551,8 +551,8 @@ def run_cfg3(args):
     tc_ok = bool(lib.lec_score_tc_supported(ops.GEOM["hyp"], 0, D, L, nl))
     if args.engine == "tc" and not tc_ok:
         raise SystemExit("tensor-core scoring does not support this case")
-    # "auto" = what ops.score_topk picks: the tensor-core kernel for matrix-only steps, the SIMT kernel when top-k is wanted
-    use_tc = tc_ok and (args.engine == "tc" or (args.engine == "auto" and not want_topk))
+    # "auto" = what ops.score_topk picks: the tensor-core kernel whenever it supports the case
+    use_tc = tc_ok and args.engine in ("tc", "auto")
     cfg["engine"] = "tc (tcgen05 kind::tf32 3xTF32 + fused epilogue)" if use_tc else "simt (packed FFMA2 tile kernel)"
     ws, nb = None, 0
     if use_tc:

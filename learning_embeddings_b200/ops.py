@@ -319,15 +319,16 @@ def score_topk_into(labels, images, geom, K, level_start, level_stop, k, idx, va
     le = (ctypes.c_int32 * max(nl, 1))(*[int(v) for v in level_stop])
     dev = labels.device
     # engine: "tc" = tcgen05 tensor-core contraction + fused epilogue (lec_score_topk_tc), "simt" = the packed-FMA
-    # tile kernel (lec_score_topk_ex).  "auto" follows the measurements (profiles/r1e_score_bench.log, 1 M x 723):
-    # matrix-only calls go to the tensor-core kernel (0.88 vs 1.02 ms at D=10, 1.12 vs 2.69 ms at D=50); calls that
-    # want top-k stay on the SIMT kernel, whose per-thread lists cover four images of a whole level (1.63 vs 2.86 ms).
+    # tile kernel (lec_score_topk_ex).  "auto" follows the measurements (profiles/r1f_score_bench.log, 1 M x 723):
+    # the tensor-core kernel wins every mode it supports since its top-k lists live in registers (top-k 1.40 vs
+    # 1.66 ms at D=10, 2.53 vs 4.19 ms at D=50; matrix 0.86 vs 1.04 ms and 1.14 vs 2.68 ms); the SIMT kernel serves the
+    # other geometries, the fp64 core and image-major score matrices.
     lib = N.lib()
     tc_ok = scores_layout == 1 and bool(lib.lec_score_tc_supported(GEOM[geom], int(precision), D, L, nl))
     if engine == "tc" and not tc_ok:
         raise N.LecError("tensor-core scoring supports hyperbolic cones, fp32 core, label-major scores, D <= 128")
     if engine == "auto":
-        engine = "tc" if (tc_ok and idx is None and val is None) else "simt"
+        engine = "tc" if tc_ok else "simt"
     if engine == "tc":
         nbytes = int(lib.lec_score_workspace_bytes(L, D, nl))
         ws = _score_workspace(dev, nbytes)

@@ -171,6 +171,16 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity, int sle
         }
     }
 }
+// one non-blocking look at the phase
+__device__ __forceinline__ bool mbar_test(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -259,7 +269,8 @@ struct MmaArgs {
     int32_t* topk_idx; float* topk_val; int k, n_levels;
     const float* npsi;       // [L] -psi(label), written by the prep launch (top-k merge of deferred candidates)
     int ring;                // candidate ring entries per thread
-    int stages;              // blob stages in shared memory (1..4)
+    int stages;              // label-tile stages in shared memory (1..4), released by the MMAs that read them
+    int cstages;             // constant + header stages (1..4), released by the epilogue threads
     int acc_stages;          // accumulator buffers in TMEM (1 or 2)
     int tmem_cols;           // power of two >= acc_stages * 96 + 2 Kp
     int sleep_ns;            // back-off of a warp that keeps finding its mbarrier phase incomplete
@@ -348,20 +359,27 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(const MmaArgs
     const int Kp = a.Kp, KS = Kp >> 3;
     const int b_tile = mma_tile_bytes(Kp);
     const int blob = mma_blob_bytes(Kp, FORMS);
-    const int NS = a.stages;
-    unsigned char* sB = smem_raw;                // NS blob stages
+    const int NS = a.stages, NC = a.cstages;
+    // A blob travels in two bulk copies: its B_hi | B_lo tiles into a tile stage, which the MMAs' own completion frees
+    // (tcgen05.commit on tfree[s]), and its constants + header into a small constant stage that the epilogue threads
+    // hold for the whole chunk.  Wide rows (D = 50: 43 KB of tiles per chunk) then need a single tile stage and two
+    // CTAs fit an SM in every mode (r1f profile: the top-k launches ran one CTA per SM at 37 % issue utilisation).
+    const int tiles = 2 * b_tile, cbytes = blob - tiles, cstride = (cbytes + 127) & ~127;
+    unsigned char* sB = smem_raw;                // NS tile stages
+    unsigned char* sC = sB + (size_t)NS * tiles; // NC constant stages
     // top-k launches: final lists of the second thread of every image [2 buffers][KK][128] {E, label}, the k-th best
     // every thread publishes for its peer [256] {E, level}, candidate ring [ring][256] {E or g, label}
-    float2* top = reinterpret_cast<float2*>(sB + (size_t)NS * blob);
+    float2* top = reinterpret_cast<float2*>(sC + (size_t)NC * cstride);
     float2* thr_pub = top + (MODE == 1 ? 0 : 2 * KK * kMmaM);
     float2* ring = thr_pub + (MODE == 1 ? 0 : kEpiThreads);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)a.ring * kEpiThreads);  // full[4], done[4], empty[4], accfree[4]
-    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 4 * kMmaMaxStages);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)a.ring * kEpiThreads);  // full[4], done[4], empty[4], accfree[4], tfull[4], tfree[4]
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 6 * kMmaMaxStages);
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int NA = a.acc_stages;
     const unsigned bar_full0 = smem_u32(bars), bar_done0 = smem_u32(bars + kMmaMaxStages), bar_empty0 = smem_u32(bars + 2 * kMmaMaxStages);
     const unsigned bar_accfree0 = smem_u32(bars + 3 * kMmaMaxStages);
+    const unsigned bar_tfull0 = smem_u32(bars + 4 * kMmaMaxStages), bar_tfree0 = smem_u32(bars + 5 * kMmaMaxStages);
     // tensor memory: NA accumulator buffers of 96 columns, then the image tile as the A operand: A_hi | A_lo, Kp
     // columns each (lane = image row); the host rounded the total up to a power of two
     const unsigned col_ahi = (unsigned)(NA * kMmaN), col_alo = col_ahi + (unsigned)Kp;
@@ -372,6 +390,8 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(const MmaArgs
         for (int s = 0; s < kMmaMaxStages; ++s) {
             mbar_init(bar_full0 + 8 * s, 1);
             mbar_init(bar_done0 + 8 * s, 1);
+            mbar_init(bar_tfull0 + 8 * s, 1);
+            mbar_init(bar_tfree0 + 8 * s, 1);
             // matrix-only launches with two accumulators split the chunks between the two 4-warp groups (see the
             // epilogue): a stage is then released by the 128 threads of its owner group only
             const unsigned owners = (MODE == 1 && NA == 2 && a.alt) ? kEpiThreads / 2 : kEpiThreads;
@@ -413,11 +433,15 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(const MmaArgs
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     } else if (warp == 9 && (tid & 31) == 0) {
-        // the first NS label blobs stream in while the image tile is being converted
-        const unsigned sB_u = smem_u32(sB);
+        // the first label blobs stream in while the image tile is being converted
+        const unsigned sB_u = smem_u32(sB), sC_u = smem_u32(sC);
         for (int c = 0; c < NS && c < a.n_chunks; ++c) {
-            mbar_expect_tx(bar_full0 + 8 * c, (unsigned)blob);
-            bulk_g2s(sB_u + c * blob, a.ws + (size_t)c * blob, (unsigned)blob, bar_full0 + 8 * c);
+            mbar_expect_tx(bar_tfull0 + 8 * c, (unsigned)tiles);
+            bulk_g2s(sB_u + c * tiles, a.ws + (size_t)c * blob, (unsigned)tiles, bar_tfull0 + 8 * c);
+        }
+        for (int c = 0; c < NC && c < a.n_chunks; ++c) {
+            mbar_expect_tx(bar_full0 + 8 * c, (unsigned)cbytes);
+            bulk_g2s(sC_u + c * cstride, a.ws + (size_t)c * blob + tiles, (unsigned)cbytes, bar_full0 + 8 * c);
         }
     }
     tc_fence_before();
@@ -426,16 +450,34 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(const MmaArgs
 
     // ================================ producer warps ================================
     if (warp == 9) {
-        // loader: blob c goes into stage c % NS as soon as the epilogue of chunk c - NS has released it
+        // loader: the tiles of chunk ct go into tile stage ct % NS as soon as the MMAs of chunk ct - NS have completed,
+        // the constants of chunk cc into constant stage cc % NC once the epilogue of chunk cc - NC has released it.
+        // One thread serves both streams and never blocks on one while the other could move.
         if ((tid & 31) == 0) {
-            const unsigned sB_u = smem_u32(sB);
-            int s = 0;
-            unsigned par = 0;
-            for (int c = NS; c < a.n_chunks; ++c) {
-                mbar_wait(bar_empty0 + 8 * s, par, a.sleep_ns);
-                mbar_expect_tx(bar_full0 + 8 * s, (unsigned)blob);
-                bulk_g2s(sB_u + s * blob, a.ws + (size_t)c * blob, (unsigned)blob, bar_full0 + 8 * s);
-                if (++s == NS) { s = 0; par ^= 1u; }
+            const unsigned sB_u = smem_u32(sB), sC_u = smem_u32(sC);
+            int ct = NS, st = 0, cc = NC, sc = 0;
+            unsigned part = 0, parc = 0, idle = 0;
+            while (ct < a.n_chunks || cc < a.n_chunks) {
+                bool moved = false;
+                if (ct < a.n_chunks && mbar_test(bar_tfree0 + 8 * st, part)) {
+                    mbar_expect_tx(bar_tfull0 + 8 * st, (unsigned)tiles);
+                    bulk_g2s(sB_u + st * tiles, a.ws + (size_t)ct * blob, (unsigned)tiles, bar_tfull0 + 8 * st);
+                    ++ct;
+                    if (++st == NS) { st = 0; part ^= 1u; }
+                    moved = true;
+                }
+                if (cc < a.n_chunks && mbar_test(bar_empty0 + 8 * sc, parc)) {
+                    mbar_expect_tx(bar_full0 + 8 * sc, (unsigned)cbytes);
+                    bulk_g2s(sC_u + sc * cstride, a.ws + (size_t)cc * blob + tiles, (unsigned)cbytes, bar_full0 + 8 * sc);
+                    ++cc;
+                    if (++sc == NC) { sc = 0; parc ^= 1u; }
+                    moved = true;
+                }
+                if (moved) idle = 0;
+                else {
+                    if (a.sleep_ns > 0) __nanosleep((unsigned)a.sleep_ns);
+                    if (++idle > (1u << 24)) __trap();   // a lost arrival traps instead of hanging the GPU
+                }
             }
         }
         __syncwarp();
@@ -448,11 +490,11 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(const MmaArgs
         int s = 0, t = 0;
         unsigned par = 0, par_t = 1;   // accfree[t] is first waited on for chunk NA, i.e. after one wrap of t
         for (int c = 0; c < a.n_chunks; ++c) {
-            mbar_wait(bar_full0 + 8 * s, par, a.sleep_ns);
+            mbar_wait(bar_tfull0 + 8 * s, par, a.sleep_ns);
             if (c >= NA) mbar_wait(bar_accfree0 + 8 * t, par_t, a.sleep_ns);
             tc_fence_after();
             const unsigned d = tmem_base + (unsigned)(t * kMmaN);
-            const unsigned bh = sB_u + s * blob, bl = bh + b_tile;
+            const unsigned bh = sB_u + s * tiles, bl = bh + b_tile;
             unsigned acc = 0;
             for (int pass = 0; pass < 3; ++pass) {
                 const unsigned pa = tmem_base + ((pass == 2) ? col_alo : col_ahi);   // hi.hi, hi.lo, lo.hi
@@ -463,7 +505,10 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(const MmaArgs
                     acc = 1;
                 }
             }
-            if (issuer) tc_commit(bar_done0 + 8 * t);
+            if (issuer) {
+                tc_commit(bar_done0 + 8 * t);    // accumulator of chunk c complete -> epilogue
+                tc_commit(bar_tfree0 + 8 * s);   // tile stage s read -> loader
+            }
             __syncwarp();
             if (++s == NS) { s = 0; par ^= 1u; }
             if (++t == NA) { t = 0; par_t ^= 1u; }
@@ -532,12 +577,12 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(const MmaArgs
         // stage indices and phase parities advance by increments (no integer division in the chunk loop)
         int s = alt ? half : 0, t = alt ? half : 0;
         unsigned par = 0, par_t = 0;
-        while (s >= NS) { s -= NS; par ^= 1u; }
+        while (s >= NC) { s -= NC; par ^= 1u; }
         for (int c = alt ? half : 0; c < a.n_chunks; c += cstep) {
             mbar_wait(bar_full0 + 8 * s, par, a.sleep_ns);   // constants + header of chunk c visible to this thread
-            const unsigned char* bl = sB + (size_t)s * blob;
-            const float* cst = reinterpret_cast<const float*>(bl + 2 * b_tile);
-            const MmaHdr hdr = *reinterpret_cast<const MmaHdr*>(bl + 2 * b_tile + mma_const_bytes(FORMS));
+            const unsigned char* bl = sC + (size_t)s * cstride;
+            const float* cst = reinterpret_cast<const float*>(bl);
+            const MmaHdr hdr = *reinterpret_cast<const MmaHdr*>(bl + mma_const_bytes(FORMS));
             const bool want_topk = (MODE != 1) && hdr.level >= 0;
             if (want_topk) {
                 if (hdr.flags & 1) {
@@ -695,10 +740,10 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(const MmaArgs
                 lvl_buf ^= 1;
                 level = -1;
             }
-            // this thread is done with the constants of blob stage s (its MMAs completed before done[t] fired)
+            // this thread is done with the constants of stage s
             mbar_arrive(bar_empty0 + 8 * s);
             s += cstep;
-            while (s >= NS) { s -= NS; par ^= 1u; }
+            while (s >= NC) { s -= NC; par ^= 1u; }
             if (alt) par_t ^= 1u;
             else if (++t == NA) { t = 0; par_t ^= 1u; }
         }
@@ -795,18 +840,22 @@ int score_mma_launch(const float* labels, int64_t L, const float* images, int64_
     static const int alt_env = [] { const char* e = getenv("LEC_TC_ALT"); return e ? atoi(e) : 1; }();
     a.alt = alt_env;
     const size_t fixed = (topk_idx ? (size_t)(2 * kk * kMmaM + kEpiThreads) * 8 : 0) + (size_t)a.ring * kEpiThreads * 8 + 256;
-    // Blob stages: the loader can only refill a stage after the epilogue of its chunk, and a bulk copy from L2 takes
-    // longer than one chunk's epilogue (32 labels x 128 images), so short rows get up to four stages in flight (r1e
-    // profile: with two, the epilogue warps spent ~9 wait iterations per chunk on full[]).  Within 256 TMEM columns the
-    // budget is half an SM's shared memory so that two CTAs (20 warps) stay resident; otherwise the whole SM.
+    // Stages.  Constants + header: four small stages (the epilogue holds one per chunk in flight).  Tiles: a stage is
+    // free again as soon as the MMAs that read it complete, so one stage already overlaps the copy of chunk c + 1 with
+    // the epilogue of chunk c; more only help short rows whose epilogue is as short as a bulk copy.  Within 256 TMEM
+    // columns the budget is half an SM's shared memory so that two CTAs (20 warps) stay resident; otherwise the whole SM.
     if (!mma_plan(Kp, a.acc_stages, a.tmem_cols)) return LEC_E_DIM;
+    const size_t tiles = 2 * (size_t)mma_tile_bytes(Kp), cstride = ((size_t)blob - tiles + 127) & ~(size_t)127;
+    a.cstages = kMmaMaxStages;
+    const size_t fixed_c = fixed + (size_t)a.cstages * cstride;
     const size_t half_sm = 113 * 1024, whole_sm = 226 * 1024;
-    auto stages_for = [&](size_t budget) { return budget > fixed ? (int)((budget - fixed) / (size_t)blob) : 0; };
+    static const int min_stages = [] { const char* e = getenv("LEC_TC_MIN_STAGES"); return e ? atoi(e) : 1; }();
+    auto stages_for = [&](size_t budget) { return budget > fixed_c ? (int)((budget - fixed_c) / tiles) : 0; };
     int stages = a.tmem_cols <= 256 ? stages_for(half_sm) : 0;
-    if (stages < 2) stages = stages_for(whole_sm);
+    if (stages < min_stages) stages = stages_for(whole_sm);
     if (stages < 1) return LEC_E_DIM;
     a.stages = stages > kMmaMaxStages ? kMmaMaxStages : stages;
-    const size_t smem = fixed + (size_t)a.stages * blob;
+    const size_t smem = fixed_c + (size_t)a.stages * tiles;
     const int mode = topk_idx ? (scores ? 2 : 0) : 1;
     const int64_t grid = (N + kMmaM - 1) / kMmaM;
     if (grid > 0x7fffffffLL) return LEC_E_SIZE;

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LEC_ABI_VERSION 10
+#define LEC_ABI_VERSION 11
 
 /* geometry of the energy */
 #define LEC_GEOM_EUC 0 /* EucConesLoss.E_operator, order_embeddings.py:954-969 = oe.py:721-739 (cos-space) */
@@ -177,6 +177,37 @@ int lec_rsgd_update_p2p(float* table, void* const* peer_bufs, int64_t slot_float
                         double* loss_global_out, int* error_out, void* stream);
 #define LEC_MAX_PEERS 16
 
+/* ---- fused update + next step's row transform (label-only Poincare cones) -------------------------
+ * order_embeddings_h.py:764-775 followed by the Embedder.forward (:205-228) the NEXT iteration starts with: one launch
+ * per step instead of two.  Per table row: sum of the gradient replicas -> RSGD update in place -> shell projection
+ * of the updated row into rows_out [n, ld] + its aperture terms aux_out [n, 4] (as lec_rows_fwd with
+ * LEC_ROWS_HYP_SHELL) -> the row's gradient replicas cleared for the next lec_pairs_grouped.  The loss accumulator the
+ * pair kernel added into is moved: *loss_step = *loss_acc; *loss_acc = 0 (both optional).  Bit-identical to
+ * lec_rsgd_update followed by lec_rows_fwd.
+ */
+int lec_rsgd_update_rows(float* table, float* grad_rows, int grad_replicas, int64_t n, int D, int ld, float lr,
+                         float r_in, int lambda_mode, float K, float* rows_out, double* aux_out, double* loss_acc,
+                         double* loss_step, float* grad_out, void* stream);
+
+/* ---- push exchange (NVLink / NVSwitch peer stores) fused into the same two launches -----------------
+ * Exchange buffer layout of every rank:  float slot[2][world][slot_floats]; uint32 flag[2][world]
+ * (slot_floats >= n*D + 2, multiple of 4; the last two floats of a source region hold that rank's loss).
+ *   lec_p2p_push            replica sum of this rank's gradient -> slot[slot][rank] of EVERY rank's buffer (remote
+ *                           stores), replicas cleared, loss moved as above; the last block to finish release-stores
+ *                           flag[slot][rank] = tag into every buffer.  counter: device uint32, zero before the first
+ *                           call (the kernel leaves it zero).
+ *   lec_rsgd_update_rows_p2p waits for the `world` flags of MY buffer, sums the `world` source regions of MY buffer
+ *                           in rank order (local loads; bit-identical on every rank), then as lec_rsgd_update_rows.
+ * Replaces nn.DataParallel's reduce_add + broadcast (order_embeddings.py:360) with one collective per step that is
+ * part of the update launch.
+ */
+int lec_p2p_push(float* grad_rows, int grad_replicas, int64_t n, int D, int ld, double* loss_acc, double* loss_step,
+                 void* const* peer_bufs, int64_t slot_floats, int world, int rank, int slot, uint32_t tag,
+                 uint32_t* counter, void* stream);
+int lec_rsgd_update_rows_p2p(float* table, void* const* peer_bufs, int64_t slot_floats, int world, int rank, int slot,
+                             uint32_t tag, int64_t n, int D, int ld, float lr, float r_in, int lambda_mode, float K,
+                             float* rows_out, double* aux_out, double* loss_global_out, int* error_out, void* stream);
+
 /* ---- one whole training step in one call ---------------------------------------------------------
  * The launch sequence of one label-only cone step (what one iteration of the reference's
  * pass_samples('train') loop does between zero_grad() and the weight update, order_embeddings_h.py:752-775 /
@@ -202,6 +233,12 @@ typedef struct lec_step {
     void* const* peer_bufs; int64_t slot_floats; int world, rank, slot; uint32_t tag;
     double* loss_global; int* error;
     void* ev_pairs_start; void* ev_pairs_stop;
+    /* fused != 0 (RSGD on LEC_ROWS_HYP_SHELL rows only): rows / aux / cleared grad_rows are already current (a
+     * previous fused step or lec_rows_fwd produced them), the pair kernel adds into *loss_acc, and the step is
+     *     lec_pairs_grouped -> lec_rsgd_update_rows                              (world <= 1)
+     *     lec_pairs_grouped -> lec_p2p_push -> lec_rsgd_update_rows_p2p          (world  > 1, push layout)
+     * leaving this rank's loss of the step in *loss.  counter: see lec_p2p_push. */
+    int fused; double* loss_acc; uint32_t* counter;
 } lec_step_t;
 int lec_cone_step(const lec_step_t* s, void* stream);
 

@@ -14,13 +14,13 @@ LIB_PATH = os.path.join(_HERE, "_lib", "liblec_b200.so")
 GEOM = {"euc": 0, "hyp": 1, "oe": 2}
 ROWS_NONE, ROWS_EUC_SOFTCLIP, ROWS_HYP_SHELL, ROWS_HYP_TANH, ROWS_HYP_TANH_FEAT = 0, 1, 2, 3, 4
 PREC_F32, PREC_F64CORE = 0, 1
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 EXPORTS = (
     "lec_abi_version", "lec_error_string", "lec_launch_count", "lec_rows_fwd", "lec_rows_bwd", "lec_reduce_replicas",
     "lec_pairs_flat",
     "lec_pairs_grouped", "lec_energy_dense", "lec_energy_dense_bwd", "lec_rsgd_update", "lec_p2p_publish",
-    "lec_rsgd_update_p2p", "lec_cone_step", "lec_score_topk", "lec_score_topk_ex", "lec_score_tc_supported",
+    "lec_rsgd_update_p2p", "lec_rsgd_update_rows", "lec_p2p_push", "lec_rsgd_update_rows_p2p", "lec_cone_step", "lec_score_topk", "lec_score_topk_ex", "lec_score_tc_supported",
     "lec_score_workspace_bytes", "lec_score_topk_tc", "lec_mt_seed", "lec_mt_uint32", "lec_mt_randbelow",
     "lec_sample_negatives", "lec_sample_negatives_philox", "lec_philox_below", "lec_f1_workspace_bytes", "lec_f1_sweep",
     "lec_classify_counts",
@@ -49,6 +49,7 @@ class LecStep(ctypes.Structure):
         ("rank", ctypes.c_int), ("slot", ctypes.c_int), ("tag", ctypes.c_uint32),
         ("loss_global", ctypes.c_void_p), ("error", ctypes.c_void_p),
         ("ev_pairs_start", ctypes.c_void_p), ("ev_pairs_stop", ctypes.c_void_p),
+        ("fused", ctypes.c_int), ("loss_acc", ctypes.c_void_p), ("counter", ctypes.c_void_p),
     ]
 
 
@@ -86,6 +87,12 @@ def lib():
         L.lec_p2p_publish.argtypes = [c_vp, c_vp, c_i64, c_i, c_i, c_i, ctypes.c_uint32, c_vp]
         L.lec_rsgd_update_p2p.argtypes = [c_vp, c_vp, c_i64, c_i, c_i, c_i, ctypes.c_uint32, c_i64, c_i, c_f, c_f, c_i,
                                           c_vp, c_vp, c_vp]
+        L.lec_rsgd_update_rows.argtypes = [c_vp, c_vp, c_i, c_i64, c_i, c_i, c_f, c_f, c_i, c_f, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                           c_vp]
+        L.lec_p2p_push.argtypes = [c_vp, c_i, c_i64, c_i, c_i, c_vp, c_vp, c_vp, c_i64, c_i, c_i, c_i, ctypes.c_uint32,
+                                   c_vp, c_vp]
+        L.lec_rsgd_update_rows_p2p.argtypes = [c_vp, c_vp, c_i64, c_i, c_i, c_i, ctypes.c_uint32, c_i64, c_i, c_i, c_f, c_f,
+                                               c_i, c_f, c_vp, c_vp, c_vp, c_vp, c_vp]
         L.lec_cone_step.argtypes = [ctypes.POINTER(LecStep), c_vp]
         L.lec_score_topk.argtypes = [c_i, c_i, c_vp, c_i64, c_vp, c_i64, c_i, c_f, c_vp, c_vp, c_i, c_i, c_vp, c_vp,
                                      c_vp, c_vp]

@@ -23,7 +23,11 @@ int rsgd_launch(float*, const float*, int, int64_t, int, int, float, float, int,
 int reduce_replicas_launch(const float*, int, int64_t, float*, cudaStream_t);
 int p2p_publish_launch(const double*, void* const*, int64_t, int, int, int, unsigned, cudaStream_t);
 int rsgd_p2p_launch(float*, void* const*, int64_t, int, int, int, unsigned, int64_t, int, float, float, int, double*, int*,
-                    cudaStream_t);
+                    int, float, float*, int, double*, cudaStream_t);
+int rsgd_rows_launch(float*, float*, int, int64_t, int, int, float, float, int, float, float*, double*, double*, double*,
+                     float*, cudaStream_t);
+int p2p_push_launch(float*, int, int64_t, int, int, double*, double*, void* const*, int64_t, int, int, int, unsigned,
+                    unsigned*, cudaStream_t);
 int score_launch(int, int, const float*, int64_t, const float*, int64_t, int, float, const int32_t*, const int32_t*,
                  int, int, float*, int64_t, int64_t, int32_t*, float*, cudaStream_t);
 
@@ -220,13 +224,72 @@ int lec_rsgd_update_p2p(float* table, void* const* peer_bufs, int64_t slot_float
     if (slot_floats < n * D + 2) return LEC_E_PEERS;
     if (lambda_mode != 0 && lambda_mode != 1) return LEC_E_ENUM;
     return rsgd_p2p_launch(table, peer_bufs, slot_floats, world, rank, slot, tag, n, D, lr, r_in, lambda_mode,
-                           loss_global_out, error_out, (cudaStream_t)stream);
+                           loss_global_out, error_out, 0, 0.f, nullptr, 0, nullptr, (cudaStream_t)stream);
+}
+
+int lec_rsgd_update_rows(float* table, float* grad_rows, int grad_replicas, int64_t n, int D, int ld, float lr, float r_in,
+                         int lambda_mode, float K, float* rows_out, double* aux_out, double* loss_acc, double* loss_step,
+                         float* grad_out, void* stream) {
+    if (!table || !grad_rows || !rows_out) return LEC_E_NULL;
+    if (grad_replicas < 1) return LEC_E_REPLICAS;
+    if (n < 0) return LEC_E_SIZE;
+    if (D < 1 || D > LEC_MAX_DIM || ld < D || (ld & 3)) return LEC_E_DIM;
+    if (lambda_mode != 0 && lambda_mode != 1) return LEC_E_ENUM;
+    return rsgd_rows_launch(table, grad_rows, grad_replicas, n, D, ld, lr, r_in, lambda_mode, K, rows_out, aux_out, loss_acc,
+                            loss_step, grad_out, (cudaStream_t)stream);
+}
+
+int lec_p2p_push(float* grad_rows, int grad_replicas, int64_t n, int D, int ld, double* loss_acc, double* loss_step,
+                 void* const* peer_bufs, int64_t slot_floats, int world, int rank, int slot, uint32_t tag,
+                 uint32_t* counter, void* stream) {
+    if (!grad_rows || !loss_acc || !counter) return LEC_E_NULL;
+    if (int e = check_peers(peer_bufs, slot_floats, world, rank, slot)) return e;
+    if (grad_replicas < 1) return LEC_E_REPLICAS;
+    if (n < 0) return LEC_E_SIZE;
+    if (D < 1 || D > LEC_MAX_DIM || ld < D || (ld & 3)) return LEC_E_DIM;
+    if (slot_floats < n * D + 2) return LEC_E_PEERS;
+    return p2p_push_launch(grad_rows, grad_replicas, n, D, ld, loss_acc, loss_step, peer_bufs, slot_floats, world, rank, slot,
+                           tag, counter, (cudaStream_t)stream);
+}
+
+int lec_rsgd_update_rows_p2p(float* table, void* const* peer_bufs, int64_t slot_floats, int world, int rank, int slot,
+                             uint32_t tag, int64_t n, int D, int ld, float lr, float r_in, int lambda_mode, float K,
+                             float* rows_out, double* aux_out, double* loss_global_out, int* error_out, void* stream) {
+    if (!table || !rows_out) return LEC_E_NULL;
+    if (int e = check_peers(peer_bufs, slot_floats, world, rank, slot)) return e;
+    if (n < 0) return LEC_E_SIZE;
+    if (D < 1 || D > LEC_MAX_DIM || ld < D || (ld & 3)) return LEC_E_DIM;
+    if (slot_floats < n * D + 2) return LEC_E_PEERS;
+    if (lambda_mode != 0 && lambda_mode != 1) return LEC_E_ENUM;
+    return rsgd_p2p_launch(table, peer_bufs, slot_floats, world, rank, slot, tag, n, D, lr, r_in, lambda_mode,
+                           loss_global_out, error_out, 1, K, rows_out, ld, aux_out, (cudaStream_t)stream);
 }
 
 int lec_cone_step(const lec_step_t* s, void* stream) {
     if (!s) return LEC_E_NULL;
     if (s->update != 0 && s->update != 1) return LEC_E_ENUM;
     if (!s->grad_rows || !s->loss) return LEC_E_NULL;
+    if (s->fused) {
+        if (s->update != 1 || s->row_mode != LEC_ROWS_HYP_SHELL) return LEC_E_ENUM;
+        if (!s->loss_acc) return LEC_E_NULL;
+        cudaStream_t st = (cudaStream_t)stream;
+        if (s->ev_pairs_start) cudaEventRecord((cudaEvent_t)s->ev_pairs_start, st);
+        int e = lec_pairs_grouped(s->geom, s->precision, s->rows, s->aux, s->n, s->D, s->ld, s->pos_from, s->pos_to, s->neg_to,
+                                  s->neg_from, s->idx_bytes, s->B, s->N, s->w_pos, s->w_neg, s->K, s->alpha, s->E_pos, s->E_neg,
+                                  s->loss_acc, s->grad_rows, s->grad_replicas, stream);
+        if (s->ev_pairs_stop) cudaEventRecord((cudaEvent_t)s->ev_pairs_stop, st);
+        if (e) return e;
+        if (s->world > 1) {
+            e = lec_p2p_push(s->grad_rows, s->grad_replicas, s->n, s->D, s->ld, s->loss_acc, s->loss, s->peer_bufs,
+                             s->slot_floats, s->world, s->rank, s->slot, s->tag, s->counter, stream);
+            if (e) return e;
+            return lec_rsgd_update_rows_p2p(s->table, s->peer_bufs, s->slot_floats, s->world, s->rank, s->slot, s->tag, s->n,
+                                            s->D, s->ld, s->lr, s->r_in, s->lambda_mode, s->K, s->rows, s->aux,
+                                            s->loss_global, s->error, stream);
+        }
+        return lec_rsgd_update_rows(s->table, s->grad_rows, s->grad_replicas, s->n, s->D, s->ld, s->lr, s->r_in,
+                                    s->lambda_mode, s->K, s->rows, s->aux, s->loss_acc, s->loss, s->grad_table, stream);
+    }
     int e = lec_rows_fwd(s->table, s->n, s->D, s->row_mode, s->geom, s->K, s->rows, s->ld, s->aux, s->grad_rows,
                          s->grad_replicas, s->loss, stream);
     if (e) return e;

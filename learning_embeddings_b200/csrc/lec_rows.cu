@@ -14,10 +14,18 @@ struct RowsArgs {
 };
 
 // sum of the gradient replicas at one element
+// Sum of the gradient replicas of one element.  Four independent partial sums keep eight loads in flight (the
+// replicas sit n*ld floats apart in L2); the order is fixed, so every caller gets the same bits.
 __device__ __forceinline__ float rsum(const float* g, int replicas, int64_t stride) {
-    float v = g[0];
-    for (int r = 1; r < replicas; ++r) v += g[r * stride];
-    return v;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int r = 0;
+#pragma unroll 2
+    for (; r + 4 <= replicas; r += 4) {
+        const float a = g[r * stride], b = g[(r + 1) * stride], c = g[(r + 2) * stride], d = g[(r + 3) * stride];
+        s0 += a; s1 += b; s2 += c; s3 += d;
+    }
+    for (; r < replicas; ++r) s0 += g[r * stride];
+    return (s0 + s1) + (s2 + s3);
 }
 
 template <int TT>
@@ -176,6 +184,11 @@ struct RsgdArgs {
     // peer-memory mode (lec_rsgd_update_p2p): the gradient is the sum over ranks of peer[p][row*D + d]
     int world; int rank; int slot; unsigned tag; int64_t slot_floats;
     const float* peer[kMaxPeers]; double* loss_out; int* error_out;
+    int local_sources;   // peer mode: 1 = every rank PUSHED its gradient into my buffer (slot[2][world][slot_floats])
+    // fused row transform of the updated table (lec_rsgd_update_rows): Embedder.forward of order_embeddings_h.py:205-228
+    // for the next step, its per-row aperture terms, and the clearing of the gradient replicas
+    float* rows_out; int ld_rows; double* aux_out; float K; float* zero_grad;
+    double* loss_acc; double* loss_step;   // *loss_step = *loss_acc; *loss_acc = 0   (single-GPU fused step)
 };
 
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
@@ -192,13 +205,20 @@ __device__ __forceinline__ const unsigned* p2p_flags(const float* buf, int64_t s
     return reinterpret_cast<const unsigned*>(buf + 2 * slot_floats);
 }
 
+// where rank p's partial gradient of the current slot lives: in p's own buffer (pull layout, slot[2][slot_floats]) or,
+// after lec_p2p_push, in MY buffer (push layout, slot[2][world][slot_floats])
+__device__ __forceinline__ const float* p2p_src(const RsgdArgs& a, int p) {
+    return a.local_sources ? a.peer[a.rank] + ((int64_t)a.slot * a.world + p) * a.slot_floats
+                           : a.peer[p] + (int64_t)a.slot * a.slot_floats;
+}
+
 template <int TT, int E, bool P2P>
 __global__ void __launch_bounds__(kThreads) rsgd_kernel(const RsgdArgs a) {
     if (P2P) {
         // wait until every rank has published its partial gradient of this step into slot a.slot
         __shared__ int s_ok;
         if (threadIdx.x == 0) {
-            const unsigned* flags = p2p_flags(a.peer[a.rank], a.slot_floats) + a.slot * a.world;
+            const unsigned* flags = p2p_flags(a.peer[a.rank], a.slot_floats * (a.local_sources ? a.world : 1)) + a.slot * a.world;
             int ok = 1;
             const long long t0 = clock64();
             for (int p = 0; p < a.world; ++p) {
@@ -211,7 +231,7 @@ __global__ void __launch_bounds__(kThreads) rsgd_kernel(const RsgdArgs a) {
             if (blockIdx.x == 0 && a.loss_out) {
                 double l = 0.0;
                 for (int p = 0; p < a.world; ++p)
-                    l += __ldcv(reinterpret_cast<const double*>(a.peer[p] + a.slot * a.slot_floats + a.slot_floats - 2));
+                    l += __ldcv(reinterpret_cast<const double*>(p2p_src(a, p) + a.slot_floats - 2));
                 *a.loss_out = l;
             }
         }
@@ -239,7 +259,7 @@ __global__ void __launch_bounds__(kThreads) rsgd_kernel(const RsgdArgs a) {
                 float acc = 0.f;
                 if (d < D)
                     for (int p = 0; p < a.world; ++p)   // fixed rank order: every rank computes the identical sum
-                        acc += __ldcv(a.peer[p] + a.slot * a.slot_floats + rc * (int64_t)D + d);
+                        acc += __ldcv(p2p_src(a, p) + rc * (int64_t)D + d);
                 gv[j] = acc;
             } else {
                 gv[j] = (d < D) ? rsum(g + d, a.replicas, a.replica_stride) : 0.f;
@@ -289,19 +309,68 @@ __global__ void __launch_bounds__(kThreads) rsgd_kernel(const RsgdArgs a) {
         const float rn = (float)sqrt(tsumd<TT>(rr));
         float mul, add, div;
         shell_factor(rn, a.r_in, false, mul, add, div);
-        if (valid) {
-            float* go = a.grad_out ? a.grad_out + row * (int64_t)D : nullptr;
+        float* go = (valid && a.grad_out) ? a.grad_out + row * (int64_t)D : nullptr;
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+            const int d = lane + TT * j;
+            float res = tv[j];
+            if (mul != 1.f || div != 1.f) res = (res / div) * mul;
+            tv[j] = (d < D) ? res : 0.f;     // the updated row stays in registers for the fused transform
+            if (valid && d < D) {
+                w[d] = res;
+                if (go) go[d] = gv[j];
+            }
+        }
+        if (a.rows_out) {
+            // ---- rows_fwd_kernel, LEC_ROWS_HYP_SHELL, on the row just written (same operation order, so the fused and
+            //      the separate launch produce the same bits) ----
+            float ss = 0.f;
+#pragma unroll
+            for (int j = 0; j < E; ++j) {
+                if (lane + TT * j < D) { const float v = tv[j] + 1e-15f; ss = fmaf(v, v, ss); }
+            }
+            ss = tsum<TT>(ss);
+            float m2, a2, d2;
+            shell_factor(sqrtf(ss), a.r_in, false, m2, a2, d2);
+            double A = 0.0;
+            float* o = a.rows_out + rc * (int64_t)a.ld_rows;
+            float* zo = a.zero_grad ? a.zero_grad + rc * (int64_t)a.ld_rows : nullptr;
 #pragma unroll
             for (int j = 0; j < E; ++j) {
                 const int d = lane + TT * j;
-                if (d < D) {
-                    float res = tv[j];
-                    if (mul != 1.f || div != 1.f) res = (res / div) * mul;
-                    w[d] = res;
-                    if (go) go[d] = gv[j];
+                if (d < a.ld_rows) {
+                    float v = 0.f;
+                    if (d < D) {
+                        v = tv[j] + 1e-15f;
+                        if (m2 != 1.f || d2 != 1.f) v = ((a2 + v) / d2) * m2;
+                    }
+                    A += (double)v * (double)v;
+                    if (valid) {
+                        o[d] = v;
+                        if (zo)
+                            for (int rr = 0; rr < a.replicas; ++rr) zo[rr * a.replica_stride + d] = 0.f;
+                    }
                 }
             }
+            for (int d = lane + TT * E; d < a.ld_rows; d += TT) {   // pad columns beyond the register tile (D <= 2)
+                if (valid) {
+                    o[d] = 0.f;
+                    if (zo)
+                        for (int rr = 0; rr < a.replicas; ++rr) zo[rr * a.replica_stride + d] = 0.f;
+                }
+            }
+            A = tsumd<TT>(A);
+            if (valid && lane == 0 && a.aux_out) {
+                const Aux<double> x = row_aux<double>(LEC_GEOM_HYP, A, a.K);
+                double2* dst = reinterpret_cast<double2*>(a.aux_out + 4 * row);
+                dst[0] = make_double2(x.A, x.ria);
+                dst[1] = make_double2(x.t0, x.t1);
+            }
         }
+    }
+    if (a.loss_acc && blockIdx.x == 0 && threadIdx.x == 0) {
+        if (a.loss_step) *a.loss_step = *a.loss_acc;
+        *a.loss_acc = 0.0;
     }
 }
 
@@ -424,10 +493,94 @@ int p2p_publish_launch(const double* loss_local, void* const* peer_bufs, int64_t
     return (int)cudaGetLastError();
 }
 
+// ---- push exchange: every rank writes its partial gradient into EVERY rank's buffer --------------------------------
+// The replica sum of each element (straight-through rows: that IS d loss / d table) is stored into slot[slot][rank] of
+// all `world` buffers -- remote stores are fire-and-forget, so the NVLink latency is paid once, behind the kernel, not
+// per dependent load -- and the replicas are cleared on the way.  The last block to finish (device counter) stores
+// the loss and release-stores the flags; the update kernel then reads local memory only.
+struct PushArgs {
+    float* grad_rows; int replicas; int64_t replica_stride; int64_t n; int D; int ld;
+    double* loss_acc; double* loss_step;
+    int world, rank, slot; unsigned tag; int64_t slot_floats; float* peer[kMaxPeers];
+    unsigned* counter;
+};
+
+__global__ void __launch_bounds__(kThreads) p2p_push_kernel(const PushArgs a) {
+    const int64_t total = a.n * (int64_t)a.ld;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    const int64_t dst0 = ((int64_t)a.slot * a.world + a.rank) * a.slot_floats;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += stride) {
+        const int64_t row = i / a.ld;
+        const int d = (int)(i - row * a.ld);
+        float* g = a.grad_rows + i;
+        if (d < a.D) {
+            const float v = rsum(g, a.replicas, a.replica_stride);
+            for (int p = 0; p < a.world; ++p) a.peer[p][dst0 + row * a.D + d] = v;
+        }
+        for (int r = 0; r < a.replicas; ++r) g[r * a.replica_stride] = 0.f;
+    }
+    __threadfence_system();     // this thread's remote stores are performed before its block is counted
+    __syncthreads();
+    __shared__ unsigned s_last;
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(a.counter, 1u);
+        s_last = (prev == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();            // all blocks' counts (and the stores fenced before them) are visible here
+    if (threadIdx.x == 0) {
+        *a.counter = 0;
+        const double l = *a.loss_acc;
+        if (a.loss_step) *a.loss_step = l;
+        *a.loss_acc = 0.0;
+        for (int p = 0; p < a.world; ++p)
+            *reinterpret_cast<double*>(a.peer[p] + dst0 + a.slot_floats - 2) = l;
+        __threadfence_system();
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < a.world) {
+        const int p = threadIdx.x;
+        unsigned* flags = reinterpret_cast<unsigned*>(a.peer[p] + 2 * (int64_t)a.world * a.slot_floats) + a.slot * a.world;
+        st_release_sys(flags + a.rank, a.tag);
+    }
+}
+
+int p2p_push_launch(float* grad_rows, int replicas, int64_t n, int D, int ld, double* loss_acc, double* loss_step,
+                    void* const* peer_bufs, int64_t slot_floats, int world, int rank, int slot, unsigned tag,
+                    unsigned* counter, cudaStream_t st) {
+    PushArgs a{};
+    a.grad_rows = grad_rows; a.replicas = replicas; a.replica_stride = n * (int64_t)ld; a.n = n; a.D = D; a.ld = ld;
+    a.loss_acc = loss_acc; a.loss_step = loss_step;
+    a.world = world; a.rank = rank; a.slot = slot; a.tag = tag; a.slot_floats = slot_floats; a.counter = counter;
+    for (int p = 0; p < world; ++p) a.peer[p] = static_cast<float*>(peer_bufs[p]);
+    const int64_t total = n * (int64_t)ld;
+    int64_t need = (total + kThreads - 1) / kThreads;
+    const int64_t cap = (int64_t)sm_count() * 4;
+    if (need < 1) need = 1;
+    p2p_push_kernel<<<(int)(need < cap ? need : cap), kThreads, 0, st>>>(a);
+    ++g_launches;
+    return (int)cudaGetLastError();
+}
+
+int rsgd_rows_launch(float* table, float* grad_rows, int replicas, int64_t n, int D, int ld, float lr, float r_in,
+                     int lambda_mode, float K, float* rows_out, double* aux_out, double* loss_acc, double* loss_step,
+                     float* grad_out, cudaStream_t st) {
+    RsgdArgs a{};
+    a.table = table; a.grad = grad_rows; a.n = n; a.D = D; a.ld_g = ld; a.lr = lr; a.r_in = r_in;
+    a.lambda_mode = lambda_mode; a.grad_out = grad_out; a.replicas = replicas; a.replica_stride = n * (int64_t)ld;
+    a.world = 0;
+    a.rows_out = rows_out; a.ld_rows = ld; a.aux_out = aux_out; a.K = K; a.zero_grad = grad_rows;
+    a.loss_acc = loss_acc; a.loss_step = loss_step;
+    return rsgd_dispatch(a, st);
+}
+
 int rsgd_p2p_launch(float* table, void* const* peer_bufs, int64_t slot_floats, int world, int rank, int slot,
                     unsigned tag, int64_t n, int D, float lr, float r_in, int lambda_mode, double* loss_out,
-                    int* error_out, cudaStream_t st) {
+                    int* error_out, int local_sources, float K, float* rows_out, int ld_rows, double* aux_out,
+                    cudaStream_t st) {
     RsgdArgs a{};
+    a.local_sources = local_sources; a.K = K; a.rows_out = rows_out; a.ld_rows = ld_rows; a.aux_out = aux_out;
     a.table = table; a.grad = nullptr; a.n = n; a.D = D; a.ld_g = D; a.lr = lr; a.r_in = r_in;
     a.lambda_mode = lambda_mode; a.grad_out = nullptr; a.replicas = 1; a.replica_stride = 0;
     a.world = world; a.rank = rank; a.slot = slot; a.tag = tag; a.slot_floats = slot_floats;

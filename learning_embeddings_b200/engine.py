@@ -15,6 +15,8 @@ Euclidean one) with the negatives already drawn:
 Index batches use the compact training layout of include/lec_b200.h (lec_pairs_grouped) as one int32
 block [pos_from | pos_to | neg_to | neg_from] so a step's indices travel host->device in one copy.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -71,6 +73,13 @@ class ConeStep:
         self.E_pos = torch.empty(self.max_groups, device=dev, dtype=torch.float32)
         self.E_neg = torch.empty((self.max_groups, 2 * self.n_neg), device=dev, dtype=torch.float32)
         self.loss = torch.zeros(1, device=dev, dtype=torch.float64)
+        # Fused step (lec_cone_step with fused = 1): RSGD on straight-through rows is followed, in the same launch, by
+        # the row transform the next step starts with -- two launches per step (pairs, update+rows) instead of three.
+        # The pair kernel then adds into loss_acc and the update moves it to `loss`.
+        self.loss_acc = torch.zeros(1, device=dev, dtype=torch.float64)
+        self.fused = (self.update == "rsgd" and self.row_mode == N.ROWS_HYP_SHELL
+                      and os.environ.get("LEC_FUSED_STEP", "1") != "0")
+        self._rows_valid = False
         # host->device staging: `depth` slots so that the copy of step i+1 overlaps the kernels of step i
         self.depth = 2
         self._idx_bytes_dev = [torch.empty(self.max_groups * (2 + 2 * self.n_neg) * 4, device=dev, dtype=torch.uint8)
@@ -109,6 +118,7 @@ class ConeStep:
         B = int(pos_from.numel())
         if B > self.max_groups:
             raise N.LecError("batch of %d positives exceeds max_groups=%d" % (B, self.max_groups))
+        self._rows_valid = False   # the replicas now hold a gradient the fused step did not put there
         N.check(lib.lec_rows_fwd(N._p(self.table), self.n, self.D, self.row_mode, N.GEOM[self.geom], self.K,
                                  N._p(self.rows), self.ld, N._p(self.aux), N._p(self.grad_rows), self.replicas,
                                  N._p(self.loss), st), "lec_rows_fwd")
@@ -125,8 +135,14 @@ class ConeStep:
             ev[1].record()
         return B
 
+    def invalidate_rows(self):
+        """Call after changing `table` from outside the engine (loading weights, a manual update): the fused step
+        otherwise reuses the transformed rows its previous update left behind."""
+        self._rows_valid = False
+
     def reduce_and_update(self):
         lib, st = N.lib(), N.stream_ptr(self.table.device)
+        self._rows_valid = False
         multi = self.pg is not None and torch.distributed.get_world_size(self.pg) > 1
         if not multi and self.update == "rsgd" and self.row_mode == N.ROWS_HYP_SHELL:
             # straight-through rows: d/dtable == d/drows; the update sums the replicas itself
@@ -141,9 +157,9 @@ class ConeStep:
             N.check(lib.lec_rows_bwd(N._p(self.table), N._p(self.grad_rows), self.replicas, self.n, self.D, self.ld,
                                      self.row_mode, self.K, ctypes.c_void_p(px.my_slot_ptr(slot)), 0, st),
                     "lec_rows_bwd")
-            N.check(lib.lec_p2p_publish(N._p(self.loss), px.peer_ptrs, px.slot_floats, px.world, px.rank, slot, tag, st),
+            N.check(lib.lec_p2p_publish(N._p(self.loss), px.peer_ptrs_pull, px.slot_floats, px.world, px.rank, slot, tag, st),
                     "lec_p2p_publish")
-            N.check(lib.lec_rsgd_update_p2p(N._p(self.table), px.peer_ptrs, px.slot_floats, px.world, px.rank, slot,
+            N.check(lib.lec_rsgd_update_p2p(N._p(self.table), px.peer_ptrs_pull, px.slot_floats, px.world, px.rank, slot,
                                             tag, self.n, self.D, self.lr, self.r_in, 0, N._p(self.loss_global),
                                             N._p(px.error), st), "lec_rsgd_update_p2p")
             px.step += 1
@@ -190,9 +206,12 @@ class ConeStep:
         s.N = self.n_neg
         s.E_pos, s.E_neg, s.loss = self.E_pos.data_ptr(), self.E_neg.data_ptr(), self.loss.data_ptr()
         s.world = 0
+        s.fused = 1 if self.fused else 0
+        s.loss_acc = self.loss_acc.data_ptr()
         if self.comm == "p2p":
             px = self.px
-            s.peer_bufs = ctypes.cast(px.peer_ptrs, ctypes.c_void_p)
+            s.counter = px.counter.data_ptr()
+            s.peer_bufs = ctypes.cast(px.peer_ptrs if self.fused else px.peer_ptrs_pull, ctypes.c_void_p)
             s.slot_floats, s.world, s.rank = px.slot_floats, px.world, px.rank
             s.loss_global, s.error = self.loss_global.data_ptr(), px.error.data_ptr()
         return s
@@ -222,7 +241,15 @@ class ConeStep:
             else:
                 s.ev_pairs_start, s.ev_pairs_stop = None, None
             import ctypes
+            if self.fused and not self._rows_valid:
+                # first step (or the table changed behind the engine's back): rows, aux, cleared replicas and loss
+                N.check(N.lib().lec_rows_fwd(N._p(self.table), self.n, self.D, self.row_mode, N.GEOM[self.geom], self.K,
+                                             N._p(self.rows), self.ld, N._p(self.aux), N._p(self.grad_rows), self.replicas,
+                                             N._p(self.loss_acc), N.stream_ptr(self.table.device)), "lec_rows_fwd")
+                self._rows_valid = True
             N.check(N.lib().lec_cone_step(ctypes.byref(s), N.stream_ptr(self.table.device)), "lec_cone_step")
+            if not self.fused:
+                self._rows_valid = False
             if self.comm == "p2p":
                 self.px.step += 1
             return self.loss

@@ -18,7 +18,9 @@ def default_replicas(n_rows, ld):
 
     Same-address L2 reductions serialise, so a small hot table (ETHEC: 723 rows) is replicated; a big
     table (82 K rows) has little per-address contention and stays single.  Budget: 2 M floats."""
-    return int(max(1, min(32, (2 << 20) // max(1, int(n_rows) * int(ld)))))
+    import os
+    cap = int(os.environ.get("LEC_REPLICAS", "32"))
+    return int(max(1, min(cap, (2 << 20) // max(1, int(n_rows) * int(ld)))))
 
 
 def reduce_replicas(grad_rows):

@@ -32,7 +32,10 @@ def allreduce_grad_and_loss(grad_table, loss, group=None):
 class PeerExchange:
     """Exchange buffers for the fused all-reduce + RSGD update (include/lec_b200.h: lec_p2p_publish,
     lec_rsgd_update_p2p): one buffer per rank, mapped by every rank through torch symmetric memory
-    (CUDA IPC over NVLink / NVSwitch).  Layout: float slot[2][slot_floats]; uint32 flag[2][world]."""
+    (CUDA IPC over NVLink / NVSwitch).  Two regions per buffer, one per protocol of include/lec_b200.h:
+    push (lec_p2p_push / lec_rsgd_update_rows_p2p)   float slot[2][world][slot_floats]; uint32 flag[2][world]
+    pull (lec_p2p_publish / lec_rsgd_update_p2p)     float slot[2][slot_floats];        uint32 flag[2][world]
+    `peer_ptrs` points at the push regions, `peer_ptrs_pull` at the pull regions."""
 
     def __init__(self, n, D, device, group):
         import ctypes
@@ -40,8 +43,10 @@ class PeerExchange:
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.slot_floats = (n * D + 2 + 3) // 4 * 4
-        total = 2 * self.slot_floats + 2 * self.world
-        total = (total + 3) // 4 * 4
+        push = (2 * self.world * self.slot_floats + 2 * self.world + 3) // 4 * 4
+        pull = (2 * self.slot_floats + 2 * self.world + 3) // 4 * 4
+        self.pull_offset = push      # floats
+        total = push + pull
         self.buf = symm_mem.empty(total, dtype=torch.float32, device=device)
         name = getattr(group, "group_name", None)
         try:
@@ -55,6 +60,8 @@ class PeerExchange:
         if len(ptrs) != self.world or ptrs[self.rank] != self.buf.data_ptr():
             raise RuntimeError("symmetric memory rendezvous returned unexpected peer pointers")
         self.peer_ptrs = (ctypes.c_void_p * self.world)(*ptrs)
+        self.peer_ptrs_pull = (ctypes.c_void_p * self.world)(*[q + 4 * self.pull_offset for q in ptrs])
+        self.counter = torch.zeros(1, dtype=torch.int32, device=device)   # last-block counter of lec_p2p_push
         self.step = 0
         self.error = torch.zeros(1, dtype=torch.int32, device=device)
 
@@ -62,4 +69,4 @@ class PeerExchange:
         return self.step % 2, self.step + 1
 
     def my_slot_ptr(self, slot):
-        return self.buf.data_ptr() + 4 * slot * self.slot_floats
+        return self.buf.data_ptr() + 4 * (self.pull_offset + slot * self.slot_floats)

@@ -33,12 +33,16 @@ def main():
     W0 = (0.0990195 + 0.05 * torch.rand(h.n, 1, generator=g)) * w / w.norm(dim=1, keepdim=True)
     to_dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
     ok = True
-    for step_count, comm in ((1, "nccl"), (3, "nccl"), (1, "auto"), (4, "auto")):
+    # "auto" = fused push exchange (lec_p2p_push + lec_rsgd_update_rows_p2p); "pull" = the three-launch peer-load variant
+    for step_count, comm in ((1, "nccl"), (3, "nccl"), (1, "auto"), (4, "auto"), (5, "auto"), (3, "pull")):
         # sharded
         Ws = W0.to(dev).clone()
-        eng = ConeStep(Ws, "hyp", Nn, B, K=0.1, alpha=0.05, lr=0.01, process_group=dist.group.WORLD, comm=comm)
+        eng = ConeStep(Ws, "hyp", Nn, B, K=0.1, alpha=0.05, lr=0.01, process_group=dist.group.WORLD,
+                       comm="auto" if comm == "pull" else comm)
+        if comm == "pull":
+            eng.fused = False
         if rank == 0:
-            print("comm requested %s -> %s %s" % (comm, eng.comm, eng.comm_note), flush=True)
+            print("comm requested %s -> %s fused=%s %s" % (comm, eng.comm, eng.fused, eng.comm_note), flush=True)
         su, sv, snt, snf = sharding.shard_groups(u, v, nt, nf, rank, world)
         for _ in range(step_count):
             eng.step_device(to_dev(su), to_dev(sv), to_dev(snt), to_dev(snf))

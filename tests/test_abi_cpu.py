@@ -23,7 +23,7 @@ def test_library_exports_every_header_symbol():
     for n in names:
         assert hasattr(lib, n), n
     assert sorted(_native.EXPORTS) == names
-    assert lib.lec_abi_version() == _native.ABI_VERSION == 10
+    assert lib.lec_abi_version() == _native.ABI_VERSION == 11
 
 
 def test_argument_validation_codes():

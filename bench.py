@@ -368,7 +368,9 @@ def run_cfg2(args):
     sync_all()
     t0.record()
     for i in range(args.steps):
-        eng.kernel_events = kev[i]
+        # the pair kernel is bracketed by CUDA events on every 4th step only: two event records per step sit between
+        # back-to-back launches and cost more than they measure
+        eng.kernel_events = kev[i] if i % 4 == 0 else None
         dev_step(i)
     t1.record()
     sync_all()
@@ -376,7 +378,7 @@ def run_cfg2(args):
     eng.kernel_events = None
     lec_launches = _native.launch_count() - launches0
     elapsed_ms = t0.elapsed_time(t1)
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    kernel_ms = float(np.mean([a.elapsed_time(b) for i, (a, b) in enumerate(kev) if i % 4 == 0]))
 
     def max_ranks(ms):
         if world > 1:
@@ -770,7 +772,9 @@ def main():
     sync_all()
     t0.record()
     for i in range(args.steps):
-        eng.kernel_events = kev[i]
+        # the pair kernel is bracketed by CUDA events on every 4th step only: two event records per step sit between
+        # back-to-back launches and cost more than they measure
+        eng.kernel_events = kev[i] if i % 4 == 0 else None
         dev_step(i)
     t1.record()
     sync_all()
@@ -778,7 +782,7 @@ def main():
     eng.kernel_events = None
     lec_launches = _native.launch_count() - launches0
     elapsed_ms = t0.elapsed_time(t1)
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    kernel_ms = float(np.mean([a.elapsed_time(b) for i, (a, b) in enumerate(kev) if i % 4 == 0]))
     final_loss = float(eng.global_loss().item())
     if world > 1:
         tt = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)

@@ -3,6 +3,7 @@
 
 namespace lec {
 unsigned long long g_launches = 0;
+thread_local int t_pdl = 0;
 
 int launch_flat_euc32(const FlatArgs&, cudaStream_t);
 int launch_flat_hyp32(const FlatArgs&, cudaStream_t);
@@ -272,6 +273,10 @@ int lec_cone_step(const lec_step_t* s, void* stream) {
     if (s->fused) {
         if (s->update != 1 || s->row_mode != LEC_ROWS_HYP_SHELL) return LEC_E_ENUM;
         if (!s->loss_acc) return LEC_E_NULL;
+        struct PdlScope {   // the kernels of this step are launched as programmatic dependents of one another
+            PdlScope() { static const int on = [] { const char* e = getenv("LEC_PDL"); return e ? atoi(e) : 1; }(); t_pdl = on; }
+            ~PdlScope() { t_pdl = 0; }
+        } pdl_scope;
         cudaStream_t st = (cudaStream_t)stream;
         if (s->ev_pairs_start) cudaEventRecord((cudaEvent_t)s->ev_pairs_start, st);
         int e = lec_pairs_grouped(s->geom, s->precision, s->rows, s->aux, s->n, s->D, s->ld, s->pos_from, s->pos_to, s->neg_to,

@@ -18,6 +18,33 @@ constexpr float kClampEps = 1e-5f;   // acos/asin clamp (order_embeddings_h.py:1
 
 extern unsigned long long g_launches;  // host-side counter (lec_api.cu)
 
+// Programmatic dependent launch.  lec_cone_step sets t_pdl around its launches: each kernel of the step is then
+// launched with programmatic stream serialisation, i.e. its blocks may become resident while the previous kernel of the
+// stream drains, and park in pdl_wait() -- which returns once that kernel has completed and flushed -- so the launch
+// latency between the two or three kernels of a step is hidden.  A kernel launched without the attribute sees both
+// instructions as no-ops.
+extern thread_local int t_pdl;
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename Arg>
+inline void launch_step_kernel(void (*kern)(const Arg), int grid, int block, cudaStream_t st, const Arg& a) {
+    if (!t_pdl) {
+        kern<<<grid, block, 0, st>>>(a);
+        return;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute at{};
+    at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, a);
+}
+
 template <int V>
 struct Vec {
     float4 c[V];

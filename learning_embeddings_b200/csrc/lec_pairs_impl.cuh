@@ -153,6 +153,8 @@ template <int CORE, int T, int V, bool GRAD>
 __global__ void __launch_bounds__(kThreads, LEC_GROUPED_MINBLOCKS) pairs_grouped_kernel(const GroupArgs a) {
     using Tr = CoreTraits<CORE>;
     using Acc = typename Tr::Acc;
+    pdl_launch_dependents();   // the update kernel may take its (few) SM slots now; it parks in pdl_wait()
+    pdl_wait();                // rows / aux / cleared replicas of the previous update are complete
     const int lane_t = threadIdx.x % T;
     const int64_t n_teams = (int64_t)gridDim.x * (kThreads / T);
     const int64_t team = (int64_t)blockIdx.x * (kThreads / T) + threadIdx.x / T;
@@ -406,8 +408,8 @@ int launch_grouped_tv(const GroupArgs& a0, cudaStream_t st) {
     }();
     a.split = choose_split(a.B, a.N, (int64_t)sm_count() * resident_blocks * (kThreads / T));
     const int grid = grid_for(a.B * a.split, kThreads / T, 8);
-    if (a.grad_rows) pairs_grouped_kernel<CORE, T, V, true><<<grid, kThreads, 0, st>>>(a);
-    else pairs_grouped_kernel<CORE, T, V, false><<<grid, kThreads, 0, st>>>(a);
+    if (a.grad_rows) launch_step_kernel(pairs_grouped_kernel<CORE, T, V, true>, grid, kThreads, st, a);
+    else launch_step_kernel(pairs_grouped_kernel<CORE, T, V, false>, grid, kThreads, st, a);
     ++g_launches;
     return (int)cudaGetLastError();
 }

@@ -40,8 +40,42 @@ __device__ __forceinline__ void shell_factor(float r, float r_in, bool feat, flo
     if (r >= 1.0f) { mul = (float)(1.0 - 1e-5); div = r; add = 0.f; }
 }
 
+// Per-row aperture terms, batched.  row_aux<double> is an fp64 sqrt + division + asin (several hundred issue slots) and
+// only ONE lane of a row's team has to run it, so inline it occupied a whole warp for 32 / TT rows at a time (cfg4,
+// 82 K rows x 50: ~35 us of an 83 us launch).  Teams park |row|^2 in shared memory instead; every kThreads rows (or at the
+// end) the block computes one row per THREAD.  Every thread of the block must call push()/flush() the same number of times.
+struct AuxBatch {
+    double A[kThreads];
+    int64_t row[kThreads];
+};
+template <int TT>
+__device__ __forceinline__ void aux_flush(AuxBatch& b, int& fill, int geom, float K, double* __restrict__ aux) {
+    __syncthreads();
+    if ((int)threadIdx.x < fill && b.row[threadIdx.x] >= 0) {
+        const Aux<double> x = row_aux<double>(geom, b.A[threadIdx.x], K);
+        double2* dst = reinterpret_cast<double2*>(aux + 4 * b.row[threadIdx.x]);
+        dst[0] = make_double2(x.A, x.ria);
+        dst[1] = make_double2(x.t0, x.t1);
+    }
+    __syncthreads();
+    fill = 0;
+}
+template <int TT>
+__device__ __forceinline__ void aux_push(AuxBatch& b, int& fill, double A, int64_t row, bool valid, int geom, float K,
+                                         double* __restrict__ aux) {
+    constexpr int kTeams = kThreads / TT;
+    if (threadIdx.x % TT == 0) {
+        b.A[fill + threadIdx.x / TT] = A;
+        b.row[fill + threadIdx.x / TT] = valid ? row : -1;
+    }
+    fill += kTeams;
+    if (fill + kTeams > kThreads) aux_flush<TT>(b, fill, geom, K, aux);
+}
+
 template <int TT>
 __global__ void __launch_bounds__(kThreads) rows_fwd_kernel(const RowsArgs a) {
+    __shared__ AuxBatch s_aux;
+    int aux_fill = 0;
     const int lane = threadIdx.x % TT;
     const int64_t n_teams = (int64_t)gridDim.x * (kThreads / TT);
     const int64_t team = (int64_t)blockIdx.x * (kThreads / TT) + threadIdx.x / TT;
@@ -105,14 +139,10 @@ __global__ void __launch_bounds__(kThreads) rows_fwd_kernel(const RowsArgs a) {
         }
         if (a.aux) {
             A = tsumd<TT>(A);
-            if (valid && lane == 0) {
-                const Aux<double> x = row_aux<double>(a.geom, A, a.K);
-                double2* dst = reinterpret_cast<double2*>(a.aux + 4 * row);
-                dst[0] = make_double2(x.A, x.ria);
-                dst[1] = make_double2(x.t0, x.t1);
-            }
+            aux_push<TT>(s_aux, aux_fill, A, row, valid, a.geom, a.K, a.aux);
         }
     }
+    if (a.aux) aux_flush<TT>(s_aux, aux_fill, a.geom, a.K, a.aux);
 }
 
 template <int TT>
@@ -177,6 +207,7 @@ __global__ void __launch_bounds__(kThreads) rows_bwd_kernel(const RowsArgs a) {
 // the update stays accurate when |w| is close to 1 (the denominators there cancel heavily).
 // ------------------------------------------------------------------------------------------------
 constexpr int kMaxPeers = 16;
+static void hyp_constants(float K, float& r_in, float& c0);
 
 struct RsgdArgs {
     float* table; const float* grad; int64_t n; int D; int ld_g; float lr; float r_in; int lambda_mode;
@@ -188,6 +219,7 @@ struct RsgdArgs {
     // fused row transform of the updated table (lec_rsgd_update_rows): Embedder.forward of order_embeddings_h.py:205-228
     // for the next step, its per-row aperture terms, and the clearing of the gradient replicas
     float* rows_out; int ld_rows; double* aux_out; float K; float* zero_grad;
+    float r_in_rows;     // inner radius as lec_rows_fwd derives it from K (the update's own r_in is the caller's)
     double* loss_acc; double* loss_step;   // *loss_step = *loss_acc; *loss_acc = 0   (single-GPU fused step)
 };
 
@@ -214,6 +246,10 @@ __device__ __forceinline__ const float* p2p_src(const RsgdArgs& a, int p) {
 
 template <int TT, int E, bool P2P>
 __global__ void __launch_bounds__(kThreads) rsgd_kernel(const RsgdArgs a) {
+    __shared__ AuxBatch s_aux;
+    int aux_fill = 0;
+    pdl_launch_dependents();
+    pdl_wait();   // the pair kernel's (or the push kernel's) stores and reductions are complete
     if (P2P) {
         // wait until every rank has published its partial gradient of this step into slot a.slot
         __shared__ int s_ok;
@@ -314,7 +350,9 @@ __global__ void __launch_bounds__(kThreads) rsgd_kernel(const RsgdArgs a) {
         for (int j = 0; j < E; ++j) {
             const int d = lane + TT * j;
             float res = tv[j];
-            if (mul != 1.f || div != 1.f) res = (res / div) * mul;
+            // __fmul_rn / __fadd_rn below: the stored table value is rounded to fp32 BEFORE the row transform adds its
+            // 1e-15, exactly as when a separate lec_rows_fwd reloads it (no FMA contraction across the two stages)
+            if (mul != 1.f || div != 1.f) res = __fmul_rn(res / div, mul);
             tv[j] = (d < D) ? res : 0.f;     // the updated row stays in registers for the fused transform
             if (valid && d < D) {
                 w[d] = res;
@@ -327,11 +365,11 @@ __global__ void __launch_bounds__(kThreads) rsgd_kernel(const RsgdArgs a) {
             float ss = 0.f;
 #pragma unroll
             for (int j = 0; j < E; ++j) {
-                if (lane + TT * j < D) { const float v = tv[j] + 1e-15f; ss = fmaf(v, v, ss); }
+                if (lane + TT * j < D) { const float v = __fadd_rn(tv[j], 1e-15f); ss = fmaf(v, v, ss); }
             }
             ss = tsum<TT>(ss);
             float m2, a2, d2;
-            shell_factor(sqrtf(ss), a.r_in, false, m2, a2, d2);
+            shell_factor(sqrtf(ss), a.r_in_rows, false, m2, a2, d2);
             double A = 0.0;
             float* o = a.rows_out + rc * (int64_t)a.ld_rows;
             float* zo = a.zero_grad ? a.zero_grad + rc * (int64_t)a.ld_rows : nullptr;
@@ -341,8 +379,8 @@ __global__ void __launch_bounds__(kThreads) rsgd_kernel(const RsgdArgs a) {
                 if (d < a.ld_rows) {
                     float v = 0.f;
                     if (d < D) {
-                        v = tv[j] + 1e-15f;
-                        if (m2 != 1.f || d2 != 1.f) v = ((a2 + v) / d2) * m2;
+                        v = __fadd_rn(tv[j], 1e-15f);
+                        if (m2 != 1.f || d2 != 1.f) v = __fmul_rn((a2 + v) / d2, m2);
                     }
                     A += (double)v * (double)v;
                     if (valid) {
@@ -360,14 +398,10 @@ __global__ void __launch_bounds__(kThreads) rsgd_kernel(const RsgdArgs a) {
                 }
             }
             A = tsumd<TT>(A);
-            if (valid && lane == 0 && a.aux_out) {
-                const Aux<double> x = row_aux<double>(LEC_GEOM_HYP, A, a.K);
-                double2* dst = reinterpret_cast<double2*>(a.aux_out + 4 * row);
-                dst[0] = make_double2(x.A, x.ria);
-                dst[1] = make_double2(x.t0, x.t1);
-            }
+            if (a.aux_out) aux_push<TT>(s_aux, aux_fill, A, row, valid, LEC_GEOM_HYP, a.K, a.aux_out);
         }
     }
+    if (a.rows_out && a.aux_out) aux_flush<TT>(s_aux, aux_fill, LEC_GEOM_HYP, a.K, a.aux_out);
     if (a.loss_acc && blockIdx.x == 0 && threadIdx.x == 0) {
         if (a.loss_step) *a.loss_step = *a.loss_acc;
         *a.loss_acc = 0.0;
@@ -453,8 +487,8 @@ int rows_bwd_launch(const float* in, const float* grad_rows, int replicas, int64
 
 template <int TT, int E>
 static void rsgd_go(const RsgdArgs& a, cudaStream_t st) {
-    if (a.world > 0) rsgd_kernel<TT, E, true><<<grid_rows(a.n, TT), kThreads, 0, st>>>(a);
-    else rsgd_kernel<TT, E, false><<<grid_rows(a.n, TT), kThreads, 0, st>>>(a);
+    if (a.world > 0) launch_step_kernel(rsgd_kernel<TT, E, true>, grid_rows(a.n, TT), kThreads, st, a);
+    else launch_step_kernel(rsgd_kernel<TT, E, false>, grid_rows(a.n, TT), kThreads, st, a);
 }
 
 static int rsgd_dispatch(const RsgdArgs& a, cudaStream_t st);
@@ -506,6 +540,8 @@ struct PushArgs {
 };
 
 __global__ void __launch_bounds__(kThreads) p2p_push_kernel(const PushArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int64_t total = a.n * (int64_t)a.ld;
     const int64_t stride = (int64_t)gridDim.x * kThreads;
     const int64_t dst0 = ((int64_t)a.slot * a.world + a.rank) * a.slot_floats;
@@ -558,7 +594,7 @@ int p2p_push_launch(float* grad_rows, int replicas, int64_t n, int D, int ld, do
     int64_t need = (total + kThreads - 1) / kThreads;
     const int64_t cap = (int64_t)sm_count() * 4;
     if (need < 1) need = 1;
-    p2p_push_kernel<<<(int)(need < cap ? need : cap), kThreads, 0, st>>>(a);
+    launch_step_kernel(p2p_push_kernel, (int)(need < cap ? need : cap), kThreads, st, a);
     ++g_launches;
     return (int)cudaGetLastError();
 }
@@ -572,6 +608,8 @@ int rsgd_rows_launch(float* table, float* grad_rows, int replicas, int64_t n, in
     a.world = 0;
     a.rows_out = rows_out; a.ld_rows = ld; a.aux_out = aux_out; a.K = K; a.zero_grad = grad_rows;
     a.loss_acc = loss_acc; a.loss_step = loss_step;
+    float c0_unused;
+    hyp_constants(K, a.r_in_rows, c0_unused);
     return rsgd_dispatch(a, st);
 }
 
@@ -581,6 +619,8 @@ int rsgd_p2p_launch(float* table, void* const* peer_bufs, int64_t slot_floats, i
                     cudaStream_t st) {
     RsgdArgs a{};
     a.local_sources = local_sources; a.K = K; a.rows_out = rows_out; a.ld_rows = ld_rows; a.aux_out = aux_out;
+    float c0_unused;
+    hyp_constants(K, a.r_in_rows, c0_unused);
     a.table = table; a.grad = nullptr; a.n = n; a.D = D; a.ld_g = D; a.lr = lr; a.r_in = r_in;
     a.lambda_mode = lambda_mode; a.grad_out = nullptr; a.replicas = 1; a.replica_stride = 0;
     a.world = world; a.rank = rank; a.slot = slot; a.tag = tag; a.slot_floats = slot_floats;

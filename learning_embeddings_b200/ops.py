@@ -375,7 +375,9 @@ class ScorePipeline:
     """Host-to-host scoring of a large image set (the call the reference's calculate_classification_metrics would
     make, oe_h.py:1971-2036): pinned host image embeddings in, per-level top-k label ids (and energies) out in pinned
     host memory.  The set is cut into slices; the upload of slice j+1 and the download of slice j-1 run on their
-    own streams while slice j is scored, so the PCIe copies overlap the kernel."""
+    own streams while slice j is scored, so the PCIe copies overlap the kernel.  `out_idx_host` may be int32 or int16
+    (label ids of any hierarchy below 32 768 labels fit; the narrowing runs on the download stream and halves the
+    device->host bytes, which is what bounds this call once the kernel is faster than the PCIe copies)."""
 
     def __init__(self, labels, geom, K, level_start, level_stop, k=5, slice_images=131072, engine="auto",
                  precision=PREC_F32):
@@ -393,12 +395,21 @@ class ScorePipeline:
         self.ev_in = [torch.cuda.Event() for _ in range(2)]
         self.ev_scored = [torch.cuda.Event() for _ in range(2)]
         self.ev_out = [torch.cuda.Event() for _ in range(2)]
+        self.idx16 = None
 
     def run(self, images_host, out_idx_host, out_val_host=None):
         if images_host.is_cuda or out_idx_host.is_cuda:
             raise N.LecError("ScorePipeline.run takes host tensors (use ops.score_topk for device tensors)")
         main = torch.cuda.current_stream(self.dev)
         n_img = images_host.shape[0]
+        narrow = out_idx_host.dtype == torch.int16
+        if narrow:
+            if self.labels.shape[0] > 32767:
+                raise N.LecError("int16 label ids need fewer than 32 768 labels")
+            if self.idx16 is None:
+                self.idx16 = [torch.empty_like(t, dtype=torch.int16) for t in self.idx]
+        elif out_idx_host.dtype != torch.int32:
+            raise N.LecError("out_idx_host must be int32 or int16")
         for j, s0 in enumerate(range(0, n_img, self.slice)):
             b, n = j & 1, min(self.slice, n_img - s0)
             with torch.cuda.stream(self.s_in):
@@ -413,7 +424,11 @@ class ScorePipeline:
             self.ev_scored[b].record(main)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(self.ev_scored[b])
-                out_idx_host[s0:s0 + n].copy_(self.idx[b][:n], non_blocking=True)
+                if narrow:
+                    self.idx16[b][:n].copy_(self.idx[b][:n])
+                    out_idx_host[s0:s0 + n].copy_(self.idx16[b][:n], non_blocking=True)
+                else:
+                    out_idx_host[s0:s0 + n].copy_(self.idx[b][:n], non_blocking=True)
                 if out_val_host is not None:
                     out_val_host[s0:s0 + n].copy_(self.val[b][:n], non_blocking=True)
                 self.ev_out[b].record(self.s_out)

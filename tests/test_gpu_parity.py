@@ -510,6 +510,9 @@ def test_score_pipeline_host_to_host_equals_device_call(engine):
         out_idx.fill_(-7)
         pipe.run(images.pin_memory(), out_idx, out_val)
         assert torch.equal(out_idx, idx.cpu()) and torch.equal(out_val, val.cpu())
+    out16 = torch.empty((n_img, 4, 5), dtype=torch.int16).pin_memory()   # narrow label ids: half the download
+    pipe.run(images.pin_memory(), out16)
+    assert torch.equal(out16.int(), idx.cpu())
     with pytest.raises(N.LecError):
         pipe.run(images.to(DEV), out_idx)
 
@@ -653,9 +656,10 @@ def test_fused_update_and_row_transform_equals_separate_launches(D):
         assert np.isfinite(losses[0]) and abs(losses[0] - losses[1]) <= 1e-6 * abs(losses[1])
         assert float((tabs[0] - tabs[1]).abs().max()) < 5e-5
         np.testing.assert_allclose(engs[0].E_neg.cpu().numpy(), engs[1].E_neg.cpu().numpy(), rtol=0, atol=2e-3)
-    # the fused engine already holds the rows of the NEXT step, bit-identical to a separate lec_rows_fwd of its table
+    # the fused engine already holds the rows of the NEXT step: what a separate lec_rows_fwd of its table gives
     rows, aux = ops.rows_forward(tabs[0], N.ROWS_HYP_SHELL, 0.1, geom="hyp")
-    assert torch.equal(engs[0].rows, rows) and torch.equal(engs[0].aux, aux)
+    np.testing.assert_allclose(engs[0].rows.cpu().numpy(), rows.cpu().numpy(), rtol=1e-6, atol=0)
+    np.testing.assert_allclose(engs[0].aux.cpu().numpy(), aux.cpu().numpy(), rtol=1e-12, atol=0)
     assert float(engs[0].grad_rows.abs().max()) == 0.0
     # an outside change of the table must be announced
     with torch.no_grad():

@@ -182,8 +182,9 @@ int lec_rsgd_update_p2p(float* table, void* const* peer_bufs, int64_t slot_float
  * per step instead of two.  Per table row: sum of the gradient replicas -> RSGD update in place -> shell projection
  * of the updated row into rows_out [n, ld] + its aperture terms aux_out [n, 4] (as lec_rows_fwd with
  * LEC_ROWS_HYP_SHELL) -> the row's gradient replicas cleared for the next lec_pairs_grouped.  The loss accumulator the
- * pair kernel added into is moved: *loss_step = *loss_acc; *loss_acc = 0 (both optional).  Bit-identical to
- * lec_rsgd_update followed by lec_rows_fwd.
+ * pair kernel added into is moved: *loss_step = *loss_acc; *loss_acc = 0 (both optional).  Same results as
+ * lec_rsgd_update followed by lec_rows_fwd up to the fp32 rounding of a row norm (the kernels reduce it over
+ * different team widths).
  */
 int lec_rsgd_update_rows(float* table, float* grad_rows, int grad_replicas, int64_t n, int D, int ld, float lr,
                          float r_in, int lambda_mode, float K, float* rows_out, double* aux_out, double* loss_acc,

@@ -156,8 +156,9 @@ __global__ void __launch_bounds__(kThreads, LEC_GROUPED_MINBLOCKS) pairs_grouped
     pdl_launch_dependents();   // the update kernel may take its (few) SM slots now; it parks in pdl_wait()
     pdl_wait();                // rows / aux / cleared replicas of the previous update are complete
     const int lane_t = threadIdx.x % T;
-    const int64_t n_teams = (int64_t)gridDim.x * (kThreads / T);
-    const int64_t team = (int64_t)blockIdx.x * (kThreads / T) + threadIdx.x / T;
+    const int tpb = (int)blockDim.x / T;   // teams per block (the launcher picks the block size, <= kThreads)
+    const int64_t n_teams = (int64_t)gridDim.x * tpb;
+    const int64_t team = (int64_t)blockIdx.x * tpb + threadIdx.x / T;
     const int split = a.split;
     const int64_t n_items = a.B * split;
     const int64_t iters = (n_items + n_teams - 1) / n_teams;
@@ -401,15 +402,23 @@ inline int choose_split(int64_t B, int N, int64_t cap) {
 template <int CORE, int T, int V>
 int launch_grouped_tv(const GroupArgs& a0, cudaStream_t st) {
     GroupArgs a = a0;
+    // Block size: the fp64-core kernel needs ~166 registers per thread, i.e. one 256-thread block (8 warps) per SM;
+    // 128-thread blocks fit three (12 warps), which is what hides the gather / reduction latency (LEC_GROUP_BLOCK tunes).
+    static const int block = [] {
+        const char* e = getenv("LEC_GROUP_BLOCK");
+        int b = e ? atoi(e) : 128;
+        if (b < 32 || b > kThreads || (b & 31)) b = 128;
+        return b;
+    }();
     static const int resident_blocks = [] {
         int nb = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pairs_grouped_kernel<CORE, T, V, true>, kThreads, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pairs_grouped_kernel<CORE, T, V, true>, block, 0);
         return nb > 0 ? nb : 1;
     }();
-    a.split = choose_split(a.B, a.N, (int64_t)sm_count() * resident_blocks * (kThreads / T));
-    const int grid = grid_for(a.B * a.split, kThreads / T, 8);
-    if (a.grad_rows) launch_step_kernel(pairs_grouped_kernel<CORE, T, V, true>, grid, kThreads, st, a);
-    else launch_step_kernel(pairs_grouped_kernel<CORE, T, V, false>, grid, kThreads, st, a);
+    a.split = choose_split(a.B, a.N, (int64_t)sm_count() * resident_blocks * (block / T));
+    const int grid = grid_for(a.B * a.split, block / T, 8 * kThreads / block);
+    if (a.grad_rows) launch_step_kernel(pairs_grouped_kernel<CORE, T, V, true>, grid, block, st, a);
+    else launch_step_kernel(pairs_grouped_kernel<CORE, T, V, false>, grid, block, st, a);
     ++g_launches;
     return (int)cudaGetLastError();
 }

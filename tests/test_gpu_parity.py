@@ -658,8 +658,10 @@ def test_fused_update_and_row_transform_equals_separate_launches(D):
         np.testing.assert_allclose(engs[0].E_neg.cpu().numpy(), engs[1].E_neg.cpu().numpy(), rtol=0, atol=2e-3)
     # the fused engine already holds the rows of the NEXT step: what a separate lec_rows_fwd of its table gives
     rows, aux = ops.rows_forward(tabs[0], N.ROWS_HYP_SHELL, 0.1, geom="hyp")
+    # (the two kernels reduce a row's norm over different team widths, so a row sitting exactly on the inner shell can
+    # differ by one fp32 rounding)
     np.testing.assert_allclose(engs[0].rows.cpu().numpy(), rows.cpu().numpy(), rtol=1e-6, atol=0)
-    np.testing.assert_allclose(engs[0].aux.cpu().numpy(), aux.cpu().numpy(), rtol=1e-12, atol=0)
+    np.testing.assert_allclose(engs[0].aux.cpu().numpy(), aux.cpu().numpy(), rtol=2e-6, atol=0)
     assert float(engs[0].grad_rows.abs().max()) == 0.0
     # an outside change of the table must be announced
     with torch.no_grad():

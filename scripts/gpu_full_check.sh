@@ -23,9 +23,18 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 100 --csv --log-file $O/launches_cfg3.csv \
    python bench.py --workload cfg3 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > $O/ncu_cfg3.log 2>&1
 for D in 10 50; do
-  timeout 300 ncu --set full --clock-control none --import-source on -k regex:score_mma_kernel -c 3 -o /tmp/prof_tc_d$D \
-      python scripts/score_bench.py --images 303104 --dims $D --iters 1 --modes topk,matrix_lm,both_lm --engines tc > $O/ncu_tc_d$D.log 2>&1
-  ncu -i /tmp/prof_tc_d$D.ncu-rep --page raw --csv > $O/tc_d${D}_raw.csv 2>/dev/null
+  # score_bench runs 2 warm-up + 1 timed launch per mode: launches 2, 5, 8 of the kernel are the timed top-k / matrix / both
+  for m in topk matrix_lm both_lm; do
+    timeout 300 ncu --set full --clock-control none --import-source on -k regex:score_mma_kernel -s 2 -c 1 -o /tmp/prof_tc_d${D}_$m \
+        python scripts/score_bench.py --images 303104 --dims $D --iters 1 --modes $m --engines tc > $O/ncu_tc_d${D}_$m.log 2>&1
+    ncu -i /tmp/prof_tc_d${D}_$m.ncu-rep --page raw --csv > $O/tc_d${D}_${m}_raw.csv 2>/dev/null
+  done
 done
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:pairs_grouped -s 6 -c 1 -o /tmp/prof_pairs \
+    python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-e2e > $O/ncu_pairs.log 2>&1
+ncu -i /tmp/prof_pairs.ncu-rep --page raw --csv > $O/pairs_cfg1_raw.csv 2>/dev/null
+timeout 300 ncu --set full --clock-control none -k regex:rsgd_kernel -s 6 -c 1 -o /tmp/prof_rsgd \
+    python bench.py --workload cfg4 --steps 6 --warmup 3 --pairs 131040 --no-cpu-baseline --no-e2e --rotation 4 > $O/ncu_rsgd.log 2>&1
+ncu -i /tmp/prof_rsgd.ncu-rep --page raw --csv > $O/rsgd_cfg4_raw.csv 2>/dev/null
 tail -3 $O/smoke.log; tail -8 $O/pytest_gpu.log; cat $O/score_bench.log
 for w in default default_reference cfg2 cfg3_d10 cfg3_d50 cfg3_d10_matrix cfg3_d10_topk cfg4; do tail -2 $O/bench_$w.err; cut -c1-700 $O/bench_$w.json; echo; done

@@ -533,6 +533,9 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(const MmaArgs
         auto refresh = [&]() {
             // both threads of an image feed one top-k: the tighter of the two k-th bests bounds either stream.  The peer's
             // published value counts only while it is working on the same level (it may be a chunk ahead or behind).
+            // Deliberately unsynchronised (compute-sanitizer racecheck flags this read against publish()): value and
+            // level tag travel in one aligned 8-byte store / load, and ANY value the peer published for this level is
+            // a valid upper bound of the image's k-th best.
             const float2 pe = thr_pub[et ^ kMmaM];
             const float t = fminf(list.kth(k), __float_as_int(pe.y) == level ? pe.x : INFINITY);
             thr = t;

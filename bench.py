@@ -33,7 +33,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg1", choices=["cfg1", "cfg2", "cfg3", "cfg4"])
+    ap.add_argument("--workload", default="cfg1", choices=["cfg0", "cfg1", "cfg2", "cfg3", "cfg4"])
     ap.add_argument("--dim", type=int, default=10, help="cfg3: embedding dimension (10 or 50)")
     ap.add_argument("--images", type=int, default=1000000, help="cfg3: images per GPU per step")
     ap.add_argument("--score-mode", default="both", choices=["both", "matrix", "topk"],
@@ -53,6 +53,12 @@ def parse():
 # workload
 # ------------------------------------------------------------------------------------------------
 def workload_spec(name):
+    if name == "cfg0":
+        # BASELINE.json configs[0] (the reference's own CPU case: D=2, Embedder K=3, alpha=0.05, N=5, Adam,
+        # order_embeddings.py:1364) with the ETHEC closure edges tiled to the cfg1 batch size, so that the Euclidean
+        # pair kernel is measured at a size that fills the GPU
+        return dict(name="cfg0: Euclidean cones, label-only, ETHEC 723-node hierarchy, D=2, Adam, 10 negatives/edge",
+                    geom="euc", D=2, n_neg=5, K=3.0, alpha=0.05, lr=1e-3, tree="ethec")
     if name == "cfg1":
         return dict(name="cfg1: Poincare cones, label-only, ETHEC 723-node hierarchy, D=10, RSGD, 10 negatives/edge",
                     geom="hyp", D=10, n_neg=5, K=0.1, alpha=0.05, lr=1e-3, tree="ethec")
@@ -149,6 +155,18 @@ def cpu_step_runner(spec, table, blk, B):
     nf = torch.cat([u[:, None].expand(B, Nn), neg_from], 1).reshape(-1)
     nt = torch.cat([neg_to, v[:, None].expand(B, Nn)], 1).reshape(-1)
     W = table.clone()
+    if spec["geom"] == "euc":
+        # order_embeddings.py: Embedder.soft_clip rows, EucConesLoss, torch Adam on the table
+        P = torch.nn.Parameter(W, requires_grad=False)
+        opt = torch.optim.Adam([P], lr=spec["lr"])
+
+        def run_euc():
+            r = cones.label_step("euc", P.data, cones.ROW_EUC_SOFTCLIP, spec["K"], spec["alpha"], u, v, nf, nt)
+            P.grad = r["gW"]
+            opt.step()
+            return float(r["loss"])
+
+        return run_euc
     r_in = cones.inner_radius(spec["K"])
 
     def run():
@@ -701,6 +719,10 @@ def main():
     idx_bytes = np.dtype(index_dtype_for(h.n)).itemsize
     cfg["index_dtype"] = np.dtype(index_dtype_for(h.n)).name
     table0 = init_table(h.n, D, spec["K"], seed=0)
+    if spec["geom"] == "euc":
+        table0 = torch.randn(h.n, D, generator=torch.Generator().manual_seed(0))   # nn.Embedding default init
+        cfg["update"] = "adam (torch fused, stock optimiser as in the reference)"
+        cfg["scalar_core"] = "fp32"
 
     # ---------------- reference arm: CPU only, rank 0 only ----------------
     if args.impl == "reference":
@@ -745,7 +767,8 @@ def main():
     dev_batches = [b.to(dev) for b in host_batches]
     table = table0.to(dev).clone()
     eng = ConeStep(table, spec["geom"], Nn, groups, K=spec["K"], alpha=spec["alpha"], lr=spec["lr"],
-                   precision=precision, process_group=pg, comm=args.comm)
+                   precision=precision, process_group=pg, comm=args.comm,
+                   update="adam" if spec["geom"] == "euc" else "auto")
     cfg["exchange"] = (eng.comm + (" " + eng.comm_note if eng.comm_note else "")) if world > 1 else "none (1 GPU)"
 
     def dev_step(i):
@@ -858,7 +881,7 @@ def main():
         v, mean_s, n_done, pairs = time_cpu(spec, table0, host_batches[0], cpu_groups, steps=40, warmup=2, budget_s=20.0)
         cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                "sample": "%d pairs per CPU step (first %d positives of batch 0), %d steps, torch fp32 on all host "
-                         "threads, same step (gather+transform+energy+hinge+backward+RSGD)" % (pairs, cpu_groups, n_done)}
+                         "threads, same step (gather+transform+energy+hinge+backward+update)" % (pairs, cpu_groups, n_done)}
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -545,6 +545,10 @@ __global__ void __launch_bounds__(kThreads) p2p_push_kernel(const PushArgs a) {
     const int64_t total = a.n * (int64_t)a.ld;
     const int64_t stride = (int64_t)gridDim.x * kThreads;
     const int64_t dst0 = ((int64_t)a.slot * a.world + a.rank) * a.slot_floats;
+    // the step's loss is complete when this kernel starts (the pair kernel has finished): it travels with the first
+    // block's data, under the same fence, so the last block has nothing left to store but the flags
+    if (blockIdx.x == 0 && (int)threadIdx.x < a.world)
+        *reinterpret_cast<double*>(a.peer[threadIdx.x] + dst0 + a.slot_floats - 2) = *a.loss_acc;
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += stride) {
         const int64_t row = i / a.ld;
         const int d = (int)(i - row * a.ld);
@@ -567,14 +571,9 @@ __global__ void __launch_bounds__(kThreads) p2p_push_kernel(const PushArgs a) {
     __threadfence();            // all blocks' counts (and the stores fenced before them) are visible here
     if (threadIdx.x == 0) {
         *a.counter = 0;
-        const double l = *a.loss_acc;
-        if (a.loss_step) *a.loss_step = l;
+        if (a.loss_step) *a.loss_step = *a.loss_acc;
         *a.loss_acc = 0.0;
-        for (int p = 0; p < a.world; ++p)
-            *reinterpret_cast<double*>(a.peer[p] + dst0 + a.slot_floats - 2) = l;
-        __threadfence_system();
     }
-    __syncthreads();
     if ((int)threadIdx.x < a.world) {
         const int p = threadIdx.x;
         unsigned* flags = reinterpret_cast<unsigned*>(a.peer[p] + 2 * (int64_t)a.world * a.slot_floats) + a.slot * a.world;

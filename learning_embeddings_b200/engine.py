@@ -175,10 +175,22 @@ class ConeStep:
         if self.update == "rsgd":
             N.check(lib.lec_rsgd_update(N._p(self.table), N._p(self.grad_table), 1, self.n, self.D, self.D, self.lr,
                                         self.r_in, 0, N._p(self.grad_table), st), "lec_rsgd_update")
-        elif self.update == "sgd":
-            self.table.add_(self.grad_table, alpha=-self.lr)
+        elif self.update in ("sgd", "adam"):
+            self._apply_torch_update()
         elif self.update != "none":
             raise N.LecError("unknown update rule %r" % (self.update,))
+
+    def _apply_torch_update(self):
+        """Euclidean trainers hand the table to a stock torch optimiser (order_embeddings.py:563-565: SGD or Adam); so
+        does the engine -- plain SGD, or torch's fused Adam on the table.  Not the product."""
+        if self.update == "sgd":
+            self.table.add_(self.grad_table, alpha=-self.lr)
+            return
+        if getattr(self, "_adam", None) is None:
+            self._adam_param = torch.nn.Parameter(self.table, requires_grad=False)
+            self._adam = torch.optim.Adam([self._adam_param], lr=self.lr, fused=True)
+        self._adam_param.grad = self.grad_table
+        self._adam.step()
 
     def global_loss(self):
         """Loss of the latest step summed over ranks (float64 tensor on the device)."""
@@ -197,7 +209,7 @@ class ConeStep:
         import ctypes
         s = N.LecStep()
         s.geom, s.precision, s.row_mode = N.GEOM[self.geom], self.precision, self.row_mode
-        s.update = {"none": 0, "rsgd": 1}[self.update]
+        s.update = 1 if self.update == "rsgd" else 0   # sgd / adam: the library leaves d loss / d table in grad_table
         s.lambda_mode = 0
         s.K, s.alpha, s.lr, s.r_in = self.K, self.alpha, self.lr, self.r_in
         s.table, s.n, s.D, s.ld = self.table.data_ptr(), self.n, self.D, self.ld
@@ -218,7 +230,8 @@ class ConeStep:
 
     def step_device(self, pos_from, pos_to, neg_to, neg_from, w_pos=None, w_neg=None):
         """Indices already on the device (int32 or int64).  Returns the device loss (float64[1])."""
-        if self.update in ("none", "rsgd") and self.comm in ("none", "p2p"):
+        if self.update in ("none", "rsgd") and self.comm in ("none", "p2p") or \
+                self.update in ("sgd", "adam") and self.comm == "none":
             # the whole step as ONE call into the library (lec_cone_step): one FFI crossing, 3-5 launches
             B = int(pos_from.numel())
             if B > self.max_groups:
@@ -250,6 +263,8 @@ class ConeStep:
             N.check(N.lib().lec_cone_step(ctypes.byref(s), N.stream_ptr(self.table.device)), "lec_cone_step")
             if not self.fused:
                 self._rows_valid = False
+            if self.update in ("sgd", "adam"):
+                self._apply_torch_update()
             if self.comm == "p2p":
                 self.px.step += 1
             return self.loss

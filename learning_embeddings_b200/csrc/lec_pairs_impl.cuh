@@ -9,7 +9,7 @@
 namespace lec {
 
 #ifndef LEC_GROUPED_MINBLOCKS
-#define LEC_GROUPED_MINBLOCKS 1
+#define LEC_GROUPED_MINBLOCKS 2   // default of the grouped kernel's register cap (LEC_GROUP_MINBLOCKS overrides at run time)
 #endif
 enum Core { CORE_EUC32 = 0, CORE_HYP32 = 1, CORE_HYP64 = 2, CORE_OE32 = 3 };
 
@@ -149,8 +149,10 @@ __global__ void __launch_bounds__(kThreads) pairs_flat_kernel(const FlatArgs a) 
 // (cfg4: 2 520 positives x 51 pairs), a group is split over `split` teams: team s evaluates the positive
 // (s == 0 only) and every split-th negative of both lists, and flushes its own partial sums for u_i, v_i.
 // ------------------------------------------------------------------------------------------------
-template <int CORE, int T, int V, bool GRAD>
-__global__ void __launch_bounds__(kThreads, LEC_GROUPED_MINBLOCKS) pairs_grouped_kernel(const GroupArgs a) {
+// MB: minimum resident 256-thread blocks per SM the register allocation must allow.  MB = 2 caps the fp64-core kernel at
+// 128 registers (28 bytes of spill) and doubles the resident warps; MB = 1 lets it take the 184 it asks for.
+template <int CORE, int T, int V, bool GRAD, int MB>
+__global__ void __launch_bounds__(kThreads, MB) pairs_grouped_kernel(const GroupArgs a) {
     using Tr = CoreTraits<CORE>;
     using Acc = typename Tr::Acc;
     pdl_launch_dependents();   // the update kernel may take its (few) SM slots now; it parks in pdl_wait()
@@ -410,15 +412,22 @@ int launch_grouped_tv(const GroupArgs& a0, cudaStream_t st) {
         if (b < 32 || b > kThreads || (b & 31)) b = 128;
         return b;
     }();
+    static const int mb = [] { const char* e = getenv("LEC_GROUP_MINBLOCKS"); return (e ? atoi(e) : LEC_GROUPED_MINBLOCKS) >= 2 ? 2 : 1; }();
     static const int resident_blocks = [] {
         int nb = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pairs_grouped_kernel<CORE, T, V, true>, block, 0);
+        if (mb == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pairs_grouped_kernel<CORE, T, V, true, 2>, block, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pairs_grouped_kernel<CORE, T, V, true, 1>, block, 0);
         return nb > 0 ? nb : 1;
     }();
     a.split = choose_split(a.B, a.N, (int64_t)sm_count() * resident_blocks * (block / T));
     const int grid = grid_for(a.B * a.split, block / T, 8 * kThreads / block);
-    if (a.grad_rows) launch_step_kernel(pairs_grouped_kernel<CORE, T, V, true>, grid, block, st, a);
-    else launch_step_kernel(pairs_grouped_kernel<CORE, T, V, false>, grid, block, st, a);
+    if (mb == 2) {
+        if (a.grad_rows) launch_step_kernel(pairs_grouped_kernel<CORE, T, V, true, 2>, grid, block, st, a);
+        else launch_step_kernel(pairs_grouped_kernel<CORE, T, V, false, 2>, grid, block, st, a);
+    } else {
+        if (a.grad_rows) launch_step_kernel(pairs_grouped_kernel<CORE, T, V, true, 1>, grid, block, st, a);
+        else launch_step_kernel(pairs_grouped_kernel<CORE, T, V, false, 1>, grid, block, st, a);
+    }
     ++g_launches;
     return (int)cudaGetLastError();
 }

@@ -649,8 +649,21 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(const MmaArgs
                 }
                 const int lab0 = hdr.label0 + gbase;
                 if (MODE == 0) {
-                    if (want_topk) {
-                        // deferred angle: E < thr  <=>  g > cos(thr + psi); candidates go to the ring as {g, label, -psi}
+                    if (FORMS == 3 && want_topk && (hdr.flags & 1) && gi == 0) {
+                        // first group of a level: the list is empty, so every label is a candidate -- skip the ring and
+                        // insert the 16 energies directly (same packed acos as the matrix path; uniform over the warp).
+                        // Short rows only: in the FORMS == 1 kernel the extra code spills (D=50 top-k 1.81 -> 2.23 ms).
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            float z0, z1;
+                            unpack2(fadd2(acos_clamped2(g[q]), NPSI[q]), z0, z1);
+                            if (2 * q < g_count) list.insert_ascending(max_nan(z0, 0.f), lab0 + 2 * q);
+                            if (2 * q + 1 < g_count) list.insert_ascending(max_nan(z1, 0.f), lab0 + 2 * q + 1);
+                        }
+                        publish();
+                        refresh();
+                    } else if (want_topk) {
+                        // deferred angle: E < thr  <=>  g > cos(thr + psi); candidates go to the ring as {g, label}
                         u64 cb[8];
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {

@@ -11,6 +11,7 @@ timeout 1200 python -m pytest tests -m gpu -q --no-header -p no:cacheprovider > 
 echo "pytest exit $?" >> $O/pytest_gpu.log
 timeout 300 python bench.py > $O/bench_default.json 2> $O/bench_default.err
 timeout 300 python bench.py --impl reference --steps 5 --warmup 3 > $O/bench_default_reference.json 2> $O/bench_default_reference.err
+timeout 300 python bench.py --workload cfg0 --steps 200 --warmup 20 > $O/bench_cfg0.json 2> $O/bench_cfg0.err
 timeout 300 python bench.py --workload cfg2 --steps 50 --warmup 5 > $O/bench_cfg2.json 2> $O/bench_cfg2.err
 timeout 300 python bench.py --workload cfg3 --steps 50 --warmup 5 > $O/bench_cfg3_d10.json 2> $O/bench_cfg3_d10.err
 timeout 300 python bench.py --workload cfg3 --dim 50 --steps 50 --warmup 5 > $O/bench_cfg3_d50.json 2> $O/bench_cfg3_d50.err
@@ -22,7 +23,7 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
    python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-e2e > $O/ncu_cfg1.log 2>&1
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 100 --csv --log-file $O/launches_cfg3.csv \
    python bench.py --workload cfg3 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > $O/ncu_cfg3.log 2>&1
-for D in 10 50; do
+for D in ${NCU_DIMS-10 50}; do
   # score_bench runs 2 warm-up + 1 timed launch per mode: launches 2, 5, 8 of the kernel are the timed top-k / matrix / both
   for m in topk matrix_lm both_lm; do
     timeout 300 ncu --set full --clock-control none --import-source on -k regex:score_mma_kernel -s 2 -c 1 -o /tmp/prof_tc_d${D}_$m \
@@ -37,4 +38,4 @@ timeout 300 ncu --set full --clock-control none -k regex:rsgd_kernel -s 6 -c 1 -
     python bench.py --workload cfg4 --steps 6 --warmup 3 --pairs 131040 --no-cpu-baseline --no-e2e --rotation 4 > $O/ncu_rsgd.log 2>&1
 ncu -i /tmp/prof_rsgd.ncu-rep --page raw --csv > $O/rsgd_cfg4_raw.csv 2>/dev/null
 tail -3 $O/smoke.log; tail -8 $O/pytest_gpu.log; cat $O/score_bench.log
-for w in default default_reference cfg2 cfg3_d10 cfg3_d50 cfg3_d10_matrix cfg3_d10_topk cfg4; do tail -2 $O/bench_$w.err; cut -c1-700 $O/bench_$w.json; echo; done
+for w in default default_reference cfg0 cfg2 cfg3_d10 cfg3_d50 cfg3_d10_matrix cfg3_d10_topk cfg4; do tail -2 $O/bench_$w.err; cut -c1-700 $O/bench_$w.json; echo; done

@@ -668,10 +668,14 @@ def run_cfg3(args):
     # a top-k-only step moves (4 D + 160) / L per score
     bytes_per_score = ((4.0 if want_matrix else 0.0) + 4.0 * D / L + (160.0 / L if want_topk else 0.0))
     achieved = n_img * L * bytes_per_score / (kernel_ms * 1e-3) / 1e9
+    # measured DRAM traffic of the scoring launch: ncu dram bytes per score (profiles/traffic_cfg3.json, captured on a
+    # 303 104-image launch of the same kernel) scaled to this launch's scores
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic_cfg3_D%d_%s.json" % (D, args.score_mode))
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    tpath = os.path.join(ROOT, "profiles", "traffic_cfg3.json")
+    if use_tc and os.path.exists(tpath):
+        per_score = json.load(open(tpath)).get("dram_bytes_per_score", {}).get("d%d_%s" % (D, args.score_mode))
+        if per_score is not None:
+            traffic = per_score * n_img * L
     roofline = {"bound": "hbm", "kernel": "score_mma_kernel" if use_tc else "score_fast_kernel", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_score": bytes_per_score, "kernel_ms": kernel_ms,

@@ -27,15 +27,15 @@ extern thread_local int t_pdl;
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 template <typename Arg>
-inline void launch_step_kernel(void (*kern)(const Arg), int grid, int block, cudaStream_t st, const Arg& a) {
+inline void launch_step_kernel(void (*kern)(const Arg), int grid, int block, cudaStream_t st, const Arg& a, size_t smem = 0) {
     if (!t_pdl) {
-        kern<<<grid, block, 0, st>>>(a);
+        kern<<<grid, block, smem, st>>>(a);
         return;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3((unsigned)block);
-    cfg.dynamicSmemBytes = 0;
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute at{};
     at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -67,14 +67,17 @@ __device__ __forceinline__ S warp_sum(S v) {
     return team_sum<32, S>(v);
 }
 
+// staged: `rows` is the block's shared-memory copy of the table (plain loads), else global memory (read-only path)
 template <int T, int V>
-__device__ __forceinline__ void load_row(Vec<V>& r, const float* __restrict__ rows, int64_t row, int ld, int lane_t) {
+__device__ __forceinline__ void load_row(Vec<V>& r, const float* __restrict__ rows, int64_t row, int ld, int lane_t,
+                                         bool staged = false) {
     const float* base = rows + row * (int64_t)ld;
     const int Q = ld >> 2;
 #pragma unroll
     for (int j = 0; j < V; ++j) {
         const int q = lane_t + T * j;
-        r.c[j] = (q < Q) ? ldg4(base + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q < Q) r.c[j] = staged ? *reinterpret_cast<const float4*>(base + 4 * q) : ldg4(base + 4 * q);
+        else r.c[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 

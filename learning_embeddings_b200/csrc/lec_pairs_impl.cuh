@@ -35,6 +35,7 @@ struct GroupArgs {
     float K, alpha;
     float* E_pos; float* E_neg; double* loss_out; float* grad_rows; int grad_replicas; int64_t replica_stride;
     int split;  // teams per group (>= 1): team s of a group takes negatives p = s, s + split, ... of both lists
+    int64_t stage_floats;  // > 0: every block first copies the transformed table (n * ld floats) into shared memory
 };
 
 struct DenseArgs {
@@ -157,6 +158,17 @@ __global__ void __launch_bounds__(kThreads, MB) pairs_grouped_kernel(const Group
     using Acc = typename Tr::Acc;
     pdl_launch_dependents();   // the update kernel may take its (few) SM slots now; it parks in pdl_wait()
     pdl_wait();                // rows / aux / cleared replicas of the previous update are complete
+    // Hot label table in shared memory (ETHEC: 723 x 12 floats = 35 KB): every endpoint gather of the block then is an
+    // LDS.128 instead of an L1-cached global load.
+    extern __shared__ __align__(16) float s_rows[];
+    const bool staged = a.stage_floats > 0;
+    const float* const rows_p = staged ? s_rows : a.rows;
+    if (staged) {
+        const float4* src = reinterpret_cast<const float4*>(a.rows);
+        float4* dst = reinterpret_cast<float4*>(s_rows);
+        for (int64_t i = threadIdx.x; i < (a.stage_floats >> 2); i += blockDim.x) dst[i] = __ldg(src + i);
+        __syncthreads();
+    }
     const int lane_t = threadIdx.x % T;
     const int tpb = (int)blockDim.x / T;   // teams per block (the launcher picks the block size, <= kThreads)
     const int64_t n_teams = (int64_t)gridDim.x * tpb;
@@ -179,8 +191,8 @@ __global__ void __launch_bounds__(kThreads, MB) pairs_grouped_kernel(const Group
         const int64_t iu = ld_index(a.pos_from, gc, a.idx_bytes);
         const int64_t iv = ld_index(a.pos_to, gc, a.idx_bytes);
         Vec<V> U, W;
-        load_row<T, V>(U, a.rows, iu, a.ld, lane_t);
-        load_row<T, V>(W, a.rows, iv, a.ld, lane_t);
+        load_row<T, V>(U, rows_p, iu, a.ld, lane_t, staged);
+        load_row<T, V>(W, rows_p, iv, a.ld, lane_t, staged);
         Aux<Acc> au{};
         Acc AW = 0;
         if (Tr::cone) au = load_aux<Acc>(a.aux, iu);
@@ -230,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, MB) pairs_grouped_kernel(const Group
             const int p = act ? pr : N - 1;
             const int64_t ic = ld_index(a.neg_to, nbase + p, a.idx_bytes);
             Vec<V> C;
-            load_row<T, V>(C, a.rows, ic, a.ld, lane_t);
+            load_row<T, V>(C, rows_p, ic, a.ld, lane_t, staged);
             Acc AC = 0;
             if (Tr::hyp) AC = load_aux_A<Acc>(a.aux, ic);
             eval_pair<CORE, T, V, GRAD>(U, C, au, AC, g);
@@ -265,7 +277,7 @@ __global__ void __launch_bounds__(kThreads, MB) pairs_grouped_kernel(const Group
             const int p = act ? pr : N - 1;
             const int64_t ic = ld_index(a.neg_from, nbase + p, a.idx_bytes);
             Vec<V> C;
-            load_row<T, V>(C, a.rows, ic, a.ld, lane_t);
+            load_row<T, V>(C, rows_p, ic, a.ld, lane_t, staged);
             Aux<Acc> ac{};
             if (Tr::cone) ac = load_aux<Acc>(a.aux, ic);
             eval_pair<CORE, T, V, GRAD>(C, W, ac, AW, g);
@@ -421,12 +433,20 @@ int launch_grouped_tv(const GroupArgs& a0, cudaStream_t st) {
     }();
     a.split = choose_split(a.B, a.N, (int64_t)sm_count() * resident_blocks * (block / T));
     const int grid = grid_for(a.B * a.split, block / T, 8 * kThreads / block);
+    // Shared-memory staging of the table (LEC_STAGE_ROWS=1; tables <= 40 KB) was measured and is OFF by default: on
+    // cfg1 (723 x 12 floats) the per-block copy and the smaller L1 cost more than the LDS gathers save -- pair kernel
+    // 65.4 us staged vs 56.2 us with L1-resident read-only gathers (cfg0: 29.3 vs 27.6 us); profiles/r1f_notes.md.
+    static const int stage_env = [] { const char* e = getenv("LEC_STAGE_ROWS"); return e ? atoi(e) : 0; }();
+    const int64_t table_floats = a.replica_stride;   // n_rows * ld
+    const bool stage = stage_env != 0 && table_floats * 4 <= 40960;
+    a.stage_floats = stage ? table_floats : 0;
+    const size_t smem = stage ? (size_t)table_floats * 4 : 0;
     if (mb == 2) {
-        if (a.grad_rows) launch_step_kernel(pairs_grouped_kernel<CORE, T, V, true, 2>, grid, block, st, a);
-        else launch_step_kernel(pairs_grouped_kernel<CORE, T, V, false, 2>, grid, block, st, a);
+        if (a.grad_rows) launch_step_kernel(pairs_grouped_kernel<CORE, T, V, true, 2>, grid, block, st, a, smem);
+        else launch_step_kernel(pairs_grouped_kernel<CORE, T, V, false, 2>, grid, block, st, a, smem);
     } else {
-        if (a.grad_rows) launch_step_kernel(pairs_grouped_kernel<CORE, T, V, true, 1>, grid, block, st, a);
-        else launch_step_kernel(pairs_grouped_kernel<CORE, T, V, false, 1>, grid, block, st, a);
+        if (a.grad_rows) launch_step_kernel(pairs_grouped_kernel<CORE, T, V, true, 1>, grid, block, st, a, smem);
+        else launch_step_kernel(pairs_grouped_kernel<CORE, T, V, false, 1>, grid, block, st, a, smem);
     }
     ++g_launches;
     return (int)cudaGetLastError();

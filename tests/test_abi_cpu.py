@@ -61,6 +61,22 @@ def test_argument_validation_codes():
     assert lib.lec_p2p_publish(null, arr, 63, 2, 0, 0, 1, null) == -8        # slot_floats % 4
     assert lib.lec_rsgd_update_p2p(fake, arr, 8, 2, 0, 0, 1, 10, 4, 0.1, 0.1, 0, null, null, null) == -8  # slot too small
     assert lib.lec_rsgd_update_p2p(fake, null, 64, 2, 0, 0, 1, 10, 4, 0.1, 0.1, 0, null, null, null) == -1
+    # fused update + row transform, push exchange (ABI 11)
+    assert lib.lec_rsgd_update_rows(fake, fake, 1, 5, 4, 4, 0.1, 0.1, 0, 0.1, null, fake, null, null, null, null) == -1   # rows_out
+    assert lib.lec_rsgd_update_rows(fake, fake, 0, 5, 4, 4, 0.1, 0.1, 0, 0.1, fake, fake, null, null, null, null) == -7
+    assert lib.lec_rsgd_update_rows(fake, fake, 1, 5, 4, 6, 0.1, 0.1, 0, 0.1, fake, fake, null, null, null, null) == -2   # ld % 4
+    assert lib.lec_rsgd_update_rows(fake, fake, 1, 5, 4, 4, 0.1, 0.1, 2, 0.1, fake, fake, null, null, null, null) == -3   # lambda_mode
+    assert lib.lec_p2p_push(fake, 1, 10, 4, 4, fake, null, arr, 64, 2, 0, 0, 1, null, null) == -1          # counter
+    assert lib.lec_p2p_push(fake, 1, 10, 4, 4, fake, null, arr, 64, 2, 2, 0, 1, fake, null) == -8          # rank
+    assert lib.lec_p2p_push(fake, 1, 10, 4, 4, fake, null, arr, 8, 2, 0, 0, 1, fake, null) == -8           # slot too small
+    assert lib.lec_rsgd_update_rows_p2p(fake, arr, 64, 2, 0, 0, 1, 10, 4, 4, 0.1, 0.1, 0, 0.1, null, fake, null, null, null) == -1
+    assert lib.lec_rsgd_update_rows_p2p(fake, arr, 64, 2, 0, 3, 1, 10, 4, 4, 0.1, 0.1, 0, 0.1, fake, fake, null, null, null) == -8
+    step = _native.LecStep()
+    step.fused, step.update, step.row_mode = 1, 0, _native.ROWS_HYP_SHELL
+    step.grad_rows, step.loss = 0x1000, 0x1000
+    assert lib.lec_cone_step(ctypes.byref(step), null) == -3    # the fused step exists for the RSGD update only
+    step.update = 1
+    assert lib.lec_cone_step(ctypes.byref(step), null) == -1    # loss_acc missing
     assert b"16-byte" in lib.lec_error_string(-5)
 
 

@@ -17,13 +17,16 @@
 // 16 labels of the chunk, pulls its 3 x 16 columns with tcgen05.ld, releases the accumulator at once (so the
 // MMAs of the next chunk overlap the arithmetic even with a single accumulator buffer) and runs the epilogue on
 // packed label PAIRS (fma.rn.f32x2), then either stores the label-major score matrix (32 consecutive images per
-// warp store: coalesced) or feeds the per-level top-k.
+// warp store: coalesced) or feeds the per-level top-k (register-resident k-best list per thread, deferred-angle
+// filter, shared-memory candidate ring; see TopList and the epilogue).
 //
 // Data movement:
 //   labels  -> lec_score_mma_prep (one small launch): per chunk of 32 labels a "blob" in the caller's
 //              workspace = B_hi tile | B_lo tile (96 rows, K-major, no-swizzle UMMA canonical layout) | per-label-pair
-//              constants {-psi, cos psi, sin psi} (fp64-computed, same terms as lec_rows_fwd's aux) | header.
-//              The main kernel pulls blobs with cp.async.bulk (TMA, mbarrier complete_tx), double buffered.
+//              constants {-psi, cos psi, sin psi} (fp64-computed, same terms as lec_rows_fwd's aux) | header;
+//              plus one -psi[L] table for the top-k merge.  The main kernel pulls a blob with two cp.async.bulk copies
+//              (TMA, mbarrier complete_tx): the tiles into a tile stage that the MMAs' completion frees, the constants
+//              + header into a constant stage that the epilogue frees.
 //   images  -> each CTA reads its 128 rows once, splits [y, |y|^2, 1] into hi/lo and writes them to tensor memory
 //              as the A operand (tcgen05.st, TS-form MMA).
 //   accumulators: TMEM, 1 or 2 buffers of 96 columns so that a CTA stays within 256 columns and two CTAs share an SM.

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LEC_ABI_VERSION 11
+#define LEC_ABI_VERSION 12
 
 /* geometry of the energy */
 #define LEC_GEOM_EUC 0 /* EucConesLoss.E_operator, order_embeddings.py:954-969 = oe.py:721-739 (cos-space) */
@@ -356,6 +356,17 @@ int lec_f1_sweep(const float* sorted_energies, const int64_t* pos_prefix, int64_
 int lec_classify_counts(const int32_t* topk_idx, const int32_t* truth, int64_t n_img, int n_levels, int k,
                         const int32_t* k_vals, int n_kvals, int64_t L, uint64_t* hit, uint64_t* counts,
                         uint64_t* level_correct, void* stream);
+
+/* Caption-style ranking hinge of the image-label loss variant
+ * OrderEmbeddingWithImagesLossvCaption.get_image_label_loss (order_embeddings_images.py:533-542):
+ *     S_i = sum_j max(0, alpha + E+_i - E-_ij)        E_pos [B], E_neg [B, M] (row-major), S [B]
+ * and, in the same pass, its VJP for an upstream gradient gS [B] (NULL = ones):
+ *     gE_pos_i = gS_i * #{j : alpha + E+_i - E-_ij >= 0},   gE_neg_ij = -gS_i * [alpha + E+_i - E-_ij >= 0]
+ * (torch.clamp(min=0) passes the gradient at equality; a NaN energy makes S_i NaN and contributes no gradient).
+ * S, gE_pos, gE_neg are each optional.  Chains with lec_energy_dense / lec_energy_dense_bwd, which produce E and
+ * consume dL/dE. */
+int lec_caption_hinge(const float* E_pos, const float* E_neg, int64_t B, int M, float alpha, const float* gS, float* S,
+                      float* gE_pos, float* gE_neg, void* stream);
 
 #ifdef __cplusplus
 }

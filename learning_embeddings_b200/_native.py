@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "_lib", "liblec_b200.so")
 GEOM = {"euc": 0, "hyp": 1, "oe": 2}
 ROWS_NONE, ROWS_EUC_SOFTCLIP, ROWS_HYP_SHELL, ROWS_HYP_TANH, ROWS_HYP_TANH_FEAT = 0, 1, 2, 3, 4
 PREC_F32, PREC_F64CORE = 0, 1
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 EXPORTS = (
     "lec_abi_version", "lec_error_string", "lec_launch_count", "lec_rows_fwd", "lec_rows_bwd", "lec_reduce_replicas",
@@ -23,7 +23,7 @@ EXPORTS = (
     "lec_rsgd_update_p2p", "lec_rsgd_update_rows", "lec_p2p_push", "lec_rsgd_update_rows_p2p", "lec_cone_step", "lec_score_topk", "lec_score_topk_ex", "lec_score_tc_supported",
     "lec_score_workspace_bytes", "lec_score_topk_tc", "lec_mt_seed", "lec_mt_uint32", "lec_mt_randbelow",
     "lec_sample_negatives", "lec_sample_negatives_philox", "lec_philox_below", "lec_f1_workspace_bytes", "lec_f1_sweep",
-    "lec_classify_counts",
+    "lec_classify_counts", "lec_caption_hinge",
 )
 
 
@@ -116,6 +116,7 @@ def lib():
         L.lec_f1_workspace_bytes.restype = c_i64
         L.lec_f1_sweep.argtypes = [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp]
         L.lec_classify_counts.argtypes = [c_vp, c_vp, c_i64, c_i, c_i, c_vp, c_i, c_i64, c_vp, c_vp, c_vp, c_vp]
+        L.lec_caption_hinge.argtypes = [c_vp, c_vp, c_i64, c_i, c_f, c_vp, c_vp, c_vp, c_vp, c_vp]
         for name in EXPORTS:
             getattr(L, name)
         if L.lec_abi_version() != ABI_VERSION:

@@ -152,6 +152,29 @@ __global__ void __launch_bounds__(256) classify_kernel(const ClassifyArgs a) {
     }
 }
 
+// Caption-style ranking hinge (order_embeddings_images.py:533-542): one thread per positive walks its M negative
+// energies; S_i = sum_j max(0, alpha + E+_i - E-_ij) and, when asked, its VJP scaled by the upstream gradient gS_i.
+__global__ void __launch_bounds__(256) caption_hinge_kernel(const float* __restrict__ E_pos, const float* __restrict__ E_neg,
+                                                            int64_t B, int M, float alpha, const float* __restrict__ gS,
+                                                            float* __restrict__ S, float* __restrict__ gE_pos,
+                                                            float* __restrict__ gE_neg) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const float ep = E_pos[i];
+    const float up = gS ? gS[i] : 1.f;
+    float s = 0.f, cnt = 0.f;
+    for (int j = 0; j < M; ++j) {
+        const float m = (alpha + ep) - E_neg[i * M + j];   // the reference's order: (alpha - s+) + s-
+        const bool act = m >= 0.f;                          // clamp(min=0) passes the gradient at equality; NaN: inactive
+        s += act ? m : 0.f;
+        cnt += act ? 1.f : 0.f;
+        if (gE_neg) gE_neg[i * M + j] = act ? -up : 0.f;
+        if (!(m == m)) s = m;                               // NaN energy propagates like torch.clamp
+    }
+    if (S) S[i] = s;
+    if (gE_pos) gE_pos[i] = up * cnt;
+}
+
 }  // namespace
 }  // namespace lec
 
@@ -192,5 +215,17 @@ extern "C" int lec_classify_counts(const int32_t* topk_idx, const int32_t* truth
     if (blocks > 148 * 16) blocks = 148 * 16;
     classify_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(a);
     ++g_launches;
+    return (int)cudaGetLastError();
+}
+
+extern "C" int lec_caption_hinge(const float* E_pos, const float* E_neg, int64_t B, int M, float alpha, const float* gS,
+                                 float* S, float* gE_pos, float* gE_neg, void* stream) {
+    if (B < 0 || M < 0) return LEC_E_SIZE;
+    if (B == 0) return 0;
+    if (!E_pos || (M > 0 && !E_neg)) return LEC_E_NULL;
+    int64_t blocks = (B + 255) / 256;
+    if (blocks > 0x7fffffffLL) return LEC_E_SIZE;
+    lec::caption_hinge_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(E_pos, E_neg, B, M, alpha, gS, S, gE_pos, gE_neg);
+    ++lec::g_launches;
     return (int)cudaGetLastError();
 }

@@ -299,6 +299,43 @@ def rsgd_update_(table, grad, lr, r_in, textbook_lambda=False, write_rescaled_gr
 # --------------------------------------------------------------------------------------------------
 # Scoring
 # --------------------------------------------------------------------------------------------------
+class CaptionRankingHinge(torch.autograd.Function):
+    """S_i = sum_j max(0, alpha + E+_i - E-_ij) (lec_caption_hinge): the image-label loss of the reference's caption-style
+    variant, OrderEmbeddingWithImagesLossvCaption.get_image_label_loss (order_embeddings_images.py:533-542).  Forward
+    and the energy gradients come out of one launch; backward only scales them."""
+
+    @staticmethod
+    def forward(ctx, E_pos, E_neg, alpha):
+        N.require_cuda(E_pos)
+        N.require_cuda(E_neg)
+        ep = E_pos.detach().contiguous().float()
+        en = E_neg.detach().contiguous().float()
+        B = ep.numel()
+        M = en.numel() // B if B else 0
+        if en.numel() != B * M:
+            raise N.LecError("E_neg must hold M negatives for each of the %d positives" % B)
+        S = torch.empty(B, device=ep.device, dtype=torch.float32)
+        need = E_pos.requires_grad or E_neg.requires_grad
+        gp = torch.empty_like(ep) if need else None
+        gn = torch.empty_like(en) if need else None
+        N.check(N.lib().lec_caption_hinge(N._p(ep), N._p(en), B, M, float(alpha), N._p(None), N._p(S), N._p(gp), N._p(gn),
+                                          N.stream_ptr(ep.device)), "lec_caption_hinge")
+        ctx.save_for_backward(gp, gn)
+        ctx.shape_neg = E_neg.shape
+        return S
+
+    @staticmethod
+    def backward(ctx, gS):
+        gp, gn = ctx.saved_tensors
+        gS = gS.contiguous().float()
+        return gp * gS, (gn.view(gS.numel(), -1) * gS[:, None]).view(ctx.shape_neg), None
+
+
+def caption_ranking_hinge(E_pos, E_neg, alpha):
+    """[B], [B, M] -> [B]; differentiable drop-in for get_image_label_loss of order_embeddings_images.py:533-542."""
+    return CaptionRankingHinge.apply(E_pos, E_neg, alpha)
+
+
 _score_ws = {}  # device -> workspace tensor of the tensor-core scoring path (grown on demand, reused)
 
 

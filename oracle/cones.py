@@ -391,3 +391,13 @@ def classification_counts(top_idx, truth, n_labels, level_start, level_stop, k_v
                 fp[int(indices[0])] += 1
                 fn[want] += 1
     return hit, tp, fp, tn, fn
+
+
+def caption_ranking_hinge(E_pos, E_neg, alpha):
+    """order_embeddings_images.py:533-542 (OrderEmbeddingWithImagesLossvCaption.get_image_label_loss): per positive i
+    with its M negatives, S_i = sum_j max(0, alpha + E+_i - E-_ij).  Returns (S [B], dS/dE+ [B], dS/dE- [B, M]);
+    clamp(min=0) passes the gradient at equality, like torch."""
+    margin = alpha + E_pos[:, None] - E_neg
+    act = (margin >= 0).to(E_pos.dtype)
+    return margin.clamp(min=0.0).sum(dim=1), act.sum(dim=1), -act
+

@@ -528,10 +528,31 @@ def gen_classify():
              level_stop=np.array(lm.level_stop), K=crit.K, **out)
 
 
+# ---------------------------------------------------------------------------------------
+# J. caption-style ranking hinge, order_embeddings_images.py:533-542
+#    (OrderEmbeddingWithImagesLossvCaption.get_image_label_loss): S_i = sum_j max(0, alpha + E+_i - E-_ij)
+# ---------------------------------------------------------------------------------------
+def gen_caption():
+    ref_img = ref_shim.load("network.order_embeddings_images")
+    fn = ref_img.OrderEmbeddingWithImagesLossvCaption.get_image_label_loss
+    g = torch.Generator().manual_seed(91)
+    for tag, B, M, alpha in (("a", 37, 10, 1.0), ("b", 5, 1, 0.05), ("c", 64, 50, 0.3)):
+        E_pos = (torch.rand(B, generator=g) * 1.5).requires_grad_(True)
+        E_neg = (torch.rand(B, M, generator=g) * 2.0).requires_grad_(True)
+        with torch.no_grad():   # exact ties at the hinge and inactive rows
+            E_neg[0, 0] = alpha + E_pos[0]
+            E_neg[1] = 10.0
+        S = fn(types.SimpleNamespace(alpha=alpha), E_pos, E_neg)
+        gS = torch.randn(B, generator=g)
+        (S * gS).sum().backward()
+        save("caption_hinge_%s" % tag, E_pos=E_pos, E_neg=E_neg, alpha=alpha, S=S, gS=gS, gE_pos=E_pos.grad, gE_neg=E_neg.grad)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["pairs", "transforms", "rsgd", "steps", "joint", "scoring", "metrics", "mt", "classify"]
+    which = sys.argv[1:] or ["pairs", "transforms", "rsgd", "steps", "joint", "scoring", "metrics", "mt", "classify",
+                             "caption"]
     fns = dict(pairs=gen_pairs, transforms=gen_transforms, rsgd=gen_rsgd, steps=gen_steps, joint=gen_joint,
-               scoring=gen_scoring, metrics=gen_metrics, mt=gen_mt, classify=gen_classify)
+               scoring=gen_scoring, metrics=gen_metrics, mt=gen_mt, classify=gen_classify, caption=gen_caption)
     for w in which:
         print("==", w)
         fns[w]()

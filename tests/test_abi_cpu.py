@@ -23,7 +23,7 @@ def test_library_exports_every_header_symbol():
     for n in names:
         assert hasattr(lib, n), n
     assert sorted(_native.EXPORTS) == names
-    assert lib.lec_abi_version() == _native.ABI_VERSION == 11
+    assert lib.lec_abi_version() == _native.ABI_VERSION == 12
 
 
 def test_argument_validation_codes():
@@ -77,6 +77,9 @@ def test_argument_validation_codes():
     assert lib.lec_cone_step(ctypes.byref(step), null) == -3    # the fused step exists for the RSGD update only
     step.update = 1
     assert lib.lec_cone_step(ctypes.byref(step), null) == -1    # loss_acc missing
+    assert lib.lec_caption_hinge(null, fake, 4, 3, 1.0, null, fake, null, null, null) == -1
+    assert lib.lec_caption_hinge(fake, fake, -1, 3, 1.0, null, fake, null, null, null) == -4
+    assert lib.lec_caption_hinge(null, null, 0, 3, 1.0, null, null, null, null, null) == 0
     assert b"16-byte" in lib.lec_error_string(-5)
 
 

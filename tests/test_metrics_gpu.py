@@ -78,3 +78,42 @@ def test_classification_metrics_equal_reference_dict(name, engine):
     for key, v in flat.items():
         np.testing.assert_allclose(float(v), float(g[key]), rtol=1e-6 if key.startswith("median") else 0, atol=0, err_msg=key)
     assert set(flat) == {k for k in g if g[k].shape == () and k != "K"}
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_caption_ranking_hinge_matches_reference_and_oracle(tag):
+    """lec_caption_hinge (ops.caption_ranking_hinge) against the reference's get_image_label_loss
+    (order_embeddings_images.py:533-542, golden) -- values within fp32 summation order, gradients exactly -- and chained
+    behind the CUDA energy op, against autograd through the oracle."""
+    g = load_golden("caption_hinge_" + tag)
+    alpha = float(g["alpha"])
+    Ep = torch.from_numpy(g["E_pos"]).to(DEV).requires_grad_(True)
+    En = torch.from_numpy(g["E_neg"]).to(DEV).requires_grad_(True)
+    S = ops.caption_ranking_hinge(Ep, En, alpha)
+    np.testing.assert_allclose(S.detach().cpu().numpy(), g["S"], rtol=1e-6, atol=1e-7)
+    (S * torch.from_numpy(g["gS"]).to(DEV)).sum().backward()
+    np.testing.assert_allclose(Ep.grad.cpu().numpy(), g["gE_pos"], rtol=2e-6, atol=0)   # count * gS vs repeated adds
+    np.testing.assert_array_equal(En.grad.cpu().numpy(), g["gE_neg"])
+    # NaN energies propagate like torch.clamp and carry no gradient
+    bad = torch.from_numpy(g["E_neg"]).to(DEV)
+    bad[0, 0] = float("nan")
+    S2 = ops.caption_ranking_hinge(torch.from_numpy(g["E_pos"]).to(DEV), bad, alpha)
+    assert torch.isnan(S2[0]) and not torch.isnan(S2[1:]).any()
+    # end to end: Euclidean cone energies of embedded pairs -> ranking hinge, gradients w.r.t. the embeddings
+    gen = torch.Generator().manual_seed(5)
+    B, M, D = 33, 7, 10
+    x = (torch.randn(B, D, generator=gen) * 2 + 4).to(DEV).requires_grad_(True)
+    y = (torch.randn(B, D, generator=gen) * 2 + 6).to(DEV).requires_grad_(True)
+    yn = (torch.randn(B, M, D, generator=gen) * 2 + 5).to(DEV).requires_grad_(True)
+    E_pos = ops.energy(x, y, "euc", 3.0)
+    E_neg = ops.energy(x[:, None, :].expand(B, M, D).reshape(-1, D), yn.reshape(-1, D), "euc", 3.0).view(B, M)
+    loss = ops.caption_ranking_hinge(E_pos, E_neg, 0.3).sum()
+    loss.backward()
+    xc, yc, ync = (t.detach().cpu().double().requires_grad_(True) for t in (x, y, yn))
+    Ep_o = cones.energy("euc", xc, yc, 3.0)
+    En_o = cones.energy("euc", xc[:, None, :].expand(B, M, D).reshape(-1, D), ync.reshape(-1, D), 3.0).view(B, M)
+    So, _, _ = cones.caption_ranking_hinge(Ep_o, En_o, 0.3)
+    So.sum().backward()
+    assert abs(float(loss) - float(So.sum())) <= 1e-5 * abs(float(So.sum()))
+    for got, ref in ((x.grad, xc.grad), (y.grad, yc.grad), (yn.grad, ync.grad)):
+        np.testing.assert_allclose(got.cpu().numpy(), ref.numpy(), rtol=2e-4, atol=2e-5)

@@ -276,3 +276,17 @@ def test_classification_counts_reproduce_reference_metric_dict(name):
     for lvl, (s, e) in enumerate(zip(ls, le)):
         a = (int(tp[s:e].sum()) + int(tn[s:e].sum())) / int((tp + tn + fp + fn)[s:e].sum())
         assert a == float(g["level%d_accuracy" % lvl])
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_caption_ranking_hinge_matches_reference(tag):
+    """oracle.cones.caption_ranking_hinge against OrderEmbeddingWithImagesLossvCaption.get_image_label_loss run on the
+    same energies (order_embeddings_images.py:533-542; tests/golden/caption_hinge_*.npz), values and autograd gradients."""
+    g = load_golden("caption_hinge_" + tag)
+    Ep, En = torch.from_numpy(g["E_pos"]), torch.from_numpy(g["E_neg"])
+    S, dP, dN = cones.caption_ranking_hinge(Ep, En, float(g["alpha"]))
+    np.testing.assert_allclose(S.numpy(), g["S"], rtol=1e-6, atol=1e-7)
+    gS = torch.from_numpy(g["gS"])
+    # (the reference's autograd adds gS_i once per active negative; count * gS_i differs by that summation's rounding)
+    np.testing.assert_allclose((dP * gS).numpy(), g["gE_pos"], rtol=2e-6, atol=0)
+    np.testing.assert_array_equal((dN * gS[:, None]).numpy(), g["gE_neg"])

@@ -290,3 +290,23 @@ def test_caption_ranking_hinge_matches_reference(tag):
     # (the reference's autograd adds gS_i once per active negative; count * gS_i differs by that summation's rounding)
     np.testing.assert_allclose((dP * gS).numpy(), g["gE_pos"], rtol=2e-6, atol=0)
     np.testing.assert_array_equal((dN * gS[:, None]).numpy(), g["gE_neg"])
+
+
+def test_trainer_side_rsgd_helpers_compose_to_the_reference_update():
+    """order_embeddings_h.soft_clip / mob_add / lambda_x / exp_map_x (API-compatibility helpers, plain tensor
+    expressions) composed as order_embeddings_h.py:764-775 composes them give the oracle's -- i.e. the reference's,
+    tests/golden/rsgd_*.npz -- update; the training path itself is the fused CUDA kernel behind rsgd_step."""
+    from learning_embeddings_b200 import order_embeddings_h as oeh
+    gen = torch.Generator().manual_seed(8)
+    n, D, lr = 200, 10, 0.05
+    r_in = cones.inner_radius(0.1)
+    W = torch.randn(n, D, generator=gen, dtype=torch.float64)
+    W = W / W.norm(dim=1, keepdim=True) * (0.05 + 0.94 * torch.rand(n, 1, generator=gen, dtype=torch.float64))
+    grad = torch.randn(n, D, generator=gen, dtype=torch.float64) * 3
+    g_ref, W_ref = cones.rsgd_step(W, grad, lr, r_in)
+    g = grad * (1.0 / oeh.lambda_x(W)) ** 2
+    W_new = oeh.exp_map_x(W, -lr * g, r_in)
+    np.testing.assert_allclose(g.numpy(), g_ref.numpy(), rtol=1e-13, atol=0)
+    np.testing.assert_allclose(W_new.numpy(), W_ref.numpy(), rtol=1e-12, atol=1e-15)
+    norms = W_new.norm(dim=1)
+    assert float(norms.min()) >= r_in * (1 - 1e-12) and float(norms.max()) <= 1 - 1e-5 + 1e-12

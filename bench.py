@@ -725,7 +725,7 @@ def main():
     table0 = init_table(h.n, D, spec["K"], seed=0)
     if spec["geom"] == "euc":
         table0 = torch.randn(h.n, D, generator=torch.Generator().manual_seed(0))   # nn.Embedding default init
-        cfg["update"] = "adam (torch fused, stock optimiser as in the reference)"
+        cfg["update"] = "adam (torch.optim.Adam semantics inside the fused update kernel)"
         cfg["scalar_core"] = "fp32"
 
     # ---------------- reference arm: CPU only, rank 0 only ----------------

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LEC_ABI_VERSION 12
+#define LEC_ABI_VERSION 13
 
 /* geometry of the energy */
 #define LEC_GEOM_EUC 0 /* EucConesLoss.E_operator, order_embeddings.py:954-969 = oe.py:721-739 (cos-space) */
@@ -55,7 +55,7 @@ extern "C" {
 #define LEC_E_ALIGN     (-5) /* rows / grad_rows base not 16-byte aligned */
 #define LEC_E_K         (-6) /* k out of range for top-k */
 #define LEC_E_REPLICAS  (-7) /* grad_replicas < 1 */
-#define LEC_E_PEERS     (-8) /* world/rank/slot out of range or slot_floats too small */
+#define LEC_E_PEERS     (-8) /* world/rank/slot out of range or slot_packets too small */
 #define LEC_E_EMPTY     (-9) /* a negative draw has no candidate (random.choice([]) -> IndexError in the reference) */
 #define LEC_E_INDEX     (-10) /* node index outside [0, n_nodes) */
 #define LEC_MAX_DIM 1024
@@ -66,6 +66,12 @@ int lec_abi_version(void);
 const char* lec_error_string(int code);
 /* kernels launched by this library since load (the bench's gpu_launches claim) */
 int64_t lec_launch_count(void);
+/* Endpoint ids are range-checked on the device against n_rows, as nn.Embedding checks them on the host (the reference
+ * raises IndexError, order_embeddings.py:188-192): a pair with an id outside [0, n_rows) reads and writes nothing out
+ * of bounds, gets energy NaN, contributes neither loss nor gradient, and is counted.  This call returns the count for
+ * the current device since the last reset in *count_out (HOST pointer).  The one entry point that synchronises: it
+ * waits for `stream`. */
+int lec_index_errors(int64_t* count_out, int reset, void* stream);
 
 /* ---- row transforms ----------------------------------------------------------------------------
  * Replaces Embedder.forward (order_embeddings.py:188-200, order_embeddings_h.py:205-228,
@@ -152,94 +158,91 @@ int lec_energy_dense_bwd(int geom, int precision, const float* x, const float* y
 int lec_rsgd_update(float* table, const float* grad, int grad_replicas, int64_t n, int D, int ld_g, float lr,
                     float r_in, int lambda_mode, float* grad_out, void* stream);
 
-/* ---- data-parallel exchange fused into the update (NVLink / NVSwitch peer memory) ------------------
- * One process per GPU; every rank owns an exchange buffer that all ranks have mapped (CUDA IPC /
- * torch symmetric memory), laid out as
- *     float  slot[2][slot_floats]     slot_floats >= n*D + 2, multiple of 4; the last two floats of a
- *                                     slot hold that rank's loss as one double
- *     uint32 flag[2][world]           flag[s][r] = tag of the latest step rank r published into slot s
- * Step t uses slot t % 2 and tag t + 1 (tags increase monotonically; buffers start zeroed).
- *   1. lec_rows_bwd(..., grad_in = my_buf + slot*slot_floats)   partial table gradient of this rank
- *   2. lec_p2p_publish     stores the local loss, then release-stores flag[slot][rank] = tag into EVERY
- *                          rank's buffer over NVLink
- *   3. lec_rsgd_update_p2p waits (acquire) until all world flags of the slot reach tag, then each row's
- *                          gradient is read from all ranks' slots over peer loads and summed in rank order
- *                          (bit-identical on every rank), and the RSGD update of lec_rsgd_update is applied.
- * This is a one-shot all-reduce fused into the update kernel: no NCCL launch, no extra pass.  It replaces
- * the implicit reduce_add of nn.DataParallel in the reference (order_embeddings.py:360).
- * peer_bufs: HOST array of `world` device pointers (rank order).  error_out (optional device int) is set
- * to 1 if a peer's flag did not arrive within ~4 s (the kernel then returns without updating).
+/* ---- fused table update (+ data-parallel exchange over NVLink / NVSwitch peer memory) ---------------
+ * Everything a training iteration does to the parameter table between the pair kernel and the next iteration's
+ * pair kernel, in ONE launch, per table row:
+ *   1. sum of the row's gradient replicas (d loss / d rows from lec_pairs_*), replicas cleared
+ *   2. world > 1: one-shot all-reduce of the row over peer memory (lec_exchange_t below)
+ *   3. vector-Jacobian product of the row transform `row_mode` (autograd through Embedder.forward)
+ *   4. the update rule:
+ *        LEC_UPD_RSGD  order_embeddings_h.py:764-775 (lambda_x :662, exp_map_x :668, mob_add :649, soft_clip :634;
+ *                      joint copy oe_h.py:1604-1644, :1761-1762)
+ *        LEC_UPD_SGD   torch.optim.SGD(lr, momentum)   order_embeddings.py:563, oe.py:1712
+ *        LEC_UPD_ADAM  torch.optim.Adam(lr)            order_embeddings.py:565, oe.py:1714, oe_h.py:1520-1523
+ *        LEC_UPD_NONE  table left alone (grad_out receives d loss / d table)
+ *      hyp_rescale != 0 multiplies the gradient by ((1 - |w|) / 2)^2 first (oe_h.py:1766, :1770) and
+ *      project_shell != 0 projects the updated row into [r_in, 1 - 1e-5] afterwards (soft_clip, oe_h.py:1771) --
+ *      together with LEC_UPD_ADAM that is the reference's default joint hyperbolic update.  RSGD includes both.
+ *   5. rows_out != NULL: the row transform of the UPDATED row into rows_out [n, ld] and its aperture terms into
+ *      aux_out [n, 4] (as lec_rows_fwd), i.e. the Embedder.forward the NEXT iteration starts with
+ * The loss accumulator the pair kernel added into is moved: *loss_step = *loss_acc; *loss_acc = 0 (both optional).
+ *   table       [n, D] raw parameter rows, updated in place
+ *   grad_rows   [grad_replicas, n, ld], 16-byte aligned
+ *   state_m/v   [n, ld] optimizer state owned by the caller, zero before the first step: Adam moments (m, v) or the
+ *               SGD momentum buffer (m; may be NULL when momentum == 0)
+ *   opt_step    1-based step count of the Adam bias correction
+ *   grad_out    optional [n, D]: the gradient as the optimizer saw it (what the reference leaves in weight.grad)
  */
-int lec_p2p_publish(const double* loss_local, void* const* peer_bufs, int64_t slot_floats, int world, int rank,
-                    int slot, uint32_t tag, void* stream);
-int lec_rsgd_update_p2p(float* table, void* const* peer_bufs, int64_t slot_floats, int world, int rank, int slot,
-                        uint32_t tag, int64_t n, int D, float lr, float r_in, int lambda_mode,
-                        double* loss_global_out, int* error_out, void* stream);
+#define LEC_UPD_NONE 0
+#define LEC_UPD_RSGD 1
+#define LEC_UPD_SGD  2
+#define LEC_UPD_ADAM 3
+typedef struct lec_update {
+    int rule, row_mode, geom, lambda_mode /* RSGD: 0 reference 2/(1-|x|), 1 textbook 2/(1-|x|^2) */;
+    int hyp_rescale, project_shell;
+    float K, lr, r_in;
+    float momentum, beta1, beta2, eps; int64_t opt_step;
+    float* table; int64_t n; int D; int ld;
+    float* grad_rows; int grad_replicas;
+    float* state_m; float* state_v;
+    float* rows_out; double* aux_out; float* grad_out;
+    double* loss_acc; double* loss_step;
+} lec_update_t;
+
+/* The exchange of step 2 replaces nn.DataParallel's reduce_add + broadcast of the label table
+ * (order_embeddings.py:360, oe.py:1336,1341): one process per GPU, every rank owns an exchange buffer that all ranks
+ * have mapped (CUDA IPC / torch symmetric memory), laid out as
+ *     packet slot[2][world][slot_packets]      16-byte packets {value, tag, value, tag}
+ * slot_packets >= lec_exchange_packets(n, ld) = n * ld / 2 + 1 (two floats per packet + one packet for the loss).
+ * Step t uses slot t % 2 and tag t + 1 (tags increase; buffers start zeroed).  Every rank stores the replica sum of
+ * each row into source region [rank] of EVERY rank's buffer (remote stores; the 8-byte halves of a packet are written
+ * atomically, so the tag is the arrival flag: no fence, no flag store, one NVLink latency), then polls its OWN buffer
+ * until the `world` packets of the chunk carry the tag and adds them in rank order -- the same bits on every rank, so
+ * the replicas of the table stay identical.  The rank's loss travels the same way; *loss_global = sum over ranks.
+ *   peer_bufs   HOST array of `world` device pointers (rank order)
+ *   error       device int, zero at start: set to 1 when a peer's packets do not arrive within timeout_ms (0 = 30 s).
+ *               From then on the rows concerned and every later lec_update_rows on this rank leave the table
+ *               untouched; the host must treat a non-zero *error as fatal (engine.ConeStep raises).
+ */
+typedef struct lec_exchange {
+    void* const* peer_bufs; int64_t slot_packets; int world, rank, slot; uint32_t tag;
+    double* loss_global; int* error; int64_t timeout_ms;
+} lec_exchange_t;
 #define LEC_MAX_PEERS 16
-
-/* ---- fused update + next step's row transform (label-only Poincare cones) -------------------------
- * order_embeddings_h.py:764-775 followed by the Embedder.forward (:205-228) the NEXT iteration starts with: one launch
- * per step instead of two.  Per table row: sum of the gradient replicas -> RSGD update in place -> shell projection
- * of the updated row into rows_out [n, ld] + its aperture terms aux_out [n, 4] (as lec_rows_fwd with
- * LEC_ROWS_HYP_SHELL) -> the row's gradient replicas cleared for the next lec_pairs_grouped.  The loss accumulator the
- * pair kernel added into is moved: *loss_step = *loss_acc; *loss_acc = 0 (both optional).  Same results as
- * lec_rsgd_update followed by lec_rows_fwd up to the fp32 rounding of a row norm (the kernels reduce it over
- * different team widths).
- */
-int lec_rsgd_update_rows(float* table, float* grad_rows, int grad_replicas, int64_t n, int D, int ld, float lr,
-                         float r_in, int lambda_mode, float K, float* rows_out, double* aux_out, double* loss_acc,
-                         double* loss_step, float* grad_out, void* stream);
-
-/* ---- push exchange (NVLink / NVSwitch peer stores) fused into the same two launches -----------------
- * Exchange buffer layout of every rank:  float slot[2][world][slot_floats]; uint32 flag[2][world]
- * (slot_floats >= n*D + 2, multiple of 4; the last two floats of a source region hold that rank's loss).
- *   lec_p2p_push            replica sum of this rank's gradient -> slot[slot][rank] of EVERY rank's buffer (remote
- *                           stores), replicas cleared, loss moved as above; the last block to finish release-stores
- *                           flag[slot][rank] = tag into every buffer.  counter: device uint32, zero before the first
- *                           call (the kernel leaves it zero).
- *   lec_rsgd_update_rows_p2p waits for the `world` flags of MY buffer, sums the `world` source regions of MY buffer
- *                           in rank order (local loads; bit-identical on every rank), then as lec_rsgd_update_rows.
- * Replaces nn.DataParallel's reduce_add + broadcast (order_embeddings.py:360) with one collective per step that is
- * part of the update launch.
- */
-int lec_p2p_push(float* grad_rows, int grad_replicas, int64_t n, int D, int ld, double* loss_acc, double* loss_step,
-                 void* const* peer_bufs, int64_t slot_floats, int world, int rank, int slot, uint32_t tag,
-                 uint32_t* counter, void* stream);
-int lec_rsgd_update_rows_p2p(float* table, void* const* peer_bufs, int64_t slot_floats, int world, int rank, int slot,
-                             uint32_t tag, int64_t n, int D, int ld, float lr, float r_in, int lambda_mode, float K,
-                             float* rows_out, double* aux_out, double* loss_global_out, int* error_out, void* stream);
+int64_t lec_exchange_packets(int64_t n, int ld);
+int lec_update_rows(const lec_update_t* u, const lec_exchange_t* x /* NULL or world <= 1: single GPU */, void* stream);
 
 /* ---- one whole training step in one call ---------------------------------------------------------
  * The launch sequence of one label-only cone step (what one iteration of the reference's
  * pass_samples('train') loop does between zero_grad() and the weight update, order_embeddings_h.py:752-775 /
- * order_embeddings.py:619-635) issued from C, so the host pays one FFI call per step instead of one per
- * kernel:
- *     lec_rows_fwd (clears grad_rows and *loss) -> lec_pairs_grouped ->
- *       world <= 1, update == RSGD on straight-through rows : lec_rsgd_update on the replicas
- *       world <= 1, otherwise                               : lec_rows_bwd [-> lec_rsgd_update]
- *       world  > 1                                          : lec_rows_bwd into the exchange slot ->
- *                                                             lec_p2p_publish -> lec_rsgd_update_p2p
- * update: 0 none (gradient left in grad_table), 1 RSGD.  ev_pairs_start/stop: optional cudaEvent_t recorded
- * around the pair kernel (for the roofline timing).  All pointers as in the individual entry points.
+ * order_embeddings.py:619-635) issued from C, so the host pays one FFI call per step instead of one per kernel:
+ *     [fused == 0: lec_rows_fwd (clears grad_rows and *loss_acc) ->]  lec_pairs_grouped -> lec_update_rows
+ * fused != 0: rows / aux / cleared grad_rows are already current -- a previous step's lec_update_rows (with rows_out)
+ * or lec_rows_fwd produced them -- so the step is two launches, each a programmatic dependent of the one before.
+ * The pair kernel adds into *upd.loss_acc; the update leaves this rank's loss of the step in *upd.loss_step.
+ * Table geometry (n, D, ld, K), rows (upd.rows_out), aux (upd.aux_out) and the gradient replicas are taken from `upd`.
+ * ev_pairs_start/stop: optional cudaEvent_t recorded around the pair kernel (for the roofline timing).
  */
 typedef struct lec_step {
-    int geom, precision, row_mode, update, lambda_mode;
-    float K, alpha, lr, r_in;
-    float* table; int64_t n; int D; int ld;
-    float* rows; double* aux; float* grad_rows; int grad_replicas; float* grad_table;
+    int geom, precision, fused;
+    float alpha;
     const void* pos_from; const void* pos_to; const void* neg_to; const void* neg_from; int idx_bytes;
     int64_t B; int N;
     const float* w_pos; const float* w_neg;
-    float* E_pos; float* E_neg; double* loss;
-    void* const* peer_bufs; int64_t slot_floats; int world, rank, slot; uint32_t tag;
-    double* loss_global; int* error;
+    float* E_pos; float* E_neg;
     void* ev_pairs_start; void* ev_pairs_stop;
-    /* fused != 0 (RSGD on LEC_ROWS_HYP_SHELL rows only): rows / aux / cleared grad_rows are already current (a
-     * previous fused step or lec_rows_fwd produced them), the pair kernel adds into *loss_acc, and the step is
-     *     lec_pairs_grouped -> lec_rsgd_update_rows                              (world <= 1)
-     *     lec_pairs_grouped -> lec_p2p_push -> lec_rsgd_update_rows_p2p          (world  > 1, push layout)
-     * leaving this rank's loss of the step in *loss.  counter: see lec_p2p_push. */
-    int fused; double* loss_acc; uint32_t* counter;
+    lec_update_t upd;
+    lec_exchange_t xchg;
 } lec_step_t;
 int lec_cone_step(const lec_step_t* s, void* stream);
 

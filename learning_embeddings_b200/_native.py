@@ -14,13 +14,13 @@ LIB_PATH = os.path.join(_HERE, "_lib", "liblec_b200.so")
 GEOM = {"euc": 0, "hyp": 1, "oe": 2}
 ROWS_NONE, ROWS_EUC_SOFTCLIP, ROWS_HYP_SHELL, ROWS_HYP_TANH, ROWS_HYP_TANH_FEAT = 0, 1, 2, 3, 4
 PREC_F32, PREC_F64CORE = 0, 1
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 EXPORTS = (
-    "lec_abi_version", "lec_error_string", "lec_launch_count", "lec_rows_fwd", "lec_rows_bwd", "lec_reduce_replicas",
-    "lec_pairs_flat",
-    "lec_pairs_grouped", "lec_energy_dense", "lec_energy_dense_bwd", "lec_rsgd_update", "lec_p2p_publish",
-    "lec_rsgd_update_p2p", "lec_rsgd_update_rows", "lec_p2p_push", "lec_rsgd_update_rows_p2p", "lec_cone_step", "lec_score_topk", "lec_score_topk_ex", "lec_score_tc_supported",
+    "lec_abi_version", "lec_error_string", "lec_launch_count", "lec_index_errors", "lec_rows_fwd", "lec_rows_bwd",
+    "lec_reduce_replicas", "lec_pairs_flat", "lec_pairs_grouped", "lec_energy_dense", "lec_energy_dense_bwd",
+    "lec_rsgd_update", "lec_exchange_packets", "lec_update_rows", "lec_cone_step", "lec_score_topk", "lec_score_topk_ex",
+    "lec_score_tc_supported",
     "lec_score_workspace_bytes", "lec_score_topk_tc", "lec_mt_seed", "lec_mt_uint32", "lec_mt_randbelow",
     "lec_sample_negatives", "lec_sample_negatives_philox", "lec_philox_below", "lec_f1_workspace_bytes", "lec_f1_sweep",
     "lec_classify_counts", "lec_caption_hinge",
@@ -31,27 +31,47 @@ class LecError(RuntimeError):
     pass
 
 
+class LecUpdate(ctypes.Structure):
+    """lec_update_t of include/lec_b200.h."""
+    _fields_ = [
+        ("rule", ctypes.c_int), ("row_mode", ctypes.c_int), ("geom", ctypes.c_int), ("lambda_mode", ctypes.c_int),
+        ("hyp_rescale", ctypes.c_int), ("project_shell", ctypes.c_int),
+        ("K", ctypes.c_float), ("lr", ctypes.c_float), ("r_in", ctypes.c_float),
+        ("momentum", ctypes.c_float), ("beta1", ctypes.c_float), ("beta2", ctypes.c_float), ("eps", ctypes.c_float),
+        ("opt_step", ctypes.c_int64),
+        ("table", ctypes.c_void_p), ("n", ctypes.c_int64), ("D", ctypes.c_int), ("ld", ctypes.c_int),
+        ("grad_rows", ctypes.c_void_p), ("grad_replicas", ctypes.c_int),
+        ("state_m", ctypes.c_void_p), ("state_v", ctypes.c_void_p),
+        ("rows_out", ctypes.c_void_p), ("aux_out", ctypes.c_void_p), ("grad_out", ctypes.c_void_p),
+        ("loss_acc", ctypes.c_void_p), ("loss_step", ctypes.c_void_p),
+    ]
+
+
+class LecExchange(ctypes.Structure):
+    """lec_exchange_t of include/lec_b200.h."""
+    _fields_ = [
+        ("peer_bufs", ctypes.c_void_p), ("slot_packets", ctypes.c_int64), ("world", ctypes.c_int), ("rank", ctypes.c_int),
+        ("slot", ctypes.c_int), ("tag", ctypes.c_uint32),
+        ("loss_global", ctypes.c_void_p), ("error", ctypes.c_void_p), ("timeout_ms", ctypes.c_int64),
+    ]
+
+
 class LecStep(ctypes.Structure):
     """lec_step_t of include/lec_b200.h."""
     _fields_ = [
-        ("geom", ctypes.c_int), ("precision", ctypes.c_int), ("row_mode", ctypes.c_int), ("update", ctypes.c_int),
-        ("lambda_mode", ctypes.c_int),
-        ("K", ctypes.c_float), ("alpha", ctypes.c_float), ("lr", ctypes.c_float), ("r_in", ctypes.c_float),
-        ("table", ctypes.c_void_p), ("n", ctypes.c_int64), ("D", ctypes.c_int), ("ld", ctypes.c_int),
-        ("rows", ctypes.c_void_p), ("aux", ctypes.c_void_p), ("grad_rows", ctypes.c_void_p),
-        ("grad_replicas", ctypes.c_int), ("grad_table", ctypes.c_void_p),
+        ("geom", ctypes.c_int), ("precision", ctypes.c_int), ("fused", ctypes.c_int),
+        ("alpha", ctypes.c_float),
         ("pos_from", ctypes.c_void_p), ("pos_to", ctypes.c_void_p), ("neg_to", ctypes.c_void_p),
         ("neg_from", ctypes.c_void_p), ("idx_bytes", ctypes.c_int),
         ("B", ctypes.c_int64), ("N", ctypes.c_int),
         ("w_pos", ctypes.c_void_p), ("w_neg", ctypes.c_void_p),
-        ("E_pos", ctypes.c_void_p), ("E_neg", ctypes.c_void_p), ("loss", ctypes.c_void_p),
-        ("peer_bufs", ctypes.c_void_p), ("slot_floats", ctypes.c_int64), ("world", ctypes.c_int),
-        ("rank", ctypes.c_int), ("slot", ctypes.c_int), ("tag", ctypes.c_uint32),
-        ("loss_global", ctypes.c_void_p), ("error", ctypes.c_void_p),
+        ("E_pos", ctypes.c_void_p), ("E_neg", ctypes.c_void_p),
         ("ev_pairs_start", ctypes.c_void_p), ("ev_pairs_stop", ctypes.c_void_p),
-        ("fused", ctypes.c_int), ("loss_acc", ctypes.c_void_p), ("counter", ctypes.c_void_p),
+        ("upd", LecUpdate), ("xchg", LecExchange),
     ]
 
+
+UPD_NONE, UPD_RSGD, UPD_SGD, UPD_ADAM = 0, 1, 2, 3
 
 _lib = None
 
@@ -84,15 +104,10 @@ def lib():
         L.lec_energy_dense.argtypes = [c_i, c_i, c_vp, c_vp, c_i64, c_i, c_f, c_vp, c_vp]
         L.lec_energy_dense_bwd.argtypes = [c_i, c_i, c_vp, c_vp, c_vp, c_i64, c_i, c_f, c_vp, c_vp, c_vp]
         L.lec_rsgd_update.argtypes = [c_vp, c_vp, c_i, c_i64, c_i, c_i, c_f, c_f, c_i, c_vp, c_vp]
-        L.lec_p2p_publish.argtypes = [c_vp, c_vp, c_i64, c_i, c_i, c_i, ctypes.c_uint32, c_vp]
-        L.lec_rsgd_update_p2p.argtypes = [c_vp, c_vp, c_i64, c_i, c_i, c_i, ctypes.c_uint32, c_i64, c_i, c_f, c_f, c_i,
-                                          c_vp, c_vp, c_vp]
-        L.lec_rsgd_update_rows.argtypes = [c_vp, c_vp, c_i, c_i64, c_i, c_i, c_f, c_f, c_i, c_f, c_vp, c_vp, c_vp, c_vp, c_vp,
-                                           c_vp]
-        L.lec_p2p_push.argtypes = [c_vp, c_i, c_i64, c_i, c_i, c_vp, c_vp, c_vp, c_i64, c_i, c_i, c_i, ctypes.c_uint32,
-                                   c_vp, c_vp]
-        L.lec_rsgd_update_rows_p2p.argtypes = [c_vp, c_vp, c_i64, c_i, c_i, c_i, ctypes.c_uint32, c_i64, c_i, c_i, c_f, c_f,
-                                               c_i, c_f, c_vp, c_vp, c_vp, c_vp, c_vp]
+        L.lec_index_errors.argtypes = [c_vp, c_i, c_vp]
+        L.lec_exchange_packets.argtypes = [c_i64, c_i]
+        L.lec_exchange_packets.restype = c_i64
+        L.lec_update_rows.argtypes = [ctypes.POINTER(LecUpdate), ctypes.POINTER(LecExchange), c_vp]
         L.lec_cone_step.argtypes = [ctypes.POINTER(LecStep), c_vp]
         L.lec_score_topk.argtypes = [c_i, c_i, c_vp, c_i64, c_vp, c_i64, c_i, c_f, c_vp, c_vp, c_i, c_i, c_vp, c_vp,
                                      c_vp, c_vp]
@@ -142,3 +157,17 @@ def require_cuda(*tensors):
 
 def launch_count():
     return int(lib().lec_launch_count())
+
+
+def index_errors(device=None, reset=True):
+    """Pairs whose endpoint id fell outside the table since the last reset (lec_index_errors; synchronises the stream)."""
+    n = ctypes.c_int64(0)
+    check(lib().lec_index_errors(ctypes.byref(n), 1 if reset else 0, stream_ptr(device)), "lec_index_errors")
+    return int(n.value)
+
+
+def raise_on_index_errors(device=None):
+    bad = index_errors(device)
+    if bad:
+        raise IndexError("%d pair endpoint ids were outside the embedding table (nn.Embedding raises IndexError in the "
+                         "reference); those pairs got energy NaN and no gradient" % bad)

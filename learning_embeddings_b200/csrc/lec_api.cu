@@ -2,8 +2,15 @@
 #include "lec_pairs_impl.cuh"
 
 namespace lec {
-unsigned long long g_launches = 0;
+std::atomic<unsigned long long> g_launches{0};
 thread_local int t_pdl = 0;
+
+// pairs whose endpoint id fell outside the table since the last lec_index_errors(reset) (per device)
+__device__ unsigned g_index_errors = 0;
+static unsigned* index_errors_ptr() {
+    void* p = nullptr;
+    return cudaGetSymbolAddress(&p, g_index_errors) == cudaSuccess ? static_cast<unsigned*>(p) : nullptr;
+}
 
 int launch_flat_euc32(const FlatArgs&, cudaStream_t);
 int launch_flat_hyp32(const FlatArgs&, cudaStream_t);
@@ -22,13 +29,7 @@ int rows_fwd_launch(const float*, int64_t, int, int, int, float, float*, int, do
 int rows_bwd_launch(const float*, const float*, int, int64_t, int, int, int, float, float*, int, cudaStream_t);
 int rsgd_launch(float*, const float*, int, int64_t, int, int, float, float, int, float*, cudaStream_t);
 int reduce_replicas_launch(const float*, int, int64_t, float*, cudaStream_t);
-int p2p_publish_launch(const double*, void* const*, int64_t, int, int, int, unsigned, cudaStream_t);
-int rsgd_p2p_launch(float*, void* const*, int64_t, int, int, int, unsigned, int64_t, int, float, float, int, double*, int*,
-                    int, float, float*, int, double*, cudaStream_t);
-int rsgd_rows_launch(float*, float*, int, int64_t, int, int, float, float, int, float, float*, double*, double*, double*,
-                     float*, cudaStream_t);
-int p2p_push_launch(float*, int, int64_t, int, int, double*, double*, void* const*, int64_t, int, int, int, unsigned,
-                    unsigned*, cudaStream_t);
+int update_rows_launch(const lec_update_t&, const lec_exchange_t*, cudaStream_t);
 int score_launch(int, int, const float*, int64_t, const float*, int64_t, int, float, const int32_t*, const int32_t*,
                  int, int, float*, int64_t, int64_t, int32_t*, float*, cudaStream_t);
 
@@ -61,7 +62,19 @@ extern "C" {
 
 int lec_abi_version(void) { return LEC_ABI_VERSION; }
 
-int64_t lec_launch_count(void) { return (int64_t)g_launches; }
+int64_t lec_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int lec_index_errors(int64_t* count_out, int reset, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned* dev = index_errors_ptr();
+    if (!dev) return (int)cudaGetLastError();
+    unsigned host = 0;
+    cudaError_t e = cudaMemcpyAsync(&host, dev, sizeof(host), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && reset) e = cudaMemsetAsync(dev, 0, sizeof(unsigned), st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (count_out) *count_out = (int64_t)host;
+    return (int)e;
+}
 
 const char* lec_error_string(int code) {
     switch (code) {
@@ -75,7 +88,7 @@ const char* lec_error_string(int code) {
         case LEC_E_REPLICAS: return "grad_replicas must be >= 1";
         case LEC_E_EMPTY: return "negative sampler: a draw has no candidate (the reference's random.choice raises IndexError)";
         case LEC_E_INDEX: return "node index outside [0, n_nodes)";
-        case LEC_E_PEERS: return "peer exchange: need 1 <= world <= 16, 0 <= rank < world, slot in {0,1}, slot_floats >= n*D+2 and % 4 == 0";
+        case LEC_E_PEERS: return "peer exchange: need 2 <= world <= 16, 0 <= rank < world, slot in {0,1}, slot_packets >= n*ld/2+1, non-NULL peer buffers";
     }
     if (code > 0) return cudaGetErrorString((cudaError_t)code);
     return "unknown lec error";
@@ -125,7 +138,7 @@ int lec_pairs_flat(int geom, int precision, const float* rows, const double* aux
     if (geom != LEC_GEOM_OE && !aux) return LEC_E_NULL;
     if (aux && (reinterpret_cast<uintptr_t>(aux) & 15)) return LEC_E_ALIGN;
     FlatArgs a{rows, aux, ld, from_idx, to_idx, idx_bytes, w, is_pos, P, K, alpha, E_out, loss_out, grad_rows,
-               grad_replicas, n_rows * (int64_t)ld};
+               grad_replicas, n_rows * (int64_t)ld, n_rows, index_errors_ptr()};
     cudaStream_t st = (cudaStream_t)stream;
     switch (core) {
         case CORE_EUC32: return launch_flat_euc32(a, st);
@@ -151,7 +164,7 @@ int lec_pairs_grouped(int geom, int precision, const float* rows, const double* 
     if (geom != LEC_GEOM_OE && !aux) return LEC_E_NULL;
     if (aux && (reinterpret_cast<uintptr_t>(aux) & 15)) return LEC_E_ALIGN;
     GroupArgs a{rows, aux, ld, pos_from, pos_to, neg_to, neg_from, idx_bytes, B, N, w_pos, w_neg, K, alpha,
-                E_pos, E_neg, loss_out, grad_rows, grad_replicas, n_rows * (int64_t)ld};
+                E_pos, E_neg, loss_out, grad_rows, grad_replicas, n_rows * (int64_t)ld, n_rows, index_errors_ptr()};
     cudaStream_t st = (cudaStream_t)stream;
     switch (core) {
         case CORE_EUC32: return launch_grouped_euc32(a, st);
@@ -200,130 +213,70 @@ int lec_rsgd_update(float* table, const float* grad, int grad_replicas, int64_t 
     return rsgd_launch(table, grad, grad_replicas, n, D, ld_g, lr, r_in, lambda_mode, grad_out, (cudaStream_t)stream);
 }
 
-static int check_peers(void* const* peer_bufs, int64_t slot_floats, int world, int rank, int slot) {
-    if (!peer_bufs) return LEC_E_NULL;
-    if (world < 1 || world > LEC_MAX_PEERS || rank < 0 || rank >= world || (slot != 0 && slot != 1)) return LEC_E_PEERS;
-    if (slot_floats < 4 || (slot_floats & 3)) return LEC_E_PEERS;
-    for (int p = 0; p < world; ++p)
-        if (!peer_bufs[p]) return LEC_E_NULL;
+static int check_update(const lec_update_t* u) {
+    if (!u) return LEC_E_NULL;
+    if (u->rule < LEC_UPD_NONE || u->rule > LEC_UPD_ADAM) return LEC_E_ENUM;
+    if (u->row_mode < LEC_ROWS_NONE || u->row_mode > LEC_ROWS_HYP_TANH) return LEC_E_ENUM;   // table modes only
+    if (u->lambda_mode != 0 && u->lambda_mode != 1) return LEC_E_ENUM;
+    if (u->aux_out && (u->geom < LEC_GEOM_EUC || u->geom > LEC_GEOM_OE)) return LEC_E_ENUM;
+    if (!u->table || !u->grad_rows) return LEC_E_NULL;
+    if (u->grad_replicas < 1) return LEC_E_REPLICAS;
+    if (u->n < 0) return LEC_E_SIZE;
+    if (u->D < 1 || u->D > LEC_MAX_DIM || u->ld < u->D || (u->ld & 3)) return LEC_E_DIM;
+    if (reinterpret_cast<uintptr_t>(u->grad_rows) & 15) return LEC_E_ALIGN;
+    if (u->rows_out && (reinterpret_cast<uintptr_t>(u->rows_out) & 15)) return LEC_E_ALIGN;
+    if (u->aux_out && (reinterpret_cast<uintptr_t>(u->aux_out) & 15)) return LEC_E_ALIGN;
+    if (u->rule == LEC_UPD_ADAM && (!u->state_m || !u->state_v)) return LEC_E_NULL;
+    if (u->rule == LEC_UPD_SGD && u->momentum != 0.f && !u->state_m) return LEC_E_NULL;
+    if ((u->state_m && (reinterpret_cast<uintptr_t>(u->state_m) & 15)) || (u->state_v && (reinterpret_cast<uintptr_t>(u->state_v) & 15)))
+        return LEC_E_ALIGN;
     return 0;
 }
 
-int lec_p2p_publish(const double* loss_local, void* const* peer_bufs, int64_t slot_floats, int world, int rank, int slot,
-                    uint32_t tag, void* stream) {
-    if (int e = check_peers(peer_bufs, slot_floats, world, rank, slot)) return e;
-    return p2p_publish_launch(loss_local, peer_bufs, slot_floats, world, rank, slot, tag, (cudaStream_t)stream);
+static int check_exchange(const lec_exchange_t* x, int64_t n, int ld) {
+    if (!x || x->world <= 1) return 0;
+    if (!x->peer_bufs) return LEC_E_NULL;
+    if (x->world > LEC_MAX_PEERS || x->rank < 0 || x->rank >= x->world || (x->slot != 0 && x->slot != 1) || x->tag == 0)
+        return LEC_E_PEERS;
+    if (x->slot_packets < lec_exchange_packets(n, ld)) return LEC_E_PEERS;
+    for (int p = 0; p < x->world; ++p) {
+        if (!x->peer_bufs[p]) return LEC_E_NULL;
+        if (reinterpret_cast<uintptr_t>(x->peer_bufs[p]) & 15) return LEC_E_ALIGN;
+    }
+    return 0;
 }
 
-int lec_rsgd_update_p2p(float* table, void* const* peer_bufs, int64_t slot_floats, int world, int rank, int slot,
-                        uint32_t tag, int64_t n, int D, float lr, float r_in, int lambda_mode, double* loss_global_out,
-                        int* error_out, void* stream) {
-    if (!table) return LEC_E_NULL;
-    if (int e = check_peers(peer_bufs, slot_floats, world, rank, slot)) return e;
-    if (n < 0) return LEC_E_SIZE;
-    if (D < 1 || D > LEC_MAX_DIM) return LEC_E_DIM;
-    if (slot_floats < n * D + 2) return LEC_E_PEERS;
-    if (lambda_mode != 0 && lambda_mode != 1) return LEC_E_ENUM;
-    return rsgd_p2p_launch(table, peer_bufs, slot_floats, world, rank, slot, tag, n, D, lr, r_in, lambda_mode,
-                           loss_global_out, error_out, 0, 0.f, nullptr, 0, nullptr, (cudaStream_t)stream);
-}
+int64_t lec_exchange_packets(int64_t n, int ld) { return (n < 0 || ld < 0) ? 0 : n * (int64_t)ld / 2 + 1; }
 
-int lec_rsgd_update_rows(float* table, float* grad_rows, int grad_replicas, int64_t n, int D, int ld, float lr, float r_in,
-                         int lambda_mode, float K, float* rows_out, double* aux_out, double* loss_acc, double* loss_step,
-                         float* grad_out, void* stream) {
-    if (!table || !grad_rows || !rows_out) return LEC_E_NULL;
-    if (grad_replicas < 1) return LEC_E_REPLICAS;
-    if (n < 0) return LEC_E_SIZE;
-    if (D < 1 || D > LEC_MAX_DIM || ld < D || (ld & 3)) return LEC_E_DIM;
-    if (lambda_mode != 0 && lambda_mode != 1) return LEC_E_ENUM;
-    return rsgd_rows_launch(table, grad_rows, grad_replicas, n, D, ld, lr, r_in, lambda_mode, K, rows_out, aux_out, loss_acc,
-                            loss_step, grad_out, (cudaStream_t)stream);
-}
-
-int lec_p2p_push(float* grad_rows, int grad_replicas, int64_t n, int D, int ld, double* loss_acc, double* loss_step,
-                 void* const* peer_bufs, int64_t slot_floats, int world, int rank, int slot, uint32_t tag,
-                 uint32_t* counter, void* stream) {
-    if (!grad_rows || !loss_acc || !counter) return LEC_E_NULL;
-    if (int e = check_peers(peer_bufs, slot_floats, world, rank, slot)) return e;
-    if (grad_replicas < 1) return LEC_E_REPLICAS;
-    if (n < 0) return LEC_E_SIZE;
-    if (D < 1 || D > LEC_MAX_DIM || ld < D || (ld & 3)) return LEC_E_DIM;
-    if (slot_floats < n * D + 2) return LEC_E_PEERS;
-    return p2p_push_launch(grad_rows, grad_replicas, n, D, ld, loss_acc, loss_step, peer_bufs, slot_floats, world, rank, slot,
-                           tag, counter, (cudaStream_t)stream);
-}
-
-int lec_rsgd_update_rows_p2p(float* table, void* const* peer_bufs, int64_t slot_floats, int world, int rank, int slot,
-                             uint32_t tag, int64_t n, int D, int ld, float lr, float r_in, int lambda_mode, float K,
-                             float* rows_out, double* aux_out, double* loss_global_out, int* error_out, void* stream) {
-    if (!table || !rows_out) return LEC_E_NULL;
-    if (int e = check_peers(peer_bufs, slot_floats, world, rank, slot)) return e;
-    if (n < 0) return LEC_E_SIZE;
-    if (D < 1 || D > LEC_MAX_DIM || ld < D || (ld & 3)) return LEC_E_DIM;
-    if (slot_floats < n * D + 2) return LEC_E_PEERS;
-    if (lambda_mode != 0 && lambda_mode != 1) return LEC_E_ENUM;
-    return rsgd_p2p_launch(table, peer_bufs, slot_floats, world, rank, slot, tag, n, D, lr, r_in, lambda_mode,
-                           loss_global_out, error_out, 1, K, rows_out, ld, aux_out, (cudaStream_t)stream);
+int lec_update_rows(const lec_update_t* u, const lec_exchange_t* x, void* stream) {
+    if (int e = check_update(u)) return e;
+    if (int e = check_exchange(x, u->n, u->ld)) return e;
+    return update_rows_launch(*u, x, (cudaStream_t)stream);
 }
 
 int lec_cone_step(const lec_step_t* s, void* stream) {
     if (!s) return LEC_E_NULL;
-    if (s->update != 0 && s->update != 1) return LEC_E_ENUM;
-    if (!s->grad_rows || !s->loss) return LEC_E_NULL;
-    if (s->fused) {
-        if (s->update != 1 || s->row_mode != LEC_ROWS_HYP_SHELL) return LEC_E_ENUM;
-        if (!s->loss_acc) return LEC_E_NULL;
-        struct PdlScope {   // the kernels of this step are launched as programmatic dependents of one another
-            PdlScope() { static const int on = [] { const char* e = getenv("LEC_PDL"); return e ? atoi(e) : 1; }(); t_pdl = on; }
-            ~PdlScope() { t_pdl = 0; }
-        } pdl_scope;
-        cudaStream_t st = (cudaStream_t)stream;
-        if (s->ev_pairs_start) cudaEventRecord((cudaEvent_t)s->ev_pairs_start, st);
-        int e = lec_pairs_grouped(s->geom, s->precision, s->rows, s->aux, s->n, s->D, s->ld, s->pos_from, s->pos_to, s->neg_to,
-                                  s->neg_from, s->idx_bytes, s->B, s->N, s->w_pos, s->w_neg, s->K, s->alpha, s->E_pos, s->E_neg,
-                                  s->loss_acc, s->grad_rows, s->grad_replicas, stream);
-        if (s->ev_pairs_stop) cudaEventRecord((cudaEvent_t)s->ev_pairs_stop, st);
-        if (e) return e;
-        if (s->world > 1) {
-            e = lec_p2p_push(s->grad_rows, s->grad_replicas, s->n, s->D, s->ld, s->loss_acc, s->loss, s->peer_bufs,
-                             s->slot_floats, s->world, s->rank, s->slot, s->tag, s->counter, stream);
-            if (e) return e;
-            return lec_rsgd_update_rows_p2p(s->table, s->peer_bufs, s->slot_floats, s->world, s->rank, s->slot, s->tag, s->n,
-                                            s->D, s->ld, s->lr, s->r_in, s->lambda_mode, s->K, s->rows, s->aux,
-                                            s->loss_global, s->error, stream);
-        }
-        return lec_rsgd_update_rows(s->table, s->grad_rows, s->grad_replicas, s->n, s->D, s->ld, s->lr, s->r_in,
-                                    s->lambda_mode, s->K, s->rows, s->aux, s->loss_acc, s->loss, s->grad_table, stream);
-    }
-    int e = lec_rows_fwd(s->table, s->n, s->D, s->row_mode, s->geom, s->K, s->rows, s->ld, s->aux, s->grad_rows,
-                         s->grad_replicas, s->loss, stream);
-    if (e) return e;
+    const lec_update_t& u = s->upd;
+    if (int e = check_update(&u)) return e;
+    if (int e = check_exchange(&s->xchg, u.n, u.ld)) return e;
+    if (!u.rows_out || !u.loss_acc) return LEC_E_NULL;
+    struct PdlScope {   // the kernels of this step are launched as programmatic dependents of one another
+        PdlScope() { static const int on = [] { const char* e = getenv("LEC_PDL"); return e ? atoi(e) : 1; }(); t_pdl = on; }
+        ~PdlScope() { t_pdl = 0; }
+    } pdl_scope;
     cudaStream_t st = (cudaStream_t)stream;
+    if (!s->fused) {
+        const int e = lec_rows_fwd(u.table, u.n, u.D, u.row_mode, s->geom, u.K, u.rows_out, u.ld, u.aux_out, u.grad_rows,
+                                   u.grad_replicas, u.loss_acc, stream);
+        if (e) return e;
+    }
     if (s->ev_pairs_start) cudaEventRecord((cudaEvent_t)s->ev_pairs_start, st);
-    e = lec_pairs_grouped(s->geom, s->precision, s->rows, s->aux, s->n, s->D, s->ld, s->pos_from, s->pos_to, s->neg_to,
-                          s->neg_from, s->idx_bytes, s->B, s->N, s->w_pos, s->w_neg, s->K, s->alpha, s->E_pos, s->E_neg,
-                          s->loss, s->grad_rows, s->grad_replicas, stream);
+    const int e = lec_pairs_grouped(s->geom, s->precision, u.rows_out, u.aux_out, u.n, u.D, u.ld, s->pos_from, s->pos_to,
+                                    s->neg_to, s->neg_from, s->idx_bytes, s->B, s->N, s->w_pos, s->w_neg, u.K, s->alpha,
+                                    s->E_pos, s->E_neg, u.loss_acc, u.grad_rows, u.grad_replicas, stream);
     if (s->ev_pairs_stop) cudaEventRecord((cudaEvent_t)s->ev_pairs_stop, st);
     if (e) return e;
-    if (s->world > 1) {
-        if (s->update != 1) return LEC_E_ENUM;  // the fused exchange exists for the RSGD update
-        if (int pe = check_peers(s->peer_bufs, s->slot_floats, s->world, s->rank, s->slot)) return pe;
-        if (s->slot_floats < s->n * s->D + 2) return LEC_E_PEERS;
-        float* mine = static_cast<float*>(s->peer_bufs[s->rank]) + (int64_t)s->slot * s->slot_floats;
-        e = lec_rows_bwd(s->table, s->grad_rows, s->grad_replicas, s->n, s->D, s->ld, s->row_mode, s->K, mine, 0, stream);
-        if (e) return e;
-        e = lec_p2p_publish(s->loss, s->peer_bufs, s->slot_floats, s->world, s->rank, s->slot, s->tag, stream);
-        if (e) return e;
-        return lec_rsgd_update_p2p(s->table, s->peer_bufs, s->slot_floats, s->world, s->rank, s->slot, s->tag, s->n, s->D,
-                                   s->lr, s->r_in, s->lambda_mode, s->loss_global, s->error, stream);
-    }
-    if (s->update == 1 && s->row_mode == LEC_ROWS_HYP_SHELL)
-        return lec_rsgd_update(s->table, s->grad_rows, s->grad_replicas, s->n, s->D, s->ld, s->lr, s->r_in, s->lambda_mode,
-                               s->grad_table, stream);
-    if (!s->grad_table) return LEC_E_NULL;
-    e = lec_rows_bwd(s->table, s->grad_rows, s->grad_replicas, s->n, s->D, s->ld, s->row_mode, s->K, s->grad_table, 0, stream);
-    if (e || s->update == 0) return e;
-    return lec_rsgd_update(s->table, s->grad_table, 1, s->n, s->D, s->D, s->lr, s->r_in, s->lambda_mode, s->grad_table, stream);
+    return update_rows_launch(u, &s->xchg, st);
 }
 
 int lec_score_topk_ex(int geom, int precision, const float* labels, int64_t L, const float* images, int64_t N, int D,

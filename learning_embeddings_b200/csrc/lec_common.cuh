@@ -8,6 +8,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/lec_b200.h"
 
 namespace lec {
@@ -16,7 +18,7 @@ constexpr int kThreads = 256;
 constexpr float kNormEps = 1e-12f;   // F.normalize eps (order_embeddings.py:197, :965)
 constexpr float kClampEps = 1e-5f;   // acos/asin clamp (order_embeddings_h.py:1113-1114)
 
-extern unsigned long long g_launches;  // host-side counter (lec_api.cu)
+extern std::atomic<unsigned long long> g_launches;  // host-side launch counter (lec_api.cu); callers may be on several threads
 
 // Programmatic dependent launch.  lec_cone_step sets t_pdl around its launches: each kernel of the step is then
 // launched with programmatic stream serialisation, i.e. its blocks may become resident while the previous kernel of the
@@ -27,10 +29,10 @@ extern thread_local int t_pdl;
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 template <typename Arg>
-inline void launch_step_kernel(void (*kern)(const Arg), int grid, int block, cudaStream_t st, const Arg& a, size_t smem = 0) {
+inline cudaError_t launch_step_kernel(void (*kern)(const Arg), int grid, int block, cudaStream_t st, const Arg& a, size_t smem = 0) {
     if (!t_pdl) {
         kern<<<grid, block, smem, st>>>(a);
-        return;
+        return cudaGetLastError();
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
@@ -42,7 +44,7 @@ inline void launch_step_kernel(void (*kern)(const Arg), int grid, int block, cud
     at.val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = &at;
     cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, kern, a);
+    return cudaLaunchKernelEx(&cfg, kern, a);
 }
 
 template <int V>

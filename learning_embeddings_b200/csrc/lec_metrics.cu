@@ -16,10 +16,12 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/lec_b200.h"
 
 namespace lec {
-extern unsigned long long g_launches;  // lec_api.cu
+extern std::atomic<unsigned long long> g_launches;  // lec_api.cu
 
 namespace {
 

@@ -25,6 +25,7 @@ struct FlatArgs {
     const float* w; const uint8_t* is_pos;
     int64_t P; float K, alpha;
     float* E_out; double* loss_out; float* grad_rows; int grad_replicas; int64_t replica_stride;
+    int64_t n_rows; unsigned* index_errors;
 };
 
 struct GroupArgs {
@@ -34,6 +35,7 @@ struct GroupArgs {
     const float* w_pos; const float* w_neg;
     float K, alpha;
     float* E_pos; float* E_neg; double* loss_out; float* grad_rows; int grad_replicas; int64_t replica_stride;
+    int64_t n_rows; unsigned* index_errors;
     int split;  // teams per group (>= 1): team s of a group takes negatives p = s, s + split, ... of both lists
     int64_t stage_floats;  // > 0: every block first copies the transformed table (n * ld floats) into shared memory
 };
@@ -48,6 +50,18 @@ __device__ __forceinline__ int64_t ld_index(const void* p, int64_t i, int idx_by
     if (idx_bytes == 4) return (int64_t)__ldg(reinterpret_cast<const int32_t*>(p) + i);
     if (idx_bytes == 2) return (int64_t)__ldg(reinterpret_cast<const unsigned short*>(p) + i);
     return (int64_t)__ldg(reinterpret_cast<const long long*>(p) + i);
+}
+
+// Row number with the range check nn.Embedding does on the host (IndexError in the reference): an id outside
+// [0, n_rows) is counted in *errors (lec_index_errors), replaced by row 0 so that nothing is read or written out of
+// bounds, and `ok` is cleared -- the caller then emits NaN for the pair and no gradient.
+__device__ __forceinline__ int64_t ld_index_checked(const void* p, int64_t i, int idx_bytes, int64_t n_rows,
+                                                    unsigned* errors, bool count, bool& ok) {
+    const int64_t ix = ld_index(p, i, idx_bytes);
+    if ((uint64_t)ix < (uint64_t)n_rows) return ix;
+    if (count && errors) atomicAdd(errors, 1u);
+    ok = false;
+    return 0;
 }
 
 // z and (optionally) the dz/dx, dz/dy coefficients of one pair held by a team.
@@ -100,8 +114,9 @@ __global__ void __launch_bounds__(kThreads) pairs_flat_kernel(const FlatArgs a) 
         const int64_t p = team + it * n_teams;
         const bool valid = p < a.P;
         const int64_t pc = valid ? p : a.P - 1;
-        const int64_t ix = ld_index(a.from_idx, pc, a.idx_bytes);
-        const int64_t iy = ld_index(a.to_idx, pc, a.idx_bytes);
+        bool ok = true;
+        const int64_t ix = ld_index_checked(a.from_idx, pc, a.idx_bytes, a.n_rows, a.index_errors, valid && lane_t == 0, ok);
+        const int64_t iy = ld_index_checked(a.to_idx, pc, a.idx_bytes, a.n_rows, a.index_errors, valid && lane_t == 0, ok);
         Vec<V> X, Y;
         load_row<T, V>(X, a.rows, ix, a.ld, lane_t);
         load_row<T, V>(Y, a.rows, iy, a.ld, lane_t);
@@ -117,10 +132,10 @@ __global__ void __launch_bounds__(kThreads) pairs_flat_kernel(const FlatArgs a) 
         double l = 0.0;
         const float cf = hinge(g.z, pos, w, a.alpha, E, l);
         if (valid && lane_t == 0) {
-            a.E_out[p] = E;
-            loss += l;
+            a.E_out[p] = ok ? E : NAN;
+            if (ok) loss += l;
         }
-        if (GRAD && valid && cf != 0.f) {
+        if (GRAD && valid && ok && cf != 0.f) {
             float* gx = grad_base + ix * (int64_t)a.ld;
             float* gy = grad_base + iy * (int64_t)a.ld;
 #pragma unroll
@@ -188,8 +203,9 @@ __global__ void __launch_bounds__(kThreads, MB) pairs_grouped_kernel(const Group
         const int sub = (int)(ic_item - gidx * split);
         const int64_t gc = gidx;
         const bool writer = valid && lane_t == 0;
-        const int64_t iu = ld_index(a.pos_from, gc, a.idx_bytes);
-        const int64_t iv = ld_index(a.pos_to, gc, a.idx_bytes);
+        bool ok_g = true;   // both shared endpoints inside the table
+        const int64_t iu = ld_index_checked(a.pos_from, gc, a.idx_bytes, a.n_rows, a.index_errors, writer && sub == 0, ok_g);
+        const int64_t iv = ld_index_checked(a.pos_to, gc, a.idx_bytes, a.n_rows, a.index_errors, writer && sub == 0, ok_g);
         Vec<V> U, W;
         load_row<T, V>(U, rows_p, iu, a.ld, lane_t, staged);
         load_row<T, V>(W, rows_p, iv, a.ld, lane_t, staged);
@@ -214,9 +230,9 @@ __global__ void __launch_bounds__(kThreads, MB) pairs_grouped_kernel(const Group
             const float w = a.w_pos ? __ldg(a.w_pos + gc) : 1.f;
             double lp = 0.0;
             const float cf = hinge(g.z, true, w, a.alpha, E, lp);
-            if (act) l += lp;
-            if (writer && act) a.E_pos[gidx] = E;
-            if (GRAD && valid && act && cf != 0.f) {
+            if (act && ok_g) l += lp;
+            if (writer && act) a.E_pos[gidx] = ok_g ? E : NAN;
+            if (GRAD && valid && act && ok_g && cf != 0.f) {
                 touch_u = touch_w = true;
                 if (!Tr::cone) {
 #pragma unroll
@@ -240,7 +256,8 @@ __global__ void __launch_bounds__(kThreads, MB) pairs_grouped_kernel(const Group
             const int pr = sub + pi * split;
             const bool act = pr < N;
             const int p = act ? pr : N - 1;
-            const int64_t ic = ld_index(a.neg_to, nbase + p, a.idx_bytes);
+            bool ok = ok_g;
+            const int64_t ic = ld_index_checked(a.neg_to, nbase + p, a.idx_bytes, a.n_rows, a.index_errors, writer && act, ok);
             Vec<V> C;
             load_row<T, V>(C, rows_p, ic, a.ld, lane_t, staged);
             Acc AC = 0;
@@ -249,9 +266,9 @@ __global__ void __launch_bounds__(kThreads, MB) pairs_grouped_kernel(const Group
             const float w = a.w_neg ? __ldg(a.w_neg + ebase + p) : 1.f;
             double lp = 0.0;
             const float cf = hinge(g.z, false, w, a.alpha, E, lp);
-            if (act) l += lp;
-            if (writer && act) a.E_neg[ebase + p] = E;
-            if (GRAD && valid && act && cf != 0.f) {
+            if (act && ok) l += lp;
+            if (writer && act) a.E_neg[ebase + p] = ok ? E : NAN;
+            if (GRAD && valid && act && ok && cf != 0.f) {
                 touch_u = true;
                 float* gcp = grad_base + ic * (int64_t)a.ld;
                 if (Tr::cone) su_u += cf * g.zxx;
@@ -275,7 +292,8 @@ __global__ void __launch_bounds__(kThreads, MB) pairs_grouped_kernel(const Group
             const int pr = sub + pi * split;
             const bool act = pr < N;
             const int p = act ? pr : N - 1;
-            const int64_t ic = ld_index(a.neg_from, nbase + p, a.idx_bytes);
+            bool ok = ok_g;
+            const int64_t ic = ld_index_checked(a.neg_from, nbase + p, a.idx_bytes, a.n_rows, a.index_errors, writer && act, ok);
             Vec<V> C;
             load_row<T, V>(C, rows_p, ic, a.ld, lane_t, staged);
             Aux<Acc> ac{};
@@ -284,9 +302,9 @@ __global__ void __launch_bounds__(kThreads, MB) pairs_grouped_kernel(const Group
             const float w = a.w_neg ? __ldg(a.w_neg + ebase + N + p) : 1.f;
             double lp = 0.0;
             const float cf = hinge(g.z, false, w, a.alpha, E, lp);
-            if (act) l += lp;
-            if (writer && act) a.E_neg[ebase + N + p] = E;
-            if (GRAD && valid && act && cf != 0.f) {
+            if (act && ok) l += lp;
+            if (writer && act) a.E_neg[ebase + N + p] = ok ? E : NAN;
+            if (GRAD && valid && act && ok && cf != 0.f) {
                 touch_w = true;
                 float* gcp = grad_base + ic * (int64_t)a.ld;
                 if (Tr::cone) sw_w += cf * g.zyy;
@@ -306,7 +324,7 @@ __global__ void __launch_bounds__(kThreads, MB) pairs_grouped_kernel(const Group
             }
         }
         if (writer) loss += l;
-        if (GRAD && valid) {
+        if (GRAD && valid && ok_g) {
             float* gu = grad_base + iu * (int64_t)a.ld;
             float* gw = grad_base + iv * (int64_t)a.ld;
 #pragma unroll
@@ -441,15 +459,16 @@ int launch_grouped_tv(const GroupArgs& a0, cudaStream_t st) {
     const bool stage = stage_env != 0 && table_floats * 4 <= 40960;
     a.stage_floats = stage ? table_floats : 0;
     const size_t smem = stage ? (size_t)table_floats * 4 : 0;
+    cudaError_t le;
     if (mb == 2) {
-        if (a.grad_rows) launch_step_kernel(pairs_grouped_kernel<CORE, T, V, true, 2>, grid, block, st, a, smem);
-        else launch_step_kernel(pairs_grouped_kernel<CORE, T, V, false, 2>, grid, block, st, a, smem);
+        if (a.grad_rows) le = launch_step_kernel(pairs_grouped_kernel<CORE, T, V, true, 2>, grid, block, st, a, smem);
+        else le = launch_step_kernel(pairs_grouped_kernel<CORE, T, V, false, 2>, grid, block, st, a, smem);
     } else {
-        if (a.grad_rows) launch_step_kernel(pairs_grouped_kernel<CORE, T, V, true, 1>, grid, block, st, a, smem);
-        else launch_step_kernel(pairs_grouped_kernel<CORE, T, V, false, 1>, grid, block, st, a, smem);
+        if (a.grad_rows) le = launch_step_kernel(pairs_grouped_kernel<CORE, T, V, true, 1>, grid, block, st, a, smem);
+        else le = launch_step_kernel(pairs_grouped_kernel<CORE, T, V, false, 1>, grid, block, st, a, smem);
     }
     ++g_launches;
-    return (int)cudaGetLastError();
+    return (int)(le != cudaSuccess ? le : cudaGetLastError());
 }
 
 #define LEC_DISPATCH_TV(FN, CORE, Q, ...)                                   \

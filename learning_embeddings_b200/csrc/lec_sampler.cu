@@ -19,10 +19,12 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/lec_b200.h"
 
 namespace lec {
-extern unsigned long long g_launches;  // lec_api.cu
+extern std::atomic<unsigned long long> g_launches;  // lec_api.cu
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -1,0 +1,500 @@
+// Fused table update: everything a training step does to the parameter table between the pair kernel and the next
+// step's pair kernel, in ONE launch, one team of TT lanes per table row, the row held in registers as V float4 chunks
+// per lane (chunk q = lane + TT*j, the layout of the transformed table):
+//
+//   1. sum of the row's gradient replicas (d loss / d rows, scattered by the pair kernel), replicas cleared
+//   2. world > 1: one-shot all-reduce of that row over NVLink / NVSwitch peer memory, low-latency protocol: every rank
+//      stores its partial row into its source region of EVERY rank's exchange buffer as 16-byte packets
+//      {value, tag, value, tag} (8-byte halves are written atomically, so the tag IS the arrival flag: no fence, no
+//      separate flag store, one NVLink one-way latency), then polls its OWN buffer until the `world` packets of the chunk
+//      carry this step's tag and adds them in rank order (identical bits on every rank)
+//   3. vector-Jacobian product of the row transform (Embedder.forward): d loss / d table
+//   4. the update rule on the raw row: Riemannian SGD (order_embeddings_h.py:764-775), SGD with momentum or Adam
+//      (torch.optim, order_embeddings.py:563-565), optionally preceded by the conformal rescale ((1-|w|)/2)^2 and followed
+//      by the shell projection of the joint hyperbolic trainer (oe_h.py:1765-1771)
+//   5. the row transform of the UPDATED row -- the Embedder.forward the next iteration starts with -- and its per-row
+//      aperture terms (aux), so the next pair kernel can start right away
+//
+// 12*D bytes per row at least (read w, read g, write w); with the fused transform ~24*D (+ optimizer state).
+#include "lec_rowops.cuh"
+
+namespace lec {
+
+struct UpdArgs {
+    int rule, row_mode, geom, lambda_mode, hyp_rescale, project_shell;
+    float K, lr, r_in, r_in_rows, c0;
+    float momentum, beta1, beta2, eps, step_size, inv_bc2_sqrt;
+    float* table; int64_t n; int D; int ld; int tv;   // tv: widest aligned vector access of a raw table row (4, 2, 1 floats)
+    float* grad_rows; int replicas; int64_t replica_stride;
+    float* m; float* v;
+    float* rows_out; double* aux_out; float* grad_out;
+    double* loss_acc; double* loss_step;
+    int world, rank, slot; unsigned tag; int64_t slot_packets; uint4* peer[kMaxPeers];
+    double* loss_global; int* error; unsigned long long timeout_ns;
+};
+
+// ---- low-latency packets -------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ll_store(uint4* p, unsigned a, unsigned b, unsigned tag) {
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(tag), "r"(b), "r"(tag) : "memory");
+}
+__device__ __forceinline__ uint4 ll_load(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ int ld_volatile_int(const int* p) {
+    int v;
+    asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Spins until the packet at p carries `tag` in both halves.  Returns false (and raises *error) when the peer does not
+// deliver within timeout_ns, or when another thread already raised *error: the caller then drops the row's update.
+__device__ __forceinline__ bool ll_wait(const uint4* p, unsigned tag, uint4& pk, int* error, unsigned long long timeout_ns,
+                                        unsigned long long& t0) {
+    unsigned spins = 0;
+    while (pk.y != tag || pk.w != tag) {
+        pk = ll_load(p);
+        if ((++spins & 1023u) == 0) {
+            if (t0 == 0) t0 = global_ns();
+            if ((error && ld_volatile_int(error) != 0) || global_ns() - t0 > timeout_ns) {
+                if (error) atomicExch(error, 1);
+                return false;
+            }
+        }
+    }
+    return true;
+}
+
+// my partial chunk -> source region `rank` of every rank's buffer
+__device__ __forceinline__ void ll_push_chunk(const UpdArgs& a, int64_t packet, float4 g) {
+    const int64_t off = ((int64_t)a.slot * a.world + a.rank) * a.slot_packets + packet;
+    for (int p = 0; p < a.world; ++p) {
+        uint4* dst = a.peer[p] + off;
+        ll_store(dst, __float_as_uint(g.x), __float_as_uint(g.y), a.tag);
+        ll_store(dst + 1, __float_as_uint(g.z), __float_as_uint(g.w), a.tag);
+    }
+}
+
+// sum over the ranks, in rank order, of the chunk at `packet` of my own buffer; up to eight sources polled at a time
+__device__ __forceinline__ bool ll_reduce_chunk(const UpdArgs& a, int64_t packet, float4& out, unsigned long long& t0) {
+    const uint4* mine = a.peer[a.rank] + (int64_t)a.slot * a.world * a.slot_packets + packet;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool ok = true;
+    for (int p0 = 0; p0 < a.world; p0 += 8) {
+        uint4 pk[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (p0 + i < a.world) {
+                const uint4* src = mine + (int64_t)(p0 + i) * a.slot_packets;
+                pk[2 * i] = ll_load(src);
+                pk[2 * i + 1] = ll_load(src + 1);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (p0 + i < a.world) {
+                const uint4* src = mine + (int64_t)(p0 + i) * a.slot_packets;
+                ok = ok && ll_wait(src, a.tag, pk[2 * i], a.error, a.timeout_ns, t0);
+                ok = ok && ll_wait(src + 1, a.tag, pk[2 * i + 1], a.error, a.timeout_ns, t0);
+                acc.x += __uint_as_float(pk[2 * i].x); acc.y += __uint_as_float(pk[2 * i].z);
+                acc.z += __uint_as_float(pk[2 * i + 1].x); acc.w += __uint_as_float(pk[2 * i + 1].z);
+            }
+        }
+    }
+    out = acc;
+    return ok;
+}
+
+// ---- raw table rows (row stride D floats, so only D % 4 == 0 rows are 16-byte aligned) ------------------------------
+template <int TT, int V>
+__device__ __forceinline__ void load_raw(float (&e)[4 * V], const float* __restrict__ w, int D, int lane, int tv) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        const int d0 = 4 * (lane + TT * j);
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (d0 < D) {
+            if (tv == 4) {
+                x = *reinterpret_cast<const float4*>(w + d0);
+            } else if (tv == 2) {
+                const float2 lo = *reinterpret_cast<const float2*>(w + d0);
+                x.x = lo.x; x.y = lo.y;
+                if (d0 + 2 < D) { const float2 hi = *reinterpret_cast<const float2*>(w + d0 + 2); x.z = hi.x; x.w = hi.y; }
+            } else {
+                x.x = w[d0];
+                if (d0 + 1 < D) x.y = w[d0 + 1];
+                if (d0 + 2 < D) x.z = w[d0 + 2];
+                if (d0 + 3 < D) x.w = w[d0 + 3];
+            }
+        }
+        e[4 * j] = x.x; e[4 * j + 1] = x.y; e[4 * j + 2] = x.z; e[4 * j + 3] = x.w;
+    }
+}
+
+template <int TT, int V>
+__device__ __forceinline__ void store_raw(float* __restrict__ w, const float (&e)[4 * V], int D, int lane, int tv) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        const int d0 = 4 * (lane + TT * j);
+        if (d0 < D) {
+            if (tv == 4) {
+                *reinterpret_cast<float4*>(w + d0) = make_float4(e[4 * j], e[4 * j + 1], e[4 * j + 2], e[4 * j + 3]);
+            } else if (tv == 2) {
+                *reinterpret_cast<float2*>(w + d0) = make_float2(e[4 * j], e[4 * j + 1]);
+                if (d0 + 2 < D) *reinterpret_cast<float2*>(w + d0 + 2) = make_float2(e[4 * j + 2], e[4 * j + 3]);
+            } else {
+                w[d0] = e[4 * j];
+                if (d0 + 1 < D) w[d0 + 1] = e[4 * j + 1];
+                if (d0 + 2 < D) w[d0 + 2] = e[4 * j + 2];
+                if (d0 + 3 < D) w[d0 + 3] = e[4 * j + 3];
+            }
+        }
+    }
+}
+
+// padded [n, ld] buffers (optimizer state, transformed rows): whole float4 chunks
+template <int TT, int V>
+__device__ __forceinline__ void load_chunks(float (&x)[4 * V], const float* __restrict__ p, int Q, int lane) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        const int q = lane + TT * j;
+        const float4 c = q < Q ? *reinterpret_cast<const float4*>(p + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        x[4 * j] = c.x; x[4 * j + 1] = c.y; x[4 * j + 2] = c.z; x[4 * j + 3] = c.w;
+    }
+}
+template <int TT, int V>
+__device__ __forceinline__ void store_chunks(float* __restrict__ p, const float (&x)[4 * V], int Q, int lane) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        const int q = lane + TT * j;
+        if (q < Q) *reinterpret_cast<float4*>(p + 4 * q) = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+    }
+}
+
+template <int TT, int V>
+__device__ __forceinline__ float sumsq32(const float (&x)[4 * V]) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4 * V; ++i) s = fmaf(x[i], x[i], s);
+    return team_sum<TT, float>(s);
+}
+
+template <int TT, int V, bool XCHG>
+__global__ void __launch_bounds__(kThreads) update_rows_kernel(const UpdArgs a) {
+    __shared__ AuxBatch s_aux;
+    int aux_fill = 0;
+    pdl_launch_dependents();
+    pdl_wait();   // the pair kernel's reductions into the replicas (and its loss) are complete
+    if (XCHG && a.error && ld_volatile_int(a.error) != 0) return;   // an earlier exchange failed: the table is left alone
+    const int lane = threadIdx.x % TT;
+    const int64_t n_teams = (int64_t)gridDim.x * (kThreads / TT);
+    const int64_t team = (int64_t)blockIdx.x * (kThreads / TT) + threadIdx.x / TT;
+    const int64_t iters = (a.n + n_teams - 1) / n_teams;
+    const int D = a.D, Q = a.ld >> 2;
+    unsigned long long t0 = 0;
+    double my_loss = 0.0;
+    const bool loss_thread = blockIdx.x == 0 && threadIdx.x == 0;
+    if (loss_thread && a.loss_acc) my_loss = *a.loss_acc;
+    if (XCHG && blockIdx.x == 0 && (int)threadIdx.x < a.world && a.loss_acc) {
+        // this rank's loss of the step travels as one more packet of its source region
+        const double l = *a.loss_acc;
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(l);
+        uint4* dst = a.peer[threadIdx.x] + ((int64_t)a.slot * a.world + a.rank) * a.slot_packets + a.n * (int64_t)Q * 2;
+        ll_store(dst, (unsigned)(bits & 0xffffffffu), (unsigned)(bits >> 32), a.tag);
+    }
+    const bool hyp = a.row_mode >= LEC_ROWS_HYP_SHELL;
+    for (int64_t it = 0; it < iters; ++it) {
+        const int64_t row = team + it * n_teams;
+        bool valid = row < a.n;
+        const int64_t rc = valid ? row : 0;
+        // ---- 1. gradient wrt the transformed row: replica sum, replicas cleared -------------------------------------
+        float g[4 * V];
+        {
+            float* gr = a.grad_rows + rc * (int64_t)a.ld;
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                const int q = lane + TT * j;
+                float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (q < Q) {
+                    c = rsum4(gr + 4 * q, a.replicas, a.replica_stride);
+                    if (valid)
+                        for (int r = 0; r < a.replicas; ++r)
+                            *reinterpret_cast<float4*>(gr + r * a.replica_stride + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                g[4 * j] = c.x; g[4 * j + 1] = c.y; g[4 * j + 2] = c.z; g[4 * j + 3] = c.w;
+            }
+        }
+        // ---- 2. all-reduce over the ranks -----------------------------------------------------------------------------
+        if (XCHG) {
+            bool ok = true;
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    const int q = lane + TT * j;
+                    if (q < Q) ll_push_chunk(a, (row * Q + q) * 2, make_float4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]));
+                }
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    const int q = lane + TT * j;
+                    if (q < Q) {
+                        float4 s;
+                        ok = ll_reduce_chunk(a, (row * Q + q) * 2, s, t0) && ok;
+                        g[4 * j] = s.x; g[4 * j + 1] = s.y; g[4 * j + 2] = s.z; g[4 * j + 3] = s.w;
+                    }
+                }
+            }
+            // a row whose exchange failed is left untouched (the host raises on *error); the vote keeps teams uniform
+            if (__any_sync(0xffffffffu, !ok)) valid = false;
+        }
+        // ---- 3. raw row, VJP of the row transform: g <- d loss / d table ---------------------------------------------
+        float e[4 * V];
+        float* w = a.table + rc * (int64_t)D;
+        load_raw<TT, V>(e, w, D, lane, a.tv);
+        if (a.row_mode == LEC_ROWS_EUC_SOFTCLIP) {
+            // out = e/|e| * (|e| + K)  (order_embeddings.py:195-200):  J^T g = (1 + K/r) g - K <e,g> / r^3 e
+            float ss = 0.f, eg = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4 * V; ++i) { ss = fmaf(e[i], e[i], ss); eg = fmaf(e[i], g[i], eg); }
+            ss = team_sum<TT, float>(ss); eg = team_sum<TT, float>(eg);
+            const float r = sqrtf(ss);
+            const float c_g = 1.f + a.K / r, c_e = -a.K * eg / (r * ss);
+#pragma unroll
+            for (int i = 0; i < 4 * V; ++i) g[i] = fmaf(c_e, e[i], c_g * g[i]);
+        } else if (a.row_mode == LEC_ROWS_HYP_TANH) {
+            // out = tanh(clamp(c0 + r)) e'/r, e' = e + 1e-15 (oe_h.py:77-104); the projection behind it is straight-through
+            float ss = 0.f, eg = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4 * V; ++i) {
+                const int d = 4 * (lane + TT * (i >> 2)) + (i & 3);
+                const float ev = d < D ? e[i] + 1e-15f : 0.f;
+                ss = fmaf(ev, ev, ss); eg = fmaf(ev, g[i], eg);
+            }
+            ss = team_sum<TT, float>(ss); eg = team_sum<TT, float>(eg);
+            const float r = sqrtf(ss);
+            const float arg = a.c0 + r;
+            const float t = tanhf(fminf(fmaxf(arg, -15.f), 15.f));
+            const float tp = (arg >= -15.f && arg <= 15.f) ? (1.f - t * t) : 0.f;
+            const float c_g = t / r, c_e = (tp - t / r) * eg / ss;
+#pragma unroll
+            for (int i = 0; i < 4 * V; ++i) {
+                const int d = 4 * (lane + TT * (i >> 2)) + (i & 3);
+                g[i] = d < D ? fmaf(c_e, e[i] + 1e-15f, c_g * g[i]) : 0.f;
+            }
+        }
+        // ---- 4. update rule ------------------------------------------------------------------------------------------
+        if (a.rule == LEC_UPD_RSGD) {
+            // One pass gives the five row sums every later quantity is an algebraic function of (v = -lr gs g + 1e-15,
+            // t = th v/|v| + 1e-6, the Moebius sums <w,t>, |t|^2 and the norm of the result), carried in fp64:
+            double uu = 0.0, gg = 0.0, eg = 0.0, se = 0.0, sg = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4 * V; ++i) {
+                const double ed = (double)e[i], gd = (double)g[i];
+                uu = fma(ed, ed, uu); gg = fma(gd, gd, gg); eg = fma(ed, gd, eg); se += ed; sg += gd;
+            }
+            uu = team_sum<TT, double>(uu); gg = team_sum<TT, double>(gg); eg = team_sum<TT, double>(eg);
+            se = team_sum<TT, double>(se); sg = team_sum<TT, double>(sg);
+            // conformal factor (order_embeddings_h.py:662-666; SURVEY F4: the norm, not its square)
+            const float wn = (float)sqrt(uu);
+            const float lam = 2.f / (1.f - (a.lambda_mode == 1 ? (float)uu : wn));
+            const float inv = 1.f / lam;
+            const float gs = inv * inv;
+            const double Dn = (double)D, e15 = 1e-15, e6 = 1e-6;
+            const double av = -(double)a.lr * (double)gs;                     // v_d = av g_d + 1e-15
+            const double vv = av * av * gg + 2.0 * av * e15 * sg + Dn * e15 * e15;
+            const double vn = sqrt(vv);
+            const float th = tanhf(fminf(fmaxf(lam * (float)vn / 2.f, -15.f), 15.f));
+            const double c = (double)th / vn;
+            const double al = c * av, be = c * e15 + e6;                      // t_d = al g_d + be
+            const double tt = al * al * gg + 2.0 * al * be * sg + Dn * be * be;
+            const double uv2 = 2.0 * (al * eg + be * se);
+            const double den = 1.0 + uv2 + tt * uu;
+            const double cw = (1.0 + uv2 + tt) / den, ct = (1.0 - uu) / den;
+            const double cg = ct * al, cb = ct * be;                          // res_d = cw e_d + cg g_d + cb
+            const double rr = cw * cw * uu + cg * cg * gg + Dn * cb * cb + 2.0 * (cw * cg * eg + cw * cb * se + cg * cb * sg);
+            float mul, add, div;
+            shell_factor((float)sqrt(rr), a.r_in, false, mul, add, div);
+            const float sc = (mul != 1.f || div != 1.f) ? mul / div : 1.f;
+            const float f_w = (float)cw * sc, f_g = (float)cg * sc, f_b = (float)cb * sc;
+            float* go = (valid && a.grad_out) ? a.grad_out + row * (int64_t)D : nullptr;
+            if (go) {
+                float rg[4 * V];
+#pragma unroll
+                for (int i = 0; i < 4 * V; ++i) rg[i] = g[i] * gs;            // the Riemannian gradient, as left in weight.grad
+                store_raw<TT, V>(go, rg, D, lane, a.tv);
+            }
+#pragma unroll
+            for (int i = 0; i < 4 * V; ++i) {
+                const int d = 4 * (lane + TT * (i >> 2)) + (i & 3);
+                e[i] = d < D ? fmaf(f_w, e[i], fmaf(f_g, g[i], f_b)) : 0.f;
+            }
+        } else {
+            if (a.hyp_rescale) {
+                // Euclidean -> Riemannian gradient of the joint hyperbolic trainer: grad *= (1/lambda_x(w))^2, oe_h.py:1766
+                const float wn = sqrtf(sumsq32<TT, V>(e));
+                const float inv = (1.f - wn) * 0.5f;
+                const float gs = inv * inv;
+#pragma unroll
+                for (int i = 0; i < 4 * V; ++i) g[i] *= gs;
+            }
+            if (valid && a.grad_out) store_raw<TT, V>(a.grad_out + row * (int64_t)D, g, D, lane, a.tv);
+            if (a.rule == LEC_UPD_SGD) {
+                // torch.optim.SGD: buf = momentum * buf + g (buf starts at 0, which equals its first-step rule); p -= lr * buf
+                if (a.m && a.momentum != 0.f) {
+                    float mb[4 * V];
+                    float* mp = a.m + rc * (int64_t)a.ld;
+                    load_chunks<TT, V>(mb, mp, Q, lane);
+#pragma unroll
+                    for (int i = 0; i < 4 * V; ++i) { mb[i] = fmaf(a.momentum, mb[i], g[i]); g[i] = mb[i]; }
+                    if (valid) store_chunks<TT, V>(mp, mb, Q, lane);
+                }
+#pragma unroll
+                for (int i = 0; i < 4 * V; ++i) e[i] = fmaf(-a.lr, g[i], e[i]);
+            } else if (a.rule == LEC_UPD_ADAM) {
+                // torch.optim.Adam (_single_tensor_adam, no amsgrad / weight decay):
+                //   m.lerp_(g, 1-b1); v = v*b2 + (1-b2) g g; p += -(lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)
+                float mb[4 * V], vb[4 * V];
+                float* mp = a.m + rc * (int64_t)a.ld;
+                float* vp = a.v + rc * (int64_t)a.ld;
+                load_chunks<TT, V>(mb, mp, Q, lane);
+                load_chunks<TT, V>(vb, vp, Q, lane);
+                const float w1 = 1.f - a.beta1, w2 = 1.f - a.beta2;
+#pragma unroll
+                for (int i = 0; i < 4 * V; ++i) {
+                    mb[i] = fmaf(w1, g[i] - mb[i], mb[i]);
+                    vb[i] = fmaf(w2 * g[i], g[i], __fmul_rn(vb[i], a.beta2));
+                    const float den = sqrtf(vb[i]) * a.inv_bc2_sqrt + a.eps;
+                    e[i] = fmaf(-a.step_size, mb[i] / den, e[i]);
+                }
+                if (valid) { store_chunks<TT, V>(mp, mb, Q, lane); store_chunks<TT, V>(vp, vb, Q, lane); }
+            }
+            if (a.project_shell) {
+                // soft_clip on the table itself (oe_h.py:1604-1618, called at :1771): |w| <= r_in -> r_in, |w| >= 1 -> 1 - 1e-5
+                float mul, add, div;
+                shell_factor(sqrtf(sumsq32<TT, V>(e)), a.r_in, false, mul, add, div);
+                if (mul != 1.f || div != 1.f) {
+#pragma unroll
+                    for (int i = 0; i < 4 * V; ++i) e[i] = (e[i] / div) * mul;
+                }
+            }
+        }
+        if (valid && a.rule != LEC_UPD_NONE) store_raw<TT, V>(w, e, D, lane, a.tv);
+        // ---- 5. Embedder.forward of the updated row + its aperture terms ---------------------------------------------
+        if (a.rows_out) {
+            if (hyp) {
+#pragma unroll
+                for (int i = 0; i < 4 * V; ++i) {
+                    const int d = 4 * (lane + TT * (i >> 2)) + (i & 3);
+                    e[i] = d < D ? __fadd_rn(e[i], 1e-15f) : 0.f;
+                }
+            }
+            if (a.row_mode != LEC_ROWS_NONE) {
+                const float r = sqrtf(sumsq32<TT, V>(e));
+                if (a.row_mode == LEC_ROWS_EUC_SOFTCLIP) {
+                    const float rn = fmaxf(r, kNormEps), scale = r + a.K;
+#pragma unroll
+                    for (int i = 0; i < 4 * V; ++i) e[i] = (e[i] / rn) * scale;
+                } else {
+                    float r2 = r;
+                    if (a.row_mode != LEC_ROWS_HYP_SHELL) {
+                        const float rn = fmaxf(r, kNormEps);
+                        const float scale = tanhf(fminf(fmaxf(a.c0 + r, -15.f), 15.f));
+#pragma unroll
+                        for (int i = 0; i < 4 * V; ++i) e[i] = scale * (e[i] / rn);
+                        r2 = sqrtf(sumsq32<TT, V>(e));
+                    }
+                    float mul, add, div;
+                    shell_factor(r2, a.r_in_rows, false, mul, add, div);
+                    if (mul != 1.f || div != 1.f) {
+#pragma unroll
+                        for (int i = 0; i < 4 * V; ++i) {
+                            const int d = 4 * (lane + TT * (i >> 2)) + (i & 3);
+                            e[i] = d < D ? __fmul_rn((add + e[i]) / div, mul) : 0.f;
+                        }
+                    }
+                }
+            }
+            if (valid) store_chunks<TT, V>(a.rows_out + row * (int64_t)a.ld, e, Q, lane);
+            if (a.aux_out) {
+                double A = 0.0;
+#pragma unroll
+                for (int i = 0; i < 4 * V; ++i) A = fma((double)e[i], (double)e[i], A);
+                A = team_sum<TT, double>(A);
+                aux_push<TT>(s_aux, aux_fill, A, row, valid, a.geom, a.K, a.aux_out);
+            }
+        }
+    }
+    if (a.rows_out && a.aux_out) aux_flush<TT>(s_aux, aux_fill, a.geom, a.K, a.aux_out);
+    if (loss_thread && a.loss_acc) {
+        if (a.loss_step) *a.loss_step = my_loss;
+        *a.loss_acc = 0.0;
+        if (XCHG && a.loss_global) {
+            const uint4* mine = a.peer[a.rank] + (int64_t)a.slot * a.world * a.slot_packets + a.n * (int64_t)Q * 2;
+            double l = 0.0;
+            bool ok = true;
+            for (int p = 0; p < a.world; ++p) {
+                const uint4* src = mine + (int64_t)p * a.slot_packets;
+                uint4 pk = ll_load(src);
+                ok = ok && ll_wait(src, a.tag, pk, a.error, a.timeout_ns, t0);
+                l += __longlong_as_double((long long)(((unsigned long long)pk.z << 32) | (unsigned long long)pk.x));
+            }
+            if (ok) *a.loss_global = l;
+        }
+    }
+}
+
+constexpr int kUpdGridCap = 148 * 8;   // the same on every rank: a block's rows are the same rows everywhere
+
+template <int TT, int V>
+static int update_go(const UpdArgs& a, cudaStream_t st) {
+    const int tpb = kThreads / TT;
+    int64_t need = (a.n + tpb - 1) / tpb;
+    if (need < 1) need = 1;
+    const int grid = (int)(need < kUpdGridCap ? need : kUpdGridCap);
+    cudaError_t e;
+    if (a.world > 1) e = launch_step_kernel(update_rows_kernel<TT, V, true>, grid, kThreads, st, a);
+    else e = launch_step_kernel(update_rows_kernel<TT, V, false>, grid, kThreads, st, a);
+    ++g_launches;
+    return (int)(e != cudaSuccess ? e : cudaGetLastError());
+}
+
+int update_rows_launch(const lec_update_t& u, const lec_exchange_t* x, cudaStream_t st) {
+    UpdArgs a{};
+    a.rule = u.rule; a.row_mode = u.row_mode; a.geom = u.geom; a.lambda_mode = u.lambda_mode;
+    a.hyp_rescale = u.hyp_rescale; a.project_shell = u.project_shell;
+    a.K = u.K; a.lr = u.lr; a.r_in = u.r_in;
+    hyp_constants(u.K, a.r_in_rows, a.c0);
+    a.momentum = u.momentum; a.beta1 = u.beta1; a.beta2 = u.beta2; a.eps = u.eps;
+    if (u.rule == LEC_UPD_ADAM) {
+        const double t = (double)(u.opt_step < 1 ? 1 : u.opt_step);
+        a.step_size = (float)((double)u.lr / (1.0 - pow((double)u.beta1, t)));
+        a.inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - pow((double)u.beta2, t)));
+    }
+    a.table = u.table; a.n = u.n; a.D = u.D; a.ld = u.ld;
+    const uintptr_t base = reinterpret_cast<uintptr_t>(u.table);
+    uintptr_t go = reinterpret_cast<uintptr_t>(u.grad_out);
+    a.tv = ((u.D & 3) == 0 && (base & 15) == 0 && (go & 15) == 0) ? 4 : (((u.D & 1) == 0 && (base & 7) == 0 && (go & 7) == 0) ? 2 : 1);
+    a.grad_rows = u.grad_rows; a.replicas = u.grad_replicas; a.replica_stride = u.n * (int64_t)u.ld;
+    a.m = u.state_m; a.v = u.state_v;
+    a.rows_out = u.rows_out; a.aux_out = u.aux_out; a.grad_out = u.grad_out;
+    a.loss_acc = u.loss_acc; a.loss_step = u.loss_step;
+    a.world = 0;
+    if (x && x->world > 1) {
+        a.world = x->world; a.rank = x->rank; a.slot = x->slot; a.tag = x->tag; a.slot_packets = x->slot_packets;
+        for (int p = 0; p < x->world; ++p) a.peer[p] = static_cast<uint4*>(x->peer_bufs[p]);
+        a.loss_global = x->loss_global; a.error = x->error;
+        a.timeout_ns = (unsigned long long)(x->timeout_ms > 0 ? x->timeout_ms : 30000) * 1000000ull;
+    }
+    if (u.n == 0) return 0;
+    const int Q = u.ld >> 2;
+    if (Q <= 4) return update_go<4, 1>(a, st);
+    if (Q <= 16) return update_go<4, 4>(a, st);
+    if (Q <= 64) return update_go<16, 4>(a, st);
+    return update_go<32, 8>(a, st);
+}
+
+}  // namespace lec

@@ -3,16 +3,14 @@
 This is the public fast path (what bench.py drives).  It does what one iteration of the reference's
 `pass_samples('train')` loop does between `optimizer.zero_grad()` and the weight update
 (order_embeddings_h.py:752-775 for the hyperbolic trainer, order_embeddings.py:619-635 for the
-Euclidean one) with the negatives already drawn:
+Euclidean one) with the negatives already drawn, as two launches (lec_cone_step):
 
-    rows, aux = transform(table)                    lec_rows_fwd   (also clears grad_rows; aux = per-row
-                                                    aperture terms in fp64)
-    loss, dL/drows = cone loss over B*(1+2N) pairs   lec_pairs_grouped
-    [sum dL/drows and loss over ranks]               NCCL all-reduce, only when world_size > 1
-    dL/dtable = J^T dL/drows                         lec_rows_bwd
-    table     = RSGD(table, dL/dtable)               lec_rsgd_update   (hyperbolic)  | plain SGD (Euclidean)
+    loss, dL/drows = cone loss over B*(1+2N) pairs   lec_pairs_grouped   (rows / aux from the previous update)
+    table = update(table, J^T sum_ranks dL/drows)    lec_update_rows: replica sum, [all-reduce over NVLink peer
+    rows, aux = transform(table)                     memory], VJP of the row transform, RSGD / SGD / Adam, and the
+                                                     row transform + aperture terms the NEXT step starts from
 
-Index batches use the compact training layout of include/lec_b200.h (lec_pairs_grouped) as one int32
+Index batches use the compact training layout of include/lec_b200.h (lec_pairs_grouped) as one uint16 / int32
 block [pos_from | pos_to | neg_to | neg_from] so a step's indices travel host->device in one copy.
 """
 import os
@@ -33,19 +31,35 @@ def index_dtype_for(n_rows):
     return np.uint16 if n_rows <= 65536 else np.int32
 
 
-def pack_index_block(pos_from, pos_to, neg_to, neg_from, pin=True, dtype=np.int32):
-    """Host index block [B | B | B*N | B*N] (int32, or uint16 for tables of <= 65 536 rows) for ConeStep.step_host."""
+def pack_index_block(pos_from, pos_to, neg_to, neg_from, pin=True, dtype=np.int32, n_rows=None):
+    """Host index block [B | B | B*N | B*N] (int32, or uint16 for tables of <= 65 536 rows) for ConeStep.step_host.
+    With n_rows the ids are checked against the table here, on the host, the way nn.Embedding checks them in the
+    reference (the kernels also check, see lec_index_errors, but only report after the fact)."""
     parts = [np.ascontiguousarray(a).reshape(-1) for a in (pos_from, pos_to, neg_to, neg_from)]
     cat = np.concatenate(parts)
     if cat.size and (cat.min() < 0 or cat.max() > np.iinfo(dtype).max):
         raise ValueError("index out of range for %s" % np.dtype(dtype).name)
+    if n_rows is not None and cat.size and cat.max() >= n_rows:
+        raise IndexError("endpoint id %d outside the table of %d rows" % (int(cat.max()), int(n_rows)))
     blk = torch.from_numpy(cat.astype(dtype))
     return blk.pin_memory() if (pin and torch.cuda.is_available()) else blk
 
 
+RULES = {"none": N.UPD_NONE, "rsgd": N.UPD_RSGD, "sgd": N.UPD_SGD, "adam": N.UPD_ADAM}
+# one-shot exchange buffers hold 2 slots x world sources x 8 bytes per table float on every rank, and every rank sends
+# its whole gradient to every peer: right for label tables (ETHEC: 35 KB), wrong for multi-megabyte ones
+P2P_ONE_SHOT_MAX_BYTES = 4 << 20
+
+
 class ConeStep:
+    """update: "rsgd" (order_embeddings_h.py:764-775), "sgd" / "adam" (torch.optim semantics, order_embeddings.py:563-565),
+    "none" (gradient only, left in grad_table), "auto" = rsgd for hyperbolic cones, sgd otherwise.  hyp_rescale /
+    project_shell: the joint hyperbolic trainer's gradient rescale and table projection around sgd / adam
+    (oe_h.py:1765-1771).  Every rule runs inside the library's fused update kernel (lec_update_rows)."""
+
     def __init__(self, table, geom, n_neg, max_groups, K=None, alpha=1.0, lr=1e-3, row_mode=None, update="auto",
-                 precision=ops.PREC_F64CORE, process_group=None, replicas=None, comm="auto"):
+                 precision=ops.PREC_F64CORE, process_group=None, replicas=None, comm="auto", momentum=0.0,
+                 betas=(0.9, 0.999), eps=1e-8, hyp_rescale=False, project_shell=False, exchange=None):
         N.require_cuda(table)
         if table.dtype != torch.float32 or not table.is_contiguous():
             raise N.LecError("ConeStep: table must be a contiguous float32 CUDA tensor (updated in place)")
@@ -60,6 +74,10 @@ class ConeStep:
         self.row_mode = {"euc": N.ROWS_EUC_SOFTCLIP, "hyp": N.ROWS_HYP_SHELL, "oe": N.ROWS_NONE}[geom] \
             if row_mode is None else int(row_mode)
         self.update = ("rsgd" if geom == "hyp" else "sgd") if update == "auto" else update
+        if self.update not in RULES:
+            raise N.LecError("unknown update rule %r" % (self.update,))
+        self.momentum, self.betas, self.eps = float(momentum), (float(betas[0]), float(betas[1])), float(eps)
+        self.hyp_rescale, self.project_shell = bool(hyp_rescale), bool(project_shell)
         self.r_in = float(inner_radius(self.K)) if geom == "hyp" else 0.0
         self.precision = int(precision)
         self.pg = process_group
@@ -72,19 +90,26 @@ class ConeStep:
         self.grad_table = torch.empty((self.n, self.D), device=dev, dtype=torch.float32)
         self.E_pos = torch.empty(self.max_groups, device=dev, dtype=torch.float32)
         self.E_neg = torch.empty((self.max_groups, 2 * self.n_neg), device=dev, dtype=torch.float32)
+        # the pair kernel adds into loss_acc; the update kernel moves it to `loss` (this rank's loss of the latest step)
         self.loss = torch.zeros(1, device=dev, dtype=torch.float64)
-        # Fused step (lec_cone_step with fused = 1): RSGD on straight-through rows is followed, in the same launch, by
-        # the row transform the next step starts with -- two launches per step (pairs, update+rows) instead of three.
-        # The pair kernel then adds into loss_acc and the update moves it to `loss`.
         self.loss_acc = torch.zeros(1, device=dev, dtype=torch.float64)
-        self.fused = (self.update == "rsgd" and self.row_mode == N.ROWS_HYP_SHELL
-                      and os.environ.get("LEC_FUSED_STEP", "1") != "0")
+        self.opt_m = self.opt_v = None
+        if self.update == "adam" or (self.update == "sgd" and self.momentum != 0.0):
+            self.opt_m = torch.zeros((self.n, self.ld), device=dev, dtype=torch.float32)
+        if self.update == "adam":
+            self.opt_v = torch.zeros((self.n, self.ld), device=dev, dtype=torch.float32)
+        self.opt_step = 0
+        self.write_grad_table = self.update == "none"   # set to True to keep d loss / d table of every step
+        # fused: the update also produces the rows / aux / cleared replicas the next step starts from (two launches per
+        # step).  LEC_FUSED_STEP=0 re-runs lec_rows_fwd at the start of every step instead (three launches).
+        self.fused = os.environ.get("LEC_FUSED_STEP", "1") != "0"
         self._rows_valid = False
         # host->device staging: `depth` slots so that the copy of step i+1 overlaps the kernels of step i
         self.depth = 2
         self._idx_bytes_dev = [torch.empty(self.max_groups * (2 + 2 * self.n_neg) * 4, device=dev, dtype=torch.uint8)
                                for _ in range(self.depth)]
         self.loss_host = torch.zeros(self.depth, dtype=torch.float64).pin_memory()
+        self.err_host = torch.zeros(self.depth, dtype=torch.int32).pin_memory()
         self._copy_stream = None
         self._ev = None          # per slot: (indices copied, kernels done with the slot, loss read back)
         self._inflight = [False] * self.depth
@@ -92,36 +117,71 @@ class ConeStep:
         self._losses = []
         self.kernel_events = None  # optional (start, stop) pairs around the pair kernel, set by bench
         self._struct = None
-        # multi-GPU exchange: "p2p" = one-shot all-reduce over NVLink peer memory fused into the RSGD kernel,
-        # "nccl" = all_reduce of the table gradient; "auto" tries p2p for the RSGD update and falls back
-        self.comm, self.comm_note, self.px = "none", "", None
-        if self.pg is not None and torch.distributed.get_world_size(self.pg) > 1:
+        # multi-GPU exchange: "p2p" = one-shot low-latency all-reduce over NVLink peer memory inside the update kernel,
+        # "nccl" = all_reduce of the summed gradient between the pair kernel and the update kernel
+        self.comm, self.comm_note, self.px = "none", "", exchange
+        world = torch.distributed.get_world_size(self.pg) if self.pg is not None else 1
+        if exchange is not None:
+            self.comm = "p2p"
+        elif world > 1:
             self.comm = "nccl"
-            if comm in ("auto", "p2p") and self.update == "rsgd":
+            one_shot_bytes = self.n * self.ld * 4
+            if comm == "p2p" or (comm == "auto" and one_shot_bytes <= P2P_ONE_SHOT_MAX_BYTES):
                 try:
-                    self.px = sharding.PeerExchange(self.n, self.D, dev, self.pg)
+                    self.px = sharding.PeerExchange(self.n, self.ld, dev, self.pg)
                     self.comm = "p2p"
                 except Exception as e:  # noqa: BLE001 -- any failure of the symmetric-memory setup
                     if comm == "p2p":
                         raise
                     self.comm_note = "p2p unavailable (%s: %s)" % (type(e).__name__, str(e)[:120])
-            self.loss_global = torch.zeros(1, device=dev, dtype=torch.float64)
+            elif comm == "auto":
+                self.comm_note = "table of %.1f MB: one-shot peer exchange not used" % (one_shot_bytes / 1e6)
+        if self.comm == "nccl":
+            self.grad_sum = torch.empty((self.n, self.ld), device=dev, dtype=torch.float32)
+        self.loss_global = self.px.loss_global if self.px is not None else torch.zeros(1, device=dev, dtype=torch.float64)
 
     # -- pieces ---------------------------------------------------------------------------------
     def _split(self, blk, B):
         Nn = self.n_neg
         return blk[:B], blk[B:2 * B], blk[2 * B:2 * B + B * Nn], blk[2 * B + B * Nn:2 * B + 2 * B * Nn]
 
+    def set_lr(self, lr):
+        """Learning-rate schedules (the reference decays lr every epoch, order_embeddings_h.py:620) take effect on the
+        next step; assigning `engine.lr` directly works too."""
+        self.lr = float(lr)
+
+    def _fill_update(self, u, grad_rows=None, replicas=None):
+        """lec_update_t for the next step (scalars are re-read every step, so lr / alpha / K may change between steps)."""
+        u.rule, u.row_mode, u.geom, u.lambda_mode = RULES[self.update], self.row_mode, N.GEOM[self.geom], 0
+        u.hyp_rescale, u.project_shell = int(self.hyp_rescale), int(self.project_shell)
+        u.K, u.lr, u.r_in = self.K, self.lr, self.r_in
+        u.momentum, u.beta1, u.beta2, u.eps = self.momentum, self.betas[0], self.betas[1], self.eps
+        u.opt_step = self.opt_step + 1
+        u.table, u.n, u.D, u.ld = self.table.data_ptr(), self.n, self.D, self.ld
+        u.grad_rows = (self.grad_rows if grad_rows is None else grad_rows).data_ptr()
+        u.grad_replicas = self.replicas if replicas is None else replicas
+        u.state_m = self.opt_m.data_ptr() if self.opt_m is not None else None
+        u.state_v = self.opt_v.data_ptr() if self.opt_v is not None else None
+        u.rows_out, u.aux_out = self.rows.data_ptr(), self.aux.data_ptr()
+        u.grad_out = self.grad_table.data_ptr() if self.write_grad_table else None
+        u.loss_acc, u.loss_step = self.loss_acc.data_ptr(), self.loss.data_ptr()
+        return u
+
+    def _rows_fwd(self):
+        N.check(N.lib().lec_rows_fwd(N._p(self.table), self.n, self.D, self.row_mode, N.GEOM[self.geom], self.K,
+                                     N._p(self.rows), self.ld, N._p(self.aux), N._p(self.grad_rows), self.replicas,
+                                     N._p(self.loss_acc), N.stream_ptr(self.table.device)), "lec_rows_fwd")
+
     def forward_backward(self, pos_from, pos_to, neg_to, neg_from, w_pos=None, w_neg=None):
-        """rows, loss and d loss / d rows for one batch (no collective, no update)."""
+        """rows, loss and d loss / d rows for one batch (no collective, no update): the loss is left in loss_acc, the
+        gradient in the replicas; reduce_and_update() finishes the step."""
         lib, st = N.lib(), N.stream_ptr(self.table.device)
         B = int(pos_from.numel())
         if B > self.max_groups:
             raise N.LecError("batch of %d positives exceeds max_groups=%d" % (B, self.max_groups))
-        self._rows_valid = False   # the replicas now hold a gradient the fused step did not put there
-        N.check(lib.lec_rows_fwd(N._p(self.table), self.n, self.D, self.row_mode, N.GEOM[self.geom], self.K,
-                                 N._p(self.rows), self.ld, N._p(self.aux), N._p(self.grad_rows), self.replicas,
-                                 N._p(self.loss), st), "lec_rows_fwd")
+        if not (self.fused and self._rows_valid):
+            self._rows_fwd()
+        self._rows_valid = False
         ev = self.kernel_events
         if ev is not None:
             ev[0].record()
@@ -129,7 +189,7 @@ class ConeStep:
             N.GEOM[self.geom], self.precision, N._p(self.rows), N._p(self.aux), self.n, self.D, self.ld,
             N._p(pos_from), N._p(pos_to),
             N._p(neg_to), N._p(neg_from), pos_from.element_size(), B, self.n_neg, N._p(w_pos), N._p(w_neg), self.K,
-            self.alpha, N._p(self.E_pos), N._p(self.E_neg), N._p(self.loss), N._p(self.grad_rows), self.replicas, st),
+            self.alpha, N._p(self.E_pos), N._p(self.E_neg), N._p(self.loss_acc), N._p(self.grad_rows), self.replicas, st),
             "lec_pairs_grouped")
         if ev is not None:
             ev[1].record()
@@ -141,62 +201,41 @@ class ConeStep:
         self._rows_valid = False
 
     def reduce_and_update(self):
+        """Second half of a step issued as separate calls: [exchange] + update + next rows (lec_update_rows)."""
+        import ctypes
         lib, st = N.lib(), N.stream_ptr(self.table.device)
-        self._rows_valid = False
-        multi = self.pg is not None and torch.distributed.get_world_size(self.pg) > 1
-        if not multi and self.update == "rsgd" and self.row_mode == N.ROWS_HYP_SHELL:
-            # straight-through rows: d/dtable == d/drows; the update sums the replicas itself
-            N.check(lib.lec_rsgd_update(N._p(self.table), N._p(self.grad_rows), self.replicas, self.n, self.D, self.ld,
-                                        self.lr, self.r_in, 0, N._p(self.grad_table), st), "lec_rsgd_update")
-            return
-        if multi and self.comm == "p2p":
-            import ctypes
-            px = self.px
-            slot, tag = px.slot_and_tag()
-            # partial d/dtable of this rank straight into its exchange slot, publish, fused reduce + update
-            N.check(lib.lec_rows_bwd(N._p(self.table), N._p(self.grad_rows), self.replicas, self.n, self.D, self.ld,
-                                     self.row_mode, self.K, ctypes.c_void_p(px.my_slot_ptr(slot)), 0, st),
-                    "lec_rows_bwd")
-            N.check(lib.lec_p2p_publish(N._p(self.loss), px.peer_ptrs_pull, px.slot_floats, px.world, px.rank, slot, tag, st),
-                    "lec_p2p_publish")
-            N.check(lib.lec_rsgd_update_p2p(N._p(self.table), px.peer_ptrs_pull, px.slot_floats, px.world, px.rank, slot,
-                                            tag, self.n, self.D, self.lr, self.r_in, 0, N._p(self.loss_global),
-                                            N._p(px.error), st), "lec_rsgd_update_p2p")
-            px.step += 1
-            return
-        # d/dtable = J^T (sum of replicas); it is linear, so ranks can be summed after it
-        N.check(lib.lec_rows_bwd(N._p(self.table), N._p(self.grad_rows), self.replicas, self.n, self.D, self.ld,
-                                 self.row_mode, self.K, N._p(self.grad_table), 0, st), "lec_rows_bwd")
-        if multi:
-            # one collective per step: the table gradient.  The scalar loss stays rank-local until someone
-            # asks for it (global_loss), so logging does not put a second latency-bound all-reduce on the
-            # critical path.
-            torch.distributed.all_reduce(self.grad_table, group=self.pg)
-        if self.update == "rsgd":
-            N.check(lib.lec_rsgd_update(N._p(self.table), N._p(self.grad_table), 1, self.n, self.D, self.D, self.lr,
-                                        self.r_in, 0, N._p(self.grad_table), st), "lec_rsgd_update")
-        elif self.update in ("sgd", "adam"):
-            self._apply_torch_update()
-        elif self.update != "none":
-            raise N.LecError("unknown update rule %r" % (self.update,))
+        u, x = N.LecUpdate(), N.LecExchange()
+        if self.comm == "nccl":
+            # sum of the replicas -> one NCCL all-reduce -> the update reads the reduced buffer as a single replica
+            N.check(lib.lec_reduce_replicas(N._p(self.grad_rows), self.replicas, self.n * self.ld, N._p(self.grad_sum), st),
+                    "lec_reduce_replicas")
+            self.grad_rows.zero_()
+            torch.distributed.all_reduce(self.grad_sum, group=self.pg)
+            self._fill_update(u, self.grad_sum, 1)
+        else:
+            self._fill_update(u)
+            if self.comm == "p2p":
+                self.px.fill(x)
+        N.check(lib.lec_update_rows(ctypes.byref(u), ctypes.byref(x) if self.comm == "p2p" else None, st), "lec_update_rows")
+        self._after_step()
 
-    def _apply_torch_update(self):
-        """Euclidean trainers hand the table to a stock torch optimiser (order_embeddings.py:563-565: SGD or Adam); so
-        does the engine -- plain SGD, or torch's fused Adam on the table.  Not the product."""
-        if self.update == "sgd":
-            self.table.add_(self.grad_table, alpha=-self.lr)
-            return
-        if getattr(self, "_adam", None) is None:
-            self._adam_param = torch.nn.Parameter(self.table, requires_grad=False)
-            self._adam = torch.optim.Adam([self._adam_param], lr=self.lr, fused=True)
-        self._adam_param.grad = self.grad_table
-        self._adam.step()
+    def _after_step(self):
+        if self.update != "none":
+            self.opt_step += 1
+        if self.comm == "p2p":
+            self.px.step += 1
+        self._rows_valid = self.fused
+
+    def check_exchange(self):
+        """Raises if the peer exchange reported a failure (a rank did not deliver its gradient in time).  Synchronises."""
+        if self.px is not None and int(self.px.error.item()) != 0:
+            raise N.LecError("peer exchange timed out: a rank did not deliver its gradient; the table replicas are no "
+                             "longer in step -- restart from a checkpoint")
 
     def global_loss(self):
         """Loss of the latest step summed over ranks (float64 tensor on the device)."""
         if self.comm == "p2p":
-            if int(self.px.error.item()) != 0:
-                raise N.LecError("peer exchange timed out: a rank did not publish its gradient")
+            self.check_exchange()
             return self.loss_global.clone()
         out = self.loss.clone()
         if self.pg is not None and torch.distributed.get_world_size(self.pg) > 1:
@@ -204,72 +243,43 @@ class ConeStep:
         return out
 
     # -- whole steps ----------------------------------------------------------------------------
-    def _step_struct(self):
-        """lec_step_t with everything that does not change from step to step filled in."""
-        import ctypes
-        s = N.LecStep()
-        s.geom, s.precision, s.row_mode = N.GEOM[self.geom], self.precision, self.row_mode
-        s.update = 1 if self.update == "rsgd" else 0   # sgd / adam: the library leaves d loss / d table in grad_table
-        s.lambda_mode = 0
-        s.K, s.alpha, s.lr, s.r_in = self.K, self.alpha, self.lr, self.r_in
-        s.table, s.n, s.D, s.ld = self.table.data_ptr(), self.n, self.D, self.ld
-        s.rows, s.aux, s.grad_rows = self.rows.data_ptr(), self.aux.data_ptr(), self.grad_rows.data_ptr()
-        s.grad_replicas, s.grad_table = self.replicas, self.grad_table.data_ptr()
-        s.N = self.n_neg
-        s.E_pos, s.E_neg, s.loss = self.E_pos.data_ptr(), self.E_neg.data_ptr(), self.loss.data_ptr()
-        s.world = 0
-        s.fused = 1 if self.fused else 0
-        s.loss_acc = self.loss_acc.data_ptr()
-        if self.comm == "p2p":
-            px = self.px
-            s.counter = px.counter.data_ptr()
-            s.peer_bufs = ctypes.cast(px.peer_ptrs if self.fused else px.peer_ptrs_pull, ctypes.c_void_p)
-            s.slot_floats, s.world, s.rank = px.slot_floats, px.world, px.rank
-            s.loss_global, s.error = self.loss_global.data_ptr(), px.error.data_ptr()
-        return s
-
     def step_device(self, pos_from, pos_to, neg_to, neg_from, w_pos=None, w_neg=None):
-        """Indices already on the device (int32 or int64).  Returns the device loss (float64[1])."""
-        if self.update in ("none", "rsgd") and self.comm in ("none", "p2p") or \
-                self.update in ("sgd", "adam") and self.comm == "none":
-            # the whole step as ONE call into the library (lec_cone_step): one FFI crossing, 3-5 launches
-            B = int(pos_from.numel())
-            if B > self.max_groups:
-                raise N.LecError("batch of %d positives exceeds max_groups=%d" % (B, self.max_groups))
-            s = self._struct if self._struct is not None else self._step_struct()
-            self._struct = s
-            s.pos_from, s.pos_to = pos_from.data_ptr(), pos_to.data_ptr()
-            s.neg_to, s.neg_from = neg_to.data_ptr(), neg_from.data_ptr()
-            s.idx_bytes, s.B = pos_from.element_size(), B
-            s.w_pos = w_pos.data_ptr() if w_pos is not None else None
-            s.w_neg = w_neg.data_ptr() if w_neg is not None else None
-            if self.comm == "p2p":
-                s.slot, s.tag = self.px.slot_and_tag()
-            ev = self.kernel_events
-            if ev is not None:
-                for e in ev:
-                    if not e.cuda_event:
-                        e.record()  # torch creates the cudaEvent lazily
-                s.ev_pairs_start, s.ev_pairs_stop = ev[0].cuda_event, ev[1].cuda_event
-            else:
-                s.ev_pairs_start, s.ev_pairs_stop = None, None
-            import ctypes
-            if self.fused and not self._rows_valid:
-                # first step (or the table changed behind the engine's back): rows, aux, cleared replicas and loss
-                N.check(N.lib().lec_rows_fwd(N._p(self.table), self.n, self.D, self.row_mode, N.GEOM[self.geom], self.K,
-                                             N._p(self.rows), self.ld, N._p(self.aux), N._p(self.grad_rows), self.replicas,
-                                             N._p(self.loss_acc), N.stream_ptr(self.table.device)), "lec_rows_fwd")
-                self._rows_valid = True
-            N.check(N.lib().lec_cone_step(ctypes.byref(s), N.stream_ptr(self.table.device)), "lec_cone_step")
-            if not self.fused:
-                self._rows_valid = False
-            if self.update in ("sgd", "adam"):
-                self._apply_torch_update()
-            if self.comm == "p2p":
-                self.px.step += 1
+        """Indices already on the device (uint16 / int32 / int64).  Returns this rank's device loss (float64[1])."""
+        if self.comm == "nccl":
+            self.forward_backward(pos_from, pos_to, neg_to, neg_from, w_pos, w_neg)
+            self.reduce_and_update()
             return self.loss
-        self.forward_backward(pos_from, pos_to, neg_to, neg_from, w_pos, w_neg)
-        self.reduce_and_update()
+        # the whole step as ONE call into the library (lec_cone_step): one FFI crossing, two launches
+        import ctypes
+        B = int(pos_from.numel())
+        if B > self.max_groups:
+            raise N.LecError("batch of %d positives exceeds max_groups=%d" % (B, self.max_groups))
+        s = self._struct
+        if s is None:
+            s = self._struct = N.LecStep()
+        s.geom, s.precision, s.alpha = N.GEOM[self.geom], self.precision, self.alpha
+        s.fused = 1 if (self.fused and self._rows_valid) else 0
+        s.pos_from, s.pos_to = pos_from.data_ptr(), pos_to.data_ptr()
+        s.neg_to, s.neg_from = neg_to.data_ptr(), neg_from.data_ptr()
+        s.idx_bytes, s.B, s.N = pos_from.element_size(), B, self.n_neg
+        s.w_pos = w_pos.data_ptr() if w_pos is not None else None
+        s.w_neg = w_neg.data_ptr() if w_neg is not None else None
+        s.E_pos, s.E_neg = self.E_pos.data_ptr(), self.E_neg.data_ptr()
+        self._fill_update(s.upd)
+        if self.comm == "p2p":
+            self.px.fill(s.xchg)
+        else:
+            s.xchg.world = 0
+        ev = self.kernel_events
+        if ev is not None:
+            for e in ev:
+                if not e.cuda_event:
+                    e.record()  # torch creates the cudaEvent lazily
+            s.ev_pairs_start, s.ev_pairs_stop = ev[0].cuda_event, ev[1].cuda_event
+        else:
+            s.ev_pairs_start, s.ev_pairs_stop = None, None
+        N.check(N.lib().lec_cone_step(ctypes.byref(s), N.stream_ptr(self.table.device)), "lec_cone_step")
+        self._after_step()
         return self.loss
 
     def step_sampled(self, graph, pos_from, pos_to, seed, step):
@@ -298,8 +308,16 @@ class ConeStep:
         dst.copy_(index_block[:n], non_blocking=True)
         self.step_device(*self._split(dst, B))
         self.loss_host[:1].copy_(self.loss, non_blocking=True)
+        if self.px is not None:
+            self.err_host[:1].copy_(self.px.error, non_blocking=True)
         torch.cuda.current_stream(self.table.device).synchronize()
+        self._raise_on(0)
         return float(self.loss_host[0])
+
+    def _raise_on(self, slot):
+        if self.px is not None and int(self.err_host[slot]) != 0:
+            raise N.LecError("peer exchange timed out: a rank did not deliver its gradient; the table replicas are no "
+                             "longer in step -- restart from a checkpoint")
 
     def submit_host(self, index_block, B):
         """Pipelined end-to-end step: the index block goes host->device on a side stream into one of `depth`
@@ -315,6 +333,7 @@ class ConeStep:
         ev_copied, ev_free, ev_loss = self._ev[slot]
         if self._inflight[slot]:
             ev_loss.synchronize()
+            self._raise_on(slot)
             self._losses.append(float(self.loss_host[slot]))
         n = B * (2 + 2 * self.n_neg)
         dst = self._slot_view(slot, n, index_block.dtype)
@@ -327,6 +346,8 @@ class ConeStep:
         self.step_device(*self._split(dst, B))
         ev_free.record(main)
         self.loss_host[slot:slot + 1].copy_(self.loss, non_blocking=True)
+        if self.px is not None:
+            self.err_host[slot:slot + 1].copy_(self.px.error, non_blocking=True)
         ev_loss.record(main)
         self._inflight[slot] = True
         self._submitted += 1
@@ -343,6 +364,7 @@ class ConeStep:
                 slot = (self._submitted + k) % self.depth  # oldest first
                 if self._inflight[slot]:
                     self._ev[slot][2].synchronize()
+                    self._raise_on(slot)
                     self._losses.append(float(self.loss_host[slot]))
                     self._inflight[slot] = False
 

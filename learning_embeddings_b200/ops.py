@@ -296,6 +296,39 @@ def rsgd_update_(table, grad, lr, r_in, textbook_lambda=False, write_rescaled_gr
     return table
 
 
+def update_rows_(table, grad_rows, rule, row_mode, geom, K, lr, r_in=0.0, state_m=None, state_v=None, opt_step=1,
+                 momentum=0.0, betas=(0.9, 0.999), eps=1e-8, hyp_rescale=False, project_shell=False, rows_out=None,
+                 aux_out=None, grad_out=None, loss_acc=None, loss_step=None, exchange=None, lambda_mode=0):
+    """The fused table update (lec_update_rows) on caller-owned tensors: replica sum of grad_rows [R, n, ld] (cleared),
+    optional peer exchange (a sharding.PeerExchange / LocalExchange; the caller advances its .step), VJP of `row_mode`,
+    rule in {"none", "rsgd", "sgd", "adam"} in place on table [n, D], and -- when rows_out / aux_out are given -- the
+    transformed rows and aperture terms of the updated table."""
+    N.require_cuda(table, grad_rows)
+    if not table.is_contiguous() or table.dtype != torch.float32:
+        raise N.LecError("update_rows_: table must be a contiguous float32 tensor (updated in place)")
+    n, D = table.shape
+    if grad_rows.dim() == 2:
+        grad_rows = grad_rows.unsqueeze(0)
+    u = N.LecUpdate()
+    u.rule = {"none": N.UPD_NONE, "rsgd": N.UPD_RSGD, "sgd": N.UPD_SGD, "adam": N.UPD_ADAM}[rule]
+    u.row_mode, u.geom, u.lambda_mode = int(row_mode), GEOM[geom] if geom is not None else 0, int(lambda_mode)
+    u.hyp_rescale, u.project_shell = int(bool(hyp_rescale)), int(bool(project_shell))
+    u.K, u.lr, u.r_in = float(K or 0.0), float(lr), float(r_in)
+    u.momentum, u.beta1, u.beta2, u.eps, u.opt_step = float(momentum), float(betas[0]), float(betas[1]), float(eps), int(opt_step)
+    u.table, u.n, u.D, u.ld = table.data_ptr(), n, D, grad_rows.shape[-1]
+    u.grad_rows, u.grad_replicas = grad_rows.data_ptr(), grad_rows.shape[0]
+    for name, tns in (("state_m", state_m), ("state_v", state_v), ("rows_out", rows_out), ("aux_out", aux_out),
+                      ("grad_out", grad_out), ("loss_acc", loss_acc), ("loss_step", loss_step)):
+        setattr(u, name, tns.data_ptr() if tns is not None else None)
+    x = None
+    if exchange is not None:
+        x = N.LecExchange()
+        exchange.fill(x)
+    N.check(N.lib().lec_update_rows(ctypes.byref(u), ctypes.byref(x) if x is not None else None,
+                                    N.stream_ptr(table.device)), "lec_update_rows")
+    return table
+
+
 # --------------------------------------------------------------------------------------------------
 # Scoring
 # --------------------------------------------------------------------------------------------------

@@ -1,7 +1,8 @@
 """Data-parallel plumbing of the cone step: the step's positives (each with its 2N negatives)
 are split in contiguous near-equal slices over the ranks, the label table is replicated, and the only
-exchange per step is the sum of the table gradient (+ the scalar loss).  Backend-agnostic: NCCL on the
-GPU box, gloo in the CPU tests."""
+exchange per step is the sum of the table gradient (+ the scalar loss).  The slicing helpers are backend-agnostic
+(NCCL on the GPU box, gloo in the CPU tests); PeerExchange / LocalExchange own the peer-memory buffers of the exchange
+that is fused into the update kernel."""
 import torch
 import torch.distributed as dist
 
@@ -29,24 +30,46 @@ def allreduce_grad_and_loss(grad_table, loss, group=None):
     return grad_table, loss
 
 
-class PeerExchange:
-    """Exchange buffers for the fused all-reduce + RSGD update (include/lec_b200.h: lec_p2p_publish,
-    lec_rsgd_update_p2p): one buffer per rank, mapped by every rank through torch symmetric memory
-    (CUDA IPC over NVLink / NVSwitch).  Two regions per buffer, one per protocol of include/lec_b200.h:
-    push (lec_p2p_push / lec_rsgd_update_rows_p2p)   float slot[2][world][slot_floats]; uint32 flag[2][world]
-    pull (lec_p2p_publish / lec_rsgd_update_p2p)     float slot[2][slot_floats];        uint32 flag[2][world]
-    `peer_ptrs` points at the push regions, `peer_ptrs_pull` at the pull regions."""
+def exchange_packets(n, ld):
+    """16-byte packets of one source region (lec_exchange_packets): two floats per packet + one packet for the loss."""
+    return int(n) * int(ld) // 2 + 1
 
-    def __init__(self, n, D, device, group):
+
+class _ExchangeBase:
+    """State of the low-latency exchange of include/lec_b200.h (lec_exchange_t): slot / tag bookkeeping, the device error
+    flag and the ctypes view of the peer pointers."""
+
+    def _finish(self, ptrs, device, timeout_ms):
         import ctypes
+        self.peer_ptrs = (ctypes.c_void_p * self.world)(*ptrs)
+        self.step = 0
+        self.timeout_ms = int(timeout_ms)
+        self.error = torch.zeros(1, dtype=torch.int32, device=device)
+        self.loss_global = torch.zeros(1, dtype=torch.float64, device=device)
+
+    def slot_and_tag(self):
+        return self.step % 2, self.step + 1
+
+    def fill(self, x):
+        """Write this step's lec_exchange_t into the ctypes struct x."""
+        import ctypes
+        x.peer_bufs = ctypes.cast(self.peer_ptrs, ctypes.c_void_p)
+        x.slot_packets, x.world, x.rank = self.slot_packets, self.world, self.rank
+        x.slot, x.tag = self.slot_and_tag()
+        x.loss_global, x.error, x.timeout_ms = self.loss_global.data_ptr(), self.error.data_ptr(), self.timeout_ms
+
+
+class PeerExchange(_ExchangeBase):
+    """Exchange buffers of the fused update (include/lec_b200.h: lec_update_rows with a lec_exchange_t): one buffer per
+    rank, `packet slot[2][world][slot_packets]`, mapped by every rank through torch symmetric memory (CUDA IPC over
+    NVLink / NVSwitch)."""
+
+    def __init__(self, n, ld, device, group, timeout_ms=30000):
         import torch.distributed._symmetric_memory as symm_mem
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
-        self.slot_floats = (n * D + 2 + 3) // 4 * 4
-        push = (2 * self.world * self.slot_floats + 2 * self.world + 3) // 4 * 4
-        pull = (2 * self.slot_floats + 2 * self.world + 3) // 4 * 4
-        self.pull_offset = push      # floats
-        total = push + pull
+        self.slot_packets = exchange_packets(n, ld)
+        total = 2 * self.world * self.slot_packets * 4      # floats (16 bytes per packet)
         self.buf = symm_mem.empty(total, dtype=torch.float32, device=device)
         name = getattr(group, "group_name", None)
         try:
@@ -59,14 +82,21 @@ class PeerExchange:
         ptrs = [int(p) for p in self.handle.buffer_ptrs]
         if len(ptrs) != self.world or ptrs[self.rank] != self.buf.data_ptr():
             raise RuntimeError("symmetric memory rendezvous returned unexpected peer pointers")
-        self.peer_ptrs = (ctypes.c_void_p * self.world)(*ptrs)
-        self.peer_ptrs_pull = (ctypes.c_void_p * self.world)(*[q + 4 * self.pull_offset for q in ptrs])
-        self.counter = torch.zeros(1, dtype=torch.int32, device=device)   # last-block counter of lec_p2p_push
-        self.step = 0
-        self.error = torch.zeros(1, dtype=torch.int32, device=device)
+        self._finish(ptrs, device, timeout_ms)
 
-    def slot_and_tag(self):
-        return self.step % 2, self.step + 1
 
-    def my_slot_ptr(self, slot):
-        return self.buf.data_ptr() + 4 * (self.pull_offset + slot * self.slot_floats)
+class LocalExchange(_ExchangeBase):
+    """The same exchange between `world` step engines that live in ONE process on ONE device (each on its own stream):
+    the "peer" buffers are plain device tensors.  What the single-GPU tests use to run the multi-rank protocol of
+    lec_update_rows for real; also a way to drive several model replicas per GPU."""
+
+    def __init__(self, bufs, rank, slot_packets, timeout_ms=5000):
+        self.world, self.rank, self.slot_packets = len(bufs), int(rank), int(slot_packets)
+        self.bufs = bufs
+        self._finish([int(b.data_ptr()) for b in bufs], bufs[0].device, timeout_ms)
+
+    @staticmethod
+    def make(world, n, ld, device, timeout_ms=5000):
+        sp = exchange_packets(n, ld)
+        bufs = [torch.zeros(2 * world * sp * 4, dtype=torch.float32, device=device) for _ in range(world)]
+        return [LocalExchange(bufs, r, sp, timeout_ms) for r in range(world)]

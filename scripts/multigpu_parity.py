@@ -24,32 +24,33 @@ def main():
     h = H.ethec()
     edges = h.closure_edges()
     rng = np.random.default_rng(0)  # same batch on every rank
-    B, Nn, D = 40000, 5, 10
+    B, Nn = 40000, 5
     sel = rng.integers(0, len(edges), size=B)
     u, v = edges[sel, 0], edges[sel, 1]
     nt, nf = h.sample_negatives(u, v, Nn, rng)
-    g = torch.Generator().manual_seed(0)
-    w = torch.randn(h.n, D, generator=g)
-    W0 = (0.0990195 + 0.05 * torch.rand(h.n, 1, generator=g)) * w / w.norm(dim=1, keepdim=True)
     to_dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
     ok = True
-    # "auto" = fused push exchange (lec_p2p_push + lec_rsgd_update_rows_p2p); "pull" = the three-launch peer-load variant
-    for step_count, comm in ((1, "nccl"), (3, "nccl"), (1, "auto"), (4, "auto"), (5, "auto"), (3, "pull")):
+    # "p2p" = the packet exchange inside the fused update kernel (lec_update_rows); "nccl" = all_reduce between the kernels
+    cases = [("hyp", 10, "rsgd", 1, "nccl"), ("hyp", 10, "rsgd", 3, "nccl"), ("hyp", 10, "rsgd", 1, "p2p"),
+             ("hyp", 10, "rsgd", 4, "p2p"), ("hyp", 10, "rsgd", 5, "p2p"), ("euc", 2, "adam", 4, "p2p"),
+             ("euc", 10, "sgd", 3, "p2p"), ("hyp", 50, "rsgd", 3, "p2p")]
+    for geom, D, update, step_count, comm in cases:
+        g = torch.Generator().manual_seed(0)
+        w = torch.randn(h.n, D, generator=g)
+        K = 0.1 if geom == "hyp" else 3.0
+        W0 = (0.0990195 + 0.05 * torch.rand(h.n, 1, generator=g)) * w / w.norm(dim=1, keepdim=True) if geom == "hyp" else w
         # sharded
         Ws = W0.to(dev).clone()
-        eng = ConeStep(Ws, "hyp", Nn, B, K=0.1, alpha=0.05, lr=0.01, process_group=dist.group.WORLD,
-                       comm="auto" if comm == "pull" else comm)
-        if comm == "pull":
-            eng.fused = False
+        eng = ConeStep(Ws, geom, Nn, B, K=K, alpha=0.05, lr=0.01, update=update, process_group=dist.group.WORLD, comm=comm)
         if rank == 0:
-            print("comm requested %s -> %s fused=%s %s" % (comm, eng.comm, eng.fused, eng.comm_note), flush=True)
+            print("%s D=%d %s: comm requested %s -> %s %s" % (geom, D, update, comm, eng.comm, eng.comm_note), flush=True)
         su, sv, snt, snf = sharding.shard_groups(u, v, nt, nf, rank, world)
         for _ in range(step_count):
             eng.step_device(to_dev(su), to_dev(sv), to_dev(snt), to_dev(snf))
         loss_s = float(eng.global_loss().item())
         # single GPU, whole batch
         W1 = W0.to(dev).clone()
-        one = ConeStep(W1, "hyp", Nn, B, K=0.1, alpha=0.05, lr=0.01)
+        one = ConeStep(W1, geom, Nn, B, K=K, alpha=0.05, lr=0.01, update=update)
         for _ in range(step_count):
             one.step_device(to_dev(u), to_dev(v), to_dev(nt), to_dev(nf))
         loss_1 = float(one.loss.item())
@@ -60,11 +61,17 @@ def main():
         ref = Ws.clone()
         dist.broadcast(ref, 0)
         same = bool(torch.equal(ref, Ws))
-        print("rank %d/%d steps=%d  max|W_sharded - W_single| = %.3e  loss rel diff %.2e  identical across ranks: %s"
-              % (rank, world, step_count, err, rel, same), flush=True)
+        print("rank %d/%d %s D=%d %s steps=%d  max|W_sharded - W_single| = %.3e  loss rel diff %.2e  identical across ranks: %s"
+              % (rank, world, geom, D, update, step_count, err, rel, same), flush=True)
         # fp32 L2 reductions are order-dependent: two runs of the SAME single-GPU step differ by ~7e-6 on this
         # batch (gradient sums ~1e3 with heavy cancellation, x lr/lambda^2), so that is the resolution here
-        ok = ok and err < 5e-5 and rel < 1e-6 and same
+        if update == "adam":
+            # Adam moves an element by ~lr * sign(g) whatever |g| is: the rare element whose gradient cancels to rounding
+            # noise may land elsewhere when the summation order changes -- bound the bulk, count the outliers
+            far = float(((Ws - W1).abs() > 1e-5).float().mean())
+            ok = ok and far < 0.005 and rel < 1e-6 and same
+        else:
+            ok = ok and err < 5e-5 and rel < 1e-6 and same
     dist.barrier()
     dist.destroy_process_group()
     if not ok:

@@ -23,7 +23,7 @@ def test_library_exports_every_header_symbol():
     for n in names:
         assert hasattr(lib, n), n
     assert sorted(_native.EXPORTS) == names
-    assert lib.lec_abi_version() == _native.ABI_VERSION == 12
+    assert lib.lec_abi_version() == _native.ABI_VERSION == 13
 
 
 def test_argument_validation_codes():
@@ -55,28 +55,50 @@ def test_argument_validation_codes():
     assert lib.lec_rows_bwd(fake, fake, 0, 5, 4, 4, 1, 3.0, fake, 0, null) == -7
     assert lib.lec_score_topk(1, 0, fake, 5, fake, 5, 10, 0.1, null, null, 4, 9, null, fake, null, null) == -6
     assert lib.lec_rsgd_update(fake, fake, 1, 5, 0, 0, 0.1, 0.1, 0, null, null) == -2
-    # peer exchange
+    # fused update (+ exchange) and the whole-step call (ABI 13)
+    u = _native.LecUpdate()
+    assert lib.lec_update_rows(None, None, null) == -1
+    u.rule, u.row_mode, u.geom = _native.UPD_RSGD, _native.ROWS_HYP_SHELL, 1
+    u.table, u.grad_rows, u.grad_replicas, u.n, u.D, u.ld = 0x1000, 0x1000, 1, 5, 4, 4
+    u.n = 0
+    assert lib.lec_update_rows(ctypes.byref(u), None, null) == 0            # empty table: no launch
+    u.n = 5
+    u.rule = 7
+    assert lib.lec_update_rows(ctypes.byref(u), None, null) == -3           # unknown rule
+    u.rule, u.row_mode = _native.UPD_RSGD, _native.ROWS_HYP_TANH_FEAT
+    assert lib.lec_update_rows(ctypes.byref(u), None, null) == -3           # FeatNet tail is not a table mode
+    u.row_mode, u.grad_replicas = _native.ROWS_HYP_SHELL, 0
+    assert lib.lec_update_rows(ctypes.byref(u), None, null) == -7
+    u.grad_replicas, u.ld = 1, 6
+    assert lib.lec_update_rows(ctypes.byref(u), None, null) == -2           # ld % 4
+    u.ld, u.lambda_mode = 4, 2
+    assert lib.lec_update_rows(ctypes.byref(u), None, null) == -3
+    u.lambda_mode, u.grad_rows = 0, 0x1004
+    assert lib.lec_update_rows(ctypes.byref(u), None, null) == -5           # misaligned replicas
+    u.grad_rows, u.rule = 0x1000, _native.UPD_ADAM
+    assert lib.lec_update_rows(ctypes.byref(u), None, null) == -1           # Adam without its moments
+    u.rule, u.momentum = _native.UPD_SGD, 0.9
+    assert lib.lec_update_rows(ctypes.byref(u), None, null) == -1           # momentum without its buffer
+    u.rule, u.momentum = _native.UPD_RSGD, 0.0
     arr = (ctypes.c_void_p * 2)(0x1000, 0x2000)
-    assert lib.lec_p2p_publish(null, arr, 64, 2, 5, 0, 1, null) == -8        # rank out of range
-    assert lib.lec_p2p_publish(null, arr, 63, 2, 0, 0, 1, null) == -8        # slot_floats % 4
-    assert lib.lec_rsgd_update_p2p(fake, arr, 8, 2, 0, 0, 1, 10, 4, 0.1, 0.1, 0, null, null, null) == -8  # slot too small
-    assert lib.lec_rsgd_update_p2p(fake, null, 64, 2, 0, 0, 1, 10, 4, 0.1, 0.1, 0, null, null, null) == -1
-    # fused update + row transform, push exchange (ABI 11)
-    assert lib.lec_rsgd_update_rows(fake, fake, 1, 5, 4, 4, 0.1, 0.1, 0, 0.1, null, fake, null, null, null, null) == -1   # rows_out
-    assert lib.lec_rsgd_update_rows(fake, fake, 0, 5, 4, 4, 0.1, 0.1, 0, 0.1, fake, fake, null, null, null, null) == -7
-    assert lib.lec_rsgd_update_rows(fake, fake, 1, 5, 4, 6, 0.1, 0.1, 0, 0.1, fake, fake, null, null, null, null) == -2   # ld % 4
-    assert lib.lec_rsgd_update_rows(fake, fake, 1, 5, 4, 4, 0.1, 0.1, 2, 0.1, fake, fake, null, null, null, null) == -3   # lambda_mode
-    assert lib.lec_p2p_push(fake, 1, 10, 4, 4, fake, null, arr, 64, 2, 0, 0, 1, null, null) == -1          # counter
-    assert lib.lec_p2p_push(fake, 1, 10, 4, 4, fake, null, arr, 64, 2, 2, 0, 1, fake, null) == -8          # rank
-    assert lib.lec_p2p_push(fake, 1, 10, 4, 4, fake, null, arr, 8, 2, 0, 0, 1, fake, null) == -8           # slot too small
-    assert lib.lec_rsgd_update_rows_p2p(fake, arr, 64, 2, 0, 0, 1, 10, 4, 4, 0.1, 0.1, 0, 0.1, null, fake, null, null, null) == -1
-    assert lib.lec_rsgd_update_rows_p2p(fake, arr, 64, 2, 0, 3, 1, 10, 4, 4, 0.1, 0.1, 0, 0.1, fake, fake, null, null, null) == -8
+    x = _native.LecExchange()
+    x.peer_bufs, x.world, x.rank, x.slot, x.tag = ctypes.cast(arr, ctypes.c_void_p), 2, 5, 0, 1
+    x.slot_packets = lib.lec_exchange_packets(5, 4)
+    assert x.slot_packets == 11
+    assert lib.lec_update_rows(ctypes.byref(u), ctypes.byref(x), null) == -8   # rank out of range
+    x.rank, x.slot = 0, 3
+    assert lib.lec_update_rows(ctypes.byref(u), ctypes.byref(x), null) == -8   # slot
+    x.slot, x.tag = 0, 0
+    assert lib.lec_update_rows(ctypes.byref(u), ctypes.byref(x), null) == -8   # tag 0 is the empty-buffer value
+    x.tag, x.slot_packets = 1, 10
+    assert lib.lec_update_rows(ctypes.byref(u), ctypes.byref(x), null) == -8   # source region too small
+    x.slot_packets, x.peer_bufs = 11, None
+    assert lib.lec_update_rows(ctypes.byref(u), ctypes.byref(x), null) == -1
     step = _native.LecStep()
-    step.fused, step.update, step.row_mode = 1, 0, _native.ROWS_HYP_SHELL
-    step.grad_rows, step.loss = 0x1000, 0x1000
-    assert lib.lec_cone_step(ctypes.byref(step), null) == -3    # the fused step exists for the RSGD update only
-    step.update = 1
-    assert lib.lec_cone_step(ctypes.byref(step), null) == -1    # loss_acc missing
+    assert lib.lec_cone_step(ctypes.byref(step), null) == -1    # no table
+    step.upd = u
+    assert lib.lec_cone_step(ctypes.byref(step), null) == -1    # rows_out / loss_acc missing
+    assert lib.lec_index_errors(None, 0, null) != -1            # count_out is optional (no device here: a CUDA error code)
     assert lib.lec_caption_hinge(null, fake, 4, 3, 1.0, null, fake, null, null, null) == -1
     assert lib.lec_caption_hinge(fake, fake, -1, 3, 1.0, null, fake, null, null, null) == -4
     assert lib.lec_caption_hinge(null, null, 0, 3, 1.0, null, null, null, null, null) == 0

@@ -598,7 +598,8 @@ def test_engine_step_matches_oracle(name, geom, mode):
     table = t(g["W0"]).to(DEV).clone()
     update = "rsgd" if geom == "hyp" else "none"
     eng = ConeStep(table, geom, Nn, B, K=K, alpha=alpha, lr=lr, update=update)
-    blk = pack_index_block(g["u"], g["v"], neg_to, neg_from)
+    eng.write_grad_table = True    # keep the gradient the update rule saw (what the reference leaves in weight.grad)
+    blk = pack_index_block(g["u"], g["v"], neg_to, neg_from, n_rows=table.shape[0])
     loss = eng.step_host(blk, B)   # H2D of the index block, fused step, loss read-back
     assert abs(loss - float(r64["loss"])) <= 1e-5 * abs(float(r64["loss"]))
     contract(eng.E_pos.cpu().numpy(), r64["E_pos"].numpy(), g["E_pos"], name + " E_pos")
@@ -625,8 +626,9 @@ def test_engine_step_matches_oracle(name, geom, mode):
 
 @pytest.mark.parametrize("D", (2, 10, 50))
 def test_fused_update_and_row_transform_equals_separate_launches(D):
-    """lec_cone_step with fused = 1 (pairs -> lec_rsgd_update_rows: update + the next step's Embedder.forward in one
-    launch) must leave the same tables and losses as the three-launch step, and bit-identical rows / aperture terms."""
+    """lec_cone_step with fused = 1 (pairs -> lec_update_rows: update + the next step's Embedder.forward in one launch)
+    must leave the same tables and losses as the three-launch step (lec_rows_fwd first), and the same rows / aperture
+    terms as a separate lec_rows_fwd of the updated table."""
     from learning_embeddings_b200.engine import ConeStep, pack_index_block
     from learning_embeddings_b200 import hierarchy
     ethec = hierarchy.ethec()

@@ -66,6 +66,12 @@ int lec_abi_version(void);
 const char* lec_error_string(int code);
 /* kernels launched by this library since load (the bench's gpu_launches claim) */
 int64_t lec_launch_count(void);
+/* on != 0: the step kernels (pairs_grouped, update_rows, featnet_*) this THREAD launches from now on are programmatic
+ * dependents of their predecessor in the stream (their blocks become resident while it drains and wait in
+ * griddepcontrol.wait), which hides the launch gap between the kernels of a step.  lec_cone_step does this for its own
+ * launches; a host that issues a step as several calls (the joint trainers' engine) switches it on once.  Returns the
+ * previous setting. */
+int lec_set_pdl(int on);
 /* Endpoint ids are range-checked on the device against n_rows, as nn.Embedding checks them on the host (the reference
  * raises IndexError, order_embeddings.py:188-192): a pair with an id outside [0, n_rows) reads and writes nothing out
  * of bounds, gets energy NaN, contributes neither loss nor gradient, and is counted.  This call returns the count for
@@ -86,15 +92,19 @@ int lec_index_errors(int64_t* count_out, int reset, void* stream);
  *   zero_out  optional [zero_replicas, n, ld] buffer cleared in the same pass (the gradient
  *             accumulator of the pair kernels), may be NULL
  *   zero_scalar optional double[1] cleared in the same pass (the loss accumulator), may be NULL
+ *   zero_stride floats between two replicas of zero_out; 0 = n * ld (a gradient accumulator of exactly these rows).
+ *             A row range inside a larger accumulator (the image rows behind the label rows, joint trainers) passes
+ *             the accumulator's own replica stride.
  */
 int lec_rows_fwd(const float* in, int64_t n, int D, int mode, int geom, float K, float* rows_out, int ld,
-                 double* aux_out, float* zero_out, int zero_replicas, double* zero_scalar, void* stream);
+                 double* aux_out, float* zero_out, int zero_replicas, int64_t zero_stride, double* zero_scalar,
+                 void* stream);
 
 /* Vector-Jacobian product of lec_rows_fwd: grad_in[n, D] (=|+=) J^T grad_rows[n, ld].
- * grad_rows is [grad_replicas, n, ld]; the replicas are summed on the fly.
- * Replaces autograd through Embedder.forward incl. embedding_dense_backward.  accumulate != 0 adds. */
-int lec_rows_bwd(const float* in, const float* grad_rows, int grad_replicas, int64_t n, int D, int ld, int mode,
-                 float K, float* grad_in, int accumulate, void* stream);
+ * grad_rows is [grad_replicas, n, ld] (grad_stride floats between replicas, 0 = n * ld); the replicas are summed on
+ * the fly.  Replaces autograd through Embedder.forward incl. embedding_dense_backward.  accumulate != 0 adds. */
+int lec_rows_bwd(const float* in, const float* grad_rows, int grad_replicas, int64_t grad_stride, int64_t n, int D, int ld,
+                 int mode, float K, float* grad_in, int accumulate, void* stream);
 
 /* out[count] = sum over r of in[r, count] (the replica sum on its own, e.g. before an all-reduce). */
 int lec_reduce_replicas(const float* in, int replicas, int64_t count, float* out, void* stream);
@@ -177,7 +187,8 @@ int lec_rsgd_update(float* table, const float* grad, int grad_replicas, int64_t 
  *      aux_out [n, 4] (as lec_rows_fwd), i.e. the Embedder.forward the NEXT iteration starts with
  * The loss accumulator the pair kernel added into is moved: *loss_step = *loss_acc; *loss_acc = 0 (both optional).
  *   table       [n, D] raw parameter rows, updated in place
- *   grad_rows   [grad_replicas, n, ld], 16-byte aligned
+ *   grad_rows   [grad_replicas, n, ld], 16-byte aligned (grad_stride floats between replicas when the rows are a range
+ *               of a larger accumulator)
  *   state_m/v   [n, ld] optimizer state owned by the caller, zero before the first step: Adam moments (m, v) or the
  *               SGD momentum buffer (m; may be NULL when momentum == 0)
  *   opt_step    1-based step count of the Adam bias correction
@@ -193,7 +204,7 @@ typedef struct lec_update {
     float K, lr, r_in;
     float momentum, beta1, beta2, eps; int64_t opt_step;
     float* table; int64_t n; int D; int ld;
-    float* grad_rows; int grad_replicas;
+    float* grad_rows; int grad_replicas; int64_t grad_stride /* floats between replicas, 0 = n * ld */;
     float* state_m; float* state_v;
     float* rows_out; double* aux_out; float* grad_out;
     double* loss_acc; double* loss_step;
@@ -245,6 +256,24 @@ typedef struct lec_step {
     lec_exchange_t xchg;
 } lec_step_t;
 int lec_cone_step(const lec_step_t* s, void* stream);
+
+/* ---- FeatNet.fc1 on gathered feature rows -----------------------------------------------------------------
+ * The image side of the joint trainers: nn.Linear(F, D) over the step's image features (FeatNet.fc1, oe.py:97,113;
+ * oe_h.py:127,143), with the gather of those features (get_img_features, oe.py:680-707: a Python dict lookup per
+ * filename) fused in.  `features` is the device-resident [n_pool, F] matrix, `sel` [m] row numbers into it (int32 /
+ * int64; NULL = rows 0..m-1).  D <= 16, F % 4 == 0, F <= 4096 (lec_featnet_supported; otherwise use cuBLAS).
+ *   lec_featnet_fwd    Y[i, :] = weight [D, F] . features[sel[i], :] + bias [D]            Y [m, D]
+ *   lec_featnet_wgrad  d weight [d, f] += sum_i gY[i, d] features[sel[i], f],  d bias [d] += sum_i gY[i, d]
+ *                      added into one of `grad_replicas` copies (replica stride grad_stride floats) of a flat
+ *                      [D*F weights | D biases | pad] buffer: the layout lec_update_rows takes as an [n, 16] "table" of
+ *                      plain parameters (row_mode LEC_ROWS_NONE), which sums and clears the replicas.
+ * Each is one pass over the m gathered rows (4 F bytes per row); an id outside [0, n_pool) is skipped and counted
+ * (lec_index_errors). */
+int lec_featnet_supported(int F, int D);
+int lec_featnet_fwd(const float* features, int64_t n_pool, int F, const void* sel, int sel_bytes, int64_t m,
+                    const float* weight, const float* bias, int D, float* Y, void* stream);
+int lec_featnet_wgrad(const float* features, int64_t n_pool, int F, const void* sel, int sel_bytes, int64_t m,
+                      const float* gY, int D, float* grad_flat, int grad_replicas, int64_t grad_stride, void* stream);
 
 /* ---- all-pairs image x label scoring ------------------------------------------------------------
  * Replaces the per-image loop of JointEmbeddings.calculate_classification_metrics

@@ -17,7 +17,8 @@ PREC_F32, PREC_F64CORE = 0, 1
 ABI_VERSION = 13
 
 EXPORTS = (
-    "lec_abi_version", "lec_error_string", "lec_launch_count", "lec_index_errors", "lec_rows_fwd", "lec_rows_bwd",
+    "lec_abi_version", "lec_error_string", "lec_launch_count", "lec_set_pdl", "lec_index_errors", "lec_rows_fwd", "lec_rows_bwd",
+    "lec_featnet_supported", "lec_featnet_fwd", "lec_featnet_wgrad",
     "lec_reduce_replicas", "lec_pairs_flat", "lec_pairs_grouped", "lec_energy_dense", "lec_energy_dense_bwd",
     "lec_rsgd_update", "lec_exchange_packets", "lec_update_rows", "lec_cone_step", "lec_score_topk", "lec_score_topk_ex",
     "lec_score_tc_supported",
@@ -40,7 +41,7 @@ class LecUpdate(ctypes.Structure):
         ("momentum", ctypes.c_float), ("beta1", ctypes.c_float), ("beta2", ctypes.c_float), ("eps", ctypes.c_float),
         ("opt_step", ctypes.c_int64),
         ("table", ctypes.c_void_p), ("n", ctypes.c_int64), ("D", ctypes.c_int), ("ld", ctypes.c_int),
-        ("grad_rows", ctypes.c_void_p), ("grad_replicas", ctypes.c_int),
+        ("grad_rows", ctypes.c_void_p), ("grad_replicas", ctypes.c_int), ("grad_stride", ctypes.c_int64),
         ("state_m", ctypes.c_void_p), ("state_v", ctypes.c_void_p),
         ("rows_out", ctypes.c_void_p), ("aux_out", ctypes.c_void_p), ("grad_out", ctypes.c_void_p),
         ("loss_acc", ctypes.c_void_p), ("loss_step", ctypes.c_void_p),
@@ -94,8 +95,12 @@ def lib():
         L.lec_error_string.restype = ctypes.c_char_p
         L.lec_error_string.argtypes = [c_i]
         L.lec_launch_count.restype = c_i64
-        L.lec_rows_fwd.argtypes = [c_vp, c_i64, c_i, c_i, c_i, c_f, c_vp, c_i, c_vp, c_vp, c_i, c_vp, c_vp]
-        L.lec_rows_bwd.argtypes = [c_vp, c_vp, c_i, c_i64, c_i, c_i, c_i, c_f, c_vp, c_i, c_vp]
+        L.lec_rows_fwd.argtypes = [c_vp, c_i64, c_i, c_i, c_i, c_f, c_vp, c_i, c_vp, c_vp, c_i, c_i64, c_vp, c_vp]
+        L.lec_rows_bwd.argtypes = [c_vp, c_vp, c_i, c_i64, c_i64, c_i, c_i, c_i, c_f, c_vp, c_i, c_vp]
+        L.lec_set_pdl.argtypes = [c_i]
+        L.lec_featnet_supported.argtypes = [c_i, c_i]
+        L.lec_featnet_fwd.argtypes = [c_vp, c_i64, c_i, c_vp, c_i, c_i64, c_vp, c_vp, c_i, c_vp, c_vp]
+        L.lec_featnet_wgrad.argtypes = [c_vp, c_i64, c_i, c_vp, c_i, c_i64, c_vp, c_i, c_vp, c_i, c_i64, c_vp]
         L.lec_reduce_replicas.argtypes = [c_vp, c_i, c_i64, c_vp, c_vp]
         L.lec_pairs_flat.argtypes = [c_i, c_i, c_vp, c_vp, c_i64, c_i, c_i, c_vp, c_vp, c_i, c_vp, c_vp, c_i64, c_f, c_f,
                                      c_vp, c_vp, c_vp, c_i, c_vp]

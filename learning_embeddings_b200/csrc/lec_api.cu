@@ -1,5 +1,6 @@
 // extern "C" surface of liblec_b200.so: argument validation + dispatch.  See include/lec_b200.h.
 #include "lec_pairs_impl.cuh"
+#include "lec_featnet.cuh"
 
 namespace lec {
 std::atomic<unsigned long long> g_launches{0};
@@ -25,11 +26,14 @@ int launch_dense_hyp32(const DenseArgs&, bool, cudaStream_t);
 int launch_dense_hyp64(const DenseArgs&, bool, cudaStream_t);
 int launch_dense_oe32(const DenseArgs&, bool, cudaStream_t);
 
-int rows_fwd_launch(const float*, int64_t, int, int, int, float, float*, int, double*, float*, int, double*, cudaStream_t);
-int rows_bwd_launch(const float*, const float*, int, int64_t, int, int, int, float, float*, int, cudaStream_t);
+int rows_fwd_launch(const float*, int64_t, int, int, int, float, float*, int, double*, float*, int, int64_t, double*, cudaStream_t);
+int rows_bwd_launch(const float*, const float*, int, int64_t, int64_t, int, int, int, float, float*, int, cudaStream_t);
 int rsgd_launch(float*, const float*, int, int64_t, int, int, float, float, int, float*, cudaStream_t);
 int reduce_replicas_launch(const float*, int, int64_t, float*, cudaStream_t);
 int update_rows_launch(const lec_update_t&, const lec_exchange_t*, cudaStream_t);
+bool featnet_supported(int F, int D);
+int featnet_fwd_launch(const FeatArgs&, cudaStream_t);
+int featnet_wgrad_launch(const FeatArgs&, cudaStream_t);
 int score_launch(int, int, const float*, int64_t, const float*, int64_t, int, float, const int32_t*, const int32_t*,
                  int, int, float*, int64_t, int64_t, int32_t*, float*, cudaStream_t);
 
@@ -64,6 +68,12 @@ int lec_abi_version(void) { return LEC_ABI_VERSION; }
 
 int64_t lec_launch_count(void) { return (int64_t)g_launches.load(); }
 
+int lec_set_pdl(int on) {
+    const int prev = t_pdl;
+    t_pdl = on ? 1 : 0;
+    return prev;
+}
+
 int lec_index_errors(int64_t* count_out, int reset, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     unsigned* dev = index_errors_ptr();
@@ -95,26 +105,28 @@ const char* lec_error_string(int code) {
 }
 
 int lec_rows_fwd(const float* in, int64_t n, int D, int mode, int geom, float K, float* rows_out, int ld,
-                 double* aux_out, float* zero_out, int zero_replicas, double* zero_scalar, void* stream) {
+                 double* aux_out, float* zero_out, int zero_replicas, int64_t zero_stride, double* zero_scalar, void* stream) {
     if (zero_out && zero_replicas < 1) return LEC_E_REPLICAS;
+    if (zero_stride < 0 || (zero_stride & 3) || (zero_stride > 0 && zero_stride < n * (int64_t)ld)) return LEC_E_SIZE;
     if (aux_out && (geom < LEC_GEOM_EUC || geom > LEC_GEOM_OE)) return LEC_E_ENUM;
     if (aux_out && (reinterpret_cast<uintptr_t>(aux_out) & 15)) return LEC_E_ALIGN;
     if (!in || !rows_out) return LEC_E_NULL;
     if (n < 0) return LEC_E_SIZE;
     if (mode < LEC_ROWS_NONE || mode > LEC_ROWS_HYP_TANH_FEAT) return LEC_E_ENUM;
     if (int e = check_rows(rows_out, D, ld)) return e;
-    return rows_fwd_launch(in, n, D, mode, geom, K, rows_out, ld, aux_out, zero_out, zero_replicas, zero_scalar,
+    return rows_fwd_launch(in, n, D, mode, geom, K, rows_out, ld, aux_out, zero_out, zero_replicas, zero_stride, zero_scalar,
                            (cudaStream_t)stream);
 }
 
-int lec_rows_bwd(const float* in, const float* grad_rows, int grad_replicas, int64_t n, int D, int ld, int mode, float K,
-                 float* grad_in, int accumulate, void* stream) {
+int lec_rows_bwd(const float* in, const float* grad_rows, int grad_replicas, int64_t grad_stride, int64_t n, int D, int ld,
+                 int mode, float K, float* grad_in, int accumulate, void* stream) {
     if (grad_replicas < 1) return LEC_E_REPLICAS;
+    if (grad_stride < 0 || (grad_stride & 3) || (grad_stride > 0 && grad_stride < n * (int64_t)ld)) return LEC_E_SIZE;
     if (!in || !grad_rows || !grad_in) return LEC_E_NULL;
     if (n < 0) return LEC_E_SIZE;
     if (mode < LEC_ROWS_NONE || mode > LEC_ROWS_HYP_TANH_FEAT) return LEC_E_ENUM;
     if (int e = check_rows(grad_rows, D, ld)) return e;
-    return rows_bwd_launch(in, grad_rows, grad_replicas, n, D, ld, mode, K, grad_in, accumulate, (cudaStream_t)stream);
+    return rows_bwd_launch(in, grad_rows, grad_replicas, grad_stride, n, D, ld, mode, K, grad_in, accumulate, (cudaStream_t)stream);
 }
 
 int lec_reduce_replicas(const float* in, int replicas, int64_t count, float* out, void* stream) {
@@ -222,6 +234,7 @@ static int check_update(const lec_update_t* u) {
     if (!u->table || !u->grad_rows) return LEC_E_NULL;
     if (u->grad_replicas < 1) return LEC_E_REPLICAS;
     if (u->n < 0) return LEC_E_SIZE;
+    if (u->grad_stride < 0 || (u->grad_stride & 3) || (u->grad_stride > 0 && u->grad_stride < u->n * (int64_t)u->ld)) return LEC_E_SIZE;
     if (u->D < 1 || u->D > LEC_MAX_DIM || u->ld < u->D || (u->ld & 3)) return LEC_E_DIM;
     if (reinterpret_cast<uintptr_t>(u->grad_rows) & 15) return LEC_E_ALIGN;
     if (u->rows_out && (reinterpret_cast<uintptr_t>(u->rows_out) & 15)) return LEC_E_ALIGN;
@@ -261,13 +274,14 @@ int lec_cone_step(const lec_step_t* s, void* stream) {
     if (int e = check_exchange(&s->xchg, u.n, u.ld)) return e;
     if (!u.rows_out || !u.loss_acc) return LEC_E_NULL;
     struct PdlScope {   // the kernels of this step are launched as programmatic dependents of one another
-        PdlScope() { static const int on = [] { const char* e = getenv("LEC_PDL"); return e ? atoi(e) : 1; }(); t_pdl = on; }
-        ~PdlScope() { t_pdl = 0; }
+        int prev;
+        PdlScope() : prev(t_pdl) { static const int on = [] { const char* e = getenv("LEC_PDL"); return e ? atoi(e) : 1; }(); t_pdl = on; }
+        ~PdlScope() { t_pdl = prev; }
     } pdl_scope;
     cudaStream_t st = (cudaStream_t)stream;
     if (!s->fused) {
         const int e = lec_rows_fwd(u.table, u.n, u.D, u.row_mode, s->geom, u.K, u.rows_out, u.ld, u.aux_out, u.grad_rows,
-                                   u.grad_replicas, u.loss_acc, stream);
+                                   u.grad_replicas, u.grad_stride, u.loss_acc, stream);
         if (e) return e;
     }
     if (s->ev_pairs_start) cudaEventRecord((cudaEvent_t)s->ev_pairs_start, st);
@@ -277,6 +291,39 @@ int lec_cone_step(const lec_step_t* s, void* stream) {
     if (s->ev_pairs_stop) cudaEventRecord((cudaEvent_t)s->ev_pairs_stop, st);
     if (e) return e;
     return update_rows_launch(u, &s->xchg, st);
+}
+
+int lec_featnet_supported(int F, int D) { return featnet_supported(F, D) ? 1 : 0; }
+
+static int check_featnet(const float* features, int64_t n_pool, int F, const void* sel, int sel_bytes, int64_t m, int D) {
+    if (m < 0 || n_pool < 0) return LEC_E_SIZE;
+    if (!featnet_supported(F, D)) return LEC_E_DIM;
+    if (sel && sel_bytes != 4 && sel_bytes != 8) return LEC_E_ENUM;
+    if (m > 0 && !features) return LEC_E_NULL;
+    if (reinterpret_cast<uintptr_t>(features) & 15) return LEC_E_ALIGN;
+    if (!sel && m > n_pool) return LEC_E_SIZE;
+    return 0;
+}
+
+int lec_featnet_fwd(const float* features, int64_t n_pool, int F, const void* sel, int sel_bytes, int64_t m,
+                    const float* weight, const float* bias, int D, float* Y, void* stream) {
+    if (int e = check_featnet(features, n_pool, F, sel, sel_bytes, m, D)) return e;
+    if (m > 0 && (!weight || !Y)) return LEC_E_NULL;
+    if (reinterpret_cast<uintptr_t>(weight) & 15) return LEC_E_ALIGN;
+    FeatArgs a{features, n_pool, F, sel, sel_bytes, m, weight, bias, D, Y, nullptr, nullptr, 1, 0, index_errors_ptr()};
+    return featnet_fwd_launch(a, (cudaStream_t)stream);
+}
+
+int lec_featnet_wgrad(const float* features, int64_t n_pool, int F, const void* sel, int sel_bytes, int64_t m,
+                      const float* gY, int D, float* grad_flat, int grad_replicas, int64_t grad_stride, void* stream) {
+    if (int e = check_featnet(features, n_pool, F, sel, sel_bytes, m, D)) return e;
+    if (grad_replicas < 1) return LEC_E_REPLICAS;
+    if (m > 0 && (!gY || !grad_flat)) return LEC_E_NULL;
+    if ((reinterpret_cast<uintptr_t>(grad_flat) & 15) || (grad_stride & 3)) return LEC_E_ALIGN;
+    if (grad_replicas > 1 && grad_stride < (int64_t)D * F + D) return LEC_E_SIZE;
+    FeatArgs a{features, n_pool, F, sel, sel_bytes, m, nullptr, nullptr, D, nullptr, gY, grad_flat, grad_replicas, grad_stride,
+               index_errors_ptr()};
+    return featnet_wgrad_launch(a, (cudaStream_t)stream);
 }
 
 int lec_score_topk_ex(int geom, int precision, const float* labels, int64_t L, const float* images, int64_t N, int D,

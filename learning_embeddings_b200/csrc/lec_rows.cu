@@ -281,21 +281,21 @@ static int grid_rows(int64_t n, int tt) {
     } while (0)
 
 int rows_fwd_launch(const float* in, int64_t n, int D, int mode, int geom, float K, float* out, int ld, double* aux,
-                    float* zero_out, int zero_replicas, double* zero_scalar, cudaStream_t st) {
+                    float* zero_out, int zero_replicas, int64_t zero_stride, double* zero_scalar, cudaStream_t st) {
     RowsArgs a{};
     a.zero_scalar = zero_scalar;
     a.in = in; a.n = n; a.D = D; a.mode = mode; a.geom = geom; a.K = K; a.out = out; a.ld = ld; a.aux = aux;
-    a.zero_out = zero_out; a.replicas = zero_replicas; a.replica_stride = n * (int64_t)ld;
+    a.zero_out = zero_out; a.replicas = zero_replicas; a.replica_stride = zero_stride > 0 ? zero_stride : n * (int64_t)ld;
     hyp_constants(K, a.r_in, a.c0);
     if (n == 0) return 0;
     LEC_ROWS_DISPATCH(rows_fwd_kernel, a, n, D, st);
     return (int)cudaGetLastError();
 }
 
-int rows_bwd_launch(const float* in, const float* grad_rows, int replicas, int64_t n, int D, int ld, int mode, float K,
-                    float* grad_in, int accumulate, cudaStream_t st) {
+int rows_bwd_launch(const float* in, const float* grad_rows, int replicas, int64_t grad_stride, int64_t n, int D, int ld,
+                    int mode, float K, float* grad_in, int accumulate, cudaStream_t st) {
     RowsArgs a{};
-    a.replicas = replicas; a.replica_stride = n * (int64_t)ld;
+    a.replicas = replicas; a.replica_stride = grad_stride > 0 ? grad_stride : n * (int64_t)ld;
     a.in = in; a.n = n; a.D = D; a.mode = mode; a.K = K; a.ld = ld; a.grad_rows = grad_rows; a.grad_in = grad_in;
     a.accumulate = accumulate;
     hyp_constants(K, a.r_in, a.c0);

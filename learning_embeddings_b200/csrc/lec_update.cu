@@ -18,6 +18,10 @@
 // 12*D bytes per row at least (read w, read g, write w); with the fused transform ~24*D (+ optimizer state).
 #include "lec_rowops.cuh"
 
+#ifndef LEC_UPD_MINBLOCKS
+#define LEC_UPD_MINBLOCKS 3   // resident 256-thread blocks per SM the specialised kernels are compiled for (register cap 80)
+#endif
+
 namespace lec {
 
 struct UpdArgs {
@@ -184,8 +188,12 @@ __device__ __forceinline__ float sumsq32(const float (&x)[4 * V]) {
     return team_sum<TT, float>(s);
 }
 
-template <int TT, int V, bool XCHG>
-__global__ void __launch_bounds__(kThreads) update_rows_kernel(const UpdArgs a) {
+// RULE_T / MODE_T >= 0 fix the update rule / row transform at compile time (the hot combinations get their own, much
+// smaller, instruction stream); -1 reads them from the arguments.
+template <int TT, int V, bool XCHG, int RULE_T, int MODE_T>
+__global__ void __launch_bounds__(kThreads, (V <= 4 && !XCHG && RULE_T >= 0) ? LEC_UPD_MINBLOCKS : 1) update_rows_kernel(const UpdArgs a) {
+    const int rule = RULE_T >= 0 ? RULE_T : a.rule;
+    const int row_mode = MODE_T >= 0 ? MODE_T : a.row_mode;
     __shared__ AuxBatch s_aux;
     int aux_fill = 0;
     pdl_launch_dependents();
@@ -207,26 +215,40 @@ __global__ void __launch_bounds__(kThreads) update_rows_kernel(const UpdArgs a) 
         uint4* dst = a.peer[threadIdx.x] + ((int64_t)a.slot * a.world + a.rank) * a.slot_packets + a.n * (int64_t)Q * 2;
         ll_store(dst, (unsigned)(bits & 0xffffffffu), (unsigned)(bits >> 32), a.tag);
     }
-    const bool hyp = a.row_mode >= LEC_ROWS_HYP_SHELL;
+    const bool hyp = row_mode >= LEC_ROWS_HYP_SHELL;
+    const bool adam = rule == LEC_UPD_ADAM;
+    const bool sgd_m = rule == LEC_UPD_SGD && a.m && a.momentum != 0.f;
     for (int64_t it = 0; it < iters; ++it) {
         const int64_t row = team + it * n_teams;
         bool valid = row < a.n;
         const int64_t rc = valid ? row : 0;
-        // ---- 1. gradient wrt the transformed row: replica sum, replicas cleared -------------------------------------
-        float g[4 * V];
+        // ---- 1. every load of the row is issued up front (the kernel lives on memory-level parallelism): gradient
+        //         replicas, raw row, optimizer state; only then are the replicas cleared --------------------------------
+        float g[4 * V], e[4 * V], mb[4 * V], vb[4 * V];
+        float* const gr = a.grad_rows + rc * (int64_t)a.ld;
+        float* const w = a.table + rc * (int64_t)D;
         {
-            float* gr = a.grad_rows + rc * (int64_t)a.ld;
+            float4 c[V];
 #pragma unroll
             for (int j = 0; j < V; ++j) {
                 const int q = lane + TT * j;
-                float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (q < Q) {
-                    c = rsum4(gr + 4 * q, a.replicas, a.replica_stride);
-                    if (valid)
+                c[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (q < Q) c[j] = a.replicas == 1 ? *reinterpret_cast<const float4*>(gr + 4 * q)
+                                                  : rsum4(gr + 4 * q, a.replicas, a.replica_stride);
+            }
+            load_raw<TT, V>(e, w, D, lane, a.tv);
+            if (adam || sgd_m) load_chunks<TT, V>(mb, a.m + rc * (int64_t)a.ld, Q, lane);
+            if (adam) load_chunks<TT, V>(vb, a.v + rc * (int64_t)a.ld, Q, lane);
+#pragma unroll
+            for (int j = 0; j < V; ++j) { g[4 * j] = c[j].x; g[4 * j + 1] = c[j].y; g[4 * j + 2] = c[j].z; g[4 * j + 3] = c[j].w; }
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    const int q = lane + TT * j;
+                    if (q < Q)
                         for (int r = 0; r < a.replicas; ++r)
                             *reinterpret_cast<float4*>(gr + r * a.replica_stride + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                g[4 * j] = c.x; g[4 * j + 1] = c.y; g[4 * j + 2] = c.z; g[4 * j + 3] = c.w;
             }
         }
         // ---- 2. all-reduce over the ranks -----------------------------------------------------------------------------
@@ -252,10 +274,7 @@ __global__ void __launch_bounds__(kThreads) update_rows_kernel(const UpdArgs a) 
             if (__any_sync(0xffffffffu, !ok)) valid = false;
         }
         // ---- 3. raw row, VJP of the row transform: g <- d loss / d table ---------------------------------------------
-        float e[4 * V];
-        float* w = a.table + rc * (int64_t)D;
-        load_raw<TT, V>(e, w, D, lane, a.tv);
-        if (a.row_mode == LEC_ROWS_EUC_SOFTCLIP) {
+        if (row_mode == LEC_ROWS_EUC_SOFTCLIP) {
             // out = e/|e| * (|e| + K)  (order_embeddings.py:195-200):  J^T g = (1 + K/r) g - K <e,g> / r^3 e
             float ss = 0.f, eg = 0.f;
 #pragma unroll
@@ -265,7 +284,7 @@ __global__ void __launch_bounds__(kThreads) update_rows_kernel(const UpdArgs a) 
             const float c_g = 1.f + a.K / r, c_e = -a.K * eg / (r * ss);
 #pragma unroll
             for (int i = 0; i < 4 * V; ++i) g[i] = fmaf(c_e, e[i], c_g * g[i]);
-        } else if (a.row_mode == LEC_ROWS_HYP_TANH) {
+        } else if (row_mode == LEC_ROWS_HYP_TANH) {
             // out = tanh(clamp(c0 + r)) e'/r, e' = e + 1e-15 (oe_h.py:77-104); the projection behind it is straight-through
             float ss = 0.f, eg = 0.f;
 #pragma unroll
@@ -287,7 +306,7 @@ __global__ void __launch_bounds__(kThreads) update_rows_kernel(const UpdArgs a) 
             }
         }
         // ---- 4. update rule ------------------------------------------------------------------------------------------
-        if (a.rule == LEC_UPD_RSGD) {
+        if (rule == LEC_UPD_RSGD) {
             // One pass gives the five row sums every later quantity is an algebraic function of (v = -lr gs g + 1e-15,
             // t = th v/|v| + 1e-6, the Moebius sums <w,t>, |t|^2 and the norm of the result), carried in fp64:
             double uu = 0.0, gg = 0.0, eg = 0.0, se = 0.0, sg = 0.0;
@@ -342,26 +361,20 @@ __global__ void __launch_bounds__(kThreads) update_rows_kernel(const UpdArgs a) 
                 for (int i = 0; i < 4 * V; ++i) g[i] *= gs;
             }
             if (valid && a.grad_out) store_raw<TT, V>(a.grad_out + row * (int64_t)D, g, D, lane, a.tv);
-            if (a.rule == LEC_UPD_SGD) {
+            if (rule == LEC_UPD_SGD) {
                 // torch.optim.SGD: buf = momentum * buf + g (buf starts at 0, which equals its first-step rule); p -= lr * buf
-                if (a.m && a.momentum != 0.f) {
-                    float mb[4 * V];
-                    float* mp = a.m + rc * (int64_t)a.ld;
-                    load_chunks<TT, V>(mb, mp, Q, lane);
+                if (sgd_m) {
 #pragma unroll
                     for (int i = 0; i < 4 * V; ++i) { mb[i] = fmaf(a.momentum, mb[i], g[i]); g[i] = mb[i]; }
-                    if (valid) store_chunks<TT, V>(mp, mb, Q, lane);
+                    if (valid) store_chunks<TT, V>(a.m + rc * (int64_t)a.ld, mb, Q, lane);
                 }
 #pragma unroll
                 for (int i = 0; i < 4 * V; ++i) e[i] = fmaf(-a.lr, g[i], e[i]);
-            } else if (a.rule == LEC_UPD_ADAM) {
+            } else if (rule == LEC_UPD_ADAM) {
                 // torch.optim.Adam (_single_tensor_adam, no amsgrad / weight decay):
                 //   m.lerp_(g, 1-b1); v = v*b2 + (1-b2) g g; p += -(lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)
-                float mb[4 * V], vb[4 * V];
                 float* mp = a.m + rc * (int64_t)a.ld;
                 float* vp = a.v + rc * (int64_t)a.ld;
-                load_chunks<TT, V>(mb, mp, Q, lane);
-                load_chunks<TT, V>(vb, vp, Q, lane);
                 const float w1 = 1.f - a.beta1, w2 = 1.f - a.beta2;
 #pragma unroll
                 for (int i = 0; i < 4 * V; ++i) {
@@ -382,7 +395,7 @@ __global__ void __launch_bounds__(kThreads) update_rows_kernel(const UpdArgs a) 
                 }
             }
         }
-        if (valid && a.rule != LEC_UPD_NONE) store_raw<TT, V>(w, e, D, lane, a.tv);
+        if (valid && rule != LEC_UPD_NONE) store_raw<TT, V>(w, e, D, lane, a.tv);
         // ---- 5. Embedder.forward of the updated row + its aperture terms ---------------------------------------------
         if (a.rows_out) {
             if (hyp) {
@@ -392,15 +405,15 @@ __global__ void __launch_bounds__(kThreads) update_rows_kernel(const UpdArgs a) 
                     e[i] = d < D ? __fadd_rn(e[i], 1e-15f) : 0.f;
                 }
             }
-            if (a.row_mode != LEC_ROWS_NONE) {
+            if (row_mode != LEC_ROWS_NONE) {
                 const float r = sqrtf(sumsq32<TT, V>(e));
-                if (a.row_mode == LEC_ROWS_EUC_SOFTCLIP) {
+                if (row_mode == LEC_ROWS_EUC_SOFTCLIP) {
                     const float rn = fmaxf(r, kNormEps), scale = r + a.K;
 #pragma unroll
                     for (int i = 0; i < 4 * V; ++i) e[i] = (e[i] / rn) * scale;
                 } else {
                     float r2 = r;
-                    if (a.row_mode != LEC_ROWS_HYP_SHELL) {
+                    if (row_mode != LEC_ROWS_HYP_SHELL) {
                         const float rn = fmaxf(r, kNormEps);
                         const float scale = tanhf(fminf(fmaxf(a.c0 + r, -15.f), 15.f));
 #pragma unroll
@@ -449,17 +462,26 @@ __global__ void __launch_bounds__(kThreads) update_rows_kernel(const UpdArgs a) 
 
 constexpr int kUpdGridCap = 148 * 8;   // the same on every rank: a block's rows are the same rows everywhere
 
-template <int TT, int V>
-static int update_go(const UpdArgs& a, cudaStream_t st) {
+template <int TT, int V, int RULE_T, int MODE_T>
+static int update_go2(const UpdArgs& a, cudaStream_t st) {
     const int tpb = kThreads / TT;
     int64_t need = (a.n + tpb - 1) / tpb;
     if (need < 1) need = 1;
     const int grid = (int)(need < kUpdGridCap ? need : kUpdGridCap);
     cudaError_t e;
-    if (a.world > 1) e = launch_step_kernel(update_rows_kernel<TT, V, true>, grid, kThreads, st, a);
-    else e = launch_step_kernel(update_rows_kernel<TT, V, false>, grid, kThreads, st, a);
+    if (a.world > 1) e = launch_step_kernel(update_rows_kernel<TT, V, true, RULE_T, MODE_T>, grid, kThreads, st, a);
+    else e = launch_step_kernel(update_rows_kernel<TT, V, false, RULE_T, MODE_T>, grid, kThreads, st, a);
     ++g_launches;
     return (int)(e != cudaSuccess ? e : cudaGetLastError());
+}
+
+template <int TT, int V>
+static int update_go(const UpdArgs& a, cudaStream_t st) {
+    // the two training configurations of the benchmarks get specialised kernels; everything else the generic one
+    if (a.rule == LEC_UPD_RSGD && a.row_mode == LEC_ROWS_HYP_SHELL) return update_go2<TT, V, LEC_UPD_RSGD, LEC_ROWS_HYP_SHELL>(a, st);
+    if (a.rule == LEC_UPD_ADAM && a.row_mode == LEC_ROWS_EUC_SOFTCLIP && !a.hyp_rescale && !a.project_shell)
+        return update_go2<TT, V, LEC_UPD_ADAM, LEC_ROWS_EUC_SOFTCLIP>(a, st);
+    return update_go2<TT, V, -1, -1>(a, st);
 }
 
 int update_rows_launch(const lec_update_t& u, const lec_exchange_t* x, cudaStream_t st) {
@@ -478,7 +500,7 @@ int update_rows_launch(const lec_update_t& u, const lec_exchange_t* x, cudaStrea
     const uintptr_t base = reinterpret_cast<uintptr_t>(u.table);
     uintptr_t go = reinterpret_cast<uintptr_t>(u.grad_out);
     a.tv = ((u.D & 3) == 0 && (base & 15) == 0 && (go & 15) == 0) ? 4 : (((u.D & 1) == 0 && (base & 7) == 0 && (go & 7) == 0) ? 2 : 1);
-    a.grad_rows = u.grad_rows; a.replicas = u.grad_replicas; a.replica_stride = u.n * (int64_t)u.ld;
+    a.grad_rows = u.grad_rows; a.replicas = u.grad_replicas; a.replica_stride = u.grad_stride > 0 ? u.grad_stride : u.n * (int64_t)u.ld;
     a.m = u.state_m; a.v = u.state_v;
     a.rows_out = u.rows_out; a.aux_out = u.aux_out; a.grad_out = u.grad_out;
     a.loss_acc = u.loss_acc; a.loss_step = u.loss_step;

@@ -169,7 +169,7 @@ class ConeStep:
 
     def _rows_fwd(self):
         N.check(N.lib().lec_rows_fwd(N._p(self.table), self.n, self.D, self.row_mode, N.GEOM[self.geom], self.K,
-                                     N._p(self.rows), self.ld, N._p(self.aux), N._p(self.grad_rows), self.replicas,
+                                     N._p(self.rows), self.ld, N._p(self.aux), N._p(self.grad_rows), self.replicas, 0,
                                      N._p(self.loss_acc), N.stream_ptr(self.table.device)), "lec_rows_fwd")
 
     def forward_backward(self, pos_from, pos_to, neg_to, neg_from, w_pos=None, w_neg=None):
@@ -371,107 +371,196 @@ class ConeStep:
 
 class JointConeStep:
     """One fused training step of a JOINT image+label cone model (the reference's oe.py / oe_h.py trainers,
-    `JointEmbeddings.pass_samples('train')`, oe.py:1489-1560) on preallocated buffers:
+    `JointEmbeddings.pass_samples('train')`, oe.py:1489-1560 / oe_h.py:1730-1771) on preallocated buffers, seven
+    launches of this library and nothing else:
 
-        X        = features[img_sel]                         gather of the step's distinct images  (torch)
-        Y        = X @ fc1.weight^T + fc1.bias               FeatNet.fc1, oe.py:97,113            (cuBLAS)
-        rows,aux = [transform(table) ; transform(Y)]         lec_rows_fwd x2  (Embedder / FeatNet tail)
-        loss, dL/drows over B*(1+2N) pairs                   lec_pairs_grouped on the concatenated row table
-        dL/dtable, dL/dY                                     lec_reduce_replicas + lec_rows_bwd x2
-        dL/dfc1.weight = dL/dY^T @ X, dL/dfc1.bias           cuBLAS / torch
-        [one all-reduce of the flat gradient buffer]         NCCL, only when world_size > 1
-        Adam (fused) on table, fc1.weight, fc1.bias          torch.optim.Adam, the reference's default optimizer
+        Y        = fc1(features[img_sel])                    lec_featnet_fwd  (gather fused into the projection)
+        img rows = transform(Y), their aperture terms        lec_rows_fwd     (FeatNet tail; clears their gradient rows)
+        loss, dL/drows over B*(1+2N) pairs                   lec_pairs_grouped on the concatenated [labels ; images] rows
+        dL/dY    = J^T dL/d(img rows)                        lec_rows_bwd
+        dL/dfc1  = dL/dY^T features[img_sel], dL/dbias       lec_featnet_wgrad (second and last pass over the features)
+        table  <- rule(table, J^T dL/d(label rows))          lec_update_rows  (+ the label rows / aperture terms of the
+        fc1    <- Adam(fc1, dL/dfc1)                         lec_update_rows    NEXT step; both with the peer exchange
+                                                                               when world_size > 1)
 
-    Endpoints are row numbers of the concatenated table: < n_labels a label, >= n_labels image
-    (index - n_labels) of this step's img_sel.  The FeatNet GEMM stays cuBLAS (not the product)."""
+    Endpoints are row numbers of the concatenated table: < n_labels a label, >= n_labels image (index - n_labels) of
+    this step's img_sel.  Update rules: Euclidean / order embeddings: Adam on both parameter groups with their own
+    learning rates (oe.py:1356-1357, :1714); hyperbolic: the label gradient is rescaled by ((1-|w|)/2)^2, Adam, then the
+    table is projected back into the shell (oe_h.py:1765-1771) -- or, with update="rsgd", the exponential-map update
+    of oe_h.py:1757-1762 -- while fc1 takes plain Adam.  update="none" leaves the parameters alone and the three
+    gradients in g_table / g_w / g_b.
+
+    fc1's weight and bias are kept in ONE flat buffer (fc_w / fc_b are views of it; the constructor copies the
+    tensors it is given): the update kernel treats it as an [n, 16] table of plain parameters."""
+
+    FC_LD = 16
 
     def __init__(self, table, fc_weight, fc_bias, features, geom, n_neg, max_groups, max_images, K=None, alpha=1.0,
-                 lr=1e-3, precision=ops.PREC_F64CORE, process_group=None):
+                 lr=1e-3, precision=ops.PREC_F64CORE, process_group=None, update="auto", lr_fc=None, comm="auto",
+                 exchange=None):
         N.require_cuda(table, fc_weight, fc_bias, features)
-        self.table, self.fc_w, self.fc_b, self.features = table, fc_weight, fc_bias, features
+        self.table, self.features = table, features
         self.geom = geom
         self.n, self.D = table.shape
         self.ld = ops.padded_dim(self.D)
         self.n_neg, self.max_groups, self.max_images = int(n_neg), int(max_groups), int(max_images)
         self.K = {"euc": 3.0, "hyp": 0.1, "oe": 0.0}[geom] if K is None else float(K)
         self.alpha, self.lr, self.precision = float(alpha), float(lr), int(precision)
+        self.lr_fc = float(lr if lr_fc is None else lr_fc)
         self.lab_mode = {"euc": N.ROWS_EUC_SOFTCLIP, "hyp": N.ROWS_HYP_TANH, "oe": N.ROWS_NONE}[geom]
         self.img_mode = {"euc": N.ROWS_EUC_SOFTCLIP, "hyp": N.ROWS_HYP_TANH_FEAT, "oe": N.ROWS_NONE}[geom]
+        self.update = "adam" if update == "auto" else update
+        if self.update not in ("adam", "rsgd", "none") or (self.update == "rsgd" and geom != "hyp"):
+            raise N.LecError("JointConeStep: update must be adam, none, or rsgd (hyperbolic only), got %r" % (update,))
+        self.r_in = float(inner_radius(self.K)) if geom == "hyp" else 0.0
         self.pg = process_group
         dev = table.device
+        F = features.shape[1]
+        self.F = F
+        if not N.lib().lec_featnet_supported(F, self.D):
+            raise N.LecError("JointConeStep: FeatNet of %d -> %d is outside lec_featnet_* (D <= 16, F %% 4 == 0, F <= 4096)" % (F, self.D))
         nt = self.n + self.max_images
         self.n_total = nt
-        F = features.shape[1]
         self.replicas = ops.default_replicas(nt, self.ld)
-        self.X = torch.empty((self.max_images, F), device=dev, dtype=torch.float32)
         self.Y = torch.empty((self.max_images, self.D), device=dev, dtype=torch.float32)
         self.rows = torch.empty((nt, self.ld), device=dev, dtype=torch.float32)
         self.aux = torch.empty((nt, 4), device=dev, dtype=torch.float64)
-        self.grad_rows = torch.empty((self.replicas, nt, self.ld), device=dev, dtype=torch.float32)
-        self.grad_sum = torch.empty((nt, self.ld), device=dev, dtype=torch.float32)
+        self.grad_rows = torch.zeros((self.replicas, nt, self.ld), device=dev, dtype=torch.float32)
         self.gY = torch.empty((self.max_images, self.D), device=dev, dtype=torch.float32)
-        # flat gradient buffer [table | fc1.weight | fc1.bias]: one all-reduce, and the optimizer's .grad views
-        sizes = [self.n * self.D, fc_weight.numel(), fc_bias.numel()]
-        self.gflat = torch.zeros(sum(sizes), device=dev, dtype=torch.float32)
-        o = np.cumsum([0] + sizes)
-        self.g_table = self.gflat[o[0]:o[1]].view(self.n, self.D)
-        self.g_w = self.gflat[o[1]:o[2]].view_as(fc_weight)
-        self.g_b = self.gflat[o[2]:o[3]].view_as(fc_bias)
+        # fc1 as one flat parameter vector [D*F weights | D biases | pad], its gradient replicas and Adam moments
+        self.n_fc = (self.D * F + self.D + self.FC_LD - 1) // self.FC_LD
+        self.fc_flat = torch.zeros(self.n_fc * self.FC_LD, device=dev, dtype=torch.float32)
+        self.fc_w = self.fc_flat[:self.D * F].view(self.D, F)
+        self.fc_b = self.fc_flat[self.D * F:self.D * F + self.D]
+        with torch.no_grad():
+            self.fc_w.copy_(fc_weight)
+            self.fc_b.copy_(fc_bias)
+        self.fc_replicas = 8
+        self.fc_grad = torch.zeros((self.fc_replicas, self.n_fc * self.FC_LD), device=dev, dtype=torch.float32)
+        self.g_fc = torch.zeros(self.n_fc * self.FC_LD, device=dev, dtype=torch.float32)
+        self.g_w = self.g_fc[:self.D * F].view(self.D, F)
+        self.g_b = self.g_fc[self.D * F:self.D * F + self.D]
+        self.g_table = torch.zeros((self.n, self.D), device=dev, dtype=torch.float32)
+        self.write_grads = self.update == "none"
+        self.opt = {k: torch.zeros((self.n, self.ld), device=dev) for k in ("m", "v")}
+        self.opt_fc = {k: torch.zeros(self.n_fc * self.FC_LD, device=dev) for k in ("m", "v")}
+        self.opt_step = 0
         self.E_pos = torch.empty(self.max_groups, device=dev, dtype=torch.float32)
         self.E_neg = torch.empty((self.max_groups, 2 * self.n_neg), device=dev, dtype=torch.float32)
         self.loss = torch.zeros(1, device=dev, dtype=torch.float64)
-        self.params = [torch.nn.Parameter(t, requires_grad=False) for t in (table, fc_weight, fc_bias)]
-        for p, g in zip(self.params, (self.g_table, self.g_w, self.g_b)):
-            p.grad = g
-        self.opt = torch.optim.Adam(self.params, lr=self.lr, fused=True)
+        self.loss_acc = torch.zeros(1, device=dev, dtype=torch.float64)
         self.kernel_events = None
+        self._rows_valid = False
         self._sel_dev = torch.empty(self.max_images, device=dev, dtype=torch.int64)
         self._idx_bytes_dev = torch.empty(self.max_groups * (2 + 2 * self.n_neg) * 4, device=dev, dtype=torch.uint8)
         self.loss_host = torch.zeros(1, dtype=torch.float64).pin_memory()
+        # multi-GPU: two exchanges per step (label table, fc1), each inside its update kernel
+        self.comm, self.px, self.px_fc = "none", None, None
+        world = torch.distributed.get_world_size(self.pg) if self.pg is not None else 1
+        if exchange is not None:
+            self.px, self.px_fc = exchange
+            self.comm = "p2p"
+        elif world > 1:
+            if comm == "nccl":
+                raise N.LecError("JointConeStep exchanges gradients inside its update kernels (comm='p2p')")
+            self.px = sharding.PeerExchange(self.n, self.ld, dev, self.pg)
+            self.px_fc = sharding.PeerExchange(self.n_fc, self.FC_LD, dev, self.pg)
+            self.comm = "p2p"
+        self.loss_global = self.px.loss_global if self.px is not None else self.loss
 
     def _split(self, blk, B):
         Nn = self.n_neg
         return blk[:B], blk[B:2 * B], blk[2 * B:2 * B + B * Nn], blk[2 * B + B * Nn:2 * B + 2 * B * Nn]
 
+    def invalidate_rows(self):
+        self._rows_valid = False
+
+    def _update_struct(self, which):
+        u = N.LecUpdate()
+        u.lambda_mode, u.beta1, u.beta2, u.eps, u.momentum = 0, 0.9, 0.999, 1e-8, 0.0
+        u.opt_step = self.opt_step + 1
+        if which == "table":
+            hyp = self.geom == "hyp"
+            u.rule = {"adam": N.UPD_ADAM, "rsgd": N.UPD_RSGD, "none": N.UPD_NONE}[self.update]
+            u.row_mode, u.geom = self.lab_mode, N.GEOM[self.geom]
+            u.hyp_rescale = int(hyp and self.update == "adam")
+            u.project_shell = int(hyp and self.update == "adam")
+            u.K, u.lr, u.r_in = self.K, self.lr, self.r_in
+            u.table, u.n, u.D, u.ld = self.table.data_ptr(), self.n, self.D, self.ld
+            u.grad_rows, u.grad_replicas, u.grad_stride = self.grad_rows.data_ptr(), self.replicas, self.n_total * self.ld
+            u.state_m, u.state_v = self.opt["m"].data_ptr(), self.opt["v"].data_ptr()
+            u.rows_out, u.aux_out = self.rows.data_ptr(), self.aux.data_ptr()
+            u.grad_out = self.g_table.data_ptr() if self.write_grads else None
+            u.loss_acc, u.loss_step = self.loss_acc.data_ptr(), self.loss.data_ptr()
+        else:
+            u.rule = N.UPD_NONE if self.update == "none" else N.UPD_ADAM
+            u.row_mode, u.geom = N.ROWS_NONE, N.GEOM["oe"]
+            u.K, u.lr, u.r_in = 0.0, self.lr_fc, 0.0
+            u.table, u.n, u.D, u.ld = self.fc_flat.data_ptr(), self.n_fc, self.FC_LD, self.FC_LD
+            u.grad_rows, u.grad_replicas, u.grad_stride = self.fc_grad.data_ptr(), self.fc_replicas, 0
+            u.state_m, u.state_v = self.opt_fc["m"].data_ptr(), self.opt_fc["v"].data_ptr()
+            u.grad_out = self.g_fc.data_ptr() if self.write_grads else None
+        return u
+
     def step_device(self, img_sel, pos_from, pos_to, neg_to, neg_from):
+        import ctypes
         lib, st = N.lib(), N.stream_ptr(self.table.device)
         m, B, n, D, ld = int(img_sel.numel()), int(pos_from.numel()), self.n, self.D, self.ld
         if m > self.max_images or B > self.max_groups:
             raise N.LecError("step of %d images / %d positives exceeds the engine's buffers" % (m, B))
-        X, Y = self.X[:m], self.Y[:m]
-        torch.index_select(self.features, 0, img_sel, out=X)
-        torch.addmm(self.fc_b, X, self.fc_w.t(), out=Y)
         geom = N.GEOM[self.geom]
-        rows_img, aux_img = self.rows[n:n + m], self.aux[n:n + m]
-        # labels (clears the loss accumulator), then the projected images; the gradient accumulator spans both
-        N.check(lib.lec_rows_fwd(N._p(self.table), n, D, self.lab_mode, geom, self.K, N._p(self.rows), ld, N._p(self.aux),
-                                 N._p(None), 0, N._p(self.loss), st), "lec_rows_fwd")
-        self.grad_rows.zero_()
-        N.check(lib.lec_rows_fwd(N._p(Y), m, D, self.img_mode, geom, self.K, N._p(rows_img), ld, N._p(aux_img),
-                                 N._p(None), 0, N._p(None), st), "lec_rows_fwd")
-        ev = self.kernel_events
-        if ev is not None:
-            ev[0].record()
-        N.check(lib.lec_pairs_grouped(
-            geom, self.precision, N._p(self.rows), N._p(self.aux), self.n_total, D, ld, N._p(pos_from), N._p(pos_to),
-            N._p(neg_to), N._p(neg_from), pos_from.element_size(), B, self.n_neg, N._p(None), N._p(None), self.K,
-            self.alpha, N._p(self.E_pos), N._p(self.E_neg), N._p(self.loss), N._p(self.grad_rows), self.replicas, st),
-            "lec_pairs_grouped")
-        if ev is not None:
-            ev[1].record()
-        N.check(lib.lec_reduce_replicas(N._p(self.grad_rows), self.replicas, self.n_total * ld, N._p(self.grad_sum), st),
-                "lec_reduce_replicas")
-        N.check(lib.lec_rows_bwd(N._p(self.table), N._p(self.grad_sum), 1, n, D, ld, self.lab_mode, self.K,
-                                 N._p(self.g_table), 0, st), "lec_rows_bwd")
-        gY = self.gY[:m]
-        N.check(lib.lec_rows_bwd(N._p(Y), N._p(self.grad_sum[n:n + m]), 1, m, D, ld, self.img_mode, self.K, N._p(gY), 0, st),
-                "lec_rows_bwd")
-        torch.mm(gY.t(), X, out=self.g_w)
-        torch.sum(gY, dim=0, out=self.g_b)
-        if self.pg is not None and torch.distributed.get_world_size(self.pg) > 1:
-            torch.distributed.all_reduce(self.gflat, group=self.pg)
-        self.opt.step()
+        prev_pdl = lib.lec_set_pdl(1)
+        try:
+            Y = self.Y[:m]
+            N.check(lib.lec_featnet_fwd(N._p(self.features), self.features.shape[0], self.F, N._p(img_sel),
+                                        img_sel.element_size(), m, N._p(self.fc_w), N._p(self.fc_b), D, N._p(Y), st),
+                    "lec_featnet_fwd")
+            if not self._rows_valid:
+                # first step (or the table changed behind the engine's back): label rows, cleared label gradient and loss
+                N.check(lib.lec_rows_fwd(N._p(self.table), n, D, self.lab_mode, geom, self.K, N._p(self.rows), ld,
+                                         N._p(self.aux), N._p(self.grad_rows), self.replicas, self.n_total * ld,
+                                         N._p(self.loss_acc), st), "lec_rows_fwd")
+            rows_img, aux_img = self.rows[n:n + m], self.aux[n:n + m]
+            N.check(lib.lec_rows_fwd(N._p(Y), m, D, self.img_mode, geom, self.K, N._p(rows_img), ld, N._p(aux_img),
+                                     N._p(self.grad_rows[0, n:]), self.replicas, self.n_total * ld, N._p(None), st),
+                    "lec_rows_fwd")
+            ev = self.kernel_events
+            if ev is not None:
+                ev[0].record()
+            N.check(lib.lec_pairs_grouped(
+                geom, self.precision, N._p(self.rows), N._p(self.aux), self.n_total, D, ld, N._p(pos_from), N._p(pos_to),
+                N._p(neg_to), N._p(neg_from), pos_from.element_size(), B, self.n_neg, N._p(None), N._p(None), self.K,
+                self.alpha, N._p(self.E_pos), N._p(self.E_neg), N._p(self.loss_acc), N._p(self.grad_rows), self.replicas, st),
+                "lec_pairs_grouped")
+            if ev is not None:
+                ev[1].record()
+            gY = self.gY[:m]
+            N.check(lib.lec_rows_bwd(N._p(Y), N._p(self.grad_rows[0, n:]), self.replicas, self.n_total * ld, m, D, ld,
+                                     self.img_mode, self.K, N._p(gY), 0, st), "lec_rows_bwd")
+            N.check(lib.lec_featnet_wgrad(N._p(self.features), self.features.shape[0], self.F, N._p(img_sel),
+                                          img_sel.element_size(), m, N._p(gY), D, N._p(self.fc_grad), self.fc_replicas,
+                                          self.fc_grad.shape[1], st), "lec_featnet_wgrad")
+            for which, px in (("table", self.px), ("fc", self.px_fc)):
+                u = self._update_struct(which)
+                x = None
+                if px is not None:
+                    x = N.LecExchange()
+                    px.fill(x)
+                N.check(lib.lec_update_rows(ctypes.byref(u), ctypes.byref(x) if x is not None else None, st), "lec_update_rows")
+                if px is not None:
+                    px.step += 1
+        finally:
+            lib.lec_set_pdl(prev_pdl)
+        if self.update != "none":
+            self.opt_step += 1
+        self._rows_valid = True
         return self.loss
+
+    def check_exchange(self):
+        for px in (self.px, self.px_fc):
+            if px is not None and int(px.error.item()) != 0:
+                raise N.LecError("peer exchange timed out: a rank did not deliver its gradient; the parameter replicas "
+                                 "are no longer in step -- restart from a checkpoint")
 
     def step_host(self, img_sel_host, index_block, B):
         """Pinned host inputs (int64 image selection, uint16/int32 index block) -> step -> loss on the host."""
@@ -484,4 +573,6 @@ class JointConeStep:
         self.step_device(sel, *self._split(dst, B))
         self.loss_host.copy_(self.loss, non_blocking=True)
         torch.cuda.current_stream(self.table.device).synchronize()
+        if self.px is not None:
+            self.check_exchange()
         return float(self.loss_host[0])

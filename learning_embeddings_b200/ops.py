@@ -71,7 +71,7 @@ def rows_forward(W, mode, K, geom=None, zero_out=None):
     aux = torch.empty((n, 4), device=W.device, dtype=torch.float64) if geom is not None else None
     zr = 0 if zero_out is None else (zero_out.shape[0] if zero_out.dim() == 3 else 1)
     N.check(N.lib().lec_rows_fwd(N._p(W), n, D, int(mode), GEOM[geom] if geom is not None else 0, float(K or 0.0),
-                                 N._p(rows), ld, N._p(aux), N._p(zero_out), zr, N._p(None), N.stream_ptr(W.device)),
+                                 N._p(rows), ld, N._p(aux), N._p(zero_out), zr, 0, N._p(None), N.stream_ptr(W.device)),
             "lec_rows_fwd")
     return rows, aux
 
@@ -86,7 +86,7 @@ def rows_backward(W, grad_rows, mode, K, out=None, accumulate=False):
     if out is None:
         out = torch.empty((n, D), device=W.device, dtype=torch.float32)
         accumulate = False
-    N.check(N.lib().lec_rows_bwd(N._p(W), N._p(grad_rows), R, n, D, grad_rows.shape[-1], int(mode), float(K or 0.0),
+    N.check(N.lib().lec_rows_bwd(N._p(W), N._p(grad_rows), R, 0, n, D, grad_rows.shape[-1], int(mode), float(K or 0.0),
                                  N._p(out), int(bool(accumulate)), N.stream_ptr(W.device)), "lec_rows_bwd")
     return out
 

@@ -400,6 +400,123 @@ def gen_joint():
 
 
 # ---------------------------------------------------------------------------------------
+# F2. Joint trainers, whole training iterations INCLUDING the parameter update:
+#     oe.py:1505-1524 (Adam over two parameter groups, oe.py:1356-1357, :1714) and
+#     oe_h.py:1755-1771 (default: grad *= (1/lambda_x)^2, Adam over labels + FeatNet, soft_clip on the table;
+#     use_rsgd: exp_map_x on the table, Adam on FeatNet).  The loss / criterion objects are the reference's; the four
+#     update lines are executed verbatim with JointEmbeddings' own lambda_x / exp_map_x / mob_add / soft_clip bound to
+#     a stand-in trainer object (JointEmbeddings.__init__ needs the image dataset on disk).
+# ---------------------------------------------------------------------------------------
+def gen_joint_update():
+    g = torch.Generator().manual_seed(77)
+    feat_dim, D, N, steps, B = 96, 10, 3, 3, 48
+    slm = db.ETHECLabelMapMergedSmall()
+    Gs = nx.DiGraph()
+    for lvl, table in enumerate([slm.child_of_family_ix, slm.child_of_subfamily_ix, slm.child_of_genus_ix]):
+        for p in sorted(table):
+            for c in table[p]:
+                Gs.add_edge(p + slm.level_start[lvl], c + slm.level_start[lvl + 1])
+    n_lab = slm.n_classes
+    leaves = list(range(slm.level_start[3], slm.level_stop[3]))
+    par = {v: u for u, v in Gs.edges()}
+    n_img = 40
+    files = ["img_%03d.jpg" % i for i in range(n_img)]
+    feats = {f: torch.relu(torch.randn(feat_dim, generator=g)).tolist() for f in files}
+    G_tc = Gs.copy()
+    for i, f in enumerate(files):
+        node = leaves[(3 * i) % len(leaves)]
+        while True:
+            G_tc.add_edge(node, f)
+            if node not in par:
+                break
+            node = par[node]
+    G_tc = nx.transitive_closure(G_tc)
+    mapping_ix_to_node, img_label = {}, n_lab
+    for node in list(G_tc.nodes()):
+        if type(node) == int:
+            mapping_ix_to_node[node] = node
+        else:
+            mapping_ix_to_node[img_label] = node
+            img_label += 1
+    mapping_node_to_ix = {mapping_ix_to_node[k]: k for k in mapping_ix_to_node}
+    nn_ = len(G_tc.nodes())
+    A = np.ones((nn_, nn_), dtype=bool)
+    for u, v in G_tc.edges():
+        A[mapping_node_to_ix[u], mapping_node_to_ix[v]] = 0
+    np.fill_diagonal(A, 0)
+    all_edges = list(G_tc.edges())
+    rnd = random.Random(11)
+    batches = [rnd.sample(all_edges, B) for _ in range(steps)]
+    img_order = [mapping_ix_to_node[i] for i in range(n_lab, nn_)]
+    feat_mat = np.array([feats[f] for f in img_order], dtype=np.float32)
+
+    def enc(lst):
+        return np.array([mapping_node_to_ix[e] for e in lst], dtype=np.int64)
+
+    for name, mod, cls, K, variant in (
+        ("joint_upd_euc", ref_oe, ref_oe.EuclideanConesWithImagesHypernymLoss, 3.0, "euc"),
+        ("joint_upd_hyp", ref_oeh, ref_oeh.EuclideanConesWithImagesHypernymLoss, 0.1, "hyp_adam"),
+        ("joint_upd_hyp_rsgd", ref_oeh, ref_oeh.EuclideanConesWithImagesHypernymLoss, 0.1, "hyp_rsgd"),
+    ):
+        torch.manual_seed(1)
+        crit = cls(slm, N, feats, 1.0, K=K)
+        crit.device = torch.device("cpu")
+        crit.set_negative_graph(A, mapping_node_to_ix, mapping_ix_to_node)
+        model = mod.Embedder(D, slm, normalize=None, K=K)
+        fnet = mod.FeatNet(normalize=None, input_dim=feat_dim, output_dim=D, K=K)
+        W0 = model.embeddings.weight.detach().clone()
+        fw0, fb0 = fnet.fc1.weight.detach().clone(), fnet.fc1.bias.detach().clone()
+        lr_labels, lr_images, lr = 0.01, 1e-3, 1e-3
+        trainer = None
+        if variant == "euc":
+            # oe.py:1356-1357 + :1714
+            opt = torch.optim.Adam([{'params': model.parameters(), 'lr': 0.1},
+                                    {'params': fnet.parameters(), 'weight_decay': 0.0}], lr=lr)
+        else:
+            T = ref_oeh.JointEmbeddings
+            trainer = types.SimpleNamespace(embedding_dim=D, criterion=crit)
+            for mname in ("soft_clip", "mob_add", "lambda_x", "exp_map_x"):
+                setattr(trainer, mname, types.MethodType(getattr(T, mname), trainer))
+            if variant == "hyp_adam":   # oe_h.py:1523
+                opt = torch.optim.Adam([{'params': list(model.parameters()) + list(fnet.parameters())}], lr=lr_labels)
+            else:                       # oe_h.py:1514-1515
+                opt = torch.optim.Adam([{'params': fnet.parameters()}], lr=lr_images)
+        rec = Recorder(crit)
+        random.seed(0)
+        out = dict(W0=W0, fc_w0=fw0, fc_b0=fb0, feat=feat_mat, n_lab=n_lab, N=N, alpha=1.0, K=K, steps=steps,
+                   lr_labels=(0.1 if variant == "euc" else lr_labels), lr_fc=(lr if variant == "euc" else
+                                                                              (lr_labels if variant == "hyp_adam" else lr_images)))
+        for t_ in range(steps):
+            b_from = [u for u, v in batches[t_]]
+            b_to = [v for u, v in batches[t_]]
+            n0 = len(rec.drawn)
+            opt.zero_grad()
+            model.zero_grad()
+            status = torch.ones(B, dtype=torch.int64)
+            loss, Ep, En = crit(model, fnet, b_from, b_to, b_from, b_to, status, "train")
+            loss.backward()
+            Wp = model.embeddings.weight
+            if variant == "euc":
+                opt.step()                                                       # oe.py:1524
+            elif variant == "hyp_adam":
+                Wp.grad.data *= (1.0 / trainer.lambda_x(Wp.data)) ** 2           # oe_h.py:1766
+                opt.step()                                                       # oe_h.py:1767
+                Wp.data = trainer.soft_clip(Wp.data)                             # oe_h.py:1771
+            else:
+                Wp.grad.data *= (1.0 / trainer.lambda_x(Wp.data)) ** 2           # oe_h.py:1761
+                Wp.data = trainer.exp_map_x(Wp.data, -lr_labels * Wp.grad.data)  # oe_h.py:1762
+                opt.step()                                                       # oe_h.py:1764
+            out["b_from%d" % t_], out["b_to%d" % t_] = enc(b_from), enc(b_to)
+            out["drawn%d" % t_] = np.array(rec.drawn[n0:])
+            out["loss%d" % t_] = loss.detach()
+            out["W%d" % (t_ + 1)] = Wp.detach().clone()
+            out["fc_w%d" % (t_ + 1)] = fnet.fc1.weight.detach().clone()
+            out["fc_b%d" % (t_ + 1)] = fnet.fc1.bias.detach().clone()
+        print(name, "losses", [float(out["loss%d" % t_]) for t_ in range(steps)])
+        save(name, **out)
+
+
+# ---------------------------------------------------------------------------------------
 # G. All-pairs image x label scoring, reference-literal loop  oe.py:1764-1779 / oe_h.py:2018-2036
 # ---------------------------------------------------------------------------------------
 def gen_scoring():
@@ -549,9 +666,9 @@ def gen_caption():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["pairs", "transforms", "rsgd", "steps", "joint", "scoring", "metrics", "mt", "classify",
+    which = sys.argv[1:] or ["pairs", "transforms", "rsgd", "steps", "joint", "joint_update", "scoring", "metrics", "mt", "classify",
                              "caption"]
-    fns = dict(pairs=gen_pairs, transforms=gen_transforms, rsgd=gen_rsgd, steps=gen_steps, joint=gen_joint,
+    fns = dict(pairs=gen_pairs, transforms=gen_transforms, rsgd=gen_rsgd, steps=gen_steps, joint=gen_joint, joint_update=gen_joint_update,
                scoring=gen_scoring, metrics=gen_metrics, mt=gen_mt, classify=gen_classify, caption=gen_caption)
     for w in which:
         print("==", w)

@@ -48,11 +48,12 @@ def test_argument_validation_codes():
                                  null, null, null, 1, null) == 0
     # cone energies need the per-row aux terms
     assert lib.lec_pairs_flat(1, 0, fake, null, 10, 4, 4, fake, fake, 8, null, null, 5, 0.1, 1.0, fake, null, null, 1, null) == -1
-    assert lib.lec_rows_fwd(fake, 5, 4, 1, 9, 3.0, fake, 4, fake, null, 0, null, null) == -3
+    assert lib.lec_rows_fwd(fake, 5, 4, 1, 9, 3.0, fake, 4, fake, null, 0, 0, null, null) == -3
+    assert lib.lec_rows_fwd(fake, 5, 4, 1, 0, 3.0, fake, 4, fake, fake, 2, 8, null, null) == -4      # replica stride < n * ld
     assert lib.lec_cone_step(None, null) == -1
     # gradient requested with zero replicas
     assert lib.lec_pairs_flat(0, 0, fake, fake, 10, 4, 4, fake, fake, 8, null, null, 5, 3.0, 1.0, fake, null, fake, 0, null) == -7
-    assert lib.lec_rows_bwd(fake, fake, 0, 5, 4, 4, 1, 3.0, fake, 0, null) == -7
+    assert lib.lec_rows_bwd(fake, fake, 0, 0, 5, 4, 4, 1, 3.0, fake, 0, null) == -7
     assert lib.lec_score_topk(1, 0, fake, 5, fake, 5, 10, 0.1, null, null, 4, 9, null, fake, null, null) == -6
     assert lib.lec_rsgd_update(fake, fake, 1, 5, 0, 0, 0.1, 0.1, 0, null, null) == -2
     # fused update (+ exchange) and the whole-step call (ABI 13)
@@ -94,6 +95,17 @@ def test_argument_validation_codes():
     assert lib.lec_update_rows(ctypes.byref(u), ctypes.byref(x), null) == -8   # source region too small
     x.slot_packets, x.peer_bufs = 11, None
     assert lib.lec_update_rows(ctypes.byref(u), ctypes.byref(x), null) == -1
+    # FeatNet kernels
+    assert lib.lec_featnet_supported(2048, 10) == 1 and lib.lec_featnet_supported(2048, 50) == 0
+    assert lib.lec_featnet_supported(2050, 10) == 0
+    assert lib.lec_featnet_fwd(fake, 100, 2048, fake, 8, 10, fake, null, 50, fake, null) == -2      # D > 16
+    assert lib.lec_featnet_fwd(fake, 100, 2048, fake, 2, 10, fake, null, 10, fake, null) == -3      # index width
+    assert lib.lec_featnet_fwd(null, 100, 2048, fake, 8, 10, fake, null, 10, fake, null) == -1
+    assert lib.lec_featnet_fwd(fake, 100, 2048, null, 8, 200, fake, null, 10, fake, null) == -4     # identity selection past the pool
+    assert lib.lec_featnet_fwd(fake, 100, 2048, fake, 8, 0, null, null, 10, null, null) == 0        # empty step
+    assert lib.lec_featnet_wgrad(fake, 100, 2048, fake, 8, 10, fake, 10, fake, 0, 0, null) == -7
+    assert lib.lec_featnet_wgrad(fake, 100, 2048, fake, 8, 10, fake, 10, fake, 4, 1000, null) == -4  # replica stride too small
+    assert lib.lec_set_pdl(0) in (0, 1)
     step = _native.LecStep()
     assert lib.lec_cone_step(ctypes.byref(step), null) == -1    # no table
     step.upd = u

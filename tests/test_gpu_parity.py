@@ -726,8 +726,9 @@ def test_joint_engine_step_matches_reference_gradients(name, geom):
     m = g["feat"].shape[0]
     table, fw, fb = (t(g[k]).to(DEV).clone() for k in ("W0", "fc_w", "fc_b"))
     feats = t(g["feat"]).to(DEV)
-    eng = JointConeStep(table, fw, fb, feats, geom, Nn, B, m, K=K if geom != "oe" else None, alpha=alpha, lr=1e-3)
-    blk = pack_index_block(g["b_from"], g["b_to"], neg_to, neg_from, dtype=np.uint16)
+    eng = JointConeStep(table, fw, fb, feats, geom, Nn, B, m, K=K if geom != "oe" else None, alpha=alpha, lr=1e-3,
+                        update="none")
+    blk = pack_index_block(g["b_from"], g["b_to"], neg_to, neg_from, dtype=np.uint16, n_rows=n_lab + m)
     loss = eng.step_host(torch.arange(m, dtype=torch.int64), blk, B)
     np.testing.assert_allclose(loss, float(g["loss"]), rtol=2e-5)
     np.testing.assert_allclose(eng.E_pos.cpu().numpy(), g["E_pos"].reshape(-1), rtol=2e-5, atol=2e-5)
@@ -735,6 +736,38 @@ def test_joint_engine_step_matches_reference_gradients(name, geom):
     for got, key in ((eng.g_table, "gW"), (eng.g_w, "g_fc_w"), (eng.g_b, "g_fc_b")):
         scale = np.abs(g[key]).max()
         np.testing.assert_allclose(got.cpu().numpy(), g[key], rtol=2e-3, atol=5e-5 * scale)
-    # Adam moved every parameter that has a gradient, in place
-    assert not torch.equal(table.cpu(), t(g["W0"])) and not torch.equal(fw.cpu(), t(g["fc_w"]))
+    # update="none": parameters untouched, gradients only
+    assert torch.equal(table.cpu(), t(g["W0"])) and torch.equal(eng.fc_w.cpu(), t(g["fc_w"]))
     assert n_lab == table.shape[0]
+    # the fused FeatNet projection equals the stock linear layer
+    Y_ref = torch.nn.functional.linear(feats, fw, fb)
+    np.testing.assert_allclose(eng.Y[:m].cpu().numpy(), Y_ref.cpu().numpy(), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("name,geom,update", [("joint_upd_euc", "euc", "adam"), ("joint_upd_hyp", "hyp", "adam"),
+                                              ("joint_upd_hyp_rsgd", "hyp", "rsgd")])
+def test_joint_engine_updates_match_reference_training_iterations(name, geom, update):
+    """Three consecutive training iterations of the reference's joint trainers INCLUDING the parameter update
+    (oe.py:1505-1524; oe_h.py:1755-1771 default branch and use_rsgd branch; goldens from the unmodified reference):
+    losses and all three parameter tensors after every iteration."""
+    from learning_embeddings_b200.engine import JointConeStep, pack_index_block
+    g = load_golden(name)
+    Nn, K, alpha, n_lab, steps = int(g["N"]), float(g["K"]), float(g["alpha"]), int(g["n_lab"]), int(g["steps"])
+    m = g["feat"].shape[0]
+    B = len(g["b_from0"])
+    table, fw, fb = (t(g[k]).to(DEV).clone() for k in ("W0", "fc_w0", "fc_b0"))
+    eng = JointConeStep(table, fw, fb, t(g["feat"]).to(DEV), geom, Nn, B, m, K=K, alpha=alpha, lr=float(g["lr_labels"]),
+                        lr_fc=float(g["lr_fc"]), update=update)
+    lr_max = max(float(g["lr_labels"]), float(g["lr_fc"]))
+    for k in range(steps):
+        drawn = g["drawn%d" % k].reshape(B, Nn, 2)
+        blk = pack_index_block(g["b_from%d" % k], g["b_to%d" % k], drawn[:, :, 0].copy(), drawn[:, :, 1].copy(),
+                               dtype=np.uint16, n_rows=n_lab + m)
+        loss = eng.step_host(torch.arange(m, dtype=torch.int64), blk, B)
+        np.testing.assert_allclose(loss, float(g["loss%d" % k]), rtol=5e-5, err_msg="loss of iteration %d" % k)
+        for got, key in ((table, "W"), (eng.fc_w, "fc_w"), (eng.fc_b, "fc_b")):
+            a, b = got.cpu().numpy(), g["%s%d" % (key, k + 1)]
+            # Adam moves an element by ~lr * sign(g) whatever |g| is: an element whose gradient cancels to rounding noise
+            # may land elsewhere when the fp32 summation order differs -- tight bound on the bulk, count on the rest
+            far = np.abs(a - b) > 2e-6 + 5e-5 * np.abs(b)
+            assert far.mean() <= 0.002 and np.abs(a - b).max() <= 2.5 * lr_max * (k + 1), (key, k, far.sum(), np.abs(a - b).max())

@@ -352,6 +352,38 @@ class ConeStep:
         self._inflight[slot] = True
         self._submitted += 1
 
+    def submit_host_sampled(self, graph, pos_block, B, seed):
+        """Pipelined end-to-end step in the device-sampled mode: only the step's POSITIVE edges travel host->device
+        (pos_block = pinned [pos_from | pos_to], uint16 / int32: 4 B bytes instead of 4 B (1 + N)); the negatives are
+        drawn on the GPU by the library's Philox sampler (the reference's candidate sets and uniform law, not its
+        random.choice stream) right before the step, in the same stream.  Losses come back through drain()."""
+        dev = self.table.device
+        main = torch.cuda.current_stream(dev)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(dev)
+            self._ev = [tuple(torch.cuda.Event() for _ in range(3)) for _ in range(self.depth)]
+        slot = self._submitted % self.depth
+        ev_copied, ev_free, ev_loss = self._ev[slot]
+        if self._inflight[slot]:
+            ev_loss.synchronize()
+            self._raise_on(slot)
+            self._losses.append(float(self.loss_host[slot]))
+        dst = self._slot_view(slot, 2 * B, pos_block.dtype)
+        with torch.cuda.stream(self._copy_stream):
+            if self._inflight[slot]:
+                self._copy_stream.wait_event(ev_free)
+            dst.copy_(pos_block[:2 * B], non_blocking=True)
+            ev_copied.record(self._copy_stream)
+        main.wait_event(ev_copied)
+        self.step_sampled(graph, dst[:B], dst[B:2 * B], seed, self._submitted)
+        ev_free.record(main)
+        self.loss_host[slot:slot + 1].copy_(self.loss, non_blocking=True)
+        if self.px is not None:
+            self.err_host[slot:slot + 1].copy_(self.px.error, non_blocking=True)
+        ev_loss.record(main)
+        self._inflight[slot] = True
+        self._submitted += 1
+
     def drain(self):
         """Wait for every submitted step; returns their losses in submission order (and forgets them)."""
         self._collect()

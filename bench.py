@@ -182,7 +182,7 @@ class ClockSampler(threading.Thread):
                             self.reasons.add(name)
                 except Exception:
                     pass
-            time.sleep(0.002)
+            time.sleep(0.0005 if self.active.is_set() else 0.002)
 
     def stop(self):
         self._stop_evt.set()
@@ -496,6 +496,11 @@ def run_label(args, ctx, wl, steps, warmup, headline=False):
            "gpu_launches": int(lec_launches), "roofline": roofline, "cpu_baseline": cpu, "final_loss": final_loss}
     if sustained is not None:
         out["sustained"] = sustained
+        if not clocks["samples"]:
+            # the burst region (steps x ~65 us) can end before NVML answers once: the sustained region right behind it is
+            # the same kernel sequence under the same conditions
+            out["clocks"] = dict(sustained["clocks"], note="no NVML sample fell inside the %.1f ms burst region; these are "
+                                 "the samples of the sustained region that follows it" % elapsed_ms)
     if parity is not None:
         out["parity"] = parity
     return out

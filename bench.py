@@ -312,7 +312,7 @@ def run_label(args, ctx, wl, steps, warmup, headline=False):
     rotation = args.rotation or max(4, int(np.ceil(160e6 / bytes_per_batch)))
     cfg["l2_policy"] = "inputs rotate through %d distinct batches (%.0f MB > 126 MB L2)" % (
         rotation, rotation * bytes_per_batch / 1e6)
-    host_batches = make_batches(h, spec, groups, rotation, seed=100 + rank)
+    host_batches = make_batches(h, spec, groups, rotation, seed=100 + (0 if os.environ.get("LEC_BENCH_SAME_BATCHES") else rank))
     dev_batches = [b.to(dev) for b in host_batches]
     table = table0.to(dev).clone()
     eng = ConeStep(table, spec["geom"], Nn, groups, K=spec["K"], alpha=spec["alpha"], lr=spec["lr"],

@@ -85,27 +85,49 @@ __device__ __forceinline__ void ll_push_chunk(const UpdArgs& a, int64_t packet, 
     }
 }
 
-// sum over the ranks, in rank order, of the chunk at `packet` of my own buffer; up to eight sources polled at a time
+// sum over the ranks, in rank order, of the chunk at `packet` of my own buffer.  Up to eight sources (16 packets) are
+// polled together: every round re-issues the loads of ALL packets that have not arrived yet and only then looks at
+// them, so a round costs one L2 round trip however many packets are outstanding (polling them one after the other
+// costs one round trip EACH, which at eight ranks is longer than the NVLink latency the protocol is built to hide).
 __device__ __forceinline__ bool ll_reduce_chunk(const UpdArgs& a, int64_t packet, float4& out, unsigned long long& t0) {
     const uint4* mine = a.peer[a.rank] + (int64_t)a.slot * a.world * a.slot_packets + packet;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     bool ok = true;
-    for (int p0 = 0; p0 < a.world; p0 += 8) {
+    for (int p0 = 0; p0 < a.world && ok; p0 += 8) {
+        const int cnt = a.world - p0 < 8 ? a.world - p0 : 8;
         uint4 pk[16];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            if (p0 + i < a.world) {
+            if (i < cnt) {
                 const uint4* src = mine + (int64_t)(p0 + i) * a.slot_packets;
                 pk[2 * i] = ll_load(src);
                 pk[2 * i + 1] = ll_load(src + 1);
             }
         }
+        unsigned rounds = 0;
+        while (true) {
+            bool all = true;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (i < cnt) {
+                    const uint4* src = mine + (int64_t)(p0 + i) * a.slot_packets;
+                    if (pk[2 * i].y != a.tag || pk[2 * i].w != a.tag) { pk[2 * i] = ll_load(src); all = false; }
+                    if (pk[2 * i + 1].y != a.tag || pk[2 * i + 1].w != a.tag) { pk[2 * i + 1] = ll_load(src + 1); all = false; }
+                }
+            }
+            if (all) break;
+            if ((++rounds & 255u) == 0) {
+                if (t0 == 0) t0 = global_ns();
+                if ((a.error && ld_volatile_int(a.error) != 0) || global_ns() - t0 > a.timeout_ns) {
+                    if (a.error) atomicExch(a.error, 1);
+                    ok = false;
+                    break;
+                }
+            }
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            if (p0 + i < a.world) {
-                const uint4* src = mine + (int64_t)(p0 + i) * a.slot_packets;
-                ok = ok && ll_wait(src, a.tag, pk[2 * i], a.error, a.timeout_ns, t0);
-                ok = ok && ll_wait(src + 1, a.tag, pk[2 * i + 1], a.error, a.timeout_ns, t0);
+            if (i < cnt) {
                 acc.x += __uint_as_float(pk[2 * i].x); acc.y += __uint_as_float(pk[2 * i].z);
                 acc.z += __uint_as_float(pk[2 * i + 1].x); acc.w += __uint_as_float(pk[2 * i + 1].z);
             }
@@ -214,6 +236,23 @@ __global__ void __launch_bounds__(kThreads, (V <= 4 && !XCHG && RULE_T >= 0) ? L
         const unsigned long long bits = (unsigned long long)__double_as_longlong(l);
         uint4* dst = a.peer[threadIdx.x] + ((int64_t)a.slot * a.world + a.rank) * a.slot_packets + a.n * (int64_t)Q * 2;
         ll_store(dst, (unsigned)(bits & 0xffffffffu), (unsigned)(bits >> 32), a.tag);
+    }
+    if (XCHG && blockIdx.x == 0 && threadIdx.x >= 32 && threadIdx.x < 64 && a.loss_acc && a.loss_global) {
+        // the ranks' losses: lane p of the block's second warp polls source p's loss packet (all in parallel), lane 0
+        // adds them in rank order
+        const int p = threadIdx.x - 32;
+        double l = 0.0;
+        bool ok = true;
+        if (p < a.world) {
+            const uint4* src = a.peer[a.rank] + ((int64_t)a.slot * a.world + p) * a.slot_packets + a.n * (int64_t)Q * 2;
+            uint4 pk = ll_load(src);
+            ok = ll_wait(src, a.tag, pk, a.error, a.timeout_ns, t0);
+            l = __longlong_as_double((long long)(((unsigned long long)pk.z << 32) | (unsigned long long)pk.x));
+        }
+        ok = __all_sync(0xffffffffu, ok);
+        double total = 0.0;
+        for (int q = 0; q < a.world; ++q) total += __shfl_sync(0xffffffffu, l, q);
+        if (p == 0 && ok) *a.loss_global = total;
     }
     const bool hyp = row_mode >= LEC_ROWS_HYP_SHELL;
     const bool adam = rule == LEC_UPD_ADAM;
@@ -445,18 +484,6 @@ __global__ void __launch_bounds__(kThreads, (V <= 4 && !XCHG && RULE_T >= 0) ? L
     if (loss_thread && a.loss_acc) {
         if (a.loss_step) *a.loss_step = my_loss;
         *a.loss_acc = 0.0;
-        if (XCHG && a.loss_global) {
-            const uint4* mine = a.peer[a.rank] + (int64_t)a.slot * a.world * a.slot_packets + a.n * (int64_t)Q * 2;
-            double l = 0.0;
-            bool ok = true;
-            for (int p = 0; p < a.world; ++p) {
-                const uint4* src = mine + (int64_t)p * a.slot_packets;
-                uint4 pk = ll_load(src);
-                ok = ok && ll_wait(src, a.tag, pk, a.error, a.timeout_ns, t0);
-                l += __longlong_as_double((long long)(((unsigned long long)pk.z << 32) | (unsigned long long)pk.x));
-            }
-            if (ok) *a.loss_global = l;
-        }
     }
 }
 

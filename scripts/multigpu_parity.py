@@ -71,7 +71,9 @@ def main():
             far = float(((Ws - W1).abs() > 1e-5).float().mean())
             ok = ok and far < 0.005 and rel < 1e-6 and same
         else:
-            ok = ok and err < 5e-5 and rel < 1e-6 and same
+            # plain SGD on Euclidean cones moves a row by lr * (a gradient sum of ~1e4 in magnitude): its fp32 summation
+            # noise is ~1e-4 where RSGD's (rescaled by (1-|w|)^2/4) is ~1e-5
+            ok = ok and err < (5e-4 if update == "sgd" else 5e-5) and rel < 1e-6 and same
     dist.barrier()
     dist.destroy_process_group()
     if not ok:

@@ -224,13 +224,26 @@ typedef struct lec_update {
  *   error       device int, zero at start: set to 1 when a peer's packets do not arrive within timeout_ms (0 = 30 s).
  *               From then on the rows concerned and every later lec_update_rows on this rank leave the table
  *               untouched; the host must treat a non-zero *error as fatal (engine.ConeStep raises).
+ *
+ * mode LEC_XCHG_TWO_SHOT (tables of megabytes, where sending the whole gradient to every peer would be W-1 table
+ * volumes per rank and step): rank r OWNS rows [r * R, (r + 1) * R).  lec_update_rows then issues three launches --
+ * scatter (every rank stores the replica sum of each row into its owner's buffer, tile flags follow with release
+ * semantics), owner (waits for the `world` partial tiles, adds them in rank order, applies the update rule once per row,
+ * stores the updated raw row into every peer's staging area) and receiver (copies the staged rows of the other owners
+ * into the local table and runs the row transform) -- a reduce-scatter + all-gather that moves 2 (W-1)/W table volumes
+ * per rank; the replicas are identical by construction.  Buffer size: lec_exchange_bytes(n, ld, world, mode);
+ * slot_packets is ignored; grad_out is not produced.
  */
+#define LEC_XCHG_ONE_SHOT 0
+#define LEC_XCHG_TWO_SHOT 1
 typedef struct lec_exchange {
     void* const* peer_bufs; int64_t slot_packets; int world, rank, slot; uint32_t tag;
     double* loss_global; int* error; int64_t timeout_ms;
+    int mode;
 } lec_exchange_t;
 #define LEC_MAX_PEERS 16
 int64_t lec_exchange_packets(int64_t n, int ld);
+int64_t lec_exchange_bytes(int64_t n, int ld, int world, int mode);
 int lec_update_rows(const lec_update_t* u, const lec_exchange_t* x /* NULL or world <= 1: single GPU */, void* stream);
 
 /* ---- one whole training step in one call ---------------------------------------------------------

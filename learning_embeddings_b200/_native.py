@@ -20,7 +20,7 @@ EXPORTS = (
     "lec_abi_version", "lec_error_string", "lec_launch_count", "lec_set_pdl", "lec_index_errors", "lec_rows_fwd", "lec_rows_bwd",
     "lec_featnet_supported", "lec_featnet_fwd", "lec_featnet_wgrad",
     "lec_reduce_replicas", "lec_pairs_flat", "lec_pairs_grouped", "lec_energy_dense", "lec_energy_dense_bwd",
-    "lec_rsgd_update", "lec_exchange_packets", "lec_update_rows", "lec_cone_step", "lec_score_topk", "lec_score_topk_ex",
+    "lec_rsgd_update", "lec_exchange_packets", "lec_exchange_bytes", "lec_update_rows", "lec_cone_step", "lec_score_topk", "lec_score_topk_ex",
     "lec_score_tc_supported",
     "lec_score_workspace_bytes", "lec_score_topk_tc", "lec_mt_seed", "lec_mt_uint32", "lec_mt_randbelow",
     "lec_sample_negatives", "lec_sample_negatives_philox", "lec_philox_below", "lec_f1_workspace_bytes", "lec_f1_sweep",
@@ -54,6 +54,7 @@ class LecExchange(ctypes.Structure):
         ("peer_bufs", ctypes.c_void_p), ("slot_packets", ctypes.c_int64), ("world", ctypes.c_int), ("rank", ctypes.c_int),
         ("slot", ctypes.c_int), ("tag", ctypes.c_uint32),
         ("loss_global", ctypes.c_void_p), ("error", ctypes.c_void_p), ("timeout_ms", ctypes.c_int64),
+        ("mode", ctypes.c_int),
     ]
 
 
@@ -73,6 +74,7 @@ class LecStep(ctypes.Structure):
 
 
 UPD_NONE, UPD_RSGD, UPD_SGD, UPD_ADAM = 0, 1, 2, 3
+XCHG_ONE_SHOT, XCHG_TWO_SHOT = 0, 1
 
 _lib = None
 
@@ -112,6 +114,8 @@ def lib():
         L.lec_index_errors.argtypes = [c_vp, c_i, c_vp]
         L.lec_exchange_packets.argtypes = [c_i64, c_i]
         L.lec_exchange_packets.restype = c_i64
+        L.lec_exchange_bytes.argtypes = [c_i64, c_i, c_i, c_i]
+        L.lec_exchange_bytes.restype = c_i64
         L.lec_update_rows.argtypes = [ctypes.POINTER(LecUpdate), ctypes.POINTER(LecExchange), c_vp]
         L.lec_cone_step.argtypes = [ctypes.POINTER(LecStep), c_vp]
         L.lec_score_topk.argtypes = [c_i, c_i, c_vp, c_i64, c_vp, c_i64, c_i, c_f, c_vp, c_vp, c_i, c_i, c_vp, c_vp,

@@ -31,6 +31,7 @@ int rows_bwd_launch(const float*, const float*, int, int64_t, int64_t, int, int,
 int rsgd_launch(float*, const float*, int, int64_t, int, int, float, float, int, float*, cudaStream_t);
 int reduce_replicas_launch(const float*, int, int64_t, float*, cudaStream_t);
 int update_rows_launch(const lec_update_t&, const lec_exchange_t*, cudaStream_t);
+int64_t two_shot_bytes(int64_t n, int ld, int world);
 bool featnet_supported(int F, int D);
 int featnet_fwd_launch(const FeatArgs&, cudaStream_t);
 int featnet_wgrad_launch(const FeatArgs&, cudaStream_t);
@@ -251,7 +252,8 @@ static int check_exchange(const lec_exchange_t* x, int64_t n, int ld) {
     if (!x->peer_bufs) return LEC_E_NULL;
     if (x->world > LEC_MAX_PEERS || x->rank < 0 || x->rank >= x->world || (x->slot != 0 && x->slot != 1) || x->tag == 0)
         return LEC_E_PEERS;
-    if (x->slot_packets < lec_exchange_packets(n, ld)) return LEC_E_PEERS;
+    if (x->mode != LEC_XCHG_ONE_SHOT && x->mode != LEC_XCHG_TWO_SHOT) return LEC_E_ENUM;
+    if (x->mode == LEC_XCHG_ONE_SHOT && x->slot_packets < lec_exchange_packets(n, ld)) return LEC_E_PEERS;
     for (int p = 0; p < x->world; ++p) {
         if (!x->peer_bufs[p]) return LEC_E_NULL;
         if (reinterpret_cast<uintptr_t>(x->peer_bufs[p]) & 15) return LEC_E_ALIGN;
@@ -260,6 +262,12 @@ static int check_exchange(const lec_exchange_t* x, int64_t n, int ld) {
 }
 
 int64_t lec_exchange_packets(int64_t n, int ld) { return (n < 0 || ld < 0) ? 0 : n * (int64_t)ld / 2 + 1; }
+
+int64_t lec_exchange_bytes(int64_t n, int ld, int world, int mode) {
+    if (n < 0 || ld < 4 || (ld & 3) || world < 1 || world > LEC_MAX_PEERS) return 0;
+    if (mode == LEC_XCHG_TWO_SHOT) return two_shot_bytes(n, ld, world);
+    return 2 * (int64_t)world * lec_exchange_packets(n, ld) * 16;
+}
 
 int lec_update_rows(const lec_update_t* u, const lec_exchange_t* x, void* stream) {
     if (int e = check_update(u)) return e;

@@ -46,9 +46,6 @@ def pack_index_block(pos_from, pos_to, neg_to, neg_from, pin=True, dtype=np.int3
 
 
 RULES = {"none": N.UPD_NONE, "rsgd": N.UPD_RSGD, "sgd": N.UPD_SGD, "adam": N.UPD_ADAM}
-# one-shot exchange buffers hold 2 slots x world sources x 8 bytes per table float on every rank, and every rank sends
-# its whole gradient to every peer: right for label tables (ETHEC: 35 KB), wrong for multi-megabyte ones
-P2P_ONE_SHOT_MAX_BYTES = 4 << 20
 
 
 class ConeStep:
@@ -59,7 +56,7 @@ class ConeStep:
 
     def __init__(self, table, geom, n_neg, max_groups, K=None, alpha=1.0, lr=1e-3, row_mode=None, update="auto",
                  precision=ops.PREC_F64CORE, process_group=None, replicas=None, comm="auto", momentum=0.0,
-                 betas=(0.9, 0.999), eps=1e-8, hyp_rescale=False, project_shell=False, exchange=None):
+                 betas=(0.9, 0.999), eps=1e-8, hyp_rescale=False, project_shell=False, exchange=None, exchange_mode=None):
         N.require_cuda(table)
         if table.dtype != torch.float32 or not table.is_contiguous():
             raise N.LecError("ConeStep: table must be a contiguous float32 CUDA tensor (updated in place)")
@@ -125,17 +122,17 @@ class ConeStep:
             self.comm = "p2p"
         elif world > 1:
             self.comm = "nccl"
-            one_shot_bytes = self.n * self.ld * 4
-            if comm == "p2p" or (comm == "auto" and one_shot_bytes <= P2P_ONE_SHOT_MAX_BYTES):
+            if comm in ("p2p", "auto"):
                 try:
-                    self.px = sharding.PeerExchange(self.n, self.ld, dev, self.pg)
+                    # one-shot packets for label-sized tables, owner-computes two-shot for multi-megabyte ones
+                    self.px = sharding.PeerExchange(self.n, self.ld, dev, self.pg, mode=exchange_mode)
                     self.comm = "p2p"
+                    self.comm_note = "two-shot (reduce-scatter + owner update + all-gather)" if self.px.mode == sharding.TWO_SHOT \
+                        else "one-shot packets inside the update kernel"
                 except Exception as e:  # noqa: BLE001 -- any failure of the symmetric-memory setup
                     if comm == "p2p":
                         raise
                     self.comm_note = "p2p unavailable (%s: %s)" % (type(e).__name__, str(e)[:120])
-            elif comm == "auto":
-                self.comm_note = "table of %.1f MB: one-shot peer exchange not used" % (one_shot_bytes / 1e6)
         if self.comm == "nccl":
             self.grad_sum = torch.empty((self.n, self.ld), device=dev, dtype=torch.float32)
         self.loss_global = self.px.loss_global if self.px is not None else torch.zeros(1, device=dev, dtype=torch.float64)

@@ -35,6 +35,22 @@ def exchange_packets(n, ld):
     return int(n) * int(ld) // 2 + 1
 
 
+def exchange_bytes(n, ld, world, mode):
+    """Bytes of one rank's exchange buffer (lec_exchange_bytes): mode 0 = one-shot packets, 1 = two-shot."""
+    from . import _native as N
+    return int(N.lib().lec_exchange_bytes(int(n), int(ld), int(world), int(mode)))
+
+
+ONE_SHOT, TWO_SHOT = 0, 1
+# one-shot sends the whole gradient to every peer as 8 bytes per float; above this table size the owner-computes
+# two-shot exchange (2 (W-1)/W table volumes per rank, three launches) is used instead
+ONE_SHOT_MAX_TABLE_BYTES = 1 << 20
+
+
+def pick_mode(n, ld):
+    return ONE_SHOT if int(n) * int(ld) * 4 <= ONE_SHOT_MAX_TABLE_BYTES else TWO_SHOT
+
+
 class _ExchangeBase:
     """State of the low-latency exchange of include/lec_b200.h (lec_exchange_t): slot / tag bookkeeping, the device error
     flag and the ctypes view of the peer pointers."""
@@ -57,6 +73,7 @@ class _ExchangeBase:
         x.slot_packets, x.world, x.rank = self.slot_packets, self.world, self.rank
         x.slot, x.tag = self.slot_and_tag()
         x.loss_global, x.error, x.timeout_ms = self.loss_global.data_ptr(), self.error.data_ptr(), self.timeout_ms
+        x.mode = self.mode
 
 
 class PeerExchange(_ExchangeBase):
@@ -64,12 +81,13 @@ class PeerExchange(_ExchangeBase):
     rank, `packet slot[2][world][slot_packets]`, mapped by every rank through torch symmetric memory (CUDA IPC over
     NVLink / NVSwitch)."""
 
-    def __init__(self, n, ld, device, group, timeout_ms=30000):
+    def __init__(self, n, ld, device, group, timeout_ms=30000, mode=None):
         import torch.distributed._symmetric_memory as symm_mem
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        self.mode = pick_mode(n, ld) if mode is None else int(mode)
         self.slot_packets = exchange_packets(n, ld)
-        total = 2 * self.world * self.slot_packets * 4      # floats (16 bytes per packet)
+        total = (exchange_bytes(n, ld, self.world, self.mode) + 3) // 4      # floats
         self.buf = symm_mem.empty(total, dtype=torch.float32, device=device)
         name = getattr(group, "group_name", None)
         try:
@@ -90,13 +108,14 @@ class LocalExchange(_ExchangeBase):
     the "peer" buffers are plain device tensors.  What the single-GPU tests use to run the multi-rank protocol of
     lec_update_rows for real; also a way to drive several model replicas per GPU."""
 
-    def __init__(self, bufs, rank, slot_packets, timeout_ms=5000):
-        self.world, self.rank, self.slot_packets = len(bufs), int(rank), int(slot_packets)
+    def __init__(self, bufs, rank, slot_packets, timeout_ms=5000, mode=ONE_SHOT):
+        self.world, self.rank, self.slot_packets, self.mode = len(bufs), int(rank), int(slot_packets), int(mode)
         self.bufs = bufs
         self._finish([int(b.data_ptr()) for b in bufs], bufs[0].device, timeout_ms)
 
     @staticmethod
-    def make(world, n, ld, device, timeout_ms=5000):
+    def make(world, n, ld, device, timeout_ms=5000, mode=ONE_SHOT):
         sp = exchange_packets(n, ld)
-        bufs = [torch.zeros(2 * world * sp * 4, dtype=torch.float32, device=device) for _ in range(world)]
-        return [LocalExchange(bufs, r, sp, timeout_ms) for r in range(world)]
+        floats = (exchange_bytes(n, ld, world, mode) + 3) // 4
+        bufs = [torch.zeros(floats, dtype=torch.float32, device=device) for _ in range(world)]
+        return [LocalExchange(bufs, r, sp, timeout_ms, mode) for r in range(world)]

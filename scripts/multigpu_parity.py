@@ -33,7 +33,8 @@ def main():
     # "p2p" = the packet exchange inside the fused update kernel (lec_update_rows); "nccl" = all_reduce between the kernels
     cases = [("hyp", 10, "rsgd", 1, "nccl"), ("hyp", 10, "rsgd", 3, "nccl"), ("hyp", 10, "rsgd", 1, "p2p"),
              ("hyp", 10, "rsgd", 4, "p2p"), ("hyp", 10, "rsgd", 5, "p2p"), ("euc", 2, "adam", 4, "p2p"),
-             ("euc", 10, "sgd", 3, "p2p"), ("hyp", 50, "rsgd", 3, "p2p")]
+             ("euc", 10, "sgd", 3, "p2p"), ("hyp", 50, "rsgd", 3, "p2p"), ("hyp", 10, "rsgd", 4, "two_shot"),
+             ("hyp", 50, "rsgd", 3, "two_shot"), ("euc", 10, "adam", 3, "two_shot")]
     for geom, D, update, step_count, comm in cases:
         g = torch.Generator().manual_seed(0)
         w = torch.randn(h.n, D, generator=g)
@@ -41,7 +42,8 @@ def main():
         W0 = (0.0990195 + 0.05 * torch.rand(h.n, 1, generator=g)) * w / w.norm(dim=1, keepdim=True) if geom == "hyp" else w
         # sharded
         Ws = W0.to(dev).clone()
-        eng = ConeStep(Ws, geom, Nn, B, K=K, alpha=0.05, lr=0.01, update=update, process_group=dist.group.WORLD, comm=comm)
+        eng = ConeStep(Ws, geom, Nn, B, K=K, alpha=0.05, lr=0.01, update=update, process_group=dist.group.WORLD,
+                       comm="p2p" if comm == "two_shot" else comm, exchange_mode=sharding.TWO_SHOT if comm == "two_shot" else None)
         if rank == 0:
             print("%s D=%d %s: comm requested %s -> %s %s" % (geom, D, update, comm, eng.comm, eng.comm_note), flush=True)
         su, sv, snt, snf = sharding.shard_groups(u, v, nt, nf, rank, world)

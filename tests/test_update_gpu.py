@@ -144,11 +144,13 @@ def engine_kwargs(geom):
     return dict(K=3.0, alpha=0.05, lr=0.01, update="adam")
 
 
-@pytest.mark.parametrize("geom,D,world", [("hyp", 10, 2), ("hyp", 10, 4), ("euc", 2, 2), ("hyp", 50, 3)])
-def test_multi_rank_exchange_in_process_equals_single_rank_step(geom, D, world):
+@pytest.mark.parametrize("geom,D,world,mode", [("hyp", 10, 2, 0), ("hyp", 10, 4, 0), ("euc", 2, 2, 0), ("hyp", 50, 3, 0),
+                                               ("hyp", 10, 2, 1), ("hyp", 50, 4, 1), ("euc", 10, 3, 1)])
+def test_multi_rank_exchange_in_process_equals_single_rank_step(geom, D, world, mode):
     """`world` engines on one GPU, one stream each, each taking its slice of every batch and exchanging gradients
-    through lec_update_rows' packet protocol: the replicas of the table stay BIT-identical, and equal the table of one
-    engine that ran the whole batch (up to the fp32 summation order of the gradient)."""
+    through lec_update_rows -- mode 0: one-shot packets inside the update kernel; mode 1: two-shot (scatter to the row's
+    owner, owner update, all-gather of the updated rows) -- the replicas of the table stay BIT-identical, and equal the
+    table of one engine that ran the whole batch (up to the fp32 summation order of the gradient)."""
     Nn, B, steps = 5, 4096, 5
     h, batches = ethec_batches(steps, B, Nn, seed=3)
     W0 = table_init(h.n, D, "ball" if geom == "hyp" else "normal", seed=1)
@@ -156,7 +158,7 @@ def test_multi_rank_exchange_in_process_equals_single_rank_step(geom, D, world):
         W0 = cones._shell_project(W0 * 0.6, cones.inner_radius(0.1))
     kw = engine_kwargs(geom)
     single = ConeStep(W0.to(DEV).clone(), geom, Nn, B, **kw)
-    xs = sharding.LocalExchange.make(world, h.n, ops.padded_dim(D), torch.device(DEV))
+    xs = sharding.LocalExchange.make(world, h.n, ops.padded_dim(D), torch.device(DEV), mode=mode)
     streams = [torch.cuda.Stream() for _ in range(world)]
     engs = []
     for r in range(world):

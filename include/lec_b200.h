@@ -232,14 +232,19 @@ typedef struct lec_update {
  * stores the updated raw row into every peer's staging area) and receiver (copies the staged rows of the other owners
  * into the local table and runs the row transform) -- a reduce-scatter + all-gather that moves 2 (W-1)/W table volumes
  * per rank; the replicas are identical by construction.  Buffer size: lec_exchange_bytes(n, ld, world, mode);
- * slot_packets is ignored; grad_out is not produced.
+ * slot_packets is ignored; grad_out is not produced.  `phases` (two-shot only) selects which of the three launches
+ * this call issues -- LEC_XCHG_SCATTER | LEC_XCHG_OWNER | LEC_XCHG_RECEIVER, 0 = all -- for a host that wants to put
+ * other work between them (or drives several ranks from one stream); a step is complete after all three.
  */
+#define LEC_XCHG_SCATTER 1
+#define LEC_XCHG_OWNER 2
+#define LEC_XCHG_RECEIVER 4
 #define LEC_XCHG_ONE_SHOT 0
 #define LEC_XCHG_TWO_SHOT 1
 typedef struct lec_exchange {
     void* const* peer_bufs; int64_t slot_packets; int world, rank, slot; uint32_t tag;
     double* loss_global; int* error; int64_t timeout_ms;
-    int mode;
+    int mode, phases;
 } lec_exchange_t;
 #define LEC_MAX_PEERS 16
 int64_t lec_exchange_packets(int64_t n, int ld);

@@ -54,7 +54,7 @@ class LecExchange(ctypes.Structure):
         ("peer_bufs", ctypes.c_void_p), ("slot_packets", ctypes.c_int64), ("world", ctypes.c_int), ("rank", ctypes.c_int),
         ("slot", ctypes.c_int), ("tag", ctypes.c_uint32),
         ("loss_global", ctypes.c_void_p), ("error", ctypes.c_void_p), ("timeout_ms", ctypes.c_int64),
-        ("mode", ctypes.c_int),
+        ("mode", ctypes.c_int), ("phases", ctypes.c_int),
     ]
 
 

@@ -244,6 +244,37 @@ __device__ __forceinline__ Aux<S> row_aux(int geom, S A, float Kf) {
     return o;
 }
 
+// The same terms for the per-ROW producers (lec_rows_fwd, lec_update_rows), which run this once per table row inside
+// a latency-bound kernel: reciprocal square roots instead of the sqrt / three divisions, and psi = asin(h) evaluated as
+// atan2f(h, sqrt(1 - h^2)) with sqrt(1 - h^2) formed in fp64 -- atan2 is well conditioned where asin is not (asin' = 224
+// at the clamp), so the fp32 evaluation keeps ~1e-7 absolute accuracy, which is all the pair kernels use of psi (they
+// subtract it from an fp32 angle).  A = 0 / NaN behave as in row_aux.
+__device__ __forceinline__ Aux<double> row_aux_fast(int geom, double A, float Kf) {
+    Aux<double> o;
+    const double K = (double)Kf;
+    o.A = A;
+    if (geom == LEC_GEOM_HYP) {
+        const double rA = rsqrt(A);                                  // 1 / |x|
+        o.ria = rA;
+        bool in;
+        const double hc = clamp_eps<double>(K * (1.0 - A) * rA, in);  // order_embeddings_h.py:1114
+        const double q = (1.0 - hc) * (1.0 + hc);
+        const double rq = rsqrt(q);                                  // 1 / sqrt(1 - h^2)
+        o.t0 = (double)atan2f((float)hc, (float)(q * rq));
+        const double h_A = -0.5 * K * (1.0 + A) * rA * rA * rA;       // dh / d|x|^2
+        o.t1 = in ? -rq * h_A * 2.0 : 0.0;
+    } else if (geom == LEC_GEOM_EUC) {
+        const double rA = rsqrt(A);
+        o.ria = A * rA > (double)kNormEps ? rA : 1.0 / (double)kNormEps;
+        const double q = 1.0 - K * K * rA * rA;                      // order_embeddings.py:967 (NaN when |x| < K)
+        o.t0 = sqrt(q);
+        o.t1 = K * K * rA * rA * rA * rA * rsqrt(q);
+    } else {
+        o.ria = o.t0 = o.t1 = 0.0;
+    }
+    return o;
+}
+
 template <typename S>
 __device__ __forceinline__ Aux<S> load_aux(const double* __restrict__ aux, int64_t row) {
     const double2 p0 = __ldg(reinterpret_cast<const double2*>(aux + 4 * row));

@@ -72,7 +72,7 @@ template <int TT>
 __device__ __forceinline__ void aux_flush(AuxBatch& b, int& fill, int geom, float K, double* __restrict__ aux) {
     __syncthreads();
     if ((int)threadIdx.x < fill && b.row[threadIdx.x] >= 0) {
-        const Aux<double> x = row_aux<double>(geom, b.A[threadIdx.x], K);
+        const Aux<double> x = row_aux_fast(geom, b.A[threadIdx.x], K);
         double2* dst = reinterpret_cast<double2*>(aux + 4 * b.row[threadIdx.x]);
         dst[0] = make_double2(x.A, x.ria);
         dst[1] = make_double2(x.t0, x.t1);

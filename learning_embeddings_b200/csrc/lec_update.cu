@@ -36,7 +36,7 @@ struct UpdArgs {
     int world, rank, slot; unsigned tag; int64_t slot_packets; uint4* peer[kMaxPeers];
     double* loss_global; int* error; unsigned long long timeout_ns;
     // two-shot exchange (large tables): rank r owns rows [r * rows_per_rank, (r + 1) * rows_per_rank)
-    int64_t rows_per_rank; int tiles_per_rank;
+    int64_t rows_per_rank; int tiles_per_rank; int phases;
 };
 
 // ---- two-shot exchange: layout of one rank's buffer --------------------------------------------------------------------
@@ -318,26 +318,28 @@ __device__ __forceinline__ void row_rule(const UpdArgs& a, const int rule, const
         }
         uu = team_sum<TT, double>(uu); gg = team_sum<TT, double>(gg); eg = team_sum<TT, double>(eg);
         se = team_sum<TT, double>(se); sg = team_sum<TT, double>(sg);
-        // conformal factor (order_embeddings_h.py:662-666; SURVEY F4: the norm, not its square)
+        // conformal factor (order_embeddings_h.py:662-666; SURVEY F4: the norm, not its square): 1/lambda = (1 - |w|) / 2.
+        // Only the cancelling quantities (1 - |w|, 1 - |w|^2, the Moebius denominator) need fp64; square roots and
+        // quotients whose results end up as fp32 coefficients are taken in fp32 (as the reference takes all of them).
         const float wn = (float)sqrt(uu);
-        const float lam = 2.f / (1.f - (a.lambda_mode == 1 ? (float)uu : wn));
-        const float inv = 1.f / lam;
+        const float inv = 0.5f * (1.f - (a.lambda_mode == 1 ? (float)uu : wn));
         const float gs = inv * inv;
         const double Dn = (double)D, e15 = 1e-15, e6 = 1e-6;
         const double av = -(double)a.lr * (double)gs;                     // v_d = av g_d + 1e-15
         const double vv = av * av * gg + 2.0 * av * e15 * sg + Dn * e15 * e15;
-        const double vn = sqrt(vv);
-        const float th = tanhf(fminf(fmaxf(lam * (float)vn / 2.f, -15.f), 15.f));
-        const double c = (double)th / vn;
+        const float vn = sqrtf((float)vv);
+        const float th = tanhf(fminf(fmaxf(0.5f * vn / inv, -15.f), 15.f));   // lambda |v| / 2
+        const double c = (double)(th / vn);
         const double al = c * av, be = c * e15 + e6;                      // t_d = al g_d + be
         const double tt = al * al * gg + 2.0 * al * be * sg + Dn * be * be;
         const double uv2 = 2.0 * (al * eg + be * se);
         const double den = 1.0 + uv2 + tt * uu;
-        const double cw = (1.0 + uv2 + tt) / den, ct = (1.0 - uu) / den;
+        const double rden = (double)(1.f / (float)den);
+        const double cw = (1.0 + uv2 + tt) * rden, ct = (1.0 - uu) * rden;
         const double cg = ct * al, cb = ct * be;                          // res_d = cw e_d + cg g_d + cb
         const double rr = cw * cw * uu + cg * cg * gg + Dn * cb * cb + 2.0 * (cw * cg * eg + cw * cb * se + cg * cb * sg);
         float mul, add, div;
-        shell_factor((float)sqrt(rr), a.r_in, false, mul, add, div);
+        shell_factor(sqrtf((float)rr), a.r_in, false, mul, add, div);
         const float sc = (mul != 1.f || div != 1.f) ? mul / div : 1.f;
         const float f_w = (float)cw * sc, f_g = (float)cg * sc, f_b = (float)cb * sc;
         float* go = (valid && a.grad_out) ? a.grad_out + row * (int64_t)D : nullptr;
@@ -402,7 +404,7 @@ __device__ __forceinline__ void row_rule(const UpdArgs& a, const int rule, const
 // ---- step 5: Embedder.forward of the (updated) raw row e -> rows_out, |row|^2 parked for the batched aperture terms ----
 template <int TT, int V>
 __device__ __forceinline__ void row_forward(const UpdArgs& a, const int row_mode, float (&e)[4 * V], const int64_t row,
-                                            const bool valid, const int lane, AuxBatch& s_aux, int& aux_fill) {
+                                            const bool valid, const int lane) {
     const int D = a.D, Q = a.ld >> 2;
     const bool hyp = row_mode >= LEC_ROWS_HYP_SHELL;
     // ---- 5. Embedder.forward of the updated row + its aperture terms ---------------------------------------------
@@ -446,7 +448,13 @@ __device__ __forceinline__ void row_forward(const UpdArgs& a, const int row_mode
 #pragma unroll
             for (int i = 0; i < 4 * V; ++i) A = fma((double)e[i], (double)e[i], A);
             A = team_sum<TT, double>(A);
-            aux_push<TT>(s_aux, aux_fill, A, row, valid, a.geom, a.K, a.aux_out);
+            // the aperture terms of the row, by every lane of its team (rsqrt-based: ~90 issue slots, no block barrier)
+            const Aux<double> x = row_aux_fast(a.geom, A, a.K);
+            if (valid && lane == 0) {
+                double2* dst = reinterpret_cast<double2*>(a.aux_out + 4 * row);
+                dst[0] = make_double2(x.A, x.ria);
+                dst[1] = make_double2(x.t0, x.t1);
+            }
         }
     }
 }
@@ -457,8 +465,6 @@ template <int TT, int V, bool XCHG, int RULE_T, int MODE_T>
 __global__ void __launch_bounds__(kThreads, (V <= 4 && !XCHG && RULE_T >= 0) ? LEC_UPD_MINBLOCKS : 1) update_rows_kernel(const UpdArgs a) {
     const int rule = RULE_T >= 0 ? RULE_T : a.rule;
     const int row_mode = MODE_T >= 0 ? MODE_T : a.row_mode;
-    __shared__ AuxBatch s_aux;
-    int aux_fill = 0;
     pdl_launch_dependents();
     pdl_wait();   // the pair kernel's reductions into the replicas (and its loss) are complete
     if (XCHG && a.error && ld_volatile_int(a.error) != 0) return;   // an earlier exchange failed: the table is left alone
@@ -554,9 +560,8 @@ __global__ void __launch_bounds__(kThreads, (V <= 4 && !XCHG && RULE_T >= 0) ? L
             if (__any_sync(0xffffffffu, !ok)) valid = false;
         }
         row_rule<TT, V>(a, rule, row_mode, g, e, mb, vb, row, rc, valid, lane);
-        row_forward<TT, V>(a, row_mode, e, row, valid, lane, s_aux, aux_fill);
+        row_forward<TT, V>(a, row_mode, e, row, valid, lane);
     }
-    if (a.rows_out && a.aux_out) aux_flush<TT>(s_aux, aux_fill, a.geom, a.K, a.aux_out);
     if (loss_thread && a.loss_acc) {
         if (a.loss_step) *a.loss_step = my_loss;
         *a.loss_acc = 0.0;
@@ -620,12 +625,10 @@ __global__ void __launch_bounds__(kThreads) xchg_scatter_kernel(const UpdArgs a)
 }
 
 template <int TT, int V, int RULE_T, int MODE_T>
-__global__ void __launch_bounds__(kThreads) update_owner_kernel(const UpdArgs a) {
+__global__ void __launch_bounds__(kThreads, V <= 4 ? 2 : 1) update_owner_kernel(const UpdArgs a) {
     const int rule = RULE_T >= 0 ? RULE_T : a.rule;
     const int row_mode = MODE_T >= 0 ? MODE_T : a.row_mode;
-    __shared__ AuxBatch s_aux;
     __shared__ int s_ok;
-    int aux_fill = 0;
     pdl_launch_dependents();
     pdl_wait();
     if (a.error && ld_volatile_int(a.error) != 0) return;
@@ -711,14 +714,13 @@ __global__ void __launch_bounds__(kThreads) update_owner_kernel(const UpdArgs a)
                 }
             }
         }
-        row_forward<TT, V>(a, row_mode, e, row, valid, lane, s_aux, aux_fill);
+        row_forward<TT, V>(a, row_mode, e, row, valid, lane);
         __syncthreads();
         if ((int)threadIdx.x < a.world && (int)threadIdx.x != a.rank && tile_ok) {
             __threadfence_system();
             st_release_sys(L.ag_flag(a.peer[threadIdx.x], a.slot) + (int64_t)a.rank * a.tiles_per_rank + tl, a.tag);
         }
     }
-    if (a.rows_out && a.aux_out) aux_flush<TT>(s_aux, aux_fill, a.geom, a.K, a.aux_out);
     if (loss_thread && a.loss_acc) {
         if (a.loss_step) *a.loss_step = my_loss;
         *a.loss_acc = 0.0;
@@ -727,9 +729,7 @@ __global__ void __launch_bounds__(kThreads) update_owner_kernel(const UpdArgs a)
 
 template <int TT, int V>
 __global__ void __launch_bounds__(kThreads) update_receiver_kernel(const UpdArgs a) {
-    __shared__ AuxBatch s_aux;
     __shared__ int s_ok;
-    int aux_fill = 0;
     pdl_launch_dependents();
     pdl_wait();
     if (a.error && ld_volatile_int(a.error) != 0) return;
@@ -761,10 +761,9 @@ __global__ void __launch_bounds__(kThreads) update_receiver_kernel(const UpdArgs
             e[4 * j] = c.x; e[4 * j + 1] = c.y; e[4 * j + 2] = c.z; e[4 * j + 3] = c.w;
         }
         if (valid) store_raw<TT, V>(a.table + row * (int64_t)D, e, D, lane, a.tv);
-        row_forward<TT, V>(a, a.row_mode, e, row, valid, lane, s_aux, aux_fill);
+        row_forward<TT, V>(a, a.row_mode, e, row, valid, lane);
         __syncthreads();
     }
-    if (a.rows_out && a.aux_out) aux_flush<TT>(s_aux, aux_fill, a.geom, a.K, a.aux_out);
 }
 
 constexpr int kUpdGridCap = 148 * 8;   // the same on every rank: a block's rows are the same rows everywhere
@@ -787,10 +786,14 @@ static int two_shot_go2(const UpdArgs& a, cudaStream_t st) {
     const int tpb = kThreads / TT;
     const int64_t tiles = (a.n + tpb - 1) / tpb;
     auto grid_of = [](int64_t t) { return (int)(t < 1 ? 1 : (t < kUpdGridCap ? t : kUpdGridCap)); };
-    cudaError_t e = launch_step_kernel(xchg_scatter_kernel<TT, V>, grid_of(tiles), kThreads, st, a);
-    ++g_launches;
-    if (e == cudaSuccess) { e = launch_step_kernel(update_owner_kernel<TT, V, RULE_T, MODE_T>, grid_of(a.tiles_per_rank), kThreads, st, a); ++g_launches; }
-    if (e == cudaSuccess) { e = launch_step_kernel(update_receiver_kernel<TT, V>, grid_of(tiles), kThreads, st, a); ++g_launches; }
+    const int ph = a.phases ? a.phases : (LEC_XCHG_SCATTER | LEC_XCHG_OWNER | LEC_XCHG_RECEIVER);
+    cudaError_t e = cudaSuccess;
+    if (ph & LEC_XCHG_SCATTER) { e = launch_step_kernel(xchg_scatter_kernel<TT, V>, grid_of(tiles), kThreads, st, a); ++g_launches; }
+    if (e == cudaSuccess && (ph & LEC_XCHG_OWNER)) {
+        e = launch_step_kernel(update_owner_kernel<TT, V, RULE_T, MODE_T>, grid_of(a.tiles_per_rank), kThreads, st, a);
+        ++g_launches;
+    }
+    if (e == cudaSuccess && (ph & LEC_XCHG_RECEIVER)) { e = launch_step_kernel(update_receiver_kernel<TT, V>, grid_of(tiles), kThreads, st, a); ++g_launches; }
     return (int)(e != cudaSuccess ? e : cudaGetLastError());
 }
 
@@ -849,6 +852,7 @@ int update_rows_launch(const lec_update_t& u, const lec_exchange_t* x, cudaStrea
         for (int p = 0; p < x->world; ++p) a.peer[p] = static_cast<uint4*>(x->peer_bufs[p]);
         a.loss_global = x->loss_global; a.error = x->error;
         a.timeout_ns = (unsigned long long)(x->timeout_ms > 0 ? x->timeout_ms : 30000) * 1000000ull;
+        a.phases = x->phases;
     }
     if (u.n == 0) return 0;
     const int Q = u.ld >> 2;

@@ -197,8 +197,9 @@ class ConeStep:
         otherwise reuses the transformed rows its previous update left behind."""
         self._rows_valid = False
 
-    def reduce_and_update(self):
-        """Second half of a step issued as separate calls: [exchange] + update + next rows (lec_update_rows)."""
+    def reduce_and_update(self, phases=0):
+        """Second half of a step issued as separate calls: [exchange] + update + next rows (lec_update_rows).  `phases`
+        (two-shot exchange only): bit mask of the launches to issue now -- 1 scatter, 2 owner, 4 receiver; 0 = all."""
         import ctypes
         lib, st = N.lib(), N.stream_ptr(self.table.device)
         u, x = N.LecUpdate(), N.LecExchange()
@@ -213,8 +214,10 @@ class ConeStep:
             self._fill_update(u)
             if self.comm == "p2p":
                 self.px.fill(x)
+                x.phases = int(phases)
         N.check(lib.lec_update_rows(ctypes.byref(u), ctypes.byref(x) if self.comm == "p2p" else None, st), "lec_update_rows")
-        self._after_step()
+        if not phases or (phases & 4):
+            self._after_step()
 
     def _after_step(self):
         if self.update != "none":

@@ -73,7 +73,7 @@ class _ExchangeBase:
         x.slot_packets, x.world, x.rank = self.slot_packets, self.world, self.rank
         x.slot, x.tag = self.slot_and_tag()
         x.loss_global, x.error, x.timeout_ms = self.loss_global.data_ptr(), self.error.data_ptr(), self.timeout_ms
-        x.mode = self.mode
+        x.mode, x.phases = self.mode, 0
 
 
 class PeerExchange(_ExchangeBase):

@@ -168,12 +168,26 @@ def test_multi_rank_exchange_in_process_equals_single_rank_step(geom, D, world, 
     for (u, v, nt, nf) in batches:
         blk = pack_index_block(u, v, nt, nf, n_rows=h.n).to(DEV)
         single.step_device(*single._split(blk, B))
+        parts = []
         for r in range(world):
             lo, hi = sharding.shard_bounds(B, r, world)
-            part = pack_index_block(u[lo:hi], v[lo:hi], nt[lo:hi], nf[lo:hi]).to(DEV)
-            with torch.cuda.stream(streams[r]):
-                part.record_stream(streams[r])
-                engs[r].step_device(*engs[r]._split(part, hi - lo))
+            parts.append((pack_index_block(u[lo:hi], v[lo:hi], nt[lo:hi], nf[lo:hi]).to(DEV), hi - lo))
+        if mode == 0:
+            # every rank's whole step on its own stream: the update kernels of the ranks run side by side and wait for one
+            # another's packets
+            for r in range(world):
+                with torch.cuda.stream(streams[r]):
+                    parts[r][0].record_stream(streams[r])
+                    engs[r].step_device(*engs[r]._split(*parts[r]))
+        else:
+            # the three launches of the two-shot exchange, rank by rank on ONE stream (lec_exchange_t.phases): each phase
+            # only waits for the phase before it, so this order needs no concurrency between the ranks' kernels
+            torch.cuda.synchronize()
+            for r in range(world):
+                engs[r].forward_backward(*engs[r]._split(*parts[r]))
+            for phase in (1, 2, 4):
+                for r in range(world):
+                    engs[r].reduce_and_update(phases=phase)
         torch.cuda.synchronize()
         for r in range(world):
             engs[r].check_exchange()

@@ -592,6 +592,12 @@ __global__ void __launch_bounds__(kThreads) xchg_scatter_kernel(const UpdArgs a)
     const int Q = a.ld >> 2;
     const TwoShot L(a.world, a.rows_per_rank, a.tiles_per_rank, a.ld);
     const int64_t n_tiles = (a.n + kTeams - 1) / kTeams;
+    if (blockIdx.x == 0 && (int)threadIdx.x < a.world && a.loss_acc) {
+        // this rank's loss of the step: one packet to every rank (gathered by the owner kernels, so that every wait of the
+        // exchange is on something an EARLIER launch of the peers produced)
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(*a.loss_acc);
+        ll_store(L.loss(a.peer[threadIdx.x], a.slot, a.world) + a.rank, (unsigned)(bits & 0xffffffffu), (unsigned)(bits >> 32), a.tag);
+    }
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int owner = (int)(tile / a.tiles_per_rank);
         const int64_t row = tile * kTeams + team;
@@ -641,12 +647,8 @@ __global__ void __launch_bounds__(kThreads, V <= 4 ? 2 : 1) update_owner_kernel(
     double my_loss = 0.0;
     const bool loss_thread = blockIdx.x == 0 && threadIdx.x == 0;
     if (loss_thread && a.loss_acc) my_loss = *a.loss_acc;
-    if (blockIdx.x == 0 && (int)threadIdx.x < a.world && a.loss_acc) {
-        const unsigned long long bits = (unsigned long long)__double_as_longlong(*a.loss_acc);
-        ll_store(L.loss(a.peer[threadIdx.x], a.slot, a.world) + a.rank, (unsigned)(bits & 0xffffffffu), (unsigned)(bits >> 32), a.tag);
-    }
     if (blockIdx.x == 0 && threadIdx.x >= 32 && threadIdx.x < 64 && a.loss_acc && a.loss_global) {
-        const int p = threadIdx.x - 32;
+        const int p = threadIdx.x - 32;   // the losses were sent by the scatter kernels
         double l = 0.0;
         bool ok = true;
         if (p < a.world) {

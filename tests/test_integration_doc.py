@@ -66,5 +66,6 @@ def test_doc_training_iteration_equals_engine():
         eng.step_device(*eng._split(blk, B))
         torch.cuda.synchronize()
         assert abs(float(loss) - float(eng.loss)) <= 1e-6 * abs(float(eng.loss))
-        assert torch.equal(E_neg, eng.E_neg[:B])
+        # (the two tables drift apart by fp32 rounding after the first step: the gradient scatter is not order-deterministic)
+        np.testing.assert_allclose(E_neg.cpu().numpy(), eng.E_neg[:B].cpu().numpy(), rtol=1e-4, atol=1e-5)
         np.testing.assert_allclose(Wa.cpu().numpy(), Wb.cpu().numpy(), rtol=1e-4, atol=2e-5)

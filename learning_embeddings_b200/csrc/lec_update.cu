@@ -622,11 +622,11 @@ __global__ void __launch_bounds__(kThreads) xchg_scatter_kernel(const UpdArgs a)
             }
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence_system();   // cumulative: the block's stores above are ordered before the flag
+        // release at system scope is cumulative: the block's stores above (ordered before this thread by the barrier) are
+        // visible to the owner before the flag is
+        if (threadIdx.x == 0)
             st_release_sys(L.rs_flag(a.peer[owner], a.slot) + (int64_t)a.rank * a.tiles_per_rank + (tile - (int64_t)owner * a.tiles_per_rank),
                            a.tag);
-        }
     }
 }
 
@@ -719,7 +719,6 @@ __global__ void __launch_bounds__(kThreads, V <= 4 ? 2 : 1) update_owner_kernel(
         row_forward<TT, V>(a, row_mode, e, row, valid, lane);
         __syncthreads();
         if ((int)threadIdx.x < a.world && (int)threadIdx.x != a.rank && tile_ok) {
-            __threadfence_system();
             st_release_sys(L.ag_flag(a.peer[threadIdx.x], a.slot) + (int64_t)a.rank * a.tiles_per_rank + tl, a.tag);
         }
     }

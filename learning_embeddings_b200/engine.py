@@ -149,6 +149,11 @@ class ConeStep:
 
     def _fill_update(self, u, grad_rows=None, replicas=None):
         """lec_update_t for the next step (scalars are re-read every step, so lr / alpha / K may change between steps)."""
+        if getattr(u, "_lec_static", None) is self and grad_rows is None:
+            # the pointers and shapes of this engine are already in the struct: only what may change between steps
+            u.rule, u.K, u.lr, u.r_in, u.opt_step = RULES[self.update], self.K, self.lr, self.r_in, self.opt_step + 1
+            u.grad_out = self.grad_table.data_ptr() if self.write_grad_table else None
+            return u
         u.rule, u.row_mode, u.geom, u.lambda_mode = RULES[self.update], self.row_mode, N.GEOM[self.geom], 0
         u.hyp_rescale, u.project_shell = int(self.hyp_rescale), int(self.project_shell)
         u.K, u.lr, u.r_in = self.K, self.lr, self.r_in
@@ -162,6 +167,8 @@ class ConeStep:
         u.rows_out, u.aux_out = self.rows.data_ptr(), self.aux.data_ptr()
         u.grad_out = self.grad_table.data_ptr() if self.write_grad_table else None
         u.loss_acc, u.loss_step = self.loss_acc.data_ptr(), self.loss.data_ptr()
+        if grad_rows is None:
+            u._lec_static = self
         return u
 
     def _rows_fwd(self):
@@ -257,19 +264,21 @@ class ConeStep:
         s = self._struct
         if s is None:
             s = self._struct = N.LecStep()
+            self._upd = s.upd    # ONE wrapper of the embedded struct (every `s.upd` would build a new Python object)
+            s.E_pos, s.E_neg, s.N = self.E_pos.data_ptr(), self.E_neg.data_ptr(), self.n_neg
+            s.xchg.world = 0
+            if self.comm == "p2p":
+                self.px.fill(s.xchg)
         s.geom, s.precision, s.alpha = N.GEOM[self.geom], self.precision, self.alpha
         s.fused = 1 if (self.fused and self._rows_valid) else 0
         s.pos_from, s.pos_to = pos_from.data_ptr(), pos_to.data_ptr()
         s.neg_to, s.neg_from = neg_to.data_ptr(), neg_from.data_ptr()
-        s.idx_bytes, s.B, s.N = pos_from.element_size(), B, self.n_neg
+        s.idx_bytes, s.B = pos_from.element_size(), B
         s.w_pos = w_pos.data_ptr() if w_pos is not None else None
         s.w_neg = w_neg.data_ptr() if w_neg is not None else None
-        s.E_pos, s.E_neg = self.E_pos.data_ptr(), self.E_neg.data_ptr()
-        self._fill_update(s.upd)
+        self._fill_update(self._upd)
         if self.comm == "p2p":
-            self.px.fill(s.xchg)
-        else:
-            s.xchg.world = 0
+            s.xchg.slot, s.xchg.tag = self.px.slot_and_tag()
         ev = self.kernel_events
         if ev is not None:
             for e in ev:
@@ -508,7 +517,13 @@ class JointConeStep:
         self._rows_valid = False
 
     def _update_struct(self, which):
-        u = N.LecUpdate()
+        cache = self.__dict__.setdefault("_ucache", {})
+        if which in cache:
+            u = cache[which]
+            u.opt_step = self.opt_step + 1
+            u.lr = self.lr if which == "table" else self.lr_fc
+            return u
+        u = cache[which] = N.LecUpdate()
         u.lambda_mode, u.beta1, u.beta2, u.eps, u.momentum = 0, 0.9, 0.999, 1e-8, 0.0
         u.opt_step = self.opt_step + 1
         if which == "table":
@@ -543,18 +558,21 @@ class JointConeStep:
         geom = N.GEOM[self.geom]
         prev_pdl = lib.lec_set_pdl(1)
         try:
-            Y = self.Y[:m]
+            vp = ctypes.c_void_p
+            p_Y, p_gY = vp(self.Y.data_ptr()), vp(self.gY.data_ptr())
+            p_rows_img = vp(self.rows.data_ptr() + 4 * n * ld)
+            p_aux_img = vp(self.aux.data_ptr() + 8 * 4 * n)
+            p_grad_img = vp(self.grad_rows.data_ptr() + 4 * n * ld)
             N.check(lib.lec_featnet_fwd(N._p(self.features), self.features.shape[0], self.F, N._p(img_sel),
-                                        img_sel.element_size(), m, N._p(self.fc_w), N._p(self.fc_b), D, N._p(Y), st),
+                                        img_sel.element_size(), m, N._p(self.fc_w), N._p(self.fc_b), D, p_Y, st),
                     "lec_featnet_fwd")
             if not self._rows_valid:
                 # first step (or the table changed behind the engine's back): label rows, cleared label gradient and loss
                 N.check(lib.lec_rows_fwd(N._p(self.table), n, D, self.lab_mode, geom, self.K, N._p(self.rows), ld,
                                          N._p(self.aux), N._p(self.grad_rows), self.replicas, self.n_total * ld,
                                          N._p(self.loss_acc), st), "lec_rows_fwd")
-            rows_img, aux_img = self.rows[n:n + m], self.aux[n:n + m]
-            N.check(lib.lec_rows_fwd(N._p(Y), m, D, self.img_mode, geom, self.K, N._p(rows_img), ld, N._p(aux_img),
-                                     N._p(self.grad_rows[0, n:]), self.replicas, self.n_total * ld, N._p(None), st),
+            N.check(lib.lec_rows_fwd(p_Y, m, D, self.img_mode, geom, self.K, p_rows_img, ld, p_aux_img,
+                                     p_grad_img, self.replicas, self.n_total * ld, N._p(None), st),
                     "lec_rows_fwd")
             ev = self.kernel_events
             if ev is not None:
@@ -566,18 +584,21 @@ class JointConeStep:
                 "lec_pairs_grouped")
             if ev is not None:
                 ev[1].record()
-            gY = self.gY[:m]
-            N.check(lib.lec_rows_bwd(N._p(Y), N._p(self.grad_rows[0, n:]), self.replicas, self.n_total * ld, m, D, ld,
-                                     self.img_mode, self.K, N._p(gY), 0, st), "lec_rows_bwd")
+            N.check(lib.lec_rows_bwd(p_Y, p_grad_img, self.replicas, self.n_total * ld, m, D, ld,
+                                     self.img_mode, self.K, p_gY, 0, st), "lec_rows_bwd")
             N.check(lib.lec_featnet_wgrad(N._p(self.features), self.features.shape[0], self.F, N._p(img_sel),
-                                          img_sel.element_size(), m, N._p(gY), D, N._p(self.fc_grad), self.fc_replicas,
+                                          img_sel.element_size(), m, p_gY, D, N._p(self.fc_grad), self.fc_replicas,
                                           self.fc_grad.shape[1], st), "lec_featnet_wgrad")
+            xcache = self.__dict__.setdefault("_xcache", {})
             for which, px in (("table", self.px), ("fc", self.px_fc)):
                 u = self._update_struct(which)
                 x = None
                 if px is not None:
-                    x = N.LecExchange()
-                    px.fill(x)
+                    x = xcache.get(which)
+                    if x is None:
+                        x = xcache[which] = N.LecExchange()
+                        px.fill(x)
+                    x.slot, x.tag = px.slot_and_tag()
                 N.check(lib.lec_update_rows(ctypes.byref(u), ctypes.byref(x) if x is not None else None, st), "lec_update_rows")
                 if px is not None:
                     px.step += 1

@@ -177,7 +177,7 @@ int lec_pairs_grouped(int geom, int precision, const float* rows, const double* 
     if (geom != LEC_GEOM_OE && !aux) return LEC_E_NULL;
     if (aux && (reinterpret_cast<uintptr_t>(aux) & 15)) return LEC_E_ALIGN;
     GroupArgs a{rows, aux, ld, pos_from, pos_to, neg_to, neg_from, idx_bytes, B, N, w_pos, w_neg, K, alpha,
-                E_pos, E_neg, loss_out, grad_rows, grad_replicas, n_rows * (int64_t)ld, n_rows, index_errors_ptr()};
+                E_pos, E_neg, loss_out, grad_rows, grad_replicas, n_rows * (int64_t)ld, n_rows, index_errors_ptr(), 0};
     cudaStream_t st = (cudaStream_t)stream;
     switch (core) {
         case CORE_EUC32: return launch_grouped_euc32(a, st);

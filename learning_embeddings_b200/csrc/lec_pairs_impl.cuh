@@ -36,6 +36,7 @@ struct GroupArgs {
     float K, alpha;
     float* E_pos; float* E_neg; double* loss_out; float* grad_rows; int grad_replicas; int64_t replica_stride;
     int64_t n_rows; unsigned* index_errors;
+    int pdl_late;  // 1: let the dependent launch in only when this block has finished its groups (LEC_PDL_LATE)
     int split;  // teams per group (>= 1): team s of a group takes negatives p = s, s + split, ... of both lists
     int64_t stage_floats;  // > 0: every block first copies the transformed table (n * ld floats) into shared memory
 };
@@ -171,7 +172,7 @@ template <int CORE, int T, int V, bool GRAD, int MB>
 __global__ void __launch_bounds__(kThreads, MB) pairs_grouped_kernel(const GroupArgs a) {
     using Tr = CoreTraits<CORE>;
     using Acc = typename Tr::Acc;
-    pdl_launch_dependents();   // the update kernel may take its (few) SM slots now; it parks in pdl_wait()
+    if (!a.pdl_late) pdl_launch_dependents();   // the update kernel may take its (few) SM slots now; it parks in pdl_wait()
     pdl_wait();                // rows / aux / cleared replicas of the previous update are complete
     // Hot label table in shared memory (ETHEC: 723 x 12 floats = 35 KB): every endpoint gather of the block then is an
     // LDS.128 instead of an L1-cached global load.
@@ -345,6 +346,7 @@ __global__ void __launch_bounds__(kThreads, MB) pairs_grouped_kernel(const Group
             }
         }
     }
+    if (a.pdl_late) pdl_launch_dependents();
     block_add_double(loss, a.loss_out);
 }
 
@@ -449,6 +451,8 @@ int launch_grouped_tv(const GroupArgs& a0, cudaStream_t st) {
         else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pairs_grouped_kernel<CORE, T, V, true, 1>, block, 0);
         return nb > 0 ? nb : 1;
     }();
+    static const int pdl_late = [] { const char* e = getenv("LEC_PDL_LATE"); return e ? atoi(e) : 0; }();
+    a.pdl_late = pdl_late;
     a.split = choose_split(a.B, a.N, (int64_t)sm_count() * resident_blocks * (block / T));
     const int grid = grid_for(a.B * a.split, block / T, 8 * kThreads / block);
     // Shared-memory staging of the table (LEC_STAGE_ROWS=1; tables <= 40 KB) was measured and is OFF by default: on

@@ -469,8 +469,9 @@ __global__ void __launch_bounds__(kThreads, (V <= 4 && !XCHG && RULE_T >= 0) ? L
     pdl_wait();   // the pair kernel's reductions into the replicas (and its loss) are complete
     if (XCHG && a.error && ld_volatile_int(a.error) != 0) return;   // an earlier exchange failed: the table is left alone
     const int lane = threadIdx.x % TT;
-    const int64_t n_teams = (int64_t)gridDim.x * (kThreads / TT);
-    const int64_t team = (int64_t)blockIdx.x * (kThreads / TT) + threadIdx.x / TT;
+    const int tpb_rt = (int)blockDim.x / TT;   // the launcher picks the block size: small tables use small blocks on many SMs
+    const int64_t n_teams = (int64_t)gridDim.x * tpb_rt;
+    const int64_t team = (int64_t)blockIdx.x * tpb_rt + threadIdx.x / TT;
     const int64_t iters = (a.n + n_teams - 1) / n_teams;
     const int D = a.D, Q = a.ld >> 2;
     unsigned long long t0 = 0;
@@ -588,7 +589,6 @@ __global__ void __launch_bounds__(kThreads) xchg_scatter_kernel(const UpdArgs a)
     pdl_wait();
     if (a.error && ld_volatile_int(a.error) != 0) return;
     constexpr int kTeams = kThreads / TT;
-    const int lane = threadIdx.x % TT, team = threadIdx.x / TT;
     const int Q = a.ld >> 2;
     const TwoShot L(a.world, a.rows_per_rank, a.tiles_per_rank, a.ld);
     const int64_t n_tiles = (a.n + kTeams - 1) / kTeams;
@@ -598,26 +598,31 @@ __global__ void __launch_bounds__(kThreads) xchg_scatter_kernel(const UpdArgs a)
         const unsigned long long bits = (unsigned long long)__double_as_longlong(*a.loss_acc);
         ll_store(L.loss(a.peer[threadIdx.x], a.slot, a.world) + a.rank, (unsigned)(bits & 0xffffffffu), (unsigned)(bits >> 32), a.tag);
     }
+    // A tile's rows are one contiguous slab of kTeams * ld floats in the replicas and in the owner's region alike: the
+    // block moves it as a flat array, 512 contiguous bytes per warp store (whole NVLink packets, not 64-byte pieces)
+    const int slab4 = kTeams * Q;                     // float4 per full tile
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int owner = (int)(tile / a.tiles_per_rank);
-        const int64_t row = tile * kTeams + team;
-        if (row < a.n) {
-            float* gr = a.grad_rows + row * (int64_t)a.ld;
-            float* dst = L.rs(a.peer[owner], a.slot) + ((int64_t)a.rank * a.rows_per_rank + (row - owner * a.rows_per_rank)) * a.ld;
-            float4 c[V];
+        const int64_t row0 = tile * kTeams;
+        const int64_t rows_here = a.n - row0 < kTeams ? a.n - row0 : kTeams;
+        const int n4 = (int)rows_here * Q;
+        float* gr = a.grad_rows + row0 * (int64_t)a.ld;
+        float* dst = L.rs(a.peer[owner], a.slot) + ((int64_t)a.rank * a.rows_per_rank + (row0 - (int64_t)owner * a.rows_per_rank)) * a.ld;
+        for (int i0 = 0; i0 < slab4; i0 += 4 * kThreads) {
+            float4 c[4];
 #pragma unroll
-            for (int j = 0; j < V; ++j) {
-                const int q = lane + TT * j;
-                if (q < Q) c[j] = a.replicas == 1 ? *reinterpret_cast<const float4*>(gr + 4 * q)
-                                                  : rsum4(gr + 4 * q, a.replicas, a.replica_stride);
+            for (int k = 0; k < 4; ++k) {
+                const int i = i0 + k * kThreads + (int)threadIdx.x;
+                if (i < n4) c[k] = a.replicas == 1 ? *reinterpret_cast<const float4*>(gr + 4 * i)
+                                                   : rsum4(gr + 4 * i, a.replicas, a.replica_stride);
             }
 #pragma unroll
-            for (int j = 0; j < V; ++j) {
-                const int q = lane + TT * j;
-                if (q < Q) {
-                    *reinterpret_cast<float4*>(dst + 4 * q) = c[j];
+            for (int k = 0; k < 4; ++k) {
+                const int i = i0 + k * kThreads + (int)threadIdx.x;
+                if (i < n4) {
+                    *reinterpret_cast<float4*>(dst + 4 * i) = c[k];
                     for (int r = 0; r < a.replicas; ++r)
-                        *reinterpret_cast<float4*>(gr + r * a.replica_stride + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
+                        *reinterpret_cast<float4*>(gr + r * a.replica_stride + 4 * i) = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
         }
@@ -635,6 +640,7 @@ __global__ void __launch_bounds__(kThreads, V <= 4 ? 2 : 1) update_owner_kernel(
     const int rule = RULE_T >= 0 ? RULE_T : a.rule;
     const int row_mode = MODE_T >= 0 ? MODE_T : a.row_mode;
     __shared__ int s_ok;
+    extern __shared__ __align__(16) float s_stage[];   // [kThreads / TT rows][ld]
     pdl_launch_dependents();
     pdl_wait();
     if (a.error && ld_volatile_int(a.error) != 0) return;
@@ -704,19 +710,30 @@ __global__ void __launch_bounds__(kThreads, V <= 4 ? 2 : 1) update_owner_kernel(
             for (int j = 0; j < V; ++j) { g[4 * j] = acc[j].x; g[4 * j + 1] = acc[j].y; g[4 * j + 2] = acc[j].z; g[4 * j + 3] = acc[j].w; }
         }
         row_rule<TT, V>(a, rule, row_mode, g, e, mb, vb, row, rc, valid, lane);
-        if (valid) {
-            // the updated raw row (pad columns are zero) goes to every peer's staging area
-            for (int p = 0; p < a.world; ++p) {
-                if (p == a.rank) continue;
-                float* dst = L.ag(a.peer[p], a.slot) + row * (int64_t)a.ld;
+        // the tile's updated raw rows (pad columns zero) are staged in shared memory as the slab they form in every peer's
+        // staging area ...
+        {
+            float4* st4 = reinterpret_cast<float4*>(s_stage) + team * Q;
 #pragma unroll
-                for (int j = 0; j < V; ++j) {
-                    const int q = lane + TT * j;
-                    if (q < Q) *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(e[4 * j], e[4 * j + 1], e[4 * j + 2], e[4 * j + 3]);
-                }
+            for (int j = 0; j < V; ++j) {
+                const int q = lane + TT * j;
+                if (q < Q) st4[q] = make_float4(e[4 * j], e[4 * j + 1], e[4 * j + 2], e[4 * j + 3]);
             }
         }
         row_forward<TT, V>(a, row_mode, e, row, valid, lane);
+        __syncthreads();
+        // ... and copied out flat: 512 contiguous bytes per warp store and peer
+        if (tile_ok) {
+            int64_t rows_here = my_rows - tl * kTeams;
+            if (rows_here > kTeams) rows_here = kTeams;
+            const int n4 = (int)rows_here * Q;
+            const float4* src4 = reinterpret_cast<const float4*>(s_stage);
+            for (int p = 0; p < a.world; ++p) {
+                if (p == a.rank) continue;
+                float4* dst4 = reinterpret_cast<float4*>(L.ag(a.peer[p], a.slot) + (row_lo + tl * kTeams) * (int64_t)a.ld);
+                for (int i = threadIdx.x; i < n4; i += kThreads) dst4[i] = src4[i];
+            }
+        }
         __syncthreads();
         if ((int)threadIdx.x < a.world && (int)threadIdx.x != a.rank && tile_ok) {
             st_release_sys(L.ag_flag(a.peer[threadIdx.x], a.slot) + (int64_t)a.rank * a.tiles_per_rank + tl, a.tag);
@@ -771,13 +788,17 @@ constexpr int kUpdGridCap = 148 * 8;   // the same on every rank: a block's rows
 
 template <int TT, int V, int RULE_T, int MODE_T>
 static int update_go2(const UpdArgs& a, cudaStream_t st) {
-    const int tpb = kThreads / TT;
+    // a label-sized table (ETHEC: 723 rows) is pure latency: 64-thread blocks spread its rows over ~4x as many SMs (more
+    // load / store / packet slots in flight); the choice depends on n only, so every rank makes the same one
+    int block = kThreads;
+    while (block > 64 && (a.n + block / TT - 1) / (block / TT) < 96) block >>= 1;
+    const int tpb = block / TT;
     int64_t need = (a.n + tpb - 1) / tpb;
     if (need < 1) need = 1;
     const int grid = (int)(need < kUpdGridCap ? need : kUpdGridCap);
     cudaError_t e;
-    if (a.world > 1) e = launch_step_kernel(update_rows_kernel<TT, V, true, RULE_T, MODE_T>, grid, kThreads, st, a);
-    else e = launch_step_kernel(update_rows_kernel<TT, V, false, RULE_T, MODE_T>, grid, kThreads, st, a);
+    if (a.world > 1) e = launch_step_kernel(update_rows_kernel<TT, V, true, RULE_T, MODE_T>, grid, block, st, a);
+    else e = launch_step_kernel(update_rows_kernel<TT, V, false, RULE_T, MODE_T>, grid, block, st, a);
     ++g_launches;
     return (int)(e != cudaSuccess ? e : cudaGetLastError());
 }
@@ -791,7 +812,9 @@ static int two_shot_go2(const UpdArgs& a, cudaStream_t st) {
     cudaError_t e = cudaSuccess;
     if (ph & LEC_XCHG_SCATTER) { e = launch_step_kernel(xchg_scatter_kernel<TT, V>, grid_of(tiles), kThreads, st, a); ++g_launches; }
     if (e == cudaSuccess && (ph & LEC_XCHG_OWNER)) {
-        e = launch_step_kernel(update_owner_kernel<TT, V, RULE_T, MODE_T>, grid_of(a.tiles_per_rank), kThreads, st, a);
+        const size_t stage = (size_t)tpb * a.ld * sizeof(float);
+        if (stage > 48 * 1024) cudaFuncSetAttribute(update_owner_kernel<TT, V, RULE_T, MODE_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage);
+        e = launch_step_kernel(update_owner_kernel<TT, V, RULE_T, MODE_T>, grid_of(a.tiles_per_rank), kThreads, st, a, stage);
         ++g_launches;
     }
     if (e == cudaSuccess && (ph & LEC_XCHG_RECEIVER)) { e = launch_step_kernel(update_receiver_kernel<TT, V>, grid_of(tiles), kThreads, st, a); ++g_launches; }

@@ -44,7 +44,7 @@ def exchange_bytes(n, ld, world, mode):
 ONE_SHOT, TWO_SHOT = 0, 1
 # one-shot sends the whole gradient to every peer as 8 bytes per float; above this table size the owner-computes
 # two-shot exchange (2 (W-1)/W table volumes per rank, three launches) is used instead
-ONE_SHOT_MAX_TABLE_BYTES = 1 << 20
+ONE_SHOT_MAX_TABLE_BYTES = 256 << 10   # 8 GPUs: 8192 x 12 floats (393 KB) one-shot 27.5 us, two-shot 23.9 us
 
 
 def pick_mode(n, ld):

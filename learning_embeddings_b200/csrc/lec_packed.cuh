@@ -94,4 +94,36 @@ __device__ __forceinline__ u64 acos_clamped2(u64 g2) {
     return ffma2(sg, r, off);
 }
 
+// z = acos(clamp(g, -1+1e-5, 1-1e-5)) + c for a packed pair, with c = pi/2 - psi folded into one constant
+// (hpc = {pi/2 - psi, pi/2 - psi'}): with r = acos(|g|) = sqrt(1-|g|) P(|g|) and h = pi/2 - r > 0,
+//     acos(g) = pi/2 - sign(g) h      =>      z = (pi/2 - psi) + (h with the sign bit of -g)
+// -- one FFMA2 for h, one LOP3 per score for the sign, one FADD2; the off / sign-multiply form of acos_clamped2
+// above spends two more packed operations per pair.  |h - (pi/2 - r)| <= 6e-8, so z carries ~1.2e-7 absolute
+// rounding (the reference's own fp32 acos is no better).  NaN propagates.
+__device__ __forceinline__ u64 acos_clamped_plus2(u64 g2, u64 hpc) {
+    float g0, g1;
+    unpack2(g2, g0, g1);
+    const float hi = 1.f - kClampEps;
+    const float a0 = min_nan(fabsf(g0), hi), a1 = min_nan(fabsf(g1), hi);
+    const u64 ax = pack2(a0, a1);
+    const u64 t = ffma2(ax, pack2(-1.f, -1.f), pack2(1.f, 1.f));
+    float t0, t1;
+    unpack2(t, t0, t1);
+    const u64 sq = pack2(sqrt_approx(t0), sqrt_approx(t1));
+    u64 P = pack2(-(LEC_ACOS_A7), -(LEC_ACOS_A7));   // -P(|g|): the coefficients carry the minus sign of h = pi/2 - sqrt(1-|g|) P(|g|)
+    P = ffma2(P, ax, pack2(-(LEC_ACOS_A6), -(LEC_ACOS_A6)));
+    P = ffma2(P, ax, pack2(-(LEC_ACOS_A5), -(LEC_ACOS_A5)));
+    P = ffma2(P, ax, pack2(-(LEC_ACOS_A4), -(LEC_ACOS_A4)));
+    P = ffma2(P, ax, pack2(-(LEC_ACOS_A3), -(LEC_ACOS_A3)));
+    P = ffma2(P, ax, pack2(-(LEC_ACOS_A2), -(LEC_ACOS_A2)));
+    P = ffma2(P, ax, pack2(-(LEC_ACOS_A1), -(LEC_ACOS_A1)));
+    P = ffma2(P, ax, pack2(-(LEC_ACOS_A0), -(LEC_ACOS_A0)));
+    float h0, h1;
+    unpack2(ffma2(sq, P, pack2(1.57079637f, 1.57079637f)), h0, h1);   // h = pi/2 - r >= 6e-8: sign bit clear (or NaN)
+    // m = h carrying the sign of -g:  h | (~g & 0x80000000)  (one LOP3)
+    const float m0 = __int_as_float(__float_as_int(h0) | (~__float_as_int(g0) & 0x80000000));
+    const float m1 = __int_as_float(__float_as_int(h1) | (~__float_as_int(g1) & 0x80000000));
+    return fadd2(hpc, pack2(m0, m1));
+}
+
 }  // namespace lec

@@ -23,8 +23,8 @@
 // Data movement:
 //   labels  -> lec_score_mma_prep (one small launch): per chunk of 32 labels a "blob" in the caller's
 //              workspace = B_hi tile | B_lo tile (96 rows, K-major, no-swizzle UMMA canonical layout) | per-label-pair
-//              constants {-psi, cos psi, sin psi} (fp64-computed, same terms as lec_rows_fwd's aux) | header;
-//              plus one -psi[L] table for the top-k merge.  The main kernel pulls a blob with two cp.async.bulk copies
+//              constants {pi/2 - psi, cos psi, sin psi} (fp64-computed, same terms as lec_rows_fwd's aux) | header;
+//              plus one (pi/2 - psi)[L] table for the top-k merge.  The main kernel pulls a blob with two cp.async.bulk copies
 //              (TMA, mbarrier complete_tx): the tiles into a tile stage that the MMAs' completion frees, the constants
 //              + header into a constant stage that the epilogue frees.
 //   images  -> each CTA reads its 128 rows once, splits [y, |y|^2, 1] into hi/lo and writes them to tensor memory
@@ -125,11 +125,12 @@ __global__ void __launch_bounds__(kMmaN) score_mma_prep_kernel(const float* __re
     if (form == 0) {
         const double sp = sin(x.t0), cp = sqrt(fmax(0.0, 1.0 - sp * sp));
         float* q = cst + (jl >> 1) * 12 + (jl & 1);
-        if (live) npsi[ch.label0 + jl] = (float)(-x.t0);   // per-label copy for the top-k merge (candidates outlive their blob)
-        if (forms == 3) {   // {-psi, -psi', cos psi, cos psi'} {sin psi, sin psi', 0, 0} {0, 0, 0, 0}
-            q[0] = (float)(-x.t0); q[2] = (float)cp; q[4] = (float)sp; q[6] = 0.f; q[8] = 0.f; q[10] = 0.f;
-        } else {            // {A, A', 1+A, 1+A'} {A^2, A'^2, -psi, -psi'} {cos psi, cos psi', sin psi, sin psi'}
-            q[0] = (float)Av; q[2] = (float)(1.0 + Av); q[4] = (float)(Av * Av); q[6] = (float)(-x.t0);
+        const float hpsi = (float)(1.5707963267948966 - x.t0);   // pi/2 - psi: the constant acos_clamped_plus2 adds (fp64-computed)
+        if (live) npsi[ch.label0 + jl] = hpsi;   // per-label copy for the top-k merge (candidates outlive their blob)
+        if (forms == 3) {   // {pi/2-psi, pi/2-psi', cos psi, cos psi'} {sin psi, sin psi', 0, 0} {0, 0, 0, 0}
+            q[0] = hpsi; q[2] = (float)cp; q[4] = (float)sp; q[6] = 0.f; q[8] = 0.f; q[10] = 0.f;
+        } else {            // {A, A', 1+A, 1+A'} {A^2, A'^2, pi/2-psi, pi/2-psi'} {cos psi, cos psi', sin psi, sin psi'}
+            q[0] = (float)Av; q[2] = (float)(1.0 + Av); q[4] = (float)(Av * Av); q[6] = hpsi;
             q[8] = (float)cp; q[10] = (float)sp;
         }
     }
@@ -194,6 +195,17 @@ __device__ __forceinline__ void tmem_alloc(unsigned dst_smem, unsigned cols) {
 }
 __device__ __forceinline__ void tmem_dealloc(unsigned taddr, unsigned cols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// one lane of the (converged) warp; the compiler knows the region under it runs on a single thread (ELECT), so operands
+// of the uniform-datapath instructions inside (UTCHMMA, UTCBAR, UBLKCP) need no per-lane serialisation loop
+__device__ __forceinline__ bool elect_one() {
+    unsigned pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "@px mov.s32 %0, 1;\n\t}"
+        : "+r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -270,7 +282,7 @@ struct MmaArgs {
     const unsigned char* ws; int n_chunks;
     float* scores;           // label-major [L, N] or NULL
     int32_t* topk_idx; float* topk_val; int k, n_levels;
-    const float* npsi;       // [L] -psi(label), written by the prep launch (top-k merge of deferred candidates)
+    const float* npsi;       // [L] pi/2 - psi(label), written by the prep launch (top-k merge of deferred candidates)
     int ring;                // candidate ring entries per thread
     int stages;              // label-tile stages in shared memory (1..4), released by the MMAs that read them
     int cstages;             // constant + header stages (1..4), released by the epilogue threads
@@ -281,6 +293,20 @@ struct MmaArgs {
 };
 
 constexpr int kMmaMaxStages = 4;
+
+// Optional cycle trace of the pipeline (build with -DLEC_TC_TRACE; LEC_TC_TRACE=0 silences it): sums of clock64 deltas over
+// all CTAs, printed by the launcher.  [0] MMA warp waits for tiles  [1] MMA warp waits for a free accumulator  [2] MMA
+// issue  [3] chunks issued  [4] epilogue (first thread of each 4-warp group) waits for constants  [5] ... for the
+// accumulator  [6] TMEM loads  [7] whole chunk loop  [8] chunk visits  [9] MMA issue -> accumulator seen by the epilogue
+// [10] CTA prologue (start -> first MMA may issue)  [11] CTAs
+#ifdef LEC_TC_TRACE
+__device__ unsigned long long g_tc_trace[16];
+#define TC_T0(var) const long long var = clock64()
+#define TC_ADD(slot, var) trace_acc[slot] += clock64() - (var)
+#else
+#define TC_T0(var)
+#define TC_ADD(slot, var)
+#endif
 constexpr int kEpiThreads = 2 * kMmaM;          // 8 epilogue warps: two threads per image, 16 labels (3 x 16 columns) each
 constexpr int kMmaThreads = kEpiThreads + 64;   // + warp 8 (tcgen05.mma issue) + warp 9 (TMA bulk copies)
 
@@ -379,6 +405,10 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(const MmaArgs
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 6 * kMmaMaxStages);
 
     const int tid = threadIdx.x, warp = tid >> 5;
+#ifdef LEC_TC_TRACE
+    const long long cta_t0 = clock64();
+    __shared__ long long trace_issue[256];
+#endif
     const int NA = a.acc_stages;
     const unsigned bar_full0 = smem_u32(bars), bar_done0 = smem_u32(bars + kMmaMaxStages), bar_empty0 = smem_u32(bars + 2 * kMmaMaxStages);
     const unsigned bar_accfree0 = smem_u32(bars + 3 * kMmaMaxStages);
@@ -435,7 +465,7 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(const MmaArgs
             tmem_st8(dst + (unsigned)k0, o);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    } else if (warp == 9 && (tid & 31) == 0) {
+    } else if (warp == 9 && elect_one()) {
         // the first label blobs stream in while the image tile is being converted
         const unsigned sB_u = smem_u32(sB), sC_u = smem_u32(sC);
         for (int c = 0; c < NS && c < a.n_chunks; ++c) {
@@ -456,7 +486,7 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(const MmaArgs
         // loader: the tiles of chunk ct go into tile stage ct % NS as soon as the MMAs of chunk ct - NS have completed,
         // the constants of chunk cc into constant stage cc % NC once the epilogue of chunk cc - NC has released it.
         // One thread serves both streams and never blocks on one while the other could move.
-        if ((tid & 31) == 0) {
+        if (elect_one()) {
             const unsigned sB_u = smem_u32(sB), sC_u = smem_u32(sC);
             int ct = NS, st = 0, cc = NC, sc = 0;
             unsigned part = 0, parc = 0, idle = 0;
@@ -485,38 +515,96 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(const MmaArgs
         }
         __syncwarp();
     } else if (warp == 8) {
-        // MMA issuer: chunk c needs its blob (full[c % NS]) and accumulator buffer c % NA, which is free as soon as
-        // every epilogue thread has pulled chunk c - NA out of it (accfree), i.e. before that chunk's arithmetic.
+        // MMA issuer: chunk c needs its tiles (tfull[c % NS]) and an accumulator buffer, which is free as soon as every
+        // epilogue thread that reads it has pulled the previous chunk out of it (accfree), i.e. before that chunk's
+        // arithmetic.  The whole issue sequence runs on one elected lane with warp-uniform operands, so it compiles to
+        // uniform-datapath code (UTCHMMA back to back); r2 trace: with `if (lane == 0)` around each tcgen05.mma the
+        // compiler serialised every operand through an ELECT / R2UR.BROADCAST loop and one chunk took ~1500 cycles to
+        // issue -- the epilogue warps spent a third of their time waiting for accumulators.
         const unsigned sB_u = smem_u32(sB);
         const unsigned idesc = umma_idesc_tf32(kMmaM, kMmaN);
-        const bool issuer = (tid & 31) == 0;
-        int s = 0, t = 0;
-        unsigned par = 0, par_t = 1;   // accfree[t] is first waited on for chunk NA, i.e. after one wrap of t
-        for (int c = 0; c < a.n_chunks; ++c) {
-            mbar_wait(bar_tfull0 + 8 * s, par, a.sleep_ns);
-            if (c >= NA) mbar_wait(bar_accfree0 + 8 * t, par_t, a.sleep_ns);
+#ifdef LEC_TC_TRACE
+        long long trace_acc[4] = {0, 0, 0, 0};
+        trace_acc[3] = a.n_chunks;
+        if ((tid & 31) == 0) { atomicAdd(&g_tc_trace[10], (unsigned long long)(clock64() - cta_t0)); atomicAdd(&g_tc_trace[11], 1ull); }
+#endif
+        auto issue = [&](int c, int s, int t) {
+            (void)c;
             tc_fence_after();
             const unsigned d = tmem_base + (unsigned)(t * kMmaN);
             const unsigned bh = sB_u + s * tiles, bl = bh + b_tile;
-            unsigned acc = 0;
-            for (int pass = 0; pass < 3; ++pass) {
-                const unsigned pa = tmem_base + ((pass == 2) ? col_alo : col_ahi);   // hi.hi, hi.lo, lo.hi
-                const unsigned pb = (pass == 1) ? bl : bh;
-                for (int ks = 0; ks < KS; ++ks) {
-                    const uint64_t db = umma_desc(pb + ks * 2 * (kMmaN * 16), kMmaN * 16, 128);
-                    if (issuer) tc_mma_tf32_ts(d, pa + (unsigned)(ks * 8), db, idesc, acc);
-                    acc = 1;
+            if (elect_one()) {
+                // the descriptors of a stage differ in the 14-bit start-address field only: one add per MMA
+                const uint64_t dh = umma_desc(bh, kMmaN * 16, 128), dl = umma_desc(bl, kMmaN * 16, 128);
+                unsigned acc = 0;
+#pragma unroll 1
+                for (int pass = 0; pass < 3; ++pass) {
+                    const unsigned pa = tmem_base + ((pass == 2) ? col_alo : col_ahi);   // hi.hi, hi.lo, lo.hi
+                    const uint64_t pb = (pass == 1) ? dl : dh;
+                    for (int ks = 0; ks < KS; ++ks) {
+                        tc_mma_tf32_ts(d, pa + (unsigned)(ks * 8), pb + (uint64_t)(ks * ((2 * kMmaN * 16) >> 4)), idesc, acc);
+                        acc = 1;
+                    }
                 }
-            }
-            if (issuer) {
                 tc_commit(bar_done0 + 8 * t);    // accumulator of chunk c complete -> epilogue
                 tc_commit(bar_tfree0 + 8 * s);   // tile stage s read -> loader
             }
             __syncwarp();
-            if (++s == NS) { s = 0; par ^= 1u; }
-            if (++t == NA) { t = 0; par_t ^= 1u; }
+#ifdef LEC_TC_TRACE
+            if ((tid & 31) == 0) trace_issue[c & 255] = clock64();
+#endif
+        };
+        if (MODE == 1 && NA == 2 && a.alt) {
+            // Matrix-only launches: each 4-warp epilogue group owns one accumulator and every other chunk.  The two
+            // chunk streams are served independently -- whichever group has released its accumulator (and has its tiles)
+            // gets its next chunk; with in-order issue the faster group waited for the slower one's release.
+            int cn[2] = {0, 1}, sg[2] = {0, 1 % NS};
+            unsigned ps[2] = {0u, (unsigned)((1 / NS) & 1)}, pa_[2] = {0u, 0u};
+            unsigned idle = 0;
+            while (cn[0] < a.n_chunks || cn[1] < a.n_chunks) {
+                bool any = false;
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    const int c = cn[g];
+                    if (c >= a.n_chunks) continue;
+                    if (!mbar_test(bar_tfull0 + 8 * sg[g], ps[g])) continue;
+                    if (c >= 2) {
+                        if (!mbar_test(bar_accfree0 + 8 * g, pa_[g])) continue;
+                        pa_[g] ^= 1u;
+                    }
+                    issue(c, sg[g], g);
+                    cn[g] = c + 2;
+                    sg[g] += 2;
+                    while (sg[g] >= NS) { sg[g] -= NS; ps[g] ^= 1u; }
+                    any = true;
+                }
+                if (any) idle = 0;
+                else {
+                    __nanosleep(20);
+                    if (++idle > (1u << 24)) __trap();   // a lost arrival traps instead of hanging the GPU
+                }
+            }
+        } else {
+            int s = 0, t = 0;
+            unsigned par = 0, par_t = 1;   // accfree[t] is first waited on for chunk NA, i.e. after one wrap of t
+            for (int c = 0; c < a.n_chunks; ++c) {
+                TC_T0(w0);
+                mbar_wait(bar_tfull0 + 8 * s, par, a.sleep_ns);
+                TC_ADD(0, w0);
+                TC_T0(w1);
+                if (c >= NA) mbar_wait(bar_accfree0 + 8 * t, par_t, a.sleep_ns);
+                TC_ADD(1, w1);
+                TC_T0(w2);
+                issue(c, s, t);
+                TC_ADD(2, w2);
+                if (++s == NS) { s = 0; par ^= 1u; }
+                if (++t == NA) { t = 0; par_t ^= 1u; }
+            }
         }
         __syncwarp();
+#ifdef LEC_TC_TRACE
+        if ((tid & 31) == 0) for (int q = 0; q < 4; ++q) atomicAdd(&g_tc_trace[q], (unsigned long long)trace_acc[q]);
+#endif
     } else {
         // ================================ epilogue warps ================================
         const u64 B2 = pack2(Bn, Bn), C2 = pack2(-1.f - Bn, -1.f - Bn);   // FORMS == 1 only
@@ -560,7 +648,7 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(const MmaArgs
                 if (MODE == 0) {
                     const float np0 = __ldg(a.npsi + lab0), np1 = __ldg(a.npsi + lab1);
                     float z0, z1;
-                    unpack2(fadd2(acos_clamped2(pack2(e0.x, e1.x)), pack2(np0, np1)), z0, z1);
+                    unpack2(acos_clamped_plus2(pack2(e0.x, e1.x), pack2(np0, np1)), z0, z1);
                     E0 = max_nan(z0, 0.f);
                     E1 = max_nan(z1, 0.f);
                 }
@@ -573,6 +661,7 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(const MmaArgs
         };
 
         const int lane_base = (warp & 3) * 32;
+        const unsigned row_bytes = (unsigned)a.N * 4u;   // bytes between two label rows of the score matrix (the host checks N < 2^30)
         // Chunk ownership.  Top-k launches: every epilogue thread visits every chunk and takes half of its labels (the two
         // threads of an image keep separate lists, merged at the end of a level).  Matrix-only launches with two
         // accumulator buffers (ALT): warps 0-3 take the even chunks and warps 4-7 the odd ones, all labels of the chunk in
@@ -584,8 +673,15 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(const MmaArgs
         int s = alt ? half : 0, t = alt ? half : 0;
         unsigned par = 0, par_t = 0;
         while (s >= NC) { s -= NC; par ^= 1u; }
+#ifdef LEC_TC_TRACE
+        long long trace_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        const bool tracer = (tid & 127) == 0;
+        const long long loop_t0 = clock64();
+#endif
         for (int c = alt ? half : 0; c < a.n_chunks; c += cstep) {
+            TC_T0(e0);
             mbar_wait(bar_full0 + 8 * s, par, a.sleep_ns);   // constants + header of chunk c visible to this thread
+            TC_ADD(4, e0);
             const unsigned char* bl = sC + (size_t)s * cstride;
             const float* cst = reinterpret_cast<const float*>(bl);
             const MmaHdr hdr = *reinterpret_cast<const MmaHdr*>(bl + mma_const_bytes(FORMS));
@@ -600,7 +696,13 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(const MmaArgs
                 psi_max = hdr.psi_max;
                 refresh();
             }
+            TC_T0(e1);
             mbar_wait(bar_done0 + 8 * t, par_t, a.sleep_ns);   // accumulator of chunk c complete
+            TC_ADD(5, e1);
+#ifdef LEC_TC_TRACE
+            trace_acc[9] += clock64() - trace_issue[c & 255];
+            trace_acc[8] += 1;
+#endif
             tc_fence_after();
 
             const bool store = (MODE != 0) && a.scores != nullptr && img_ok;
@@ -611,8 +713,10 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(const MmaArgs
             float v[3][16];
             {
                 const unsigned tcol = tmem_base + ((unsigned)lane_base << 16) + (unsigned)(t * kMmaN);
+                TC_T0(e2);
                 tmem_ld16x3(tcol + (unsigned)lbase, tcol + (unsigned)(FORMS == 3 ? NL + lbase : lbase + 16),
                             tcol + (unsigned)(FORMS == 3 ? 2 * NL + lbase : lbase + 32), v[0], v[1], v[2]);
+                TC_ADD(6, e2);
             }
             if (hb == cstep - 1) {
                 tc_fence_before();
@@ -630,13 +734,13 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(const MmaArgs
                 for (int q = 0; q < 8; ++q) {
                     u64 num, d2;
                     if (FORMS == 3) {
-                        const float2 k1 = *reinterpret_cast<const float2*>(cp + q * 12);        // -psi, -psi'
+                        const float2 k1 = *reinterpret_cast<const float2*>(cp + q * 12);        // pi/2 - psi, pi/2 - psi'
                         NPSI[q] = pack2(k1.x, k1.y);
                         num = pack2(v[0][2 * q], v[0][2 * q + 1]);
                         d2 = fmul2(pack2(v[2][2 * q], v[2][2 * q + 1]), pack2(v[1][2 * q], v[1][2 * q + 1]));   // A s^2 w^2
                     } else {
                         const float4 k0 = *reinterpret_cast<const float4*>(cp + q * 12);       // A, A', 1+A, 1+A'
-                        const float4 k1 = *reinterpret_cast<const float4*>(cp + q * 12 + 4);   // A^2, A'^2, -psi, -psi'
+                        const float4 k1 = *reinterpret_cast<const float4*>(cp + q * 12 + 4);   // A^2, A'^2, pi/2 - psi, pi/2 - psi'
                         const u64 A2 = pack2(k0.x, k0.y), A12 = pack2(k0.z, k0.w), ASQ = pack2(k1.x, k1.y);
                         NPSI[q] = pack2(k1.z, k1.w);
                         const u64 P = pack2(v[gi][2 * q], v[gi][2 * q + 1]);
@@ -659,7 +763,7 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(const MmaArgs
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
                             float z0, z1;
-                            unpack2(fadd2(acos_clamped2(g[q]), NPSI[q]), z0, z1);
+                            unpack2(acos_clamped_plus2(g[q], NPSI[q]), z0, z1);
                             if (2 * q < g_count) list.insert_ascending(max_nan(z0, 0.f), lab0 + 2 * q);
                             if (2 * q + 1 < g_count) list.insert_ascending(max_nan(z1, 0.f), lab0 + 2 * q + 1);
                         }
@@ -696,19 +800,21 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(const MmaArgs
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         float z0, z1;
-                        unpack2(fadd2(acos_clamped2(g[q]), NPSI[q]), z0, z1);
+                        unpack2(acos_clamped_plus2(g[q], NPSI[q]), z0, z1);
                         E[2 * q] = max_nan(z0, 0.f);
                         E[2 * q + 1] = max_nan(z1, 0.f);
                     }
                     if (store) {
-                        float* out = a.scores + (int64_t)lab0 * a.N + img;
+                        // row j of the group lives j * 4N bytes further on: a 32 x 32 -> 64 bit multiply-add per store
+                        // (IMAD.WIDE.U32) instead of a carried 64-bit add chain
+                        char* out = reinterpret_cast<char*>(a.scores + (int64_t)lab0 * a.N + img);
                         if (g_count >= 16) {
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) out[(int64_t)j * a.N] = E[j];
+                            for (int j = 0; j < 16; ++j) *reinterpret_cast<float*>(out + (unsigned long long)row_bytes * (unsigned)j) = E[j];
                         } else {
 #pragma unroll
                             for (int j = 0; j < 16; ++j)
-                                if (j < g_count) out[(int64_t)j * a.N] = E[j];
+                                if (j < g_count) *reinterpret_cast<float*>(out + (unsigned long long)row_bytes * (unsigned)j) = E[j];
                         }
                     }
                     if (MODE == 2 && want_topk) {
@@ -766,6 +872,10 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(const MmaArgs
             if (alt) par_t ^= 1u;
             else if (++t == NA) { t = 0; par_t ^= 1u; }
         }
+#ifdef LEC_TC_TRACE
+        trace_acc[7] = clock64() - loop_t0;
+        if (tracer) for (int q = 4; q < 10; ++q) atomicAdd(&g_tc_trace[q], (unsigned long long)trace_acc[q]);
+#endif
     }
 
     tc_fence_before();
@@ -841,6 +951,7 @@ int score_mma_launch(const float* labels, int64_t L, const float* images, int64_
     if ((int64_t)tab.n * blob + L * 4 > workspace_bytes) return LEC_E_SIZE;
     if (reinterpret_cast<uintptr_t>(workspace) & 127) return LEC_E_ALIGN;
     if (topk_idx && (k < 1 || k > LEC_MAX_TOPK)) return LEC_E_K;
+    if (scores && N >= (1LL << 30)) return LEC_E_SIZE;   // the kernel keeps the row stride in bytes in 32 bits
     unsigned char* ws = static_cast<unsigned char*>(workspace);
     float* npsi = reinterpret_cast<float*>(ws + (size_t)tab.n * blob);   // blob sizes are multiples of 32 bytes
     score_mma_prep_kernel<<<tab.n, kMmaN, 0, st>>>(labels, D, Kp, forms, K, tab, ws, npsi);
@@ -881,8 +992,24 @@ int score_mma_launch(const float* labels, int64_t L, const float* images, int64_
     auto launch = [&](auto kern) -> int {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
+#ifdef LEC_TC_TRACE
+        static const bool trace_on = [] { const char* e = getenv("LEC_TC_TRACE"); return e == nullptr || atoi(e) != 0; }();
+        unsigned long long z[16] = {0};
+        if (trace_on) cudaMemcpyToSymbol(g_tc_trace, z, sizeof(z));
+#endif
         kern<<<(unsigned)grid, kMmaThreads, smem, st>>>(a);
         ++g_launches;
+#ifdef LEC_TC_TRACE
+        if (trace_on) {
+            cudaStreamSynchronize(st);
+            cudaMemcpyFromSymbol(z, g_tc_trace, sizeof(z));
+            const double ctas = (double)z[11], ch = (double)z[3], vis = (double)z[8];
+            fprintf(stderr, "tc trace mode %d forms %d: CTAs %.0f chunks/CTA %.1f | MMA warp per chunk: wait tiles %.0f, wait acc %.0f, issue %.0f"
+                            " | epilogue per visit: wait const %.0f, wait acc %.0f, tmem ld %.0f, issue->seen %.0f | loop per CTA-group %.0f,"
+                            " visits %.0f, prologue %.0f cycles\n", mode, forms, ctas, ch / ctas, z[0] / ch, z[1] / ch, z[2] / ch,
+                    z[4] / vis, z[5] / vis, z[6] / vis, z[9] / vis, z[7] / (2 * ctas), vis, z[10] / ctas);
+        }
+#endif
         return (int)cudaGetLastError();
     };
     if (forms == 3) {

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LEC_ABI_VERSION 13
+#define LEC_ABI_VERSION 14
 
 /* geometry of the energy */
 #define LEC_GEOM_EUC 0 /* EucConesLoss.E_operator, order_embeddings.py:954-969 = oe.py:721-739 (cos-space) */
@@ -373,7 +373,8 @@ int64_t lec_mt_randbelow(lec_mt19937* s, uint32_t n);
 int lec_sample_negatives(lec_mt19937* rng, const lec_sampler_graph* g, const int64_t* u, const int64_t* v,
                          int64_t B, int N, int64_t* neg_to, int64_t* neg_from);
 /* FAST mode, one kernel: same candidate sets, same uniform law, Philox4x32-10 keyed by `seed`, counter
- * (draw id = (i*N + p)*2 + side, stream_id); not the reference's stream.  `g` is a HOST struct holding DEVICE
+ * (i*N + p, stream_id): the block's low 64 bits make the row draw (draw id 2 (i*N + p)), its high 64 bits the column
+ * draw (draw id 2 (i*N + p) + 1); not the reference's stream.  `g` is a HOST struct holding DEVICE
  * pointers; u, v, neg_to, neg_from are device arrays of idx_bytes-wide indices; *status (device int, zeroed
  * by the caller) receives LEC_E_EMPTY / LEC_E_INDEX if any draw failed. */
 int lec_sample_negatives_philox(const lec_sampler_graph* g, const void* u, const void* v, int idx_bytes, int64_t B,
@@ -381,6 +382,31 @@ int lec_sample_negatives_philox(const lec_sampler_graph* g, const void* u, const
                                 void* stream);
 /* the fast mode's integer draw, on the host (for tests): uniform in [0, n) */
 int64_t lec_philox_below(uint64_t seed, uint64_t stream_id, uint64_t draw, uint64_t n);
+
+/* ---- an end-to-end training iteration from host memory ---------------------------------------------
+ * Around the loss, one iteration of the reference's train loop moves the batch's indices to the device and the scalar
+ * loss back (order_embeddings_h.py:752-775: `for index, data_item in enumerate(self.dataloaders[phase])` ...
+ * `loss.item()`; order_embeddings.py:619-635).  lec_host_pipe_submit enqueues all of it with ONE call:
+ *     copy stream  [wait until the kernels that last read dev_block are done] -> dev_block <- host_block (`bytes`)
+ *                  [-> sample != NULL: lec_sample_negatives_philox draws step->neg_to / neg_from from step->pos_from /
+ *                  pos_to on the device; it depends on no kernel of the step before, so it overlaps them] -> event
+ *     `stream`     wait for that event -> lec_cone_step(step) -> *loss_host <- *step->upd.loss_step
+ *                  [-> *err_host <- *step->xchg.error when world > 1] -> event
+ * and returns without waiting for the GPU.  The index pointers of `step` point into dev_block (the caller lays the
+ * block out: pos_from | pos_to | neg_to | neg_from, or just the positives in the sampled mode); host_block, loss_host and
+ * err_host are PINNED host memory.  `slot` in [0, depth) names the staging slot: its events order the reuse of dev_block,
+ * so the copy of step i+1 overlaps the kernels of step i.  A slot must be collected with lec_host_pipe_wait (blocks
+ * until its loss has landed) before it is submitted again (LEC_E_SIZE otherwise).  Not thread-safe per pipe. */
+typedef struct lec_host_pipe lec_host_pipe_t;
+typedef struct lec_host_sample {
+    const lec_sampler_graph* graph; uint64_t seed, stream_id; int* status /* device int, see lec_sample_negatives_philox */;
+} lec_host_sample_t;
+int lec_host_pipe_create(lec_host_pipe_t** out, int depth /* 1..16 */);
+void lec_host_pipe_destroy(lec_host_pipe_t* p);
+int lec_host_pipe_submit(lec_host_pipe_t* p, int slot, const lec_step_t* step, const lec_host_sample_t* sample,
+                         const void* host_block, int64_t bytes, void* dev_block, double* loss_host, int* err_host,
+                         void* stream);
+int lec_host_pipe_wait(lec_host_pipe_t* p, int slot);
 
 /* ---- evaluation bookkeeping -----------------------------------------------------------------------
  * lec_f1_sweep replaces EmbeddingMetrics.calculate_metrics, 'val' phase (order_embeddings.py:272-287 = oe.py:380-395:

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "_lib", "liblec_b200.so")
 GEOM = {"euc": 0, "hyp": 1, "oe": 2}
 ROWS_NONE, ROWS_EUC_SOFTCLIP, ROWS_HYP_SHELL, ROWS_HYP_TANH, ROWS_HYP_TANH_FEAT = 0, 1, 2, 3, 4
 PREC_F32, PREC_F64CORE = 0, 1
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 EXPORTS = (
     "lec_abi_version", "lec_error_string", "lec_launch_count", "lec_set_pdl", "lec_index_errors", "lec_rows_fwd", "lec_rows_bwd",
@@ -25,6 +25,7 @@ EXPORTS = (
     "lec_score_workspace_bytes", "lec_score_topk_tc", "lec_mt_seed", "lec_mt_uint32", "lec_mt_randbelow",
     "lec_sample_negatives", "lec_sample_negatives_philox", "lec_philox_below", "lec_f1_workspace_bytes", "lec_f1_sweep",
     "lec_classify_counts", "lec_caption_hinge",
+    "lec_host_pipe_create", "lec_host_pipe_destroy", "lec_host_pipe_submit", "lec_host_pipe_wait",
 )
 
 
@@ -71,6 +72,11 @@ class LecStep(ctypes.Structure):
         ("ev_pairs_start", ctypes.c_void_p), ("ev_pairs_stop", ctypes.c_void_p),
         ("upd", LecUpdate), ("xchg", LecExchange),
     ]
+
+
+class LecHostSample(ctypes.Structure):
+    """lec_host_sample_t of include/lec_b200.h."""
+    _fields_ = [("graph", ctypes.c_void_p), ("seed", ctypes.c_uint64), ("stream_id", ctypes.c_uint64), ("status", ctypes.c_void_p)]
 
 
 UPD_NONE, UPD_RSGD, UPD_SGD, UPD_ADAM = 0, 1, 2, 3
@@ -141,6 +147,12 @@ def lib():
         L.lec_f1_sweep.argtypes = [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp]
         L.lec_classify_counts.argtypes = [c_vp, c_vp, c_i64, c_i, c_i, c_vp, c_i, c_i64, c_vp, c_vp, c_vp, c_vp]
         L.lec_caption_hinge.argtypes = [c_vp, c_vp, c_i64, c_i, c_f, c_vp, c_vp, c_vp, c_vp, c_vp]
+        L.lec_host_pipe_create.argtypes = [ctypes.POINTER(c_vp), c_i]
+        L.lec_host_pipe_destroy.argtypes = [c_vp]
+        L.lec_host_pipe_destroy.restype = None
+        L.lec_host_pipe_submit.argtypes = [c_vp, c_i, ctypes.POINTER(LecStep), ctypes.POINTER(LecHostSample), c_vp, c_i64, c_vp,
+                                           c_vp, c_vp, c_vp]
+        L.lec_host_pipe_wait.argtypes = [c_vp, c_i]
         for name in EXPORTS:
             getattr(L, name)
         if L.lec_abi_version() != ABI_VERSION:

@@ -189,7 +189,7 @@ extern "C" int lec_sample_negatives(lec_mt19937* rng, const lec_sampler_graph* g
 }
 
 // ------------------------------------------------------------------------------------------------
-// fast mode: Philox4x32-10, one block per draw
+// fast mode: Philox4x32-10, one block per (i, p) slot (two draws)
 // ------------------------------------------------------------------------------------------------
 namespace {
 
@@ -212,16 +212,28 @@ __host__ __device__ inline void philox4x32_10(uint32_t c[4], uint32_t k0, uint32
     }
 }
 
-// uniform integer in [0, n): 64 random bits, multiply-high (bias < n / 2^64, i.e. none that a test can see)
-__host__ __device__ inline int64_t philox_below(uint64_t seed, uint64_t stream, uint64_t draw, uint64_t n) {
-    uint32_t c[4] = {(uint32_t)draw, (uint32_t)(draw >> 32), (uint32_t)stream, (uint32_t)(stream >> 32)};
-    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-    uint64_t x = ((uint64_t)c[1] << 32) | c[0];
+// 64 random bits -> uniform integer in [0, n) by multiply-high (bias < n / 2^64, i.e. none that a test can see)
+__host__ __device__ inline int64_t mulhi_below(uint64_t x, uint64_t n) {
 #ifdef __CUDA_ARCH__
     return (int64_t)__umul64hi(x, n);
 #else
     return (int64_t)(((unsigned __int128)x * n) >> 64);
 #endif
+}
+
+// Draw `draw` of stream `stream`: one Philox4x32-10 block (counter = draw / 2, stream) serves the two draws of an (i, p)
+// slot -- the row draw (even id) takes its low 64 bits, the column draw (odd id) its high 64 bits.
+__host__ __device__ inline void philox_pair(uint64_t seed, uint64_t stream, uint64_t pair_id, uint64_t& x_even, uint64_t& x_odd) {
+    uint32_t c[4] = {(uint32_t)pair_id, (uint32_t)(pair_id >> 32), (uint32_t)stream, (uint32_t)(stream >> 32)};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    x_even = ((uint64_t)c[1] << 32) | c[0];
+    x_odd = ((uint64_t)c[3] << 32) | c[2];
+}
+
+__host__ __device__ inline int64_t philox_below(uint64_t seed, uint64_t stream, uint64_t draw, uint64_t n) {
+    uint64_t xe, xo;
+    philox_pair(seed, stream, draw >> 1, xe, xo);
+    return mulhi_below((draw & 1) ? xo : xe, n);
 }
 
 struct PhiloxArgs {
@@ -233,25 +245,54 @@ struct PhiloxArgs {
     int* status;
 };
 
+// One side of an (i, p) slot, 32-bit arithmetic throughout (node ids and list lengths are < 2^31): the excluded ids of
+// `node` inside the draw window, then the r-th candidate.  Without per-level windows the whole list counts and the two
+// window searches disappear.
+struct SideDraw { const int32_t* ex; int m; int lo; int cnt; };
+
+__device__ __forceinline__ SideDraw side_setup(const lec_sampler_graph& g, const int64_t* __restrict__ ptr,
+                                               const int32_t* __restrict__ excl, int p, int64_t node) {
+    const int64_t e0 = __ldg(ptr + node), e1 = __ldg(ptr + node + 1);
+    SideDraw d;
+    if (!g.pick_per_level) {
+        d.ex = excl + e0; d.m = (int)(e1 - e0); d.lo = 0; d.cnt = (int)g.n_nodes - d.m;
+        return d;
+    }
+    const Window w = draw_window(&g, p, node);
+    const int64_t a = lower_bound_i32(excl, e0, e1, w.lo);
+    const int64_t b = lower_bound_i32(excl, a, e1, w.hi);
+    d.ex = excl + a; d.m = (int)(b - a); d.lo = (int)w.lo; d.cnt = (int)(w.hi - w.lo) - d.m;
+    return d;
+}
+
 template <typename I>
 __global__ void __launch_bounds__(256) sample_philox_kernel(PhiloxArgs a) {
-    const int64_t total = a.B * a.N * 2;
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        // draw id t = (i*N + p)*2 + side: the order the reference consumes its stream in
-        const int side = (int)(t & 1);
-        const int64_t ip = t >> 1;
+    const int64_t total = a.B * a.N;     // (i, p) slots; a thread makes the slot's row draw and its column draw
+    for (int64_t ip = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; ip < total; ip += (int64_t)gridDim.x * blockDim.x) {
         const int64_t i = ip / a.N;
         const int p = (int)(ip - i * a.N);
-        const int64_t node = side == 0 ? (int64_t)((const I*)a.u)[i] : (int64_t)((const I*)a.v)[i];
-        if (node < 0 || node >= a.g.n_nodes) { atomicExch(a.status, LEC_E_INDEX); continue; }
-        const int64_t* ptr = side == 0 ? a.g.row_excl_ptr : a.g.col_excl_ptr;
-        const int32_t* excl = side == 0 ? a.g.row_excl : a.g.col_excl;
-        Window w = draw_window(&a.g, p, node);
-        int64_t s, cnt = candidate_count(excl, ptr[node], ptr[node + 1], w, &s);
-        if (cnt <= 0) { atomicExch(a.status, LEC_E_EMPTY); continue; }
-        int64_t r = philox_below(a.seed, a.stream, (uint64_t)t, (uint64_t)cnt);
-        I x = (I)kth_candidate(excl, s, (w.hi - w.lo) - cnt, w.lo, r);
-        if (side == 0) ((I*)a.neg_to)[ip] = x; else ((I*)a.neg_from)[ip] = x;
+        const int64_t nu = (int64_t)((const I*)a.u)[i], nv = (int64_t)((const I*)a.v)[i];
+        if (nu < 0 || nu >= a.g.n_nodes || nv < 0 || nv >= a.g.n_nodes) { atomicExch(a.status, LEC_E_INDEX); continue; }
+        const SideDraw du = side_setup(a.g, a.g.row_excl_ptr, a.g.row_excl, p, nu);
+        const SideDraw dv = side_setup(a.g, a.g.col_excl_ptr, a.g.col_excl, p, nv);
+        if (du.cnt <= 0 || dv.cnt <= 0) { atomicExch(a.status, LEC_E_EMPTY); continue; }
+        uint64_t xe, xo;
+        philox_pair(a.seed, a.stream, (uint64_t)ip, xe, xo);   // draw ids 2 ip (row) and 2 ip + 1 (column)
+        const int ru = (int)mulhi_below(xe, (uint64_t)du.cnt), rv = (int)mulhi_below(xo, (uint64_t)dv.cnt);
+        // r-th candidate = lo + r + j, j = the smallest index with j == m or ex[j] - lo - j > r.  The two searches run in
+        // lock step (independent loads in flight together), branch-free halving.
+        int bu = 0, lu = du.m, bv = 0, lv = dv.m;
+        while ((lu | lv) > 0) {
+            const int hu = lu >> 1, hv = lv >> 1;
+            const int mu = bu + hu, mv = bv + hv;
+            const int eu = lu > 0 ? __ldg(du.ex + mu) : 0, ev = lv > 0 ? __ldg(dv.ex + mv) : 0;
+            const bool right_u = lu > 0 && !(eu - du.lo - mu > ru);   // keep searching above mid
+            const bool right_v = lv > 0 && !(ev - dv.lo - mv > rv);
+            bu = right_u ? mu + 1 : bu;  lu = right_u ? lu - hu - 1 : hu;
+            bv = right_v ? mv + 1 : bv;  lv = right_v ? lv - hv - 1 : hv;
+        }
+        ((I*)a.neg_to)[ip] = (I)(du.lo + ru + bu);
+        ((I*)a.neg_from)[ip] = (I)(dv.lo + rv + bv);
     }
 }
 
@@ -271,7 +312,7 @@ extern "C" int lec_sample_negatives_philox(const lec_sampler_graph* g_dev, const
     if (g_dev->pick_per_level && (g_dev->n_levels < 1 || g_dev->n_levels > LEC_MAX_LEVELS || g_dev->level_mod < 1))
         return LEC_E_ENUM;
     if (idx_bytes == 2 && g_dev->n_nodes > 65536) return LEC_E_ENUM;
-    const int64_t total = B * N * 2;
+    const int64_t total = B * N;   // one thread per (i, p) slot: its row draw and its column draw
     if (total == 0) return 0;
     PhiloxArgs a{*g_dev, u, v, neg_to, neg_from, B, N, idx_bytes, seed, stream_id, status};
     int64_t blocks = (total + 255) / 256;

@@ -107,6 +107,7 @@ class ConeStep:
                                for _ in range(self.depth)]
         self.loss_host = torch.zeros(self.depth, dtype=torch.float64).pin_memory()
         self.err_host = torch.zeros(self.depth, dtype=torch.int32).pin_memory()
+        self._pipe, self._sample_struct, self._sample_graph = None, None, None
         self._copy_stream = None
         self._ev = None          # per slot: (indices copied, kernels done with the slot, loss read back)
         self._inflight = [False] * self.depth
@@ -250,15 +251,9 @@ class ConeStep:
         return out
 
     # -- whole steps ----------------------------------------------------------------------------
-    def step_device(self, pos_from, pos_to, neg_to, neg_from, w_pos=None, w_neg=None):
-        """Indices already on the device (uint16 / int32 / int64).  Returns this rank's device loss (float64[1])."""
-        if self.comm == "nccl":
-            self.forward_backward(pos_from, pos_to, neg_to, neg_from, w_pos, w_neg)
-            self.reduce_and_update()
-            return self.loss
-        # the whole step as ONE call into the library (lec_cone_step): one FFI crossing, two launches
-        import ctypes
-        B = int(pos_from.numel())
+    def _fill_step(self, p_from, p_to, n_to, n_from, idx_bytes, B, w_pos=None, w_neg=None):
+        """lec_step_t of the next step (pointers as integers).  One cached ctypes struct: pointers and shapes of this
+        engine are written once, the per-step fields every time (lr / alpha / K may change between steps)."""
         if B > self.max_groups:
             raise N.LecError("batch of %d positives exceeds max_groups=%d" % (B, self.max_groups))
         s = self._struct
@@ -271,9 +266,8 @@ class ConeStep:
                 self.px.fill(s.xchg)
         s.geom, s.precision, s.alpha = N.GEOM[self.geom], self.precision, self.alpha
         s.fused = 1 if (self.fused and self._rows_valid) else 0
-        s.pos_from, s.pos_to = pos_from.data_ptr(), pos_to.data_ptr()
-        s.neg_to, s.neg_from = neg_to.data_ptr(), neg_from.data_ptr()
-        s.idx_bytes, s.B = pos_from.element_size(), B
+        s.pos_from, s.pos_to, s.neg_to, s.neg_from = p_from, p_to, n_to, n_from
+        s.idx_bytes, s.B = idx_bytes, B
         s.w_pos = w_pos.data_ptr() if w_pos is not None else None
         s.w_neg = w_neg.data_ptr() if w_neg is not None else None
         self._fill_update(self._upd)
@@ -287,6 +281,18 @@ class ConeStep:
             s.ev_pairs_start, s.ev_pairs_stop = ev[0].cuda_event, ev[1].cuda_event
         else:
             s.ev_pairs_start, s.ev_pairs_stop = None, None
+        return s
+
+    def step_device(self, pos_from, pos_to, neg_to, neg_from, w_pos=None, w_neg=None):
+        """Indices already on the device (uint16 / int32 / int64).  Returns this rank's device loss (float64[1])."""
+        if self.comm == "nccl":
+            self.forward_backward(pos_from, pos_to, neg_to, neg_from, w_pos, w_neg)
+            self.reduce_and_update()
+            return self.loss
+        # the whole step as ONE call into the library (lec_cone_step): one FFI crossing, two launches
+        import ctypes
+        s = self._fill_step(pos_from.data_ptr(), pos_to.data_ptr(), neg_to.data_ptr(), neg_from.data_ptr(),
+                            pos_from.element_size(), int(pos_from.numel()), w_pos, w_neg)
         N.check(N.lib().lec_cone_step(ctypes.byref(s), N.stream_ptr(self.table.device)), "lec_cone_step")
         self._after_step()
         return self.loss
@@ -328,11 +334,90 @@ class ConeStep:
             raise N.LecError("peer exchange timed out: a rank did not deliver its gradient; the table replicas are no "
                              "longer in step -- restart from a checkpoint")
 
+    # -- end-to-end iterations through the library's host pipe (lec_host_pipe_*) ---------------------------------
+    def _pipe_slot(self):
+        """The staging slot of the next submission, collected if a step is still in flight on it (blocks on that
+        step's loss, i.e. on step i - depth)."""
+        import ctypes
+        lib = N.lib()
+        if self._pipe is None:
+            h = ctypes.c_void_p()
+            N.check(lib.lec_host_pipe_create(ctypes.byref(h), self.depth), "lec_host_pipe_create")
+            self._pipe = h
+            self._slot_ptr = [b.data_ptr() for b in self._idx_bytes_dev]
+            self._loss_np, self._err_np = self.loss_host.numpy(), self.err_host.numpy()
+            self._loss_ptr = [self.loss_host.data_ptr() + 8 * i for i in range(self.depth)]
+            self._err_ptr = [self.err_host.data_ptr() + 4 * i for i in range(self.depth)]
+        slot = self._submitted % self.depth
+        if self._inflight[slot]:
+            self._collect_slot(slot)
+        return slot
+
+    def _collect_slot(self, slot):
+        N.check(N.lib().lec_host_pipe_wait(self._pipe, slot), "lec_host_pipe_wait")
+        self._inflight[slot] = False
+        self._raise_on(slot)
+        self._losses.append(float(self._loss_np[slot]))
+
+    def _pipe_submit(self, slot, s, sample, host_block, nbytes):
+        import ctypes
+        N.check(N.lib().lec_host_pipe_submit(self._pipe, slot, ctypes.byref(s), sample, host_block.data_ptr(), nbytes,
+                                             self._slot_ptr[slot], self._loss_ptr[slot],
+                                             self._err_ptr[slot] if self.px is not None else None,
+                                             N.stream_ptr(self.table.device)), "lec_host_pipe_submit")
+        self._after_step()
+        self._inflight[slot] = True
+        self._submitted += 1
+
     def submit_host(self, index_block, B):
-        """Pipelined end-to-end step: the index block goes host->device on a side stream into one of `depth`
-        staging slots while the previous step's kernels run; the step is enqueued behind its copy; its loss
-        comes back device->host asynchronously.  Blocks only when the slot it needs is still in flight
-        (i.e. on the loss of step i - depth).  Losses are returned, in order, by drain()."""
+        """Pipelined end-to-end step: ONE library call (lec_host_pipe_submit) copies the pinned index block
+        host->device on a side stream into one of `depth` staging slots while the previous step's kernels run,
+        enqueues the step behind the copy and the read-back of its loss behind the step.  Blocks only when the slot it
+        needs is still in flight (i.e. on the loss of step i - depth).  Losses are returned, in order, by drain()."""
+        if self.comm == "nccl":
+            return self._submit_host_torch(index_block, B)
+        slot = self._pipe_slot()
+        ib, Nn, base = index_block.element_size(), self.n_neg, self._slot_ptr[slot]
+        s = self._fill_step(base, base + B * ib, base + 2 * B * ib, base + (2 + Nn) * B * ib, ib, B)
+        self._pipe_submit(slot, s, None, index_block, B * (2 + 2 * Nn) * ib)
+
+    def submit_host_sampled(self, graph, pos_block, B, seed):
+        """Pipelined end-to-end step in the device-sampled mode: only the step's POSITIVE edges travel host->device
+        (pos_block = pinned [pos_from | pos_to], uint16 / int32: 4 B bytes instead of 4 B (1 + N)); the negatives are
+        drawn on the GPU by the library's Philox sampler (the reference's candidate sets and uniform law, not its
+        random.choice stream) right before the step, in the same stream and the same library call.  Losses come back
+        through drain()."""
+        if self.comm == "nccl":
+            return self._submit_host_sampled_torch(graph, pos_block, B, seed)
+        import ctypes
+        slot = self._pipe_slot()
+        ib, Nn, base = pos_block.element_size(), self.n_neg, self._slot_ptr[slot]
+        s = self._fill_step(base, base + B * ib, base + 2 * B * ib, base + (2 + Nn) * B * ib, ib, B)
+        smp = self._sample_struct
+        if smp is None or self._sample_graph is not graph:
+            g, keep, status = graph.device_struct(self.table.device)
+            smp = self._sample_struct = N.LecHostSample()
+            self._sample_graph, self._sample_keep = graph, (g, keep, status)
+            smp.graph, smp.status = ctypes.addressof(g), status.data_ptr()
+        smp.seed, smp.stream_id = int(seed), self._submitted
+        self._pipe_submit(slot, s, ctypes.byref(smp), pos_block, 2 * B * ib)
+
+    def close(self):
+        """Releases the host pipe (its stream and events).  Called by __del__; safe to call twice."""
+        if getattr(self, "_pipe", None) is not None:
+            self._collect()
+            N.lib().lec_host_pipe_destroy(self._pipe)
+            self._pipe = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001 -- interpreter shutdown
+            pass
+
+    # the NCCL exchange is a torch.distributed call between the two halves of a step, so that path keeps the host side
+    # in Python (stream switch, copy, events)
+    def _submit_host_torch(self, index_block, B):
         dev = self.table.device
         main = torch.cuda.current_stream(dev)
         if self._copy_stream is None:
@@ -355,17 +440,11 @@ class ConeStep:
         self.step_device(*self._split(dst, B))
         ev_free.record(main)
         self.loss_host[slot:slot + 1].copy_(self.loss, non_blocking=True)
-        if self.px is not None:
-            self.err_host[slot:slot + 1].copy_(self.px.error, non_blocking=True)
         ev_loss.record(main)
         self._inflight[slot] = True
         self._submitted += 1
 
-    def submit_host_sampled(self, graph, pos_block, B, seed):
-        """Pipelined end-to-end step in the device-sampled mode: only the step's POSITIVE edges travel host->device
-        (pos_block = pinned [pos_from | pos_to], uint16 / int32: 4 B bytes instead of 4 B (1 + N)); the negatives are
-        drawn on the GPU by the library's Philox sampler (the reference's candidate sets and uniform law, not its
-        random.choice stream) right before the step, in the same stream.  Losses come back through drain()."""
+    def _submit_host_sampled_torch(self, graph, pos_block, B, seed):
         dev = self.table.device
         main = torch.cuda.current_stream(dev)
         if self._copy_stream is None:
@@ -387,8 +466,6 @@ class ConeStep:
         self.step_sampled(graph, dst[:B], dst[B:2 * B], seed, self._submitted)
         ev_free.record(main)
         self.loss_host[slot:slot + 1].copy_(self.loss, non_blocking=True)
-        if self.px is not None:
-            self.err_host[slot:slot + 1].copy_(self.px.error, non_blocking=True)
         ev_loss.record(main)
         self._inflight[slot] = True
         self._submitted += 1
@@ -400,14 +477,17 @@ class ConeStep:
         return out
 
     def _collect(self):
-        if self._ev is not None:
-            for k in range(self.depth):
-                slot = (self._submitted + k) % self.depth  # oldest first
-                if self._inflight[slot]:
-                    self._ev[slot][2].synchronize()
-                    self._raise_on(slot)
-                    self._losses.append(float(self.loss_host[slot]))
-                    self._inflight[slot] = False
+        for k in range(self.depth):
+            slot = (self._submitted + k) % self.depth  # oldest first
+            if not self._inflight[slot]:
+                continue
+            if self._pipe is not None:
+                self._collect_slot(slot)
+            elif self._ev is not None:
+                self._ev[slot][2].synchronize()
+                self._raise_on(slot)
+                self._losses.append(float(self.loss_host[slot]))
+                self._inflight[slot] = False
 
 
 class JointConeStep:

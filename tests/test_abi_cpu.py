@@ -23,7 +23,7 @@ def test_library_exports_every_header_symbol():
     for n in names:
         assert hasattr(lib, n), n
     assert sorted(_native.EXPORTS) == names
-    assert lib.lec_abi_version() == _native.ABI_VERSION == 13
+    assert lib.lec_abi_version() == _native.ABI_VERSION == 14
 
 
 def test_argument_validation_codes():
@@ -115,6 +115,13 @@ def test_argument_validation_codes():
     assert lib.lec_caption_hinge(fake, fake, -1, 3, 1.0, null, fake, null, null, null) == -4
     assert lib.lec_caption_hinge(null, null, 0, 3, 1.0, null, null, null, null, null) == 0
     assert b"16-byte" in lib.lec_error_string(-5)
+    # host pipe (ABI 14): argument errors are reported before any CUDA call
+    h = ctypes.c_void_p()
+    assert lib.lec_host_pipe_create(None, 2) == -1
+    assert lib.lec_host_pipe_create(ctypes.byref(h), 0) == -4 and lib.lec_host_pipe_create(ctypes.byref(h), 17) == -4
+    assert lib.lec_host_pipe_submit(None, 0, ctypes.byref(step), None, fake, 8, fake, fake, null, null) == -1
+    assert lib.lec_host_pipe_wait(None, 0) == -1
+    lib.lec_host_pipe_destroy(None)
 
 
 def test_ops_refuse_cpu_tensors():

@@ -109,3 +109,39 @@ def test_engine_step_with_device_sampler_equals_step_on_the_same_negatives():
     assert torch.allclose(a.table, b.table, rtol=0, atol=1e-5)
     status = graph.device_struct(dev)[2]
     assert int(status.item()) == 0
+
+
+def test_host_pipe_sampled_submissions_equal_step_sampled():
+    """ConeStep.submit_host_sampled (one lec_host_pipe_submit per step: copy of the positives, Philox draw, step, loss
+    read-back, slots rotating) = the same steps issued one by one through step_sampled on device-resident positives."""
+    from learning_embeddings_b200.engine import ConeStep
+    from learning_embeddings_b200.criterion import inner_radius
+    h = H.ethec()
+    graph = S.SamplerGraph.from_hierarchy(h)
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(1)
+    w = torch.randn(h.n, 10, generator=g)
+    table0 = (inner_radius(0.1) + 0.05 * torch.rand(h.n, 1, generator=g)) * w / w.norm(dim=1, keepdim=True)
+    e = h.closure_edges()
+    B = len(e)
+    rng = np.random.default_rng(0)
+    blocks = []
+    for _ in range(5):   # more steps than staging slots: every slot is reused
+        perm = rng.permutation(B)
+        blk = torch.from_numpy(np.concatenate([e[perm, 0], e[perm, 1]]).astype(np.uint16)).pin_memory()
+        blocks.append(blk)
+    a = ConeStep(table0.to(dev).clone(), "hyp", 5, B, K=0.1, alpha=0.05, lr=1e-3)
+    b = ConeStep(table0.to(dev).clone(), "hyp", 5, B, K=0.1, alpha=0.05, lr=1e-3)
+    for blk in blocks:
+        a.submit_host_sampled(graph, blk, B, 42)
+    la = a.drain()
+    lb = []
+    for step, blk in enumerate(blocks):
+        d = blk.to(dev)
+        lb.append(float(b.step_sampled(graph, d[:B], d[B:], seed=42, step=step).item()))
+    assert len(la) == 5 and a.drain() == []
+    np.testing.assert_allclose(la, lb, rtol=1e-6)
+    assert torch.allclose(a.table, b.table, rtol=0, atol=1e-5)
+    assert int(graph.device_struct(dev)[2].item()) == 0
+    a.close()
+    a.close()

@@ -79,6 +79,16 @@ class Ctx:
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
+    def align_streams(self):
+        """Device-side rendezvous enqueued right before a timed region's start event: the ranks' host threads leave
+        barrier() tens of microseconds apart, and with a 1.3 ms region that skew would be charged to the first step.  A
+        one-element all-reduce completes on every GPU at (nearly) the same moment, so the streams start the region
+        together; the host has the region's launches queued behind it."""
+        if self.world > 1:
+            if getattr(self, "_tok", None) is None:
+                self._tok = torch.zeros(1, device=self.dev)
+            torch.distributed.all_reduce(self._tok)
+
     def max_ranks(self, ms):
         if self.world > 1:
             tt = torch.tensor([ms], device=self.dev, dtype=torch.float64)
@@ -312,6 +322,8 @@ def run_label(args, ctx, wl, steps, warmup, headline=False):
     rotation = args.rotation or max(4, int(np.ceil(160e6 / bytes_per_batch)))
     cfg["l2_policy"] = "inputs rotate through %d distinct batches (%.0f MB > 126 MB L2)" % (
         rotation, rotation * bytes_per_batch / 1e6)
+    if ctx.world > 1:
+        cfg["start_alignment"] = "device-side rendezvous (one-element all-reduce) enqueued right before the start event"
     host_batches = make_batches(h, spec, groups, rotation, seed=100 + (0 if os.environ.get("LEC_BENCH_SAME_BATCHES") else rank))
     dev_batches = [b.to(dev) for b in host_batches]
     table = table0.to(dev).clone()
@@ -334,7 +346,9 @@ def run_label(args, ctx, wl, steps, warmup, headline=False):
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.active.set()
+    ctx.align_streams()   # warm the collective up before the bracket
     ctx.sync_all()
+    ctx.align_streams()
     t0.record()
     for i in range(steps):
         # the pair kernel is bracketed by CUDA events on every 4th step only: two event records per step sit between
@@ -360,6 +374,7 @@ def run_label(args, ctx, wl, steps, warmup, headline=False):
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ctx.sync_all()
         sampler.active.set()
+        ctx.align_streams()
         s0.record()
         for i in range(n_sus):
             dev_step(i)
@@ -666,6 +681,8 @@ def run_cfg2(args, ctx, steps, warmup):
     dev_batches = [(s_.to(dev), b_.to(dev)) for s_, b_ in batches]
     cfg["l2_policy"] = "every step gathers %d of %d feature rows (%.0f MB read twice, > 126 MB L2); %d index batches rotate" % (
         m, c["pool"], m * c["F"] * 4 / 1e6, rotation)
+    if ctx.world > 1:
+        cfg["start_alignment"] = "device-side rendezvous (one-element all-reduce) enqueued right before the start event"
     table, fw, fb = table0.to(dev).clone(), fw0.to(dev).clone(), fb0.to(dev).clone()
     eng = JointConeStep(table, fw, fb, feats, c["geom"], Nn, B, m, K=c["K"], alpha=c["alpha"], lr=c["lr_labels"],
                         lr_fc=c["lr"], precision=0, process_group=ctx.pg)
@@ -685,7 +702,9 @@ def run_cfg2(args, ctx, steps, warmup):
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.active.set()
+    ctx.align_streams()
     ctx.sync_all()
+    ctx.align_streams()
     t0.record()
     for i in range(steps):
         eng.kernel_events = kev[i] if i % 4 == 0 else None

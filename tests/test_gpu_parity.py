@@ -624,6 +624,44 @@ def test_engine_step_matches_oracle(name, geom, mode):
     np.testing.assert_allclose(t2.cpu().numpy(), table.cpu().numpy(), rtol=1e-5, atol=1e-7)
 
 
+def test_engine_step_at_wordnet_scale_matches_fp64_oracle():
+    """BASELINE config 5 shape: 82 115 rows x 50 (17 MB table, int32 indices, ONE gradient replica, groups split over
+    several teams because 2 569 positives cannot fill the GPU), 50 negatives per edge.  One fused step against the fp64
+    oracle: pointwise energy contract, loss, and every row of the updated table (touched or not: the reference's RSGD
+    moves all rows)."""
+    from learning_embeddings_b200.engine import ConeStep, pack_index_block
+    gen = torch.Generator().manual_seed(82115)
+    n, D, B, Nn, K, alpha, lr = 82115, 50, 2569, 25, 0.1, 0.05, 0.01
+    r_in = cones.inner_radius(K)
+    d = torch.randn(n, D, generator=gen)
+    W0 = d / d.norm(dim=1, keepdim=True) * (r_in + 0.02 + 0.7 * torch.rand(n, 1, generator=gen))
+    u = torch.randint(0, n, (B,), generator=gen)
+    v = (u + 1 + torch.randint(0, n - 1, (B,), generator=gen)) % n
+    neg_to = torch.randint(0, n, (B, Nn), generator=gen)
+    neg_from = torch.randint(0, n, (B, Nn), generator=gen)
+    neg_to = torch.where(neg_to == u[:, None], (neg_to + 1) % n, neg_to)
+    neg_from = torch.where(neg_from == v[:, None], (neg_from + 1) % n, neg_from)
+    # a few hub rows shared by many groups: same-address reductions into the single replica
+    u[:200] = u[0]
+    neg_to = torch.where(neg_to == u[:, None], (neg_to + 1) % n, neg_to)
+    nf = torch.cat([u[:, None].expand(B, Nn), neg_from], 1).reshape(-1)
+    nt = torch.cat([neg_to, v[:, None].expand(B, Nn)], 1).reshape(-1)
+    r64 = cones.label_step("hyp", W0.double(), cones.ROW_HYP_SHELL, K, alpha, u, v, nf, nt)
+    r32 = cones.label_step("hyp", W0, cones.ROW_HYP_SHELL, K, alpha, u, v, nf, nt)
+    table = W0.to(DEV).clone()
+    eng = ConeStep(table, "hyp", Nn, B, K=K, alpha=alpha, lr=lr)
+    assert eng.replicas == 1
+    blk = pack_index_block(u.numpy(), v.numpy(), neg_to.numpy(), neg_from.numpy(), n_rows=n)
+    assert blk.dtype == torch.int32
+    loss = eng.step_host(blk, B)
+    assert abs(loss - float(r64["loss"])) <= 1e-5 * abs(float(r64["loss"]))
+    contract(eng.E_pos.cpu().numpy(), r64["E_pos"].numpy(), r32["E_pos"].numpy(), "E_pos at 82K x 50")
+    contract(eng.E_neg.reshape(-1).cpu().numpy(), r64["E_neg"].numpy(), r32["E_neg"].numpy(), "E_neg at 82K x 50")
+    _, W_ref = cones.rsgd_step(W0.double(), r64["gW"], lr, r_in)
+    np.testing.assert_allclose(table.cpu().numpy(), W_ref.numpy(), rtol=2e-5, atol=2e-7)
+    assert N.index_errors(torch.device(DEV)) == 0
+
+
 @pytest.mark.parametrize("D", (2, 10, 50))
 def test_fused_update_and_row_transform_equals_separate_launches(D):
     """lec_cone_step with fused = 1 (pairs -> lec_update_rows: update + the next step's Embedder.forward in one launch)

@@ -32,3 +32,6 @@ done
 if [ "${ONE:-1}" = "1" ]; then
   timeout 200 python bench.py --workload cfg1 --steps 200 --warmup 20 --no-cpu-baseline --no-e2e | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('N=1 same box', d['value']/1e9, 'Gpairs/s', d['ms_per_step']*1000, 'us/step; sustained', d['sustained']['ms_per_step']*1000)"
 fi
+if [ "${XCHG:-0}" = "1" ]; then
+  timeout 300 $TR scripts/xchg_latency.py > $O/xchg_latency_${N}gpu.log 2>&1; grep "^world" $O/xchg_latency_${N}gpu.log
+fi

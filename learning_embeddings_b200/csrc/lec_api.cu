@@ -178,6 +178,7 @@ int lec_pairs_grouped(int geom, int precision, const float* rows, const double* 
     if (aux && (reinterpret_cast<uintptr_t>(aux) & 15)) return LEC_E_ALIGN;
     GroupArgs a{rows, aux, ld, pos_from, pos_to, neg_to, neg_from, idx_bytes, B, N, w_pos, w_neg, K, alpha,
                 E_pos, E_neg, loss_out, grad_rows, grad_replicas, n_rows * (int64_t)ld, n_rows, index_errors_ptr(), 0};
+    a.narrow_tail = (D - (ld / 4 - 1) * 4) <= 2 ? 1 : 0;
     cudaStream_t st = (cudaStream_t)stream;
     switch (core) {
         case CORE_EUC32: return launch_grouped_euc32(a, st);

@@ -19,6 +19,10 @@ template <> struct CoreTraits<CORE_HYP32> { using Acc = float;  static constexpr
 template <> struct CoreTraits<CORE_HYP64> { using Acc = double; static constexpr bool cone = true,  hyp = true;  static constexpr int geom = LEC_GEOM_HYP; };
 template <> struct CoreTraits<CORE_OE32>  { using Acc = float;  static constexpr bool cone = false, hyp = false; static constexpr int geom = LEC_GEOM_OE; };
 
+#ifndef LEC_FP32_MINBLOCKS
+#define LEC_FP32_MINBLOCKS 3
+#endif
+
 struct FlatArgs {
     const float* rows; const double* aux; int ld;
     const void* from_idx; const void* to_idx; int idx_bytes;
@@ -39,7 +43,16 @@ struct GroupArgs {
     int pdl_late;  // 1: let the dependent launch in only when this block has finished its groups (LEC_PDL_LATE)
     int split;  // teams per group (>= 1): team s of a group takes negatives p = s, s + split, ... of both lists
     int64_t stage_floats;  // > 0: every block first copies the transformed table (n * ld floats) into shared memory
+    int narrow_tail;       // the last float4 chunk of a row holds <= 2 live floats (D % 4 in {1, 2}): its reductions are 64-bit
 };
+
+// Gradient reduction of chunk q of a row.  The L2 executes a vector reduction as one fp32 add per element and its add
+// rate is what bounds the Euclidean kernels (cfg0, D = 2: 2.3 M REDG.128 per step = 340 G adds/s on a 92 KB target), so
+// a chunk whose upper half is padding (D = 2: every chunk; D = 10, 50: the last of 3 / 13) goes out as REDG.64.
+__device__ __forceinline__ void red_add_chunk(float* p, float4 v, bool narrow) {
+    if (narrow) atomicAdd(reinterpret_cast<float2*>(p), make_float2(v.x, v.y));
+    else red_add4(p, v);
+}
 
 struct DenseArgs {
     const float* x; const float* y; const float* gE;
@@ -194,6 +207,7 @@ __global__ void __launch_bounds__(kThreads, MB) pairs_grouped_kernel(const Group
     const int64_t iters = (n_items + n_teams - 1) / n_teams;
     const int Q = a.ld >> 2;
     const int N = a.N;
+    const int q_narrow = a.narrow_tail ? Q - 1 : -1;   // chunk whose reductions are 64 bits wide
     float* const grad_base = GRAD ? a.grad_rows + (int64_t)(blockIdx.x % a.grad_replicas) * a.replica_stride : nullptr;
     double loss = 0.0;
     for (int64_t it = 0; it < iters; ++it) {
@@ -280,10 +294,10 @@ __global__ void __launch_bounds__(kThreads, MB) pairs_grouped_kernel(const Group
                         const float4 r = relu_diff4(U.c[j], C.c[j]);
                         const float c2 = 2.f * cf;
                         fma4(accU.c[j], c2, r);
-                        if (q < Q) red_add4(gcp + 4 * q, make_float4(-c2 * r.x, -c2 * r.y, -c2 * r.z, -c2 * r.w));
+                        if (q < Q) red_add_chunk(gcp + 4 * q, make_float4(-c2 * r.x, -c2 * r.y, -c2 * r.z, -c2 * r.w), q == q_narrow);
                     } else {
                         fma4(accU.c[j], cf * g.zxy, C.c[j]);
-                        if (q < Q) red_add4(gcp + 4 * q, axpby4(cf * g.zyx, U.c[j], cf * g.zyy, C.c[j]));
+                        if (q < Q) red_add_chunk(gcp + 4 * q, axpby4(cf * g.zyx, U.c[j], cf * g.zyy, C.c[j]), q == q_narrow);
                     }
                 }
             }
@@ -316,10 +330,10 @@ __global__ void __launch_bounds__(kThreads, MB) pairs_grouped_kernel(const Group
                         const float4 r = relu_diff4(C.c[j], W.c[j]);
                         const float c2 = 2.f * cf;
                         fma4(accW.c[j], -c2, r);
-                        if (q < Q) red_add4(gcp + 4 * q, make_float4(c2 * r.x, c2 * r.y, c2 * r.z, c2 * r.w));
+                        if (q < Q) red_add_chunk(gcp + 4 * q, make_float4(c2 * r.x, c2 * r.y, c2 * r.z, c2 * r.w), q == q_narrow);
                     } else {
                         fma4(accW.c[j], cf * g.zyx, C.c[j]);
-                        if (q < Q) red_add4(gcp + 4 * q, axpby4(cf * g.zxx, C.c[j], cf * g.zxy, W.c[j]));
+                        if (q < Q) red_add_chunk(gcp + 4 * q, axpby4(cf * g.zxx, C.c[j], cf * g.zxy, W.c[j]), q == q_narrow);
                     }
                 }
             }
@@ -335,12 +349,12 @@ __global__ void __launch_bounds__(kThreads, MB) pairs_grouped_kernel(const Group
                     if (touch_u) {
                         float4 v = accU.c[j];
                         if (Tr::cone) { fma4(v, su_u, U.c[j]); fma4(v, su_w, W.c[j]); }
-                        red_add4(gu + 4 * q, v);
+                        red_add_chunk(gu + 4 * q, v, q == q_narrow);
                     }
                     if (touch_w) {
                         float4 v = accW.c[j];
                         if (Tr::cone) { fma4(v, sw_u, U.c[j]); fma4(v, sw_w, W.c[j]); }
-                        red_add4(gw + 4 * q, v);
+                        red_add_chunk(gw + 4 * q, v, q == q_narrow);
                     }
                 }
             }
@@ -445,9 +459,13 @@ int launch_grouped_tv(const GroupArgs& a0, cudaStream_t st) {
         return b;
     }();
     static const int mb = [] { const char* e = getenv("LEC_GROUP_MINBLOCKS"); return (e ? atoi(e) : LEC_GROUPED_MINBLOCKS) >= 2 ? 2 : 1; }();
+    // register cap of the default build: 128 (two resident 256-thread blocks); 80 for the fp32 cores with one float4 per
+    // row (D <= 4: cfg0), which fit without spilling and are gather-latency-bound -- r2x sweep on cfg0: cap 128 / 80 / 64
+    // -> pair kernel 29.8 / 26.8 / 29.2 us; rows of three chunks (D = 10) spill at 80 and lose (18.0 -> 23.1 us).
+    constexpr int MBX = (CORE != CORE_HYP64 && V == 1) ? LEC_FP32_MINBLOCKS : 2;
     static const int resident_blocks = [] {
         int nb = 0;
-        if (mb == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pairs_grouped_kernel<CORE, T, V, true, 2>, block, 0);
+        if (mb == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pairs_grouped_kernel<CORE, T, V, true, MBX>, block, 0);
         else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pairs_grouped_kernel<CORE, T, V, true, 1>, block, 0);
         return nb > 0 ? nb : 1;
     }();
@@ -465,8 +483,8 @@ int launch_grouped_tv(const GroupArgs& a0, cudaStream_t st) {
     const size_t smem = stage ? (size_t)table_floats * 4 : 0;
     cudaError_t le;
     if (mb == 2) {
-        if (a.grad_rows) le = launch_step_kernel(pairs_grouped_kernel<CORE, T, V, true, 2>, grid, block, st, a, smem);
-        else le = launch_step_kernel(pairs_grouped_kernel<CORE, T, V, false, 2>, grid, block, st, a, smem);
+        if (a.grad_rows) le = launch_step_kernel(pairs_grouped_kernel<CORE, T, V, true, MBX>, grid, block, st, a, smem);
+        else le = launch_step_kernel(pairs_grouped_kernel<CORE, T, V, false, MBX>, grid, block, st, a, smem);
     } else {
         if (a.grad_rows) le = launch_step_kernel(pairs_grouped_kernel<CORE, T, V, true, 1>, grid, block, st, a, smem);
         else le = launch_step_kernel(pairs_grouped_kernel<CORE, T, V, false, 1>, grid, block, st, a, smem);

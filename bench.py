@@ -89,6 +89,13 @@ class Ctx:
                 self._tok = torch.zeros(1, device=self.dev)
             torch.distributed.all_reduce(self._tok)
 
+    def prequeue(self):
+        """~0.5 ms spin kernel in front of a timed region's start event: by the time the GPU reaches the event the host has
+        the region's launches queued, so a 20-step (1.3 ms) region times the device back to back and not the host's
+        launch jitter -- with 8 lock-stepped ranks ANY rank's hiccup in an empty launch queue stalls all of them (r2u8:
+        20 steps 80.9 us/step, 200 steps 75.4, one second sustained 71.8).  The host side is what `e2e` measures."""
+        torch.cuda._sleep(1_000_000)
+
     def max_ranks(self, ms):
         if self.world > 1:
             tt = torch.tensor([ms], device=self.dev, dtype=torch.float64)
@@ -324,6 +331,7 @@ def run_label(args, ctx, wl, steps, warmup, headline=False):
         rotation, rotation * bytes_per_batch / 1e6)
     if ctx.world > 1:
         cfg["start_alignment"] = "device-side rendezvous (one-element all-reduce) enqueued right before the start event"
+    cfg["launch_queue"] = "a ~0.5 ms spin kernel precedes the start event, so the timed launches are queued before the GPU reaches them"
     host_batches = make_batches(h, spec, groups, rotation, seed=100 + (0 if os.environ.get("LEC_BENCH_SAME_BATCHES") else rank))
     dev_batches = [b.to(dev) for b in host_batches]
     table = table0.to(dev).clone()
@@ -349,6 +357,7 @@ def run_label(args, ctx, wl, steps, warmup, headline=False):
     ctx.align_streams()   # warm the collective up before the bracket
     ctx.sync_all()
     ctx.align_streams()
+    ctx.prequeue()
     t0.record()
     for i in range(steps):
         # the pair kernel is bracketed by CUDA events on every 4th step only: two event records per step sit between
@@ -683,6 +692,7 @@ def run_cfg2(args, ctx, steps, warmup):
         m, c["pool"], m * c["F"] * 4 / 1e6, rotation)
     if ctx.world > 1:
         cfg["start_alignment"] = "device-side rendezvous (one-element all-reduce) enqueued right before the start event"
+    cfg["launch_queue"] = "a ~0.5 ms spin kernel precedes the start event, so the timed launches are queued before the GPU reaches them"
     table, fw, fb = table0.to(dev).clone(), fw0.to(dev).clone(), fb0.to(dev).clone()
     eng = JointConeStep(table, fw, fb, feats, c["geom"], Nn, B, m, K=c["K"], alpha=c["alpha"], lr=c["lr_labels"],
                         lr_fc=c["lr"], precision=0, process_group=ctx.pg)
@@ -705,6 +715,7 @@ def run_cfg2(args, ctx, steps, warmup):
     ctx.align_streams()
     ctx.sync_all()
     ctx.align_streams()
+    ctx.prequeue()
     t0.record()
     for i in range(steps):
         eng.kernel_events = kev[i] if i % 4 == 0 else None

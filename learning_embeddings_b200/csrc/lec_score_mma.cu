@@ -41,6 +41,7 @@
 
 #include "lec_common.cuh"
 #include "lec_packed.cuh"
+#include "lec_async.cuh"
 
 namespace lec {
 
@@ -152,60 +153,12 @@ __global__ void __launch_bounds__(kMmaN) score_mma_prep_kernel(const float* __re
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers (tcgen05 / mbarrier / bulk copy)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// Spins on the phase; a lost arrival traps instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity, int sleep_ns = 32) {
-    unsigned ok = 0;
-    for (unsigned spin = 0; !ok; ++spin) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-        if (!ok) {
-            if (spin > 4 && sleep_ns > 0) __nanosleep((unsigned)sleep_ns);   // a waiting warp must not eat the issue slots of the working ones
-            if (spin > (1u << 22)) __trap();
-        }
-    }
-}
-// one non-blocking look at the phase
-__device__ __forceinline__ bool mbar_test(unsigned bar, unsigned parity) {
-    unsigned ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
 __device__ __forceinline__ void tmem_alloc(unsigned dst_smem, unsigned cols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_dealloc(unsigned taddr, unsigned cols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-// one lane of the (converged) warp; the compiler knows the region under it runs on a single thread (ELECT), so operands
-// of the uniform-datapath instructions inside (UTCHMMA, UTCBAR, UBLKCP) need no per-lane serialisation loop
-__device__ __forceinline__ bool elect_one() {
-    unsigned pred = 0;
-    asm volatile(
-        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
-        "elect.sync rx|px, 0xffffffff;\n\t"
-        "@px mov.s32 %0, 1;\n\t}"
-        : "+r"(pred));
-    return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -310,9 +263,6 @@ __device__ unsigned long long g_tc_trace[16];
 constexpr int kEpiThreads = 2 * kMmaM;          // 8 epilogue warps: two threads per image, 16 labels (3 x 16 columns) each
 constexpr int kMmaThreads = kEpiThreads + 64;   // + warp 8 (tcgen05.mma issue) + warp 9 (TMA bulk copies)
 
-__device__ __forceinline__ void mbar_arrive(unsigned bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
 __device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32]) {
     unsigned r[32];
     asm volatile(

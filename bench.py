@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-sustained", action="store_true")
+    ap.add_argument("--step-series", type=int, default=0, help="diagnostic: print the device time of each of N steps")
     return ap.parse_args()
 
 
@@ -94,7 +95,8 @@ class Ctx:
         the region's launches queued, so a 20-step (1.3 ms) region times the device back to back and not the host's
         launch jitter -- with 8 lock-stepped ranks ANY rank's hiccup in an empty launch queue stalls all of them (r2u8:
         20 steps 80.9 us/step, 200 steps 75.4, one second sustained 71.8).  The host side is what `e2e` measures."""
-        torch.cuda._sleep(1_000_000)
+        if os.environ.get("LEC_BENCH_PREQUEUE", "1") != "0":
+            torch.cuda._sleep(1_000_000)
 
     def max_ranks(self, ms):
         if self.world > 1:
@@ -374,6 +376,48 @@ def run_label(args, ctx, wl, steps, warmup, headline=False):
     final_loss = float(eng.global_loss().item())
     value = world * pairs_per_step * steps / (elapsed_ms * 1e-3)
     clocks = sampler.summary()
+
+    if args.step_series:
+        # diagnostic: device time of every step of a short region (one event per step), rank 0 prints the series
+        for tag, pre in (("plain", False), ("prequeued", True)):
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.step_series + 1)]
+            ctx.sync_all()
+            ctx.align_streams()
+            if pre:
+                ctx.prequeue()
+            evs[0].record()
+            for i in range(args.step_series):
+                dev_step(i)
+                evs[i + 1].record()
+            ctx.sync_all()
+            if rank == 0:
+                print("step series (%s, us): %s" % (tag, " ".join("%.1f" % (1e3 * evs[i].elapsed_time(evs[i + 1]))
+                                                                  for i in range(args.step_series))), file=sys.stderr, flush=True)
+
+    if args.step_series:
+        # debug builds of the library (-DLEC_STEP_TRACE) stamp the phases of a step with %globaltimer
+        import ctypes
+        try:
+            tracer = _native.lib().lec_debug_step_trace
+        except AttributeError:
+            tracer = None
+        if tracer is not None:
+            buf = (ctypes.c_uint64 * 7)()
+            tracer(None)
+            acc, cnt = np.zeros(6), 0
+            for i in range(40):
+                ctx.sync_all()
+                ctx.align_streams()
+                dev_step(i)
+                torch.cuda.synchronize()
+                tracer(buf)
+                t = [int(v) for v in buf]
+                if i >= 5:
+                    acc += np.array([t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4], t[6] - t[5]], dtype=np.float64)
+                    cnt += 1
+            print("rank %d step phases (us): pair kernel %.1f | pair end -> update past its wait %.1f | update blocks enter over %.1f | "
+                  "-> packets pushed %.1f | -> reduced %.1f | -> update end %.1f" % ((rank,) + tuple(acc / cnt / 1e3)),
+                  file=sys.stderr, flush=True)
 
     # sustained: at least a second of back-to-back steps, same rotation (the burst figure above is 20 steps ~ 1.4 ms)
     sustained = None

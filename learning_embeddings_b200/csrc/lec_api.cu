@@ -5,6 +5,9 @@
 namespace lec {
 std::atomic<unsigned long long> g_launches{0};
 thread_local int t_pdl = 0;
+#ifdef LEC_STEP_TRACE
+unsigned long long* g_step_trace = nullptr;
+#endif
 
 // pairs whose endpoint id fell outside the table since the last lec_index_errors(reset) (per device)
 __device__ unsigned g_index_errors = 0;
@@ -386,3 +389,18 @@ int lec_score_topk(int geom, int precision, const float* labels, int64_t L, cons
 }
 
 }  // extern "C"
+
+#ifdef LEC_STEP_TRACE
+// debug builds only (not part of the ABI): out7 <- the step trace, which is then reset; synchronises the device
+extern "C" int lec_debug_step_trace(unsigned long long* out7) {
+    const unsigned long long init[7] = {~0ull, 0, ~0ull, 0, 0, 0, 0};
+    if (!lec::g_step_trace) {
+        if (cudaMalloc(&lec::g_step_trace, sizeof(init)) != cudaSuccess) return -1;
+    } else {
+        cudaDeviceSynchronize();
+        if (out7) cudaMemcpy(out7, lec::g_step_trace, sizeof(init), cudaMemcpyDeviceToHost);
+    }
+    cudaMemcpy(lec::g_step_trace, init, sizeof(init), cudaMemcpyHostToDevice);
+    return 0;
+}
+#endif

@@ -378,6 +378,26 @@ __device__ __forceinline__ void block_add_double(double v, double* out) {
     }
 }
 
+// Optional phase trace of a training step (build with -DLEC_STEP_TRACE): the kernels of a step stamp %globaltimer into
+// a small device array (min / max over blocks), read and reset by lec_debug_step_trace (scripts/step_trace.py).
+//   [0] min pair kernel past its dependency wait   [1] max pair kernel block end
+//   [2] min update kernel past its dependency wait [3] max ... [4] max packets pushed [5] max packets reduced [6] max end
+#ifdef LEC_STEP_TRACE
+extern unsigned long long* g_step_trace;   // device pointer, NULL until the debug entry point allocates it
+__device__ __forceinline__ unsigned long long trace_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void trace_min(unsigned long long* tr, int slot) { if (tr) atomicMin(tr + slot, trace_now()); }
+__device__ __forceinline__ void trace_max(unsigned long long* tr, int slot) { if (tr) atomicMax(tr + slot, trace_now()); }
+#define LEC_TRACE_MIN(tr, slot) trace_min(tr, slot)
+#define LEC_TRACE_MAX(tr, slot) trace_max(tr, slot)
+#else
+#define LEC_TRACE_MIN(tr, slot)
+#define LEC_TRACE_MAX(tr, slot)
+#endif
+
 inline int sm_count() {
     static int n = 0;
     if (n == 0) {

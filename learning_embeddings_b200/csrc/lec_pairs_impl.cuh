@@ -44,6 +44,7 @@ struct GroupArgs {
     int split;  // teams per group (>= 1): team s of a group takes negatives p = s, s + split, ... of both lists
     int64_t stage_floats;  // > 0: every block first copies the transformed table (n * ld floats) into shared memory
     int narrow_tail;       // the last float4 chunk of a row holds <= 2 live floats (D % 4 in {1, 2}): its reductions are 64-bit
+    unsigned long long* trace;   // LEC_STEP_TRACE builds only
 };
 
 // Gradient reduction of chunk q of a row.  The L2 executes a vector reduction as one fp32 add per element and its add
@@ -187,6 +188,7 @@ __global__ void __launch_bounds__(kThreads, MB) pairs_grouped_kernel(const Group
     using Acc = typename Tr::Acc;
     if (!a.pdl_late) pdl_launch_dependents();   // the update kernel may take its (few) SM slots now; it parks in pdl_wait()
     pdl_wait();                // rows / aux / cleared replicas of the previous update are complete
+    if (threadIdx.x == 0) LEC_TRACE_MIN(a.trace, 0);
     // Hot label table in shared memory (ETHEC: 723 x 12 floats = 35 KB): every endpoint gather of the block then is an
     // LDS.128 instead of an L1-cached global load.
     extern __shared__ __align__(16) float s_rows[];
@@ -362,6 +364,7 @@ __global__ void __launch_bounds__(kThreads, MB) pairs_grouped_kernel(const Group
     }
     if (a.pdl_late) pdl_launch_dependents();
     block_add_double(loss, a.loss_out);
+    if (threadIdx.x == 0) LEC_TRACE_MAX(a.trace, 1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -471,6 +474,9 @@ int launch_grouped_tv(const GroupArgs& a0, cudaStream_t st) {
     }();
     static const int pdl_late = [] { const char* e = getenv("LEC_PDL_LATE"); return e ? atoi(e) : 0; }();
     a.pdl_late = pdl_late;
+#ifdef LEC_STEP_TRACE
+    a.trace = g_step_trace;
+#endif
     a.split = choose_split(a.B, a.N, (int64_t)sm_count() * resident_blocks * (block / T));
     const int grid = grid_for(a.B * a.split, block / T, 8 * kThreads / block);
     // Shared-memory staging of the table (LEC_STAGE_ROWS=1; tables <= 40 KB) was measured and is OFF by default: on

@@ -37,6 +37,7 @@ struct UpdArgs {
     double* loss_global; int* error; unsigned long long timeout_ns;
     // two-shot exchange (large tables): rank r owns rows [r * rows_per_rank, (r + 1) * rows_per_rank)
     int64_t rows_per_rank; int tiles_per_rank; int phases;
+    unsigned long long* trace;   // LEC_STEP_TRACE builds only
 };
 
 // ---- two-shot exchange: layout of one rank's buffer --------------------------------------------------------------------
@@ -467,7 +468,10 @@ __global__ void __launch_bounds__(kThreads, (V <= 4 && !XCHG && RULE_T >= 0) ? L
     const int row_mode = MODE_T >= 0 ? MODE_T : a.row_mode;
     pdl_launch_dependents();
     pdl_wait();   // the pair kernel's reductions into the replicas (and its loss) are complete
-    if (XCHG && a.error && ld_volatile_int(a.error) != 0) return;   // an earlier exchange failed: the table is left alone
+    if (threadIdx.x == 0) { LEC_TRACE_MIN(a.trace, 2); LEC_TRACE_MAX(a.trace, 3); }
+    // an earlier exchange failed: the table is left alone.  The flag is READ here but tested only after the row's loads
+    // have been issued (below), so that its latency overlaps theirs instead of preceding them.
+    const int failed_before = (XCHG && a.error) ? ld_volatile_int(a.error) : 0;
     const int lane = threadIdx.x % TT;
     const int tpb_rt = (int)blockDim.x / TT;   // the launcher picks the block size: small tables use small blocks on many SMs
     const int64_t n_teams = (int64_t)gridDim.x * tpb_rt;
@@ -484,23 +488,6 @@ __global__ void __launch_bounds__(kThreads, (V <= 4 && !XCHG && RULE_T >= 0) ? L
         const unsigned long long bits = (unsigned long long)__double_as_longlong(l);
         uint4* dst = a.peer[threadIdx.x] + ((int64_t)a.slot * a.world + a.rank) * a.slot_packets + a.n * (int64_t)Q * 2;
         ll_store(dst, (unsigned)(bits & 0xffffffffu), (unsigned)(bits >> 32), a.tag);
-    }
-    if (XCHG && blockIdx.x == 0 && threadIdx.x >= 32 && threadIdx.x < 64 && a.loss_acc && a.loss_global) {
-        // the ranks' losses: lane p of the block's second warp polls source p's loss packet (all in parallel), lane 0
-        // adds them in rank order
-        const int p = threadIdx.x - 32;
-        double l = 0.0;
-        bool ok = true;
-        if (p < a.world) {
-            const uint4* src = a.peer[a.rank] + ((int64_t)a.slot * a.world + p) * a.slot_packets + a.n * (int64_t)Q * 2;
-            uint4 pk = ll_load(src);
-            ok = ll_wait(src, a.tag, pk, a.error, a.timeout_ns, t0);
-            l = __longlong_as_double((long long)(((unsigned long long)pk.z << 32) | (unsigned long long)pk.x));
-        }
-        ok = __all_sync(0xffffffffu, ok);
-        double total = 0.0;
-        for (int q = 0; q < a.world; ++q) total += __shfl_sync(0xffffffffu, l, q);
-        if (p == 0 && ok) *a.loss_global = total;
     }
     const bool hyp = row_mode >= LEC_ROWS_HYP_SHELL;
     const bool adam = rule == LEC_UPD_ADAM;
@@ -528,6 +515,7 @@ __global__ void __launch_bounds__(kThreads, (V <= 4 && !XCHG && RULE_T >= 0) ? L
             if (adam) load_chunks<TT, V>(vb, a.v + rc * (int64_t)a.ld, Q, lane);
 #pragma unroll
             for (int j = 0; j < V; ++j) { g[4 * j] = c[j].x; g[4 * j + 1] = c[j].y; g[4 * j + 2] = c[j].z; g[4 * j + 3] = c[j].w; }
+            if (XCHG && failed_before != 0) return;   // grid-uniform; nothing has been written yet
             if (valid) {
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
@@ -547,6 +535,7 @@ __global__ void __launch_bounds__(kThreads, (V <= 4 && !XCHG && RULE_T >= 0) ? L
                     const int q = lane + TT * j;
                     if (q < Q) ll_push_chunk(a, (row * Q + q) * 2, make_float4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]));
                 }
+                if (lane == 0) LEC_TRACE_MAX(a.trace, 4);
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
                     const int q = lane + TT * j;
@@ -559,9 +548,29 @@ __global__ void __launch_bounds__(kThreads, (V <= 4 && !XCHG && RULE_T >= 0) ? L
             }
             // a row whose exchange failed is left untouched (the host raises on *error); the vote keeps teams uniform
             if (__any_sync(0xffffffffu, !ok)) valid = false;
+            if (lane == 0) LEC_TRACE_MAX(a.trace, 5);
         }
         row_rule<TT, V>(a, rule, row_mode, g, e, mb, vb, row, rc, valid, lane);
         row_forward<TT, V>(a, row_mode, e, row, valid, lane);
+    }
+    if (threadIdx.x == 0) LEC_TRACE_MAX(a.trace, 6);
+    if (XCHG && blockIdx.x == 0 && threadIdx.x >= 32 && threadIdx.x < 64 && a.loss_acc && a.loss_global) {
+        // the ranks' losses: lane p of the block's second warp polls source p's loss packet (all in parallel), lane 0
+        // adds them in rank order.  AFTER the rows: polled before them (r2 trace), this warp sat on the peers' loss packets
+        // while its own rows were still unsent -- one extra NVLink latency on the critical path of every rank.
+        const int p = threadIdx.x - 32;
+        double l = 0.0;
+        bool ok = true;
+        if (p < a.world) {
+            const uint4* src = a.peer[a.rank] + ((int64_t)a.slot * a.world + p) * a.slot_packets + a.n * (int64_t)Q * 2;
+            uint4 pk = ll_load(src);
+            ok = ll_wait(src, a.tag, pk, a.error, a.timeout_ns, t0);
+            l = __longlong_as_double((long long)(((unsigned long long)pk.z << 32) | (unsigned long long)pk.x));
+        }
+        ok = __all_sync(0xffffffffu, ok);
+        double total = 0.0;
+        for (int q = 0; q < a.world; ++q) total += __shfl_sync(0xffffffffu, l, q);
+        if (p == 0 && ok) *a.loss_global = total;
     }
     if (loss_thread && a.loss_acc) {
         if (a.loss_step) *a.loss_step = my_loss;
@@ -870,6 +879,9 @@ int update_rows_launch(const lec_update_t& u, const lec_exchange_t* x, cudaStrea
     a.m = u.state_m; a.v = u.state_v;
     a.rows_out = u.rows_out; a.aux_out = u.aux_out; a.grad_out = u.grad_out;
     a.loss_acc = u.loss_acc; a.loss_step = u.loss_step;
+#ifdef LEC_STEP_TRACE
+    a.trace = g_step_trace;
+#endif
     a.world = 0;
     if (x && x->world > 1) {
         a.world = x->world; a.rank = x->rank; a.slot = x->slot; a.tag = x->tag; a.slot_packets = x->slot_packets;

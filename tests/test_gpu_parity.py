@@ -306,13 +306,24 @@ def test_dropin_criterion_reproduces_reference_step(name, geom, ethec):
     drawn = np.stack([nt.reshape(B, 2 * Nn)[:, :Nn], nf.reshape(B, 2 * Nn)[:, Nn:]], axis=2).reshape(-1)
     assert drawn.tolist() == g["drawn"].tolist()  # bit-exact negative indices
     np.testing.assert_allclose(float(loss), float(g["loss"]), rtol=2e-5)
-    np.testing.assert_allclose(E_pos.cpu().numpy(), g["E_pos"], rtol=1e-4, atol=1e-4)
-    np.testing.assert_allclose(E_neg.cpu().numpy(), g["E_neg"], rtol=1e-4, atol=1e-4)
     np.testing.assert_allclose(from_emb.detach().cpu().numpy(), g["from_emb"], rtol=3e-6, atol=2e-7)
     np.testing.assert_allclose(to_emb.detach().cpu().numpy(), g["to_emb"], rtol=3e-6, atol=2e-7)
     gW = model.embeddings.weight.grad.cpu().numpy()
-    scale = np.abs(g["gW"]).max()
-    np.testing.assert_allclose(gW, g["gW"], rtol=5e-3, atol=1e-4 * scale)
+    if not bool(g["weigh_neg_term"]):   # the weighted order-embedding golden keeps the coarse bound below
+        # The SURVEY 8(c) contract, pointwise: the golden is the reference's own FP32 run, whose error against the truth
+        # is O(1e-5) near the acos clamp, so the drop-in is held to the FP64 oracle on the same pairs -- within 1e-5
+        # relative, or within twice the reference's own FP32 error where that is larger.
+        mode = {"euc": cones.ROW_EUC_SOFTCLIP, "hyp": cones.ROW_HYP_SHELL, "oe": cones.ROW_NONE}[geom]
+        r64 = cones.label_step(geom, t(g["W0"], torch.float64), mode, float(crit.K) if geom != "oe" else 0.0, alpha,
+                               t(g["u"]), t(g["v"]), t(nf.reshape(-1)), t(nt.reshape(-1)))
+        contract(E_pos.cpu().numpy(), r64["E_pos"].numpy(), g["E_pos"], name + " E_pos")
+        contract(E_neg.cpu().numpy().reshape(-1), r64["E_neg"].numpy(), g["E_neg"].reshape(-1), name + " E_neg")
+        contract_rows(gW, r64["gW"].numpy(), g["gW"], name + " gW", floor=2e-5)
+    else:
+        np.testing.assert_allclose(E_pos.cpu().numpy(), g["E_pos"], rtol=1e-4, atol=1e-4)
+        np.testing.assert_allclose(E_neg.cpu().numpy(), g["E_neg"], rtol=1e-4, atol=1e-4)
+        scale = np.abs(g["gW"]).max()
+        np.testing.assert_allclose(gW, g["gW"], rtol=5e-3, atol=1e-4 * scale)
     # eval phase on a mixed-status batch
     with torch.no_grad():
         _, _, ev_loss, ev_Ep, ev_En = crit(model, g["ev_from"].tolist(), g["ev_to"].tolist(), t(g["ev_status"]),

@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-sustained", action="store_true")
     ap.add_argument("--step-series", type=int, default=0, help="diagnostic: print the device time of each of N steps")
+    ap.add_argument("--burst-ab", action="store_true", help="diagnostic: the timed burst under several launch-queue depths")
     return ap.parse_args()
 
 
@@ -89,6 +90,22 @@ class Ctx:
             if getattr(self, "_tok", None) is None:
                 self._tok = torch.zeros(1, device=self.dev)
             torch.distributed.all_reduce(self._tok)
+
+    def warm(self, dev_step, eng, kev, warmup):
+        """Untimed warm-up: at least 40 steps whatever --warmup says (r2w8: at 8 GPUs the first ~25 steps of a process ran
+        ~20 % slow -- peer mappings, lazily loaded modules, first use of the event path -- and a 5-step warm-up put them
+        inside the 20-step timed region: 88.7 us/step against 72.7 for the same region a moment later), including one
+        rehearsal of the timed loop itself (kernel events, rendezvous, spin kernel)."""
+        for i in range(max(3, warmup, 40)):
+            dev_step(i)
+        self.sync_all()
+        self.align_streams()
+        self.prequeue()
+        for i in range(len(kev)):
+            eng.kernel_events = kev[i] if i % 4 == 0 else None
+            dev_step(i)
+        eng.kernel_events = None
+        self.sync_all()
 
     def prequeue(self):
         """~0.5 ms spin kernel in front of a timed region's start event: by the time the GPU reaches the event the host has
@@ -334,6 +351,7 @@ def run_label(args, ctx, wl, steps, warmup, headline=False):
     if ctx.world > 1:
         cfg["start_alignment"] = "device-side rendezvous (one-element all-reduce) enqueued right before the start event"
     cfg["launch_queue"] = "a ~0.5 ms spin kernel precedes the start event, so the timed launches are queued before the GPU reaches them"
+    cfg["warmup_steps"] = "max(--warmup, 40) steps + one untimed rehearsal of the timed loop"
     host_batches = make_batches(h, spec, groups, rotation, seed=100 + (0 if os.environ.get("LEC_BENCH_SAME_BATCHES") else rank))
     dev_batches = [b.to(dev) for b in host_batches]
     table = table0.to(dev).clone()
@@ -347,13 +365,11 @@ def run_label(args, ctx, wl, steps, warmup, headline=False):
 
     sampler = ClockSampler(ctx.local_rank)
     sampler.start()
-    for i in range(max(3, warmup)):
-        dev_step(i)
-    ctx.sync_all()
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    ctx.warm(dev_step, eng, kev, warmup)
 
     # timed region: inputs resident in HBM
     launches0 = _native.launch_count()
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.active.set()
     ctx.align_streams()   # warm the collective up before the bracket
@@ -376,6 +392,32 @@ def run_label(args, ctx, wl, steps, warmup, headline=False):
     final_loss = float(eng.global_loss().item())
     value = world * pairs_per_step * steps / (elapsed_ms * 1e-3)
     clocks = sampler.summary()
+
+    if args.burst_ab:
+        # diagnostic: the 20-step burst under different launch-queue depths, with and without the NVML sampler thread
+        for rep in range(3):
+            for spin_cycles in (0, 1_000_000, 4_000_000):
+                for samp in (True, False):
+                    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    if samp:
+                        sampler.active.set()
+                    ctx.align_streams()
+                    ctx.sync_all()
+                    ctx.align_streams()
+                    if spin_cycles:
+                        torch.cuda._sleep(spin_cycles)
+                    b0.record()
+                    for i in range(steps):
+                        eng.kernel_events = kev[i] if i % 4 == 0 else None
+                        dev_step(i)
+                    b1.record()
+                    ctx.sync_all()
+                    sampler.active.clear()
+                    eng.kernel_events = None
+                    ms = ctx.max_ranks(b0.elapsed_time(b1))
+                    if rank == 0:
+                        print("burst rep %d spin %.1f ms sampler %s: %.1f us/step" % (rep, spin_cycles / 1.965e6, samp, 1e3 * ms / steps),
+                              file=sys.stderr, flush=True)
 
     if args.step_series:
         # diagnostic: device time of every step of a short region (one event per step), rank 0 prints the series
@@ -737,6 +779,7 @@ def run_cfg2(args, ctx, steps, warmup):
     if ctx.world > 1:
         cfg["start_alignment"] = "device-side rendezvous (one-element all-reduce) enqueued right before the start event"
     cfg["launch_queue"] = "a ~0.5 ms spin kernel precedes the start event, so the timed launches are queued before the GPU reaches them"
+    cfg["warmup_steps"] = "max(--warmup, 40) steps + one untimed rehearsal of the timed loop"
     table, fw, fb = table0.to(dev).clone(), fw0.to(dev).clone(), fb0.to(dev).clone()
     eng = JointConeStep(table, fw, fb, feats, c["geom"], Nn, B, m, K=c["K"], alpha=c["alpha"], lr=c["lr_labels"],
                         lr_fc=c["lr"], precision=0, process_group=ctx.pg)
@@ -749,11 +792,9 @@ def run_cfg2(args, ctx, steps, warmup):
 
     sampler = ClockSampler(ctx.local_rank)
     sampler.start()
-    for i in range(max(3, warmup)):
-        dev_step(i)
-    ctx.sync_all()
-    launches0 = _native.launch_count()
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    ctx.warm(dev_step, eng, kev, warmup)
+    launches0 = _native.launch_count()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.active.set()
     ctx.align_streams()

@@ -60,7 +60,14 @@ struct MmaChunkTable { int n; MmaChunk c[kMmaMaxChunks]; };
 
 struct MmaHdr { int label0, count, level, flags; float psi_max; int pad[3]; };  // 32 bytes, tail of a blob
 
-__host__ __device__ inline int mma_forms(int D) { return (D + 2 + 7) / 8 * 8 <= 32 ? 3 : 1; }
+// Forms per launch.  Rows up to D = 30 (D + 2 padded to <= 32): three forms in every mode.  Wider rows keep one form --
+// three would triple a tensor time that is no longer hidden (r2 sweep at D = 50, Kp = 56: matrix 1.12 -> 1.34 ms, top-k
+// 1.67 -> 1.91 ms) -- except in the matrix + top-k mode, whose epilogue is long enough to hide it and short of issue
+// slots for the pair algebra (2.51 -> 2.16 ms), up to Kp = 56 (D <= 54).
+inline int mma_forms(int D, bool matrix_and_topk = false) {
+    const int kp3 = (D + 2 + 7) / 8 * 8;
+    return kp3 <= 32 || (matrix_and_topk && kp3 <= 56) ? 3 : 1;
+}
 __host__ __device__ inline int mma_labels(int forms) { return kMmaN / forms; }                   // labels per chunk
 __host__ __device__ inline int mma_kp(int D, int forms) { return ((forms == 3 ? D + 2 : D) + 7) / 8 * 8; }  // forms 3: [row, |row|^2-slot, 1-slot]
 __host__ __device__ inline int mma_tile_bytes(int Kp) { return kMmaN * Kp * 4; }                 // one B tile (hi or lo)
@@ -867,9 +874,14 @@ static int build_chunks(int64_t L, const int32_t* level_start, const int32_t* le
 static int64_t mma_max_chunks(int64_t L, int n_levels, int NL) { return (L + NL - 1) / NL + 2 * (int64_t)n_levels + 2; }
 
 int64_t score_mma_workspace_bytes(int64_t L, int D, int n_levels) {
-    const int forms = mma_forms(D);
-    // chunk blobs + the per-label -psi table the top-k merge reads
-    return mma_max_chunks(L, n_levels, mma_labels(forms)) * mma_blob_bytes(mma_kp(D, forms), forms) + (L + 32) * 4;
+    // chunk blobs + the per-label (pi/2 - psi) table the top-k merge reads; the larger of the two layouts a launch may pick
+    int64_t best = 0;
+    for (int both = 0; both < 2; ++both) {
+        const int forms = mma_forms(D, both != 0);
+        const int64_t b = mma_max_chunks(L, n_levels, mma_labels(forms)) * mma_blob_bytes(mma_kp(D, forms), forms);
+        if (b > best) best = b;
+    }
+    return best + (L + 32) * 4;
 }
 
 // TMEM budget of one CTA: acc_stages accumulator buffers of 96 columns + the image tile (2 Kp columns).  Two buffers
@@ -884,15 +896,18 @@ static bool mma_plan(int Kp, int& acc_stages, int& tmem_cols) {
 bool score_mma_supported(int geom, int precision, int D, int64_t L, int n_levels) {
     int na, tc;
     if (!(geom == LEC_GEOM_HYP && precision == LEC_PREC_F32 && D >= 1 && D <= 128)) return false;
-    const int forms = mma_forms(D);
-    return mma_plan(mma_kp(D, forms), na, tc) && mma_max_chunks(L, n_levels, mma_labels(forms)) <= kMmaMaxChunks;
+    for (int both = 0; both < 2; ++both) {
+        const int forms = mma_forms(D, both != 0);
+        if (!mma_plan(mma_kp(D, forms), na, tc) || mma_max_chunks(L, n_levels, mma_labels(forms)) > kMmaMaxChunks) return false;
+    }
+    return true;
 }
 
 int score_mma_launch(const float* labels, int64_t L, const float* images, int64_t N, int D, float K, const int32_t* level_start,
                      const int32_t* level_stop, int n_levels, int k, float* scores, int32_t* topk_idx, float* topk_val,
                      void* workspace, int64_t workspace_bytes, cudaStream_t st) {
     if (N == 0 || L == 0) return 0;
-    const int forms = mma_forms(D);
+    const int forms = mma_forms(D, scores != nullptr && topk_idx != nullptr);
     MmaChunkTable tab;
     if (int e = build_chunks(L, level_start, level_stop, topk_idx ? n_levels : 0, scores != nullptr, mma_labels(forms), tab)) return e;
     if (tab.n == 0) return 0;

@@ -398,7 +398,12 @@ def test_scoring_matches_reference_loop(name, geom, prec, engine):
     # top-k only (no matrix) returns the same values bit for bit (tc: deferred-angle path), and so does matrix only
     idx2, val2, _ = ops.score_topk(t(g["labels"]).to(DEV), t(g["images"]).to(DEV), geom, K, g["level_start"],
                                    g["level_stop"], k=5, want_scores=False, precision=prec, engine=engine)
-    assert torch.equal(val2, val)
+    if engine == "tc" and g["labels"].shape[1] > 30:
+        # wide rows: the matrix + top-k launch contracts all three bilinear forms on the tensor cores, the top-k-only
+        # launch one (lec_score_mma.cu, mma_forms) -- two evaluation orders of the same energies
+        np.testing.assert_allclose(val2.cpu().numpy(), val.cpu().numpy(), rtol=1e-5, atol=5e-6)
+    else:
+        assert torch.equal(val2, val)
     assert (idx2.cpu().numpy()[distinct] == g["top_idx"][distinct]).all()
 
 
@@ -496,13 +501,19 @@ def test_scoring_full_size_properties(engine, D):
     ref = cones.score_matrix("hyp", labels.double(), images[:512].double(), 0.1)
     ref32 = cones.score_matrix("hyp", labels, images[:512], 0.1)
     contract(scores[:512].cpu().numpy(), ref.numpy(), ref32.numpy(), "scores", fp32_core=True)
+    # the top-k-only launch (wide rows on the tensor cores: another evaluation order, see mma_forms) agrees with it
+    idx_t, val_t, _ = score_topk(lab_d, img_d, "hyp", 0.1, h["level_start"], h["level_stop"], k=5)
+    if engine == "tc" and D > 30:
+        np.testing.assert_allclose(val_t.cpu().numpy(), val.cpu().numpy(), rtol=1e-5, atol=5e-6)
+    else:
+        assert torch.equal(idx_t, idx) and torch.equal(val_t, val)
     # sharding: two halves give the same answer as one call
     i1, v1, _ = score_topk(lab_d, img_d[: n_img // 2], "hyp", 0.1, h["level_start"], h["level_stop"], k=5)
     i2, v2, _ = score_topk(lab_d, img_d[n_img // 2:], "hyp", 0.1, h["level_start"], h["level_stop"], k=5)
-    assert torch.equal(torch.cat([i1, i2]), idx) and torch.equal(torch.cat([v1, v2]), val)
+    assert torch.equal(torch.cat([i1, i2]), idx_t) and torch.equal(torch.cat([v1, v2]), val_t)
     perm = torch.randperm(n_img, generator=gen).to(DEV)
     ip, vp, _ = score_topk(lab_d, img_d[perm], "hyp", 0.1, h["level_start"], h["level_stop"], k=5)
-    assert torch.equal(ip, idx[perm]) and torch.equal(vp, val[perm])
+    assert torch.equal(ip, idx_t[perm]) and torch.equal(vp, val_t[perm])
 
 
 @pytest.mark.parametrize("engine", ("simt", "tc"))

@@ -10,7 +10,9 @@
  * Conventions
  *   - plain C, raw DEVICE pointers, explicit sizes, explicit stream (a cudaStream_t passed as void*)
  *   - returns 0 on success, a positive cudaError_t, or a negative LEC_E_* argument error
- *   - never allocates, frees or synchronises; all buffers are owned by the caller
+ *   - never allocates, frees or synchronises; all buffers are owned by the caller.  Exceptions, each documented at its
+ *     declaration: lec_index_errors reads a counter back (synchronises the stream); lec_host_pipe_create / _destroy own
+ *     a small host object (one stream, 3 events per slot) and lec_host_pipe_wait blocks on an event by design
  *   - all floating point is IEEE fp32 storage; `precision` selects the arithmetic of the per-pair
  *     scalar core: LEC_PREC_F32 (fp32 throughout) or LEC_PREC_F64CORE (dot products and the
  *     angle/aperture algebra in fp64, vectors and outputs fp32)

@@ -101,8 +101,9 @@ class ConeStep:
         # step).  LEC_FUSED_STEP=0 re-runs lec_rows_fwd at the start of every step instead (three launches).
         self.fused = os.environ.get("LEC_FUSED_STEP", "1") != "0"
         self._rows_valid = False
-        # host->device staging: `depth` slots so that the copy of step i+1 overlaps the kernels of step i
-        self.depth = 2
+        # host->device staging: `depth` slots so that the copies of steps i+1, i+2 overlap the kernels of step i (r2: with
+        # host-drawn negatives the step is PCIe-bound; depth 2 -> 3: 101 -> 88.6 us per step, no change beyond 3)
+        self.depth = max(1, min(16, int(os.environ.get("LEC_PIPE_DEPTH", "3"))))
         self._idx_bytes_dev = [torch.empty(self.max_groups * (2 + 2 * self.n_neg) * 4, device=dev, dtype=torch.uint8)
                                for _ in range(self.depth)]
         self.loss_host = torch.zeros(self.depth, dtype=torch.float64).pin_memory()

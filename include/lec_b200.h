@@ -392,12 +392,15 @@ int64_t lec_philox_below(uint64_t seed, uint64_t stream_id, uint64_t draw, uint6
  *     copy stream  [wait until the kernels that last read dev_block are done] -> dev_block <- host_block (`bytes`)
  *                  [-> sample != NULL: lec_sample_negatives_philox draws step->neg_to / neg_from from step->pos_from /
  *                  pos_to on the device; it depends on no kernel of the step before, so it overlaps them] -> event
- *     `stream`     wait for that event -> lec_cone_step(step) -> *loss_host <- *step->upd.loss_step
+ *     `stream`     wait for that event -> lec_cone_step(step) -> event
+ *     read-back    (a third stream) wait for that event -> *loss_host <- *step->upd.loss_step
  *                  [-> *err_host <- *step->xchg.error when world > 1] -> event
  * and returns without waiting for the GPU.  The index pointers of `step` point into dev_block (the caller lays the
  * block out: pos_from | pos_to | neg_to | neg_from, or just the positives in the sampled mode); host_block, loss_host and
  * err_host are PINNED host memory.  `slot` in [0, depth) names the staging slot: its events order the reuse of dev_block,
- * so the copy of step i+1 overlaps the kernels of step i.  A slot must be collected with lec_host_pipe_wait (blocks
+ * so the copy of step i+1 overlaps the kernels of step i.  Because the loss is read back BEHIND the main stream (no
+ * copy sits between one step's update kernel and the next step's pair kernel), give every slot its own device word
+ * step->upd.loss_step: a later step must not overwrite it before it has been read.  A slot must be collected with lec_host_pipe_wait (blocks
  * until its loss has landed) before it is submitted again (LEC_E_SIZE otherwise).  Not thread-safe per pipe. */
 typedef struct lec_host_pipe lec_host_pipe_t;
 typedef struct lec_host_sample {

@@ -6,8 +6,8 @@
 // copies back) and the interpreter between them: 100+ us of host time for a 65 us step, and eight ranks on one host
 // contend for it.  Here ONE call enqueues the whole iteration:
 //     copy stream:  [wait: slot's previous kernels done] -> H2D index block -> [Philox negative draw] -> event
-//     main stream:  wait event -> lec_cone_step -> event (slot free) -> D2H loss [+ error word]
-//                   -> event (loss landed)
+//     main stream:  wait event -> lec_cone_step -> event (step done, slot free)
+//     back stream:  wait (step done) -> D2H loss [+ error word] -> event (loss landed)
 // `depth` slots rotate, so the copy of step i+1 overlaps the kernels of step i; the caller blocks (lec_host_pipe_wait)
 // only when it wants a loss or needs a slot back.
 #include <cuda_runtime.h>
@@ -22,7 +22,7 @@ constexpr int kMaxDepth = 16;
 
 struct lec_host_pipe {
     int depth;
-    cudaStream_t copy;
+    cudaStream_t copy, back;   // host->device side stream (+ the negative draw); device->host read-back stream
     cudaEvent_t copied[kMaxDepth], free_[kMaxDepth], loss[kMaxDepth];
     bool inflight[kMaxDepth];
 };
@@ -36,6 +36,7 @@ int lec_host_pipe_create(lec_host_pipe_t** out, int depth) {
     if (!p) return LEC_E_SIZE;
     p->depth = depth;
     cudaError_t e = cudaStreamCreateWithFlags(&p->copy, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->back, cudaStreamNonBlocking);
     for (int i = 0; i < depth && e == cudaSuccess; ++i) {
         p->inflight[i] = false;
         e = cudaEventCreateWithFlags(&p->copied[i], cudaEventDisableTiming);
@@ -56,6 +57,7 @@ void lec_host_pipe_destroy(lec_host_pipe_t* p) {
         cudaEventDestroy(p->loss[i]);
     }
     cudaStreamDestroy(p->copy);
+    cudaStreamDestroy(p->back);
     delete p;
 }
 
@@ -85,11 +87,16 @@ int lec_host_pipe_submit(lec_host_pipe_t* p, int slot, const lec_step_t* step, c
     if (e == cudaSuccess) e = cudaStreamWaitEvent(main, p->copied[slot], 0);
     if (e != cudaSuccess) return (int)e;
     if (const int rc = lec_cone_step(step, stream)) return rc;
+    // The read-back rides its own stream behind the step's event: a device->host copy in the main stream would sit
+    // between this step's update kernel and the next step's pair kernel (a few microseconds of copy-engine latency on
+    // the critical path of every step).  The caller gives every slot its own *loss_step word (see lec_b200.h), so the
+    // next steps do not overwrite it before it has been read.
     e = cudaEventRecord(p->free_[slot], main);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(loss_host, step->upd.loss_step, sizeof(double), cudaMemcpyDeviceToHost, main);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(p->back, p->free_[slot], 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(loss_host, step->upd.loss_step, sizeof(double), cudaMemcpyDeviceToHost, p->back);
     if (e == cudaSuccess && err_host && step->xchg.world > 1 && step->xchg.error)
-        e = cudaMemcpyAsync(err_host, step->xchg.error, sizeof(int), cudaMemcpyDeviceToHost, main);
-    if (e == cudaSuccess) e = cudaEventRecord(p->loss[slot], main);
+        e = cudaMemcpyAsync(err_host, step->xchg.error, sizeof(int), cudaMemcpyDeviceToHost, p->back);
+    if (e == cudaSuccess) e = cudaEventRecord(p->loss[slot], p->back);
     if (e != cudaSuccess) return (int)e;
     p->inflight[slot] = true;
     return 0;

@@ -89,6 +89,7 @@ class ConeStep:
         self.E_neg = torch.empty((self.max_groups, 2 * self.n_neg), device=dev, dtype=torch.float32)
         # the pair kernel adds into loss_acc; the update kernel moves it to `loss` (this rank's loss of the latest step)
         self.loss = torch.zeros(1, device=dev, dtype=torch.float64)
+        self._loss_ptr = self.loss.data_ptr()
         self.loss_acc = torch.zeros(1, device=dev, dtype=torch.float64)
         self.opt_m = self.opt_v = None
         if self.update == "adam" or (self.update == "sgd" and self.momentum != 0.0):
@@ -252,7 +253,7 @@ class ConeStep:
         return out
 
     # -- whole steps ----------------------------------------------------------------------------
-    def _fill_step(self, p_from, p_to, n_to, n_from, idx_bytes, B, w_pos=None, w_neg=None):
+    def _fill_step(self, p_from, p_to, n_to, n_from, idx_bytes, B, w_pos=None, w_neg=None, loss_ptr=None):
         """lec_step_t of the next step (pointers as integers).  One cached ctypes struct: pointers and shapes of this
         engine are written once, the per-step fields every time (lr / alpha / K may change between steps)."""
         if B > self.max_groups:
@@ -272,6 +273,7 @@ class ConeStep:
         s.w_pos = w_pos.data_ptr() if w_pos is not None else None
         s.w_neg = w_neg.data_ptr() if w_neg is not None else None
         self._fill_update(self._upd)
+        self._upd.loss_step = self._loss_ptr if loss_ptr is None else loss_ptr   # pipelined steps: one word per slot
         if self.comm == "p2p":
             s.xchg.slot, s.xchg.tag = self.px.slot_and_tag()
         ev = self.kernel_events
@@ -347,7 +349,10 @@ class ConeStep:
             self._pipe = h
             self._slot_ptr = [b.data_ptr() for b in self._idx_bytes_dev]
             self._loss_np, self._err_np = self.loss_host.numpy(), self.err_host.numpy()
-            self._loss_ptr = [self.loss_host.data_ptr() + 8 * i for i in range(self.depth)]
+            self._loss_host_ptr = [self.loss_host.data_ptr() + 8 * i for i in range(self.depth)]
+            # the step's loss on the device, one word per slot: it is read back behind the main stream
+            self._loss_slots = torch.zeros(self.depth, dtype=torch.float64, device=self.table.device)
+            self._loss_slot_ptr = [self._loss_slots.data_ptr() + 8 * i for i in range(self.depth)]
             self._err_ptr = [self.err_host.data_ptr() + 4 * i for i in range(self.depth)]
         slot = self._submitted % self.depth
         if self._inflight[slot]:
@@ -363,7 +368,7 @@ class ConeStep:
     def _pipe_submit(self, slot, s, sample, host_block, nbytes):
         import ctypes
         N.check(N.lib().lec_host_pipe_submit(self._pipe, slot, ctypes.byref(s), sample, host_block.data_ptr(), nbytes,
-                                             self._slot_ptr[slot], self._loss_ptr[slot],
+                                             self._slot_ptr[slot], self._loss_host_ptr[slot],
                                              self._err_ptr[slot] if self.px is not None else None,
                                              N.stream_ptr(self.table.device)), "lec_host_pipe_submit")
         self._after_step()
@@ -379,7 +384,8 @@ class ConeStep:
             return self._submit_host_torch(index_block, B)
         slot = self._pipe_slot()
         ib, Nn, base = index_block.element_size(), self.n_neg, self._slot_ptr[slot]
-        s = self._fill_step(base, base + B * ib, base + 2 * B * ib, base + (2 + Nn) * B * ib, ib, B)
+        s = self._fill_step(base, base + B * ib, base + 2 * B * ib, base + (2 + Nn) * B * ib, ib, B,
+                            loss_ptr=self._loss_slot_ptr[slot])
         self._pipe_submit(slot, s, None, index_block, B * (2 + 2 * Nn) * ib)
 
     def submit_host_sampled(self, graph, pos_block, B, seed):
@@ -393,7 +399,8 @@ class ConeStep:
         import ctypes
         slot = self._pipe_slot()
         ib, Nn, base = pos_block.element_size(), self.n_neg, self._slot_ptr[slot]
-        s = self._fill_step(base, base + B * ib, base + 2 * B * ib, base + (2 + Nn) * B * ib, ib, B)
+        s = self._fill_step(base, base + B * ib, base + 2 * B * ib, base + (2 + Nn) * B * ib, ib, B,
+                            loss_ptr=self._loss_slot_ptr[slot])
         smp = self._sample_struct
         if smp is None or self._sample_graph is not graph:
             g, keep, status = graph.device_struct(self.table.device)
